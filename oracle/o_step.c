@@ -1,0 +1,595 @@
+/*
+ * o_step.c -- ORACLE (test infrastructure): time-step drivers.
+ * Restates source/surface_hgt.F90:131-286 (dhdt); source/baroclinic.F90:578-1210
+ * (baroclinic_driver), :1217-1497 (baroclinic_correct_adjust), :1635-1895 (clinic), :1902-2306
+ * (tracer_update); source/barotropic.F90:107-260 (init_barotropic), :267-735
+ * (barotropic_driver); source/step_mod.F90:296-626,634-640,663-832 (step).
+ * Benchmark-config hooks that are no-ops there (tavg, diagnostics, overflows, interior restoring,
+ * KPP non-local sources, SW absorption, ice) are omitted.  Matsuno steps are not supported
+ * (PCSI refuses them, POP_SolversMod.F90:729-735; not supported in CESM).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "pop_oracle.h"
+
+void* o_alloc_i(size_t n);
+#define NXB (M.nxb)
+#define NYB (M.nyb)
+#define NB (M.nblocks)
+static double* tmp2(void) { return (double*)calloc(M.n2, sizeof(double)); }
+static double* tmp2n(int n) { return (double*)calloc(M.n2 * n, sizeof(double)); }
+
+/* dhdt: surface_hgt.F90:206-286 (mix_pass /= 2) */
+void o_dhdt(void) {
+  for (int b = 0; b < NB; b++) {
+    double *DH = B2(M.DH, b), *DHU = B2(M.DHU, b);
+    const double *Pc = B2(M.PSURF[M.curtime], b), *Po = B2(M.PSURF[M.oldtime], b);
+    switch (M.cfg.sfc_layer_type) {
+      case POP_SFC_VARTHICK:
+        for (size_t q = 0; q < M.n2; q++)
+          DH[q] = (Pc[q] - Po[q]) / (O_GRAV * M.dtp) - B2(M.FW_OLD, b)[q];
+        break;
+      case POP_SFC_RIGID:
+        for (size_t q = 0; q < M.n2; q++) DH[q] = 0.0;
+        break;
+      default:
+        for (size_t q = 0; q < M.n2; q++) DH[q] = (Pc[q] - Po[q]) / (O_GRAV * M.dtp);
+    }
+    o_tgrid_to_ugrid(DHU, DH, b);
+    for (size_t q = 0; q < M.n2; q++)
+      if (B2(M.RCALCU, b)[q] == 0.0) DHU[q] = 0.0;
+  }
+}
+
+/* tracer_update: baroclinic.F90:1902-2306 */
+static void tracer_update(int k, double* WTK, double* TNEW, const double* TOLD, const double* TMIX,
+                          const double* TCUR, const double* UCUR, const double* VCUR,
+                          const double* UMIX, const double* VMIX, const double* STF_IN,
+                          const double* TFW_IN, const double* DH_IN, const double* POLD,
+                          const double* PCUR, int b) {
+  const int nt = M.nt;
+  const int* KMT = M.KMT + (size_t)b * M.n2;
+  double *FT = tmp2n(nt), *WORKN = tmp2n(nt);
+  o_hdifft(k, WORKN, TMIX, UMIX, VMIX, b);
+  for (size_t q = 0; q < M.n2 * nt; q++) FT[q] = FT[q] + WORKN[q];
+  if (k == 1) memcpy(WTK, DH_IN, sizeof(double) * M.n2);
+  o_advt(k, WORKN, WTK, TMIX, TCUR, UCUR, VCUR, b);
+  for (size_t q = 0; q < M.n2 * nt; q++) FT[q] = FT[q] - WORKN[q];
+  {
+    double t0 = o_now();
+    o_vdifft(k, WORKN, TOLD, STF_IN, b);
+    M.timer[OT_VMIXT] += o_now() - t0;
+  }
+  for (size_t q = 0; q < M.n2 * nt; q++) FT[q] = FT[q] + WORKN[q];
+  if (k == 1 && M.cfg.sfc_layer_type == POP_SFC_VARTHICK)
+    for (size_t q = 0; q < M.n2 * nt; q++) FT[q] = FT[q] + M.dzr[1] * TFW_IN[q];
+  /* sources: WORKN = 0 in the benchmark configs; FT = FT + WORKN */
+  for (size_t q = 0; q < M.n2 * nt; q++) FT[q] = FT[q] + 0.0;
+  const int predictor = (M.cfg.sfc_layer_type == POP_SFC_VARTHICK && k == 1 &&
+                         M.cfg.lpressure_avg && M.leapfrogts);
+  if (M.cfg.implicit_vertical_mix) {
+    for (int n = 1; n <= nt; n++) {
+      double* Tn = KN4(TNEW, k, n);
+      const double* F = FT + (size_t)(n - 1) * M.n2;
+      if (predictor && n <= 2) {
+        const double* Tc = KN4(TCUR, 1, n);
+        for (size_t q = 0; q < M.n2; q++)
+          if (KMT[q] > 0)
+            Tn[q] = M.c2dtt[1] * F[q] - 2.0 * Tc[q] * (PCUR[q] - POLD[q]) / (O_GRAV * M.dz[1]);
+      } else {
+        for (size_t q = 0; q < M.n2; q++) Tn[q] = (k <= KMT[q]) ? M.c2dtt[k] * F[q] : 0.0;
+      }
+    }
+  } else {
+    for (int n = 1; n <= nt; n++) {
+      double* Tn = KN4(TNEW, k, n);
+      const double *To = KN4(TOLD, k, n), *F = FT + (size_t)(n - 1) * M.n2;
+      if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK && k == 1) {
+        if (predictor && n <= 2) {
+          const double* Tc = KN4(TCUR, 1, n);
+          for (size_t q = 0; q < M.n2; q++)
+            Tn[q] = (KMT[q] > 0)
+                        ? To[q] + (1.0 / (1.0 + PCUR[q] / (O_GRAV * M.dz[1]))) *
+                                      (M.c2dtt[1] * F[q] -
+                                       2.0 * Tc[q] * (PCUR[q] - POLD[q]) / (O_GRAV * M.dz[1]))
+                        : 0.0;
+        } else {
+          for (size_t q = 0; q < M.n2; q++) Tn[q] = (k <= KMT[q]) ? M.c2dtt[k] * F[q] : 0.0;
+        }
+      } else {
+        for (size_t q = 0; q < M.n2; q++) Tn[q] = (k <= KMT[q]) ? To[q] + M.c2dtt[k] * F[q] : 0.0;
+      }
+    }
+  }
+  free(FT); free(WORKN);
+}
+
+/* clinic: baroclinic.F90:1635-1895 */
+static void clinic(int k, double* FX, double* FY, double* WUK, const double* UCUR,
+                   const double* VCUR, const double* UOLD, const double* VOLD, const double* UMIXK,
+                   const double* VMIXK, const double* RHOKOLD, const double* RHOKCUR,
+                   const double* RHOKNEW, const double* SMF_BLOCK, const double* DHU_BLOCK, int b) {
+  const int* KMU = M.KMU + (size_t)b * M.n2;
+  const double* FCOR = B2(M.FCOR, b);
+  double *WORKX = tmp2(), *WORKY = tmp2();
+  if (k == 1) memcpy(WUK, DHU_BLOCK, sizeof(double) * M.n2);
+  o_advu(k, WORKX, WORKY, WUK, UCUR, VCUR, b);
+  for (size_t q = 0; q < M.n2; q++) { FX[q] = -WORKX[q]; FY[q] = -WORKY[q]; }
+  const double *Uc = K3(UCUR, k), *Vc = K3(VCUR, k), *Uo = K3(UOLD, k), *Vo = K3(VOLD, k);
+  if (M.cfg.impcor && M.leapfrogts) {
+    for (size_t q = 0; q < M.n2; q++) {
+      FX[q] = FX[q] + FCOR[q] * (M.gamma_ * Vc[q] + (1.0 - M.gamma_) * Vo[q]);
+      FY[q] = FY[q] - FCOR[q] * (M.gamma_ * Uc[q] + (1.0 - M.gamma_) * Uo[q]);
+    }
+  } else if (!M.cfg.impcor && M.leapfrogts) {
+    for (size_t q = 0; q < M.n2; q++) {
+      FX[q] = FX[q] + FCOR[q] * Vc[q];
+      FY[q] = FY[q] - FCOR[q] * Uc[q];
+    }
+  } else {
+    for (size_t q = 0; q < M.n2; q++) {
+      FX[q] = FX[q] + FCOR[q] * Vo[q];
+      FY[q] = FY[q] - FCOR[q] * Uo[q];
+    }
+  }
+  o_gradp(k, WORKX, WORKY, RHOKOLD, RHOKCUR, RHOKNEW, b);
+  for (size_t q = 0; q < M.n2; q++) { FX[q] = FX[q] - WORKX[q]; FY[q] = FY[q] - WORKY[q]; }
+  o_hdiffu(k, WORKX, WORKY, UMIXK, VMIXK, b);
+  for (size_t q = 0; q < M.n2; q++) { FX[q] = FX[q] + WORKX[q]; FY[q] = FY[q] + WORKY[q]; }
+  {
+    double t0 = o_now();
+    o_vdiffu(k, WORKX, WORKY, UOLD, VOLD, SMF_BLOCK, b);
+    M.timer[OT_VMIXU] += o_now() - t0;
+  }
+  for (size_t q = 0; q < M.n2; q++) { FX[q] = FX[q] + WORKX[q]; FY[q] = FY[q] + WORKY[q]; }
+  for (size_t q = 0; q < M.n2; q++)
+    if (k > KMU[q]) { FX[q] = 0.0; FY[q] = 0.0; }
+  free(WORKX); free(WORKY);
+}
+
+/* baroclinic_driver: baroclinic.F90:578-1210 */
+int o_baroclinic_driver(void) {
+  const int km = M.km, nt = M.nt;
+  const int o = M.oldtime, c = M.curtime, n_ = M.newtime, mx = M.mixtime;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < NB; b++) {
+    double* WTK = tmp2();
+    for (int k = 1; k <= km; k++) {
+      o_vmix_coeffs(k, B4(M.TRACER[mx], b), B3(M.UVEL[mx], b), B3(M.VVEL[mx], b), B3(M.RHO[mx], b), b);
+      tracer_update(k, WTK, B4(M.TRACER[n_], b), B4(M.TRACER[o], b), B4(M.TRACER[mx], b),
+                    B4(M.TRACER[c], b), B3(M.UVEL[c], b), B3(M.VVEL[c], b), B3(M.UVEL[mx], b),
+                    B3(M.VVEL[mx], b), M.STF + (size_t)b * nt * M.n2, M.TFW + (size_t)b * nt * M.n2,
+                    B2(M.DH, b), B2(M.PSURF[o], b), B2(M.PSURF[c], b), b);
+    }
+    if (M.cfg.implicit_vertical_mix) {
+      if (M.cfg.sfc_layer_type != POP_SFC_VARTHICK)
+        o_impvmixt(B4(M.TRACER[n_], b), B4(M.TRACER[o], b), B2(M.PSURF[c], b), 1, nt, b);
+      else if (M.cfg.lpressure_avg && M.leapfrogts)
+        o_impvmixt(B4(M.TRACER[n_], b), B4(M.TRACER[o], b), B2(M.PSURF[c], b), 1, 2, b);
+    }
+    free(WTK);
+  }
+  if (M.cfg.lpressure_avg && M.leapfrogts) {
+    /* halo of T and S (new): baroclinic.F90:919-935; TRACER(:,:,:,n,newtime,:) is a 3-d halo per
+       tracer; with nt tracers stored [b][n][k] this is a 4-d halo restricted to n=1,2 */
+    for (int n = 1; n <= 2; n++) {
+      /* per-tracer 3-d slices are strided by nt*km*n2 between blocks: use the 2-d primitive */
+      extern void oracle_halo_2d(double*, int, int, double);
+      double* base = M.TRACER[n_] + (size_t)(n - 1) * M.n3;
+      /* emulate: array(nxb,nyb,km,nblocks) with block stride nt*n3 */
+      for (int k = 0; k < km; k++) {
+        /* temporarily view level k of tracer n across blocks */
+        double* lev = (double*)malloc(sizeof(double) * M.n2 * NB);
+        for (int b = 0; b < NB; b++)
+          memcpy(lev + (size_t)b * M.n2, base + (size_t)b * nt * M.n3 + (size_t)k * M.n2, sizeof(double) * M.n2);
+        oracle_halo_2d(lev, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+        for (int b = 0; b < NB; b++)
+          memcpy(base + (size_t)b * nt * M.n3 + (size_t)k * M.n2, lev + (size_t)b * M.n2, sizeof(double) * M.n2);
+        free(lev);
+      }
+    }
+  }
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < NB; b++) {
+    double *FX = tmp2(), *FY = tmp2(), *WUK = tmp2(), *WORK1 = tmp2(), *WORK2 = tmp2();
+    double *ZX = B2(M.ZX, b), *ZY = B2(M.ZY, b);
+    const double *FCOR = B2(M.FCOR, b), *HUR = B2(M.HUR, b);
+    const int* KMU = M.KMU + (size_t)b * M.n2;
+    double *Un = B3(M.UVEL[n_], b), *Vn = B3(M.VVEL[n_], b);
+    memset(ZX, 0, sizeof(double) * M.n2);
+    memset(ZY, 0, sizeof(double) * M.n2);
+    for (int k = 1; k <= km; k++) {
+      if (M.cfg.lpressure_avg && M.leapfrogts)
+        o_state(k, k, KN4(B4(M.TRACER[n_], b), k, 1), KN4(B4(M.TRACER[n_], b), k, 2), b,
+                K3(B3(M.RHO[n_], b), k), NULL, NULL, NULL);
+      clinic(k, FX, FY, WUK, B3(M.UVEL[c], b), B3(M.VVEL[c], b), B3(M.UVEL[o], b), B3(M.VVEL[o], b),
+             K3(B3(M.UVEL[mx], b), k), K3(B3(M.VVEL[mx], b), k), K3(B3(M.RHO[o], b), k),
+             K3(B3(M.RHO[c], b), k), K3(B3(M.RHO[n_], b), k), M.SMF + (size_t)b * 2 * M.n2,
+             B2(M.DHU, b), b);
+      double *Uk = K3(Un, k), *Vk = K3(Vn, k);
+      if (M.cfg.impcor) {
+        for (size_t q = 0; q < M.n2; q++) {
+          WORK1[q] = M.c2dtu * M.beta * FCOR[q];
+          WORK2[q] = M.c2dtu / (1.0 + WORK1[q] * WORK1[q]);
+          Uk[q] = (FX[q] + WORK1[q] * FY[q]) * WORK2[q];
+          Vk[q] = (FY[q] - WORK1[q] * FX[q]) * WORK2[q];
+        }
+      } else {
+        for (size_t q = 0; q < M.n2; q++) { Uk[q] = M.c2dtu * FX[q]; Vk[q] = M.c2dtu * FY[q]; }
+      }
+      for (size_t q = 0; q < M.n2; q++) {
+        ZX[q] = ZX[q] + FX[q] * M.dz[k];
+        ZY[q] = ZY[q] + FY[q] * M.dz[k];
+      }
+    }
+    for (size_t q = 0; q < M.n2; q++) { ZX[q] = ZX[q] * HUR[q]; ZY[q] = ZY[q] * HUR[q]; }
+    if (M.cfg.implicit_vertical_mix) o_impvmixu(Un, Vn, b);
+    {
+      const double *Uo = B3(M.UVEL[o], b), *Vo = B3(M.VVEL[o], b);
+      for (size_t q = 0; q < M.n3; q++) { Un[q] = Uo[q] + Un[q]; Vn[q] = Vo[q] + Vn[q]; }
+    }
+    memset(WORK1, 0, sizeof(double) * M.n2);
+    memset(WORK2, 0, sizeof(double) * M.n2);
+    for (int k = 1; k <= km; k++)
+      for (size_t q = 0; q < M.n2; q++) {
+        WORK1[q] = WORK1[q] + K3(Un, k)[q] * M.dz[k];
+        WORK2[q] = WORK2[q] + K3(Vn, k)[q] * M.dz[k];
+      }
+    for (size_t q = 0; q < M.n2; q++) { WORK1[q] = WORK1[q] * HUR[q]; WORK2[q] = WORK2[q] * HUR[q]; }
+    for (int k = 1; k <= km; k++)
+      for (size_t q = 0; q < M.n2; q++) {
+        if (k <= KMU[q]) {
+          K3(Un, k)[q] = K3(Un, k)[q] - WORK1[q];
+          K3(Vn, k)[q] = K3(Vn, k)[q] - WORK2[q];
+        } else {
+          K3(Un, k)[q] = 0.0;
+          K3(Vn, k)[q] = 0.0;
+        }
+      }
+    free(FX); free(FY); free(WUK); free(WORK1); free(WORK2);
+  }
+  return 0;
+}
+
+/* baroclinic_correct_adjust: baroclinic.F90:1217-1497 */
+void o_baroclinic_correct_adjust(void) {
+  const int km = M.km, nt = M.nt;
+  const int o = M.oldtime, c = M.curtime, n_ = M.newtime, mx = M.mixtime;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < NB; b++) {
+    const int* KMT = M.KMT + (size_t)b * M.n2;
+    double *Tn = B4(M.TRACER[n_], b), *To = B4(M.TRACER[o], b), *Tc = B4(M.TRACER[c], b);
+    const double *Pn = B2(M.PSURF[n_], b), *Pc = B2(M.PSURF[c], b), *Po = B2(M.PSURF[o], b),
+                 *Pm = B2(M.PSURF[mx], b);
+    if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+      if (M.cfg.implicit_vertical_mix) {
+        if (M.cfg.lpressure_avg && M.leapfrogts) {
+          double* RHS1 = tmp2n(nt);
+          for (int n = 1; n <= 2; n++) {
+            double* R = RHS1 + (size_t)(n - 1) * M.n2;
+            const double *tc = KN4(Tc, 1, n), *to = KN4(To, 1, n), *tn = KN4(Tn, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              R[q] = (KMT[q] > 0) ? ((2.0 * tc[q] - to[q]) * (Pc[q] - Po[q]) - tn[q] * (Pn[q] - Pc[q])) /
+                                        (O_GRAV * M.dz[1])
+                                  : 0.0;
+          }
+          o_impvmixt_correct(Tn, Pn, RHS1, 1, 2, b);
+          for (int n = 3; n <= nt; n++) {
+            double* tn = KN4(Tn, 1, n);
+            const double* to = KN4(To, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              if (KMT[q] > 0) tn[q] = tn[q] - to[q] * (Pn[q] - Po[q]) / (O_GRAV * M.dz[1]);
+          }
+          o_impvmixt(Tn, To, Pn, 3, nt, b);
+          free(RHS1);
+        } else {
+          for (int n = 1; n <= nt; n++) {
+            double* tn = KN4(Tn, 1, n);
+            const double* to = KN4(To, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              if (KMT[q] > 0) tn[q] = tn[q] - to[q] * (Pn[q] - Pm[q]) / (O_GRAV * M.dz[1]);
+          }
+          o_impvmixt(Tn, To, Pn, 1, nt, b);
+        }
+      } else {
+        if (M.cfg.lpressure_avg && M.leapfrogts) {
+          for (int n = 1; n <= 2; n++) {
+            double* tn = KN4(Tn, 1, n);
+            const double *tc = KN4(Tc, 1, n), *to = KN4(To, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              tn[q] = (KMT[q] > 0)
+                          ? (tn[q] * (M.dz[1] + Pc[q] / O_GRAV) +
+                             (2.0 * tc[q] - to[q]) * (Pc[q] - Po[q]) / O_GRAV) /
+                                (M.dz[1] + Pn[q] / O_GRAV)
+                          : 0.0;
+          }
+          for (int n = 3; n <= nt; n++) {
+            double* tn = KN4(Tn, 1, n);
+            const double* to = KN4(To, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              tn[q] = (KMT[q] > 0) ? (to[q] * (M.dz[1] + Po[q] / O_GRAV) + M.dz[1] * tn[q]) /
+                                         (M.dz[1] + Pn[q] / O_GRAV)
+                                   : 0.0;
+          }
+        } else {
+          for (int n = 1; n <= nt; n++) {
+            double* tn = KN4(Tn, 1, n);
+            const double* to = KN4(To, 1, n);
+            for (size_t q = 0; q < M.n2; q++)
+              tn[q] = (KMT[q] > 0) ? (to[q] * (M.dz[1] + Pm[q] / O_GRAV) + M.dz[1] * tn[q]) /
+                                         (M.dz[1] + Pn[q] / O_GRAV)
+                                   : 0.0;
+          }
+        }
+      }
+    }
+    /* convad: convection_type = 'diffusion' -> immediate return (vertical_mix.F90:1925) */
+    for (int k = 1; k <= km; k++)
+      o_state(k, k, KN4(Tn, k, 1), KN4(Tn, k, 2), b, K3(B3(M.RHO[n_], b), k), NULL, NULL, NULL);
+  }
+}
+
+/* init_barotropic: barotropic.F90:170-252 */
+void o_init_barotropic(void) {
+  size_t ntot = M.n2 * (size_t)NB;
+  M.CHECKER = o_alloc_i(ntot);
+  M.CONSTNT = o_alloc_i(ntot);
+  double *CHK = (double*)calloc(ntot, sizeof(double)), *CST = (double*)calloc(ntot, sizeof(double)),
+         *CHKA = (double*)calloc(ntot, sizeof(double)), *CSTA = (double*)calloc(ntot, sizeof(double));
+  if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+    for (int b = 0; b < NB; b++) {
+      const int *ig = M.i_glob + (size_t)b * NXB, *jg = M.j_glob + (size_t)b * NYB;
+      const int* KMT = M.KMT + (size_t)b * M.n2;
+      for (int j = 1; j <= NYB; j++)
+        for (int i = 1; i <= NXB; i++) {
+          size_t q = (size_t)b * M.n2 + IX2(i, j);
+          int n = ig[i - 1] + abs(jg[j - 1]);
+          int chk = 2 * (n % 2) - 1;
+          if (KMT[IX2(i, j)] > 0) {
+            M.CHECKER[q] = chk; M.CONSTNT[q] = 1;
+            CHKA[q] = chk * M.TAREA[q]; CSTA[q] = M.TAREA[q];
+          } else {
+            M.CHECKER[q] = 0; M.CONSTNT[q] = 0; CHKA[q] = 0.0; CSTA[q] = 0.0;
+          }
+          CHK[q] = M.CHECKER[q]; CST[q] = M.CONSTNT[q];
+        }
+    }
+    /* sum_check, sum_const are integers in the reference (integer global_sum) */
+    long sum_check = lround(oracle_global_sum(CHK, POP_LOC_CENTER, NULL));
+    long sum_const = lround(oracle_global_sum(CST, POP_LOC_CENTER, NULL));
+    double acheck = oracle_global_sum(CHKA, POP_LOC_CENTER, NULL) / oracle_global_sum(CSTA, POP_LOC_CENTER, NULL);
+    M.rcheck = acheck / ((double)sum_const - acheck * (double)sum_check);
+    M.rconst = 1.0 / ((double)sum_const - acheck * (double)sum_check);
+  }
+  free(CHK); free(CST); free(CHKA); free(CSTA);
+  double* dc = tmp2();
+  for (int b = 0; b < NB; b++) {
+    for (size_t q = 0; q < M.n2; q++) {
+      if (M.cfg.sfc_layer_type == POP_SFC_RIGID) dc[q] = 0.0;
+      else
+        dc[q] = (B2(M.RCALCT, b)[q] != 0.0)
+                    ? B2(M.TAREA, b)[q] / (M.alpha * 2.0 * M.dtp * M.dtp * O_GRAV)
+                    : 0.0;
+    }
+    o_solvers_diagonal(dc, b);
+  }
+  free(dc);
+}
+
+/* barotropic_driver: barotropic.F90:267-735 (leapfrog / forward-euler branches) */
+int o_barotropic_driver(void) {
+  const int o = M.oldtime, c = M.curtime, n_ = M.newtime;
+  size_t ntot = M.n2 * (size_t)NB;
+  double *RHS = (double*)calloc(ntot, sizeof(double)), *UH = (double*)calloc(ntot, sizeof(double)),
+         *VH = (double*)calloc(ntot, sizeof(double)), *PCHECK = (double*)calloc(ntot, sizeof(double));
+  const double c2dtp = M.c2dtp, beta = M.beta, gam = M.gamma_;
+  for (int b = 0; b < NB; b++) {
+    double *W1 = tmp2(), *W2 = tmp2(), *W3 = tmp2(), *W4 = tmp2(), *dc = tmp2();
+    const double *ZX = B2(M.ZX, b), *ZY = B2(M.ZY, b), *GXc = B2(M.GRADPX[c], b),
+                 *GXo = B2(M.GRADPX[o], b), *GYc = B2(M.GRADPY[c], b), *GYo = B2(M.GRADPY[o], b),
+                 *FCOR = B2(M.FCOR, b), *HU = B2(M.HU, b);
+    double *UHb = B2(UH, b), *VHb = B2(VH, b), *RHSb = B2(RHS, b);
+    if (M.leapfrogts) {
+      for (size_t q = 0; q < M.n2; q++) {
+        W3[q] = c2dtp * (ZX[q] - gam * GXc[q] - (1.0 - gam) * GXo[q]);
+        W4[q] = c2dtp * (ZY[q] - gam * GYc[q] - (1.0 - gam) * GYo[q]);
+      }
+    } else {
+      for (size_t q = 0; q < M.n2; q++) {
+        W3[q] = c2dtp * (ZX[q] - GXc[q]);
+        W4[q] = c2dtp * (ZY[q] - GYc[q]);
+      }
+    }
+    if (M.cfg.impcor) {
+      for (size_t q = 0; q < M.n2; q++) {
+        W1[q] = c2dtp * beta * FCOR[q];
+        W2[q] = 1.0 / (1.0 + W1[q] * W1[q]);
+        UHb[q] = W2[q] * (W3[q] + W1[q] * W4[q]) + B2(M.UBTROP[o], b)[q];
+        VHb[q] = W2[q] * (W4[q] - W1[q] * W3[q]) + B2(M.VBTROP[o], b)[q];
+      }
+    } else {
+      for (size_t q = 0; q < M.n2; q++) {
+        UHb[q] = W3[q] + B2(M.UBTROP[o], b)[q];
+        VHb[q] = W4[q] + B2(M.VBTROP[o], b)[q];
+      }
+    }
+    const double *GX = M.leapfrogts ? GXo : GXc, *GY = M.leapfrogts ? GYo : GYc;
+    for (size_t q = 0; q < M.n2; q++) {
+      W3[q] = HU[q] * (UHb[q] + beta * c2dtp * GX[q]);
+      W4[q] = HU[q] * (VHb[q] + beta * c2dtp * GY[q]);
+    }
+    o_div(1, RHSb, W3, W4, b);
+    for (size_t q = 0; q < M.n2; q++) RHSb[q] = RHSb[q] / (beta * c2dtp);
+    switch (M.cfg.sfc_layer_type) {
+      case POP_SFC_VARTHICK:
+        for (size_t q = 0; q < M.n2; q++) {
+          dc[q] = (B2(M.RCALCT, b)[q] != 0.0) ? B2(M.TAREA, b)[q] / (beta * c2dtp * M.dtp * O_GRAV) : 0.0;
+          RHSb[q] = RHSb[q] - dc[q] * B2(M.PSURF[c], b)[q] -
+                    B2(M.FW, b)[q] * B2(M.TAREA, b)[q] / (beta * c2dtp);
+        }
+        break;
+      case POP_SFC_RIGID:
+        for (size_t q = 0; q < M.n2; q++) dc[q] = 0.0;
+        break;
+      default:
+        for (size_t q = 0; q < M.n2; q++) {
+          dc[q] = (B2(M.RCALCT, b)[q] != 0.0) ? B2(M.TAREA, b)[q] / (beta * c2dtp * M.dtp * O_GRAV) : 0.0;
+          RHSb[q] = RHSb[q] - dc[q] * B2(M.PSURF[c], b)[q];
+        }
+    }
+    o_solvers_diagonal(dc, b);
+    memcpy(B2(M.PSURF[n_], b), B2(M.PGUESS, b), sizeof(double) * M.n2);
+    free(W1); free(W2); free(W3); free(W4); free(dc);
+  }
+  oracle_halo_2d(RHS, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+  int rc = o_solvers_run(M.PSURF[n_], RHS);
+  if (rc == 0) {
+    double xcheck = 0.0;
+    if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+      for (size_t q = 0; q < ntot; q++) PCHECK[q] = M.PSURF[n_][q] * M.CHECKER[q];
+      xcheck = oracle_global_sum(PCHECK, POP_LOC_CENTER, NULL);
+    }
+    for (int b = 0; b < NB; b++) {
+      double* Pn = B2(M.PSURF[n_], b);
+      if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK)
+        for (size_t q = 0; q < M.n2; q++)
+          Pn[q] = Pn[q] + (M.CONSTNT + (size_t)b * M.n2)[q] * M.rcheck * xcheck -
+                  (M.CHECKER + (size_t)b * M.n2)[q] * M.rconst * xcheck;
+      double *GXn = B2(M.GRADPX[n_], b), *GYn = B2(M.GRADPY[n_], b);
+      o_grad(1, GXn, GYn, Pn, b);
+      const double *GXr = M.leapfrogts ? B2(M.GRADPX[o], b) : B2(M.GRADPX[c], b),
+                   *GYr = M.leapfrogts ? B2(M.GRADPY[o], b) : B2(M.GRADPY[c], b);
+      for (size_t q = 0; q < M.n2; q++) {
+        B2(M.UBTROP[n_], b)[q] = B2(UH, b)[q] - beta * c2dtp * (GXn[q] - GXr[q]);
+        B2(M.VBTROP[n_], b)[q] = B2(VH, b)[q] - beta * c2dtp * (GYn[q] - GYr[q]);
+      }
+    }
+    oracle_halo_2d(M.PSURF[n_], POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+    oracle_halo_2d(M.GRADPX[n_], POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+    oracle_halo_2d(M.GRADPY[n_], POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  }
+  free(RHS); free(UH); free(VH); free(PCHECK);
+  return rc;
+}
+
+/* step: step_mod.F90:296-626, 634-640, 663-832 */
+int oracle_step(int ts_type) {
+  double t0 = o_now(), t1;
+  const int km = M.km, nt = M.nt;
+  oracle_set_timestep(ts_type);
+  o_dhdt();
+  t1 = o_now();
+  if (o_baroclinic_driver() != 0) return -1;
+  M.timer[OT_BAROCLINIC] += o_now() - t1;
+  oracle_halo_2d(M.ZX, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  oracle_halo_2d(M.ZY, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  t1 = o_now();
+  if (o_barotropic_driver() != 0) return -1;
+  M.timer[OT_BAROTROPIC] += o_now() - t1;
+  t1 = o_now();
+  o_baroclinic_correct_adjust();
+  M.timer[OT_BAROCLINIC] += o_now() - t1;
+  const int n_ = M.newtime;
+  oracle_halo_2d(M.UBTROP[n_], POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  oracle_halo_2d(M.VBTROP[n_], POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  oracle_halo_3d(M.UVEL[n_], km, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  oracle_halo_3d(M.VVEL[n_], km, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0);
+  oracle_halo_3d(M.RHO[n_], km, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+  oracle_halo_4d(M.TRACER[n_], km, nt, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+  /* add barotropic to baroclinic velocities: step_mod.F90:574-592 */
+  for (int b = 0; b < NB; b++) {
+    const int* KMU = M.KMU + (size_t)b * M.n2;
+    for (int k = 1; k <= km; k++) {
+      double *U = K3(B3(M.UVEL[n_], b), k), *V = K3(B3(M.VVEL[n_], b), k);
+      const double *UB = B2(M.UBTROP[n_], b), *VB = B2(M.VBTROP[n_], b);
+      for (size_t q = 0; q < M.n2; q++)
+        if (k <= KMU[q]) { U[q] = U[q] + UB[q]; V[q] = V[q] + VB[q]; }
+    }
+  }
+  /* PGUESS: step_mod.F90:634-640 */
+  for (size_t q = 0; q < M.n2 * (size_t)NB; q++)
+    M.PGUESS[q] = 3.0 * (M.PSURF[M.newtime][q] - M.PSURF[M.curtime][q]) + M.PSURF[M.oldtime][q];
+  if (M.avg_ts) {
+    /* averaging step: step_mod.F90:663-796 */
+    const int o = M.oldtime, c = M.curtime;
+    size_t n2t = M.n2 * (size_t)NB, n3t = M.n3 * (size_t)NB;
+#define AVG2(F) for (size_t q = 0; q < n2t; q++) { F[o][q] = 0.5 * (F[o][q] + F[c][q]); } \
+                for (size_t q = 0; q < n2t; q++) { F[c][q] = 0.5 * (F[c][q] + F[n_][q]); }
+    AVG2(M.UBTROP) AVG2(M.VBTROP) AVG2(M.GRADPX) AVG2(M.GRADPY)
+#undef AVG2
+    for (size_t q = 0; q < n2t; q++) M.FW_OLD[q] = 0.5 * (M.FW[q] + M.FW_OLD[q]);
+    for (size_t q = 0; q < n3t; q++) {
+      M.UVEL[o][q] = 0.5 * (M.UVEL[o][q] + M.UVEL[c][q]);
+      M.VVEL[o][q] = 0.5 * (M.VVEL[o][q] + M.VVEL[c][q]);
+    }
+    for (size_t q = 0; q < n3t; q++) {
+      M.UVEL[c][q] = 0.5 * (M.UVEL[c][q] + M.UVEL[n_][q]);
+      M.VVEL[c][q] = 0.5 * (M.VVEL[c][q] + M.VVEL[n_][q]);
+    }
+    for (int b = 0; b < NB; b++) {
+      double *To = B4(M.TRACER[o], b), *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+      for (int n = 1; n <= nt; n++)
+        for (int k = 2; k <= km; k++)
+          for (size_t q = 0; q < M.n2; q++) {
+            KN4(To, k, n)[q] = 0.5 * (KN4(To, k, n)[q] + KN4(Tc, k, n)[q]);
+            KN4(Tc, k, n)[q] = 0.5 * (KN4(Tc, k, n)[q] + KN4(Tn, k, n)[q]);
+          }
+      double *Po = B2(M.PSURF[o], b), *Pc = B2(M.PSURF[c], b), *Pn = B2(M.PSURF[n_], b);
+      if (M.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+        double *PFO = tmp2(), *PFC = tmp2();
+        for (size_t q = 0; q < M.n2; q++) {
+          PFO[q] = 0.5 * (Po[q] + Pc[q]);
+          PFC[q] = 0.5 * (Pc[q] + Pn[q]);
+        }
+        for (int n = 1; n <= nt; n++) {
+          double *to = KN4(To, 1, n), *tc = KN4(Tc, 1, n), *tn = KN4(Tn, 1, n);
+          for (size_t q = 0; q < M.n2; q++) {
+            double wmin = fmin(to[q], tc[q]), wmax = fmax(to[q], tc[q]);
+            double v = 0.5 * ((M.dz[1] + Po[q] / O_GRAV) * to[q] + (M.dz[1] + Pc[q] / O_GRAV) * tc[q]);
+            v = v / (M.dz[1] + PFO[q] / O_GRAV);
+            if (v < wmin) v = wmin;
+            if (v > wmax) v = wmax;
+            double wmin2 = fmin(tc[q], tn[q]), wmax2 = fmax(tc[q], tn[q]);
+            double w = 0.5 * ((M.dz[1] + Pc[q] / O_GRAV) * tc[q] + (M.dz[1] + Pn[q] / O_GRAV) * tn[q]);
+            w = w / (M.dz[1] + PFC[q] / O_GRAV);
+            if (w < wmin2) w = wmin2;
+            if (w > wmax2) w = wmax2;
+            to[q] = v;
+            tc[q] = w;
+          }
+        }
+        memcpy(Po, PFO, sizeof(double) * M.n2);
+        memcpy(Pc, PFC, sizeof(double) * M.n2);
+        free(PFO); free(PFC);
+      } else {
+        for (int n = 1; n <= nt; n++) {
+          double *to = KN4(To, 1, n), *tc = KN4(Tc, 1, n), *tn = KN4(Tn, 1, n);
+          for (size_t q = 0; q < M.n2; q++) {
+            to[q] = 0.5 * (to[q] + tc[q]);
+            tc[q] = 0.5 * (tc[q] + tn[q]);
+          }
+        }
+        for (size_t q = 0; q < M.n2; q++) {
+          Po[q] = 0.5 * (Po[q] + Pc[q]);
+          Pc[q] = 0.5 * (Pc[q] + Pn[q]);
+        }
+      }
+      for (int k = 1; k <= km; k++) {
+        o_state(k, k, KN4(To, k, 1), KN4(To, k, 2), b, K3(B3(M.RHO[o], b), k), NULL, NULL, NULL);
+        o_state(k, k, KN4(Tc, k, 1), KN4(Tc, k, 2), b, K3(B3(M.RHO[c], b), k), NULL, NULL, NULL);
+      }
+      for (size_t q = 0; q < M.n2; q++) B2(M.PGUESS, b)[q] = 0.5 * (B2(M.PGUESS, b)[q] + Pn[q]);
+    }
+  } else {
+    /* non-averaging step: FW_OLD = FW; rotate time levels (step_mod.F90:804-830) */
+    memcpy(M.FW_OLD, M.FW, sizeof(double) * M.n2 * (size_t)NB);
+    int tmptime = M.oldtime;
+    M.oldtime = M.curtime;
+    M.curtime = M.newtime;
+    M.newtime = tmptime;
+  }
+  M.timer[OT_STEP] += o_now() - t0;
+  return 0;
+}
