@@ -1,0 +1,414 @@
+// pop_core.cu -- context, error stack, field registry, lifecycle, time-step scalars.
+// Replaces (for this path) pop_init_phase1/2 bookkeeping of source/initial.F90:133,464 and the
+// time-step switches of source/step_mod.F90:302-320 / source/time_management.F90:434-439.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "pop_dev.cuh"
+
+Ctx G;
+__constant__ VertConst c_vc;
+
+static thread_local char g_err[1024] = "";
+static char g_err_shared[1024] = "";
+
+void pop_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  strncpy(g_err_shared, g_err, sizeof(g_err_shared) - 1);
+}
+
+extern "C" const char* pop_last_error(void) { return g_err[0] ? g_err : g_err_shared; }
+
+int pop_post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pop_set_error("kernel launch failed (%s): %s", what, cudaGetErrorString(e));
+    return POP_FAIL;
+  }
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ timers
+ScopedTimer::ScopedTimer(const char* n) : name(n), on(G.timers_on) {
+  if (!on) return;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, G.stream);
+}
+ScopedTimer::~ScopedTimer() {
+  if (!on) return;
+  cudaEventRecord(e1, G.stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  Timer& t = G.timers[name];
+  t.ms += ms;
+  t.calls++;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+// ------------------------------------------------------------------ registry
+static const char* kPrognostic[] = {"TRACER", "UVEL",   "VVEL",   "RHO",   "PSURF",
+                                    "GRADPX", "GRADPY", "UBTROP", "VBTROP"};
+
+bool resolve_name(const char* name, int tlev, std::string* out) {
+  for (const char* p : kPrognostic)
+    if (!strcmp(name, p)) {
+      int s = (tlev == POP_TIME_OLD) ? G.oldtime : (tlev == POP_TIME_NEW) ? G.newtime : G.curtime;
+      *out = std::string(name) + "#" + std::to_string(s);
+      return true;
+    }
+  *out = name;
+  return G.fields.count(*out) > 0;
+}
+
+double* fld(const char* name) {
+  auto it = G.fields.find(name);
+  return (it == G.fields.end() || it->second.is_int) ? nullptr : (double*)it->second.p;
+}
+int* fldi(const char* name) {
+  auto it = G.fields.find(name);
+  return (it == G.fields.end() || !it->second.is_int) ? nullptr : (int*)it->second.p;
+}
+double* fld_t(const char* base, int storage) {
+  return fld((std::string(base) + "#" + std::to_string(storage)).c_str());
+}
+
+int alloc_field(const char* name, int nz, bool is_int) {
+  if (G.fields.count(name)) return POP_SUCCESS;
+  DevField f;
+  f.nz = nz;
+  f.is_int = is_int;
+  f.elems = G.n2 * (size_t)nz;
+  size_t bytes = f.elems * (is_int ? sizeof(int) : sizeof(double));
+  cudaError_t e = cudaMalloc(&f.p, bytes);
+  if (e != cudaSuccess) {
+    pop_set_error("cudaMalloc(%s, %zu bytes) failed: %s", name, bytes, cudaGetErrorString(e));
+    return POP_FAIL;
+  }
+  POP_CHECK_CUDA(cudaMemsetAsync(f.p, 0, bytes, G.stream));
+  G.fields[name] = f;
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ config defaults
+extern "C" void pop_config_defaults(pop_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->nt = 2;
+  c->ew_boundary_type = POP_BNDY_CYCLIC;
+  c->ns_boundary_type = POP_BNDY_CLOSED;
+  for (int n = 0; n < POP_MAX_NT; n++) c->tadvect_itype[n] = POP_TADVECT_CENTERED;
+  c->hmix_tracer_itype = POP_HMIX_DEL2;
+  c->hmix_momentum_itype = POP_HMIX_DEL2;
+  c->ah = 1.0e7;
+  c->am = 1.0e7;
+  c->ah_gm = c->ah_bolus = c->ah_bkg_srfbl = 0.8e7;
+  c->slm_r = c->slm_b = 0.3;
+  c->vmix_itype = POP_VMIX_CONST;
+  c->implicit_vertical_mix = 1;
+  c->vdc_ndim = 1;
+  c->aidif = 1.0;
+  c->bottom_drag = 1.0e-3;
+  c->const_vdc = 0.25;
+  c->const_vvc = 0.25;
+  c->bckgrnd_vdc = 0.1;
+  c->bckgrnd_vvc = 1.0;
+  c->rich_mix = 50.0;
+  c->convection_diff = 1;
+  c->convect_diff = 1000.0;
+  c->convect_visc = 1000.0;
+  c->sfc_layer_type = POP_SFC_VARTHICK;
+  c->lpressure_avg = 1;
+  c->lbouss_correct = 1;
+  c->impcor = 1;
+  c->state_itype = POP_STATE_MWJF;
+  c->state_range_iopt = POP_STATE_RANGE_ENFORCE;
+  c->solver_choice = POP_SOLVER_CHRONGEAR;
+  c->max_iterations = 1000;
+  c->convergence_check_freq = 10;
+  c->convergence_check_start = 60;
+  c->max_lanczos_step = 20;
+  c->convergence_criterion = 1.0e-13;
+  c->lanczos_convergence_criterion = 0.1;
+  c->dtt = 3600.0;
+  c->nranks = 1;
+}
+
+// ------------------------------------------------------------------ lifecycle
+extern "C" int pop_is_initialized(void) { return G.initialized ? 1 : 0; }
+
+static int alloc_all_fields() {
+  const pop_config& c = G.cfg;
+  const int km = G.km, nt = G.nt;
+  for (int s = 0; s < 3; s++) {
+    std::string sfx = "#" + std::to_string(s);
+    POP_TRY(alloc_field(("TRACER" + sfx).c_str(), km * nt, false));
+    POP_TRY(alloc_field(("UVEL" + sfx).c_str(), km, false));
+    POP_TRY(alloc_field(("VVEL" + sfx).c_str(), km, false));
+    POP_TRY(alloc_field(("RHO" + sfx).c_str(), km, false));
+    for (const char* n2d : {"PSURF", "GRADPX", "GRADPY", "UBTROP", "VBTROP"})
+      POP_TRY(alloc_field((std::string(n2d) + sfx).c_str(), 1, false));
+  }
+  POP_TRY(alloc_field("PGUESS", 1, false));
+  POP_TRY(alloc_field("STF", nt, false));
+  POP_TRY(alloc_field("TFW", nt, false));
+  POP_TRY(alloc_field("SMF", 2, false));
+  for (const char* n2d : {"SHF_QSW", "FW", "FW_OLD", "DH", "DHU", "ZX", "ZY", "VUF", "VVF", "SUMX",
+                          "SUMY", "RHOKMX", "RHOKMY", "WTK_C", "WUK_C", "RHS_BT", "UH_BT", "VH_BT",
+                          "DIAGC", "W2A", "W2B", "W2C", "W2D"})
+    POP_TRY(alloc_field(n2d, 1, false));
+  POP_TRY(alloc_field("VTF", nt, false));
+  POP_TRY(alloc_field("AUX", nt, false));
+  POP_TRY(alloc_field("RHS1", nt, false));
+  // vertical_mix.F90:383-419: VDC/VVC shapes
+  if (c.vmix_itype == POP_VMIX_GIVEN) {
+    G.vdc_nk = c.vdc_kdim_halo ? km + 2 : km;
+    G.vdc_k0 = c.vdc_kdim_halo ? 0 : 1;
+    G.vdc_nd = c.vdc_ndim > 0 ? c.vdc_ndim : 1;
+    G.vvc_nk = km;
+  } else if (c.vmix_itype == POP_VMIX_CONST) {
+    G.vdc_nk = c.implicit_vertical_mix ? km : 1;
+    G.vdc_k0 = 1;
+    G.vdc_nd = 1;
+    G.vvc_nk = c.implicit_vertical_mix ? km : 1;
+  } else {
+    G.vdc_nk = c.implicit_vertical_mix ? km : 1;
+    G.vdc_k0 = 1;
+    G.vdc_nd = 1;
+    G.vvc_nk = km;
+  }
+  POP_TRY(alloc_field("VDC", G.vdc_nk * G.vdc_nd, false));
+  POP_TRY(alloc_field("VVC", G.vvc_nk, false));
+  // work: Thomas E coefficients; momentum Thomas E
+  POP_TRY(alloc_field("WORK3D_E", km, false));
+  return POP_SUCCESS;
+}
+
+extern "C" int pop_init(const pop_config* cfg) {
+  if (G.initialized) pop_finalize();
+  POP_REQUIRE(cfg != nullptr, "pop_init: null config");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  POP_REQUIRE(e == cudaSuccess && ndev > 0,
+              "pop_init: no usable CUDA device (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  POP_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "pop_init: device %d out of range (%d)",
+              cfg->device, ndev);
+  POP_CHECK_CUDA(cudaSetDevice(cfg->device));
+  G.cfg = *cfg;
+  G.nxg = cfg->nx_global;
+  G.nyg = cfg->ny_global;
+  G.km = cfg->km;
+  G.nt = cfg->nt;
+  G.rank = cfg->rank;
+  G.nranks = cfg->nranks > 0 ? cfg->nranks : 1;
+  POP_REQUIRE(G.nxg > 0 && G.nyg > 0 && G.km >= 3 && G.km <= POP_KMAX, "pop_init: bad sizes %d x %d x %d",
+              G.nxg, G.nyg, G.km);
+  POP_REQUIRE(G.nt >= 2 && G.nt <= POP_MAX_NT, "pop_init: nt=%d out of range", G.nt);
+  POP_REQUIRE(G.nyg % G.nranks == 0, "pop_init: ny_global=%d not divisible by nranks=%d", G.nyg,
+              G.nranks);
+  POP_REQUIRE(!cfg->partial_bottom_cells, "pop_init: partial bottom cells are not implemented");
+  POP_REQUIRE(G.nranks == 1 || G.nccl_comm != nullptr,
+              "pop_init: nranks=%d but pop_comm_init was not called", G.nranks);
+  G.ny_local = G.nyg / G.nranks;
+  POP_REQUIRE(G.ny_local >= 2 * POP_NGHOST, "pop_init: strip of %d rows is thinner than the halo",
+              G.ny_local);
+  G.j0 = G.rank * G.ny_local + 1;
+  G.nxb = G.nxg + 2 * POP_NGHOST;
+  G.nyb = G.ny_local + 2 * POP_NGHOST;
+  G.ib = POP_NGHOST + 1;
+  G.ie = G.nxb - POP_NGHOST;
+  G.jb = POP_NGHOST + 1;
+  G.je = G.nyb - POP_NGHOST;
+  G.n2 = (size_t)G.nxb * G.nyb;
+  G.n3 = G.n2 * G.km;
+  // i_glob / j_glob: source/blocks.F90:166-268 for one block spanning the strip
+  G.i_glob.assign(G.nxb, 0);
+  G.j_glob.assign(G.nyb, 0);
+  for (int i = 1; i <= G.nxb; i++) {
+    int v = i - POP_NGHOST;
+    if (v < 1) v = (cfg->ew_boundary_type == POP_BNDY_CYCLIC) ? v + G.nxg : 0;
+    else if (v > G.nxg) v = (cfg->ew_boundary_type == POP_BNDY_CYCLIC) ? v - G.nxg : 0;
+    G.i_glob[i - 1] = v;
+  }
+  for (int j = 1; j <= G.nyb; j++) {
+    int v = G.j0 - POP_NGHOST + j - 1;
+    if (v < 1) v = (cfg->ns_boundary_type == POP_BNDY_CYCLIC) ? v + G.nyg : 0;
+    else if (v > G.nyg) {
+      if (cfg->ns_boundary_type == POP_BNDY_CYCLIC) v -= G.nyg;
+      else if (cfg->ns_boundary_type == POP_BNDY_TRIPOLE) v = -v;
+      else v = 0;
+    }
+    G.j_glob[j - 1] = v;
+  }
+  cudaDeviceProp prop;
+  POP_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  G.sm_count = prop.multiProcessorCount;
+  if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  G.oldtime = 0;
+  G.curtime = 1;
+  G.newtime = 2;
+  G.mixtime = 0;
+  G.use_upwind3 = G.use_centered = false;
+  for (int n = 0; n < G.nt; n++) {
+    if (cfg->tadvect_itype[n] == POP_TADVECT_UPWIND3) G.use_upwind3 = true;
+    else if (cfg->tadvect_itype[n] == POP_TADVECT_CENTERED) G.use_centered = true;
+    else POP_REQUIRE(false, "pop_init: tadvect_itype[%d]=%d not supported", n, cfg->tadvect_itype[n]);
+  }
+  POP_REQUIRE(cfg->hmix_tracer_itype == POP_HMIX_DEL2 || cfg->hmix_tracer_itype == POP_HMIX_DEL4,
+              "pop_init: hmix_tracer_itype=%d not supported (del2, del4)", cfg->hmix_tracer_itype);
+  POP_REQUIRE(cfg->hmix_momentum_itype == POP_HMIX_DEL2 || cfg->hmix_momentum_itype == POP_HMIX_DEL4,
+              "pop_init: hmix_momentum_itype=%d not supported", cfg->hmix_momentum_itype);
+  POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH, "pop_init: vmix 'rich' is not implemented");
+  POP_TRY(alloc_all_fields());
+  POP_TRY(reduce_alloc());
+  // time constants: time_management.F90:962-964,434-439
+  G.dtt = G.dtu = G.dtp = cfg->dtt;
+  G.alpha = 1.0 / 3.0;
+  G.theta = 0.5;
+  G.gamma = 1.0 - 2.0 * G.alpha;
+  memset(&G.vc, 0, sizeof(G.vc));
+  G.launches = 0;
+  G.timers.clear();
+  G.grid_set = false;
+  G.initialized = true;
+  return POP_SUCCESS;
+}
+
+extern "C" int pop_finalize(void) {
+  if (G.stream) cudaStreamSynchronize(G.stream);
+  for (auto& kv : G.fields) cudaFree(kv.second.p);
+  G.fields.clear();
+  for (auto& kv : G.stage) cudaFree(kv.second.first);
+  G.stage.clear();
+  cudaFree(G.d_partials);
+  cudaFree(G.d_sums);
+  cudaFree(G.d_gather);
+  if (G.h_sums) cudaFreeHost(G.h_sums);
+  G.d_partials = G.d_sums = G.d_gather = nullptr;
+  G.h_sums = nullptr;
+  cudaFree(G.d_sendS);
+  cudaFree(G.d_sendN);
+  cudaFree(G.d_recvS);
+  cudaFree(G.d_recvN);
+  G.d_sendS = G.d_sendN = G.d_recvS = G.d_recvN = nullptr;
+  G.halo_buf_elems = 0;
+  G.initialized = false;
+  G.grid_set = false;
+  return POP_SUCCESS;
+}
+
+extern "C" int pop_get_block(pop_block* blk) {
+  POP_REQUIRE(G.initialized, "pop_get_block: not initialized");
+  blk->block_id = G.rank + 1;
+  blk->local_id = 1;
+  blk->ib = G.ib;
+  blk->ie = G.ie;
+  blk->jb = G.jb;
+  blk->je = G.je;
+  blk->iblock = 1;
+  blk->jblock = G.rank + 1;
+  blk->i_glob = G.i_glob.data();
+  blk->j_glob = G.j_glob.data();
+  return POP_SUCCESS;
+}
+
+extern "C" int pop_local_shape(int* nx_block, int* ny_block, int* j_start_global, int* ny_local) {
+  POP_REQUIRE(G.initialized, "pop_local_shape: not initialized");
+  if (nx_block) *nx_block = G.nxb;
+  if (ny_block) *ny_block = G.nyb;
+  if (j_start_global) *j_start_global = G.j0;
+  if (ny_local) *ny_local = G.ny_local;
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ time step scalars
+int upload_vert_const() {
+  POP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_vc, &G.vc, sizeof(VertConst), 0, cudaMemcpyHostToDevice,
+                                         G.stream));
+  // the host copy may be modified right after this call: make the copy complete first
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  return POP_SUCCESS;
+}
+
+// step_mod.F90:302-320
+int set_timestep(int ts_type) {
+  POP_REQUIRE(G.grid_set, "pop_set_timestep: grid not set");
+  bool leap = (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_AVG);
+  bool changed = (leap != G.leapfrogts) || G.vc.c2dtt[1] == 0.0;
+  G.leapfrogts = leap;
+  G.f_euler_ts = (ts_type == POP_TS_EULER);
+  G.avg_ts = (ts_type == POP_TS_AVG);
+  if (leap) {
+    G.mixtime = G.oldtime;
+    G.beta = G.alpha;
+    for (int k = 1; k <= G.km; k++) G.vc.c2dtt[k] = 2.0 * G.dtt;
+    G.c2dtu = 2.0 * G.dtu;
+    G.c2dtp = 2.0 * G.dtp;
+  } else {
+    G.mixtime = G.curtime;
+    G.beta = G.theta;
+    for (int k = 1; k <= G.km; k++) G.vc.c2dtt[k] = G.dtt;
+    G.c2dtu = G.dtu;
+    G.c2dtp = G.dtp;
+  }
+  if (changed) POP_TRY(upload_vert_const());
+  return POP_SUCCESS;
+}
+
+extern "C" int pop_set_timestep(int ts_type) {
+  POP_REQUIRE(G.initialized, "pop_set_timestep: not initialized");
+  return set_timestep(ts_type);
+}
+
+GridView grid_view() {
+  GridView g;
+  memset(&g, 0, sizeof(g));
+  g.nxb = G.nxb; g.nyb = G.nyb; g.km = G.km; g.nt = G.nt;
+  g.ib = G.ib; g.ie = G.ie; g.jb = G.jb; g.je = G.je;
+  g.n2 = G.n2; g.n3 = G.n3;
+  g.KMT = fldi("KMT"); g.KMU = fldi("KMU");
+#define GV(n) g.n = fld(#n)
+  GV(DXU); GV(DYU); GV(DXUR); GV(DYUR); GV(UAREA_R); GV(TAREA_R); GV(TAREA); GV(HUR); GV(HU);
+  GV(FCOR); GV(KXU); GV(KYU); GV(DTN); GV(DTS); GV(DTE); GV(DTW); GV(AHF);
+  GV(DUC); GV(DUN); GV(DUS); GV(DUE); GV(DUW); GV(DMC); GV(DMN); GV(DMS); GV(DME); GV(DMW);
+  GV(DUM); GV(AMF); GV(AU0); GV(AUN); GV(AUE); GV(AUNE); GV(RCALCT); GV(RCALCU);
+  GV(TALFXP); GV(TBETXP); GV(TGAMXP); GV(TALFYP); GV(TBETYP); GV(TGAMYP);
+  GV(TALFXM); GV(TBETXM); GV(TDELXM); GV(TALFYM); GV(TBETYM); GV(TDELYM);
+  GV(VDC); GV(VVC);
+#undef GV
+  g.vdc_nk = G.vdc_nk; g.vdc_k0 = G.vdc_k0; g.vdc_nd = G.vdc_nd; g.vvc_nk = G.vvc_nk;
+  return g;
+}
+
+// ------------------------------------------------------------------ instrumentation
+extern "C" long pop_kernel_launch_count(void) { return G.launches; }
+extern "C" int pop_timer_get(const char* name, double* ms, long* calls) {
+  auto it = G.timers.find(name);
+  if (it == G.timers.end()) {
+    if (ms) *ms = 0.0;
+    if (calls) *calls = 0;
+    return POP_FAIL;
+  }
+  if (ms) *ms = it->second.ms;
+  if (calls) *calls = it->second.calls;
+  return POP_SUCCESS;
+}
+extern "C" int pop_timers_reset(void) {
+  G.timers.clear();
+  return POP_SUCCESS;
+}
+extern "C" int pop_timers_enable(int on) {
+  G.timers_on = on != 0;
+  return POP_SUCCESS;
+}
+extern "C" int pop_sync(void) {
+  POP_REQUIRE(G.stream != nullptr, "pop_sync: not initialized");
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  return POP_SUCCESS;
+}
+extern "C" void* pop_stream(void) { return (void*)G.stream; }

@@ -1,0 +1,226 @@
+// pop_ctx.h -- library context of the B200-native POP2 hot path (one process / one block per GPU).
+//
+// Data layout in HBM: exactly the reference's block layout (source/prognostic.F90:38-61): every
+// array is (nx_block, ny_block [,km [,nt]]) with i fastest and a 2-cell ghost ring
+// (source/blocks.F90:51-56); one block per rank = a 1 x P strip in j, so
+// nx_block = nx_global+4 and ny_block = ny_global/P+4.  Three time levels are separate
+// allocations addressed through rotating indices (step_mod.F90:827-830: zero bytes moved).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/pop_b200.h"
+
+#define POP_NGHOST 2
+#define POP_KMAX 128  // capacity of the per-level constant tables
+
+// physical constants: standalone (non-CCSMCOUPLED) values, source/pop_constants.F90:235-241
+#define POP_GRAV 980.6
+#define POP_OMEGA 7.292123625e-5
+#define POP_RADIUS 6370.0e5
+#define POP_PI 3.14159265358979323846
+
+// per-level tables, uploaded to __constant__ memory (uniform index across a warp)
+struct VertConst {
+  double dz[POP_KMAX + 2], dzw[POP_KMAX + 2], dzr[POP_KMAX + 2], dz2r[POP_KMAX + 2];
+  double dzwr[POP_KMAX + 2], c2dz[POP_KMAX + 2], zt[POP_KMAX + 2], zw[POP_KMAX + 2];
+  double c2dtt[POP_KMAX + 2], afac_t[POP_KMAX + 2], afac_u[POP_KMAX + 2];
+  double pressz[POP_KMAX + 2], tmin[POP_KMAX + 2], tmax[POP_KMAX + 2], smin[POP_KMAX + 2];
+  double smax[POP_KMAX + 2], bouss[POP_KMAX + 2];
+  double talfzp[POP_KMAX + 2], tbetzp[POP_KMAX + 2], tgamzp[POP_KMAX + 2];
+  double talfzm[POP_KMAX + 2], tbetzm[POP_KMAX + 2], tdelzm[POP_KMAX + 2];
+};
+
+struct DevField {
+  void* p = nullptr;
+  size_t elems = 0;  // number of elements of the padded local array
+  int nz = 1;        // product of the trailing dims (km, nt*km, ...)
+  bool is_int = false;
+};
+
+struct Timer {
+  double ms = 0.0;
+  long calls = 0;
+};
+
+struct Ctx {
+  pop_config cfg;
+  bool initialized = false, grid_set = false;
+  int nxg = 0, nyg = 0, km = 0, nt = 0;
+  int rank = 0, nranks = 1;
+  int ny_local = 0, j0 = 1;  // physical rows of this strip: global rows j0 .. j0+ny_local-1
+  int nxb = 0, nyb = 0, ib = 3, ie = 0, jb = 3, je = 0;  // 1-based like the reference
+  size_t n2 = 0, n3 = 0;
+  std::vector<int> i_glob, j_glob;
+  cudaStream_t stream = nullptr;
+  std::map<std::string, DevField> fields;
+  VertConst vc;  // host copy
+  // rotating time indices (prognostic.F90:63-68)
+  int oldtime = 0, curtime = 1, newtime = 2, mixtime = 0;
+  // time-step scalars (step_mod.F90:302-320, time_management.F90:434-439)
+  double dtt = 0, dtu = 0, dtp = 0, c2dtu = 0, c2dtp = 0, beta = 0;
+  double alpha = 1.0 / 3.0, theta = 0.5, gamma = 1.0 - 2.0 * (1.0 / 3.0);
+  bool leapfrogts = true, f_euler_ts = false, avg_ts = false;
+  // hmix / misc scalars
+  double ah = 0, am = 0, uarea_equator = 0;
+  int vdc_nk = 0, vdc_k0 = 1, vdc_nd = 1, vvc_nk = 0;
+  bool use_upwind3 = false, use_centered = false;
+  // solver
+  double residualNorm = 0, convergenceCriterion = 0, rmsResidual = 0;
+  int numIterations = 0;
+  double pcsiMaxEigs = 0, pcsiMinEigs = 0;
+  int lanczosSteps = 0;
+  double rcheck = 0, rconst = 0;
+  // reduction scratch (pop_reduce.cu)
+  double* d_partials = nullptr;  // [max_red_blocks][nfields<=4][2] double-double partials
+  double* d_sums = nullptr;      // device results: [16] doubles (hi parts rounded) + dd pairs
+  double* h_sums = nullptr;      // pinned mirror
+  double* d_gather = nullptr;    // [nranks][8] all-gathered dd pairs (multi-rank)
+  int max_red_blocks = 0;
+  // halo message buffers (multi-rank): rows to/from the south and north neighbours
+  double* d_sendS = nullptr;
+  double* d_sendN = nullptr;
+  double* d_recvS = nullptr;
+  double* d_recvN = nullptr;
+  size_t halo_buf_elems = 0;
+  void* nccl_comm = nullptr;
+  // staging buffers for host-pointer arguments of the slab API
+  std::map<std::string, std::pair<void*, size_t>> stage;
+  // instrumentation
+  long launches = 0;
+  bool timers_on = false;
+  std::map<std::string, Timer> timers;
+  int sm_count = 148;
+};
+
+extern Ctx G;
+
+// ---- error handling (POP_ErrorMod.F90:45-47 convention) ----
+void pop_set_error(const char* fmt, ...);
+#define POP_CHECK_CUDA(call)                                                                 \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      pop_set_error("%s:%d CUDA error %s in %s", __FILE__, __LINE__, cudaGetErrorString(e_), \
+                    #call);                                                                  \
+      return POP_FAIL;                                                                       \
+    }                                                                                        \
+  } while (0)
+#define POP_REQUIRE(cond, ...)    \
+  do {                            \
+    if (!(cond)) {                \
+      pop_set_error(__VA_ARGS__); \
+      return POP_FAIL;            \
+    }                             \
+  } while (0)
+#define POP_TRY(call)                   \
+  do {                                  \
+    int rc_ = (call);                   \
+    if (rc_ != POP_SUCCESS) return rc_; \
+  } while (0)
+
+// ---- field registry ----
+double* fld(const char* name);                  // device pointer (double field), nullptr if absent
+int* fldi(const char* name);                    // device pointer (int field)
+double* fld_t(const char* base, int storage);   // prognostic field at storage index 0..2
+int alloc_field(const char* name, int nz, bool is_int);
+bool resolve_name(const char* name, int tlev, std::string* out);
+
+// launch bookkeeping: every kernel launch of this library goes through POP_LAUNCH
+#define POP_LAUNCH(kernel, grid, block, smem, ...)                    \
+  do {                                                                \
+    kernel<<<(grid), (block), (smem), G.stream>>>(__VA_ARGS__);       \
+    G.launches++;                                                     \
+  } while (0)
+int pop_post_launch(const char* what);  // cudaGetLastError -> POP error
+
+// scoped CUDA-event timer with the reference timer names (timers.F90)
+struct ScopedTimer {
+  const char* name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool on;
+  explicit ScopedTimer(const char* n);
+  ~ScopedTimer();
+};
+
+// device-side view of everything a kernel needs (passed by value as a kernel parameter)
+struct GridView {
+  int nxb, nyb, km, nt, ib, ie, jb, je;  // ib..je 1-based
+  size_t n2, n3;
+  const int *KMT, *KMU;
+  const double *DXU, *DYU, *DXUR, *DYUR, *UAREA_R, *TAREA_R, *TAREA, *HUR, *HU, *FCOR, *KXU, *KYU;
+  const double *DTN, *DTS, *DTE, *DTW, *AHF;
+  const double *DUC, *DUN, *DUS, *DUE, *DUW, *DMC, *DMN, *DMS, *DME, *DMW, *DUM, *AMF;
+  const double *AU0, *AUN, *AUE, *AUNE, *RCALCT, *RCALCU;
+  const double *TALFXP, *TBETXP, *TGAMXP, *TALFYP, *TBETYP, *TGAMYP;
+  const double *TALFXM, *TBETXM, *TDELXM, *TALFYM, *TBETYM, *TDELYM;
+  const double *VDC, *VVC;
+  int vdc_nk, vdc_k0, vdc_nd, vvc_nk;
+};
+GridView grid_view();
+
+// ---- internal entry points implemented across the .cu files ----
+int upload_vert_const();
+int set_timestep(int ts_type);
+// halo (pop_halo.cu)
+int halo_update(double* a, int nz, int loc, int kind, double fill);
+int halo_update_i4(int* a, int nz, int loc, int kind, int fill);
+int comm_init(int rank, int nranks, const char* id128);
+int comm_unique_id(char* id128);
+int comm_finalize();
+// reductions (pop_reduce.cu): masked physical-domain sums of nfields 2-d fields, accumulated in
+// double-double; results (rounded to double) land in out_host[nfields] when out_host != nullptr
+// and always in G.d_sums[0..nfields-1] on the device (stream ordered).
+int global_sum_dev(const double* a, int nfields, size_t field_stride, int loc, const double* mask,
+                   double* out_host);
+int reduce_alloc();
+// state (pop_state.cu)
+int state_slab(int k, int kk, const double* T, const double* S, double* RHOOUT, double* RHOFULL,
+               double* DRHODT, double* DRHODS, size_t n);
+int state_3d(const double* TRACER, double* RHO);
+// tracer path (pop_tracer.cu)
+enum { TR_FULL = 0, TR_ADVT = 1, TR_HDIFFT = 2, TR_VDIFFT = 3 };
+struct TracerIO {
+  const double *TCUR, *TMIX, *TOLD, *UCUR, *VCUR, *STF, *TFW, *DH, *POLD, *PCUR;
+  double* TNEW;  // FULL: (nxb,nyb,km,nt); slab modes: OUT(nxb,nyb,nt)
+  double* WTK;   // slab modes: carried vertical velocity (in/out); FULL: unused
+};
+int tracer_column(int mode, int k, const TracerIO& io);
+int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const double* RHS,
+                 int nfirst, int nlast, int correct);
+int impvmixu_dev(double* UNEW, double* VNEW);
+int vmix_coeffs_dev(int k0, int k1, const double* TMIX, const double* UMIX, const double* VMIX,
+                    const double* RHOMIX);
+// momentum path (pop_momentum.cu)
+enum { MO_FULL = 0, MO_ADVU = 1, MO_HDIFFU = 2, MO_GRADP = 3, MO_VDIFFU = 4 };
+struct MomentumIO {
+  const double *UCUR, *VCUR, *UOLD, *VOLD, *UMIX, *VMIX, *RHOOLD, *RHOCUR, *RHONEW, *SMF, *DHU;
+  double *UNEW, *VNEW, *ZX, *ZY;  // FULL outputs; slab modes: UNEW/VNEW = OUT1/OUT2 (nxb,nyb)
+  double* WUK;                    // slab modes: carried (in/out)
+};
+int momentum_column(int mode, int k, const MomentumIO& io);
+int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD);
+int grad_dev(int k, double* GX, double* GY, const double* F);
+int div_dev(int k, double* D, const double* UX, const double* UY);
+// barotropic + solver (pop_barotropic.cu)
+int solvers_init_dev();
+int solvers_prep_dev();
+int solvers_diagonal_dev(const double* diagCorr);
+int solvers_run_dev(double* X, const double* B);
+int btrop_operator_dev(double* AX, const double* X);
+int init_barotropic_dev();
+int barotropic_driver_dev();
+// drivers (pop_step.cu)
+int dhdt_dev();
+int baroclinic_driver_dev();
+int baroclinic_correct_adjust_dev();
+int step_dev(int ts_type);
+// grid (pop_grid.cu)
+int set_grid_host(const double* ULAT, const double* HTN, const double* HTE, const double* HUS,
+                  const double* HUW, const double* DXU, const double* DYU, const double* DXT,
+                  const double* DYT, const int* KMT, const double* dz);
+// staging of host pointers (pop_abi.cu)
+bool is_device_ptr(const void* p);
