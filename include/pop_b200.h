@@ -134,6 +134,9 @@ int pop_get_field(const char* name, int tlev, void* host);
 /* scatter/gather this rank's physical strip (nx_global x ny_local [x nz]) */
 int pop_scatter_field(const char* name, int tlev, const void* host_strip);
 int pop_gather_field(const char* name, int tlev, void* host_strip);
+/* levels z0 .. z0+nz-1 only (0-based; level index runs over km, or n*km+k for TRACER); `strip` may be
+   a host or a device pointer */
+int pop_scatter_field_levels(const char* name, int tlev, int z0, int nz, const void* strip);
 
 /* ---- time-step scalars (a29): step_mod.F90:302-320 ---- */
 int pop_set_timestep(int ts_type);

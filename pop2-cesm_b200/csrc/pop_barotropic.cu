@@ -1,0 +1,607 @@
+// pop_barotropic.cu -- barotropic driver and the elliptic solver.
+//
+//   POP_SolversMod.F90: btropOperator :2376-2431; pcg :1200-1503; PCSI :1510-1835; ChronGear
+//   :1841-2266; PcsiLanczos :2699-2990 + ratqr :3122-3222; POP_SolversDiagonal :1110-1151;
+//   POP_SolversRun :327-495 (clinic == tropic distribution, so POP_RedistributeBlocks is a copy).
+//   barotropic.F90: init_barotropic :170-252 (pop_grid.cu), barotropic_driver :267-735.
+//
+// Every iteration is a fixed sequence of fused stencil-plus-update kernels; dot products are written
+// as per-CTA double-double partials by the kernel that produces the operands and finished by
+// reduce_finish() (block order, then rank order).  The ChronGear / PCG recurrence scalars live on
+// the device (SolverScalars), so an iteration needs no host round trip; the host reads the residual
+// norm only on the convergence checks every `convergenceCheckFreq` iterations, as the reference.
+#include <cmath>
+#include <vector>
+#include "pop_dev.cuh"
+
+struct BtView {
+  int nxb, nyb, ib, jb, nxp, nyp;  // ib,jb 1-based; physical extent nxp x nyp
+  const double *C, *N, *E, *NE, *mask;
+};
+static BtView bt_view() {
+  BtView v;
+  v.nxb = G.nxb; v.nyb = G.nyb; v.ib = G.ib; v.jb = G.jb;
+  v.nxp = G.ie - G.ib + 1; v.nyp = G.je - G.jb + 1;
+  v.C = fld("btropWgtCenter"); v.N = fld("btropWgtNorth"); v.E = fld("btropWgtEast");
+  v.NE = fld("btropWgtNE"); v.mask = fld("mMaskTropic");
+  return v;
+}
+
+// 9-point operator at array point q=(i,j) (0-based); zero outside 1..nxb-2 x 1..nyb-2
+__device__ __forceinline__ double btrop_point(const BtView& v, const double* __restrict__ X, int i, int j) {
+  if (i < 1 || i > v.nxb - 2 || j < 1 || j > v.nyb - 2) return 0.0;
+  const int nxb = v.nxb;
+  const size_t q = (size_t)j * nxb + i;
+  return v.C[q] * X[q] + v.N[q] * X[q + nxb] + v.N[q - nxb] * X[q - nxb] + v.E[q] * X[q + 1] +
+         v.E[q - 1] * X[q - 1] + v.NE[q] * X[q + nxb + 1] + v.NE[q - nxb] * X[q - nxb + 1] +
+         v.NE[q - 1] * X[q + nxb - 1] + v.NE[q - nxb - 1] * X[q - nxb - 1];
+}
+__device__ __forceinline__ bool bt_physical(const BtView& v, int i, int j) {
+  return i >= v.ib - 1 && i < v.ib - 1 + v.nxp && j >= v.jb - 1 && j < v.jb - 1 + v.nyp;
+}
+__device__ __forceinline__ void bt_store_partials(dd* acc, int nf, double* partials, int red_blocks) {
+  for (int f = 0; f < nf; f++) {
+    dd r = block_reduce_dd(acc[f]);
+    if (threadIdx.x == 0) {
+      partials[((size_t)f * red_blocks + blockIdx.x) * 2] = r.hi;
+      partials[((size_t)f * red_blocks + blockIdx.x) * 2 + 1] = r.lo;
+    }
+  }
+}
+
+// Generic fused solver kernel: grid-stride over all points of the padded block, fixed grid
+// (red_blocks CTAs) so that the partial sums are reproducible.
+enum {
+  BT_APPLY = 0,     // V0 = A V1
+  BT_RESID,         // V0 = V2 - A V1                                    [sum0 = V0^2]
+  BT_RESID_A0R,     // r = V2 - A V1 ; sum0 += r^2 ; V0 = r * V3(A0R)
+  BT_CG_ZS,         // Z(V0) = R(V1)*A0R(V2) ; S(V3) = Z
+  BT_CG_QSUM,       // Q(V0) = A S(V1) ; sums: R(V2)*Z(V3), S*Q
+  BT_CG_AZSUM,      // AZ(V0) = A Z(V1) ; sums: R(V2)*Z, AZ*Z
+  BT_PCG_AS,        // Q(V0) = A S(V1) ; sum: Q*S
+  BT_LZ_AP          // R(V0) = A P(V1) - s0*Q1(V2) ; sum: P*R
+};
+template <int OP>
+__global__ void __launch_bounds__(POP_EW_THREADS)
+bt_stencil_kernel(BtView v, double* __restrict__ V0, const double* __restrict__ V1,
+                  const double* __restrict__ V2, double* __restrict__ V3, double s0, int want_sums,
+                  double* __restrict__ partials, int red_blocks) {
+  dd acc[2] = {dd{0.0, 0.0}, dd{0.0, 0.0}};
+  const size_t n = (size_t)v.nxb * v.nyb;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q % v.nxb), j = (int)(q / v.nxb);
+    const bool phys = bt_physical(v, i, j);
+    const double m = phys ? v.mask[q] : 0.0;
+    if (OP == BT_APPLY) {
+      V0[q] = btrop_point(v, V1, i, j);
+    } else if (OP == BT_RESID) {
+      const double r = V2[q] - btrop_point(v, V1, i, j);
+      V0[q] = r;
+      if (want_sums && phys) acc[0] = dd_add_d(acc[0], (r * r) * m);
+    } else if (OP == BT_RESID_A0R) {
+      const double r = V2[q] - btrop_point(v, V1, i, j);
+      if (want_sums && phys) acc[0] = dd_add_d(acc[0], (r * r) * m);
+      V0[q] = r * V3[q];
+    } else if (OP == BT_CG_ZS) {
+      const double z = V1[q] * V2[q];
+      V0[q] = z;
+      V3[q] = z;
+    } else if (OP == BT_CG_QSUM) {
+      const double qv = btrop_point(v, V1, i, j);
+      V0[q] = qv;
+      if (phys) {
+        acc[0] = dd_add_d(acc[0], (V2[q] * V3[q]) * m);
+        acc[1] = dd_add_d(acc[1], (V1[q] * qv) * m);
+      }
+    } else if (OP == BT_CG_AZSUM) {
+      const double az = btrop_point(v, V1, i, j);
+      V0[q] = az;
+      if (phys) {
+        acc[0] = dd_add_d(acc[0], (V2[q] * V1[q]) * m);
+        acc[1] = dd_add_d(acc[1], (az * V1[q]) * m);
+      }
+    } else if (OP == BT_PCG_AS) {
+      const double qv = btrop_point(v, V1, i, j);
+      V0[q] = qv;
+      if (phys) acc[0] = dd_add_d(acc[0], (qv * V1[q]) * m);
+    } else if (OP == BT_LZ_AP) {
+      const double r = btrop_point(v, V1, i, j) - s0 * V2[q];
+      V0[q] = r;
+      if (phys) acc[0] = dd_add_d(acc[0], (V1[q] * r) * m);
+    }
+  }
+  if (OP == BT_CG_QSUM || OP == BT_CG_AZSUM) bt_store_partials(acc, 2, partials, red_blocks);
+  else if (OP == BT_PCG_AS || OP == BT_LZ_AP || ((OP == BT_RESID || OP == BT_RESID_A0R) && want_sums))
+    bt_store_partials(acc, 1, partials, red_blocks);
+}
+
+// element-wise updates (all points of the padded block, like the reference's whole-array statements)
+enum {
+  EW_A0R = 0,     // V0 = C != 0 ? 1/C : 0
+  EW_CG_UPDATE0,  // X += alpha*S ; R -= alpha*Q
+  EW_CG_UPDATE,   // S = Z + beta*S ; Q = AZ + beta*Q ; X += alpha*S ; R -= alpha*Q ; [Z = R*A0R]
+  EW_MUL,         // V0 = V1 * V2
+  EW_PCSI_INIT,   // R = R*A0R ; Q = (1/csy)*R
+  EW_PCSI_QX,     // Q = om*R + (csy*om-1)*Q ; X += Q
+  EW_ADD,         // V0 = V0 + V1
+  EW_PCG_W1,      // W1(V0) = C!=0 ? R/C : 0 ; sum R*W1
+  EW_PCG_S,       // S = W1 + S*(eta1/eta0)
+  EW_PCG_UPDATE,  // X += eta1*S ; R -= eta1*Q
+  EW_LZ_SR,       // S(V0) = R(V1)*A0R(V2) ; sum S*R
+  EW_SCALE,       // V0 = s0 * V1
+  EW_AXPY,        // V0 = V0 - s0*V1
+  EW_SET,         // V0 = s0
+  EW_LZ_SHIFT     // Q1(V0) = Q(V1) ; Q(V1) = s0*R(V2)
+};
+struct EwArgs {
+  double *V0, *V1, *V2, *V3, *V4, *V5, *V6;
+  double s0, s1;
+  int flag;
+};
+template <int OP>
+__global__ void __launch_bounds__(POP_EW_THREADS)
+bt_ew_kernel(BtView v, EwArgs a, const SolverScalars* __restrict__ sc, double* __restrict__ partials,
+             int red_blocks) {
+  dd acc[1] = {dd{0.0, 0.0}};
+  const size_t n = (size_t)v.nxb * v.nyb;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (size_t)gridDim.x * blockDim.x) {
+    if (OP == EW_A0R) {
+      const double c = a.V1[q];
+      a.V0[q] = (c != 0.0) ? 1.0 / c : 0.0;
+    } else if (OP == EW_CG_UPDATE0) {  // V0=X V1=R V2=S V3=Q
+      const double al = sc->cgAlpha;
+      a.V0[q] = a.V0[q] + al * a.V2[q];
+      a.V1[q] = a.V1[q] - al * a.V3[q];
+    } else if (OP == EW_CG_UPDATE) {  // V0=X V1=R V2=S V3=Q V4=Z V5=AZ V6=A0R
+      const double al = sc->cgAlpha, be = sc->cgBeta;
+      const double s = a.V4[q] + be * a.V2[q];
+      const double qq = a.V5[q] + be * a.V3[q];
+      a.V2[q] = s;
+      a.V3[q] = qq;
+      a.V0[q] = a.V0[q] + al * s;
+      const double r = a.V1[q] - al * qq;
+      a.V1[q] = r;
+      if (a.flag) a.V4[q] = r * a.V6[q];
+    } else if (OP == EW_MUL) {
+      a.V0[q] = a.V1[q] * a.V2[q];
+    } else if (OP == EW_PCSI_INIT) {  // V0=R V1=Q V2=A0R
+      const double r = a.V0[q] * a.V2[q];
+      a.V0[q] = r;
+      a.V1[q] = a.s0 * r;
+    } else if (OP == EW_PCSI_QX) {  // V0=Q V1=X V2=R ; s0 = csomga, s1 = csy*csomga-1
+      const double qv = a.s0 * a.V2[q] + a.s1 * a.V0[q];
+      a.V0[q] = qv;
+      a.V1[q] = a.V1[q] + qv;
+    } else if (OP == EW_ADD) {
+      a.V0[q] = a.V0[q] + a.V1[q];
+    } else if (OP == EW_PCG_W1) {  // V0=W1 V1=R V2=C
+      const double c = a.V2[q], r = a.V1[q];
+      const double w = (c != 0.0) ? r / c : 0.0;
+      a.V0[q] = w;
+      const int i = (int)(q % v.nxb), j = (int)(q / v.nxb);
+      if (bt_physical(v, i, j)) acc[0] = dd_add_d(acc[0], (r * w) * v.mask[q]);
+    } else if (OP == EW_PCG_S) {  // V0=S V1=W1
+      a.V0[q] = a.V1[q] + a.V0[q] * (sc->eta1 / sc->eta0);
+    } else if (OP == EW_PCG_UPDATE) {  // V0=X V1=R V2=S V3=Q
+      const double e = sc->eta1;
+      a.V0[q] = a.V0[q] + e * a.V2[q];
+      a.V1[q] = a.V1[q] - e * a.V3[q];
+    } else if (OP == EW_LZ_SR) {  // V0=S V1=R V2=A0R
+      const double s = a.V1[q] * a.V2[q];
+      a.V0[q] = s;
+      const int i = (int)(q % v.nxb), j = (int)(q / v.nxb);
+      if (bt_physical(v, i, j)) acc[0] = dd_add_d(acc[0], (s * a.V1[q]) * v.mask[q]);
+    } else if (OP == EW_SCALE) {
+      a.V0[q] = a.s0 * a.V1[q];
+    } else if (OP == EW_AXPY) {
+      a.V0[q] = a.V0[q] - a.s0 * a.V1[q];
+    } else if (OP == EW_SET) {
+      a.V0[q] = a.s0;
+    } else if (OP == EW_LZ_SHIFT) {
+      a.V0[q] = a.V1[q];
+      a.V1[q] = a.s0 * a.V2[q];
+    }
+  }
+  if (OP == EW_PCG_W1 || OP == EW_LZ_SR) bt_store_partials(acc, 1, partials, red_blocks);
+}
+
+#define BT_ST(OP, V0, V1, V2, V3, s0, want)                                                            \
+  do {                                                                                                 \
+    auto kf_ = bt_stencil_kernel<OP>;                                                                  \
+    POP_LAUNCH(kf_, G.red_blocks, POP_EW_THREADS, 0, bt_view(), V0, V1, V2, V3, s0, want, G.d_partials, \
+               G.red_blocks);                                                                          \
+  } while (0)
+template <int OP>
+static void bt_ew(double* V0, double* V1 = nullptr, double* V2 = nullptr, double* V3 = nullptr,
+                  double* V4 = nullptr, double* V5 = nullptr, double* V6 = nullptr, double s0 = 0.0,
+                  double s1 = 0.0, int flag = 0) {
+  EwArgs a{V0, V1, V2, V3, V4, V5, V6, s0, s1, flag};
+  auto kf = bt_ew_kernel<OP>;
+  POP_LAUNCH(kf, G.red_blocks, POP_EW_THREADS, 0, bt_view(), a, (const SolverScalars*)G.d_scal,
+             G.d_partials, G.red_blocks);
+}
+static int bt_halo(double* v) { return halo_update(v, 1, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0); }
+
+// ------------------------------------------------------------------ init / diagonal
+int solvers_init_dev() {
+  // residualNorm and convergenceCriterion: POP_SolversMod.F90:895-906
+  double* w = fld("W2A");
+  bt_ew<EW_MUL>(w, fld("TAREA"), fld("TAREA"));
+  double s = 0.0;
+  POP_TRY(global_sum_dev(w, 1, G.n2, POP_LOC_CENTER, fld("mMaskTropic"), &s));
+  G.residualNorm = 1.0 / s;
+  G.convergenceCriterion = (G.cfg.convergence_criterion * G.cfg.convergence_criterion) / G.residualNorm;
+  return POP_SUCCESS;
+}
+
+__global__ void diag_kernel(double* __restrict__ cwc, const double* __restrict__ indep,
+                            const double* __restrict__ dc, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) cwc[q] = indep[q] - dc[q];
+}
+int solvers_diagonal_dev(const double* diagCorr) {
+  POP_LAUNCH(diag_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("centerWgtClinic"),
+             fld("centerWgtClinicIndep"), diagCorr, G.n2);
+  return pop_post_launch("solvers_diagonal");
+}
+
+int btrop_operator_dev(double* AX, const double* X) {
+  BT_ST(BT_APPLY, AX, X, (const double*)nullptr, (double*)nullptr, 0.0, 0);
+  return pop_post_launch("btropOperator");
+}
+
+static int refresh_center() {  // POP_SolversRun :390-391 / POP_SolversPrep: btropWgtCenter <- centerWgtClinic
+  POP_CHECK_CUDA(cudaMemcpyAsync(fld("btropWgtCenter"), fld("centerWgtClinic"), sizeof(double) * G.n2,
+                                 cudaMemcpyDeviceToDevice, G.stream));
+  bt_ew<EW_A0R>(fld("BT_A0R"), fld("btropWgtCenter"));
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ ChronGear :1841-2266
+static int chrongear(double* X, const double* B) {
+  const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq;
+  double *R = fld("BT_R"), *S = fld("BT_S"), *Q = fld("BT_Q"), *Z = fld("BT_Z"), *AZ = fld("BT_AZ"),
+         *A0R = fld("BT_A0R");
+  double rr = 0.0;
+  G.numIterations = maxIt;
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  POP_TRY(bt_halo(R));
+  BT_ST(BT_CG_ZS, Z, R, A0R, S, 0.0, 0);
+  BT_ST(BT_CG_QSUM, Q, S, R, Z, 0.0, 1);
+  POP_TRY(bt_halo(Q));
+  POP_TRY(reduce_finish(2, RED_POST_CG_INIT, nullptr));
+  bt_ew<EW_CG_UPDATE0>(X, R, S, Q);
+  bt_ew<EW_MUL>(Z, R, A0R);
+  for (int m = 1; m <= maxIt; m++) {
+    POP_TRY(bt_halo(Z));
+    BT_ST(BT_CG_AZSUM, AZ, Z, R, (double*)nullptr, 0.0, 1);
+    POP_TRY(reduce_finish(2, RED_POST_CG_ITER, nullptr));
+    const bool check = (m % freq == 0);
+    bt_ew<EW_CG_UPDATE>(X, R, S, Q, Z, AZ, A0R, 0.0, 0.0, check ? 0 : 1);
+    if (check) {
+      BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 1);
+      POP_TRY(bt_halo(R));
+      POP_TRY(reduce_finish(1, RED_POST_RR, &rr));
+      if (rr < G.convergenceCriterion) {
+        G.numIterations = m;
+        break;
+      }
+      bt_ew<EW_MUL>(Z, R, A0R);
+    }
+  }
+  G.rmsResidual = sqrt(rr * G.residualNorm);
+  POP_TRY(pop_post_launch("ChronGear"));
+  POP_REQUIRE(!(G.numIterations == maxIt && G.convergenceCriterion != 0.0),
+              "POP_SolversRun: ChronGear solver did not converge in %d iterations (rms residual %g)",
+              maxIt, G.rmsResidual);
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ PCSI :1510-1835
+static int pcsi(double* X, const double* B) {
+  const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
+            start = G.cfg.convergence_check_start;
+  double *R = fld("BT_R"), *Q = fld("BT_Q"), *A0R = fld("BT_A0R");
+  double rr = 0.0;
+  const double csalpha = 2.0 / (G.pcsiMaxEigs - G.pcsiMinEigs);
+  const double csbeta = (G.pcsiMaxEigs + G.pcsiMinEigs) / (G.pcsiMaxEigs - G.pcsiMinEigs);
+  const double csy = csbeta / csalpha;
+  double csomga = 2.0 / csy;
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  bt_ew<EW_PCSI_INIT>(R, Q, A0R, nullptr, nullptr, nullptr, nullptr, 1.0 / csy);
+  POP_TRY(bt_halo(Q));
+  bt_ew<EW_ADD>(X, Q);
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  POP_TRY(bt_halo(R));
+  bt_ew<EW_MUL>(R, R, A0R);
+  G.numIterations = maxIt;
+  for (int m = 1; m <= maxIt; m++) {
+    csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
+    POP_TRY(bt_halo(R));  // R already holds M^-1 R
+    const bool check = (m % freq == 0) && (m >= start);
+    bt_ew<EW_PCSI_QX>(Q, X, R, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
+    BT_ST(BT_RESID_A0R, R, X, B, A0R, 0.0, check ? 1 : 0);
+    if (check) {
+      POP_TRY(reduce_finish(1, RED_POST_RR, &rr));
+      if (rr < G.convergenceCriterion) {
+        G.numIterations = m;
+        break;
+      }
+    }
+  }
+  G.rmsResidual = sqrt(rr * G.residualNorm);
+  return pop_post_launch("PCSI");  // PCSI returns silently when not converged (:1828-1830)
+}
+
+// ------------------------------------------------------------------ pcg :1200-1503
+static int pcg(double* X, const double* B) {
+  const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq;
+  double *R = fld("BT_R"), *S = fld("BT_S"), *Q = fld("BT_Q"), *W1 = fld("BT_Z");
+  double rr = 0.0;
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  bt_ew<EW_SET>(S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0);
+  POP_TRY(bt_halo(R));
+  SolverScalars sc0;
+  memset(&sc0, 0, sizeof(sc0));
+  sc0.eta0 = 1.0;
+  POP_CHECK_CUDA(cudaMemcpyAsync(G.d_scal, &sc0, sizeof(sc0), cudaMemcpyHostToDevice, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  G.numIterations = maxIt;
+  for (int m = 1; m <= maxIt; m++) {
+    bt_ew<EW_PCG_W1>(W1, R, fld("btropWgtCenter"));
+    POP_TRY(reduce_finish(1, RED_POST_PCG_ETA1, nullptr));
+    bt_ew<EW_PCG_S>(S, W1);
+    BT_ST(BT_PCG_AS, Q, S, (const double*)nullptr, (double*)nullptr, 0.0, 1);
+    POP_TRY(bt_halo(Q));
+    POP_TRY(reduce_finish(1, RED_POST_PCG_ETA2, nullptr));
+    bt_ew<EW_PCG_UPDATE>(X, R, S, Q);
+    if (m % freq == 0) {
+      BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 1);
+      POP_TRY(bt_halo(R));
+      POP_TRY(reduce_finish(1, RED_POST_RR, &rr));
+      if (rr < G.convergenceCriterion) {
+        G.numIterations = m;
+        break;
+      }
+    }
+  }
+  G.rmsResidual = sqrt(rr * G.residualNorm);
+  POP_TRY(pop_post_launch("pcg"));
+  POP_REQUIRE(!(G.numIterations == maxIt && G.convergenceCriterion != 0.0),
+              "POP_SolversRun: pcg solver did not converge in %d iterations (rms residual %g)", maxIt,
+              G.rmsResidual);
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ Lanczos :2699-2990, ratqr :3122-3222
+static int ratqr(int n, double eps1, const double* d, const double* e, double* mineig) {
+  std::vector<double> bd(n + 1, 0.0), w(n + 1, 0.0);
+  double f, ep, delta = 0.0, p, q = 0.0, qp, r, s = 0.0, tot;
+  for (int i = 1; i <= n; i++) w[i] = d[i - 1];
+  tot = w[1];
+  for (int i = 1; i <= n; i++) {
+    p = q;
+    bd[i] = e[i - 1] * e[i - 1];
+    q = 0.0;
+    if (i != n) q = fabs(e[i]);
+    const double c = w[i] - p - q;
+    tot = (c < tot) ? c : tot;
+  }
+  bd[1] = 0.0;
+  if (tot < 0.0) tot = 0.0;
+  else
+    for (int i = 1; i <= n; i++) w[i] = w[i] - tot;
+  for (;;) {
+    tot = tot + s;
+    delta = w[n] - s;
+    if (delta <= eps1) break;
+    f = bd[n] / delta;
+    qp = delta + f;
+    p = 1.0;
+    for (int ii = 1; ii <= n - 1; ii++) {
+      const int i = n - ii;
+      q = w[i] - s - f;
+      r = q / qp;
+      p = p * r + 1.0;
+      ep = f * r;
+      w[i + 1] = qp + ep;
+      delta = q - ep;
+      if (delta <= eps1) break;
+      f = bd[i] / q;
+      qp = delta + f;
+      bd[i + 1] = qp * ep;
+    }
+    if (delta <= eps1) break;
+    w[1] = qp;
+    s = qp / p;
+    if (tot + s <= tot) return 1;
+  }
+  *mineig = tot;
+  return 0;
+}
+
+static int pcsi_lanczos() {
+  const int maxstep = G.cfg.max_lanczos_step;
+  double *R = fld("BT_R"), *S = fld("BT_S"), *Q = fld("BT_Q"), *Q1 = fld("BT_Z"), *P = fld("BT_AZ"),
+         *A0R = fld("BT_A0R");
+  std::vector<double> vcsa(maxstep + 1, 0.0), vcsb(maxstep + 1, 0.0);
+  double csa, csb, csc, mineig, u = 0.0, v = 0.0, sum = 0.0;
+  bt_ew<EW_SET>(R, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0);
+  bt_ew<EW_SET>(Q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0);
+  bt_ew<EW_SET>(Q1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0);
+  bt_ew<EW_LZ_SR>(S, R, A0R);
+  POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
+  csc = -sum;
+  POP_REQUIRE(csc > 0.0, "PcsiLanczos: preconditioned operator is not negative definite (csc=%g)", csc);
+  bt_ew<EW_SCALE>(Q, R, nullptr, nullptr, nullptr, nullptr, nullptr, 1 / sqrt(csc));
+  POP_TRY(bt_halo(Q));
+  csb = 0.0;
+  mineig = 1.0;
+  G.lanczosSteps = 0;
+  for (int m = 1; m <= maxstep; m++) {
+    G.lanczosSteps = m;
+    bt_ew<EW_MUL>(P, Q, A0R);
+    POP_TRY(bt_halo(P));
+    BT_ST(BT_LZ_AP, R, P, Q1, (double*)nullptr, csb, 1);
+    POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
+    csa = -sum;
+    bt_ew<EW_AXPY>(R, Q, nullptr, nullptr, nullptr, nullptr, nullptr, csa);
+    POP_TRY(bt_halo(R));
+    bt_ew<EW_LZ_SR>(S, R, A0R);
+    POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
+    csc = -sum;
+    csb = sqrt(csc);
+    vcsa[m] = csa;
+    vcsb[m] = csb;
+    if (m == 1) u = vcsa[1] + vcsb[1];
+    else {
+      const double c = vcsa[m] + vcsb[m] + vcsb[m - 1];
+      u = (u > c) ? u : c;
+    }
+    POP_REQUIRE(csb != 0.0, "PcsiLanczos: breakdown (csb = 0) at step %d", m);
+    bt_ew<EW_LZ_SHIFT>(Q1, Q, R, nullptr, nullptr, nullptr, nullptr, 1 / csb);
+    if (m % 10 == 0 || m == maxstep) {
+      std::vector<double> mcsa(m + 1, 0.0), mcsb(m + 1, 0.0);
+      for (int i = 1; i <= m - 1; i++) { mcsa[i - 1] = vcsa[i]; mcsb[i] = vcsb[i]; }
+      mcsa[m - 1] = vcsa[m];
+      mcsb[0] = 0.0;
+      POP_REQUIRE(ratqr(m, 1.0e-8, mcsa.data(), mcsb.data(), &v) == 0, "PcsiLanczos: ratqr failed");
+      if (fabs(1 - v / mineig) < G.cfg.lanczos_convergence_criterion) break;
+      mineig = v;
+    }
+  }
+  G.pcsiMaxEigs = u;
+  G.pcsiMinEigs = v;
+  return pop_post_launch("PcsiLanczos");
+}
+
+int solvers_prep_dev() {
+  POP_TRY(refresh_center());
+  if (G.cfg.solver_choice == POP_SOLVER_PCSI) return pcsi_lanczos();
+  return POP_SUCCESS;
+}
+
+int solvers_run_dev(double* X, const double* B) {
+  ScopedTimer tm("SOLVER");
+  POP_TRY(refresh_center());
+  G.timer_suppress++;
+  int rc;
+  switch (G.cfg.solver_choice) {
+    case POP_SOLVER_PCG: rc = pcg(X, B); break;
+    case POP_SOLVER_PCSI: rc = pcsi(X, B); break;
+    default: rc = chrongear(X, B); break;
+  }
+  G.timer_suppress--;
+  return rc;
+}
+
+// ------------------------------------------------------------------ barotropic_driver :267-735
+struct BtDrv {
+  const double *ZX, *ZY, *GXc, *GXo, *GYc, *GYo, *FCOR, *HU, *UBo, *VBo, *RCALCT, *TAREA, *Pc, *FW, *PGUESS,
+      *indep;
+  const int *CHECKER, *CONSTNT;
+  double *UH, *VH, *W3, *W4, *RHS, *dc, *cwc, *Pn, *GXn, *GYn, *UBn, *VBn;
+  double c2dtp, beta, gamma, dtp, rcheck, rconst;
+  int leapfrog, impcor, sfc;
+  size_t n;
+};
+__global__ void bt_rhs1_kernel(BtDrv d) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.n) return;
+  double w3, w4;
+  if (d.leapfrog) {
+    w3 = d.c2dtp * (d.ZX[q] - d.gamma * d.GXc[q] - (1.0 - d.gamma) * d.GXo[q]);
+    w4 = d.c2dtp * (d.ZY[q] - d.gamma * d.GYc[q] - (1.0 - d.gamma) * d.GYo[q]);
+  } else {
+    w3 = d.c2dtp * (d.ZX[q] - d.GXc[q]);
+    w4 = d.c2dtp * (d.ZY[q] - d.GYc[q]);
+  }
+  double uh, vh;
+  if (d.impcor) {
+    const double w1 = d.c2dtp * d.beta * d.FCOR[q];
+    const double w2 = 1.0 / (1.0 + w1 * w1);
+    uh = w2 * (w3 + w1 * w4) + d.UBo[q];
+    vh = w2 * (w4 - w1 * w3) + d.VBo[q];
+  } else {
+    uh = w3 + d.UBo[q];
+    vh = w4 + d.VBo[q];
+  }
+  d.UH[q] = uh;
+  d.VH[q] = vh;
+  const double gx = d.leapfrog ? d.GXo[q] : d.GXc[q], gy = d.leapfrog ? d.GYo[q] : d.GYc[q];
+  d.W3[q] = d.HU[q] * (uh + d.beta * d.c2dtp * gx);
+  d.W4[q] = d.HU[q] * (vh + d.beta * d.c2dtp * gy);
+}
+__global__ void bt_rhs2_kernel(BtDrv d) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.n) return;
+  double rhs = d.RHS[q] / (d.beta * d.c2dtp);
+  double dc = 0.0;
+  if (d.sfc == POP_SFC_VARTHICK) {
+    dc = (d.RCALCT[q] != 0.0) ? d.TAREA[q] / (d.beta * d.c2dtp * d.dtp * POP_GRAV) : 0.0;
+    rhs = rhs - dc * d.Pc[q] - d.FW[q] * d.TAREA[q] / (d.beta * d.c2dtp);
+  } else if (d.sfc != POP_SFC_RIGID) {
+    dc = (d.RCALCT[q] != 0.0) ? d.TAREA[q] / (d.beta * d.c2dtp * d.dtp * POP_GRAV) : 0.0;
+    rhs = rhs - dc * d.Pc[q];
+  }
+  d.RHS[q] = rhs;
+  d.cwc[q] = d.indep[q] - dc;  // POP_SolversDiagonal
+  d.Pn[q] = d.PGUESS[q];
+}
+__global__ void bt_pcheck_kernel(double* __restrict__ out, const double* __restrict__ P,
+                                 const int* __restrict__ CHECKER, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = P[q] * CHECKER[q];
+}
+__global__ void bt_fin1_kernel(BtDrv d, const double* __restrict__ sums) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.n) return;
+  const double xcheck = sums[0];
+  d.Pn[q] = d.Pn[q] + d.CONSTNT[q] * d.rcheck * xcheck - d.CHECKER[q] * d.rconst * xcheck;
+}
+__global__ void bt_fin2_kernel(BtDrv d) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.n) return;
+  const double gxr = d.leapfrog ? d.GXo[q] : d.GXc[q], gyr = d.leapfrog ? d.GYo[q] : d.GYc[q];
+  d.UBn[q] = d.UH[q] - d.beta * d.c2dtp * (d.GXn[q] - gxr);
+  d.VBn[q] = d.VH[q] - d.beta * d.c2dtp * (d.GYn[q] - gyr);
+}
+
+int barotropic_driver_dev() {
+  ScopedTimer tm("BAROTROPIC");
+  const int o = G.oldtime, c = G.curtime, n_ = G.newtime;
+  BtDrv d;
+  memset(&d, 0, sizeof(d));
+  d.ZX = fld("ZX"); d.ZY = fld("ZY");
+  d.GXc = fld_t("GRADPX", c); d.GXo = fld_t("GRADPX", o); d.GYc = fld_t("GRADPY", c); d.GYo = fld_t("GRADPY", o);
+  d.FCOR = fld("FCOR"); d.HU = fld("HU"); d.UBo = fld_t("UBTROP", o); d.VBo = fld_t("VBTROP", o);
+  d.RCALCT = fld("RCALCT"); d.TAREA = fld("TAREA"); d.Pc = fld_t("PSURF", c); d.FW = fld("FW");
+  d.PGUESS = fld("PGUESS"); d.indep = fld("centerWgtClinicIndep");
+  d.CHECKER = fldi("CHECKER"); d.CONSTNT = fldi("CONSTNT");
+  d.UH = fld("UH_BT"); d.VH = fld("VH_BT"); d.W3 = fld("W2A"); d.W4 = fld("W2B"); d.RHS = fld("RHS_BT");
+  d.dc = fld("DIAGC"); d.cwc = fld("centerWgtClinic"); d.Pn = fld_t("PSURF", n_);
+  d.GXn = fld_t("GRADPX", n_); d.GYn = fld_t("GRADPY", n_); d.UBn = fld_t("UBTROP", n_); d.VBn = fld_t("VBTROP", n_);
+  d.c2dtp = G.c2dtp; d.beta = G.beta; d.gamma = G.gamma; d.dtp = G.dtp; d.rcheck = G.rcheck; d.rconst = G.rconst;
+  d.leapfrog = G.leapfrogts; d.impcor = G.cfg.impcor; d.sfc = G.cfg.sfc_layer_type;
+  d.n = G.n2;
+  const unsigned grid = ew_grid(G.n2);
+  POP_LAUNCH(bt_rhs1_kernel, grid, POP_EW_THREADS, 0, d);
+  POP_TRY(div_dev(1, d.RHS, d.W3, d.W4));
+  POP_LAUNCH(bt_rhs2_kernel, grid, POP_EW_THREADS, 0, d);
+  POP_TRY(halo_update(d.RHS, 1, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+  POP_TRY(solvers_run_dev(d.Pn, d.RHS));
+  if (G.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+    // remove the checkerboard null space: barotropic.F90:606-640
+    POP_LAUNCH(bt_pcheck_kernel, grid, POP_EW_THREADS, 0, d.W3, d.Pn, d.CHECKER, G.n2);
+    POP_TRY(global_sum_dev(d.W3, 1, G.n2, POP_LOC_CENTER, nullptr, nullptr));
+    POP_LAUNCH(bt_fin1_kernel, grid, POP_EW_THREADS, 0, d, (const double*)G.d_sums);
+  }
+  POP_TRY(grad_dev(1, d.GXn, d.GYn, d.Pn));
+  POP_LAUNCH(bt_fin2_kernel, grid, POP_EW_THREADS, 0, d);
+  POP_TRY(halo_update(d.Pn, 1, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+  POP_TRY(halo_update(d.GXn, 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(halo_update(d.GYn, 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  return pop_post_launch("barotropic_driver");
+}

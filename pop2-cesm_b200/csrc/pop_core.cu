@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "pop_dev.cuh"
 
 Ctx G;
@@ -32,7 +33,28 @@ int pop_post_launch(const char* what) {
 }
 
 // ------------------------------------------------------------------ timers
-ScopedTimer::ScopedTimer(const char* n) : name(n), on(G.timers_on) {
+// CUDA-event timers under the reference's timer names (timers.F90).  Events are recorded on the
+// library stream without synchronising; elapsed times are resolved lazily when a timer is read, so
+// timers can stay enabled inside a timed region.
+struct PendingTimer {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::vector<PendingTimer> g_pending;
+static void resolve_timers() {
+  for (auto& t : g_pending) {
+    cudaEventSynchronize(t.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.e0, t.e1);
+    Timer& tm = G.timers[t.name];
+    tm.ms += ms;
+    tm.calls++;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_pending.clear();
+}
+ScopedTimer::ScopedTimer(const char* n) : name(n), on(G.timers_on && G.timer_suppress == 0) {
   if (!on) return;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -41,14 +63,8 @@ ScopedTimer::ScopedTimer(const char* n) : name(n), on(G.timers_on) {
 ScopedTimer::~ScopedTimer() {
   if (!on) return;
   cudaEventRecord(e1, G.stream);
-  cudaEventSynchronize(e1);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  Timer& t = G.timers[name];
-  t.ms += ms;
-  t.calls++;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  g_pending.push_back(PendingTimer{name, e0, e1});
+  if (g_pending.size() > 4096) resolve_timers();
 }
 
 // ------------------------------------------------------------------ registry
@@ -249,6 +265,12 @@ extern "C" int pop_init(const pop_config* cfg) {
   POP_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   G.sm_count = prop.multiProcessorCount;
   if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  POP_REQUIRE(cfg->ns_boundary_type != POP_BNDY_TRIPOLE || cfg->ew_boundary_type == POP_BNDY_CYCLIC,
+              "pop_init: a tripole grid needs a cyclic east-west boundary");
+  POP_CHECK_CUDA(cudaMalloc(&G.d_iglob, sizeof(int) * G.nxb));
+  POP_CHECK_CUDA(cudaMalloc(&G.d_jglob, sizeof(int) * G.nyb));
+  POP_CHECK_CUDA(cudaMemcpy(G.d_iglob, G.i_glob.data(), sizeof(int) * G.nxb, cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(G.d_jglob, G.j_glob.data(), sizeof(int) * G.nyb, cudaMemcpyHostToDevice));
   G.oldtime = 0;
   G.curtime = 1;
   G.newtime = 2;
@@ -263,7 +285,8 @@ extern "C" int pop_init(const pop_config* cfg) {
               "pop_init: hmix_tracer_itype=%d not supported (del2, del4)", cfg->hmix_tracer_itype);
   POP_REQUIRE(cfg->hmix_momentum_itype == POP_HMIX_DEL2 || cfg->hmix_momentum_itype == POP_HMIX_DEL4,
               "pop_init: hmix_momentum_itype=%d not supported", cfg->hmix_momentum_itype);
-  POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH, "pop_init: vmix 'rich' is not implemented");
+  POP_REQUIRE(cfg->vmix_itype == POP_VMIX_CONST || cfg->vmix_itype == POP_VMIX_GIVEN,
+              "pop_init: vmix_itype=%d is not implemented (const, given)", cfg->vmix_itype);
   POP_TRY(alloc_all_fields());
   POP_TRY(reduce_alloc());
   // time constants: time_management.F90:962-964,434-439
@@ -288,8 +311,16 @@ extern "C" int pop_finalize(void) {
   cudaFree(G.d_partials);
   cudaFree(G.d_sums);
   cudaFree(G.d_gather);
+  cudaFree(G.d_local);
+  cudaFree(G.d_scal);
+  cudaFree(G.d_tripole);
+  cudaFree(G.d_iglob);
+  cudaFree(G.d_jglob);
   if (G.h_sums) cudaFreeHost(G.h_sums);
-  G.d_partials = G.d_sums = G.d_gather = nullptr;
+  G.d_partials = G.d_sums = G.d_gather = G.d_local = G.d_tripole = nullptr;
+  G.d_scal = nullptr;
+  G.d_iglob = G.d_jglob = nullptr;
+  G.tripole_elems = 0;
   G.h_sums = nullptr;
   cudaFree(G.d_sendS);
   cudaFree(G.d_sendN);
@@ -388,6 +419,7 @@ GridView grid_view() {
 // ------------------------------------------------------------------ instrumentation
 extern "C" long pop_kernel_launch_count(void) { return G.launches; }
 extern "C" int pop_timer_get(const char* name, double* ms, long* calls) {
+  resolve_timers();
   auto it = G.timers.find(name);
   if (it == G.timers.end()) {
     if (ms) *ms = 0.0;
@@ -399,6 +431,7 @@ extern "C" int pop_timer_get(const char* name, double* ms, long* calls) {
   return POP_SUCCESS;
 }
 extern "C" int pop_timers_reset(void) {
+  resolve_timers();
   G.timers.clear();
   return POP_SUCCESS;
 }

@@ -55,6 +55,7 @@ struct Ctx {
   int nxb = 0, nyb = 0, ib = 3, ie = 0, jb = 3, je = 0;  // 1-based like the reference
   size_t n2 = 0, n3 = 0;
   std::vector<int> i_glob, j_glob;
+  int *d_iglob = nullptr, *d_jglob = nullptr;  // device copies
   cudaStream_t stream = nullptr;
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy
@@ -75,11 +76,15 @@ struct Ctx {
   int lanczosSteps = 0;
   double rcheck = 0, rconst = 0;
   // reduction scratch (pop_reduce.cu)
-  double* d_partials = nullptr;  // [max_red_blocks][nfields<=4][2] double-double partials
-  double* d_sums = nullptr;      // device results: [16] doubles (hi parts rounded) + dd pairs
-  double* h_sums = nullptr;      // pinned mirror
-  double* d_gather = nullptr;    // [nranks][8] all-gathered dd pairs (multi-rank)
-  int max_red_blocks = 0;
+  double* d_partials = nullptr;  // [POP_RED_NF][red_blocks][2] double-double block partials
+  double* d_sums = nullptr;      // device results: [POP_RED_NF] doubles
+  double* h_sums = nullptr;      // pinned mirror of d_sums
+  double* d_local = nullptr;     // [POP_RED_NF][2] this rank's dd sums (all-gather send buffer)
+  double* d_gather = nullptr;    // [nranks][POP_RED_NF][2] all-gathered dd sums
+  void* d_scal = nullptr;        // SolverScalars on the device
+  int red_blocks = 0;            // fixed grid of every reduction (determinism)
+  double* d_tripole = nullptr;   // bufTripole(nxGlobal, haloWidth+1, nz) of the tripole fold
+  size_t tripole_elems = 0;
   // halo message buffers (multi-rank): rows to/from the south and north neighbours
   double* d_sendS = nullptr;
   double* d_sendN = nullptr;
@@ -92,6 +97,7 @@ struct Ctx {
   // instrumentation
   long launches = 0;
   bool timers_on = false;
+  int timer_suppress = 0;  // >0 inside the solver iterations (no per-iteration events)
   std::map<std::string, Timer> timers;
   int sm_count = 148;
 };
@@ -130,11 +136,13 @@ int alloc_field(const char* name, int nz, bool is_int);
 bool resolve_name(const char* name, int tlev, std::string* out);
 
 // launch bookkeeping: every kernel launch of this library goes through POP_LAUNCH
+#ifndef POP_LAUNCH
 #define POP_LAUNCH(kernel, grid, block, smem, ...)                    \
   do {                                                                \
     kernel<<<(grid), (block), (smem), G.stream>>>(__VA_ARGS__);       \
     G.launches++;                                                     \
   } while (0)
+#endif
 int pop_post_launch(const char* what);  // cudaGetLastError -> POP error
 
 // scoped CUDA-event timer with the reference timer names (timers.F90)
@@ -171,12 +179,20 @@ int halo_update_i4(int* a, int nz, int loc, int kind, int fill);
 int comm_init(int rank, int nranks, const char* id128);
 int comm_unique_id(char* id128);
 int comm_finalize();
+int comm_allreduce_min(double* host_value);
 // reductions (pop_reduce.cu): masked physical-domain sums of nfields 2-d fields, accumulated in
 // double-double; results (rounded to double) land in out_host[nfields] when out_host != nullptr
 // and always in G.d_sums[0..nfields-1] on the device (stream ordered).
+#define POP_RED_NF 4
+enum { RED_POST_NONE = 0, RED_POST_CG_INIT, RED_POST_CG_ITER, RED_POST_PCG_ETA1, RED_POST_PCG_ETA2,
+       RED_POST_RR };
 int global_sum_dev(const double* a, int nfields, size_t field_stride, int loc, const double* mask,
                    double* out_host);
 int reduce_alloc();
+// second stage for kernels that wrote their own block partials into G.d_partials with a grid of
+// G.red_blocks blocks: combine blocks (fixed order), combine ranks (rank order), apply `postop` to
+// the device-resident SolverScalars, optionally copy the sums to the host (synchronises).
+int reduce_finish(int nfields, int postop, double* out_host);
 // state (pop_state.cu)
 int state_slab(int k, int kk, const double* T, const double* S, double* RHOOUT, double* RHOFULL,
                double* DRHODT, double* DRHODS, size_t n);

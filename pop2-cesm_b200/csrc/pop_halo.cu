@@ -1,0 +1,263 @@
+// pop_halo.cu -- POP_HaloUpdate (mpi/POP_HaloMod.F90:1732-2071; 3-d :2766, 4-d :4122; 2-d I4) for the
+// 1 x P j-strip decomposition: one block per rank spanning all of i.
+//
+//   * north/south ghost rows come from the neighbouring rank: the two boundary rows of every level
+//     are packed into one message per neighbour (k fastest in the reference's messages; here a
+//     message is [nz][2][nx_global], contiguous runs of a full row) and exchanged with grouped
+//     ncclSend/ncclRecv over NVLink; with one rank and a cyclic north-south boundary it is a local
+//     copy.  Ghost rows that face a closed boundary are left untouched, exactly like the reference
+//     (no message targets them, mpi/POP_HaloMod.F90:5632-5700).
+//   * east/west ghost columns are a GPU-local cyclic wrap (done after the row exchange so that the
+//     corner cells receive the diagonal neighbour's values).
+//   * the tripole fold (mpi/POP_HaloMod.F90:1947-2048, :5846-5882) is local to the last rank: the top
+//     haloWidth+1 physical rows are gathered into bufTripole, symmetrised for NEcorner / Nface
+//     fields, and copied out with the sign of the field kind and the (ioffset, joffset) of the
+//     field location.
+#include "pop_dev.cuh"
+
+#ifndef POP_EMUL
+#include <nccl.h>
+#endif
+
+// ------------------------------------------------------------------ kernels
+// pack rows (jrow0, jrow0+1) of physical columns of every level: buf[z][r][ig]
+template <typename T>
+__global__ void halo_pack_rows(const T* __restrict__ a, T* __restrict__ buf, int nz, int nxb, size_t n2,
+                               int nxg, int jrow0 /*0-based*/) {
+  const size_t n = (size_t)nz * 2 * nxg;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
+    const size_t z = p / ((size_t)2 * nxg);
+    buf[p] = a[z * n2 + (size_t)(jrow0 + r) * nxb + (POP_NGHOST + ig)];
+  }
+}
+template <typename T>
+__global__ void halo_unpack_rows(T* __restrict__ a, const T* __restrict__ buf, int nz, int nxb,
+                                 size_t n2, int nxg, int jrow0) {
+  const size_t n = (size_t)nz * 2 * nxg;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
+    const size_t z = p / ((size_t)2 * nxg);
+    a[z * n2 + (size_t)(jrow0 + r) * nxb + (POP_NGHOST + ig)] = buf[p];
+  }
+}
+// single rank, cyclic north-south: ghost rows from the opposite physical rows (physical columns)
+template <typename T>
+__global__ void halo_ns_cyclic_local(T* __restrict__ a, int nz, int nxb, int nyb, size_t n2, int nxg) {
+  const size_t n = (size_t)nz * 4 * nxg;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 4);
+    const size_t z = p / ((size_t)4 * nxg);
+    // r = 0,1: south ghost rows 0,1 <- rows nyb-4, nyb-3 ; r = 2,3: north ghost rows <- rows 2,3
+    const int jd = (r < 2) ? r : nyb - 4 + r;
+    const int js = (r < 2) ? nyb - 4 + r : r;
+    T* az = a + z * n2;
+    az[(size_t)jd * nxb + POP_NGHOST + ig] = az[(size_t)js * nxb + POP_NGHOST + ig];
+  }
+}
+// east-west cyclic wrap of every row whose global j index is positive (closed-boundary ghost rows and
+// tripole ghost rows are not touched here)
+template <typename T>
+__global__ void halo_ew_wrap(T* __restrict__ a, int nz, int nxb, int nyb, size_t n2,
+                             const int* __restrict__ jglob) {
+  const size_t n = (size_t)nz * nyb * 4;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(p % 4), j = (int)((p / 4) % nyb);
+    const size_t z = p / ((size_t)4 * nyb);
+    if (jglob[j] <= 0) continue;
+    T* row = a + z * n2 + (size_t)j * nxb;
+    // c = 0,1: west ghost columns 0,1 <- columns nxb-4, nxb-3 ; c = 2,3: east ghost <- columns 2,3
+    if (c < 2) row[c] = row[nxb - 4 + c];
+    else row[nxb - 4 + c] = row[c];
+  }
+}
+
+__device__ __forceinline__ double sym_val(double xp, double xq, int isign) {
+  const double xavg = 0.5 * (fabs(xp) + fabs(xq));
+  return isign * copysign(xavg, xq);
+}
+__device__ __forceinline__ int sym_val(int xp, int xq, int isign) {
+  const int xavg = (int)lround(0.5 * (abs(xp) + abs(xq)));
+  return isign * (xq < 0 ? -xavg : xavg);
+}
+// tripole copy-in: bufTripole(ig, r, z) <- physical rows je-2..je (r = 0..2), with the top row
+// symmetrised for NEcorner / Nface fields (mpi/POP_HaloMod.F90:1961-2030)
+template <typename T>
+__global__ void halo_tripole_in(const T* __restrict__ a, T* __restrict__ buf, int nz, int nxb,
+                                size_t n2, int nxg, int je0 /*0-based row of je*/, int loc, int isign) {
+  const size_t n = (size_t)nz * 3 * nxg;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int ig = (int)(p % nxg) + 1, r = (int)((p / nxg) % 3);  // ig 1-based
+    const size_t z = p / ((size_t)3 * nxg);
+    const T* row = a + z * n2 + (size_t)(je0 - 2 + r) * nxb + (POP_NGHOST - 1);  // row[ig]
+    T v = row[ig];
+    if (r == 2) {
+      if (loc == POP_LOC_NECORNER) {
+        if (ig == nxg) v = (T)(isign * v);
+        else v = sym_val(v, row[nxg - ig], isign);
+      } else if (loc == POP_LOC_NFACE) {
+        const int partner = nxg + 1 - ig;
+        if (partner != ig) v = sym_val(v, row[partner], isign);
+      }
+    }
+    buf[p] = v;
+  }
+}
+// tripole copy-out into rows je..je+2, all columns (mpi/POP_HaloMod.F90:2032-2048)
+template <typename T>
+__global__ void halo_tripole_out(T* __restrict__ a, const T* __restrict__ buf, int nz, int nxb,
+                                 size_t n2, int nxg, int je0, int ioff, int joff, int isign,
+                                 const int* __restrict__ iglob) {
+  const size_t n = (size_t)nz * 3 * nxb;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p % nxb), j = (int)((p / nxb) % 3) + 1;  // j = 1..3
+    const size_t z = p / ((size_t)3 * nxb);
+    int is = nxg - iglob[i] + 1 - ioff;
+    const int js = POP_NGHOST + 3 - j - joff;
+    if (is == 0) is = nxg;
+    if (js <= POP_NGHOST + 1 && js >= 1 && is >= 1 && is <= nxg)
+      a[z * n2 + (size_t)(je0 + j - 1) * nxb + i] =
+          (T)(isign * buf[(z * 3 + (js - 1)) * nxg + (is - 1)]);
+  }
+}
+
+// ------------------------------------------------------------------ communicator
+#ifndef POP_EMUL
+int comm_unique_id(char* id128) {
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  POP_REQUIRE(r == ncclSuccess, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId larger than 128 bytes");
+  memset(id128, 0, 128);
+  memcpy(id128, &id, sizeof(id));
+  return POP_SUCCESS;
+}
+int comm_init(int rank, int nranks, const char* id128) {
+  POP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "pop_comm_init: bad rank %d/%d", rank, nranks);
+  if (G.nccl_comm) comm_finalize();
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  ncclResult_t r = ncclCommInitRank(&comm, nranks, id, rank);
+  POP_REQUIRE(r == ncclSuccess, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  G.nccl_comm = (void*)comm;
+  return POP_SUCCESS;
+}
+int comm_finalize() {
+  if (G.nccl_comm) ncclCommDestroy((ncclComm_t)G.nccl_comm);
+  G.nccl_comm = nullptr;
+  return POP_SUCCESS;
+}
+int comm_allreduce_min(double* v) {
+  if (G.nranks == 1) return POP_SUCCESS;
+  double* d = G.d_local;
+  POP_CHECK_CUDA(cudaMemcpyAsync(d, v, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  ncclResult_t r = ncclAllReduce(d, d, 1, ncclDouble, ncclMin, (ncclComm_t)G.nccl_comm, G.stream);
+  POP_REQUIRE(r == ncclSuccess, "ncclAllReduce(min): %s", ncclGetErrorString(r));
+  POP_CHECK_CUDA(cudaMemcpyAsync(v, d, sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  return POP_SUCCESS;
+}
+#else
+int comm_unique_id(char* id128) { memset(id128, 0, 128); return POP_SUCCESS; }
+int comm_init(int, int, const char*) { return POP_SUCCESS; }
+int comm_finalize() { return POP_SUCCESS; }
+int comm_allreduce_min(double*) { return POP_SUCCESS; }
+#endif
+
+static int ensure_halo_buffers(size_t elems) {  // elems: doubles per message
+  if (elems <= G.halo_buf_elems) return POP_SUCCESS;
+  cudaFree(G.d_sendS); cudaFree(G.d_sendN); cudaFree(G.d_recvS); cudaFree(G.d_recvN);
+  G.d_sendS = G.d_sendN = G.d_recvS = G.d_recvN = nullptr;
+  G.halo_buf_elems = 0;
+  POP_CHECK_CUDA(cudaMalloc(&G.d_sendS, elems * sizeof(double)));
+  POP_CHECK_CUDA(cudaMalloc(&G.d_sendN, elems * sizeof(double)));
+  POP_CHECK_CUDA(cudaMalloc(&G.d_recvS, elems * sizeof(double)));
+  POP_CHECK_CUDA(cudaMalloc(&G.d_recvN, elems * sizeof(double)));
+  G.halo_buf_elems = elems;
+  return POP_SUCCESS;
+}
+
+template <typename T>
+static int halo_update_t(T* a, int nz, int loc, int kind, T fill) {
+  (void)fill;  // no eliminated land blocks in the strip decomposition: nothing receives fillValue
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: library not initialized");
+  POP_REQUIRE(a != nullptr && nz >= 1, "POP_HaloUpdate: bad array");
+  POP_REQUIRE(loc >= POP_LOC_CENTER && loc <= POP_LOC_EFACE, "POP_HaloUpdate: unknown field location %d", loc);
+  POP_REQUIRE(kind >= POP_KIND_SCALAR && kind <= POP_KIND_ANGLE, "POP_HaloUpdate: unknown field kind %d", kind);
+  ScopedTimer tm("HALO");
+  const int nxb = G.nxb, nyb = G.nyb, nxg = G.nxg;
+  const size_t n2 = G.n2;
+  const int ns = G.cfg.ns_boundary_type, ew = G.cfg.ew_boundary_type;
+  const size_t msg = (size_t)nz * 2 * nxg;
+  const unsigned gmsg = ew_grid(msg) < 4096 ? ew_grid(msg) : 4096;
+  // ---- north/south
+  if (G.nranks > 1) {
+#ifndef POP_EMUL
+    const int south = (G.rank > 0) ? G.rank - 1 : (ns == POP_BNDY_CYCLIC ? G.nranks - 1 : -1);
+    const int north = (G.rank < G.nranks - 1) ? G.rank + 1 : (ns == POP_BNDY_CYCLIC ? 0 : -1);
+    const size_t msg_d = (msg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
+    POP_TRY(ensure_halo_buffers(msg_d));
+    T *sS = (T*)G.d_sendS, *sN = (T*)G.d_sendN, *rS = (T*)G.d_recvS, *rN = (T*)G.d_recvN;
+    if (south >= 0) POP_LAUNCH(halo_pack_rows<T>, gmsg, POP_EW_THREADS, 0, a, sS, nz, nxb, n2, nxg, G.jb - 1);
+    if (north >= 0) POP_LAUNCH(halo_pack_rows<T>, gmsg, POP_EW_THREADS, 0, a, sN, nz, nxb, n2, nxg, G.je - 2);
+    ncclComm_t comm = (ncclComm_t)G.nccl_comm;
+    const size_t bytes = msg * sizeof(T);
+    ncclGroupStart();
+    if (south >= 0) {
+      ncclSend(sS, bytes, ncclChar, south, comm, G.stream);
+      ncclRecv(rS, bytes, ncclChar, south, comm, G.stream);
+    }
+    if (north >= 0) {
+      ncclSend(sN, bytes, ncclChar, north, comm, G.stream);
+      ncclRecv(rN, bytes, ncclChar, north, comm, G.stream);
+    }
+    ncclResult_t r = ncclGroupEnd();
+    POP_REQUIRE(r == ncclSuccess, "halo ncclGroupEnd: %s", ncclGetErrorString(r));
+    if (south >= 0) POP_LAUNCH(halo_unpack_rows<T>, gmsg, POP_EW_THREADS, 0, a, rS, nz, nxb, n2, nxg, 0);
+    if (north >= 0) POP_LAUNCH(halo_unpack_rows<T>, gmsg, POP_EW_THREADS, 0, a, rN, nz, nxb, n2, nxg, G.je);
+#endif
+  } else if (ns == POP_BNDY_CYCLIC) {
+    const size_t n = (size_t)nz * 4 * nxg;
+    POP_LAUNCH(halo_ns_cyclic_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb, nyb, n2, nxg);
+  }
+  // ---- east/west
+  if (ew == POP_BNDY_CYCLIC) {
+    const size_t n = (size_t)nz * nyb * 4;
+    POP_LAUNCH(halo_ew_wrap<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb, nyb, n2, G.d_jglob);
+  }
+  // ---- tripole fold on the last rank
+  if (ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) {
+    const size_t need = ((size_t)nz * 3 * nxg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
+    if (need > G.tripole_elems) {
+      cudaFree(G.d_tripole);
+      G.d_tripole = nullptr;
+      G.tripole_elems = 0;
+      POP_CHECK_CUDA(cudaMalloc(&G.d_tripole, need * sizeof(double)));
+      G.tripole_elems = need;
+    }
+    T* buf = (T*)G.d_tripole;
+    const int isign = (kind == POP_KIND_SCALAR) ? 1 : -1;
+    int ioff = 0, joff = 0;
+    if (loc == POP_LOC_NECORNER) { ioff = 1; joff = 1; }
+    else if (loc == POP_LOC_EFACE) { ioff = 1; joff = 0; }
+    else if (loc == POP_LOC_NFACE) { ioff = 0; joff = 1; }
+    const size_t nin = (size_t)nz * 3 * nxg, nout = (size_t)nz * 3 * nxb;
+    POP_LAUNCH(halo_tripole_in<T>, ew_grid(nin) < 4096 ? ew_grid(nin) : 4096, POP_EW_THREADS, 0, a, buf, nz, nxb, n2, nxg, G.je - 1, loc, isign);
+    POP_LAUNCH(halo_tripole_out<T>, ew_grid(nout) < 4096 ? ew_grid(nout) : 4096, POP_EW_THREADS, 0, a, buf, nz, nxb, n2, nxg, G.je - 1, ioff, joff, isign, G.d_iglob);
+  }
+  return pop_post_launch("halo_update");
+}
+
+int halo_update(double* a, int nz, int loc, int kind, double fill) {
+  return halo_update_t<double>(a, nz, loc, kind, fill);
+}
+int halo_update_i4(int* a, int nz, int loc, int kind, int fill) {
+  return halo_update_t<int>(a, nz, loc, kind, fill);
+}

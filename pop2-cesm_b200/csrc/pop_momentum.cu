@@ -1,0 +1,575 @@
+// pop_momentum.cu -- the momentum half of the baroclinic step.
+//
+//   momentum_column : ONE fused column kernel for everything `clinic` does per level
+//                     (baroclinic.F90:1635-1895): advu (advection.F90:1127-1570), Coriolis, gradp + grad
+//                     (pressure_grad.F90:187-306, operators.F90:126-192), hdiffu del2/del4
+//                     (hmix_del2.F90:670-963, hmix_del4.F90:597-882), vdiffu
+//                     (vertical_mix.F90:853-1026), plus the implicit-Coriolis solve and the ZX/ZY
+//                     vertical integrals of baroclinic_driver (baroclinic.F90:1013-1057).  A thread
+//                     owns an (i,j) column and carries WUK, SUMX/SUMY, RHOKMX/RHOKMY, VUF/VVF in
+//                     registers; restricted to one level and one term it implements the slab entry
+//                     points pop_advu / pop_hdiffu / pop_gradp / pop_vdiffu.
+//   momentum_finish : impvmixu (vertical_mix.F90:1679-1881) + U = Uold + dU + removal of the
+//                     vertical mean + KMU mask (baroclinic.F90:1067-1129).
+//   grad / div      : operators.F90:126-192, :49-119 (2-d, used by the barotropic driver).
+#include "pop_dev.cuh"
+
+struct MomentumArgs {
+  GridView g;
+  const double *UCUR, *VCUR, *UOLD, *VOLD, *UMIX, *VMIX, *RHOOLD, *RHOCUR, *RHONEW, *SMF, *DHU;
+  double *OUT1, *OUT2;  // FULL: UVEL/VVEL(new) (nxb,nyb,km); slab modes: two (nxb,nyb) slabs
+  double *ZX, *ZY;
+  double* WUK;          // slab ADVU: carried (in/out)
+  double *SUMX, *SUMY, *RHOKMX, *RHOKMY, *VUF, *VVF;  // slab carried state
+  int k0, k1;
+  int lvariable_hmixu, impcor, leapfrog, pavg;
+  double am, c2dtu, beta, gamma, bottom_drag;
+};
+
+struct MomCoefTiles {
+  const double *cc, *dun, *dus, *due, *duw, *dmc, *dmn, *dms, *dme, *dmw;
+};
+// 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*
+__device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const double* A, const double* B,
+                                              int ii, int jj, bool plus) {
+  const int q = TIX(ii, jj);
+  const double s1 = c.cc[q] * A[q] + c.dun[q] * A[TIX(ii, jj + 1)] + c.dus[q] * A[TIX(ii, jj - 1)] +
+                    c.due[q] * A[TIX(ii + 1, jj)] + c.duw[q] * A[TIX(ii - 1, jj)];
+  const double s2 = c.dmc[q] * B[q] + c.dmn[q] * B[TIX(ii, jj + 1)] + c.dms[q] * B[TIX(ii, jj - 1)] +
+                    c.dme[q] * B[TIX(ii + 1, jj)] + c.dmw[q] * B[TIX(ii - 1, jj)];
+  return plus ? (s1 + s2) : (s1 - s2);
+}
+
+#define MOM_NTILES 20
+template <int MODE, bool DEL4>
+__global__ void __launch_bounds__(POP_NTHREADS)
+momentum_column_kernel(const MomentumArgs a) {
+  POP_DYN_SMEM(smem_raw);
+  double* sm = (double*)smem_raw;
+  double* s_dyu = sm;
+  double* s_dxu = s_dyu + POP_TN;
+  double* s_cc = s_dxu + POP_TN;
+  double* s_dun = s_cc + POP_TN;
+  double* s_dus = s_dun + POP_TN;
+  double* s_due = s_dus + POP_TN;
+  double* s_duw = s_due + POP_TN;
+  double* s_dmc = s_duw + POP_TN;
+  double* s_dmn = s_dmc + POP_TN;
+  double* s_dms = s_dmn + POP_TN;
+  double* s_dme = s_dms + POP_TN;
+  double* s_dmw = s_dme + POP_TN;
+  double* s_amf = s_dmw + POP_TN;
+  double* s_uc = s_amf + POP_TN;
+  double* s_vc = s_uc + POP_TN;
+  double* s_um = s_vc + POP_TN;
+  double* s_vm = s_um + POP_TN;
+  double* s_rho = s_vm + POP_TN;
+  double* s_d2u = s_rho + POP_TN;
+  double* s_d2v = s_d2u + POP_TN;
+  int* s_kmu = (int*)(s_d2v + POP_TN);
+
+  const GridView& g = a.g;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
+  const int i0 = (g.ib - 1) + blockIdx.x * POP_BX;
+  const int j0 = (g.jb - 1) + blockIdx.y * POP_BY;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = (i <= g.ie - 1) && (j <= g.je - 1);
+  const size_t q = (size_t)j * g.nxb + i;
+  const size_t n2 = g.n2;
+  const int km = g.km, nxb = g.nxb, nyb = g.nyb;
+  constexpr bool DO_ADV = (MODE == MO_FULL || MODE == MO_ADVU);
+  constexpr bool DO_HMIX = (MODE == MO_FULL || MODE == MO_HDIFFU);
+  constexpr bool DO_GRADP = (MODE == MO_FULL || MODE == MO_GRADP);
+  constexpr bool DO_VDIF = (MODE == MO_FULL || MODE == MO_VDIFFU);
+  constexpr int HM = DEL4 ? 2 : 1;
+  const bool same_mix = (a.UMIX == a.UCUR) && DO_ADV && !DEL4;
+
+  // ---- k-invariant staging
+  if (DO_ADV) {
+    tile_load(s_dyu, g.DYU, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    tile_load(s_dxu, g.DXU, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+  }
+  if (DO_HMIX) {
+    constexpr int R = DEL4 ? 1 : 0;  // coefficients are needed on the first halo ring for del4
+    const int w = POP_BX + 2 * R, npts = w * (POP_BY + 2 * R);
+    for (int p = tid; p < npts; p += POP_NTHREADS) {
+      const int jj = p / w - R, ii = p % w - R;
+      const int gi = i0 + ii, gj = j0 + jj, t = TIX(ii, jj);
+      const bool in = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb);
+      const size_t qq = (size_t)gj * nxb + gi;
+      s_cc[t] = in ? g.DUC[qq] + g.DUM[qq] : 0.0;
+      s_dun[t] = in ? g.DUN[qq] : 0.0;
+      s_dus[t] = in ? g.DUS[qq] : 0.0;
+      s_due[t] = in ? g.DUE[qq] : 0.0;
+      s_duw[t] = in ? g.DUW[qq] : 0.0;
+      s_dmc[t] = in ? g.DMC[qq] : 0.0;
+      s_dmn[t] = in ? g.DMN[qq] : 0.0;
+      s_dms[t] = in ? g.DMS[qq] : 0.0;
+      s_dme[t] = in ? g.DME[qq] : 0.0;
+      s_dmw[t] = in ? g.DMW[qq] : 0.0;
+      s_amf[t] = in ? g.AMF[qq] : 0.0;
+      s_kmu[t] = in ? g.KMU[qq] : 0;
+    }
+  }
+  const MomCoefTiles ct{s_cc, s_dun, s_dus, s_due, s_duw, s_dmc, s_dmn, s_dms, s_dme, s_dmw};
+  int kmu = 0;
+  double uarea_r = 0, kxu = 0, kyu = 0, fcor = 0, dxur = 0, dyur = 0;
+  if (active) {
+    kmu = g.KMU[q];
+    uarea_r = g.UAREA_R[q];
+    kxu = g.KXU[q];
+    kyu = g.KYU[q];
+    fcor = g.FCOR[q];
+    dxur = g.DXUR[q];
+    dyur = g.DYUR[q];
+  }
+  // ---- carried state
+  double wuk = 0, u_m = 0, v_m = 0, uo_c = 0, vo_c = 0;
+  double sumx = 0, sumy = 0, rmx = 0, rmy = 0, vuf = 0, vvf = 0, zx = 0, zy = 0;
+  if (active) {
+    if (DO_ADV) {
+      wuk = (MODE == MO_FULL) ? a.DHU[q] : a.WUK[q];
+      if (a.k0 > 1) {
+        u_m = a.UCUR[(size_t)(a.k0 - 2) * n2 + q];
+        v_m = a.VCUR[(size_t)(a.k0 - 2) * n2 + q];
+      }
+    }
+    if (DO_VDIF || MODE == MO_FULL) {
+      uo_c = a.UOLD[(size_t)(a.k0 - 1) * n2 + q];
+      vo_c = a.VOLD[(size_t)(a.k0 - 1) * n2 + q];
+    }
+    if (DO_VDIF && a.k0 > 1) {
+      vuf = a.VUF[q];
+      vvf = a.VVF[q];
+    }
+    if (DO_GRADP && a.k0 > 1) {
+      sumx = a.SUMX[q];
+      sumy = a.SUMY[q];
+      rmx = a.RHOKMX[q];
+      rmy = a.RHOKMY[q];
+    }
+  }
+
+  for (int k = a.k0; k <= a.k1; k++) {
+    __syncthreads();
+    const size_t lev = (size_t)(k - 1) * n2;
+    if (DO_ADV) {
+      tile_load(s_uc, a.UCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+      tile_load(s_vc, a.VCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    }
+    if (DO_HMIX && !same_mix) {
+      tile_load(s_um, a.UMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+      tile_load(s_vm, a.VMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+    }
+    if (DO_GRADP) {
+      // RHOAVG on the (i..i+1, j..j+1) corners: pressure_grad.F90:258-266
+      constexpr int w = POP_BX + 1, npts = w * (POP_BY + 1);
+      const double bouss = c_vc.bouss[k];
+      for (int p = tid; p < npts; p += POP_NTHREADS) {
+        const int jj = p / w, ii = p % w;
+        const int gi = i0 + ii, gj = j0 + jj;
+        double v = 0.0;
+        if (gi < nxb && gj < nyb) {
+          const size_t qq = lev + (size_t)gj * nxb + gi;
+          if (a.pavg) v = 0.25 * (a.RHONEW[qq] + 2.0 * a.RHOCUR[qq] + a.RHOOLD[qq]) * bouss;
+          else v = a.RHOCUR[qq] * bouss;
+        }
+        s_rho[TIX(ii, jj)] = v;
+      }
+    }
+    __syncthreads();
+    const double* um = same_mix ? s_uc : s_um;
+    const double* vm = same_mix ? s_vc : s_vm;
+    if (DO_HMIX && DEL4) {
+      // first application of the operator on the halo ring (hmix_del4.F90:730-790)
+      constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
+      for (int p = tid; p < npts; p += POP_NTHREADS) {
+        const int jj = p / w - 1, ii = p % w - 1, t = TIX(ii, jj);
+        double d2u = mom_stencil(ct, um, vm, ii, jj, true);
+        double d2v = mom_stencil(ct, vm, um, ii, jj, false);
+        if (a.lvariable_hmixu) {
+          if (k <= s_kmu[t]) { d2u = s_amf[t] * d2u; d2v = s_amf[t] * d2v; }
+          else { d2u = 0.0; d2v = 0.0; }
+        } else if (k > s_kmu[t]) { d2u = 0.0; d2v = 0.0; }
+        s_d2u[t] = d2u;
+        s_d2v[t] = d2v;
+      }
+      __syncthreads();
+    }
+    if (!active) continue;
+
+    double fx = 0.0, fy = 0.0;
+    const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
+    // ---- advu: advection.F90:1307-1491
+    double luk = 0.0, lvk = 0.0;
+    if (DO_ADV) {
+#define UD(di, dj) (s_uc[TIX(tx + (di), ty + (dj))] * s_dyu[TIX(tx + (di), ty + (dj))])
+#define VD(di, dj) (s_vc[TIX(tx + (di), ty + (dj))] * s_dxu[TIX(tx + (di), ty + (dj))])
+      const double uuw = 0.25 * (UD(0, 0) + UD(-1, 0)) + 0.125 * (UD(0, -1) + UD(-1, -1) + UD(0, 1) + UD(-1, 1));
+      const double uue = 0.25 * (UD(1, 0) + UD(0, 0)) + 0.125 * (UD(1, -1) + UD(0, -1) + UD(1, 1) + UD(0, 1));
+      const double vus = 0.25 * (VD(0, 0) + VD(0, -1)) + 0.125 * (VD(-1, 0) + VD(-1, -1) + VD(1, 0) + VD(1, -1));
+      const double vun = 0.25 * (VD(0, 1) + VD(0, 0)) + 0.125 * (VD(-1, 1) + VD(-1, 0) + VD(1, 1) + VD(1, 0));
+#undef UD
+#undef VD
+      const double wukb = wuk + c_vc.c2dz[k] * 0.5 * (vun - vus + uue - uuw) * uarea_r;
+      const double cc = vun - vus + uue - uuw;  // VUS(i,j+1) - VUS(i,j) + UUW(i+1,j) - UUW(i,j)
+      luk = 0.5 * (cc * U + vun * s_uc[TIX(tx, ty + 1)] - vus * s_uc[TIX(tx, ty - 1)] +
+                   uue * s_uc[TIX(tx + 1, ty)] - uuw * s_uc[TIX(tx - 1, ty)]) * uarea_r;
+      lvk = 0.5 * (cc * V + vun * s_vc[TIX(tx, ty + 1)] - vus * s_vc[TIX(tx, ty - 1)] +
+                   uue * s_vc[TIX(tx + 1, ty)] - uuw * s_vc[TIX(tx - 1, ty)]) * uarea_r;
+      if (k == 1) {
+        luk = luk + c_vc.dzr[k] * wuk * U;
+        lvk = lvk + c_vc.dzr[k] * wuk * V;
+      } else {
+        luk = luk + c_vc.dz2r[k] * wuk * (u_m + U);
+        lvk = lvk + c_vc.dz2r[k] * wuk * (v_m + V);
+      }
+      if (k < km) {
+        const double Up = a.UCUR[lev + n2 + q], Vp = a.VCUR[lev + n2 + q];
+        luk = luk - c_vc.dz2r[k] * wukb * (U + Up);
+        lvk = lvk - c_vc.dz2r[k] * wukb * (V + Vp);
+      }
+      if (k <= kmu) {
+        luk = luk + U * V * kyu - (V * V) * kxu;
+        lvk = lvk + U * V * kxu - (U * U) * kyu;
+      } else {
+        luk = 0.0;
+        lvk = 0.0;
+      }
+      wuk = wukb;
+      u_m = U;
+      v_m = V;
+    }
+    // ---- gradp: pressure_grad.F90:268-301 with grad of operators.F90:178-187
+    double pkx = 0.0, pky = 0.0;
+    if (DO_GRADP) {
+      double rkx = 0.0, rky = 0.0;
+      if (k <= kmu) {
+        const double f11 = s_rho[TIX(tx + 1, ty + 1)], f00 = s_rho[TIX(tx, ty)],
+                     f01 = s_rho[TIX(tx, ty + 1)], f10 = s_rho[TIX(tx + 1, ty)];
+        rkx = dxur * 0.5 * (f11 - f00 - f01 + f10);
+        rky = dyur * 0.5 * (f11 - f00 + f01 - f10);
+      }
+      if (k == 1) {
+        rmx = rkx;
+        rmy = rky;
+        sumx = 0.0;
+        sumy = 0.0;
+      }
+      const double factor = c_vc.dzw[k - 1] * POP_GRAV * 0.5;
+      sumx = sumx + factor * (rkx + rmx);
+      sumy = sumy + factor * (rky + rmy);
+      pkx = sumx;
+      pky = sumy;
+      rmx = rkx;
+      rmy = rky;
+    }
+    // ---- hdiffu
+    double hdu = 0.0, hdv = 0.0;
+    if (DO_HMIX) {
+      if (DEL4) {
+        hdu = a.am * mom_stencil(ct, s_d2u, s_d2v, tx, ty, true);
+        hdv = a.am * mom_stencil(ct, s_d2v, s_d2u, tx, ty, false);
+      } else {
+        hdu = a.am * mom_stencil(ct, um, vm, tx, ty, true);
+        hdv = a.am * mom_stencil(ct, vm, um, tx, ty, false);
+      }
+      if (k > kmu) { hdu = 0.0; hdv = 0.0; }
+    }
+    // ---- vdiffu: vertical_mix.F90:935-1010
+    double vdu = 0.0, vdv = 0.0;
+    double uo_p = 0.0, vo_p = 0.0;
+    if (DO_VDIF || MODE == MO_FULL) {
+      uo_p = (k < km) ? a.UOLD[lev + n2 + q] : uo_c;
+      vo_p = (k < km) ? a.VOLD[lev + n2 + q] : vo_c;
+    }
+    if (DO_VDIF) {
+      const int kk = (g.vvc_nk == 1) ? 1 : k;
+      const double vvc = g.VVC[(size_t)(kk - 1) * n2 + q];
+      if (k == 1) {
+        vuf = (kmu >= 1) ? a.SMF[q] : 0.0;
+        vvf = (kmu >= 1) ? a.SMF[n2 + q] : 0.0;
+      }
+      double vufb = vvc * (uo_c - uo_p) * c_vc.dzwr[k];
+      double vvfb = vvc * (vo_c - vo_p) * c_vc.dzwr[k];
+      if (k == kmu) {
+        const double vmag = a.bottom_drag * sqrt(uo_c * uo_c + vo_c * vo_c);
+        vufb = vmag * uo_c;
+        vvfb = vmag * vo_c;
+      }
+      vdu = (k <= kmu) ? (vuf - vufb) * c_vc.dzr[k] : 0.0;
+      vdv = (k <= kmu) ? (vvf - vvfb) * c_vc.dzr[k] : 0.0;
+      vuf = vufb;
+      vvf = vvfb;
+    }
+    if (MODE == MO_ADVU) { a.OUT1[q] = luk; a.OUT2[q] = lvk; }
+    else if (MODE == MO_GRADP) { a.OUT1[q] = pkx; a.OUT2[q] = pky; }
+    else if (MODE == MO_HDIFFU) { a.OUT1[q] = hdu; a.OUT2[q] = hdv; }
+    else if (MODE == MO_VDIFFU) { a.OUT1[q] = vdu; a.OUT2[q] = vdv; }
+    else {
+      // ---- clinic assembly: baroclinic.F90:1728-1895
+      fx = -luk;
+      fy = -lvk;
+      if (a.impcor && a.leapfrog) {
+        fx = fx + fcor * (a.gamma * V + (1.0 - a.gamma) * vo_c);
+        fy = fy - fcor * (a.gamma * U + (1.0 - a.gamma) * uo_c);
+      } else if (!a.impcor && a.leapfrog) {
+        fx = fx + fcor * V;
+        fy = fy - fcor * U;
+      } else {
+        fx = fx + fcor * vo_c;
+        fy = fy - fcor * uo_c;
+      }
+      fx = fx - pkx;
+      fy = fy - pky;
+      fx = fx + hdu;
+      fy = fy + hdv;
+      fx = fx + vdu;
+      fy = fy + vdv;
+      if (k > kmu) { fx = 0.0; fy = 0.0; }
+      // ---- implicit Coriolis and vertical integrals: baroclinic.F90:1013-1045
+      double un, vn;
+      if (a.impcor) {
+        const double w1 = a.c2dtu * a.beta * fcor;
+        const double w2 = a.c2dtu / (1.0 + w1 * w1);
+        un = (fx + w1 * fy) * w2;
+        vn = (fy - w1 * fx) * w2;
+      } else {
+        un = a.c2dtu * fx;
+        vn = a.c2dtu * fy;
+      }
+      a.OUT1[lev + q] = un;
+      a.OUT2[lev + q] = vn;
+      zx = zx + fx * c_vc.dz[k];
+      zy = zy + fy * c_vc.dz[k];
+    }
+    uo_c = uo_p;
+    vo_c = vo_p;
+  }
+  if (!active) return;
+  if (MODE == MO_FULL) {
+    const double hur = g.HUR[q];
+    a.ZX[q] = zx * hur;
+    a.ZY[q] = zy * hur;
+  } else if (MODE == MO_ADVU) {
+    a.WUK[q] = wuk;
+  } else if (MODE == MO_GRADP) {
+    a.SUMX[q] = sumx; a.SUMY[q] = sumy; a.RHOKMX[q] = rmx; a.RHOKMY[q] = rmy;
+  } else if (MODE == MO_VDIFFU) {
+    a.VUF[q] = vuf; a.VVF[q] = vvf;
+  }
+}
+
+template <int MODE>
+static int launch_momentum(const MomentumArgs& a, bool del4) {
+  void (*kfn)(const MomentumArgs) = del4 ? momentum_column_kernel<MODE, true> : momentum_column_kernel<MODE, false>;
+  const size_t smem = sizeof(double) * POP_TN * MOM_NTILES + sizeof(int) * POP_TN;
+#ifndef POP_EMUL
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  POP_LAUNCH(kfn, col_grid(G.nxg, G.ny_local), col_block(), smem, a);
+  return POP_SUCCESS;
+}
+
+int momentum_column(int mode, int k, const MomentumIO& io) {
+  MomentumArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = grid_view();
+  a.UCUR = io.UCUR; a.VCUR = io.VCUR; a.UOLD = io.UOLD; a.VOLD = io.VOLD; a.UMIX = io.UMIX;
+  a.VMIX = io.VMIX; a.RHOOLD = io.RHOOLD; a.RHOCUR = io.RHOCUR; a.RHONEW = io.RHONEW;
+  a.SMF = io.SMF; a.DHU = io.DHU;
+  a.OUT1 = io.UNEW; a.OUT2 = io.VNEW; a.ZX = io.ZX; a.ZY = io.ZY; a.WUK = io.WUK;
+  a.SUMX = fld("SUMX"); a.SUMY = fld("SUMY"); a.RHOKMX = fld("RHOKMX"); a.RHOKMY = fld("RHOKMY");
+  a.VUF = fld("VUF"); a.VVF = fld("VVF");
+  a.lvariable_hmixu = G.cfg.lvariable_hmixu;
+  a.impcor = G.cfg.impcor;
+  a.leapfrog = G.leapfrogts;
+  a.pavg = (G.cfg.lpressure_avg && G.leapfrogts);
+  a.am = G.am; a.c2dtu = G.c2dtu; a.beta = G.beta; a.gamma = G.gamma;
+  a.bottom_drag = G.cfg.bottom_drag;
+  const bool del4 = (G.cfg.hmix_momentum_itype == POP_HMIX_DEL4);
+  if (mode == MO_FULL) { a.k0 = 1; a.k1 = G.km; }
+  else {
+    POP_REQUIRE(k >= 1 && k <= G.km, "momentum slab operator: k=%d out of range", k);
+    a.k0 = a.k1 = k;
+    // 2-d slab arguments of the reference signatures are addressed as "level k" of a virtual 3-d array
+    const size_t off = (size_t)(k - 1) * G.n2;
+    if (mode == MO_HDIFFU) { a.UMIX -= off; a.VMIX -= off; }
+    if (mode == MO_GRADP) {
+      POP_REQUIRE(a.RHOCUR && (!a.pavg || (a.RHOOLD && a.RHONEW)), "gradp: null density slab");
+      a.RHOCUR -= off;
+      if (a.RHOOLD) a.RHOOLD -= off;
+      if (a.RHONEW) a.RHONEW -= off;
+    }
+  }
+  switch (mode) {
+    case MO_FULL: POP_TRY(launch_momentum<MO_FULL>(a, del4)); break;
+    case MO_ADVU: POP_TRY(launch_momentum<MO_ADVU>(a, false)); break;
+    case MO_HDIFFU: POP_TRY(launch_momentum<MO_HDIFFU>(a, del4)); break;
+    case MO_GRADP: POP_TRY(launch_momentum<MO_GRADP>(a, false)); break;
+    case MO_VDIFFU: POP_TRY(launch_momentum<MO_VDIFFU>(a, false)); break;
+    default: POP_REQUIRE(false, "momentum_column: bad mode %d", mode);
+  }
+  return pop_post_launch("momentum_column");
+}
+
+// =====================================================================================
+// impvmixu + velocity finish
+// =====================================================================================
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
+                       const double* __restrict__ UOLD, const double* __restrict__ VOLD, double c2dtu,
+                       int implicit_vmix, int finish) {
+  const int i = (g.ib - 1) + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (g.jb - 1) + blockIdx.y;
+  if (i > g.ie - 1 || j > g.je - 1) return;
+  const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
+  const int km = g.km, kmu = g.KMU[q];
+  double* Un = UNEW + q;
+  double* Vn = VNEW + q;
+  if (implicit_vmix) {
+    double E[KMAX];
+    double A, B, C, D, F1, F2;
+    {
+      const double hfac = c_vc.dz[1] / c2dtu;
+      A = c_vc.afac_u[1] * g.VVC[q];
+      D = hfac + A;
+      E[0] = A / D;
+      B = hfac * E[0];
+      F1 = hfac * Un[0] / D;
+      F2 = hfac * Vn[0] / D;
+      Un[0] = F1;
+      Vn[0] = F2;
+    }
+#pragma unroll
+    for (int k = 2; k <= KMAX; k++) {
+      if (k <= km) {
+        const int kk = (g.vvc_nk == 1) ? 1 : k;
+        const double hfac = c_vc.dz[k] / c2dtu;
+        C = A;
+        A = c_vc.afac_u[k] * g.VVC[(size_t)(kk - 1) * n2 + q];
+        if (k < kmu) D = hfac + A + B;
+        else if (k == kmu) D = hfac + B;
+        if (k <= kmu) {
+          E[k - 1] = A / D;
+          B = (hfac + B) * E[k - 1];
+          F1 = (hfac * Un[(size_t)(k - 1) * n2] + C * F1) / D;
+          F2 = (hfac * Vn[(size_t)(k - 1) * n2] + C * F2) / D;
+        } else {
+          E[k - 1] = 0.0;
+          F1 = 0.0;
+          F2 = 0.0;
+        }
+        Un[(size_t)(k - 1) * n2] = F1;
+        Vn[(size_t)(k - 1) * n2] = F2;
+      }
+    }
+    // back substitution; F1,F2 = F(km)
+#pragma unroll
+    for (int k = KMAX - 1; k >= 1; k--) {
+      if (k <= km - 1) {
+        double f1 = Un[(size_t)(k - 1) * n2], f2 = Vn[(size_t)(k - 1) * n2];
+        if (k < kmu) {
+          f1 = f1 + E[k - 1] * F1;
+          f2 = f2 + E[k - 1] * F2;
+          Un[(size_t)(k - 1) * n2] = f1;
+          Vn[(size_t)(k - 1) * n2] = f2;
+        }
+        F1 = f1;
+        F2 = f2;
+      }
+    }
+  }
+  if (!finish) return;
+  // U = Uold + dU ; remove the vertical mean ; KMU mask (baroclinic.F90:1077-1129)
+  const double hur = g.HUR[q];
+  double w1 = 0.0, w2 = 0.0;
+  for (int k = 1; k <= km; k++) {
+    const size_t o = (size_t)(k - 1) * n2;
+    const double u = UOLD[o + q] + Un[o], v = VOLD[o + q] + Vn[o];
+    Un[o] = u;
+    Vn[o] = v;
+    w1 = w1 + u * c_vc.dz[k];
+    w2 = w2 + v * c_vc.dz[k];
+  }
+  w1 = w1 * hur;
+  w2 = w2 * hur;
+  for (int k = 1; k <= km; k++) {
+    const size_t o = (size_t)(k - 1) * n2;
+    if (k <= kmu) {
+      Un[o] = Un[o] - w1;
+      Vn[o] = Vn[o] - w2;
+    } else {
+      Un[o] = 0.0;
+      Vn[o] = 0.0;
+    }
+  }
+}
+
+static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD,
+                         int implicit_vmix, int finish) {
+  GridView g = grid_view();
+  dim3 block(128, 1, 1), grid((unsigned)((G.nxg + 127) / 128), (unsigned)G.ny_local, 1);
+  auto k32 = momentum_finish_kernel<32>;
+  auto k64 = momentum_finish_kernel<64>;
+  auto kmx = momentum_finish_kernel<POP_KMAX>;
+  if (G.km <= 32) POP_LAUNCH(k32, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
+  else if (G.km <= 64) POP_LAUNCH(k64, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
+  else POP_LAUNCH(kmx, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
+  return pop_post_launch("momentum_finish");
+}
+
+int impvmixu_dev(double* UNEW, double* VNEW) {
+  ScopedTimer tm("VMIX_MOMENTUM_IMPLICIT");
+  return launch_finish(UNEW, VNEW, nullptr, nullptr, 1, 0);
+}
+int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD) {
+  return launch_finish(UNEW, VNEW, UOLD, VOLD, G.cfg.implicit_vertical_mix, 1);
+}
+
+// =====================================================================================
+// grad / div (operators.F90:126-192, :49-119)
+// =====================================================================================
+__global__ void grad_kernel(int k, double* __restrict__ GX, double* __restrict__ GY,
+                            const double* __restrict__ F, const int* __restrict__ KMU,
+                            const double* __restrict__ DXUR, const double* __restrict__ DYUR, int nxb,
+                            int nyb) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)nxb * nyb) return;
+  const int i = (int)(q % nxb), j = (int)(q / nxb);
+  double gx = 0.0, gy = 0.0;
+  if (i < nxb - 1 && j < nyb - 1 && k <= KMU[q]) {
+    const double f11 = F[q + nxb + 1], f00 = F[q], f01 = F[q + nxb], f10 = F[q + 1];
+    gx = DXUR[q] * 0.5 * (f11 - f00 - f01 + f10);
+    gy = DYUR[q] * 0.5 * (f11 - f00 + f01 - f10);
+  }
+  GX[q] = gx;
+  GY[q] = gy;
+}
+__global__ void div_kernel(int k, double* __restrict__ D, const double* __restrict__ UX,
+                           const double* __restrict__ UY, const int* __restrict__ KMT,
+                           const double* __restrict__ DXU, const double* __restrict__ DYU, int nxb,
+                           int nyb) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)nxb * nyb) return;
+  const int i = (int)(q % nxb), j = (int)(q / nxb);
+  double d = 0.0;
+  if (i >= 1 && j >= 1 && k <= KMT[q]) {
+    const size_t s = q - nxb, w = q - 1, sw = q - nxb - 1;
+    d = 0.5 * (UX[q] * DYU[q] + UX[s] * DYU[s] - UX[w] * DYU[w] - UX[sw] * DYU[sw] + UY[q] * DXU[q] +
+               UY[w] * DXU[w] - UY[s] * DXU[s] - UY[sw] * DXU[sw]);
+  }
+  D[q] = d;
+}
+
+int grad_dev(int k, double* GX, double* GY, const double* F) {
+  POP_LAUNCH(grad_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, k, GX, GY, F, fldi("KMU"), fld("DXUR"),
+             fld("DYUR"), G.nxb, G.nyb);
+  return pop_post_launch("grad");
+}
+int div_dev(int k, double* D, const double* UX, const double* UY) {
+  POP_LAUNCH(div_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, k, D, UX, UY, fldi("KMT"), fld("DXU"),
+             fld("DYU"), G.nxb, G.nyb);
+  return pop_post_launch("div");
+}

@@ -1,0 +1,300 @@
+// pop_step.cu -- time-step drivers on the library-resident state.
+//   dhdt                        surface_hgt.F90:131-286 (+ tgrid_to_ugrid, grid.F90:3362-3415)
+//   baroclinic_driver           baroclinic.F90:578-1210
+//   baroclinic_correct_adjust   baroclinic.F90:1217-1497
+//   step                        step_mod.F90:296-626, :634-640, :663-832
+// The reference loops over blocks and levels on the host and calls one operator per slab; here each
+// driver is a short sequence of fused column kernels plus the halo updates the reference issues at
+// the same points of the step.
+#include "pop_dev.cuh"
+
+// ------------------------------------------------------------------ dhdt
+__global__ void dhdt_kernel(double* __restrict__ DH, const double* __restrict__ Pc,
+                            const double* __restrict__ Po, const double* __restrict__ FW_OLD, double dtp,
+                            int sfc, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  double v;
+  if (sfc == POP_SFC_VARTHICK) v = (Pc[q] - Po[q]) / (POP_GRAV * dtp) - FW_OLD[q];
+  else if (sfc == POP_SFC_RIGID) v = 0.0;
+  else v = (Pc[q] - Po[q]) / (POP_GRAV * dtp);
+  DH[q] = v;
+}
+__global__ void t2u_kernel(double* __restrict__ AU, const double* __restrict__ AT,
+                           const double* __restrict__ AU0, const double* __restrict__ AUN,
+                           const double* __restrict__ AUE, const double* __restrict__ AUNE,
+                           const double* __restrict__ RCALCU, int nxb, int nyb) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)nxb * nyb) return;
+  const int i = (int)(q % nxb), j = (int)(q / nxb);
+  double v = 0.0;
+  if (i < nxb - 1 && j < nyb - 1)
+    v = AU0[q] * AT[q] + AUN[q] * AT[q + nxb] + AUE[q] * AT[q + 1] + AUNE[q] * AT[q + nxb + 1];
+  if (RCALCU[q] == 0.0) v = 0.0;
+  AU[q] = v;
+}
+int dhdt_dev() {
+  POP_LAUNCH(dhdt_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("DH"), fld_t("PSURF", G.curtime),
+             fld_t("PSURF", G.oldtime), fld("FW_OLD"), G.dtp, G.cfg.sfc_layer_type, G.n2);
+  POP_LAUNCH(t2u_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("DHU"), fld("DH"), fld("AU0"), fld("AUN"),
+             fld("AUE"), fld("AUNE"), fld("RCALCU"), G.nxb, G.nyb);
+  return pop_post_launch("dhdt");
+}
+
+// ------------------------------------------------------------------ baroclinic_driver
+int baroclinic_driver_dev() {
+  ScopedTimer tm("BAROCLINIC");
+  const int o = G.oldtime, c = G.curtime, n_ = G.newtime, mx = G.mixtime;
+  const bool pavg = G.cfg.lpressure_avg && G.leapfrogts;
+  const bool varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
+  POP_TRY(vmix_coeffs_dev(1, G.km, fld_t("TRACER", mx), fld_t("UVEL", mx), fld_t("VVEL", mx), fld_t("RHO", mx)));
+  {
+    ScopedTimer t2("TRACER_UPDATE");
+    TracerIO io;
+    io.TCUR = fld_t("TRACER", c); io.TMIX = fld_t("TRACER", mx); io.TOLD = fld_t("TRACER", o);
+    io.UCUR = fld_t("UVEL", c); io.VCUR = fld_t("VVEL", c);
+    io.STF = fld("STF"); io.TFW = fld("TFW"); io.DH = fld("DH");
+    io.POLD = fld_t("PSURF", o); io.PCUR = fld_t("PSURF", c);
+    io.TNEW = fld_t("TRACER", n_);
+    io.WTK = nullptr;
+    POP_TRY(tracer_column(TR_FULL, 0, io));
+  }
+  if (G.cfg.implicit_vertical_mix) {  // baroclinic.F90:878-896
+    if (!varthick)
+      POP_TRY(impvmixt_dev(fld_t("TRACER", n_), fld_t("TRACER", o), fld_t("PSURF", c), nullptr, 1, G.nt, 0));
+    else if (pavg)
+      POP_TRY(impvmixt_dev(fld_t("TRACER", n_), fld_t("TRACER", o), fld_t("PSURF", c), nullptr, 1, 2, 0));
+  }
+  if (pavg) {
+    // T,S at the new time are needed in the ghost cells for the pressure average: baroclinic.F90:919-935
+    POP_TRY(halo_update(fld_t("TRACER", n_), 2 * G.km, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+    POP_TRY(state_3d(fld_t("TRACER", n_), fld_t("RHO", n_)));  // baroclinic.F90:981-985
+  }
+  {
+    ScopedTimer t2("CLINIC");
+    MomentumIO io;
+    io.UCUR = fld_t("UVEL", c); io.VCUR = fld_t("VVEL", c); io.UOLD = fld_t("UVEL", o); io.VOLD = fld_t("VVEL", o);
+    io.UMIX = fld_t("UVEL", mx); io.VMIX = fld_t("VVEL", mx);
+    io.RHOOLD = fld_t("RHO", o); io.RHOCUR = fld_t("RHO", c); io.RHONEW = fld_t("RHO", n_);
+    io.SMF = fld("SMF"); io.DHU = fld("DHU");
+    io.UNEW = fld_t("UVEL", n_); io.VNEW = fld_t("VVEL", n_); io.ZX = fld("ZX"); io.ZY = fld("ZY");
+    io.WUK = nullptr;
+    POP_TRY(momentum_column(MO_FULL, 0, io));
+    POP_TRY(momentum_finish(io.UNEW, io.VNEW, io.UOLD, io.VOLD));
+  }
+  return POP_SUCCESS;
+}
+
+// ------------------------------------------------------------------ baroclinic_correct_adjust
+struct SfcArgs {
+  double *Tn;
+  const double *To, *Tc, *Pn, *Pc, *Po, *Pm;
+  double* RHS;
+  const int* KMT;
+  size_t n2, n3;
+  double dz1;
+  int nt, mode;
+};
+// surface-layer corrections of baroclinic.F90:1283-1420; one thread per (i,j), loop over tracers
+__global__ void sfc_correct_kernel(SfcArgs a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n2) return;
+  const bool ocean = a.KMT[q] > 0;
+  const double Pn = a.Pn[q], Pc = a.Pc[q], Po = a.Po[q], Pm = a.Pm[q];
+  for (int n = 0; n < a.nt; n++) {
+    double* tn = a.Tn + (size_t)n * a.n3 + q;
+    const double to = a.To[(size_t)n * a.n3 + q], tc = a.Tc[(size_t)n * a.n3 + q];
+    switch (a.mode) {
+      case 0:  // implicit vmix, pressure averaging: RHS for T,S (:1283-1296), passive tracers (:1303-1312)
+        if (n < 2)
+          a.RHS[(size_t)n * a.n2 + q] =
+              ocean ? ((2.0 * tc - to) * (Pc - Po) - *tn * (Pn - Pc)) / (POP_GRAV * a.dz1) : 0.0;
+        else if (ocean)
+          *tn = *tn - to * (Pn - Po) / (POP_GRAV * a.dz1);
+        break;
+      case 1:  // implicit vmix, no pressure averaging (:1327-1337)
+        if (ocean) *tn = *tn - to * (Pn - Pm) / (POP_GRAV * a.dz1);
+        break;
+      case 2:  // explicit vmix, pressure averaging (:1355-1392)
+        if (n < 2)
+          *tn = ocean ? (*tn * (a.dz1 + Pc / POP_GRAV) + (2.0 * tc - to) * (Pc - Po) / POP_GRAV) /
+                            (a.dz1 + Pn / POP_GRAV)
+                      : 0.0;
+        else
+          *tn = ocean ? (to * (a.dz1 + Po / POP_GRAV) + a.dz1 * *tn) / (a.dz1 + Pn / POP_GRAV) : 0.0;
+        break;
+      default:  // explicit vmix, no pressure averaging (:1398-1412)
+        *tn = ocean ? (to * (a.dz1 + Pm / POP_GRAV) + a.dz1 * *tn) / (a.dz1 + Pn / POP_GRAV) : 0.0;
+        break;
+    }
+  }
+}
+
+int baroclinic_correct_adjust_dev() {
+  ScopedTimer tm("BAROCLINIC");
+  const int o = G.oldtime, c = G.curtime, n_ = G.newtime, mx = G.mixtime;
+  const bool pavg = G.cfg.lpressure_avg && G.leapfrogts;
+  double* Tn = fld_t("TRACER", n_);
+  if (G.cfg.sfc_layer_type == POP_SFC_VARTHICK) {
+    SfcArgs a;
+    a.Tn = Tn; a.To = fld_t("TRACER", o); a.Tc = fld_t("TRACER", c);
+    a.Pn = fld_t("PSURF", n_); a.Pc = fld_t("PSURF", c); a.Po = fld_t("PSURF", o); a.Pm = fld_t("PSURF", mx);
+    a.RHS = fld("RHS1"); a.KMT = fldi("KMT"); a.n2 = G.n2; a.n3 = G.n3; a.dz1 = G.vc.dz[1]; a.nt = G.nt;
+    a.mode = G.cfg.implicit_vertical_mix ? (pavg ? 0 : 1) : (pavg ? 2 : 3);
+    POP_LAUNCH(sfc_correct_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, a);
+    if (G.cfg.implicit_vertical_mix) {
+      if (pavg) {
+        POP_TRY(impvmixt_dev(Tn, nullptr, a.Pn, a.RHS, 1, 2, 1));
+        POP_TRY(impvmixt_dev(Tn, a.To, a.Pn, nullptr, 3, G.nt, 0));
+      } else {
+        POP_TRY(impvmixt_dev(Tn, a.To, a.Pn, nullptr, 1, G.nt, 0));
+      }
+    }
+  }
+  // convad: convection_type = 'diffusion' returns immediately (vertical_mix.F90:1925)
+  POP_TRY(state_3d(Tn, fld_t("RHO", n_)));  // baroclinic.F90:1476-1482
+  return pop_post_launch("baroclinic_correct_adjust");
+}
+
+// ------------------------------------------------------------------ step
+__global__ void add_barotropic_kernel(double* __restrict__ U, double* __restrict__ V,
+                                      const double* __restrict__ UB, const double* __restrict__ VB,
+                                      const int* __restrict__ KMU, size_t n2) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y + 1;
+  if (q >= n2) return;
+  if (k <= KMU[q]) {
+    const size_t c = (size_t)(k - 1) * n2 + q;
+    U[c] = U[c] + UB[q];
+    V[c] = V[c] + VB[q];
+  }
+}
+__global__ void pguess_kernel(double* __restrict__ PG, const double* __restrict__ Pn,
+                              const double* __restrict__ Pc, const double* __restrict__ Po, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) PG[q] = 3.0 * (Pn[q] - Pc[q]) + Po[q];
+}
+// averaging step (step_mod.F90:663-796): old <- (old+cur)/2 then cur <- (cur+new)/2
+__global__ void avg_kernel(double* __restrict__ Fo, double* __restrict__ Fc, const double* __restrict__ Fn,
+                           size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double c = Fc[q];
+  Fo[q] = 0.5 * (Fo[q] + c);
+  Fc[q] = 0.5 * (c + Fn[q]);
+}
+__global__ void avg_fw_kernel(double* __restrict__ FW_OLD, const double* __restrict__ FW, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) FW_OLD[q] = 0.5 * (FW[q] + FW_OLD[q]);
+}
+struct AvgSfc {
+  double *To, *Tc, *Po, *Pc, *PG;
+  const double *Tn, *Pn;
+  size_t n2, n3;
+  double dz1;
+  int nt, varthick;
+};
+__global__ void avg_surface_kernel(AvgSfc a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n2) return;
+  const double Po = a.Po[q], Pc = a.Pc[q], Pn = a.Pn[q];
+  if (a.varthick) {
+    const double PFO = 0.5 * (Po + Pc), PFC = 0.5 * (Pc + Pn);
+    for (int n = 0; n < a.nt; n++) {
+      const size_t c = (size_t)n * a.n3 + q;
+      const double to = a.To[c], tc = a.Tc[c], tn = a.Tn[c];
+      const double wmin = fmin(to, tc), wmax = fmax(to, tc);
+      double v = 0.5 * ((a.dz1 + Po / POP_GRAV) * to + (a.dz1 + Pc / POP_GRAV) * tc);
+      v = v / (a.dz1 + PFO / POP_GRAV);
+      if (v < wmin) v = wmin;
+      if (v > wmax) v = wmax;
+      const double wmin2 = fmin(tc, tn), wmax2 = fmax(tc, tn);
+      double w = 0.5 * ((a.dz1 + Pc / POP_GRAV) * tc + (a.dz1 + Pn / POP_GRAV) * tn);
+      w = w / (a.dz1 + PFC / POP_GRAV);
+      if (w < wmin2) w = wmin2;
+      if (w > wmax2) w = wmax2;
+      a.To[c] = v;
+      a.Tc[c] = w;
+    }
+    a.Po[q] = PFO;
+    a.Pc[q] = PFC;
+  } else {
+    for (int n = 0; n < a.nt; n++) {
+      const size_t c = (size_t)n * a.n3 + q;
+      const double tc = a.Tc[c];
+      a.To[c] = 0.5 * (a.To[c] + tc);
+      a.Tc[c] = 0.5 * (tc + a.Tn[c]);
+    }
+    a.Po[q] = 0.5 * (Po + Pc);
+    a.Pc[q] = 0.5 * (Pc + Pn);
+  }
+  a.PG[q] = 0.5 * (a.PG[q] + Pn);
+}
+// tracer levels 2..km of the averaging step, all tracers
+__global__ void avg_tracer_kernel(double* __restrict__ To, double* __restrict__ Tc,
+                                  const double* __restrict__ Tn, size_t n2, int km) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  const int z = blockIdx.y;  // 0 .. nt*km-1
+  if (z % km == 0) return;   // level 1 is handled by avg_surface_kernel
+  const size_t c = (size_t)z * n2 + q;
+  const double tc = Tc[c];
+  To[c] = 0.5 * (To[c] + tc);
+  Tc[c] = 0.5 * (tc + Tn[c]);
+}
+
+int step_dev(int ts_type) {
+  POP_REQUIRE(G.grid_set, "pop_step: grid not set");
+  POP_REQUIRE(ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER || ts_type == POP_TS_AVG,
+              "pop_step: unknown time-step type %d (matsuno steps are not supported)", ts_type);
+  ScopedTimer tm("STEP");
+  POP_TRY(set_timestep(ts_type));
+  const int km = G.km;
+  POP_TRY(dhdt_dev());
+  POP_TRY(baroclinic_driver_dev());
+  POP_TRY(halo_update(fld("ZX"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));  // step_mod.F90:405-417
+  POP_TRY(halo_update(fld("ZY"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(barotropic_driver_dev());
+  POP_TRY(baroclinic_correct_adjust_dev());
+  const int n_ = G.newtime, c = G.curtime, o = G.oldtime;
+  // step_mod.F90:467-560
+  POP_TRY(halo_update(fld_t("UBTROP", n_), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(halo_update(fld_t("VBTROP", n_), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(halo_update(fld_t("UVEL", n_), km, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(halo_update(fld_t("VVEL", n_), km, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
+  POP_TRY(halo_update(fld_t("RHO", n_), km, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+  POP_TRY(halo_update(fld_t("TRACER", n_), km * G.nt, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+  {  // step_mod.F90:581-592
+    dim3 grid(ew_grid(G.n2), (unsigned)km, 1);
+    POP_LAUNCH(add_barotropic_kernel, grid, POP_EW_THREADS, 0, fld_t("UVEL", n_), fld_t("VVEL", n_),
+               fld_t("UBTROP", n_), fld_t("VBTROP", n_), fldi("KMU"), G.n2);
+  }
+  POP_LAUNCH(pguess_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("PGUESS"), fld_t("PSURF", n_),
+             fld_t("PSURF", c), fld_t("PSURF", o), G.n2);  // step_mod.F90:634-640
+  if (G.avg_ts) {
+    for (const char* f : {"UBTROP", "VBTROP", "GRADPX", "GRADPY"})
+      POP_LAUNCH(avg_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld_t(f, o), fld_t(f, c), fld_t(f, n_), G.n2);
+    POP_LAUNCH(avg_fw_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("FW_OLD"), fld("FW"), G.n2);
+    for (const char* f : {"UVEL", "VVEL"})
+      POP_LAUNCH(avg_kernel, ew_grid(G.n3), POP_EW_THREADS, 0, fld_t(f, o), fld_t(f, c), fld_t(f, n_), G.n3);
+    dim3 gt(ew_grid(G.n2), (unsigned)(km * G.nt), 1);
+    POP_LAUNCH(avg_tracer_kernel, gt, POP_EW_THREADS, 0, fld_t("TRACER", o), fld_t("TRACER", c),
+               fld_t("TRACER", n_), G.n2, km);
+    AvgSfc a;
+    a.To = fld_t("TRACER", o); a.Tc = fld_t("TRACER", c); a.Tn = fld_t("TRACER", n_);
+    a.Po = fld_t("PSURF", o); a.Pc = fld_t("PSURF", c); a.Pn = fld_t("PSURF", n_); a.PG = fld("PGUESS");
+    a.n2 = G.n2; a.n3 = G.n3; a.dz1 = G.vc.dz[1]; a.nt = G.nt;
+    a.varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
+    POP_LAUNCH(avg_surface_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, a);
+    POP_TRY(state_3d(fld_t("TRACER", o), fld_t("RHO", o)));
+    POP_TRY(state_3d(fld_t("TRACER", c), fld_t("RHO", c)));
+  } else {
+    // FW_OLD = FW; rotate the time levels (step_mod.F90:804-830): an index swap, no data moves
+    POP_CHECK_CUDA(cudaMemcpyAsync(fld("FW_OLD"), fld("FW"), sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+    const int tmp = G.oldtime;
+    G.oldtime = G.curtime;
+    G.curtime = G.newtime;
+    G.newtime = tmp;
+  }
+  return pop_post_launch("step");
+}

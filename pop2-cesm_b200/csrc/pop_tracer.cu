@@ -1,0 +1,565 @@
+// pop_tracer.cu -- the tracer half of the baroclinic step.
+//
+//   tracer_column : ONE fused column kernel for everything tracer_update does per level
+//                   (baroclinic.F90:1902-2306): hdifft del2/del4 (hmix_del2.F90:970-1144,
+//                   hmix_del4.F90:889-1106), comp_flux_vel + advt centered/upwind3
+//                   (advection.F90:1970-2132, :2139-2306, :2313-2677), vdifft
+//                   (vertical_mix.F90:691-847) and the TNEW assembly (baroclinic.F90:2212-2300).
+//                   The reference calls these once per (block, level) slab and carries WTK, VTF and
+//                   AUX between calls; here a thread owns an (i,j) column, marches k and keeps the
+//                   carried quantities in registers.  The same kernel, restricted to one level and
+//                   one term, implements the slab entry points pop_advt / pop_hdifft / pop_vdifft.
+//   impvmixt_dev  : implicit vertical mixing of tracers (vertical_mix.F90:1164-1382) and its
+//                   corrector (:1460-1672): one column per thread, Thomas coefficients E(k) resident
+//                   in registers, the solution streamed in place through the output array.
+//
+// Data movement: per level a CTA stages the (32+4) x (8+4) halo tile of each tracer (and the
+// U*DYU, V*DXU flux operands) in shared memory; the k-invariant masks/coefficients (KMT, DTN..DTW,
+// AHF) are staged once per CTA for the whole column march, so 2-d arrays cost ~1/km of a 3-d field.
+#include "pop_state.cuh"
+
+#define NTC 2  // tracers processed per pass of the column kernel
+
+struct TracerArgs {
+  GridView g;
+  const double *TCUR, *TMIX, *TOLD, *UCUR, *VCUR, *STF, *TFW, *DH, *POLD, *PCUR;
+  double* OUT;   // FULL: TRACER(new) (nxb,nyb,km,nt); slab modes: (nxb,nyb,nt)
+  double* WTK;   // slab modes: carried vertical velocity at the top of level k (in/out)
+  double *VTF, *AUX;  // slab modes: carried fluxes (nxb,nyb,nt)
+  int k0, k1;    // level range (1-based, inclusive)
+  int n0, nn;    // tracers n0 .. n0+nn-1 (0-based)
+  int adv[NTC];  // advection scheme of each tracer of this pass
+  int hmix, lvariable_hmixt, varthick, implicit_vmix, predictor;
+  double ah;
+};
+
+// masked 5-point coefficients at tile point (ii,jj): hmix_del2.F90:1064-1078 / hmix_del4.F90:1014-1023
+struct Coef5 {
+  double cc, cn, cs, ce, cw;
+};
+__device__ __forceinline__ Coef5 tracer_coef(const int* s_kmt, const double* s_dtn, const double* s_dts,
+                                             const double* s_dte, const double* s_dtw, int ii, int jj,
+                                             int k) {
+  const int q = TIX(ii, jj);
+  const int kmt = s_kmt[q];
+  Coef5 c;
+  c.cn = (k <= s_kmt[TIX(ii, jj + 1)] && k <= kmt) ? s_dtn[q] : 0.0;
+  c.cs = (k <= s_kmt[TIX(ii, jj - 1)] && k <= kmt) ? s_dts[q] : 0.0;
+  c.ce = (k <= s_kmt[TIX(ii + 1, jj)] && k <= kmt) ? s_dte[q] : 0.0;
+  c.cw = (k <= s_kmt[TIX(ii - 1, jj)] && k <= kmt) ? s_dtw[q] : 0.0;
+  c.cc = -(c.cn + c.cs + c.ce + c.cw);
+  return c;
+}
+__device__ __forceinline__ double lap5(const Coef5& c, const double* t, int ii, int jj) {
+  return c.cc * t[TIX(ii, jj)] + c.cn * t[TIX(ii, jj + 1)] + c.cs * t[TIX(ii, jj - 1)] +
+         c.ce * t[TIX(ii + 1, jj)] + c.cw * t[TIX(ii - 1, jj)];
+}
+
+template <int MODE, bool DEL4, bool UPW>
+__global__ void __launch_bounds__(POP_NTHREADS)
+tracer_column_kernel(const TracerArgs a) {
+  POP_DYN_SMEM(smem_raw);
+  double* sm = (double*)smem_raw;
+  double* s_dtn = sm;
+  double* s_dts = s_dtn + POP_TN;
+  double* s_dte = s_dts + POP_TN;
+  double* s_dtw = s_dte + POP_TN;
+  double* s_ahf = s_dtw + POP_TN;
+  double* s_ud = s_ahf + POP_TN;
+  double* s_vd = s_ud + POP_TN;
+  double* s_tc = s_vd + POP_TN;            // [NTC][TN]
+  double* s_tm = s_tc + NTC * POP_TN;      // [NTC][TN]
+  double* s_d2 = s_tm + NTC * POP_TN;      // [NTC][TN]
+  int* s_kmt = (int*)(s_d2 + NTC * POP_TN);
+
+  const GridView& g = a.g;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
+  const int i0 = (g.ib - 1) + blockIdx.x * POP_BX;  // 0-based index of tile column 0
+  const int j0 = (g.jb - 1) + blockIdx.y * POP_BY;
+  const int i = i0 + tx, j = j0 + ty;                // 0-based
+  const bool active = (i <= g.ie - 1) && (j <= g.je - 1);
+  const size_t q = (size_t)j * g.nxb + i;
+  const size_t n2 = g.n2;
+  const int km = g.km, nxb = g.nxb, nyb = g.nyb;
+  const bool same_mix = (a.TMIX == a.TCUR);
+  constexpr bool DO_ADV = (MODE == TR_FULL || MODE == TR_ADVT);
+  constexpr bool DO_HMIX = (MODE == TR_FULL || MODE == TR_HDIFFT);
+  constexpr bool DO_VDIF = (MODE == TR_FULL || MODE == TR_VDIFFT);
+  constexpr int HA = UPW ? 2 : 1;   // halo of the advected tracer tile
+  constexpr int HM = DEL4 ? 2 : 1;  // halo of the mixed tracer tile
+
+  // ---- k-invariant staging
+  if (DO_HMIX) {
+    tile_load_i(s_kmt, g.KMT, i0, j0, nxb, nyb, -2, POP_BX + 1, -2, POP_BY + 1, tid);
+    tile_load(s_dtn, g.DTN, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    tile_load(s_dts, g.DTS, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    tile_load(s_dte, g.DTE, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    tile_load(s_dtw, g.DTW, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+    if (DEL4 && a.lvariable_hmixt) tile_load(s_ahf, g.AHF, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+  }
+  int kmt = 0;
+  double tarea_r = 0.0, tarea_rw = 0.0, tarea_rs = 0.0;
+  if (active) {
+    kmt = g.KMT[q];
+    tarea_r = g.TAREA_R[q];
+    if (UPW) {
+      tarea_rw = g.TAREA_R[q - 1];
+      tarea_rs = g.TAREA_R[q - nxb];
+    }
+  }
+  // ---- carried state
+  double wtk = 0.0;
+  double tc_m[NTC], told_c[NTC], vtf[NTC], aux[NTC];
+#pragma unroll
+  for (int m = 0; m < NTC; m++) tc_m[m] = told_c[m] = vtf[m] = aux[m] = 0.0;
+  if (active) {
+    if (DO_ADV) wtk = (a.k0 == 1 && MODE == TR_FULL) ? a.DH[q] : (MODE == TR_FULL ? 0.0 : a.WTK[q]);
+#pragma unroll
+    for (int m = 0; m < NTC; m++) {
+      if (m >= a.nn) continue;
+      const int n = a.n0 + m;
+      if (DO_ADV && a.k0 > 1) tc_m[m] = a.TCUR[((size_t)n * km + (a.k0 - 2)) * n2 + q];
+      if (DO_VDIF) {
+        told_c[m] = a.TOLD[((size_t)n * km + (a.k0 - 1)) * n2 + q];
+        if (a.k0 > 1) vtf[m] = a.VTF[(size_t)n * n2 + q];
+      }
+      if (DO_ADV && UPW && a.k0 > 1) aux[m] = a.AUX[(size_t)n * n2 + q];
+    }
+  }
+
+  for (int k = a.k0; k <= a.k1; k++) {
+    __syncthreads();
+    // ---- stage level k
+    if (DO_ADV) {
+      tile_load_prod(s_ud, a.UCUR + (size_t)(k - 1) * n2, g.DYU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+      tile_load_prod(s_vd, a.VCUR + (size_t)(k - 1) * n2, g.DXU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+    }
+#pragma unroll
+    for (int m = 0; m < NTC; m++) {
+      if (m >= a.nn) continue;
+      const size_t lev = ((size_t)(a.n0 + m) * km + (k - 1)) * n2;
+      if (DO_ADV) tile_load(s_tc + m * POP_TN, a.TCUR + lev, i0, j0, nxb, nyb, -HA, POP_BX - 1 + HA, -HA, POP_BY - 1 + HA, tid);
+      if (DO_HMIX && !(same_mix && DO_ADV && HA >= HM))
+        tile_load(s_tm + m * POP_TN, a.TMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+    }
+    __syncthreads();
+    if (DO_HMIX && DEL4) {
+      // D2TK = AHF * L(T) on the first halo ring (hmix_del4.F90:1025-1046)
+      constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
+      for (int p = tid; p < npts; p += POP_NTHREADS) {
+        const int jj = p / w - 1, ii = p % w - 1;
+        const Coef5 c = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, ii, jj, k);
+#pragma unroll
+        for (int m = 0; m < NTC; m++) {
+          if (m >= a.nn) continue;
+          const double* tmix = (same_mix && DO_ADV && HA >= HM) ? s_tc + m * POP_TN : s_tm + m * POP_TN;
+          const double v = lap5(c, tmix, ii, jj);
+          s_d2[m * POP_TN + TIX(ii, jj)] = a.lvariable_hmixt ? s_ahf[TIX(ii, jj)] * v : v;
+        }
+      }
+      __syncthreads();
+    }
+    if (!active) continue;
+
+    // ---- flux velocities and the vertical velocity at the bottom of the level
+    double ute = 0.0, utw = 0.0, vtn = 0.0, vts = 0.0, wtkb = 0.0;
+    if (DO_ADV) {
+      ute = 0.5 * (s_ud[TIX(tx, ty)] + s_ud[TIX(tx, ty - 1)]);
+      utw = 0.5 * (s_ud[TIX(tx - 1, ty)] + s_ud[TIX(tx - 1, ty - 1)]);
+      vtn = 0.5 * (s_vd[TIX(tx, ty)] + s_vd[TIX(tx - 1, ty)]);
+      vts = 0.5 * (s_vd[TIX(tx, ty - 1)] + s_vd[TIX(tx - 1, ty - 1)]);
+      if (k < km) {
+        const double FC = (vtn - vts + ute - utw) * tarea_r;
+        wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
+      }
+    }
+    Coef5 cc5;
+    if (DO_HMIX) cc5 = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, tx, ty, k);
+
+#pragma unroll
+    for (int m = 0; m < NTC; m++) {
+      if (m >= a.nn) continue;
+      const int n = a.n0 + m;  // 0-based tracer index
+      const size_t lev = ((size_t)n * km + (k - 1)) * n2 + q;
+      const double* tc = s_tc + m * POP_TN;
+      // ---- horizontal mixing
+      double hd = 0.0;
+      if (DO_HMIX) {
+        if (DEL4) hd = a.ah * lap5(cc5, s_d2 + m * POP_TN, tx, ty);
+        else {
+          const double* tmix = (same_mix && DO_ADV && HA >= HM) ? tc : s_tm + m * POP_TN;
+          hd = a.ah * lap5(cc5, tmix, tx, ty);
+        }
+      }
+      // ---- advection
+      double L = 0.0;
+      if (DO_ADV) {
+        const double T = tc[TIX(tx, ty)];
+        const double Tp = (k < km) ? a.TCUR[lev + n2] : 0.0;
+        if (a.adv[m] == POP_TADVECT_CENTERED) {  // advection.F90:2243-2301
+          L = 0.5 *
+              ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
+               ute * tc[TIX(tx + 1, ty)] - utw * tc[TIX(tx - 1, ty)]) *
+              tarea_r;
+          if (k == 1) {
+            if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
+          } else {
+            L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+          }
+          if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+        } else if (UPW) {  // upwind3: advection.F90:2387-2476 + hupw3 :2543-2672
+          const double CE = ute * tarea_r, CW = -utw * tarea_r, CN = vtn * tarea_r, CS = -vts * tarea_r;
+          const double CEw = utw * tarea_rw;  // CE(i-1,j) = UTE(i-1,j)*TAREA_R(i-1,j)
+          const double CNs = vts * tarea_rs;  // CN(i,j-1)
+          double TE[2], TN[2];
+#pragma unroll
+          for (int s = 0; s < 2; s++) {  // s=0: face (i,j); s=1: face (i-1,j)
+            const int ii = tx - s;
+            const size_t qq = q - s;
+            const int kE = g.KMT[qq + 1], kW = g.KMT[qq - 1], kEE = g.KMT[qq + 2];
+            double work, ap, bp, gp, am, bm, dm;
+            if (k <= kE) { work = g.TBETXP[qq]; ap = g.TALFXP[qq]; }
+            else { work = g.TBETXP[qq] + g.TALFXP[qq]; ap = 0.0; }
+            if (k <= kW) { bp = work; gp = g.TGAMXP[qq]; }
+            else { bp = work + g.TGAMXP[qq]; gp = 0.0; }
+            if (k <= kEE) { am = g.TALFXM[qq]; dm = g.TDELXM[qq]; }
+            else { am = g.TALFXM[qq] + g.TDELXM[qq]; dm = 0.0; }
+            bm = g.TBETXM[qq];
+            const double cface = s ? CEw : CE;
+            if (cface > 0.0) TE[s] = ap * tc[TIX(ii + 1, ty)] + bp * tc[TIX(ii, ty)] + gp * tc[TIX(ii - 1, ty)];
+            else TE[s] = am * tc[TIX(ii + 1, ty)] + bm * tc[TIX(ii, ty)] + dm * tc[TIX(ii + 2, ty)];
+          }
+#pragma unroll
+          for (int s = 0; s < 2; s++) {  // s=0: face (i,j); s=1: face (i,j-1)
+            const int jj = ty - s;
+            const size_t qq = q - (size_t)s * nxb;
+            const int kN = g.KMT[qq + nxb], kS = g.KMT[qq - nxb], kNN = g.KMT[qq + 2 * (size_t)nxb];
+            double work, ap, bp, gp, am, bm, dm;
+            if (k <= kN) { work = g.TBETYP[qq]; ap = g.TALFYP[qq]; }
+            else { work = g.TBETYP[qq] + g.TALFYP[qq]; ap = 0.0; }
+            if (k <= kS) { bp = work; gp = g.TGAMYP[qq]; }
+            else { bp = work + g.TGAMYP[qq]; gp = 0.0; }
+            if (k <= kNN) { am = g.TALFYM[qq]; dm = g.TDELYM[qq]; }
+            else { am = g.TALFYM[qq] + g.TDELYM[qq]; dm = 0.0; }
+            bm = g.TBETYM[qq];
+            const double cface = s ? CNs : CN;
+            if (cface > 0.0) TN[s] = ap * tc[TIX(tx, jj + 1)] + bp * tc[TIX(tx, jj)] + gp * tc[TIX(tx, jj - 1)];
+            else TN[s] = am * tc[TIX(tx, jj + 1)] + bm * tc[TIX(tx, jj)] + dm * tc[TIX(tx, jj + 2)];
+          }
+          L = CE * TE[0] + CW * TE[1];
+          L = L + CN * TN[0] + CS * TN[1];
+          // vertical: advection.F90:2402-2476
+          double AZM, DZM;
+          if (k < kmt - 1) { AZM = c_vc.talfzm[k]; DZM = c_vc.tdelzm[k]; }
+          else { AZM = c_vc.talfzm[k] + c_vc.tdelzm[k]; DZM = 0.0; }
+          double auxb;
+          if (k < km - 1 && k > 1) {
+            const double Tpp = a.TCUR[lev + 2 * n2];
+            const double TPLUS = c_vc.talfzp[k] * Tp + c_vc.tbetzp[k] * T + c_vc.tgamzp[k] * tc_m[m];
+            const double TMINUS = AZM * Tp + c_vc.tbetzm[k] * T + DZM * Tpp;
+            auxb = (wtkb - fabs(wtkb)) * TPLUS + (wtkb + fabs(wtkb)) * TMINUS;
+          } else if (k == 1) {
+            const double Tpp = (k + 2 <= km) ? a.TCUR[lev + 2 * n2] : 0.0;
+            const double TPLUS = c_vc.talfzp[k] * Tp + c_vc.tbetzp[k] * T;
+            const double TMINUS = AZM * Tp + c_vc.tbetzm[k] * T + DZM * Tpp;
+            auxb = (wtkb - fabs(wtkb)) * TPLUS + (wtkb + fabs(wtkb)) * TMINUS;
+          } else if (k == km - 1) {
+            const double TPLUS = c_vc.talfzp[k] * Tp + c_vc.tbetzp[k] * T + c_vc.tgamzp[k] * tc_m[m];
+            const double TMINUS = AZM * Tp + c_vc.tbetzm[k] * T;
+            auxb = (wtkb - fabs(wtkb)) * TPLUS + (wtkb + fabs(wtkb)) * TMINUS;
+          } else {
+            auxb = 0.0;
+          }
+          if (k == 1) {
+            if (!a.varthick) {
+              const double FLUX_T = c_vc.dzr[k] * wtk * T;
+              L = L + FLUX_T - c_vc.dz2r[k] * auxb;
+            } else {
+              L = L - c_vc.dz2r[k] * auxb;
+            }
+          } else {
+            L = L + c_vc.dz2r[k] * (aux[m] - auxb);
+          }
+          aux[m] = auxb;
+        }
+        tc_m[m] = T;
+      }
+      // ---- explicit vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
+      double vd = 0.0;
+      if (DO_VDIF) {
+        const int mt2 = (n + 1 < g.vdc_nd) ? n + 1 : g.vdc_nd;
+        const int kk = (g.vdc_nk == 1) ? 1 : k;
+        const double vdc = g.VDC[((size_t)(mt2 - 1) * g.vdc_nk + (kk - g.vdc_k0)) * n2 + q];
+        const double told_p = (k < km) ? a.TOLD[lev + n2] : told_c[m];
+        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
+        const double VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
+        vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        vtf[m] = VTFB;
+        told_c[m] = told_p;
+      }
+      // ---- output
+      if (MODE == TR_HDIFFT) a.OUT[(size_t)n * n2 + q] = hd;
+      else if (MODE == TR_ADVT) a.OUT[(size_t)n * n2 + q] = L;
+      else if (MODE == TR_VDIFFT) a.OUT[(size_t)n * n2 + q] = vd;
+      else {  // tracer_update: baroclinic.F90:1993-2300
+        double FT = 0.0 + hd;
+        FT = FT - L;
+        FT = FT + vd;
+        if (k == 1 && a.varthick) FT = FT + c_vc.dzr[1] * a.TFW[(size_t)n * n2 + q];
+        FT = FT + 0.0;  // source terms are zero on this path
+        const bool pred = a.predictor && k == 1 && n < 2;
+        double* out = a.OUT + lev;
+        if (a.implicit_vmix) {
+          if (pred) {
+            if (kmt > 0)
+              *out = c_vc.c2dtt[1] * FT -
+                     2.0 * tc[TIX(tx, ty)] * (a.PCUR[q] - a.POLD[q]) / (POP_GRAV * c_vc.dz[1]);
+          } else {
+            *out = (k <= kmt) ? c_vc.c2dtt[k] * FT : 0.0;
+          }
+        } else {
+          const double To = a.TOLD[lev];
+          if (a.varthick && k == 1) {
+            if (pred)
+              *out = (kmt > 0) ? To + (1.0 / (1.0 + a.PCUR[q] / (POP_GRAV * c_vc.dz[1]))) *
+                                          (c_vc.c2dtt[1] * FT - 2.0 * tc[TIX(tx, ty)] * (a.PCUR[q] - a.POLD[q]) /
+                                                                    (POP_GRAV * c_vc.dz[1]))
+                               : 0.0;
+            else
+              *out = (k <= kmt) ? c_vc.c2dtt[k] * FT : 0.0;
+          } else {
+            *out = (k <= kmt) ? To + c_vc.c2dtt[k] * FT : 0.0;
+          }
+        }
+      }
+    }
+    if (DO_ADV) wtk = wtkb;  // advection.F90:1960
+  }
+  // ---- hand the carried state back to the slab caller
+  if (MODE != TR_FULL && active) {
+    if (MODE == TR_ADVT) a.WTK[q] = wtk;
+#pragma unroll
+    for (int m = 0; m < NTC; m++) {
+      if (m >= a.nn) continue;
+      const int n = a.n0 + m;
+      if (MODE == TR_VDIFFT) a.VTF[(size_t)n * n2 + q] = vtf[m];
+      if (MODE == TR_ADVT && UPW) a.AUX[(size_t)n * n2 + q] = aux[m];
+    }
+  }
+}
+
+static size_t tracer_smem_bytes() { return sizeof(double) * POP_TN * (7 + 3 * NTC) + sizeof(int) * POP_TN; }
+
+template <int MODE>
+static int launch_tracer(const TracerArgs& a, bool del4, bool upw) {
+  void (*kfn)(const TracerArgs) = nullptr;
+  if (del4 && upw) kfn = tracer_column_kernel<MODE, true, true>;
+  else if (del4) kfn = tracer_column_kernel<MODE, true, false>;
+  else if (upw) kfn = tracer_column_kernel<MODE, false, true>;
+  else kfn = tracer_column_kernel<MODE, false, false>;
+  const size_t smem = tracer_smem_bytes();
+#ifndef POP_EMUL
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  POP_LAUNCH(kfn, col_grid(G.nxg, G.ny_local), col_block(), smem, a);
+  return POP_SUCCESS;
+}
+
+int tracer_column(int mode, int k, const TracerIO& io) {
+  TracerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = grid_view();
+  a.TCUR = io.TCUR; a.TMIX = io.TMIX; a.TOLD = io.TOLD; a.UCUR = io.UCUR; a.VCUR = io.VCUR;
+  a.STF = io.STF; a.TFW = io.TFW; a.DH = io.DH; a.POLD = io.POLD; a.PCUR = io.PCUR;
+  a.OUT = io.TNEW;
+  a.WTK = io.WTK;
+  a.VTF = fld("VTF");
+  a.AUX = fld("AUX");
+  a.hmix = G.cfg.hmix_tracer_itype;
+  a.lvariable_hmixt = G.cfg.lvariable_hmixt;
+  a.varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
+  a.implicit_vmix = G.cfg.implicit_vertical_mix;
+  a.predictor = (a.varthick && G.cfg.lpressure_avg && G.leapfrogts);
+  a.ah = G.ah;
+  if (mode == TR_FULL) { a.k0 = 1; a.k1 = G.km; }
+  else {
+    POP_REQUIRE(k >= 1 && k <= G.km, "tracer slab operator: k=%d out of range", k);
+    a.k0 = a.k1 = k;
+  }
+  const bool del4 = (G.cfg.hmix_tracer_itype == POP_HMIX_DEL4);
+  for (int n0 = 0; n0 < G.nt; n0 += NTC) {
+    a.n0 = n0;
+    a.nn = (G.nt - n0 < NTC) ? G.nt - n0 : NTC;
+    bool upw = false;
+    for (int m = 0; m < a.nn; m++) {
+      a.adv[m] = G.cfg.tadvect_itype[n0 + m];
+      if (a.adv[m] == POP_TADVECT_UPWIND3) upw = true;
+    }
+    switch (mode) {
+      case TR_FULL: POP_TRY(launch_tracer<TR_FULL>(a, del4, upw)); break;
+      case TR_ADVT: {
+        // every pass restarts from the caller's WTK; only the last pass stores WTKB back
+        TracerArgs b = a;
+        if (n0 + NTC < G.nt) b.WTK = fld("WTK_C");  // scratch copy so the input survives
+        if (n0 + NTC < G.nt)
+          POP_CHECK_CUDA(cudaMemcpyAsync(b.WTK, a.WTK, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+        POP_TRY(launch_tracer<TR_ADVT>(b, false, upw));
+        break;
+      }
+      case TR_HDIFFT: POP_TRY(launch_tracer<TR_HDIFFT>(a, del4, false)); break;
+      case TR_VDIFFT: POP_TRY(launch_tracer<TR_VDIFFT>(a, false, false)); break;
+      default: POP_REQUIRE(false, "tracer_column: bad mode %d", mode);
+    }
+  }
+  return pop_post_launch("tracer_column");
+}
+
+// =====================================================================================
+// impvmixt / impvmixt_correct: vertical_mix.F90:1164-1382, :1460-1672
+// =====================================================================================
+// One thread per physical column.  For each tracer: forward elimination keeps E(k) in registers
+// (fully unrolled, KMAX compile-time) and streams F(k) through FB (the output array itself for the
+// predictor form, a work array for the corrector); back substitution re-reads F(k) while it is
+// still L2-resident.
+template <int KMAX, bool CORRECT>
+__global__ void __launch_bounds__(128)
+impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict__ TOLD,
+                const double* __restrict__ PSFC, const double* __restrict__ RHS, double* FB,
+                int nfirst, int nlast, int varthick) {
+  const int i = (g.ib - 1) + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (g.jb - 1) + blockIdx.y;
+  if (i > g.ie - 1 || j > g.je - 1) return;
+  const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
+  const int km = g.km, kmt = g.KMT[q];
+  const double hfac1 = c_vc.dz[1] / c_vc.c2dtt[1];
+  const double H1 = varthick ? hfac1 + PSFC[q] / (POP_GRAV * c_vc.c2dtt[1]) : hfac1;
+  double E[KMAX];
+  for (int n = nfirst; n <= nlast; n++) {  // 1-based tracer index
+    const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
+    const double* VDC = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q;  // + (kk - k0)*n2
+    double* Tn = TNEW + (size_t)(n - 1) * km * n2 + q;
+    double* Fb = CORRECT ? FB + q : Tn;
+    double A, B, C, D, Fm;
+    {
+      const int kk = (g.vdc_nk == 1) ? 1 : 1;
+      A = c_vc.afac_t[1] * VDC[(size_t)(kk - g.vdc_k0) * n2];
+      D = H1 + A;
+      E[0] = A / D;
+      B = H1 * E[0];
+      const double R1 = CORRECT ? RHS[(size_t)(n - 1) * n2 + q] : Tn[0];
+      Fm = hfac1 * R1 / D;
+      Fb[0] = Fm;
+    }
+#pragma unroll
+    for (int k = 2; k <= KMAX; k++) {
+      if (k <= km) {
+        const int kk = (g.vdc_nk == 1) ? 1 : k;
+        C = A;
+        A = c_vc.afac_t[k] * VDC[(size_t)(kk - g.vdc_k0) * n2];
+        const double hfac = c_vc.dz[k] / c_vc.c2dtt[k];
+        double F;
+        if (k > kmt) {
+          F = 0.0;
+          E[k - 1] = 0.0;
+        } else {
+          if (k == kmt) D = hfac + B;
+          else D = hfac + A + B;
+          E[k - 1] = A / D;
+          B = (hfac + B) * E[k - 1];
+          if (CORRECT) F = C * Fm / D;
+          else F = (hfac * Tn[(size_t)(k - 1) * n2] + C * Fm) / D;
+        }
+        Fb[(size_t)(k - 1) * n2] = F;
+        Fm = F;
+      }
+    }
+    // back substitution + final update; Fm = F(km)
+    double Fp = Fm;
+    {
+      double* t = Tn + (size_t)(km - 1) * n2;
+      const double base = CORRECT ? *t : TOLD[(size_t)((n - 1) * km + (km - 1)) * n2 + q];
+      *t = base + Fp;
+    }
+#pragma unroll
+    for (int k = KMAX - 1; k >= 1; k--) {
+      if (k <= km - 1) {
+        double F = Fb[(size_t)(k - 1) * n2];
+        if (k < kmt) F = F + E[k - 1] * Fp;
+        double* t = Tn + (size_t)(k - 1) * n2;
+        const double base = CORRECT ? *t : TOLD[(size_t)((n - 1) * km + (k - 1)) * n2 + q];
+        *t = base + F;
+        Fp = F;
+      }
+    }
+  }
+}
+
+int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const double* RHS, int nfirst,
+                 int nlast, int correct) {
+  if (nfirst > nlast || nfirst > G.nt) return POP_SUCCESS;  // vertical_mix.F90:1232
+  POP_REQUIRE(nfirst >= 1 && nlast <= G.nt, "impvmixt: tracer range %d..%d", nfirst, nlast);
+  ScopedTimer tm("VMIX_TRACER_IMPLICIT");
+  GridView g = grid_view();
+  const int varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
+  dim3 block(128, 1, 1), grid((unsigned)((G.nxg + 127) / 128), (unsigned)G.ny_local, 1);
+  double* FB = fld("WORK3D_E");
+#define IMPV(KM_)                                                                              \
+  do {                                                                                         \
+    auto kc = impvmixt_kernel<KM_, true>;                                                      \
+    auto kp = impvmixt_kernel<KM_, false>;                                                     \
+    if (correct)                                                                               \
+      POP_LAUNCH(kc, grid, block, 0, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);    \
+    else                                                                                       \
+      POP_LAUNCH(kp, grid, block, 0, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);    \
+  } while (0)
+  if (G.km <= 32) IMPV(32);
+  else if (G.km <= 64) IMPV(64);
+  else IMPV(POP_KMAX);
+#undef IMPV
+  return pop_post_launch("impvmixt");
+}
+
+// vmix_coeffs (vertical_mix.F90:518-670).  'given' (KPP-shaped VDC/VVC supplied by the caller) needs
+// no work.  'const' (vmix_const.F90:144-233): constant coefficients, replaced by the convective
+// values where the column is statically unstable (convection_type = 'diffusion').
+__global__ void vmix_const_kernel(StateOpt o, const double* __restrict__ TMIX, const int* __restrict__ KMT,
+                                  double* __restrict__ VDC, double* __restrict__ VVC, size_t n2, int km,
+                                  int k0, double const_vdc, double const_vvc, double convect_diff,
+                                  double vvconv) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = k0 + blockIdx.y;
+  if (q >= n2) return;
+  const int kp1 = (k + 1 < km) ? k + 1 : km;
+  const size_t c = (size_t)(k - 1) * n2 + q, cp = (size_t)(kp1 - 1) * n2 + q;
+  double rhok, rhokp;
+  state_cell(o, kp1, TMIX[c], TMIX[(size_t)km * n2 + c], &rhok, nullptr, nullptr, nullptr);
+  state_cell(o, kp1, TMIX[cp], TMIX[(size_t)km * n2 + cp], &rhokp, nullptr, nullptr, nullptr);
+  double vdc = const_vdc, vvc = const_vvc;
+  if (rhok > rhokp && k < KMT[q]) {
+    vdc = convect_diff;
+    vvc = vvconv;
+  }
+  VDC[c] = vdc;
+  VVC[c] = vvc;
+}
+
+int vmix_coeffs_dev(int k0, int k1, const double* TMIX, const double* UMIX, const double* VMIX,
+                    const double* RHOMIX) {
+  (void)UMIX; (void)VMIX; (void)RHOMIX;
+  const pop_config& c = G.cfg;
+  if (c.vmix_itype == POP_VMIX_GIVEN) return POP_SUCCESS;
+  if (c.vmix_itype == POP_VMIX_CONST) {
+    if (!c.convection_diff) return POP_SUCCESS;  // vmix_const.F90: coefficients stay at their constants
+    POP_REQUIRE(G.vdc_nk == G.km, "vmix_coeffs(const, convective diffusion) needs implicit vertical mixing");
+    POP_REQUIRE(k0 >= 1 && k1 <= G.km && k0 <= k1, "vmix_coeffs: bad level range %d..%d", k0, k1);
+    ScopedTimer tm("VMIX_COEFFICIENTS_CONSTANT");
+    StateOpt o{c.state_itype, c.state_range_iopt};
+    const double vvconv = (c.convect_visc != 0.0) ? c.convect_visc : c.const_vvc;
+    dim3 grid(ew_grid(G.n2), (unsigned)(k1 - k0 + 1), 1);
+    POP_LAUNCH(vmix_const_kernel, grid, POP_EW_THREADS, 0, o, TMIX, fldi("KMT"), fld("VDC"), fld("VVC"),
+               G.n2, G.km, k0, c.const_vdc, c.const_vvc, c.convect_diff, vvconv);
+    return pop_post_launch("vmix_coeffs");
+  }
+  POP_REQUIRE(false, "vmix_coeffs: vmix_itype=%d is not implemented", c.vmix_itype);
+  return POP_FAIL;
+}

@@ -1,0 +1,150 @@
+"""GPU parity of the fused drivers (pop_step = dhdt + baroclinic_driver + barotropic_driver +
+baroclinic_correct_adjust + halo updates + time-level rotation) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fields agree within a relative tolerance of 1e-12 after one
+step; KMT/KMU masking (exact zeros below the bottom) and solver iteration counts are bit-exact.
+Everything before the elliptic solve is bit-identical; the only source of rounding differences is
+the order of the global dot products (double-double tree on the GPU, sequential on the CPU)."""
+import numpy as np
+import pytest
+
+from parity import *  # noqa: F401,F403
+
+pytestmark = pytest.mark.gpu
+RTOL_1STEP = 1.0e-12
+PROG = ("TRACER", "UVEL", "VVEL", "RHO", "PSURF", "UBTROP", "VBTROP", "GRADPX", "GRADPY")
+
+
+def compare(o, p, rtol, tag):
+    worst = 0.0
+    for n in PROG + ("PGUESS",):
+        for t in (c.TIME_OLD, c.TIME_CUR, c.TIME_NEW):
+            if n == "PGUESS" and t != c.TIME_CUR:
+                continue
+            a = oracle_global(o, n, t)
+            b = pop_global(p, n, t)
+            e = relerr(b, a)
+            worst = max(worst, e)
+            assert e <= rtol, "%s: %s[%d] relative error %.3e > %.1e" % (tag, n, t, e, rtol)
+            # masking is exact: wherever the oracle has an exact zero (land / below the bottom) so do we
+            assert np.array_equal(a == 0.0, b == 0.0), "%s: %s[%d] zero-mask differs" % (tag, n, t)
+    return worst
+
+
+CASES = {
+    # config 1/2 flavour: centred advection + del2 + const vmix with convective diffusion, ChronGear
+    "del2_chrongear": dict(nx=48, ny=36, km=8, seed=21, convergence_criterion=1e-12),
+    # config 4 flavour: tripole, variable biharmonic mixing, KPP-shaped given coefficients, P-CSI
+    "tripole_del4_pcsi": dict(nx=48, ny=36, km=8, seed=22, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                              hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21,
+                              am=-27.0e21, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0),
+    # gx flavour: upwind3 advection, pcg, extra passive tracer, cyclic north-south, no convective diffusion
+    "upwind3_pcg": dict(nx=40, ny=32, km=7, nt=3, seed=23, ns=c.BNDY_CYCLIC, tadvect=c.TADVECT_UPWIND3,
+                        solver_choice=c.SOLVER_PCG, convection_diff=0),
+    # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
+    "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
+                             lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_step_sequence_matches_oracle(name):
+    kw = dict(CASES[name])
+    cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
+    o, p = load_oracle(cs), load_pop(cs)
+    try:
+        # first step is forward Euler, then leapfrog, an averaging step, leapfrog again
+        for i, ts in enumerate([c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG]):
+            assert o.step(ts) == 0
+            p.step(ts)
+            it_o, res_o = o.solver_diag()
+            it_p, res_p = p.solvers_get_diagnostics()
+            assert it_o == it_p, "%s step %d: solver iterations %d (oracle) vs %d" % (name, i, it_o, it_p)
+            compare(o, p, RTOL_1STEP * (i + 1), "%s step %d" % (name, i))
+    finally:
+        p.finalize()
+
+
+def test_ten_steps_stay_within_solver_tolerance():
+    cs = make_case(48, 36, 8, seed=31, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=900.0)
+    o, p = load_oracle(cs), load_pop(cs)
+    try:
+        seq = [c.TS_EULER, c.TS_AVG] + [c.TS_LEAPFROG] * 8
+        for ts in seq:
+            assert o.step(ts) == 0
+            p.step(ts)
+            assert o.solver_diag()[0] == p.solvers_get_diagnostics()[0]
+        # "stay within the solver convergence tolerance over 10 steps": criterion 1e-13 (relative rms)
+        compare(o, p, 1.0e-10, "10 steps")
+    finally:
+        p.finalize()
+
+
+def test_product_is_decomposition_independent_of_oracle_blocks():
+    """The oracle run as 4x3 blocks of 12x12 (the reference's multi-block layout) and the library's
+    single strip give the same physical-domain answer."""
+    cs = make_case(48, 36, 6, seed=41)
+    o, p = load_oracle(cs, block_size=(12, 12)), load_pop(cs)
+    try:
+        for ts in (c.TS_EULER, c.TS_LEAPFROG):
+            assert o.step(ts) == 0
+            p.step(ts)
+            assert o.solver_diag()[0] == p.solvers_get_diagnostics()[0]
+        compare(o, p, 2.0e-12, "blocks")
+    finally:
+        p.finalize()
+
+
+def test_conservation_constant_preservation_and_masking():
+    """Size-independent properties, also used at full size by bench.py --check:
+    (1) cells below KMT stay exactly 0; (2) with a rigid lid and closed/cyclic boundaries the flux-form
+    advection + mixing + implicit vertical mixing conserve the volume integral of every tracer;
+    (3) with the ocean at rest a spatially constant tracer stays constant."""
+    cs = make_case(64, 40, 10, nt=3, seed=51, sfc_layer_type=c.SFC_RIGID, lpressure_avg=0, given_vmix=True)
+    kmask = (np.arange(1, cs.km + 1)[:, None, None] <= cs.kmt[None]).astype(np.float64)
+    for f in ("STF", "TFW"):
+        cs.forcing[f][:] = 0.0
+    vol = kmask * cs.dz[:, None, None] * (cs.grid["DXT"] * cs.grid["DYT"])[None]
+    p = load_pop(cs)
+    try:
+        Told = pop_global(p, "TRACER", c.TIME_OLD).reshape(3, cs.km, cs.ny, cs.nx)
+        p.step(c.TS_EULER)
+        T = pop_global(p, "TRACER", c.TIME_CUR).reshape(3, cs.km, cs.ny, cs.nx)
+        assert np.array_equal(T[:, kmask == 0.0], np.zeros_like(T[:, kmask == 0.0]))
+        for n in range(3):
+            before, after = np.sum(Told[n] * vol), np.sum(T[n] * vol)
+            assert abs(after - before) <= 1.0e-11 * np.sum(np.abs(Told[n]) * vol), (n, before, after)
+    finally:
+        p.finalize()
+    for lev in ("cur", "old"):
+        cs.state["TRACER_" + lev][2] = 3.25 * kmask
+        cs.state["UVEL_" + lev][:] = 0.0
+        cs.state["VVEL_" + lev][:] = 0.0
+    p = load_pop(cs)
+    try:
+        p.step(c.TS_EULER)
+        T = pop_global(p, "TRACER", c.TIME_CUR).reshape(3, cs.km, cs.ny, cs.nx)
+        assert np.max(np.abs(T[2][kmask == 1.0] - 3.25)) <= 3.25 * 1.0e-12
+    finally:
+        p.finalize()
+
+
+def test_step_coupled_host_buffers_match_resident_step():
+    cs = make_case(40, 32, 6, seed=61)
+    p = load_pop(cs)
+    try:
+        p.step(c.TS_EULER)
+        ref = {n: pop_global(p, n, c.TIME_CUR) for n in ("TRACER", "PSURF", "UVEL", "VVEL")}
+    finally:
+        p.finalize()
+    p = load_pop(cs)
+    try:
+        out = np.zeros((5, cs.ny, cs.nx))
+        f = cs.forcing
+        p.step_coupled(c.TS_EULER, np.ascontiguousarray(f["STF"]), np.ascontiguousarray(f["SMF"]),
+                       np.zeros((cs.ny, cs.nx)), np.ascontiguousarray(f["FW"]), out)
+        assert np.array_equal(out[0], ref["TRACER"][0]) and np.array_equal(out[1], ref["TRACER"][cs.km])
+        assert np.array_equal(out[2], ref["PSURF"][0])
+        assert np.array_equal(out[3], ref["UVEL"][0]) and np.array_equal(out[4], ref["VVEL"][0])
+    finally:
+        p.finalize()
