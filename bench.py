@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- POP2 baroclinic + barotropic step throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl pop|reference] [--workload NAME]
+
+One "step" = one full leapfrog step (dhdt, baroclinic_driver, barotropic_driver with the P-CSI
+solve, baroclinic_correct_adjust, all halo updates, time-level rotation) of the tx0.1v3-shape
+configuration (3600 x 2400 x 62, nt=2, tripole, centred advection, variable biharmonic mixing,
+KPP-shaped implicit vertical mixing, P-CSI diagonal-preconditioned, dt = 288 s)
+on seeded synthetic fields.  N > 1 splits the same grid into N j-strips (strong scaling).
+
+Printed JSON line (rank 0): value = cell-updates/s with the state resident in HBM; e2e = the same
+through pop_step_coupled with the per-step coupling fields in pinned HOST buffers (surface forcing
+in, surface state out); roofline = the dominant kernel's algorithmic bytes / CUDA-event duration
+against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle (a line-by-line C restatement of the
+reference routines; the Fortran reference itself cannot be built in this image) on a bounded
+sub-domain with all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import pop_pkg  # noqa: E402
+
+P = pop_pkg.load()
+c = P.config
+syn = P.synthetic
+
+WORKLOADS = {
+    # name: (nx, ny, km, vertical grid, dt[s])
+    "tx0.1v3": (3600, 2400, 62, "tx0.1v3", 288.0),
+    "gx1v7": (320, 384, 60, "gx1v7", 3600.0),
+    "tx_sample": (1200, 800, 62, "tx0.1v3", 864.0),     # bounded CPU sample of the tx0.1v3 workload
+    "tiny": (120, 80, 12, "stretched", 2880.0),
+}
+
+
+def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
+    nx, ny, km, vg, dt = WORKLOADS[workload]
+    scale = 3600.0 / nx   # biharmonic coefficients scale with dx^3 (hmix_del4.F90 lauto rule ~ 1/nx)
+    kw = dict(nx_global=nx, ny_global=ny, km=km, nt=nt, ew_boundary_type=c.BNDY_CYCLIC,
+              ns_boundary_type=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
+              lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e17 * scale ** 3, am=-27.0e17 * scale ** 3,
+              vmix_itype=c.VMIX_GIVEN, vdc_kdim_halo=1, vdc_ndim=2, solver_choice=c.SOLVER_PCSI,
+              convergence_criterion=1.0e-13, dtt=dt, rank=rank, nranks=nranks, device=device,
+              tadvect=c.TADVECT_CENTERED)
+    if block:
+        kw.update(block_size_x=block[0], block_size_y=block[1])
+    return c.make_config(**kw), vg
+
+
+# ------------------------------------------------------------------------------------------------
+# decomposition-independent synthetic fields, generated level by level on the device
+# ------------------------------------------------------------------------------------------------
+def hash_noise(xp, i, j, k, salt):
+    """deterministic pseudo-noise in [-1, 1) from global indices (same on any decomposition)."""
+    t = xp.sin(i * 12.9898 + j * 78.233 + (k * 37.719 + salt * 0.137)) * 43758.5453
+    return 2.0 * (t - xp.floor(t)) - 1.0
+
+
+class Fields:
+    """xp = torch (device generation for the GPU run) or numpy (oracle arm); rows = global row slice."""
+
+    def __init__(self, xp, nx, ny, km, dz, kmt, kmu, rows, dev=None):
+        self.xp, self.nx, self.ny, self.km, self.dz = xp, nx, ny, km, dz
+        if xp is np:
+            conv = lambda a: np.asarray(a, dtype=np.float64)
+        else:
+            conv = lambda a: xp.as_tensor(np.ascontiguousarray(a), dtype=xp.float64, device=dev)
+        self.conv = conv
+        jj, ii = np.meshgrid(np.arange(ny, dtype=np.float64)[rows], np.arange(nx, dtype=np.float64), indexing="ij")
+        self.i, self.j = conv(ii), conv(jj)
+        self.kmt, self.kmu = conv(kmt[rows].astype(np.float64)), conv(kmu[rows].astype(np.float64))
+        self.zt = (np.cumsum(dz) - 0.5 * dz) * 0.01
+        xi, yj = ii / nx, jj / ny
+        psi = (np.sin(2 * np.pi * 2 * xi + 0.3) * np.sin(np.pi * 2 * yj + 0.1)
+               + 0.6 * np.sin(2 * np.pi * 3 * xi + 1.1) * np.sin(np.pi * 3 * yj + 0.7))
+        # smooth non-divergent part from a stream function (global analytic derivatives)
+        dpx = (2 * np.pi * 2 * np.cos(2 * np.pi * 2 * xi + 0.3) * np.sin(np.pi * 2 * yj + 0.1)
+               + 0.6 * 2 * np.pi * 3 * np.cos(2 * np.pi * 3 * xi + 1.1) * np.sin(np.pi * 3 * yj + 0.7))
+        dpy = (np.pi * 2 * np.sin(2 * np.pi * 2 * xi + 0.3) * np.cos(np.pi * 2 * yj + 0.1)
+               + 0.6 * np.pi * 3 * np.sin(2 * np.pi * 3 * xi + 1.1) * np.cos(np.pi * 3 * yj + 0.7))
+        del psi
+        s = 40.0 / max(np.abs(dpx).max(), np.abs(dpy).max())
+        self.u0, self.v0 = conv(-s * dpy), conv(s * dpx)
+        self.eta = conv(50.0 * np.sin(2 * np.pi * 2 * xi) * np.cos(np.pi * yj))
+        self.hbl = conv(3.0 + 7.0 * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * xi + 0.5) * np.cos(np.pi * 2 * yj)))
+
+    def tracer(self, n, k, lev):   # k 1-based
+        xp, z = self.xp, self.zt[k - 1]
+        salt = 10 * n + (0 if lev == "cur" else 5)
+        nz = hash_noise(xp, self.i, self.j, float(k), salt)
+        if n == 0:
+            v = 2.0 + 23.0 * math.exp(-z / 800.0) + 0.5 * math.exp(-z / 500.0) * nz
+        elif n == 1:
+            v = (34.7 + 0.2 * nz) / 1000.0
+        else:
+            v = 0.5 + 0.5 * nz
+        return v * (self.kmt >= k)
+
+    def vel(self, comp, k, lev):
+        xp, z = self.xp, self.zt[k - 1]
+        base = self.u0 if comp == 0 else self.v0
+        nz = hash_noise(xp, self.i, self.j, float(k), 100 + comp * 7 + (0 if lev == "cur" else 3))
+        return (base * math.exp(-z / 1000.0) + nz) * (self.kmu >= k)
+
+    def psurf(self, lev):
+        nz = hash_noise(self.xp, self.i, self.j, 0.0, 300)
+        return (syn.GRAV * self.eta + (0.0 if lev == "cur" else 10.0 * nz)) * (self.kmt > 0)
+
+    def vdc(self, d, kk):          # kk = 0..km+1 (KPP shape)
+        xp = self.xp
+        shape = xp.clip(1.0 - kk / self.hbl, 0.0, 1.0)
+        return 0.1 + 500.0 * shape ** 2 * (1.0 + 0.1 * d) + 0.025 * (1.0 + hash_noise(xp, self.i, self.j, float(kk), 400 + d))
+
+    def vvc(self, k):
+        xp = self.xp
+        shape = xp.clip(1.0 - k / self.hbl, 0.0, 1.0)
+        return 1.0 + 800.0 * shape ** 2 + 0.05 * (1.0 + hash_noise(xp, self.i, self.j, float(k), 500))
+
+
+def static_inputs(workload):
+    nx, ny, km, vg, _ = WORKLOADS[workload]
+    grid = syn.horiz_grid(nx, ny, tripole=True)
+    dz = syn.vert_grid(vg, km)
+    kmt = syn.bathymetry(nx, ny, km, 20240611 + 4)
+    kmt[-3:, :] = np.minimum(kmt[-3:, :], kmt[-3:, ::-1])
+    kmu = syn.kmu_from_kmt(kmt, ew_cyclic=True, ns_type=c.BNDY_TRIPOLE)
+    return grid, dz, kmt, kmu
+
+
+def fill_pop(p, F, nt):
+    """upload every prognostic field level by level (device-to-device when F lives on the GPU)."""
+    km = p.km
+    if F.xp is not np:
+        def ptr(a):
+            F.xp.cuda.current_stream().synchronize()   # generation runs on torch's stream, the copy on the library's
+            return a.data_ptr()
+    else:
+        ptr = lambda a: np.ascontiguousarray(a)[None]
+    for lev, t in (("cur", c.TIME_CUR), ("old", c.TIME_OLD)):
+        for n in range(nt):
+            for k in range(1, km + 1):
+                a = F.tracer(n, k, lev).contiguous() if F.xp is not np else F.tracer(n, k, lev)
+                p.scatter_levels("TRACER", t, n * km + k - 1, 1, ptr(a))
+        for comp, name in ((0, "UVEL"), (1, "VVEL")):
+            for k in range(1, km + 1):
+                a = F.vel(comp, k, lev)
+                a = a.contiguous() if F.xp is not np else a
+                p.scatter_levels(name, t, k - 1, 1, ptr(a))
+        a = F.psurf(lev)
+        a = a.contiguous() if F.xp is not np else a
+        p.scatter_levels("PSURF", t, 0, 1, ptr(a))
+        for name, loc, kind in (("TRACER", c.LOC_CENTER, c.KIND_SCALAR), ("UVEL", c.LOC_NECORNER, c.KIND_VECTOR),
+                                ("VVEL", c.LOC_NECORNER, c.KIND_VECTOR), ("PSURF", c.LOC_CENTER, c.KIND_SCALAR)):
+            p.halo_field(name, t, loc, kind)
+        n2 = p.nxb * p.nyb
+        T, R = p.dptr("TRACER", t), p.dptr("RHO", t)
+        for k in range(1, km + 1):
+            p.state(k, k, T + 8 * n2 * (k - 1), T + 8 * n2 * (km + k - 1), R + 8 * n2 * (k - 1))
+        p.grad(1, p.dptr("GRADPX", t), p.dptr("GRADPY", t), p.dptr("PSURF", t))
+        p.halo_field("GRADPX", t, c.LOC_NECORNER, c.KIND_VECTOR)
+        p.halo_field("GRADPY", t, c.LOC_NECORNER, c.KIND_VECTOR)
+    a = F.psurf("cur")
+    a = a.contiguous() if F.xp is not np else a
+    p.scatter_levels("PGUESS", 0, 0, 1, ptr(a))
+    p.halo_field("PGUESS", 0, c.LOC_CENTER, c.KIND_SCALAR)
+    for d in range(2):
+        for kk in range(km + 2):
+            a = F.vdc(d, kk)
+            a = a.contiguous() if F.xp is not np else a
+            p.scatter_levels("VDC", 0, d * (km + 2) + kk, 1, ptr(a))
+    for k in range(1, km + 1):
+        a = F.vvc(k)
+        a = a.contiguous() if F.xp is not np else a
+        p.scatter_levels("VVC", 0, k - 1, 1, ptr(a))
+    p.halo_field("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
+    p.halo_field("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
+    p.solvers_prep()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic bytes per 3-d cell of each timed kernel: every
+# distinct fp64 array element counted once per launch, 2-d arrays neglected
+def kernel_bytes_per_cell(nt, v=2):
+    return {
+        "TRACER_UPDATE": 8 * (3 * nt + 2 + v),      # TCUR, TMIX(=TOLD) x nt, U, V, VDC x v -> TNEW x nt
+        "CLINIC": 8 * (4 + 3 + 1 + 2),              # Ucur,Vcur,Uold,Vold, RHO x3, VVC -> Unew,Vnew
+        "VMIX_TRACER_IMPLICIT": 24 * 2 + 8 * v,     # per call on 2 tracers: RHS,TOLD in, TNEW out, VDC x v
+        "STATE": 24,                                # T,S -> RHO
+    }
+
+
+def run_pop(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        obj = [P.api.Pop.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        comm_id = obj[0]
+    nt = args.nt
+    cfg, vg = make_cfg(args.workload, nt, rank, world, local)
+    nx, ny, km = cfg.nx_global, cfg.ny_global, cfg.km
+    grid, dz, kmt, kmu = static_inputs(args.workload)
+    p = P.api.Pop(cfg, comm_id)
+    p.set_grid(grid, kmt, dz)
+    F = Fields(torch, nx, ny, km, dz, kmt, kmu, p.rows(), dev)
+    fill_pop(p, F, nt)
+    del F
+    torch.cuda.empty_cache()
+    stream = torch.cuda.ExternalStream(p.L.pop_stream(), device=dev)
+
+    def barrier():
+        p.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up: forward-Euler first step, then leapfrog
+    W, K = max(args.warmup, 3), args.steps
+    p.step(c.TS_EULER)
+    for _ in range(W - 1):
+        p.step(c.TS_LEAPFROG)
+    iters_warm = p.solvers_get_diagnostics()[0]
+    # ---- timed region 1: state resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    p.L.pop_timers_reset()
+    p.timers(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = p.launches()
+    e0.record(stream)
+    iters = []
+    for _ in range(K):
+        p.step(c.TS_LEAPFROG)
+        iters.append(p.solvers_get_diagnostics()[0])
+    e1.record(stream)
+    barrier()
+    launches = p.launches() - l0
+    ms = e0.elapsed_time(e1)
+    p.timers(False)
+    tnames = ["TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "SOLVER", "BAROTROPIC", "HALO", "STEP"]
+    tm = {n: p.timer(n) for n in tnames}
+    # ---- timed region 2: end to end through pop_step_coupled with pinned host buffers
+    strip = p.ny_local * nx
+    h_in = torch.zeros((nt + 4) * strip, dtype=torch.float64).pin_memory()
+    h_out = torch.zeros(5 * strip, dtype=torch.float64).pin_memory()
+    hin = h_in.numpy()
+    hin[:] = 1.0e-6 * np.sin(np.arange(hin.size, dtype=np.float64))
+    STF, SMF = hin[: nt * strip], hin[nt * strip:(nt + 2) * strip]
+    QSW, FW = hin[(nt + 2) * strip:(nt + 3) * strip], hin[(nt + 3) * strip:]
+    FW[:] *= 1.0e-3
+    p.step_coupled(c.TS_LEAPFROG, STF, SMF, QSW, FW, h_out.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(K):
+        p.step_coupled(c.TS_LEAPFROG, STF, SMF, QSW, FW, h_out.numpy())
+        _ = float(h_out[0])      # the host reads the step's result
+    f1.record(stream)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)   # host-side copies are part of the end-to-end time
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    cells = float(nx) * ny * km
+    ocean = float(np.sum(kmt))
+    p.finalize()
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    bpc = kernel_bytes_per_cell(nt)
+    local_cells = float(nx) * p.ny_local * km
+    kern = {}
+    for n in ("TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE"):
+        tms, calls = tm[n]
+        if calls:
+            per = tms / calls
+            kern[n] = {"ms_per_launch": per, "calls": calls, "GBs": bpc[n] * local_cells / (per * 1e-3) / 1e9,
+                       "share_of_step": tms / ms}
+    dom = max(kern, key=lambda n: kern[n]["ms_per_launch"] * kern[n]["calls"]) if kern else None
+    roof = None
+    if dom:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_cell": bpc[dom], "cells_per_launch": local_cells,
+                "ms_per_launch": kern[dom]["ms_per_launch"], "all_kernels": kern}
+    out = {
+        "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)" if args.workload == "tx0.1v3"
+                  else "cell-updates/s, full baroclinic+barotropic step",
+        "value": cells * K / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (seeded analytic fields + hash noise, synthetic bathymetry)",
+        "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt del4(variable) given-KPP-shaped-vmix "
+                               "PCSI/diagonal 1e-13 dt=%gs full-cells, 1x%d j-strips" % (args.workload, nx, ny, km, nt, cfg.dtt, world),
+                   "l2": "inputs larger than L2 (state is %.0f GB; no explicit flush)" % (cells * 8 * (3 * nt + 9 + 3) / 1e9),
+                   "solver_iterations_per_step": iters, "ocean_cell_updates_per_s": ocean * K / (ms * 1e-3)},
+        "roofline": roof,
+        "step_fraction_of_fused_lower_bound": (24 * nt + 136) * cells / world / (ms / K * 1e-3) / 1e9 / peak,
+        "phases_ms_per_step": {n: tm[n][0] / K for n in tm},
+        "e2e": {"value": cells * K / (ms_e2e * 1e-3), "unit": "cell-updates/s",
+                "h2d_bytes_per_step": 8 * (nt + 4) * nx * ny, "d2h_bytes_per_step": 8 * 5 * nx * ny,
+                "ms_per_step": ms_e2e / K, "api": "pop_step_coupled (host forcing in, host surface state out)"},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, steps=2)
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (test infrastructure) timed on the host cores on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def oracle_setup(sample, nt):
+    from oracle import oracle as O
+    O.build()
+    nx, ny, km, vg, dt = WORKLOADS[sample]
+    cfg, _ = make_cfg(sample, nt, block=(60, 40))
+    grid, dz, kmt, kmu = static_inputs(sample)
+    o = O.Oracle(cfg)
+    o.set_grid(grid, kmt, dz)
+    F = Fields(np, nx, ny, km, dz, kmt, kmu, slice(0, ny))
+    for lev, t in (("cur", c.TIME_CUR), ("old", c.TIME_OLD)):
+        T = np.stack([np.stack([F.tracer(n, k, lev) for k in range(1, km + 1)]) for n in range(nt)])
+        o.scatter("TRACER", t, T)
+        o.scatter("UVEL", t, np.stack([F.vel(0, k, lev) for k in range(1, km + 1)]))
+        o.scatter("VVEL", t, np.stack([F.vel(1, k, lev) for k in range(1, km + 1)]))
+        o.scatter("PSURF", t, F.psurf(lev))
+        for name, loc, kind in (("TRACER", c.LOC_CENTER, c.KIND_SCALAR), ("UVEL", c.LOC_NECORNER, c.KIND_VECTOR),
+                                ("VVEL", c.LOC_NECORNER, c.KIND_VECTOR), ("PSURF", c.LOC_CENTER, c.KIND_SCALAR)):
+            o.halo(name, t, loc, kind)
+        o.state_all(t)
+        o.grad_psurf(t)
+    o.scatter("PGUESS", c.TIME_CUR, F.psurf("cur"))
+    o.halo("PGUESS", c.TIME_CUR, c.LOC_CENTER, c.KIND_SCALAR)
+    o.scatter("VDC", 0, np.stack([np.stack([F.vdc(d, kk) for kk in range(km + 2)]) for d in range(2)]))
+    o.halo("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
+    o.scatter("VVC", 0, np.stack([F.vvc(k) for k in range(1, km + 1)]))
+    o.halo("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
+    assert o.solvers_prep() == 0
+    return o, float(nx) * ny * km
+
+
+def cpu_baseline(args, steps):
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sample = "tiny" if args.workload == "tiny" else "tx_sample"
+    o, cells = oracle_setup(sample, args.nt)
+    assert o.step(c.TS_EULER) == 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        assert o.step(c.TS_LEAPFROG) == 0
+    dt = time.perf_counter() - t0
+    nx, ny, km = WORKLOADS[sample][:3]
+    return {"value": cells * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": "%d leapfrog steps of the same configuration on a %dx%dx%d sub-grid (60x40 blocks, OpenMP over "
+                      "blocks); CPU oracle = C restatement of the reference (the Fortran reference cannot be built here)"
+                      % (steps, nx, ny, km), "s_per_step": dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sample = "tiny" if args.workload == "tiny" else "tx_sample"
+    o, cells = oracle_setup(sample, args.nt)
+    W, K = max(args.warmup, 1), args.steps
+    W, K = min(W, 2), min(K, 5)     # bounded: ~6 s per step on 8 cores
+    assert o.step(c.TS_EULER) == 0
+    for _ in range(W - 1):
+        assert o.step(c.TS_LEAPFROG) == 0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        assert o.step(c.TS_LEAPFROG) == 0
+    dt = time.perf_counter() - t0
+    nx, ny, km = WORKLOADS[sample][:3]
+    val = cells * K / dt
+    desc = ("%d leapfrog steps of the tx0.1v3 configuration on a %dx%dx%d sub-grid, all host cores (OpenMP over 60x40 "
+            "blocks)" % (K, nx, ny, km))
+    cfg, _ = make_cfg(args.workload, args.nt)
+    print(json.dumps({
+        "impl": "reference", "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)",
+        "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (same seeded fields as the GPU arm)",
+        "config": {"workload": "%s configuration, bounded CPU sample %dx%dx%d nt=%d" % (args.workload, nx, ny, km, args.nt)},
+        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "kind=port: the reference is Fortran (no compiler in this image); this is its C restatement oracle/",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pop", choices=["pop", "reference"])
+    ap.add_argument("--workload", default="tx0.1v3", choices=list(WORKLOADS))
+    ap.add_argument("--nt", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_pop(args)
+
+
+if __name__ == "__main__":
+    main()
