@@ -3,6 +3,7 @@
 // time-step switches of source/step_mod.F90:302-320 / source/time_management.F90:434-439.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "pop_dev.cuh"
@@ -296,6 +297,7 @@ extern "C" int pop_init(const pop_config* cfg) {
   G.gamma = 1.0 - 2.0 * G.alpha;
   memset(&G.vc, 0, sizeof(G.vc));
   G.launches = 0;
+  G.no_tma = getenv("POP_B200_NO_TMA") != nullptr && getenv("POP_B200_NO_TMA")[0] == '1';
   G.timers.clear();
   G.grid_set = false;
   G.initialized = true;
@@ -445,3 +447,43 @@ extern "C" int pop_sync(void) {
   return POP_SUCCESS;
 }
 extern "C" void* pop_stream(void) { return (void*)G.stream; }
+
+// ------------------------------------------------------------------ TMA tensor maps
+#ifndef POP_EMUL
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+bool make_tmap(PopTmap* out, const double* field, int nlev) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc || !field || (G.nxb % 2) != 0 || G.cfg.device < 0) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)G.nxb, (cuuint64_t)G.nyb, (cuuint64_t)nlev};
+  cuuint64_t strides[2] = {(cuuint64_t)G.nxb * 8, (cuuint64_t)G.n2 * 8};
+  cuuint32_t box[3] = {POP_TW, POP_TH, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&out->m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)field, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+#else
+bool make_tmap(PopTmap* out, const double* field, int nlev) {
+  if (!field || (G.nxb % 2) != 0) return false;
+  out->p = field; out->nx = G.nxb; out->ny = G.nyb; out->nz = nlev;
+  return true;
+}
+#endif

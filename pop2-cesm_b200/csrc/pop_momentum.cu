@@ -24,10 +24,12 @@ struct MomentumArgs {
   int k0, k1;
   int lvariable_hmixu, impcor, leapfrog, pavg;
   double am, c2dtu, beta, gamma, bottom_drag;
+  PopTmap tm_uc, tm_vc, tm_um, tm_vm, tm_ro, tm_rc, tm_rn;  // TMA descriptors (FULL mode)
 };
+#define MO_NS 2  // TMA pipeline depth
 
-struct MomCoefTiles {
-  const double *cc, *dun, *dus, *due, *duw, *dmc, *dmn, *dms, *dme, *dmw;
+struct MomCoefTiles {  // DMS = -DMN and DMW = -DME exactly (hmix_del2.F90:395-396), so they are not staged
+  const double *cc, *dun, *dus, *due, *duw, *dmc, *dmn, *dme;
 };
 // 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*
 __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const double* A, const double* B,
@@ -35,18 +37,21 @@ __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const doubl
   const int q = TIX(ii, jj);
   const double s1 = c.cc[q] * A[q] + c.dun[q] * A[TIX(ii, jj + 1)] + c.dus[q] * A[TIX(ii, jj - 1)] +
                     c.due[q] * A[TIX(ii + 1, jj)] + c.duw[q] * A[TIX(ii - 1, jj)];
-  const double s2 = c.dmc[q] * B[q] + c.dmn[q] * B[TIX(ii, jj + 1)] + c.dms[q] * B[TIX(ii, jj - 1)] +
-                    c.dme[q] * B[TIX(ii + 1, jj)] + c.dmw[q] * B[TIX(ii - 1, jj)];
+  const double s2 = c.dmc[q] * B[q] + c.dmn[q] * B[TIX(ii, jj + 1)] + (-c.dmn[q]) * B[TIX(ii, jj - 1)] +
+                    c.dme[q] * B[TIX(ii + 1, jj)] + (-c.dme[q]) * B[TIX(ii - 1, jj)];
   return plus ? (s1 + s2) : (s1 - s2);
 }
 
-#define MOM_NTILES 20
-template <int MODE, bool DEL4>
-__global__ void __launch_bounds__(POP_NTHREADS)
-momentum_column_kernel(const MomentumArgs a) {
+#define MOM_STAGE_TILES 7   // uc, vc, um, vm, rho old/cur/new
+#define MOM_FIXED_TILES 13  // dyu, dxu, cc, dun, dus, due, duw, dmc, dmn, dme, amf, d2u, d2v
+template <int MODE, bool DEL4, bool TMA>
+__global__ void __launch_bounds__(POP_NTHREADS, 2)
+momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   POP_DYN_SMEM(smem_raw);
+  constexpr int NS = TMA ? MO_NS : 1;
   double* sm = (double*)smem_raw;
-  double* s_dyu = sm;
+  double* s_stage = sm;  // [NS][MOM_STAGE_TILES][TN]
+  double* s_dyu = s_stage + NS * MOM_STAGE_TILES * POP_TN;
   double* s_dxu = s_dyu + POP_TN;
   double* s_cc = s_dxu + POP_TN;
   double* s_dun = s_cc + POP_TN;
@@ -55,18 +60,12 @@ momentum_column_kernel(const MomentumArgs a) {
   double* s_duw = s_due + POP_TN;
   double* s_dmc = s_duw + POP_TN;
   double* s_dmn = s_dmc + POP_TN;
-  double* s_dms = s_dmn + POP_TN;
-  double* s_dme = s_dms + POP_TN;
-  double* s_dmw = s_dme + POP_TN;
-  double* s_amf = s_dmw + POP_TN;
-  double* s_uc = s_amf + POP_TN;
-  double* s_vc = s_uc + POP_TN;
-  double* s_um = s_vc + POP_TN;
-  double* s_vm = s_um + POP_TN;
-  double* s_rho = s_vm + POP_TN;
-  double* s_d2u = s_rho + POP_TN;
+  double* s_dme = s_dmn + POP_TN;
+  double* s_amf = s_dme + POP_TN;
+  double* s_d2u = s_amf + POP_TN;
   double* s_d2v = s_d2u + POP_TN;
   int* s_kmu = (int*)(s_d2v + POP_TN);
+  uint64_t* s_bar = (uint64_t*)(s_kmu + POP_TN);
 
   const GridView& g = a.g;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
@@ -82,7 +81,7 @@ momentum_column_kernel(const MomentumArgs a) {
   constexpr bool DO_GRADP = (MODE == MO_FULL || MODE == MO_GRADP);
   constexpr bool DO_VDIF = (MODE == MO_FULL || MODE == MO_VDIFFU);
   constexpr int HM = DEL4 ? 2 : 1;
-  const bool same_mix = (a.UMIX == a.UCUR) && DO_ADV && !DEL4;
+  const bool same_mix = (a.UMIX == a.UCUR) && DO_ADV && (TMA || !DEL4);
 
   // ---- k-invariant staging
   if (DO_ADV) {
@@ -104,14 +103,12 @@ momentum_column_kernel(const MomentumArgs a) {
       s_duw[t] = in ? g.DUW[qq] : 0.0;
       s_dmc[t] = in ? g.DMC[qq] : 0.0;
       s_dmn[t] = in ? g.DMN[qq] : 0.0;
-      s_dms[t] = in ? g.DMS[qq] : 0.0;
       s_dme[t] = in ? g.DME[qq] : 0.0;
-      s_dmw[t] = in ? g.DMW[qq] : 0.0;
       s_amf[t] = in ? g.AMF[qq] : 0.0;
       s_kmu[t] = in ? g.KMU[qq] : 0;
     }
   }
-  const MomCoefTiles ct{s_cc, s_dun, s_dus, s_due, s_duw, s_dmc, s_dmn, s_dms, s_dme, s_dmw};
+  const MomCoefTiles ct{s_cc, s_dun, s_dus, s_due, s_duw, s_dmc, s_dmn, s_dme};
   int kmu = 0;
   double uarea_r = 0, kxu = 0, kyu = 0, fcor = 0, dxur = 0, dyur = 0;
   if (active) {
@@ -150,34 +147,65 @@ momentum_column_kernel(const MomentumArgs a) {
     }
   }
 
+  const uint32_t stage_bytes = (uint32_t)((2 + (same_mix ? 0 : 2) + (a.pavg ? 3 : 1)) * POP_TILE_BYTES);
+  auto issue = [&](int kk) {
+    const int sl = (kk - a.k0) % NS;
+    double* st = s_stage + (size_t)sl * MOM_STAGE_TILES * POP_TN;
+    const int x = i0 - POP_H, y = j0 - POP_H, z = kk - 1;
+    mbar_expect_tx(&s_bar[sl], stage_bytes);
+    tma_load_tile(st, &a.tm_uc, x, y, z, &s_bar[sl]);
+    tma_load_tile(st + POP_TN, &a.tm_vc, x, y, z, &s_bar[sl]);
+    if (!same_mix) {
+      tma_load_tile(st + 2 * POP_TN, &a.tm_um, x, y, z, &s_bar[sl]);
+      tma_load_tile(st + 3 * POP_TN, &a.tm_vm, x, y, z, &s_bar[sl]);
+    }
+    tma_load_tile(st + 5 * POP_TN, &a.tm_rc, x, y, z, &s_bar[sl]);
+    if (a.pavg) {
+      tma_load_tile(st + 4 * POP_TN, &a.tm_ro, x, y, z, &s_bar[sl]);
+      tma_load_tile(st + 6 * POP_TN, &a.tm_rn, x, y, z, &s_bar[sl]);
+    }
+  };
+  if (TMA) {
+    if (tid == 0) {
+      for (int sl = 0; sl < NS; sl++) mbar_init(&s_bar[sl], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int kk = a.k0; kk <= a.k1 && kk < a.k0 + NS; kk++) issue(kk);
+  }
+
   for (int k = a.k0; k <= a.k1; k++) {
-    __syncthreads();
     const size_t lev = (size_t)(k - 1) * n2;
-    if (DO_ADV) {
-      tile_load(s_uc, a.UCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
-      tile_load(s_vc, a.VCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
-    }
-    if (DO_HMIX && !same_mix) {
-      tile_load(s_um, a.UMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
-      tile_load(s_vm, a.VMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
-    }
-    if (DO_GRADP) {
-      // RHOAVG on the (i..i+1, j..j+1) corners: pressure_grad.F90:258-266
-      constexpr int w = POP_BX + 1, npts = w * (POP_BY + 1);
-      const double bouss = c_vc.bouss[k];
-      for (int p = tid; p < npts; p += POP_NTHREADS) {
-        const int jj = p / w, ii = p % w;
-        const int gi = i0 + ii, gj = j0 + jj;
-        double v = 0.0;
-        if (gi < nxb && gj < nyb) {
-          const size_t qq = lev + (size_t)gj * nxb + gi;
-          if (a.pavg) v = 0.25 * (a.RHONEW[qq] + 2.0 * a.RHOCUR[qq] + a.RHOOLD[qq]) * bouss;
-          else v = a.RHOCUR[qq] * bouss;
-        }
-        s_rho[TIX(ii, jj)] = v;
+    const int slot = (k - a.k0) % NS;
+    double* s_uc = s_stage + (size_t)slot * MOM_STAGE_TILES * POP_TN;
+    double* s_vc = s_uc + POP_TN;
+    double* s_um = s_uc + 2 * POP_TN;
+    double* s_vm = s_uc + 3 * POP_TN;
+    double* s_ro = s_uc + 4 * POP_TN;
+    double* s_rc = s_uc + 5 * POP_TN;
+    double* s_rn = s_uc + 6 * POP_TN;
+    if (TMA) {
+      mbar_wait(&s_bar[slot], (uint32_t)(((k - a.k0) / NS) & 1));
+    } else {
+      __syncthreads();
+      if (DO_ADV) {
+        tile_load(s_uc, a.UCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
+        tile_load(s_vc, a.VCUR + lev, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
       }
+      if (DO_HMIX && !same_mix) {
+        tile_load(s_um, a.UMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+        tile_load(s_vm, a.VMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+      }
+      if (DO_GRADP) {
+        tile_load(s_rc, a.RHOCUR + lev, i0, j0, nxb, nyb, 0, POP_BX, 0, POP_BY, tid);
+        if (a.pavg) {
+          tile_load(s_ro, a.RHOOLD + lev, i0, j0, nxb, nyb, 0, POP_BX, 0, POP_BY, tid);
+          tile_load(s_rn, a.RHONEW + lev, i0, j0, nxb, nyb, 0, POP_BX, 0, POP_BY, tid);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     const double* um = same_mix ? s_uc : s_um;
     const double* vm = same_mix ? s_vc : s_vm;
     if (DO_HMIX && DEL4) {
@@ -196,8 +224,7 @@ momentum_column_kernel(const MomentumArgs a) {
       }
       __syncthreads();
     }
-    if (!active) continue;
-
+    if (active) {
     double fx = 0.0, fy = 0.0;
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
     // ---- advu: advection.F90:1307-1491
@@ -245,8 +272,14 @@ momentum_column_kernel(const MomentumArgs a) {
     if (DO_GRADP) {
       double rkx = 0.0, rky = 0.0;
       if (k <= kmu) {
-        const double f11 = s_rho[TIX(tx + 1, ty + 1)], f00 = s_rho[TIX(tx, ty)],
-                     f01 = s_rho[TIX(tx, ty + 1)], f10 = s_rho[TIX(tx + 1, ty)];
+        // RHOAVG at the four T corners: pressure_grad.F90:258-266
+        const double bouss = c_vc.bouss[k];
+#define RAVG(di, dj)                                                                                   \
+  (a.pavg ? 0.25 * (s_rn[TIX(tx + (di), ty + (dj))] + 2.0 * s_rc[TIX(tx + (di), ty + (dj))] +          \
+                    s_ro[TIX(tx + (di), ty + (dj))]) * bouss                                           \
+          : s_rc[TIX(tx + (di), ty + (dj))] * bouss)
+        const double f11 = RAVG(1, 1), f00 = RAVG(0, 0), f01 = RAVG(0, 1), f10 = RAVG(1, 0);
+#undef RAVG
         rkx = dxur * 0.5 * (f11 - f00 - f01 + f10);
         rky = dyur * 0.5 * (f11 - f00 + f01 - f10);
       }
@@ -345,6 +378,11 @@ momentum_column_kernel(const MomentumArgs a) {
     }
     uo_c = uo_p;
     vo_c = vo_p;
+    }  // active
+    if (TMA) {
+      __syncthreads();  // every thread is done with this ring slot (and with the D2 tiles)
+      if (tid == 0 && k + NS <= a.k1) issue(k + NS);
+    }
   }
   if (!active) return;
   if (MODE == MO_FULL) {
@@ -361,11 +399,15 @@ momentum_column_kernel(const MomentumArgs a) {
 }
 
 template <int MODE>
-static int launch_momentum(const MomentumArgs& a, bool del4) {
-  void (*kfn)(const MomentumArgs) = del4 ? momentum_column_kernel<MODE, true> : momentum_column_kernel<MODE, false>;
-  const size_t smem = sizeof(double) * POP_TN * MOM_NTILES + sizeof(int) * POP_TN;
+static int launch_momentum(const MomentumArgs& a, bool del4, bool tma) {
+  void (*kfn)(const MomentumArgs) = nullptr;
+  if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true> : momentum_column_kernel<MODE, false, true>;
+  else kfn = del4 ? momentum_column_kernel<MODE, true, false> : momentum_column_kernel<MODE, false, false>;
+  const int ns = tma ? MO_NS : 1;
+  const size_t smem = sizeof(double) * POP_TN * (ns * MOM_STAGE_TILES + MOM_FIXED_TILES) + sizeof(int) * POP_TN + 8 * MO_NS;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
   POP_LAUNCH(kfn, col_grid(G.nxg, G.ny_local), col_block(), smem, a);
   return POP_SUCCESS;
@@ -403,11 +445,18 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
     }
   }
   switch (mode) {
-    case MO_FULL: POP_TRY(launch_momentum<MO_FULL>(a, del4)); break;
-    case MO_ADVU: POP_TRY(launch_momentum<MO_ADVU>(a, false)); break;
-    case MO_HDIFFU: POP_TRY(launch_momentum<MO_HDIFFU>(a, del4)); break;
-    case MO_GRADP: POP_TRY(launch_momentum<MO_GRADP>(a, false)); break;
-    case MO_VDIFFU: POP_TRY(launch_momentum<MO_VDIFFU>(a, false)); break;
+    case MO_FULL: {
+      const bool tma = !G.no_tma && make_tmap(&a.tm_uc, a.UCUR, G.km) && make_tmap(&a.tm_vc, a.VCUR, G.km) &&
+                       make_tmap(&a.tm_um, a.UMIX, G.km) && make_tmap(&a.tm_vm, a.VMIX, G.km) &&
+                       make_tmap(&a.tm_rc, a.RHOCUR, G.km) &&
+                       (!a.pavg || (make_tmap(&a.tm_ro, a.RHOOLD, G.km) && make_tmap(&a.tm_rn, a.RHONEW, G.km)));
+      POP_TRY(launch_momentum<MO_FULL>(a, del4, tma));
+      break;
+    }
+    case MO_ADVU: POP_TRY(launch_momentum<MO_ADVU>(a, false, false)); break;
+    case MO_HDIFFU: POP_TRY(launch_momentum<MO_HDIFFU>(a, del4, false)); break;
+    case MO_GRADP: POP_TRY(launch_momentum<MO_GRADP>(a, false, false)); break;
+    case MO_VDIFFU: POP_TRY(launch_momentum<MO_VDIFFU>(a, false, false)); break;
     default: POP_REQUIRE(false, "momentum_column: bad mode %d", mode);
   }
   return pop_post_launch("momentum_column");

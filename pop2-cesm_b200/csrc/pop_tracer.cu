@@ -31,7 +31,9 @@ struct TracerArgs {
   int adv[NTC];  // advection scheme of each tracer of this pass
   int hmix, lvariable_hmixt, varthick, implicit_vmix, predictor;
   double ah;
+  PopTmap tm_tcur, tm_tmix, tm_u, tm_v;  // TMA descriptors (FULL mode, even nx_block)
 };
+#define TR_NS 3  // TMA pipeline depth (levels in flight per CTA)
 
 // masked 5-point coefficients at tile point (ii,jj): hmix_del2.F90:1064-1078 / hmix_del4.F90:1014-1023
 struct Coef5 {
@@ -55,22 +57,28 @@ __device__ __forceinline__ double lap5(const Coef5& c, const double* t, int ii, 
          c.ce * t[TIX(ii + 1, jj)] + c.cw * t[TIX(ii - 1, jj)];
 }
 
-template <int MODE, bool DEL4, bool UPW>
-__global__ void __launch_bounds__(POP_NTHREADS)
-tracer_column_kernel(const TracerArgs a) {
+// TMA = true : levels are staged by cp.async.bulk.tensor into a TR_NS-deep ring of stages, one mbarrier
+//              per stage; a single elected thread issues the copies, so no thread spends instructions
+//              or registers on halo loads and DRAM latency is hidden by the ring, not by occupancy.
+// TMA = false: cooperative plain loads into a single stage (slab entry points, odd nx_block).
+template <int MODE, bool DEL4, bool UPW, bool TMA>
+__global__ void __launch_bounds__(POP_NTHREADS, 2)
+tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
   POP_DYN_SMEM(smem_raw);
+  constexpr int NS = TMA ? TR_NS : 1;
+  constexpr int STAGE_TILES = 2 * NTC + 2;  // tc[NTC], tm[NTC], u, v
   double* sm = (double*)smem_raw;
-  double* s_dtn = sm;
+  double* s_stage = sm;                                   // [NS][STAGE_TILES][TN]
+  double* s_dtn = s_stage + NS * STAGE_TILES * POP_TN;
   double* s_dts = s_dtn + POP_TN;
   double* s_dte = s_dts + POP_TN;
   double* s_dtw = s_dte + POP_TN;
   double* s_ahf = s_dtw + POP_TN;
-  double* s_ud = s_ahf + POP_TN;
-  double* s_vd = s_ud + POP_TN;
-  double* s_tc = s_vd + POP_TN;            // [NTC][TN]
-  double* s_tm = s_tc + NTC * POP_TN;      // [NTC][TN]
-  double* s_d2 = s_tm + NTC * POP_TN;      // [NTC][TN]
+  double* s_dyu = s_ahf + POP_TN;
+  double* s_dxu = s_dyu + POP_TN;
+  double* s_d2 = s_dxu + POP_TN;           // [NTC][TN]
   int* s_kmt = (int*)(s_d2 + NTC * POP_TN);
+  uint64_t* s_bar = (uint64_t*)(s_kmt + POP_TN);  // [NS]
 
   const GridView& g = a.g;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
@@ -89,6 +97,10 @@ tracer_column_kernel(const TracerArgs a) {
   constexpr int HM = DEL4 ? 2 : 1;  // halo of the mixed tracer tile
 
   // ---- k-invariant staging
+  if (DO_ADV) {
+    tile_load(s_dyu, g.DYU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+    tile_load(s_dxu, g.DXU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+  }
   if (DO_HMIX) {
     tile_load_i(s_kmt, g.KMT, i0, j0, nxb, nyb, -2, POP_BX + 1, -2, POP_BY + 1, tid);
     tile_load(s_dtn, g.DTN, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
@@ -127,22 +139,56 @@ tracer_column_kernel(const TracerArgs a) {
     }
   }
 
+  const bool mix_alias = same_mix && DO_ADV && (TMA || HA >= HM);  // TMIX tile == TCUR tile
+  const uint32_t stage_bytes = (uint32_t)((a.nn * (mix_alias ? 1 : 2) + 2) * POP_TILE_BYTES);
+  // issue the TMA copies of level kk into ring slot (kk - k0) % NS (one thread)
+  auto issue = [&](int kk) {
+    const int sl = (kk - a.k0) % NS;
+    double* st = s_stage + (size_t)sl * STAGE_TILES * POP_TN;
+    mbar_expect_tx(&s_bar[sl], stage_bytes);
+    for (int m = 0; m < a.nn; m++) {
+      const int z = (a.n0 + m) * km + (kk - 1);
+      tma_load_tile(st + m * POP_TN, &a.tm_tcur, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
+      if (!mix_alias) tma_load_tile(st + (NTC + m) * POP_TN, &a.tm_tmix, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
+    }
+    tma_load_tile(st + 2 * NTC * POP_TN, &a.tm_u, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
+    tma_load_tile(st + (2 * NTC + 1) * POP_TN, &a.tm_v, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
+  };
+  if (TMA) {
+    if (tid == 0) {
+      for (int sl = 0; sl < NS; sl++) mbar_init(&s_bar[sl], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int kk = a.k0; kk <= a.k1 && kk < a.k0 + NS; kk++) issue(kk);
+  }
+
   for (int k = a.k0; k <= a.k1; k++) {
-    __syncthreads();
-    // ---- stage level k
-    if (DO_ADV) {
-      tile_load_prod(s_ud, a.UCUR + (size_t)(k - 1) * n2, g.DYU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
-      tile_load_prod(s_vd, a.VCUR + (size_t)(k - 1) * n2, g.DXU, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
-    }
+    const int slot = (k - a.k0) % NS;
+    double* s_tc = s_stage + (size_t)slot * STAGE_TILES * POP_TN;  // [NTC][TN]
+    double* s_tm = mix_alias ? s_tc : s_tc + NTC * POP_TN;          // [NTC][TN]
+    double* s_u = s_tc + 2 * NTC * POP_TN;
+    double* s_v = s_u + POP_TN;
+    if (TMA) {
+      mbar_wait(&s_bar[slot], (uint32_t)(((k - a.k0) / NS) & 1));
+    } else {
+      __syncthreads();
+      // ---- stage level k
+      if (DO_ADV) {
+        tile_load(s_u, a.UCUR + (size_t)(k - 1) * n2, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+        tile_load(s_v, a.VCUR + (size_t)(k - 1) * n2, i0, j0, nxb, nyb, -1, POP_BX - 1, -1, POP_BY - 1, tid);
+      }
 #pragma unroll
-    for (int m = 0; m < NTC; m++) {
-      if (m >= a.nn) continue;
-      const size_t lev = ((size_t)(a.n0 + m) * km + (k - 1)) * n2;
-      if (DO_ADV) tile_load(s_tc + m * POP_TN, a.TCUR + lev, i0, j0, nxb, nyb, -HA, POP_BX - 1 + HA, -HA, POP_BY - 1 + HA, tid);
-      if (DO_HMIX && !(same_mix && DO_ADV && HA >= HM))
-        tile_load(s_tm + m * POP_TN, a.TMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+      for (int m = 0; m < NTC; m++) {
+        if (m >= a.nn) continue;
+        const size_t lev = ((size_t)(a.n0 + m) * km + (k - 1)) * n2;
+        if (DO_ADV) tile_load(s_tc + m * POP_TN, a.TCUR + lev, i0, j0, nxb, nyb, -HA, POP_BX - 1 + HA, -HA, POP_BY - 1 + HA, tid);
+        if (DO_HMIX && !mix_alias)
+          tile_load(s_tm + m * POP_TN, a.TMIX + lev, i0, j0, nxb, nyb, -HM, POP_BX - 1 + HM, -HM, POP_BY - 1 + HM, tid);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (DO_HMIX && DEL4) {
       // D2TK = AHF * L(T) on the first halo ring (hmix_del4.F90:1025-1046)
       constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
@@ -152,22 +198,24 @@ tracer_column_kernel(const TracerArgs a) {
 #pragma unroll
         for (int m = 0; m < NTC; m++) {
           if (m >= a.nn) continue;
-          const double* tmix = (same_mix && DO_ADV && HA >= HM) ? s_tc + m * POP_TN : s_tm + m * POP_TN;
-          const double v = lap5(c, tmix, ii, jj);
+          const double v = lap5(c, s_tm + m * POP_TN, ii, jj);
           s_d2[m * POP_TN + TIX(ii, jj)] = a.lvariable_hmixt ? s_ahf[TIX(ii, jj)] * v : v;
         }
       }
       __syncthreads();
     }
-    if (!active) continue;
-
+    if (active) {
     // ---- flux velocities and the vertical velocity at the bottom of the level
     double ute = 0.0, utw = 0.0, vtn = 0.0, vts = 0.0, wtkb = 0.0;
     if (DO_ADV) {
-      ute = 0.5 * (s_ud[TIX(tx, ty)] + s_ud[TIX(tx, ty - 1)]);
-      utw = 0.5 * (s_ud[TIX(tx - 1, ty)] + s_ud[TIX(tx - 1, ty - 1)]);
-      vtn = 0.5 * (s_vd[TIX(tx, ty)] + s_vd[TIX(tx - 1, ty)]);
-      vts = 0.5 * (s_vd[TIX(tx, ty - 1)] + s_vd[TIX(tx - 1, ty - 1)]);
+#define UD(di, dj) (s_u[TIX(tx + (di), ty + (dj))] * s_dyu[TIX(tx + (di), ty + (dj))])
+#define VD(di, dj) (s_v[TIX(tx + (di), ty + (dj))] * s_dxu[TIX(tx + (di), ty + (dj))])
+      ute = 0.5 * (UD(0, 0) + UD(0, -1));
+      utw = 0.5 * (UD(-1, 0) + UD(-1, -1));
+      vtn = 0.5 * (VD(0, 0) + VD(-1, 0));
+      vts = 0.5 * (VD(0, -1) + VD(-1, -1));
+#undef UD
+#undef VD
       if (k < km) {
         const double FC = (vtn - vts + ute - utw) * tarea_r;
         wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
@@ -187,8 +235,7 @@ tracer_column_kernel(const TracerArgs a) {
       if (DO_HMIX) {
         if (DEL4) hd = a.ah * lap5(cc5, s_d2 + m * POP_TN, tx, ty);
         else {
-          const double* tmix = (same_mix && DO_ADV && HA >= HM) ? tc : s_tm + m * POP_TN;
-          hd = a.ah * lap5(cc5, tmix, tx, ty);
+          hd = a.ah * lap5(cc5, s_tm + m * POP_TN, tx, ty);
         }
       }
       // ---- advection
@@ -334,6 +381,11 @@ tracer_column_kernel(const TracerArgs a) {
       }
     }
     if (DO_ADV) wtk = wtkb;  // advection.F90:1960
+    }  // active
+    if (TMA) {
+      __syncthreads();  // every thread is done with this ring slot (and with the D2 tile)
+      if (tid == 0 && k + NS <= a.k1) issue(k + NS);
+    }
   }
   // ---- hand the carried state back to the slab caller
   if (MODE != TR_FULL && active) {
@@ -348,18 +400,29 @@ tracer_column_kernel(const TracerArgs a) {
   }
 }
 
-static size_t tracer_smem_bytes() { return sizeof(double) * POP_TN * (7 + 3 * NTC) + sizeof(int) * POP_TN; }
+static size_t tracer_smem_bytes(bool tma) {
+  const int ns = tma ? TR_NS : 1;
+  return sizeof(double) * POP_TN * (ns * (2 * NTC + 2) + 7 + NTC) + sizeof(int) * POP_TN + 8 * TR_NS;
+}
 
 template <int MODE>
-static int launch_tracer(const TracerArgs& a, bool del4, bool upw) {
+static int launch_tracer(const TracerArgs& a, bool del4, bool upw, bool tma) {
   void (*kfn)(const TracerArgs) = nullptr;
-  if (del4 && upw) kfn = tracer_column_kernel<MODE, true, true>;
-  else if (del4) kfn = tracer_column_kernel<MODE, true, false>;
-  else if (upw) kfn = tracer_column_kernel<MODE, false, true>;
-  else kfn = tracer_column_kernel<MODE, false, false>;
-  const size_t smem = tracer_smem_bytes();
+  if (tma) {
+    if (del4 && upw) kfn = tracer_column_kernel<MODE, true, true, true>;
+    else if (del4) kfn = tracer_column_kernel<MODE, true, false, true>;
+    else if (upw) kfn = tracer_column_kernel<MODE, false, true, true>;
+    else kfn = tracer_column_kernel<MODE, false, false, true>;
+  } else {
+    if (del4 && upw) kfn = tracer_column_kernel<MODE, true, true, false>;
+    else if (del4) kfn = tracer_column_kernel<MODE, true, false, false>;
+    else if (upw) kfn = tracer_column_kernel<MODE, false, true, false>;
+    else kfn = tracer_column_kernel<MODE, false, false, false>;
+  }
+  const size_t smem = tracer_smem_bytes(tma);
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
   POP_LAUNCH(kfn, col_grid(G.nxg, G.ny_local), col_block(), smem, a);
   return POP_SUCCESS;
@@ -396,18 +459,24 @@ int tracer_column(int mode, int k, const TracerIO& io) {
       if (a.adv[m] == POP_TADVECT_UPWIND3) upw = true;
     }
     switch (mode) {
-      case TR_FULL: POP_TRY(launch_tracer<TR_FULL>(a, del4, upw)); break;
+      case TR_FULL: {
+        const bool tma = !G.no_tma && make_tmap(&a.tm_tcur, a.TCUR, G.km * G.nt) &&
+                         make_tmap(&a.tm_tmix, a.TMIX, G.km * G.nt) && make_tmap(&a.tm_u, a.UCUR, G.km) &&
+                         make_tmap(&a.tm_v, a.VCUR, G.km);
+        POP_TRY(launch_tracer<TR_FULL>(a, del4, upw, tma));
+        break;
+      }
       case TR_ADVT: {
         // every pass restarts from the caller's WTK; only the last pass stores WTKB back
         TracerArgs b = a;
         if (n0 + NTC < G.nt) b.WTK = fld("WTK_C");  // scratch copy so the input survives
         if (n0 + NTC < G.nt)
           POP_CHECK_CUDA(cudaMemcpyAsync(b.WTK, a.WTK, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
-        POP_TRY(launch_tracer<TR_ADVT>(b, false, upw));
+        POP_TRY(launch_tracer<TR_ADVT>(b, false, upw, false));
         break;
       }
-      case TR_HDIFFT: POP_TRY(launch_tracer<TR_HDIFFT>(a, del4, false)); break;
-      case TR_VDIFFT: POP_TRY(launch_tracer<TR_VDIFFT>(a, false, false)); break;
+      case TR_HDIFFT: POP_TRY(launch_tracer<TR_HDIFFT>(a, del4, false, false)); break;
+      case TR_VDIFFT: POP_TRY(launch_tracer<TR_VDIFFT>(a, false, false, false)); break;
       default: POP_REQUIRE(false, "tracer_column: bad mode %d", mode);
     }
   }
