@@ -237,6 +237,7 @@ def kernel_bytes_per_cell(nt, v=2):
         "CLINIC": 8 * (4 + 3 + 1 + 2),              # Ucur,Vcur,Uold,Vold, RHO x3, VVC -> Unew,Vnew
         "VMIX_TRACER_IMPLICIT": 24 * 2 + 8 * v,     # per call on 2 tracers: RHS,TOLD in, TNEW out, VDC x v
         "STATE": 24,                                # T,S -> RHO
+        "MOMENTUM_FINISH": 8 * 7,                   # RHS u,v, VVC, Uold, Vold -> Unew, Vnew
     }
 
 
@@ -298,7 +299,7 @@ def run_pop(args):
     launches = p.launches() - l0
     ms = e0.elapsed_time(e1)
     p.timers(False)
-    tnames = ["TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "SOLVER", "BAROTROPIC", "HALO", "STEP"]
+    tnames = ["TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "MOMENTUM_FINISH", "SOLVER", "BAROTROPIC", "HALO", "STEP"]
     tm = {n: p.timer(n) for n in tnames}
     # ---- timed region 2: end to end through pop_step_coupled with pinned host buffers
     strip = p.ny_local * nx
@@ -336,7 +337,7 @@ def run_pop(args):
     bpc = kernel_bytes_per_cell(nt)
     local_cells = float(nx) * p.ny_local * km
     kern = {}
-    for n in ("TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE"):
+    for n in ("TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "MOMENTUM_FINISH"):
         tms, calls = tm[n]
         if calls:
             per = tms / calls

@@ -62,9 +62,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   double* s_dmn = s_dmc + POP_TN;
   double* s_dme = s_dmn + POP_TN;
   double* s_amf = s_dme + POP_TN;
-  double* s_d2u = s_amf + POP_TN;
-  double* s_d2v = s_d2u + POP_TN;
-  int* s_kmu = (int*)(s_d2v + POP_TN);
+  double* s_d2base = s_amf + POP_TN;  // [TMA ? 2 : 1][2][TN]: D2U, D2V
+  int* s_kmu = (int*)(s_d2base + (TMA ? 4 : 2) * POP_TN);
   uint64_t* s_bar = (uint64_t*)(s_kmu + POP_TN);
 
   const GridView& g = a.g;
@@ -175,6 +174,32 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       for (int kk = a.k0; kk <= a.k1 && kk < a.k0 + NS; kk++) issue(kk);
   }
 
+  // first application of the del4 operator on the halo ring (hmix_del4.F90:730-790)
+  auto compute_d2 = [&](int kk, const double* um, const double* vm, double* d2) {
+    constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
+    for (int p = tid; p < npts; p += POP_NTHREADS) {
+      const int jj = p / w - 1, ii = p % w - 1, t = TIX(ii, jj);
+      double d2u = mom_stencil(ct, um, vm, ii, jj, true);
+      double d2v = mom_stencil(ct, vm, um, ii, jj, false);
+      if (a.lvariable_hmixu) {
+        if (kk <= s_kmu[t]) { d2u = s_amf[t] * d2u; d2v = s_amf[t] * d2v; }
+        else { d2u = 0.0; d2v = 0.0; }
+      } else if (kk > s_kmu[t]) { d2u = 0.0; d2v = 0.0; }
+      d2[t] = d2u;
+      d2[POP_TN + t] = d2v;
+    }
+  };
+  if (TMA && DO_HMIX && DEL4) {
+    mbar_wait(&s_bar[0], 0u);
+    __syncthreads();  // coefficient tiles are staged
+    compute_d2(a.k0, same_mix ? s_stage : s_stage + 2 * POP_TN, same_mix ? s_stage + POP_TN : s_stage + 3 * POP_TN, s_d2base);
+    __syncthreads();
+  }
+  const bool uold_is_mix = (a.UOLD == a.UMIX) && !same_mix;
+  double vvc_nx = 0.0;
+  auto vvc_at = [&](int kk) { return g.VVC[(size_t)(((g.vvc_nk == 1) ? 1 : kk) - 1) * n2 + q]; };
+  if (DO_VDIF && active) vvc_nx = vvc_at(a.k0);
+
   for (int k = a.k0; k <= a.k1; k++) {
     const size_t lev = (size_t)(k - 1) * n2;
     const int slot = (k - a.k0) % NS;
@@ -208,22 +233,19 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     }
     const double* um = same_mix ? s_uc : s_um;
     const double* vm = same_mix ? s_vc : s_vm;
-    if (DO_HMIX && DEL4) {
-      // first application of the operator on the halo ring (hmix_del4.F90:730-790)
-      constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
-      for (int p = tid; p < npts; p += POP_NTHREADS) {
-        const int jj = p / w - 1, ii = p % w - 1, t = TIX(ii, jj);
-        double d2u = mom_stencil(ct, um, vm, ii, jj, true);
-        double d2v = mom_stencil(ct, vm, um, ii, jj, false);
-        if (a.lvariable_hmixu) {
-          if (k <= s_kmu[t]) { d2u = s_amf[t] * d2u; d2v = s_amf[t] * d2v; }
-          else { d2u = 0.0; d2v = 0.0; }
-        } else if (k > s_kmu[t]) { d2u = 0.0; d2v = 0.0; }
-        s_d2u[t] = d2u;
-        s_d2v[t] = d2v;
-      }
+    double* s_d2u = s_d2base + (TMA ? ((k - a.k0) & 1) * 2 * POP_TN : 0);
+    double* s_d2v = s_d2u + POP_TN;
+    if (DO_HMIX && DEL4 && !TMA) {
+      compute_d2(k, um, vm, s_d2u);
       __syncthreads();
     }
+    const bool have_next = TMA && (k < a.k1);
+    const int nslot = (k + 1 - a.k0) % NS;
+    const double* n_uc = s_stage + (size_t)nslot * MOM_STAGE_TILES * POP_TN;
+    const double* n_vc = n_uc + POP_TN;
+    const double* n_um = same_mix ? n_uc : n_uc + 2 * POP_TN;
+    const double* n_vm = same_mix ? n_vc : n_uc + 3 * POP_TN;
+    if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)(((k + 1 - a.k0) / NS) & 1));
     if (active) {
     double fx = 0.0, fy = 0.0;
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
@@ -252,7 +274,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         lvk = lvk + c_vc.dz2r[k] * wuk * (v_m + V);
       }
       if (k < km) {
-        const double Up = a.UCUR[lev + n2 + q], Vp = a.VCUR[lev + n2 + q];
+        const double Up = have_next ? n_uc[TIX(tx, ty)] : a.UCUR[lev + n2 + q];
+        const double Vp = have_next ? n_vc[TIX(tx, ty)] : a.VCUR[lev + n2 + q];
         luk = luk - c_vc.dz2r[k] * wukb * (U + Up);
         lvk = lvk - c_vc.dz2r[k] * wukb * (V + Vp);
       }
@@ -313,12 +336,13 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     double vdu = 0.0, vdv = 0.0;
     double uo_p = 0.0, vo_p = 0.0;
     if (DO_VDIF || MODE == MO_FULL) {
-      uo_p = (k < km) ? a.UOLD[lev + n2 + q] : uo_c;
-      vo_p = (k < km) ? a.VOLD[lev + n2 + q] : vo_c;
+      const bool from_tile = have_next && uold_is_mix;
+      uo_p = (k < km) ? (from_tile ? n_um[TIX(tx, ty)] : a.UOLD[lev + n2 + q]) : uo_c;
+      vo_p = (k < km) ? (from_tile ? n_vm[TIX(tx, ty)] : a.VOLD[lev + n2 + q]) : vo_c;
     }
     if (DO_VDIF) {
-      const int kk = (g.vvc_nk == 1) ? 1 : k;
-      const double vvc = g.VVC[(size_t)(kk - 1) * n2 + q];
+      const double vvc = vvc_nx;
+      if (k < a.k1) vvc_nx = vvc_at(k + 1);
       if (k == 1) {
         vuf = (kmu >= 1) ? a.SMF[q] : 0.0;
         vvf = (kmu >= 1) ? a.SMF[n2 + q] : 0.0;
@@ -380,7 +404,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     vo_c = vo_p;
     }  // active
     if (TMA) {
-      __syncthreads();  // every thread is done with this ring slot (and with the D2 tiles)
+      if (DO_HMIX && DEL4 && have_next) compute_d2(k + 1, n_um, n_vm, s_d2base + ((k + 1 - a.k0) & 1) * 2 * POP_TN);
+      __syncthreads();  // every thread is done with this ring slot; D2(k+1) is complete
       if (tid == 0 && k + NS <= a.k1) issue(k + NS);
     }
   }
@@ -404,7 +429,7 @@ static int launch_momentum(const MomentumArgs& a, bool del4, bool tma) {
   if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true> : momentum_column_kernel<MODE, false, true>;
   else kfn = del4 ? momentum_column_kernel<MODE, true, false> : momentum_column_kernel<MODE, false, false>;
   const int ns = tma ? MO_NS : 1;
-  const size_t smem = sizeof(double) * POP_TN * (ns * MOM_STAGE_TILES + MOM_FIXED_TILES) + sizeof(int) * POP_TN + 8 * MO_NS;
+  const size_t smem = sizeof(double) * POP_TN * (ns * MOM_STAGE_TILES + MOM_FIXED_TILES + (tma ? 2 : 0)) + sizeof(int) * POP_TN + 8 * MO_NS;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -465,75 +490,122 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
 // =====================================================================================
 // impvmixu + velocity finish
 // =====================================================================================
-template <int KMAX>
-__global__ void __launch_bounds__(128)
+// Same layout as impvmixt (pop_tracer.cu): E(k) in shared memory, F1/F2 streamed in place through
+// UNEW/VNEW, loads issued one chunk of MF_CH levels ahead of the recurrence.
+#define MF_CH 8
+#define MF_THREADS 128
+__global__ void __launch_bounds__(MF_THREADS, 3)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
                        const double* __restrict__ UOLD, const double* __restrict__ VOLD, double c2dtu,
                        int implicit_vmix, int finish) {
-  const int i = (g.ib - 1) + blockIdx.x * blockDim.x + threadIdx.x;
+  POP_DYN_SMEM(smem_raw);
+  double* sE = (double*)smem_raw + threadIdx.x;
+  const int i = (g.ib - 1) + blockIdx.x * MF_THREADS + threadIdx.x;
   const int j = (g.jb - 1) + blockIdx.y;
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
   const int km = g.km, kmu = g.KMU[q];
   double* Un = UNEW + q;
   double* Vn = VNEW + q;
+  const double* VVCq = g.VVC + q;
+  const size_t vstr = (g.vvc_nk == 1) ? 0 : n2;
   if (implicit_vmix) {
-    double E[KMAX];
     double A, B, C, D, F1, F2;
     {
       const double hfac = c_vc.dz[1] / c2dtu;
-      A = c_vc.afac_u[1] * g.VVC[q];
+      A = c_vc.afac_u[1] * VVCq[0];
       D = hfac + A;
-      E[0] = A / D;
-      B = hfac * E[0];
+      const double e = A / D;
+      sE[0] = e;
+      B = hfac * e;
       F1 = hfac * Un[0] / D;
       F2 = hfac * Vn[0] / D;
       Un[0] = F1;
       Vn[0] = F2;
     }
+    double uv[MF_CH], vv[MF_CH], cv[MF_CH], un[MF_CH], vn[MF_CH], cn[MF_CH];
 #pragma unroll
-    for (int k = 2; k <= KMAX; k++) {
-      if (k <= km) {
-        const int kk = (g.vvc_nk == 1) ? 1 : k;
-        const double hfac = c_vc.dz[k] / c2dtu;
-        C = A;
-        A = c_vc.afac_u[k] * g.VVC[(size_t)(kk - 1) * n2 + q];
-        if (k < kmu) D = hfac + A + B;
-        else if (k == kmu) D = hfac + B;
-        if (k <= kmu) {
-          E[k - 1] = A / D;
-          B = (hfac + B) * E[k - 1];
-          F1 = (hfac * Un[(size_t)(k - 1) * n2] + C * F1) / D;
-          F2 = (hfac * Vn[(size_t)(k - 1) * n2] + C * F2) / D;
-        } else {
-          E[k - 1] = 0.0;
-          F1 = 0.0;
-          F2 = 0.0;
-        }
-        Un[(size_t)(k - 1) * n2] = F1;
-        Vn[(size_t)(k - 1) * n2] = F2;
-      }
+    for (int c = 0; c < MF_CH; c++) {
+      const int k = 2 + c;
+      const bool in = (k <= km);
+      cv[c] = in ? VVCq[(size_t)(k - 1) * vstr] : 0.0;
+      uv[c] = in ? Un[(size_t)(k - 1) * n2] : 0.0;
+      vv[c] = in ? Vn[(size_t)(k - 1) * n2] : 0.0;
     }
-    // back substitution; F1,F2 = F(km)
+    for (int kb = 2; kb <= km; kb += MF_CH) {
 #pragma unroll
-    for (int k = KMAX - 1; k >= 1; k--) {
-      if (k <= km - 1) {
-        double f1 = Un[(size_t)(k - 1) * n2], f2 = Vn[(size_t)(k - 1) * n2];
-        if (k < kmu) {
-          f1 = f1 + E[k - 1] * F1;
-          f2 = f2 + E[k - 1] * F2;
-          Un[(size_t)(k - 1) * n2] = f1;
-          Vn[(size_t)(k - 1) * n2] = f2;
-        }
-        F1 = f1;
-        F2 = f2;
+      for (int c = 0; c < MF_CH; c++) {
+        const int k = kb + MF_CH + c;
+        const bool in = (k <= km);
+        cn[c] = in ? VVCq[(size_t)(k - 1) * vstr] : 0.0;
+        un[c] = in ? Un[(size_t)(k - 1) * n2] : 0.0;
+        vn[c] = in ? Vn[(size_t)(k - 1) * n2] : 0.0;
       }
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) {
+        const int k = kb + c;
+        if (k <= km) {
+          const double hfac = c_vc.dz[k] / c2dtu;
+          C = A;
+          A = c_vc.afac_u[k] * cv[c];
+          if (k < kmu) D = hfac + A + B;
+          else if (k == kmu) D = hfac + B;
+          if (k <= kmu) {
+            const double e = A / D;
+            sE[(size_t)(k - 1) * MF_THREADS] = e;
+            B = (hfac + B) * e;
+            F1 = (hfac * uv[c] + C * F1) / D;
+            F2 = (hfac * vv[c] + C * F2) / D;
+          } else {
+            F1 = 0.0;
+            F2 = 0.0;
+          }
+          Un[(size_t)(k - 1) * n2] = F1;
+          Vn[(size_t)(k - 1) * n2] = F2;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) { cv[c] = cn[c]; uv[c] = un[c]; vv[c] = vn[c]; }
+    }
+    // back substitution: only levels k < kmu change; F1,F2 = F(km)
+#pragma unroll
+    for (int c = 0; c < MF_CH; c++) {
+      const int k = km - 1 - c;
+      uv[c] = (k >= 1) ? Un[(size_t)(k - 1) * n2] : 0.0;
+      vv[c] = (k >= 1) ? Vn[(size_t)(k - 1) * n2] : 0.0;
+    }
+    for (int kt = km - 1; kt >= 1; kt -= MF_CH) {
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) {
+        const int k = kt - MF_CH - c;
+        un[c] = (k >= 1) ? Un[(size_t)(k - 1) * n2] : 0.0;
+        vn[c] = (k >= 1) ? Vn[(size_t)(k - 1) * n2] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) {
+        const int k = kt - c;
+        if (k >= 1) {
+          double f1 = uv[c], f2 = vv[c];
+          if (k < kmu) {
+            const double e = sE[(size_t)(k - 1) * MF_THREADS];
+            f1 = f1 + e * F1;
+            f2 = f2 + e * F2;
+            Un[(size_t)(k - 1) * n2] = f1;
+            Vn[(size_t)(k - 1) * n2] = f2;
+          }
+          F1 = f1;
+          F2 = f2;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) { uv[c] = un[c]; vv[c] = vn[c]; }
     }
   }
   if (!finish) return;
   // U = Uold + dU ; remove the vertical mean ; KMU mask (baroclinic.F90:1077-1129)
   const double hur = g.HUR[q];
   double w1 = 0.0, w2 = 0.0;
+#pragma unroll 8
   for (int k = 1; k <= km; k++) {
     const size_t o = (size_t)(k - 1) * n2;
     const double u = UOLD[o + q] + Un[o], v = VOLD[o + q] + Vn[o];
@@ -544,6 +616,7 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   }
   w1 = w1 * hur;
   w2 = w2 * hur;
+#pragma unroll 8
   for (int k = 1; k <= km; k++) {
     const size_t o = (size_t)(k - 1) * n2;
     if (k <= kmu) {
@@ -559,13 +632,13 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
 static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD,
                          int implicit_vmix, int finish) {
   GridView g = grid_view();
-  dim3 block(128, 1, 1), grid((unsigned)((G.nxg + 127) / 128), (unsigned)G.ny_local, 1);
-  auto k32 = momentum_finish_kernel<32>;
-  auto k64 = momentum_finish_kernel<64>;
-  auto kmx = momentum_finish_kernel<POP_KMAX>;
-  if (G.km <= 32) POP_LAUNCH(k32, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
-  else if (G.km <= 64) POP_LAUNCH(k64, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
-  else POP_LAUNCH(kmx, grid, block, 0, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
+  dim3 block(MF_THREADS, 1, 1), grid((unsigned)((G.nxg + MF_THREADS - 1) / MF_THREADS), (unsigned)G.ny_local, 1);
+  const size_t smem = sizeof(double) * MF_THREADS * (size_t)G.km;
+#ifndef POP_EMUL
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+  POP_LAUNCH(momentum_finish_kernel, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
   return pop_post_launch("momentum_finish");
 }
 
@@ -574,6 +647,7 @@ int impvmixu_dev(double* UNEW, double* VNEW) {
   return launch_finish(UNEW, VNEW, nullptr, nullptr, 1, 0);
 }
 int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD) {
+  ScopedTimer tm("MOMENTUM_FINISH");
   return launch_finish(UNEW, VNEW, UOLD, VOLD, G.cfg.implicit_vertical_mix, 1);
 }
 

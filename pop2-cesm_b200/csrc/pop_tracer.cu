@@ -76,8 +76,8 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
   double* s_ahf = s_dtw + POP_TN;
   double* s_dyu = s_ahf + POP_TN;
   double* s_dxu = s_dyu + POP_TN;
-  double* s_d2 = s_dxu + POP_TN;           // [NTC][TN]
-  int* s_kmt = (int*)(s_d2 + NTC * POP_TN);
+  double* s_d2base = s_dxu + POP_TN;       // [TMA ? 2 : 1][NTC][TN]
+  int* s_kmt = (int*)(s_d2base + (TMA ? 2 : 1) * NTC * POP_TN);
   uint64_t* s_bar = (uint64_t*)(s_kmt + POP_TN);  // [NS]
 
   const GridView& g = a.g;
@@ -164,6 +164,42 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       for (int kk = a.k0; kk <= a.k1 && kk < a.k0 + NS; kk++) issue(kk);
   }
 
+  // D2TK = AHF * L(T) on the first halo ring (hmix_del4.F90:1025-1046)
+  auto compute_d2 = [&](int kk, const double* tmix, double* d2) {
+    constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
+    for (int p = tid; p < npts; p += POP_NTHREADS) {
+      const int jj = p / w - 1, ii = p % w - 1;
+      const Coef5 c = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, ii, jj, kk);
+#pragma unroll
+      for (int m = 0; m < NTC; m++) {
+        if (m >= a.nn) continue;
+        const double v = lap5(c, tmix + m * POP_TN, ii, jj);
+        d2[m * POP_TN + TIX(ii, jj)] = a.lvariable_hmixt ? s_ahf[TIX(ii, jj)] * v : v;
+      }
+    }
+  };
+  if (TMA && DO_HMIX && DEL4) {  // prologue of the software pipeline: D2 of the first level
+    mbar_wait(&s_bar[0], 0u);
+    compute_d2(a.k0, mix_alias ? s_stage : s_stage + NTC * POP_TN, s_d2base);
+    __syncthreads();
+  }
+  const bool told_is_mix = (a.TOLD == a.TMIX);
+  // VDC of the next level is fetched one level ahead (its latency hides behind a whole level)
+  double vdc_nx[NTC];
+#pragma unroll
+  for (int m = 0; m < NTC; m++) vdc_nx[m] = 0.0;
+  auto vdc_at = [&](int m, int kk) {
+    const int n = a.n0 + m;
+    const int mt2 = (n + 1 < g.vdc_nd) ? n + 1 : g.vdc_nd;
+    const int kq = (g.vdc_nk == 1) ? 1 : kk;
+    return g.VDC[((size_t)(mt2 - 1) * g.vdc_nk + (kq - g.vdc_k0)) * n2 + q];
+  };
+  if (DO_VDIF && active) {
+#pragma unroll
+    for (int m = 0; m < NTC; m++)
+      if (m < a.nn) vdc_nx[m] = vdc_at(m, a.k0);
+  }
+
   for (int k = a.k0; k <= a.k1; k++) {
     const int slot = (k - a.k0) % NS;
     double* s_tc = s_stage + (size_t)slot * STAGE_TILES * POP_TN;  // [NTC][TN]
@@ -189,21 +225,18 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       }
       __syncthreads();
     }
-    if (DO_HMIX && DEL4) {
-      // D2TK = AHF * L(T) on the first halo ring (hmix_del4.F90:1025-1046)
-      constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
-      for (int p = tid; p < npts; p += POP_NTHREADS) {
-        const int jj = p / w - 1, ii = p % w - 1;
-        const Coef5 c = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, ii, jj, k);
-#pragma unroll
-        for (int m = 0; m < NTC; m++) {
-          if (m >= a.nn) continue;
-          const double v = lap5(c, s_tm + m * POP_TN, ii, jj);
-          s_d2[m * POP_TN + TIX(ii, jj)] = a.lvariable_hmixt ? s_ahf[TIX(ii, jj)] * v : v;
-        }
-      }
+    double* s_d2 = s_d2base + (TMA ? ((k - a.k0) & 1) * NTC * POP_TN : 0);
+    if (DO_HMIX && DEL4 && !TMA) {
+      compute_d2(k, s_tm, s_d2);
       __syncthreads();
     }
+    // TMA path: the next level has (normally) landed already; it provides T(k+1) at the column and is
+    // the input of the D2 pass that is overlapped with this level's output pass
+    const bool have_next = TMA && (k < a.k1);
+    const int nslot = (k + 1 - a.k0) % NS;
+    double* n_tc = s_stage + (size_t)nslot * STAGE_TILES * POP_TN;
+    double* n_tm = mix_alias ? n_tc : n_tc + NTC * POP_TN;
+    if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)(((k + 1 - a.k0) / NS) & 1));
     if (active) {
     // ---- flux velocities and the vertical velocity at the bottom of the level
     double ute = 0.0, utw = 0.0, vtn = 0.0, vts = 0.0, wtkb = 0.0;
@@ -242,7 +275,7 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       double L = 0.0;
       if (DO_ADV) {
         const double T = tc[TIX(tx, ty)];
-        const double Tp = (k < km) ? a.TCUR[lev + n2] : 0.0;
+        const double Tp = (k < km) ? (have_next ? n_tc[m * POP_TN + TIX(tx, ty)] : a.TCUR[lev + n2]) : 0.0;
         if (a.adv[m] == POP_TADVECT_CENTERED) {  // advection.F90:2243-2301
           L = 0.5 *
               ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
@@ -334,10 +367,10 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       // ---- explicit vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
       double vd = 0.0;
       if (DO_VDIF) {
-        const int mt2 = (n + 1 < g.vdc_nd) ? n + 1 : g.vdc_nd;
-        const int kk = (g.vdc_nk == 1) ? 1 : k;
-        const double vdc = g.VDC[((size_t)(mt2 - 1) * g.vdc_nk + (kk - g.vdc_k0)) * n2 + q];
-        const double told_p = (k < km) ? a.TOLD[lev + n2] : told_c[m];
+        const double vdc = vdc_nx[m];
+        if (k < a.k1) vdc_nx[m] = vdc_at(m, k + 1);
+        const double told_p = (k < km) ? ((have_next && told_is_mix) ? n_tm[m * POP_TN + TIX(tx, ty)] : a.TOLD[lev + n2])
+                                       : told_c[m];
         if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
         const double VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
         vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
@@ -383,7 +416,9 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
     if (DO_ADV) wtk = wtkb;  // advection.F90:1960
     }  // active
     if (TMA) {
-      __syncthreads();  // every thread is done with this ring slot (and with the D2 tile)
+      if (DO_HMIX && DEL4 && have_next)
+        compute_d2(k + 1, n_tm, s_d2base + ((k + 1 - a.k0) & 1) * NTC * POP_TN);
+      __syncthreads();  // every thread is done with this ring slot; D2(k+1) is complete
       if (tid == 0 && k + NS <= a.k1) issue(k + NS);
     }
   }
@@ -402,7 +437,7 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
 
 static size_t tracer_smem_bytes(bool tma) {
   const int ns = tma ? TR_NS : 1;
-  return sizeof(double) * POP_TN * (ns * (2 * NTC + 2) + 7 + NTC) + sizeof(int) * POP_TN + 8 * TR_NS;
+  return sizeof(double) * POP_TN * (ns * (2 * NTC + 2) + 7 + (tma ? 2 : 1) * NTC) + sizeof(int) * POP_TN + 8 * TR_NS;
 }
 
 template <int MODE>
@@ -486,79 +521,122 @@ int tracer_column(int mode, int k, const TracerIO& io) {
 // =====================================================================================
 // impvmixt / impvmixt_correct: vertical_mix.F90:1164-1382, :1460-1672
 // =====================================================================================
-// One thread per physical column.  For each tracer: forward elimination keeps E(k) in registers
-// (fully unrolled, KMAX compile-time) and streams F(k) through FB (the output array itself for the
-// predictor form, a work array for the corrector); back substitution re-reads F(k) while it is
-// still L2-resident.
-template <int KMAX, bool CORRECT>
-__global__ void __launch_bounds__(128)
+// One thread per physical column, 128 columns (one row segment) per CTA.  The Thomas coefficients
+// E(k) of the CTA's columns live in shared memory (km x 128 doubles, conflict-free), the eliminated
+// right-hand side F(k) is streamed in place through the output array (it is re-read by the back
+// substitution while still L2-resident), and every global load of a chunk of IV_CH levels is issued
+// one chunk ahead of the (division-bound) recurrence that consumes it, so the dependent chain never
+// waits on DRAM.  Registers stay small, so 3 CTAs are resident per SM.
+#define IV_CH 8
+#define IV_THREADS 128
+template <bool CORRECT>
+__global__ void __launch_bounds__(IV_THREADS, 3)
 impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict__ TOLD,
                 const double* __restrict__ PSFC, const double* __restrict__ RHS, double* FB,
                 int nfirst, int nlast, int varthick) {
-  const int i = (g.ib - 1) + blockIdx.x * blockDim.x + threadIdx.x;
+  POP_DYN_SMEM(smem_raw);
+  double* sE = (double*)smem_raw + threadIdx.x;  // E(k) at sE[(k-1)*IV_THREADS]
+  const int i = (g.ib - 1) + blockIdx.x * IV_THREADS + threadIdx.x;
   const int j = (g.jb - 1) + blockIdx.y;
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
   const int km = g.km, kmt = g.KMT[q];
   const double hfac1 = c_vc.dz[1] / c_vc.c2dtt[1];
   const double H1 = varthick ? hfac1 + PSFC[q] / (POP_GRAV * c_vc.c2dtt[1]) : hfac1;
-  double E[KMAX];
   for (int n = nfirst; n <= nlast; n++) {  // 1-based tracer index
     const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
-    const double* VDC = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q;  // + (kk - k0)*n2
+    // VDC(:,:,k,mt2) = VDCq[(k - vdc_k0) * n2] (a single level when vdc_nk == 1)
+    const double* VDCq = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q;
+    const size_t vstr = (g.vdc_nk == 1) ? 0 : n2;
+    const size_t voff = (g.vdc_nk == 1) ? (size_t)(1 - g.vdc_k0) * n2 : (size_t)(0 - g.vdc_k0) * n2;  // + k*vstr
     double* Tn = TNEW + (size_t)(n - 1) * km * n2 + q;
+    const double* To = CORRECT ? nullptr : TOLD + (size_t)(n - 1) * km * n2 + q;
     double* Fb = CORRECT ? FB + q : Tn;
     double A, B, C, D, Fm;
     {
-      const int kk = (g.vdc_nk == 1) ? 1 : 1;
-      A = c_vc.afac_t[1] * VDC[(size_t)(kk - g.vdc_k0) * n2];
+      A = c_vc.afac_t[1] * VDCq[voff + vstr];
       D = H1 + A;
-      E[0] = A / D;
-      B = H1 * E[0];
+      const double e = A / D;
+      sE[0] = e;
+      B = H1 * e;
       const double R1 = CORRECT ? RHS[(size_t)(n - 1) * n2 + q] : Tn[0];
       Fm = hfac1 * R1 / D;
       Fb[0] = Fm;
     }
+    // ---- forward elimination, levels 2..km in chunks; loads of chunk c+1 are in flight during chunk c
+    double rv[IV_CH], vv[IV_CH], rn[IV_CH], vn[IV_CH];
 #pragma unroll
-    for (int k = 2; k <= KMAX; k++) {
-      if (k <= km) {
-        const int kk = (g.vdc_nk == 1) ? 1 : k;
-        C = A;
-        A = c_vc.afac_t[k] * VDC[(size_t)(kk - g.vdc_k0) * n2];
-        const double hfac = c_vc.dz[k] / c_vc.c2dtt[k];
-        double F;
-        if (k > kmt) {
-          F = 0.0;
-          E[k - 1] = 0.0;
-        } else {
-          if (k == kmt) D = hfac + B;
-          else D = hfac + A + B;
-          E[k - 1] = A / D;
-          B = (hfac + B) * E[k - 1];
-          if (CORRECT) F = C * Fm / D;
-          else F = (hfac * Tn[(size_t)(k - 1) * n2] + C * Fm) / D;
-        }
-        Fb[(size_t)(k - 1) * n2] = F;
-        Fm = F;
-      }
+    for (int c = 0; c < IV_CH; c++) {
+      const int k = 2 + c;
+      vv[c] = (k <= km) ? VDCq[voff + (size_t)k * vstr] : 0.0;
+      rv[c] = (!CORRECT && k <= km) ? Tn[(size_t)(k - 1) * n2] : 0.0;
     }
-    // back substitution + final update; Fm = F(km)
+    for (int kb = 2; kb <= km; kb += IV_CH) {
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) {
+        const int k = kb + IV_CH + c;
+        vn[c] = (k <= km) ? VDCq[voff + (size_t)k * vstr] : 0.0;
+        rn[c] = (!CORRECT && k <= km) ? Tn[(size_t)(k - 1) * n2] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) {
+        const int k = kb + c;
+        if (k <= km) {
+          C = A;
+          A = c_vc.afac_t[k] * vv[c];
+          const double hfac = c_vc.dz[k] / c_vc.c2dtt[k];
+          double F;
+          if (k > kmt) {
+            F = 0.0;
+          } else {
+            if (k == kmt) D = hfac + B;
+            else D = hfac + A + B;
+            const double e = A / D;
+            sE[(size_t)(k - 1) * IV_THREADS] = e;
+            B = (hfac + B) * e;
+            if (CORRECT) F = C * Fm / D;
+            else F = (hfac * rv[c] + C * Fm) / D;
+          }
+          Fb[(size_t)(k - 1) * n2] = F;
+          Fm = F;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) { vv[c] = vn[c]; rv[c] = rn[c]; }
+    }
+    // ---- back substitution + final update, levels km..1 in chunks (Fm = F(km))
     double Fp = Fm;
     {
       double* t = Tn + (size_t)(km - 1) * n2;
-      const double base = CORRECT ? *t : TOLD[(size_t)((n - 1) * km + (km - 1)) * n2 + q];
+      const double base = CORRECT ? *t : To[(size_t)(km - 1) * n2];
       *t = base + Fp;
     }
+    // chunk covers levels kt, kt-1, ..., kt-IV_CH+1
 #pragma unroll
-    for (int k = KMAX - 1; k >= 1; k--) {
-      if (k <= km - 1) {
-        double F = Fb[(size_t)(k - 1) * n2];
-        if (k < kmt) F = F + E[k - 1] * Fp;
-        double* t = Tn + (size_t)(k - 1) * n2;
-        const double base = CORRECT ? *t : TOLD[(size_t)((n - 1) * km + (k - 1)) * n2 + q];
-        *t = base + F;
-        Fp = F;
+    for (int c = 0; c < IV_CH; c++) {
+      const int k = km - 1 - c;
+      rv[c] = (k >= 1) ? Fb[(size_t)(k - 1) * n2] : 0.0;
+      vv[c] = (k >= 1) ? (CORRECT ? Tn[(size_t)(k - 1) * n2] : To[(size_t)(k - 1) * n2]) : 0.0;
+    }
+    for (int kt = km - 1; kt >= 1; kt -= IV_CH) {
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) {
+        const int k = kt - IV_CH - c;
+        rn[c] = (k >= 1) ? Fb[(size_t)(k - 1) * n2] : 0.0;
+        vn[c] = (k >= 1) ? (CORRECT ? Tn[(size_t)(k - 1) * n2] : To[(size_t)(k - 1) * n2]) : 0.0;
       }
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) {
+        const int k = kt - c;
+        if (k >= 1) {
+          double F = rv[c];
+          if (k < kmt) F = F + sE[(size_t)(k - 1) * IV_THREADS] * Fp;
+          Tn[(size_t)(k - 1) * n2] = vv[c] + F;
+          Fp = F;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) { rv[c] = rn[c]; vv[c] = vn[c]; }
     }
   }
 }
@@ -570,21 +648,17 @@ int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const dou
   ScopedTimer tm("VMIX_TRACER_IMPLICIT");
   GridView g = grid_view();
   const int varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
-  dim3 block(128, 1, 1), grid((unsigned)((G.nxg + 127) / 128), (unsigned)G.ny_local, 1);
+  dim3 block(IV_THREADS, 1, 1), grid((unsigned)((G.nxg + IV_THREADS - 1) / IV_THREADS), (unsigned)G.ny_local, 1);
   double* FB = fld("WORK3D_E");
-#define IMPV(KM_)                                                                              \
-  do {                                                                                         \
-    auto kc = impvmixt_kernel<KM_, true>;                                                      \
-    auto kp = impvmixt_kernel<KM_, false>;                                                     \
-    if (correct)                                                                               \
-      POP_LAUNCH(kc, grid, block, 0, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);    \
-    else                                                                                       \
-      POP_LAUNCH(kp, grid, block, 0, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);    \
-  } while (0)
-  if (G.km <= 32) IMPV(32);
-  else if (G.km <= 64) IMPV(64);
-  else IMPV(POP_KMAX);
-#undef IMPV
+  const size_t smem = sizeof(double) * IV_THREADS * (size_t)G.km;
+  auto kc = impvmixt_kernel<true>;
+  auto kp = impvmixt_kernel<false>;
+#ifndef POP_EMUL
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+  if (correct) POP_LAUNCH(kc, grid, block, smem, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);
+  else POP_LAUNCH(kp, grid, block, smem, g, TNEW, TOLD, PSFC, RHS, FB, nfirst, nlast, varthick);
   return pop_post_launch("impvmixt");
 }
 
