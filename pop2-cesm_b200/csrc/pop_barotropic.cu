@@ -300,15 +300,82 @@ static int chrongear(double* X, const double* B) {
 }
 
 // ------------------------------------------------------------------ PCSI :1510-1835
+// One fused kernel per iteration.  The reference iteration m is
+//     halo(R) ; Q = om_m R + (csy om_m - 1) Q ; X = X + Q ; R = (B - A X) A0R        [check: sum r^2]
+// and here the same arithmetic is cut one half-iteration later: kernel K(m) takes X_m and produces
+//     r = B - A X_m  [check: sum r^2] ; R = r A0R ; Q_{m+1} = om_{m+1} R + (csy om_{m+1} - 1) Q_m ;
+//     X_{m+1} = X_m + Q_{m+1}
+// so R never touches memory and every operand is read once: X (stencil, through L1), B, Q, the four
+// stored weights (A0R = 1/C is recomputed from the centre weight, bit-identical to EW_A0R) in, Q and
+// the NEXT X out = 72 B per point instead of 13 array passes.  X is double-buffered because a
+// neighbouring CTA still reads X_m while this one writes X_{m+1}.  Ghost cells: the reference
+// refreshes R's ghost cells before the update, which makes Q and X ghost cells bitwise copies of
+// their source points; here the kernel updates every point from the locally computed R (exactly what
+// the reference does on ghost rows no message targets, i.e. closed boundaries) and one fused halo
+// pass then overwrites the ghost cells of Q_{m+1} and X_{m+1} with those copies.
+#define PC_TX 64
+#define PC_TY 4
+struct PcsiArgs {
+  BtView v;
+  const double* X;   // X_m
+  double* Xn;        // X_{m+1}
+  double* Q;         // in: Q_m, out: Q_{m+1}
+  const double* B;
+  double om, c1;     // om_{m+1}, csy*om_{m+1} - 1
+  int advance;       // 0: last iteration (residual only)
+  double* partials;  // [gridDim.x*gridDim.y][2] dd block partials of sum r^2 (SUM only)
+};
+template <bool SUM>
+__global__ void __launch_bounds__(PC_TX * PC_TY)
+pcsi_iter_kernel(const PcsiArgs a) {
+  const BtView& v = a.v;
+  const int tx = threadIdx.x % PC_TX, ty = threadIdx.x / PC_TX;
+  const int i = blockIdx.x * PC_TX + tx, j = blockIdx.y * PC_TY + ty;
+  dd acc{0.0, 0.0};
+  if (i < v.nxb && j < v.nyb) {
+    const int nxb = v.nxb;
+    const size_t q = (size_t)j * nxb + i;
+    const double c = ldg(v.C + q);
+    double ax = 0.0;
+    if (i >= 1 && i <= nxb - 2 && j >= 1 && j <= v.nyb - 2) {
+      const double* X = a.X;
+      ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
+           ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
+           ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
+           ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
+    }
+    const double r = ldg(a.B + q) - ax;
+    if (SUM && bt_physical(v, i, j)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + q));
+    if (a.advance) {
+      const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+      const double R = r * a0r;
+      const double qv = a.om * R + a.c1 * a.Q[q];
+      a.Q[q] = qv;
+      a.Xn[q] = ldg(a.X + q) + qv;
+    }
+  }
+  if (SUM) {
+    dd rsum = block_reduce_dd(acc);
+    if (threadIdx.x == 0) {
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      a.partials[b * 2] = rsum.hi;
+      a.partials[b * 2 + 1] = rsum.lo;
+    }
+  }
+}
+
 static int pcsi(double* X, const double* B) {
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
             start = G.cfg.convergence_check_start;
-  double *R = fld("BT_R"), *Q = fld("BT_Q"), *A0R = fld("BT_A0R");
+  double *R = fld("BT_R"), *A0R = fld("BT_A0R");
+  double* W = fld("BT_PCSI");  // [X0, Q, X1]: (X0,Q) and (Q,X1) are both 2-level fields for the halo pass
+  double *Xb[2] = {W, W + 2 * G.n2}, *Q = W + G.n2;
   double rr = 0.0;
   const double csalpha = 2.0 / (G.pcsiMaxEigs - G.pcsiMinEigs);
   const double csbeta = (G.pcsiMaxEigs + G.pcsiMinEigs) / (G.pcsiMaxEigs - G.pcsiMinEigs);
   const double csy = csbeta / csalpha;
   double csomga = 2.0 / csy;
+  // ---- prologue, as the reference (:1640-1700)
   BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
   bt_ew<EW_PCSI_INIT>(R, Q, A0R, nullptr, nullptr, nullptr, nullptr, 1.0 / csy);
   POP_TRY(bt_halo(Q));
@@ -316,21 +383,39 @@ static int pcsi(double* X, const double* B) {
   BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
   POP_TRY(bt_halo(R));
   bt_ew<EW_MUL>(R, R, A0R);
+  POP_TRY(bt_halo(R));
+  // ---- first half-iteration: Q_1, X_1 from the halo-updated preconditioned residual
+  csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
+  POP_CHECK_CUDA(cudaMemcpyAsync(Xb[0], X, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  bt_ew<EW_PCSI_QX>(Q, Xb[0], R, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
   G.numIterations = maxIt;
+  const dim3 grid((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((G.nyb + PC_TY - 1) / PC_TY), 1);
+  const int nblk = (int)(grid.x * grid.y);
+  POP_TRY(reduce_reserve_partials(nblk));
+  int cur = 0;  // X_m lives in Xb[cur]
   for (int m = 1; m <= maxIt; m++) {
-    csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
-    POP_TRY(bt_halo(R));  // R already holds M^-1 R
     const bool check = (m % freq == 0) && (m >= start);
-    bt_ew<EW_PCSI_QX>(Q, X, R, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
-    BT_ST(BT_RESID_A0R, R, X, B, A0R, 0.0, check ? 1 : 0);
+    csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
+    PcsiArgs a;
+    a.v = bt_view();
+    a.X = Xb[cur]; a.Xn = Xb[cur ^ 1]; a.Q = Q; a.B = B;
+    a.om = csomga; a.c1 = csy * csomga - 1.0;
+    a.advance = (m < maxIt) ? 1 : 0;
+    a.partials = G.d_partials_big;
+    if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid, PC_TX * PC_TY, 0, a);
+    else POP_LAUNCH(pcsi_iter_kernel<false>, grid, PC_TX * PC_TY, 0, a);
+    if (a.advance) POP_TRY(halo_update(cur == 0 ? Q : W, 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));  // (Q,X1) / (X0,Q)
     if (check) {
-      POP_TRY(reduce_finish(1, RED_POST_RR, &rr));
+      POP_TRY(reduce_finish_n(1, RED_POST_RR, &rr, G.d_partials_big, nblk));
       if (rr < G.convergenceCriterion) {
         G.numIterations = m;
         break;
       }
     }
+    if (a.advance) cur ^= 1;
   }
+  // the answer is X_m of the last residual evaluation
+  POP_CHECK_CUDA(cudaMemcpyAsync(X, Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   G.rmsResidual = sqrt(rr * G.residualNorm);
   return pop_post_launch("PCSI");  // PCSI returns silently when not converged (:1828-1830)
 }

@@ -311,6 +311,9 @@ extern "C" int pop_finalize(void) {
   for (auto& kv : G.stage) cudaFree(kv.second.first);
   G.stage.clear();
   cudaFree(G.d_partials);
+  cudaFree(G.d_partials_big);
+  G.d_partials_big = nullptr;
+  G.partials_big_n = 0;
   cudaFree(G.d_sums);
   cudaFree(G.d_gather);
   cudaFree(G.d_local);

@@ -77,6 +77,8 @@ struct Ctx {
   double rcheck = 0, rconst = 0;
   // reduction scratch (pop_reduce.cu)
   double* d_partials = nullptr;  // [POP_RED_NF][red_blocks][2] double-double block partials
+  double* d_partials_big = nullptr;  // [n][2] partials of kernels with their own (fixed) grid
+  int partials_big_n = 0;
   double* d_sums = nullptr;      // device results: [POP_RED_NF] doubles
   double* h_sums = nullptr;      // pinned mirror of d_sums
   double* d_local = nullptr;     // [POP_RED_NF][2] this rank's dd sums (all-gather send buffer)
@@ -194,6 +196,9 @@ int reduce_alloc();
 // G.red_blocks blocks: combine blocks (fixed order), combine ranks (rank order), apply `postop` to
 // the device-resident SolverScalars, optionally copy the sums to the host (synchronises).
 int reduce_finish(int nfields, int postop, double* out_host);
+// the same for block partials in `partials` ([nfields][nblocks][2]) written by a kernel with its own grid
+int reduce_finish_n(int nfields, int postop, double* out_host, const double* partials, int nblocks);
+int reduce_reserve_partials(int nblocks);  // sizes G.d_partials_big for POP_RED_NF fields x nblocks
 // state (pop_state.cu)
 int state_slab(int k, int kk, const double* T, const double* S, double* RHOOUT, double* RHOFULL,
                double* DRHODT, double* DRHODS, size_t n);

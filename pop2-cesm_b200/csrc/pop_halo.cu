@@ -127,6 +127,40 @@ __global__ void halo_tripole_out(T* __restrict__ a, const T* __restrict__ buf, i
   }
 }
 
+// Centre-located scalar fields (every solver vector, TRACER, RHO, PSURF): the fold needs neither the
+// symmetrisation of the top row nor a sign, so the east-west wrap and the tripole copy only read
+// physical columns and only write ghost cells; both run in ONE launch, straight from the source rows
+// (ghost row je+1 <- mirrored row je, ghost row je+2 <- mirrored row je-1; same cells and values as
+// halo_ew_wrap + halo_tripole_in + halo_tripole_out with ioffset = joffset = 0).
+template <typename T>
+__global__ void halo_center_scalar_local(T* __restrict__ a, int nz, int nxb, int nyb, size_t n2, int nxg,
+                                         int do_ew, int do_tripole, int je0,
+                                         const int* __restrict__ iglob, const int* __restrict__ jglob) {
+  const size_t n_ew = do_ew ? (size_t)nz * nyb * 4 : 0;
+  const size_t n_tp = do_tripole ? (size_t)nz * 2 * nxb : 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_ew + n_tp;
+       p += (size_t)gridDim.x * blockDim.x) {
+    if (p < n_ew) {
+      const int c = (int)(p % 4), j = (int)((p / 4) % nyb);
+      const size_t z = p / ((size_t)4 * nyb);
+      if (jglob[j] <= 0) continue;
+      T* row = a + z * n2 + (size_t)j * nxb;
+      if (c < 2) row[c] = row[nxb - 4 + c];
+      else row[nxb - 4 + c] = row[c];
+    } else {
+      const size_t t = p - n_ew;
+      const int i = (int)(t % nxb), r = (int)((t / nxb) % 2);  // r = 0: ghost row je+1, r = 1: je+2
+      const size_t z = t / ((size_t)2 * nxb);
+      int is = nxg - iglob[i] + 1;
+      if (is == 0) is = nxg;
+      if (is >= 1 && is <= nxg) {
+        T* az = a + z * n2;
+        az[(size_t)(je0 + 1 + r) * nxb + i] = az[(size_t)(je0 - r) * nxb + (POP_NGHOST - 1 + is)];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ communicator
 #ifndef POP_EMUL
 int comm_unique_id(char* id128) {
@@ -227,13 +261,22 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill) {
     const size_t n = (size_t)nz * 4 * nxg;
     POP_LAUNCH(halo_ns_cyclic_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb, nyb, n2, nxg);
   }
+  const bool tripole_here = (ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1);
+  if (loc == POP_LOC_CENTER && kind == POP_KIND_SCALAR) {  // fused east-west wrap + tripole copy
+    const int do_ew = (ew == POP_BNDY_CYCLIC) ? 1 : 0, do_tp = tripole_here ? 1 : 0;
+    const size_t n = (do_ew ? (size_t)nz * nyb * 4 : 0) + (do_tp ? (size_t)nz * 2 * nxb : 0);
+    if (n > 0)
+      POP_LAUNCH(halo_center_scalar_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb,
+                 nyb, n2, nxg, do_ew, do_tp, G.je - 1, G.d_iglob, G.d_jglob);
+    return pop_post_launch("halo_update");
+  }
   // ---- east/west
   if (ew == POP_BNDY_CYCLIC) {
     const size_t n = (size_t)nz * nyb * 4;
     POP_LAUNCH(halo_ew_wrap<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb, nyb, n2, G.d_jglob);
   }
   // ---- tripole fold on the last rank
-  if (ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) {
+  if (tripole_here) {
     const size_t need = ((size_t)nz * 3 * nxg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
     if (need > G.tripole_elems) {
       cudaFree(G.d_tripole);

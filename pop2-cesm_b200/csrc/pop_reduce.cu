@@ -116,9 +116,23 @@ __global__ void sum_ranks_kernel(const double* __restrict__ gathered, int nranks
   }
 }
 
+int reduce_reserve_partials(int nblocks) {
+  if (nblocks <= G.partials_big_n) return POP_SUCCESS;
+  cudaFree(G.d_partials_big);
+  G.d_partials_big = nullptr;
+  G.partials_big_n = 0;
+  POP_CHECK_CUDA(cudaMalloc(&G.d_partials_big, sizeof(double) * 2 * POP_RED_NF * (size_t)nblocks));
+  G.partials_big_n = nblocks;
+  return POP_SUCCESS;
+}
+
 int reduce_finish(int nfields, int postop, double* out_host) {
+  return reduce_finish_n(nfields, postop, out_host, G.d_partials, G.red_blocks);
+}
+
+int reduce_finish_n(int nfields, int postop, double* out_host, const double* partials, int nblocks) {
   POP_REQUIRE(nfields >= 1 && nfields <= POP_RED_NF, "reduce_finish: nfields=%d", nfields);
-  POP_LAUNCH(sum_blocks_kernel, 1, POP_EW_THREADS, 0, G.d_partials, nfields, G.red_blocks, G.d_local);
+  POP_LAUNCH(sum_blocks_kernel, 1, POP_EW_THREADS, 0, partials, nfields, nblocks, G.d_local);
   const double* gathered = G.d_local;
 #ifndef POP_EMUL
   if (G.nranks > 1) {

@@ -49,3 +49,34 @@ def test_no_cpu_fallback(built, pkg):
     with pytest.raises(pkg.api.PopError) as e:
         pkg.api.Pop(cfg)
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_fortran_binding_names_are_header_symbols():
+    """pop2-cesm_b200/fortran/pop_b200_bind.F90 cannot be compiled here (no Fortran compiler): keep
+    its bind(C) names and the field order of its pop_config mirror in sync with the header."""
+    f90 = open(os.path.join(ROOT, "pop2-cesm_b200", "fortran", "pop_b200_bind.F90")).read()
+    names = re.findall(r"bind\(C,\s*name='(pop_[a-z0-9_]+)'\)", f90)
+    assert len(names) >= 35
+    hdr = set(header_functions())
+    assert not [n for n in names if n not in hdr]
+    # every reference-signature slab operator and collective is bound
+    for must in ("pop_advt", "pop_advu", "pop_hdifft", "pop_hdiffu", "pop_gradp", "pop_vdifft", "pop_vdiffu",
+                 "pop_impvmixt", "pop_impvmixt_correct", "pop_impvmixu", "pop_state", "pop_solvers_run",
+                 "pop_solvers_diagonal", "pop_solvers_get_diagnostics", "pop_halo_update_2d_r8",
+                 "pop_halo_update_3d_r8", "pop_halo_update_4d_r8", "pop_global_sum_2d_r8", "pop_step"):
+        assert must in names, must
+    # struct field order: C header vs Fortran derived type
+    h = open(os.path.join(ROOT, "include", "pop_b200.h")).read()
+    body = re.search(r"typedef struct pop_config \{(.*?)\} pop_config;", h, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    cf = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            cf += [re.sub(r"\[.*?\]", "", x).strip() for x in decl.split(None, 1)[1].split(",")]
+    ft = re.search(r"type, bind\(C\) :: pop_config(.*?)end type pop_config", f90, flags=re.S).group(1)
+    ff = []
+    for line in ft.splitlines():
+        if "::" in line:
+            ff += [re.sub(r"\(.*?\)", "", x).strip() for x in line.split("::")[1].split(",")]
+    assert cf == ff
