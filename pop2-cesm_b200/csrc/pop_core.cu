@@ -392,6 +392,10 @@ int set_timestep(int ts_type) {
     G.c2dtu = G.dtu;
     G.c2dtp = G.dtp;
   }
+  for (int k = 1; k <= G.km; k++) {
+    G.vc.hfac_t[k] = G.vc.dz[k] / G.vc.c2dtt[k];
+    G.vc.hfac_u[k] = G.vc.dz[k] / G.c2dtu;
+  }
   if (changed) POP_TRY(upload_vert_const());
   return POP_SUCCESS;
 }

@@ -26,24 +26,32 @@ struct MomentumArgs {
   double am, c2dtu, beta, gamma, bottom_drag;
   PopTmap tm_uc, tm_vc, tm_um, tm_vm, tm_ro, tm_rc, tm_rn;  // TMA descriptors (FULL mode)
 };
-#define MO_NS 2  // TMA pipeline depth
+#define MO_NS 3  // TMA pipeline depth (levels in flight per CTA)
 
-struct MomCoefTiles {  // DMS = -DMN and DMW = -DME exactly (hmix_del2.F90:395-396), so they are not staged
+struct MomCoefTiles {  // ring-1 tiles; DMS = -DMN and DMW = -DME exactly (hmix_del2.F90:395-396): not staged
   const double *cc, *dun, *dus, *due, *duw, *dmc, *dmn, *dme;
 };
-// 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*
+// 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*.
+// R1 = true: A and B are ring-1 tiles (TIX1); false: halo tiles of a pipeline stage (TIX).
+template <bool R1>
 __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const double* A, const double* B,
                                               int ii, int jj, bool plus) {
-  const int q = TIX(ii, jj);
-  const double s1 = c.cc[q] * A[q] + c.dun[q] * A[TIX(ii, jj + 1)] + c.dus[q] * A[TIX(ii, jj - 1)] +
-                    c.due[q] * A[TIX(ii + 1, jj)] + c.duw[q] * A[TIX(ii - 1, jj)];
-  const double s2 = c.dmc[q] * B[q] + c.dmn[q] * B[TIX(ii, jj + 1)] + (-c.dmn[q]) * B[TIX(ii, jj - 1)] +
-                    c.dme[q] * B[TIX(ii + 1, jj)] + (-c.dme[q]) * B[TIX(ii - 1, jj)];
+  const int q = TIX1(ii, jj);
+  const int o = R1 ? q : TIX(ii, jj);
+  constexpr int W = R1 ? POP_T1W : POP_TW;
+  const double s1 = c.cc[q] * A[o] + c.dun[q] * A[o + W] + c.dus[q] * A[o - W] + c.due[q] * A[o + 1] +
+                    c.duw[q] * A[o - 1];
+  const double s2 = c.dmc[q] * B[o] + c.dmn[q] * B[o + W] + (-c.dmn[q]) * B[o - W] + c.dme[q] * B[o + 1] +
+                    (-c.dme[q]) * B[o - 1];
   return plus ? (s1 + s2) : (s1 - s2);
 }
 
-#define MOM_STAGE_TILES 7   // uc, vc, um, vm, rho old/cur/new
-#define MOM_FIXED_TILES 13  // dyu, dxu, cc, dun, dus, due, duw, dmc, dmn, dme, amf, d2u, d2v
+#define MOM_STAGE_TILES 7   // uc, vc, um, vm, rho old/cur/new (halo tiles, TMA boxes)
+#define MOM_FIXED_TILES 13  // ring-1: cc, dun, dus, due, duw, dmc, dmn, dme, amf, ud, vd, d2u, d2v
+// Per level: every thread first finishes the "main" pass of level k (which reads the per-level
+// intermediates UD = U*DYU, VD = V*DXU and, for del4, D2U/D2V = AMF*L(U,V) of level k), then the CTA
+// rebuilds those intermediates for level k+1 from the stage that has already landed.  The products
+// and the first Laplacian are thus computed once per tile point instead of once per stencil use.
 template <int MODE, bool DEL4, bool TMA>
 __global__ void __launch_bounds__(POP_NTHREADS, 2)
 momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
@@ -51,20 +59,21 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   constexpr int NS = TMA ? MO_NS : 1;
   double* sm = (double*)smem_raw;
   double* s_stage = sm;  // [NS][MOM_STAGE_TILES][TN]
-  double* s_dyu = s_stage + NS * MOM_STAGE_TILES * POP_TN;
-  double* s_dxu = s_dyu + POP_TN;
-  double* s_cc = s_dxu + POP_TN;
-  double* s_dun = s_cc + POP_TN;
-  double* s_dus = s_dun + POP_TN;
-  double* s_due = s_dus + POP_TN;
-  double* s_duw = s_due + POP_TN;
-  double* s_dmc = s_duw + POP_TN;
-  double* s_dmn = s_dmc + POP_TN;
-  double* s_dme = s_dmn + POP_TN;
-  double* s_amf = s_dme + POP_TN;
-  double* s_d2base = s_amf + POP_TN;  // [TMA ? 2 : 1][2][TN]: D2U, D2V
-  int* s_kmu = (int*)(s_d2base + (TMA ? 4 : 2) * POP_TN);
-  uint64_t* s_bar = (uint64_t*)(s_kmu + POP_TN);
+  double* s_cc = s_stage + NS * MOM_STAGE_TILES * POP_TN;
+  double* s_dun = s_cc + POP_T1N;
+  double* s_dus = s_dun + POP_T1N;
+  double* s_due = s_dus + POP_T1N;
+  double* s_duw = s_due + POP_T1N;
+  double* s_dmc = s_duw + POP_T1N;
+  double* s_dmn = s_dmc + POP_T1N;
+  double* s_dme = s_dmn + POP_T1N;
+  double* s_amf = s_dme + POP_T1N;
+  double* s_ud = s_amf + POP_T1N;
+  double* s_vd = s_ud + POP_T1N;
+  double* s_d2u = s_vd + POP_T1N;
+  double* s_d2v = s_d2u + POP_T1N;
+  int* s_kmu = (int*)(s_d2v + POP_T1N);
+  uint64_t* s_bar = (uint64_t*)(s_kmu + POP_T1N);
 
   const GridView& g = a.g;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
@@ -82,70 +91,7 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   constexpr int HM = DEL4 ? 2 : 1;
   const bool same_mix = (a.UMIX == a.UCUR) && DO_ADV && (TMA || !DEL4);
 
-  // ---- k-invariant staging
-  if (DO_ADV) {
-    tile_load(s_dyu, g.DYU, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
-    tile_load(s_dxu, g.DXU, i0, j0, nxb, nyb, -1, POP_BX, -1, POP_BY, tid);
-  }
-  if (DO_HMIX) {
-    constexpr int R = DEL4 ? 1 : 0;  // coefficients are needed on the first halo ring for del4
-    const int w = POP_BX + 2 * R, npts = w * (POP_BY + 2 * R);
-    for (int p = tid; p < npts; p += POP_NTHREADS) {
-      const int jj = p / w - R, ii = p % w - R;
-      const int gi = i0 + ii, gj = j0 + jj, t = TIX(ii, jj);
-      const bool in = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb);
-      const size_t qq = (size_t)gj * nxb + gi;
-      s_cc[t] = in ? g.DUC[qq] + g.DUM[qq] : 0.0;
-      s_dun[t] = in ? g.DUN[qq] : 0.0;
-      s_dus[t] = in ? g.DUS[qq] : 0.0;
-      s_due[t] = in ? g.DUE[qq] : 0.0;
-      s_duw[t] = in ? g.DUW[qq] : 0.0;
-      s_dmc[t] = in ? g.DMC[qq] : 0.0;
-      s_dmn[t] = in ? g.DMN[qq] : 0.0;
-      s_dme[t] = in ? g.DME[qq] : 0.0;
-      s_amf[t] = in ? g.AMF[qq] : 0.0;
-      s_kmu[t] = in ? g.KMU[qq] : 0;
-    }
-  }
-  const MomCoefTiles ct{s_cc, s_dun, s_dus, s_due, s_duw, s_dmc, s_dmn, s_dme};
-  int kmu = 0;
-  double uarea_r = 0, kxu = 0, kyu = 0, fcor = 0, dxur = 0, dyur = 0;
-  if (active) {
-    kmu = g.KMU[q];
-    uarea_r = g.UAREA_R[q];
-    kxu = g.KXU[q];
-    kyu = g.KYU[q];
-    fcor = g.FCOR[q];
-    dxur = g.DXUR[q];
-    dyur = g.DYUR[q];
-  }
-  // ---- carried state
-  double wuk = 0, u_m = 0, v_m = 0, uo_c = 0, vo_c = 0;
-  double sumx = 0, sumy = 0, rmx = 0, rmy = 0, vuf = 0, vvf = 0, zx = 0, zy = 0;
-  if (active) {
-    if (DO_ADV) {
-      wuk = (MODE == MO_FULL) ? a.DHU[q] : a.WUK[q];
-      if (a.k0 > 1) {
-        u_m = a.UCUR[(size_t)(a.k0 - 2) * n2 + q];
-        v_m = a.VCUR[(size_t)(a.k0 - 2) * n2 + q];
-      }
-    }
-    if (DO_VDIF || MODE == MO_FULL) {
-      uo_c = a.UOLD[(size_t)(a.k0 - 1) * n2 + q];
-      vo_c = a.VOLD[(size_t)(a.k0 - 1) * n2 + q];
-    }
-    if (DO_VDIF && a.k0 > 1) {
-      vuf = a.VUF[q];
-      vvf = a.VVF[q];
-    }
-    if (DO_GRADP && a.k0 > 1) {
-      sumx = a.SUMX[q];
-      sumy = a.SUMY[q];
-      rmx = a.RHOKMX[q];
-      rmy = a.RHOKMY[q];
-    }
-  }
-
+  // ---- pipeline start (one thread): the first NS levels are in flight while the k-invariants load
   const uint32_t stage_bytes = (uint32_t)((2 + (same_mix ? 0 : 2) + (a.pavg ? 3 : 1)) * POP_TILE_BYTES);
   auto issue = [&](int kk) {
     const int sl = (kk - a.k0) % NS;
@@ -174,25 +120,107 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       for (int kk = a.k0; kk <= a.k1 && kk < a.k0 + NS; kk++) issue(kk);
   }
 
-  // first application of the del4 operator on the halo ring (hmix_del4.F90:730-790)
-  auto compute_d2 = [&](int kk, const double* um, const double* vm, double* d2) {
-    constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
-    for (int p = tid; p < npts; p += POP_NTHREADS) {
-      const int jj = p / w - 1, ii = p % w - 1, t = TIX(ii, jj);
-      double d2u = mom_stencil(ct, um, vm, ii, jj, true);
-      double d2v = mom_stencil(ct, vm, um, ii, jj, false);
-      if (a.lvariable_hmixu) {
-        if (kk <= s_kmu[t]) { d2u = s_amf[t] * d2u; d2v = s_amf[t] * d2v; }
-        else { d2u = 0.0; d2v = 0.0; }
-      } else if (kk > s_kmu[t]) { d2u = 0.0; d2v = 0.0; }
-      d2[t] = d2u;
-      d2[POP_TN + t] = d2v;
+  // ---- k-invariant staging: coefficients on the ring-1 tile; DYU/DXU of the (at most two) ring-1
+  // points this thread rebuilds every level stay in registers
+  double r_dyu[2] = {0.0, 0.0}, r_dxu[2] = {0.0, 0.0};
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int p = tid + s * POP_NTHREADS;
+    if (p < POP_T1N) {
+      const int jj = p / POP_T1W - 1, ii = p % POP_T1W - 1;
+      const int gi = i0 + ii, gj = j0 + jj;
+      const bool in = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb);
+      const size_t qq = (size_t)gj * nxb + gi;
+      if (DO_ADV) {
+        r_dyu[s] = in ? g.DYU[qq] : 0.0;
+        r_dxu[s] = in ? g.DXU[qq] : 0.0;
+      }
+      if (DO_HMIX) {
+        s_cc[p] = in ? g.DUC[qq] + g.DUM[qq] : 0.0;
+        s_dun[p] = in ? g.DUN[qq] : 0.0;
+        s_dus[p] = in ? g.DUS[qq] : 0.0;
+        s_due[p] = in ? g.DUE[qq] : 0.0;
+        s_duw[p] = in ? g.DUW[qq] : 0.0;
+        s_dmc[p] = in ? g.DMC[qq] : 0.0;
+        s_dmn[p] = in ? g.DMN[qq] : 0.0;
+        s_dme[p] = in ? g.DME[qq] : 0.0;
+        s_amf[p] = in ? g.AMF[qq] : 0.0;
+        s_kmu[p] = in ? g.KMU[qq] : 0;
+      }
+    }
+  }
+  const MomCoefTiles ct{s_cc, s_dun, s_dus, s_due, s_duw, s_dmc, s_dmn, s_dme};
+  int kmu = 0;
+  double uarea_r = 0, kxu = 0, kyu = 0, fcor = 0, dxur = 0, dyur = 0;
+  if (active) {
+    kmu = g.KMU[q];
+    uarea_r = g.UAREA_R[q];
+    kxu = g.KXU[q];
+    kyu = g.KYU[q];
+    fcor = g.FCOR[q];
+    dxur = g.DXUR[q];
+    dyur = g.DYUR[q];
+  }
+  // implicit Coriolis factors of the column (baroclinic.F90:1013-1030)
+  const double cor_w1 = a.c2dtu * a.beta * fcor;
+  const double cor_w2 = a.c2dtu / (1.0 + cor_w1 * cor_w1);
+  // ---- carried state
+  double wuk = 0, u_m = 0, v_m = 0, uo_c = 0, vo_c = 0;
+  double sumx = 0, sumy = 0, rmx = 0, rmy = 0, vuf = 0, vvf = 0, zx = 0, zy = 0;
+  if (active) {
+    if (DO_ADV) {
+      wuk = (MODE == MO_FULL) ? a.DHU[q] : a.WUK[q];
+      if (a.k0 > 1) {
+        u_m = a.UCUR[(size_t)(a.k0 - 2) * n2 + q];
+        v_m = a.VCUR[(size_t)(a.k0 - 2) * n2 + q];
+      }
+    }
+    if (DO_VDIF || MODE == MO_FULL) {
+      uo_c = a.UOLD[(size_t)(a.k0 - 1) * n2 + q];
+      vo_c = a.VOLD[(size_t)(a.k0 - 1) * n2 + q];
+    }
+    if (DO_VDIF && a.k0 > 1) {
+      vuf = a.VUF[q];
+      vvf = a.VVF[q];
+    }
+    if (DO_GRADP && a.k0 > 1) {
+      sumx = a.SUMX[q];
+      sumy = a.SUMY[q];
+      rmx = a.RHOKMX[q];
+      rmy = a.RHOKMY[q];
+    }
+  }
+
+  // per-level intermediates on the ring-1 tile: flux operands (advection.F90:1307-1340) and the first
+  // application of the del4 operator (hmix_del4.F90:730-790)
+  auto pre = [&](int kk, const double* uc, const double* vc, const double* um, const double* vm) {
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int p = tid + s * POP_NTHREADS;
+      if (p < POP_T1N) {
+        const int jj = p / POP_T1W - 1, ii = p % POP_T1W - 1;
+        if (DO_ADV) {
+          s_ud[p] = uc[TIX(ii, jj)] * r_dyu[s];
+          s_vd[p] = vc[TIX(ii, jj)] * r_dxu[s];
+        }
+        if (DO_HMIX && DEL4) {
+          double d2u = mom_stencil<false>(ct, um, vm, ii, jj, true);
+          double d2v = mom_stencil<false>(ct, vm, um, ii, jj, false);
+          if (a.lvariable_hmixu) {
+            if (kk <= s_kmu[p]) { d2u = s_amf[p] * d2u; d2v = s_amf[p] * d2v; }
+            else { d2u = 0.0; d2v = 0.0; }
+          } else if (kk > s_kmu[p]) { d2u = 0.0; d2v = 0.0; }
+          s_d2u[p] = d2u;
+          s_d2v[p] = d2v;
+        }
+      }
     }
   };
-  if (TMA && DO_HMIX && DEL4) {
+  if (TMA) {
     mbar_wait(&s_bar[0], 0u);
     __syncthreads();  // coefficient tiles are staged
-    compute_d2(a.k0, same_mix ? s_stage : s_stage + 2 * POP_TN, same_mix ? s_stage + POP_TN : s_stage + 3 * POP_TN, s_d2base);
+    pre(a.k0, s_stage, s_stage + POP_TN, same_mix ? s_stage : s_stage + 2 * POP_TN,
+        same_mix ? s_stage + POP_TN : s_stage + 3 * POP_TN);
     __syncthreads();
   }
   const bool uold_is_mix = (a.UOLD == a.UMIX) && !same_mix;
@@ -210,6 +238,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     double* s_ro = s_uc + 4 * POP_TN;
     double* s_rc = s_uc + 5 * POP_TN;
     double* s_rn = s_uc + 6 * POP_TN;
+    const double* um = same_mix ? s_uc : s_um;
+    const double* vm = same_mix ? s_vc : s_vm;
     if (TMA) {
       mbar_wait(&s_bar[slot], (uint32_t)(((k - a.k0) / NS) & 1));
     } else {
@@ -230,14 +260,10 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         }
       }
       __syncthreads();
-    }
-    const double* um = same_mix ? s_uc : s_um;
-    const double* vm = same_mix ? s_vc : s_vm;
-    double* s_d2u = s_d2base + (TMA ? ((k - a.k0) & 1) * 2 * POP_TN : 0);
-    double* s_d2v = s_d2u + POP_TN;
-    if (DO_HMIX && DEL4 && !TMA) {
-      compute_d2(k, um, vm, s_d2u);
-      __syncthreads();
+      if (DO_ADV || (DO_HMIX && DEL4)) {
+        pre(k, s_uc, s_vc, um, vm);
+        __syncthreads();
+      }
     }
     const bool have_next = TMA && (k < a.k1);
     const int nslot = (k + 1 - a.k0) % NS;
@@ -252,8 +278,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     // ---- advu: advection.F90:1307-1491
     double luk = 0.0, lvk = 0.0;
     if (DO_ADV) {
-#define UD(di, dj) (s_uc[TIX(tx + (di), ty + (dj))] * s_dyu[TIX(tx + (di), ty + (dj))])
-#define VD(di, dj) (s_vc[TIX(tx + (di), ty + (dj))] * s_dxu[TIX(tx + (di), ty + (dj))])
+#define UD(di, dj) s_ud[TIX1(tx + (di), ty + (dj))]
+#define VD(di, dj) s_vd[TIX1(tx + (di), ty + (dj))]
       const double uuw = 0.25 * (UD(0, 0) + UD(-1, 0)) + 0.125 * (UD(0, -1) + UD(-1, -1) + UD(0, 1) + UD(-1, 1));
       const double uue = 0.25 * (UD(1, 0) + UD(0, 0)) + 0.125 * (UD(1, -1) + UD(0, -1) + UD(1, 1) + UD(0, 1));
       const double vus = 0.25 * (VD(0, 0) + VD(0, -1)) + 0.125 * (VD(-1, 0) + VD(-1, -1) + VD(1, 0) + VD(1, -1));
@@ -324,11 +350,11 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     double hdu = 0.0, hdv = 0.0;
     if (DO_HMIX) {
       if (DEL4) {
-        hdu = a.am * mom_stencil(ct, s_d2u, s_d2v, tx, ty, true);
-        hdv = a.am * mom_stencil(ct, s_d2v, s_d2u, tx, ty, false);
+        hdu = a.am * mom_stencil<true>(ct, s_d2u, s_d2v, tx, ty, true);
+        hdv = a.am * mom_stencil<true>(ct, s_d2v, s_d2u, tx, ty, false);
       } else {
-        hdu = a.am * mom_stencil(ct, um, vm, tx, ty, true);
-        hdv = a.am * mom_stencil(ct, vm, um, tx, ty, false);
+        hdu = a.am * mom_stencil<false>(ct, um, vm, tx, ty, true);
+        hdv = a.am * mom_stencil<false>(ct, vm, um, tx, ty, false);
       }
       if (k > kmu) { hdu = 0.0; hdv = 0.0; }
     }
@@ -387,10 +413,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       // ---- implicit Coriolis and vertical integrals: baroclinic.F90:1013-1045
       double un, vn;
       if (a.impcor) {
-        const double w1 = a.c2dtu * a.beta * fcor;
-        const double w2 = a.c2dtu / (1.0 + w1 * w1);
-        un = (fx + w1 * fy) * w2;
-        vn = (fy - w1 * fx) * w2;
+        un = (fx + cor_w1 * fy) * cor_w2;
+        vn = (fy - cor_w1 * fx) * cor_w2;
       } else {
         un = a.c2dtu * fx;
         vn = a.c2dtu * fy;
@@ -404,9 +428,12 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     vo_c = vo_p;
     }  // active
     if (TMA) {
-      if (DO_HMIX && DEL4 && have_next) compute_d2(k + 1, n_um, n_vm, s_d2base + ((k + 1 - a.k0) & 1) * 2 * POP_TN);
-      __syncthreads();  // every thread is done with this ring slot; D2(k+1) is complete
+      __syncthreads();  // every thread is done with ring slot k and with the intermediates of level k
       if (tid == 0 && k + NS <= a.k1) issue(k + NS);
+      if (have_next) {
+        pre(k + 1, n_uc, n_vc, n_um, n_vm);
+        __syncthreads();
+      }
     }
   }
   if (!active) return;
@@ -429,7 +456,8 @@ static int launch_momentum(const MomentumArgs& a, bool del4, bool tma) {
   if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true> : momentum_column_kernel<MODE, false, true>;
   else kfn = del4 ? momentum_column_kernel<MODE, true, false> : momentum_column_kernel<MODE, false, false>;
   const int ns = tma ? MO_NS : 1;
-  const size_t smem = sizeof(double) * POP_TN * (ns * MOM_STAGE_TILES + MOM_FIXED_TILES + (tma ? 2 : 0)) + sizeof(int) * POP_TN + 8 * MO_NS;
+  const size_t smem = sizeof(double) * ((size_t)POP_TN * ns * MOM_STAGE_TILES + (size_t)POP_T1N * MOM_FIXED_TILES) +
+                      sizeof(int) * POP_T1N + 8 * MO_NS;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -512,7 +540,7 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   if (implicit_vmix) {
     double A, B, C, D, F1, F2;
     {
-      const double hfac = c_vc.dz[1] / c2dtu;
+      const double hfac = c_vc.hfac_u[1];
       A = c_vc.afac_u[1] * VVCq[0];
       D = hfac + A;
       const double e = A / D;
@@ -545,7 +573,7 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
       for (int c = 0; c < MF_CH; c++) {
         const int k = kb + c;
         if (k <= km) {
-          const double hfac = c_vc.dz[k] / c2dtu;
+          const double hfac = c_vc.hfac_u[k];
           C = A;
           A = c_vc.afac_u[k] * cv[c];
           if (k < kmu) D = hfac + A + B;

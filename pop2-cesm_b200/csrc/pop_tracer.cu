@@ -541,7 +541,7 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
   const int km = g.km, kmt = g.KMT[q];
-  const double hfac1 = c_vc.dz[1] / c_vc.c2dtt[1];
+  const double hfac1 = c_vc.hfac_t[1];
   const double H1 = varthick ? hfac1 + PSFC[q] / (POP_GRAV * c_vc.c2dtt[1]) : hfac1;
   for (int n = nfirst; n <= nlast; n++) {  // 1-based tracer index
     const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
@@ -584,7 +584,7 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
         if (k <= km) {
           C = A;
           A = c_vc.afac_t[k] * vv[c];
-          const double hfac = c_vc.dz[k] / c_vc.c2dtt[k];
+          const double hfac = c_vc.hfac_t[k];
           double F;
           if (k > kmt) {
             F = 0.0;
