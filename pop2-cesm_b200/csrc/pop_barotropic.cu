@@ -324,9 +324,13 @@ struct PcsiArgs {
   double om, c1;     // om_{m+1}, csy*om_{m+1} - 1
   int advance;       // 0: last iteration (residual only)
   double* partials;  // [gridDim.x*gridDim.y][2] dd block partials of sum r^2 (SUM only)
+  // single rank: ghost cells are filled in the same pass by evaluating the update at the cell the
+  // halo update would copy from (east-west wrap, tripole fold), so no halo launch follows
+  int map_ghost, do_ew, do_tripole, je0, nxg;
+  const int *iglob, *jglob;
 };
 template <bool SUM>
-__global__ void __launch_bounds__(PC_TX * PC_TY)
+__global__ void __launch_bounds__(PC_TX * PC_TY, 8)
 pcsi_iter_kernel(const PcsiArgs a) {
   const BtView& v = a.v;
   const int tx = threadIdx.x % PC_TX, ty = threadIdx.x / PC_TX;
@@ -334,6 +338,23 @@ pcsi_iter_kernel(const PcsiArgs a) {
   dd acc{0.0, 0.0};
   if (i < v.nxb && j < v.nyb) {
     const int nxb = v.nxb;
+    const size_t qd = (size_t)j * nxb + i;  // cell written by this thread
+    int is = i, js = j;                     // cell whose update it evaluates
+    if (a.map_ghost) {
+      if (a.do_tripole && j > a.je0) {
+        int ig = a.nxg - a.iglob[i] + 1;
+        if (ig == 0) ig = a.nxg;
+        if (ig >= 1 && ig <= a.nxg) {
+          is = POP_NGHOST - 1 + ig;
+          js = 2 * a.je0 + 1 - j;
+        }
+      } else if (a.do_ew && (i < POP_NGHOST || i >= nxb - POP_NGHOST) && a.jglob[j] > 0) {
+        is = (i < POP_NGHOST) ? i + (nxb - 2 * POP_NGHOST) : i - (nxb - 2 * POP_NGHOST);
+      }
+    }
+    const bool ghost_copy = (is != i) || (js != j);
+    {
+    const int i = is, j = js;
     const size_t q = (size_t)j * nxb + i;
     const double c = ldg(v.C + q);
     double ax = 0.0;
@@ -345,13 +366,17 @@ pcsi_iter_kernel(const PcsiArgs a) {
            ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
     }
     const double r = ldg(a.B + q) - ax;
-    if (SUM && bt_physical(v, i, j)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + q));
+    if (SUM && !ghost_copy && bt_physical(v, i, j)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + q));
     if (a.advance) {
       const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
       const double R = r * a0r;
-      const double qv = a.om * R + a.c1 * a.Q[q];
-      a.Q[q] = qv;
-      a.Xn[q] = ldg(a.X + q) + qv;
+      // Q is updated in place: a ghost thread reads Q_m of its source cell, which the owner of that cell
+      // may already have replaced -> ghost threads read the previous Q from their own (ghost) cell,
+      // which holds the same bits
+      const double qv = a.om * R + a.c1 * a.Q[qd];
+      a.Q[qd] = qv;
+      a.Xn[qd] = ldg(a.X + q) + qv;
+    }
     }
   }
   if (SUM) {
@@ -402,9 +427,14 @@ static int pcsi(double* X, const double* B) {
     a.om = csomga; a.c1 = csy * csomga - 1.0;
     a.advance = (m < maxIt) ? 1 : 0;
     a.partials = G.d_partials_big;
+    a.map_ghost = (G.nranks == 1) ? 1 : 0;
+    a.do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
+    a.do_tripole = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
+    a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
     if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid, PC_TX * PC_TY, 0, a);
     else POP_LAUNCH(pcsi_iter_kernel<false>, grid, PC_TX * PC_TY, 0, a);
-    if (a.advance) POP_TRY(halo_update(cur == 0 ? Q : W, 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));  // (Q,X1) / (X0,Q)
+    if (a.advance && !a.map_ghost)
+      POP_TRY(halo_update(cur == 0 ? Q : W, 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));  // (Q,X1) / (X0,Q)
     if (check) {
       POP_TRY(reduce_finish_n(1, RED_POST_RR, &rr, G.d_partials_big, nblk));
       if (rr < G.convergenceCriterion) {
