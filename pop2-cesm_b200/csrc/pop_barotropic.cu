@@ -319,7 +319,8 @@ struct PcsiArgs {
   BtView v;
   const double* X;   // X_m
   double* Xn;        // X_{m+1}
-  double* Q;         // in: Q_m, out: Q_{m+1}
+  const double* Q;   // Q_m
+  double* Qn;        // Q_{m+1} (other buffer)
   const double* B;
   double om, c1;     // om_{m+1}, csy*om_{m+1} - 1
   int advance;       // 0: last iteration (residual only)
@@ -370,11 +371,8 @@ pcsi_iter_kernel(const PcsiArgs a) {
     if (a.advance) {
       const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
       const double R = r * a0r;
-      // Q is updated in place: a ghost thread reads Q_m of its source cell, which the owner of that cell
-      // may already have replaced -> ghost threads read the previous Q from their own (ghost) cell,
-      // which holds the same bits
-      const double qv = a.om * R + a.c1 * a.Q[qd];
-      a.Q[qd] = qv;
+      const double qv = a.om * R + a.c1 * ldg(a.Q + q);
+      a.Qn[qd] = qv;
       a.Xn[qd] = ldg(a.X + q) + qv;
     }
     }
@@ -389,18 +387,174 @@ pcsi_iter_kernel(const PcsiArgs a) {
   }
 }
 
+// ---- two iterations per pass (temporal blocking) -----------------------------------------------
+// K2(m): a CTA loads X_m on its tile plus a 2-cell ring, evaluates iteration m on the tile plus a 1-cell
+// ring (X_{m+1} stays in shared memory), then iteration m+1 on the tile, and writes only Q_{m+2} and
+// X_{m+2}: the seven input arrays and the two outputs cross HBM once per TWO iterations.  The values are
+// the same bits as two K passes: a ring cell that is a ghost cell of the block is evaluated at the
+// cell a halo update would copy from (east-west wrap / tripole mirror, read from global memory), and
+// ghost rows owned by a neighbouring rank hold that rank's bits two cells deep.  One 2-level halo
+// update of (X,Q) follows every pass (P > 1: one strip exchange per two iterations).
+#define P2_TX 64
+#define P2_TY 8
+#define P2_NT 256
+#define P2_XW (P2_TX + 4)  // width of the tiles that start two cells west of the tile (X, E, NE)
+#define P2_1W (P2_TX + 2)  // width of the tiles that start one cell west (X1, C, B, Q, N)
+#define P2_SMEM_DOUBLES                                                                              \
+  ((P2_TY + 4) * P2_XW + 4 * (P2_TY + 2) * P2_1W + (P2_TY + 3) * P2_1W + (P2_TY + 2) * P2_XW +      \
+   (P2_TY + 3) * P2_XW)
+struct Pcsi2Args {
+  BtView v;
+  const double *X, *Q, *B;  // X_m, Q_m
+  double *Xn, *Qn;          // X_{m+2}, Q_{m+2}
+  double om1, c11, om2, c12;
+  double* partials;
+  int do_ew, do_tripole, je0, nxg;
+  const int *iglob, *jglob;
+};
+// cooperative asynchronous staging of a w x h window of a 2-d field (origin gi0,gj0; zero outside)
+__device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__ src, int w, int h, int gi0,
+                                         int gj0, int nxb, int nyb, int tid) {
+  for (int p = tid; p < w * h; p += P2_NT) {
+    const int gi = gi0 + p % w, gj = gj0 + p / w;
+    const bool in = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb);
+    cp_async8(dst + p, src + (in ? (size_t)gj * nxb + gi : 0), in);
+  }
+}
+template <bool SUM>
+__global__ void __launch_bounds__(P2_NT, 4)
+pcsi_iter2_kernel(const Pcsi2Args a) {
+  POP_DYN_SMEM(smem_raw);
+  double* sX = (double*)smem_raw;                  // X_m: tile + 2-cell ring        (TY+4) x XW
+  double* sX1 = sX + (P2_TY + 4) * P2_XW;          // X_{m+1}: tile + 1-cell ring    (TY+2) x 1W
+  double* sC = sX1 + (P2_TY + 2) * P2_1W;          // centre weight                  (TY+2) x 1W
+  double* sB = sC + (P2_TY + 2) * P2_1W;           // right-hand side
+  double* sQ = sB + (P2_TY + 2) * P2_1W;           // Q_m
+  double* sN = sQ + (P2_TY + 2) * P2_1W;           // north weight, one extra row south  (TY+3) x 1W
+  double* sE = sN + (P2_TY + 3) * P2_1W;           // east weight, one extra column west (TY+2) x XW
+  double* sNE = sE + (P2_TY + 2) * P2_XW;          // NE weight, extra row + column      (TY+3) x XW
+  const BtView& v = a.v;
+  const int nxb = v.nxb, nyb = v.nyb;
+  const int i0 = POP_NGHOST + blockIdx.x * P2_TX, j0 = POP_NGHOST + blockIdx.y * P2_TY;  // 0-based tile origin
+  const int tid = threadIdx.x;
+  // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA)
+  p2_stage(sX, a.X, P2_XW, P2_TY + 4, i0 - 2, j0 - 2, nxb, nyb, tid);
+  p2_stage(sC, v.C, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
+  p2_stage(sB, a.B, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
+  p2_stage(sQ, a.Q, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
+  p2_stage(sN, v.N, P2_1W, P2_TY + 3, i0 - 1, j0 - 2, nxb, nyb, tid);
+  p2_stage(sE, v.E, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
+  p2_stage(sNE, v.NE, P2_XW, P2_TY + 3, i0 - 2, j0 - 2, nxb, nyb, tid);
+  cp_async_wait_all();
+  __syncthreads();
+  // 9-point operator at tile-relative cell (ii,jj), X values from tile `x` of width `xw` whose element
+  // (ii,jj) is x[0]
+#define P2_AX(x, xw, ii, jj)                                                                              \
+  (sC[((jj) + 1) * P2_1W + (ii) + 1] * (x)[0] + sN[((jj) + 2) * P2_1W + (ii) + 1] * (x)[(xw)] +           \
+   sN[((jj) + 1) * P2_1W + (ii) + 1] * (x)[-(xw)] + sE[((jj) + 1) * P2_XW + (ii) + 2] * (x)[1] +          \
+   sE[((jj) + 1) * P2_XW + (ii) + 1] * (x)[-1] + sNE[((jj) + 2) * P2_XW + (ii) + 2] * (x)[(xw) + 1] +     \
+   sNE[((jj) + 1) * P2_XW + (ii) + 2] * (x)[-(xw) + 1] + sNE[((jj) + 2) * P2_XW + (ii) + 1] * (x)[(xw) - 1] + \
+   sNE[((jj) + 1) * P2_XW + (ii) + 1] * (x)[-(xw) - 1])
+  dd acc{0.0, 0.0};
+  constexpr int NSLOT = (P2_TX * P2_TY) / P2_NT;  // tile cells per thread
+  constexpr int NRING = 2 * P2_1W + 2 * P2_TY;
+  double q1[NSLOT];
+  // ---- iteration m on the tile + ring.  Slots 0..NSLOT-1: the thread's tile cells; NSLOT: a ring cell.
+#pragma unroll
+  for (int s = 0; s <= NSLOT; s++) {
+    int ii, jj;
+    if (s < NSLOT) {
+      ii = tid % P2_TX;
+      jj = (tid / P2_TX) * NSLOT + s;
+    } else {
+      // ring enumeration: bottom and top rows (2 x P2_1W), then left and right columns (2 x P2_TY)
+      if (tid >= NRING) break;
+      if (tid < 2 * P2_1W) { ii = tid % P2_1W - 1; jj = (tid < P2_1W) ? -1 : P2_TY; }
+      else { const int t = tid - 2 * P2_1W; ii = (t < P2_TY) ? -1 : P2_TX; jj = t % P2_TY; }
+    }
+    const int gi = i0 + ii, gj = j0 + jj;
+    double x1 = 0.0, qv = 0.0;
+    if (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
+      // ghost cell with a source: evaluate there, from global memory
+      int si = gi, sj = gj;
+      if (a.do_tripole && gj > a.je0) {
+        int ig = a.nxg - a.iglob[gi] + 1;
+        if (ig == 0) ig = a.nxg;
+        if (ig >= 1 && ig <= a.nxg) { si = POP_NGHOST - 1 + ig; sj = 2 * a.je0 + 1 - gj; }
+      } else if (a.do_ew && (gi < POP_NGHOST || gi >= nxb - POP_NGHOST) && a.jglob[gj] > 0) {
+        si = (gi < POP_NGHOST) ? gi + (nxb - 2 * POP_NGHOST) : gi - (nxb - 2 * POP_NGHOST);
+      }
+      double c, ax, xc, b, qm;
+      if (si != gi || sj != gj) {
+        const size_t q = (size_t)sj * nxb + si;
+        const double* X = a.X;
+        c = ldg(v.C + q);
+        ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
+             ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
+             ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
+             ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
+        xc = ldg(X + q);
+        b = ldg(a.B + q);
+        qm = ldg(a.Q + q);
+      } else {
+        const double* x = sX + (jj + 2) * P2_XW + (ii + 2);
+        c = sC[(jj + 1) * P2_1W + ii + 1];
+        ax = P2_AX(x, P2_XW, ii, jj);
+        xc = x[0];
+        b = sB[(jj + 1) * P2_1W + ii + 1];
+        qm = sQ[(jj + 1) * P2_1W + ii + 1];
+      }
+      const double r = b - ax;
+      if (SUM && s < NSLOT && bt_physical(v, gi, gj)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + (size_t)gj * nxb + gi));
+      const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+      qv = a.om1 * (r * a0r) + a.c11 * qm;
+      x1 = xc + qv;
+    }
+    sX1[(jj + 1) * P2_1W + (ii + 1)] = x1;
+    if (s < NSLOT) q1[s] = qv;
+  }
+  __syncthreads();
+  // ---- iteration m+1 on the tile (physical cells only)
+#pragma unroll
+  for (int s = 0; s < NSLOT; s++) {
+    const int ii = tid % P2_TX, jj = (tid / P2_TX) * NSLOT + s;
+    const int gi = i0 + ii, gj = j0 + jj;
+    if (gi <= nxb - POP_NGHOST - 1 && gj <= nyb - POP_NGHOST - 1) {
+      const size_t q = (size_t)gj * nxb + gi;
+      const double c = sC[(jj + 1) * P2_1W + ii + 1];
+      const double* x = sX1 + (jj + 1) * P2_1W + (ii + 1);
+      const double ax = P2_AX(x, P2_1W, ii, jj);
+      const double r = sB[(jj + 1) * P2_1W + ii + 1] - ax;
+      const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+      const double qv = a.om2 * (r * a0r) + a.c12 * q1[s];
+      a.Qn[q] = qv;
+      a.Xn[q] = x[0] + qv;
+    }
+  }
+#undef P2_AX
+  if (SUM) {
+    dd rsum = block_reduce_dd(acc);
+    if (threadIdx.x == 0) {
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      a.partials[b * 2] = rsum.hi;
+      a.partials[b * 2 + 1] = rsum.lo;
+    }
+  }
+}
+
 static int pcsi(double* X, const double* B) {
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
             start = G.cfg.convergence_check_start;
   double *R = fld("BT_R"), *A0R = fld("BT_A0R");
-  double* W = fld("BT_PCSI");  // [X0, Q, X1]: (X0,Q) and (Q,X1) are both 2-level fields for the halo pass
-  double *Xb[2] = {W, W + 2 * G.n2}, *Q = W + G.n2;
+  double* W = fld("BT_PCSI");  // [X0, Q0, X1, Q1]: (X,Q) pairs are 2-level fields for the halo pass
+  double *Xb[2] = {W, W + 2 * G.n2}, *Qb[2] = {W + G.n2, W + 3 * G.n2};
   double rr = 0.0;
   const double csalpha = 2.0 / (G.pcsiMaxEigs - G.pcsiMinEigs);
   const double csbeta = (G.pcsiMaxEigs + G.pcsiMinEigs) / (G.pcsiMaxEigs - G.pcsiMinEigs);
   const double csy = csbeta / csalpha;
   double csomga = 2.0 / csy;
   // ---- prologue, as the reference (:1640-1700)
+  double* Q = Qb[0];
   BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
   bt_ew<EW_PCSI_INIT>(R, Q, A0R, nullptr, nullptr, nullptr, nullptr, 1.0 / csy);
   POP_TRY(bt_halo(Q));
@@ -413,28 +567,65 @@ static int pcsi(double* X, const double* B) {
   csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
   POP_CHECK_CUDA(cudaMemcpyAsync(Xb[0], X, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   bt_ew<EW_PCSI_QX>(Q, Xb[0], R, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
+  // the other pair starts as a copy so that cells no pass writes (closed-boundary ghost rows) agree
+  POP_CHECK_CUDA(cudaMemcpyAsync(Xb[1], Xb[0], sizeof(double) * 2 * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   G.numIterations = maxIt;
-  const dim3 grid((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((G.nyb + PC_TY - 1) / PC_TY), 1);
-  const int nblk = (int)(grid.x * grid.y);
-  POP_TRY(reduce_reserve_partials(nblk));
-  int cur = 0;  // X_m lives in Xb[cur]
-  for (int m = 1; m <= maxIt; m++) {
+  const dim3 grid1((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((G.nyb + PC_TY - 1) / PC_TY), 1);
+  const dim3 grid2((unsigned)((G.nxg + P2_TX - 1) / P2_TX), (unsigned)((G.ny_local + P2_TY - 1) / P2_TY), 1);
+  const int nblk1 = (int)(grid1.x * grid1.y), nblk2 = (int)(grid2.x * grid2.y);
+  POP_TRY(reduce_reserve_partials(nblk1 > nblk2 ? nblk1 : nblk2));
+  const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
+  const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
+  const bool blocking = !G.no_pcsi_blocking;
+#ifndef POP_EMUL
+  if (blocking) {
+    const int smem2 = (int)(sizeof(double) * P2_SMEM_DOUBLES);
+    POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)pcsi_iter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)pcsi_iter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  }
+#endif
+  int cur = 0;  // (X_m, Q_m) live in (Xb[cur], Qb[cur])
+  int m = 1;
+  while (m <= maxIt) {
     const bool check = (m % freq == 0) && (m >= start);
-    csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
-    PcsiArgs a;
-    a.v = bt_view();
-    a.X = Xb[cur]; a.Xn = Xb[cur ^ 1]; a.Q = Q; a.B = B;
-    a.om = csomga; a.c1 = csy * csomga - 1.0;
-    a.advance = (m < maxIt) ? 1 : 0;
-    a.partials = G.d_partials_big;
-    a.map_ghost = (G.nranks == 1) ? 1 : 0;
-    a.do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
-    a.do_tripole = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
-    a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
-    if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid, PC_TX * PC_TY, 0, a);
-    else POP_LAUNCH(pcsi_iter_kernel<false>, grid, PC_TX * PC_TY, 0, a);
-    if (a.advance && !a.map_ghost)
-      POP_TRY(halo_update(cur == 0 ? Q : W, 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));  // (Q,X1) / (X0,Q)
+    const bool next_is_check = ((m + 1) % freq == 0) && (m + 1 >= start);
+    int adv;  // iterations this pass advances X by
+    int nblk;
+    if (blocking && m + 2 <= maxIt && !next_is_check) {
+      Pcsi2Args a;
+      a.v = bt_view();
+      a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[cur ^ 1]; a.Qn = Qb[cur ^ 1];
+      csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
+      a.om1 = csomga; a.c11 = csy * csomga - 1.0;
+      csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+2}
+      a.om2 = csomga; a.c12 = csy * csomga - 1.0;
+      a.partials = G.d_partials_big;
+      a.do_ew = do_ew; a.do_tripole = do_tp; a.je0 = G.je - 1; a.nxg = G.nxg;
+      a.iglob = G.d_iglob; a.jglob = G.d_jglob;
+      const size_t smem2 = sizeof(double) * P2_SMEM_DOUBLES;
+      if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, grid2, P2_NT, smem2, a);
+      else POP_LAUNCH(pcsi_iter2_kernel<false>, grid2, P2_NT, smem2, a);
+      POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+      adv = 2;
+      nblk = nblk2;
+    } else {
+      csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
+      PcsiArgs a;
+      a.v = bt_view();
+      a.X = Xb[cur]; a.Xn = Xb[cur ^ 1]; a.Q = Qb[cur]; a.Qn = Qb[cur ^ 1]; a.B = B;
+      a.om = csomga; a.c1 = csy * csomga - 1.0;
+      a.advance = (m < maxIt) ? 1 : 0;
+      a.partials = G.d_partials_big;
+      a.map_ghost = (G.nranks == 1) ? 1 : 0;
+      a.do_ew = do_ew; a.do_tripole = do_tp;
+      a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
+      if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid1, PC_TX * PC_TY, 0, a);
+      else POP_LAUNCH(pcsi_iter_kernel<false>, grid1, PC_TX * PC_TY, 0, a);
+      if (a.advance && !a.map_ghost)
+        POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+      adv = a.advance;
+      nblk = nblk1;
+    }
     if (check) {
       POP_TRY(reduce_finish_n(1, RED_POST_RR, &rr, G.d_partials_big, nblk));
       if (rr < G.convergenceCriterion) {
@@ -442,7 +633,8 @@ static int pcsi(double* X, const double* B) {
         break;
       }
     }
-    if (a.advance) cur ^= 1;
+    if (adv) cur ^= 1;
+    m += (adv > 0) ? adv : 1;
   }
   // the answer is X_m of the last residual evaluation
   POP_CHECK_CUDA(cudaMemcpyAsync(X, Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));

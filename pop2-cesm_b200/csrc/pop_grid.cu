@@ -426,7 +426,7 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   POP_TRY(put("centerWgtClinic", CWC)); POP_TRY(put("btropWgtCenter", CWC));
   POP_TRY(puti("CHECKER", CHECKER)); POP_TRY(puti("CONSTNT", CONSTNT));
   for (const char* w : {"BT_R", "BT_S", "BT_Q", "BT_Z", "BT_AZ", "BT_A0R"}) POP_TRY(alloc_field(w, 1, false));
-  POP_TRY(alloc_field("BT_PCSI", 3, false));  // [X0, Q, X1] of the fused PCSI iteration
+  POP_TRY(alloc_field("BT_PCSI", 4, false));  // [X0, Q0, X1, Q1] of the fused PCSI iterations
   // vmix_const init: VVC = const_vvc, VDC = const_vdc
   if (c.vmix_itype == POP_VMIX_CONST) {
     HV v((size_t)G.vdc_nk * G.vdc_nd * n2, c.const_vdc);

@@ -148,3 +148,35 @@ def test_step_coupled_host_buffers_match_resident_step():
         assert np.array_equal(out[3], ref["UVEL"][0]) and np.array_equal(out[4], ref["VVEL"][0])
     finally:
         p.finalize()
+
+
+def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypatch):
+    """The temporally blocked P-CSI kernel (two iterations per pass, pcsi_iter2_kernel) must produce
+    the same bits and the same iteration count as one iteration per pass, on a grid with several tiles
+    in both directions, the tripole seam and the cyclic east-west seam (edge tiles are partial)."""
+    import os
+    cs = make_case(200, 90, 5, seed=71, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                   hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21,
+                   given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
+    res = {}
+    for tag, env in (("blocked", "0"), ("single", "1")):
+        monkeypatch.setenv("POP_B200_NO_PCSI_BLOCKING", env)
+        p = load_pop(cs)
+        try:
+            its = []
+            for ts in (c.TS_EULER, c.TS_LEAPFROG):
+                p.step(ts)
+                its.append(p.solvers_get_diagnostics()[0])
+            res[tag] = (its, pop_global(p, "PSURF", c.TIME_CUR), pop_global(p, "UVEL", c.TIME_CUR))
+        finally:
+            p.finalize()
+    assert res["blocked"][0] == res["single"][0]
+    assert min(res["blocked"][0]) >= 60
+    assert np.array_equal(res["blocked"][1], res["single"][1])
+    assert np.array_equal(res["blocked"][2], res["single"][2])
+    # and against the oracle
+    o = load_oracle(cs)
+    for ts in (c.TS_EULER, c.TS_LEAPFROG):
+        assert o.step(ts) == 0
+    assert o.solver_diag()[0] == res["blocked"][0][-1]
+    assert relerr(res["blocked"][1], oracle_global(o, "PSURF", c.TIME_CUR)) <= 2.0e-12
