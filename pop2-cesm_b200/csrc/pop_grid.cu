@@ -91,7 +91,9 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
       KMT[(size_t)(j + POP_NGHOST) * nxb + (i + POP_NGHOST)] = KMT_S[(size_t)j * G.nxg + i];
   POP_TRY(puti("KMT", KMT));
   POP_TRY(halo_update_i4(fldi("KMT"), 1, POP_LOC_CENTER, POP_KIND_SCALAR, 0));
-  POP_CHECK_CUDA(cudaMemcpy(KMT.data(), fldi("KMT"), n2 * sizeof(int), cudaMemcpyDeviceToHost));
+  // (ordered on the library stream: G.stream is non-blocking, a legacy-stream copy would race the halo)
+  POP_CHECK_CUDA(cudaMemcpyAsync(KMT.data(), fldi("KMT"), n2 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   for (HV* f : {&HTN, &HTE, &HUS, &HUW, &DXU, &DYU, &DXT, &DYT})  // grid.F90:1531-1538
     for (size_t q = 0; q < n2; q++)
       if ((*f)[q] <= 0.0) (*f)[q] = 1.0;
@@ -169,7 +171,8 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
     }
   POP_TRY(puti("KMU", KMU));
   POP_TRY(halo_update_i4(fldi("KMU"), 1, POP_LOC_NECORNER, POP_KIND_SCALAR, 0));
-  POP_CHECK_CUDA(cudaMemcpy(KMU.data(), fldi("KMU"), n2 * sizeof(int), cudaMemcpyDeviceToHost));
+  POP_CHECK_CUDA(cudaMemcpyAsync(KMU.data(), fldi("KMU"), n2 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   // ---- HT, HU, HUR, masks: grid.F90:1024-1041
   HV HT(n2), HU(n2), HUR(n2), RCALCT(n2), RCALCU(n2), FCOR(n2);
   for (size_t q = 0; q < n2; q++) {
@@ -425,6 +428,12 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   POP_TRY(put("centerWgtClinicIndep", CIND)); POP_TRY(put("mMaskTropic", MASK));
   POP_TRY(put("centerWgtClinic", CWC)); POP_TRY(put("btropWgtCenter", CWC));
   POP_TRY(puti("CHECKER", CHECKER)); POP_TRY(puti("CONSTNT", CONSTNT));
+  // the operator weights are derived from HU one row/column beyond each cell: on the outermost ghost row
+  // of a strip that neighbour does not exist locally, so take the owner's values (the two-iteration
+  // P-CSI pass evaluates the operator on the first ghost ring and must reproduce the owner's bits)
+  if (G.nranks > 1)
+    for (const char* w : {"btropWgtNE", "btropWgtEast", "btropWgtNorth", "centerWgtClinicIndep"})
+      POP_TRY(halo_rows_only(fld(w), 1));
   for (const char* w : {"BT_R", "BT_S", "BT_Q", "BT_Z", "BT_AZ", "BT_A0R"}) POP_TRY(alloc_field(w, 1, false));
   POP_TRY(alloc_field("BT_PCSI", 4, false));  // [X0, Q0, X1, Q1] of the fused PCSI iterations
   // vmix_const init: VVC = const_vvc, VDC = const_vdc

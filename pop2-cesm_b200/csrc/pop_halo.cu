@@ -219,7 +219,7 @@ static int ensure_halo_buffers(size_t elems) {  // elems: doubles per message
 }
 
 template <typename T>
-static int halo_update_t(T* a, int nz, int loc, int kind, T fill) {
+static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only = false) {
   (void)fill;  // no eliminated land blocks in the strip decomposition: nothing receives fillValue
   POP_REQUIRE(G.initialized, "POP_HaloUpdate: library not initialized");
   POP_REQUIRE(a != nullptr && nz >= 1, "POP_HaloUpdate: bad array");
@@ -261,7 +261,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill) {
     const size_t n = (size_t)nz * 4 * nxg;
     POP_LAUNCH(halo_ns_cyclic_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb, nyb, n2, nxg);
   }
-  const bool tripole_here = (ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1);
+  const bool tripole_here = (ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) && !rows_only;
   if (loc == POP_LOC_CENTER && kind == POP_KIND_SCALAR) {  // fused east-west wrap + tripole copy
     const int do_ew = (ew == POP_BNDY_CYCLIC) ? 1 : 0, do_tp = tripole_here ? 1 : 0;
     const size_t n = (do_ew ? (size_t)nz * nyb * 4 : 0) + (do_tp ? (size_t)nz * 2 * nxb : 0);
@@ -300,6 +300,11 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill) {
 
 int halo_update(double* a, int nz, int loc, int kind, double fill) {
   return halo_update_t<double>(a, nz, loc, kind, fill);
+}
+// strip rows from the neighbouring ranks + east-west wrap only (no fold): makes k-invariant coefficient
+// arrays that were derived locally exact copies of the owner's values two ghost rows deep
+int halo_rows_only(double* a, int nz) {
+  return halo_update_t<double>(a, nz, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0, true);
 }
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill) {
   return halo_update_t<int>(a, nz, loc, kind, fill);

@@ -1,0 +1,81 @@
+"""Worker of tests/test_gpu_multirank.py (one process per GPU, launched with torch.distributed.run):
+the same seeded case is advanced with one strip per rank (NCCL / peer-memory halos, rank-ordered
+double-double sums) and, on rank 0, with a single strip; the gathered fields must be bitwise equal and
+the solver iteration counts identical (decomposition independence)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from parity import *  # noqa: F401,F403,E402
+
+FIELDS_CMP = ("TRACER", "UVEL", "VVEL", "RHO", "PSURF", "UBTROP", "VBTROP", "GRADPX", "GRADPY")
+
+
+def run(cs, cfg, comm_id, steps):
+    p = load_pop(cs, cfg, comm_id)
+    try:
+        its = []
+        for ts in steps:
+            p.step(ts)
+            its.append(p.solvers_get_diagnostics()[0])
+        out = {n: p.gather(n, c.TIME_CUR) for n in FIELDS_CMP}
+        return its, out, p.rows()
+    finally:
+        p.finalize()
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    which = sys.argv[1] if len(sys.argv) > 1 else "pcsi"
+    kw = dict(nx=96, ny=64, km=6, seed=81)
+    if which == "pcsi":
+        kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
+                  lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21, given_vmix=True,
+                  solver_choice=c.SOLVER_PCSI, dtt=600.0)
+    elif which == "chrongear":
+        kw.update(convergence_criterion=1e-12)
+    elif which == "cyclic_pcg":
+        kw.update(ns=c.BNDY_CYCLIC, solver_choice=c.SOLVER_PCG, tadvect=c.TADVECT_UPWIND3, nt=3)
+    cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
+    steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG]
+    ref = None
+    if rank == 0:
+        ref = run(cs, c.copy_config(cs.cfg, rank=0, nranks=1, device=0), None, steps)
+    dist.barrier()
+    obj = [P.api.Pop.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    its, out, rows = run(cs, c.copy_config(cs.cfg, rank=rank, nranks=world, device=int(os.environ["LOCAL_RANK"])),
+                         obj[0], steps)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((its, out, (rows.start, rows.stop)), parts, dst=0)
+    ok = True
+    if rank == 0:
+        its1, out1, _ = ref
+        for r, (itr, _, _) in enumerate(parts):
+            if itr != its1:
+                print("FAIL rank %d solver iterations %s vs single-strip %s" % (r, itr, its1))
+                ok = False
+        for n in FIELDS_CMP:
+            full = np.concatenate([p_[1][n] for p_ in parts], axis=1)
+            if not np.array_equal(full, out1[n]):
+                d = np.max(np.abs(full - out1[n]))
+                s = np.max(np.abs(out1[n]))
+                print("FAIL %s differs from the single-strip run: max abs %.3e (rel %.3e)" % (n, d, d / max(s, 1e-300)))
+                ok = False
+        print("MULTIRANK %s world=%d iterations=%s %s" % (which, world, its1, "OK" if ok else "FAILED"))
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()
