@@ -243,15 +243,14 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
     if (north >= 0) POP_LAUNCH(halo_pack_rows<T>, gmsg, POP_EW_THREADS, 0, a, sN, nz, nxb, n2, nxg, G.je - 2);
     ncclComm_t comm = (ncclComm_t)G.nccl_comm;
     const size_t bytes = msg * sizeof(T);
+    // Two ranks on a cyclic north-south boundary have the same peer on both sides: NCCL pairs the
+    // sends and receives of a peer in issue order, so my message for the peer's SOUTH ghost rows (my
+    // north rows) must be my first send, matching the peer's first receive (from its south).
     ncclGroupStart();
-    if (south >= 0) {
-      ncclSend(sS, bytes, ncclChar, south, comm, G.stream);
-      ncclRecv(rS, bytes, ncclChar, south, comm, G.stream);
-    }
-    if (north >= 0) {
-      ncclSend(sN, bytes, ncclChar, north, comm, G.stream);
-      ncclRecv(rN, bytes, ncclChar, north, comm, G.stream);
-    }
+    if (north >= 0) ncclSend(sN, bytes, ncclChar, north, comm, G.stream);
+    if (south >= 0) ncclSend(sS, bytes, ncclChar, south, comm, G.stream);
+    if (south >= 0) ncclRecv(rS, bytes, ncclChar, south, comm, G.stream);
+    if (north >= 0) ncclRecv(rN, bytes, ncclChar, north, comm, G.stream);
     ncclResult_t r = ncclGroupEnd();
     POP_REQUIRE(r == ncclSuccess, "halo ncclGroupEnd: %s", ncclGetErrorString(r));
     if (south >= 0) POP_LAUNCH(halo_unpack_rows<T>, gmsg, POP_EW_THREADS, 0, a, rS, nz, nxb, n2, nxg, 0);
