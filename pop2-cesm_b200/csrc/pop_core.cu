@@ -290,6 +290,7 @@ extern "C" int pop_init(const pop_config* cfg) {
               "pop_init: vmix_itype=%d is not implemented (const, given)", cfg->vmix_itype);
   POP_TRY(alloc_all_fields());
   POP_TRY(reduce_alloc());
+  POP_TRY(p2p_setup());
   // time constants: time_management.F90:962-964,434-439
   G.dtt = G.dtu = G.dtp = cfg->dtt;
   G.alpha = 1.0 / 3.0;
@@ -307,6 +308,7 @@ extern "C" int pop_init(const pop_config* cfg) {
 
 extern "C" int pop_finalize(void) {
   if (G.stream) cudaStreamSynchronize(G.stream);
+  p2p_teardown();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();
   for (auto& kv : G.stage) cudaFree(kv.second.first);

@@ -95,6 +95,14 @@ struct Ctx {
   double* d_recvN = nullptr;
   size_t halo_buf_elems = 0;
   void* nccl_comm = nullptr;
+  // peer-memory halo (pop_halo.cu): mailbox in HBM that the neighbouring ranks write over NVLink
+  bool p2p_on = false;
+  double* p2p_mbox = nullptr;                       // [2 parities][2 sides][p2p_cap] + 2 flags
+  double *p2p_peerS = nullptr, *p2p_peerN = nullptr;  // the neighbours' mailboxes (CUDA IPC mappings)
+  size_t p2p_cap = 0;                               // doubles per message slot
+  unsigned long long p2p_seq = 0;                   // halo sequence number (same on every rank)
+  unsigned int* p2p_counter = nullptr;              // CTA arrival counter of the fused kernel
+  int* p2p_err = nullptr;                           // set by a kernel whose wait timed out
   // staging buffers for host-pointer arguments of the slab API
   std::map<std::string, std::pair<void*, size_t>> stage;
   // instrumentation
@@ -185,6 +193,9 @@ int halo_rows_only(double* a, int nz);
 int comm_init(int rank, int nranks, const char* id128);
 int comm_unique_id(char* id128);
 int comm_finalize();
+int p2p_setup();     // after the sizes are known (pop_init); falls back to NCCL send/recv when unavailable
+int p2p_teardown();
+int p2p_check();     // POP_FAIL if a peer wait timed out
 int comm_allreduce_min(double* host_value);
 // reductions (pop_reduce.cu): masked physical-domain sums of nfields 2-d fields, accumulated in
 // double-double; results (rounded to double) land in out_host[nfields] when out_host != nullptr

@@ -161,6 +161,66 @@ __global__ void halo_center_scalar_local(T* __restrict__ a, int nz, int nxb, int
   }
 }
 
+// ------------------------------------------------------------------ peer-memory strip exchange
+// One fused kernel per halo update replaces pack + ncclSend/ncclRecv + unpack: every CTA stores its
+// share of the two boundary rows of every level straight into the neighbour's mailbox (peer stores over
+// NVLink), the last CTA to finish publishes the sequence number in the neighbours' flag words, and the
+// CTAs then wait for their own flags and copy the received rows into the ghost rows.  A push never
+// waits, so the wait of any rank depends only on kernels its neighbours have already been able to
+// start; the grid is kept within one resident wave so that waiting CTAs cannot starve CTAs that still
+// have to push.  Mailbox slots alternate with the parity of the sequence number: slot p is rewritten
+// by the neighbour's update n+2, which it can only start after this rank pushed n+1, i.e. after this
+// rank finished reading update n.
+#ifndef POP_EMUL
+#define P2P_SPIN_LIMIT (4000000000LL)  // clock cycles (~2 s): a lost neighbour must not hang the GPU
+__global__ void __launch_bounds__(POP_EW_THREADS)
+halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int rowS, int rowN, int ghostS,
+                int ghostN, double* __restrict__ toS, double* __restrict__ toN,
+                unsigned long long* flagAtS, unsigned long long* flagAtN, const double* __restrict__ fromS,
+                const double* __restrict__ fromN, volatile unsigned long long* myFlags,
+                unsigned long long seq, unsigned int* counter, int* err) {
+  const size_t n = (size_t)nz * 2 * nxg;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // ---- push
+  for (size_t p = t0; p < n; p += stride) {
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
+    const size_t z = p / ((size_t)2 * nxg);
+    const double* az = a + z * n2 + POP_NGHOST + ig;
+    if (toS) toS[p] = az[(size_t)(rowS + r) * nxb];
+    if (toN) toN[p] = az[(size_t)(rowN + r) * nxb];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u) + 1u;
+    if (done == gridDim.x) {  // every CTA of this rank has pushed and fenced
+      *counter = 0u;
+      __threadfence_system();
+      if (flagAtS) *(volatile unsigned long long*)flagAtS = seq;
+      if (flagAtN) *(volatile unsigned long long*)flagAtN = seq;
+      __threadfence_system();
+    }
+    // ---- wait for the neighbours' rows (flag 0: from the south, flag 1: from the north)
+    const long long t_start = clock64();
+    bool ok = true;
+    while ((fromS && myFlags[0] < seq) || (fromN && myFlags[1] < seq)) {
+      if (clock64() - t_start > P2P_SPIN_LIMIT) { ok = false; break; }
+    }
+    if (!ok) *err = 1;
+    __threadfence_system();
+  }
+  __syncthreads();
+  // ---- pull
+  for (size_t p = t0; p < n; p += stride) {
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
+    const size_t z = p / ((size_t)2 * nxg);
+    double* az = a + z * n2 + POP_NGHOST + ig;
+    if (fromS) az[(size_t)(ghostS + r) * nxb] = __ldcv(fromS + p);
+    if (fromN) az[(size_t)(ghostN + r) * nxb] = __ldcv(fromN + p);
+  }
+}
+#endif
+
 // ------------------------------------------------------------------ communicator
 #ifndef POP_EMUL
 int comm_unique_id(char* id128) {
@@ -188,6 +248,82 @@ int comm_finalize() {
   G.nccl_comm = nullptr;
   return POP_SUCCESS;
 }
+int p2p_teardown() {
+  if (G.p2p_peerS) cudaIpcCloseMemHandle(G.p2p_peerS);
+  if (G.p2p_peerN && G.p2p_peerN != G.p2p_peerS) cudaIpcCloseMemHandle(G.p2p_peerN);
+  cudaFree(G.p2p_mbox);
+  cudaFree(G.p2p_counter);
+  cudaFree(G.p2p_err);
+  G.p2p_peerS = G.p2p_peerN = G.p2p_mbox = nullptr;
+  G.p2p_counter = nullptr;
+  G.p2p_err = nullptr;
+  G.p2p_on = false;
+  G.p2p_cap = 0;
+  G.p2p_seq = 0;
+  return POP_SUCCESS;
+}
+int p2p_setup() {
+  p2p_teardown();
+  if (G.nranks <= 1 || !G.nccl_comm) return POP_SUCCESS;
+  if (getenv("POP_B200_NO_P2P") && getenv("POP_B200_NO_P2P")[0] == '1') return POP_SUCCESS;
+  const int ns = G.cfg.ns_boundary_type;
+  const int south = (G.rank > 0) ? G.rank - 1 : (ns == POP_BNDY_CYCLIC ? G.nranks - 1 : -1);
+  const int north = (G.rank < G.nranks - 1) ? G.rank + 1 : (ns == POP_BNDY_CYCLIC ? 0 : -1);
+  const int nzmax = G.km * G.nt > G.km + 2 ? G.km * G.nt : G.km + 2;
+  G.p2p_cap = (size_t)nzmax * 2 * G.nxg;
+  const size_t bytes = (4 * G.p2p_cap + 2) * sizeof(double);
+  // every step below is collective; a rank that fails still takes part and the verdict is agreed with a
+  // min-reduction so that all ranks choose the same path
+  double ok = 1.0;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&G.p2p_mbox, bytes) != cudaSuccess || cudaMemset(G.p2p_mbox, 0, bytes) != cudaSuccess ||
+      cudaMalloc(&G.p2p_counter, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(G.p2p_counter, 0, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMalloc(&G.p2p_err, sizeof(int)) != cudaSuccess || cudaMemset(G.p2p_err, 0, sizeof(int)) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, G.p2p_mbox) != cudaSuccess)
+    ok = 0.0;
+  cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  char *d_send = nullptr, *d_all = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(G.nranks);
+  POP_CHECK_CUDA(cudaMalloc(&d_send, 64));
+  POP_CHECK_CUDA(cudaMalloc(&d_all, 64 * (size_t)G.nranks));
+  POP_CHECK_CUDA(cudaMemcpyAsync(d_send, &mine, 64, cudaMemcpyHostToDevice, G.stream));
+  ncclResult_t r = ncclAllGather(d_send, d_all, 64, ncclChar, (ncclComm_t)G.nccl_comm, G.stream);
+  POP_REQUIRE(r == ncclSuccess, "p2p_setup ncclAllGather: %s", ncclGetErrorString(r));
+  POP_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_all, 64 * (size_t)G.nranks, cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  cudaFree(d_send);
+  cudaFree(d_all);
+  if (ok == 1.0) {
+    void* ps = nullptr;
+    void* pn = nullptr;
+    if (south >= 0 && cudaIpcOpenMemHandle(&ps, all[south], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+    if (ok == 1.0 && north >= 0) {
+      if (north == south) pn = ps;
+      else if (cudaIpcOpenMemHandle(&pn, all[north], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+    }
+    cudaGetLastError();
+    G.p2p_peerS = (double*)ps;
+    G.p2p_peerN = (double*)pn;
+  }
+  POP_TRY(comm_allreduce_min(&ok));
+  if (ok != 1.0) {
+    p2p_teardown();
+    return POP_SUCCESS;  // NCCL send/recv path
+  }
+  G.p2p_on = true;
+  return POP_SUCCESS;
+}
+int p2p_check() {
+  if (!G.p2p_on) return POP_SUCCESS;
+  int e = 0;
+  POP_CHECK_CUDA(cudaMemcpyAsync(&e, G.p2p_err, sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  POP_REQUIRE(e == 0, "POP_HaloUpdate: timed out waiting for a neighbouring rank's strip rows");
+  return POP_SUCCESS;
+}
 int comm_allreduce_min(double* v) {
   if (G.nranks == 1) return POP_SUCCESS;
   double* d = G.d_local;
@@ -203,6 +339,9 @@ int comm_unique_id(char* id128) { memset(id128, 0, 128); return POP_SUCCESS; }
 int comm_init(int, int, const char*) { return POP_SUCCESS; }
 int comm_finalize() { return POP_SUCCESS; }
 int comm_allreduce_min(double*) { return POP_SUCCESS; }
+int p2p_setup() { return POP_SUCCESS; }
+int p2p_teardown() { return POP_SUCCESS; }
+int p2p_check() { return POP_SUCCESS; }
 #endif
 
 static int ensure_halo_buffers(size_t elems) {  // elems: doubles per message
@@ -236,6 +375,25 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
 #ifndef POP_EMUL
     const int south = (G.rank > 0) ? G.rank - 1 : (ns == POP_BNDY_CYCLIC ? G.nranks - 1 : -1);
     const int north = (G.rank < G.nranks - 1) ? G.rank + 1 : (ns == POP_BNDY_CYCLIC ? 0 : -1);
+    if (G.p2p_on && sizeof(T) == sizeof(double) && msg <= G.p2p_cap) {
+      const unsigned long long seq = ++G.p2p_seq;
+      const size_t par = (size_t)(seq & 1ull);
+      double* mb = G.p2p_mbox;
+      unsigned long long* myFlags = (unsigned long long*)(mb + 4 * G.p2p_cap);
+      // slot(parity, side): side 0 holds rows from the south neighbour, side 1 rows from the north neighbour
+      double* toS = south >= 0 ? G.p2p_peerS + (par * 2 + 1) * G.p2p_cap : nullptr;  // I am its north neighbour
+      double* toN = north >= 0 ? G.p2p_peerN + (par * 2 + 0) * G.p2p_cap : nullptr;
+      unsigned long long* fS = south >= 0 ? (unsigned long long*)(G.p2p_peerS + 4 * G.p2p_cap) + 1 : nullptr;
+      unsigned long long* fN = north >= 0 ? (unsigned long long*)(G.p2p_peerN + 4 * G.p2p_cap) + 0 : nullptr;
+      const double* fromS = south >= 0 ? mb + (par * 2 + 0) * G.p2p_cap : nullptr;
+      const double* fromN = north >= 0 ? mb + (par * 2 + 1) * G.p2p_cap : nullptr;
+      unsigned grid = ew_grid(msg);
+      const unsigned wave = (unsigned)G.sm_count * 2;  // one resident wave (<= 8 CTAs of 256 threads fit per SM)
+      if (grid > wave) grid = wave;
+      POP_LAUNCH(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
+                 toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter,
+                 G.p2p_err);
+    } else {
     const size_t msg_d = (msg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
     POP_TRY(ensure_halo_buffers(msg_d));
     T *sS = (T*)G.d_sendS, *sN = (T*)G.d_sendN, *rS = (T*)G.d_recvS, *rN = (T*)G.d_recvN;
@@ -255,6 +413,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
     POP_REQUIRE(r == ncclSuccess, "halo ncclGroupEnd: %s", ncclGetErrorString(r));
     if (south >= 0) POP_LAUNCH(halo_unpack_rows<T>, gmsg, POP_EW_THREADS, 0, a, rS, nz, nxb, n2, nxg, 0);
     if (north >= 0) POP_LAUNCH(halo_unpack_rows<T>, gmsg, POP_EW_THREADS, 0, a, rN, nz, nxb, n2, nxg, G.je);
+    }
 #endif
   } else if (ns == POP_BNDY_CYCLIC) {
     const size_t n = (size_t)nz * 4 * nxg;

@@ -296,5 +296,6 @@ int step_dev(int ts_type) {
     G.curtime = G.newtime;
     G.newtime = tmp;
   }
+  POP_TRY(p2p_check());
   return pop_post_launch("step");
 }
