@@ -225,6 +225,12 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def ncu_traffic():
+    """measured DRAM bytes per unit of work of each kernel, from the committed ncu capture"""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -302,7 +308,8 @@ def run_pop(args):
     launches = p.launches() - l0
     ms = e0.elapsed_time(e1)
     p.timers(False)
-    tnames = ["TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "MOMENTUM_FINISH", "SOLVER", "BAROTROPIC", "HALO", "STEP"]
+    tnames = ["TRACER_UPDATE", "CLINIC", "VMIX_TRACER_IMPLICIT", "STATE", "MOMENTUM_FINISH", "SOLVER", "BAROTROPIC", "HALO", "STEP",
+              "PCSI_PASS2_KERNEL"]
     tm = {n: p.timer(n) for n in tnames}
     if args.no_e2e:      # profiling runs (tools/ncu_kernels.sh): device-resident region only, no JSON contract
         p.finalize()
@@ -339,6 +346,7 @@ def run_pop(args):
         ms, ms_e2e = float(t[0]), float(t[1])
     cells = float(nx) * ny * km
     ocean = float(np.sum(kmt))
+    p_nxb, p_nyb = p.nxb, p.nyb
     p.finalize()
     if rank != 0:
         return
@@ -352,13 +360,37 @@ def run_pop(args):
             per = tms / calls
             kern[n] = {"ms_per_launch": per, "calls": calls, "GBs": bpc[n] * local_cells / (per * 1e-3) / 1e9,
                        "share_of_step": tms / ms}
-    dom = max(kern, key=lambda n: kern[n]["ms_per_launch"] * kern[n]["calls"]) if kern else None
+    if "CLINIC" in kern and "MOMENTUM_FINISH" in kern:   # the CLINIC timer spans the column kernel and the finish kernel
+        per = (tm["CLINIC"][0] - tm["MOMENTUM_FINISH"][0]) / tm["CLINIC"][1]
+        kern["MOMENTUM_COLUMN"] = {"ms_per_launch": per, "calls": tm["CLINIC"][1],
+                                   "GBs": bpc["CLINIC"] * local_cells / (per * 1e-3) / 1e9,
+                                   "share_of_step": per * tm["CLINIC"][1] / ms}
+        del kern["CLINIC"]
+    # the P-CSI pass kernel (two iterations per launch): 72 B per 2-d point per launch = X,Q,B and the four
+    # operator weights read once, Q and X written once; sampled with CUDA events
+    pts = float(p_nxb) * p_nyb
+    if tm["PCSI_PASS2_KERNEL"][1]:
+        per = tm["PCSI_PASS2_KERNEL"][0] / tm["PCSI_PASS2_KERNEL"][1]
+        passes = sum(iters) / 2.0
+        kern["PCSI_PASS2_KERNEL"] = {"ms_per_launch": per, "calls": tm["PCSI_PASS2_KERNEL"][1], "launches_per_run": passes,
+                                     "GBs": 72.0 * pts / (per * 1e-3) / 1e9, "share_of_step": per * passes / ms,
+                                     "note": "every 16th launch timed; share = sampled mean x launches"}
+    traffic = ncu_traffic()
+    for n in kern:
+        unit = pts if n == "PCSI_PASS2_KERNEL" else local_cells
+        kern[n]["traffic_bytes"] = traffic[n]["bytes_per_unit"] * unit if n in traffic else None
+    share = lambda n: kern[n]["share_of_step"]
+    dom = max(kern, key=share) if kern else None
     roof = None
     if dom:
+        unit = pts if dom == "PCSI_PASS2_KERNEL" else local_cells
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBs"] / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_cell": bpc[dom], "cells_per_launch": local_cells,
-                "ms_per_launch": kern[dom]["ms_per_launch"], "all_kernels": kern}
+                "frac": kern[dom]["GBs"] / peak, "traffic": kern[dom]["traffic_bytes"], "peak_source": peak_src,
+                "bytes_per_unit": 72 if dom == "PCSI_PASS2_KERNEL" else bpc["CLINIC" if dom == "MOMENTUM_COLUMN" else dom],
+                "units_per_launch": unit, "unit_of_work": "2-d point (two P-CSI iterations)" if dom == "PCSI_PASS2_KERNEL" else "3-d cell",
+                "ms_per_launch": kern[dom]["ms_per_launch"],
+                "traffic_source": "ncu dram__bytes_read+write per unit (profiles/ncu_traffic.json) x units per launch",
+                "all_kernels": kern}
     out = {
         "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)" if args.workload == "tx0.1v3"
                   else "cell-updates/s, full baroclinic+barotropic step",
