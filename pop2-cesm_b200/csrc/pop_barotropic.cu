@@ -396,13 +396,16 @@ pcsi_iter_kernel(const PcsiArgs a) {
 // ghost rows owned by a neighbouring rank hold that rank's bits two cells deep.  One 2-level halo
 // update of (X,Q) follows every pass (P > 1: one strip exchange per two iterations).
 #define P2_TX 64
-#define P2_TY 8
+#define P2_TY 16
 #define P2_NT 256
-#define P2_XW (P2_TX + 4)  // width of the tiles that start two cells west of the tile (X, E, NE)
-#define P2_1W (P2_TX + 2)  // width of the tiles that start one cell west (X1, C, B, Q, N)
-#define P2_SMEM_DOUBLES                                                                              \
-  ((P2_TY + 4) * P2_XW + 4 * (P2_TY + 2) * P2_1W + (P2_TY + 3) * P2_1W + (P2_TY + 2) * P2_XW +      \
-   (P2_TY + 3) * P2_XW)
+// every staged tile starts two cells west of the tile (an even column: TMA needs the first element of a
+// box on a 16-byte boundary) and is P2_XW wide; X, N, NE start two rows south, the others one row south
+#define P2_XW (P2_TX + 4)
+#define P2_PAD16(n) (((n) + 15) / 16 * 16)  // TMA destinations start on 128-byte boundaries
+#define P2_N_X P2_PAD16((P2_TY + 4) * P2_XW)
+#define P2_N_1 P2_PAD16((P2_TY + 2) * P2_XW)
+#define P2_N_2 P2_PAD16((P2_TY + 3) * P2_XW)
+#define P2_SMEM_DOUBLES (P2_N_X + 5 * P2_N_1 + 2 * P2_N_2 + 16)
 struct Pcsi2Args {
   BtView v;
   const double *X, *Q, *B;  // X_m, Q_m
@@ -411,6 +414,8 @@ struct Pcsi2Args {
   double* partials;
   int do_ew, do_tripole, je0, nxg;
   const int *iglob, *jglob;
+  int use_tma;
+  PopTmap tmX, tmC, tmB, tmQ, tmN, tmE, tmNE;  // 2-d tensor maps with the box of each staged tile
 };
 // cooperative asynchronous staging of a w x h window of a 2-d field (origin gi0,gj0; zero outside)
 __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__ src, int w, int h, int gi0,
@@ -422,116 +427,180 @@ __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__
   }
 }
 template <bool SUM>
-__global__ void __launch_bounds__(P2_NT, 4)
-pcsi_iter2_kernel(const Pcsi2Args a) {
+__global__ void __launch_bounds__(P2_NT, 2)
+pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   POP_DYN_SMEM(smem_raw);
-  double* sX = (double*)smem_raw;                  // X_m: tile + 2-cell ring        (TY+4) x XW
-  double* sX1 = sX + (P2_TY + 4) * P2_XW;          // X_{m+1}: tile + 1-cell ring    (TY+2) x 1W
-  double* sC = sX1 + (P2_TY + 2) * P2_1W;          // centre weight                  (TY+2) x 1W
-  double* sB = sC + (P2_TY + 2) * P2_1W;           // right-hand side
-  double* sQ = sB + (P2_TY + 2) * P2_1W;           // Q_m
-  double* sN = sQ + (P2_TY + 2) * P2_1W;           // north weight, one extra row south  (TY+3) x 1W
-  double* sE = sN + (P2_TY + 3) * P2_1W;           // east weight, one extra column west (TY+2) x XW
-  double* sNE = sE + (P2_TY + 2) * P2_XW;          // NE weight, extra row + column      (TY+3) x XW
+  double* sX = (double*)smem_raw;  // X_m              rows j0-2 .. j0+TY+1
+  double* sX1 = sX + P2_N_X;       // X_{m+1}          rows j0-1 .. j0+TY
+  double* sC = sX1 + P2_N_1;       // centre weight    rows j0-1 ..
+  double* sB = sC + P2_N_1;        // right-hand side
+  double* sQ = sB + P2_N_1;        // Q_m, then Q_{m+1}
+  double* sE = sQ + P2_N_1;        // east weight
+  double* sN = sE + P2_N_1;        // north weight     rows j0-2 .. j0+TY
+  double* sNE = sN + P2_N_2;       // NE weight        rows j0-2 .. j0+TY
+  uint64_t* s_bar = (uint64_t*)(sNE + P2_N_2);
   const BtView& v = a.v;
   const int nxb = v.nxb, nyb = v.nyb;
   const int i0 = POP_NGHOST + blockIdx.x * P2_TX, j0 = POP_NGHOST + blockIdx.y * P2_TY;  // 0-based tile origin
   const int tid = threadIdx.x;
-  // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA)
-  p2_stage(sX, a.X, P2_XW, P2_TY + 4, i0 - 2, j0 - 2, nxb, nyb, tid);
-  p2_stage(sC, v.C, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
-  p2_stage(sB, a.B, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
-  p2_stage(sQ, a.Q, P2_1W, P2_TY + 2, i0 - 1, j0 - 1, nxb, nyb, tid);
-  p2_stage(sN, v.N, P2_1W, P2_TY + 3, i0 - 1, j0 - 2, nxb, nyb, tid);
-  p2_stage(sE, v.E, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
-  p2_stage(sNE, v.NE, P2_XW, P2_TY + 3, i0 - 2, j0 - 2, nxb, nyb, tid);
-  cp_async_wait_all();
-  __syncthreads();
-  // 9-point operator at tile-relative cell (ii,jj), X values from tile `x` of width `xw` whose element
-  // (ii,jj) is x[0]
-#define P2_AX(x, xw, ii, jj)                                                                              \
-  (sC[((jj) + 1) * P2_1W + (ii) + 1] * (x)[0] + sN[((jj) + 2) * P2_1W + (ii) + 1] * (x)[(xw)] +           \
-   sN[((jj) + 1) * P2_1W + (ii) + 1] * (x)[-(xw)] + sE[((jj) + 1) * P2_XW + (ii) + 2] * (x)[1] +          \
-   sE[((jj) + 1) * P2_XW + (ii) + 1] * (x)[-1] + sNE[((jj) + 2) * P2_XW + (ii) + 2] * (x)[(xw) + 1] +     \
-   sNE[((jj) + 1) * P2_XW + (ii) + 2] * (x)[-(xw) + 1] + sNE[((jj) + 2) * P2_XW + (ii) + 1] * (x)[(xw) - 1] + \
-   sNE[((jj) + 1) * P2_XW + (ii) + 1] * (x)[-(xw) - 1])
+  // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA):
+  // seven TMA box copies issued by one thread (no per-element instructions), or per-thread cp.async
+  if (a.use_tma) {
+    if (tid == 0) {
+      mbar_init(s_bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      constexpr uint32_t bytes = 8u * P2_XW * ((P2_TY + 4) + 4 * (P2_TY + 2) + 2 * (P2_TY + 3));
+      mbar_expect_tx(s_bar, bytes);
+      tma_load_box2d(sX, &a.tmX, i0 - 2, j0 - 2, s_bar);
+      tma_load_box2d(sC, &a.tmC, i0 - 2, j0 - 1, s_bar);
+      tma_load_box2d(sB, &a.tmB, i0 - 2, j0 - 1, s_bar);
+      tma_load_box2d(sQ, &a.tmQ, i0 - 2, j0 - 1, s_bar);
+      tma_load_box2d(sE, &a.tmE, i0 - 2, j0 - 1, s_bar);
+      tma_load_box2d(sN, &a.tmN, i0 - 2, j0 - 2, s_bar);
+      tma_load_box2d(sNE, &a.tmNE, i0 - 2, j0 - 2, s_bar);
+    }
+    mbar_wait(s_bar, 0u);
+  } else {
+    p2_stage(sX, a.X, P2_XW, P2_TY + 4, i0 - 2, j0 - 2, nxb, nyb, tid);
+    p2_stage(sC, v.C, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
+    p2_stage(sB, a.B, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
+    p2_stage(sQ, a.Q, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
+    p2_stage(sE, v.E, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
+    p2_stage(sN, v.N, P2_XW, P2_TY + 3, i0 - 2, j0 - 2, nxb, nyb, tid);
+    p2_stage(sNE, v.NE, P2_XW, P2_TY + 3, i0 - 2, j0 - 2, nxb, nyb, tid);
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  // Thread <-> column ii of a strip of rows; it marches north keeping the 3x3 X window and the three
+  // "southern" weights in registers, so an evaluation costs 11 shared-memory loads instead of 20.
   dd acc{0.0, 0.0};
-  constexpr int NSLOT = (P2_TX * P2_TY) / P2_NT;  // tile cells per thread
-  constexpr int NRING = 2 * P2_1W + 2 * P2_TY;
-  double q1[NSLOT];
-  // ---- iteration m on the tile + ring.  Slots 0..NSLOT-1: the thread's tile cells; NSLOT: a ring cell.
-#pragma unroll
-  for (int s = 0; s <= NSLOT; s++) {
-    int ii, jj;
-    if (s < NSLOT) {
-      ii = tid % P2_TX;
-      jj = (tid / P2_TX) * NSLOT + s;
-    } else {
-      // ring enumeration: bottom and top rows (2 x P2_1W), then left and right columns (2 x P2_TY)
-      if (tid >= NRING) break;
-      if (tid < 2 * P2_1W) { ii = tid % P2_1W - 1; jj = (tid < P2_1W) ? -1 : P2_TY; }
-      else { const int t = tid - 2 * P2_1W; ii = (t < P2_TY) ? -1 : P2_TX; jj = t % P2_TY; }
+  constexpr int NSTRIP = P2_NT / P2_TX;  // 4 strips of rows
+  const int ii = tid % P2_TX, strip = tid / P2_TX;
+  const int gi = i0 + ii;
+  // where the first ghost ring of the block has a source cell the update is evaluated there (global memory)
+  auto eval_at_source = [&](int gi_, int gj_, bool& mapped, double& x1) {
+    int si = gi_, sj = gj_;
+    if (a.do_tripole && gj_ > a.je0) {
+      int ig = a.nxg - a.iglob[gi_] + 1;
+      if (ig == 0) ig = a.nxg;
+      if (ig >= 1 && ig <= a.nxg) { si = POP_NGHOST - 1 + ig; sj = 2 * a.je0 + 1 - gj_; }
+    } else if (a.do_ew && (gi_ < POP_NGHOST || gi_ >= nxb - POP_NGHOST) && a.jglob[gj_] > 0) {
+      si = (gi_ < POP_NGHOST) ? gi_ + (nxb - 2 * POP_NGHOST) : gi_ - (nxb - 2 * POP_NGHOST);
     }
-    const int gi = i0 + ii, gj = j0 + jj;
-    double x1 = 0.0, qv = 0.0;
-    if (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
-      // ghost cell with a source: evaluate there, from global memory
-      int si = gi, sj = gj;
-      if (a.do_tripole && gj > a.je0) {
-        int ig = a.nxg - a.iglob[gi] + 1;
-        if (ig == 0) ig = a.nxg;
-        if (ig >= 1 && ig <= a.nxg) { si = POP_NGHOST - 1 + ig; sj = 2 * a.je0 + 1 - gj; }
-      } else if (a.do_ew && (gi < POP_NGHOST || gi >= nxb - POP_NGHOST) && a.jglob[gj] > 0) {
-        si = (gi < POP_NGHOST) ? gi + (nxb - 2 * POP_NGHOST) : gi - (nxb - 2 * POP_NGHOST);
+    mapped = (si != gi_ || sj != gj_);
+    if (!mapped) return;
+    const size_t q = (size_t)sj * nxb + si;
+    const double* X = a.X;
+    const double c = ldg(v.C + q);
+    const double ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
+                      ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
+                      ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
+                      ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
+    const double r = ldg(a.B + q) - ax;
+    const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+    x1 = ldg(X + q) + (a.om1 * (r * a0r) + a.c11 * ldg(a.Q + q));
+  };
+  const bool edge_cta = (i0 + P2_TX + 1 >= nxb - POP_NGHOST) || (i0 - 1 < POP_NGHOST) || (j0 - 1 < POP_NGHOST) ||
+                        (j0 + P2_TY >= nyb - POP_NGHOST);  // the tile + ring touches ghost cells of the block
+  // ---- iteration m on the tile + ring: rows -1 .. TY split over the strips
+  {
+    constexpr int NR1 = P2_TY + 2;
+    const int r0 = -1 + (strip * NR1) / NSTRIP, r1 = -1 + ((strip + 1) * NR1) / NSTRIP;  // [r0, r1)
+    // window rows (r0-1, r0) of X_m at columns ii-1..ii+1; tile row jj is row jj+2 of sX
+    const double* xr = sX + (r0 + 1) * P2_XW + (ii + 2);
+    double xm0 = xr[-1], xm1 = xr[0], xm2 = xr[1];
+    double xc0 = xr[P2_XW - 1], xc1 = xr[P2_XW], xc2 = xr[P2_XW + 1];
+    double n_s = sN[(r0 + 1) * P2_XW + ii + 2];      // N(ii, r0-1): sN row jj+2
+    double ne_s = sNE[(r0 + 1) * P2_XW + ii + 2];    // NE(ii, r0-1)
+    double ne_sw = sNE[(r0 + 1) * P2_XW + ii + 1];   // NE(ii-1, r0-1)
+    for (int jj = r0; jj < r1; jj++) {
+      const int o1 = (jj + 1) * P2_XW + ii + 2;       // cell in the tiles whose first row is j0-1, first col i0-1
+      const int oX = (jj + 1) * P2_XW + ii + 2;       // same for first col i0-2
+      const double* xn = sX + (jj + 3) * P2_XW + (ii + 2);
+      const double xp0 = xn[-1], xp1 = xn[0], xp2 = xn[1];
+      const double c = sC[o1], n = sN[o1 + P2_XW], e = sE[oX], ew = sE[oX - 1];
+      const double ne = sNE[oX + P2_XW], nw = sNE[oX + P2_XW - 1];
+      const int gj = j0 + jj;
+      double x1 = 0.0, qv = 0.0;
+      if (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
+        bool mapped = false;
+        if (edge_cta) eval_at_source(gi, gj, mapped, x1);
+        if (!mapped) {
+          const double ax = c * xc1 + n * xp1 + n_s * xm1 + e * xc2 + ew * xc0 + ne * xp2 + ne_s * xm2 + nw * xp0 +
+                            ne_sw * xm0;
+          const double r = sB[o1] - ax;
+          if (SUM && jj >= 0 && jj < P2_TY && bt_physical(v, gi, gj))
+            acc = dd_add_d(acc, (r * r) * ldg(v.mask + (size_t)gj * nxb + gi));
+          const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+          qv = a.om1 * (r * a0r) + a.c11 * sQ[o1];
+          x1 = xc1 + qv;
+        }
       }
-      double c, ax, xc, b, qm;
-      if (si != gi || sj != gj) {
-        const size_t q = (size_t)sj * nxb + si;
-        const double* X = a.X;
-        c = ldg(v.C + q);
-        ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
-             ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
-             ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
-             ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
-        xc = ldg(X + q);
-        b = ldg(a.B + q);
-        qm = ldg(a.Q + q);
-      } else {
-        const double* x = sX + (jj + 2) * P2_XW + (ii + 2);
-        c = sC[(jj + 1) * P2_1W + ii + 1];
-        ax = P2_AX(x, P2_XW, ii, jj);
-        xc = x[0];
-        b = sB[(jj + 1) * P2_1W + ii + 1];
-        qm = sQ[(jj + 1) * P2_1W + ii + 1];
-      }
-      const double r = b - ax;
-      if (SUM && s < NSLOT && bt_physical(v, gi, gj)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + (size_t)gj * nxb + gi));
-      const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
-      qv = a.om1 * (r * a0r) + a.c11 * qm;
-      x1 = xc + qv;
+      sX1[o1] = x1;
+      sQ[o1] = qv;  // Q_{m+1} of the cell (only this thread touches it before the barrier)
+      xm0 = xc0; xm1 = xc1; xm2 = xc2;
+      xc0 = xp0; xc1 = xp1; xc2 = xp2;
+      n_s = n; ne_s = ne; ne_sw = nw;
     }
-    sX1[(jj + 1) * P2_1W + (ii + 1)] = x1;
-    if (s < NSLOT) q1[s] = qv;
+    // the two ring columns ii = -1 and ii = TX: one cell per thread, straight from the tiles
+    if (tid < 2 * NR1) {
+      const int jj = tid % NR1 - 1, ic = (tid < NR1) ? -1 : P2_TX;
+      const int gic = i0 + ic, gj = j0 + jj;
+      const int o1 = (jj + 1) * P2_XW + ic + 2, oX = (jj + 1) * P2_XW + ic + 2;
+      double x1 = 0.0;
+      if (gic >= 1 && gic <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
+        bool mapped = false;
+        if (edge_cta) eval_at_source(gic, gj, mapped, x1);
+        if (!mapped) {
+          const double* x = sX + (jj + 2) * P2_XW + (ic + 2);
+          const double c = sC[o1];
+          const double ax = c * x[0] + sN[o1 + P2_XW] * x[P2_XW] + sN[o1] * x[-P2_XW] + sE[oX] * x[1] +
+                            sE[oX - 1] * x[-1] + sNE[oX + P2_XW] * x[P2_XW + 1] + sNE[oX] * x[-P2_XW + 1] +
+                            sNE[oX + P2_XW - 1] * x[P2_XW - 1] + sNE[oX - 1] * x[-P2_XW - 1];
+          const double r = sB[o1] - ax;
+          const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+          x1 = x[0] + (a.om1 * (r * a0r) + a.c11 * sQ[o1]);
+        }
+      }
+      sX1[o1] = x1;
+    }
   }
   __syncthreads();
-  // ---- iteration m+1 on the tile (physical cells only)
-#pragma unroll
-  for (int s = 0; s < NSLOT; s++) {
-    const int ii = tid % P2_TX, jj = (tid / P2_TX) * NSLOT + s;
-    const int gi = i0 + ii, gj = j0 + jj;
-    if (gi <= nxb - POP_NGHOST - 1 && gj <= nyb - POP_NGHOST - 1) {
-      const size_t q = (size_t)gj * nxb + gi;
-      const double c = sC[(jj + 1) * P2_1W + ii + 1];
-      const double* x = sX1 + (jj + 1) * P2_1W + (ii + 1);
-      const double ax = P2_AX(x, P2_1W, ii, jj);
-      const double r = sB[(jj + 1) * P2_1W + ii + 1] - ax;
-      const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
-      const double qv = a.om2 * (r * a0r) + a.c12 * q1[s];
-      a.Qn[q] = qv;
-      a.Xn[q] = x[0] + qv;
+  // ---- iteration m+1 on the tile (physical cells only): rows 0 .. TY-1 split over the strips
+  {
+    const int r0 = (strip * P2_TY) / NSTRIP, r1 = ((strip + 1) * P2_TY) / NSTRIP;
+    // tile row jj is row jj+1 of sX1
+    const double* xr = sX1 + r0 * P2_XW + (ii + 2);
+    double xm0 = xr[-1], xm1 = xr[0], xm2 = xr[1];
+    double xc0 = xr[P2_XW - 1], xc1 = xr[P2_XW], xc2 = xr[P2_XW + 1];
+    double n_s = sN[(r0 + 1) * P2_XW + ii + 2];
+    double ne_s = sNE[(r0 + 1) * P2_XW + ii + 2];
+    double ne_sw = sNE[(r0 + 1) * P2_XW + ii + 1];
+    for (int jj = r0; jj < r1; jj++) {
+      const int o1 = (jj + 1) * P2_XW + ii + 2, oX = (jj + 1) * P2_XW + ii + 2;
+      const double* xn = sX1 + (jj + 2) * P2_XW + (ii + 2);
+      const double xp0 = xn[-1], xp1 = xn[0], xp2 = xn[1];
+      const double c = sC[o1], n = sN[o1 + P2_XW], e = sE[oX], ew = sE[oX - 1];
+      const double ne = sNE[oX + P2_XW], nw = sNE[oX + P2_XW - 1];
+      const int gj = j0 + jj;
+      if (gi <= nxb - POP_NGHOST - 1 && gj <= nyb - POP_NGHOST - 1) {
+        const double ax = c * xc1 + n * xp1 + n_s * xm1 + e * xc2 + ew * xc0 + ne * xp2 + ne_s * xm2 + nw * xp0 +
+                          ne_sw * xm0;
+        const double r = sB[o1] - ax;
+        const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
+        const double qv = a.om2 * (r * a0r) + a.c12 * sQ[o1];
+        const size_t q = (size_t)gj * nxb + gi;
+        a.Qn[q] = qv;
+        a.Xn[q] = xc1 + qv;
+      }
+      xm0 = xc0; xm1 = xc1; xm2 = xc2;
+      xc0 = xp0; xc1 = xp1; xc2 = xp2;
+      n_s = n; ne_s = ne; ne_sw = nw;
     }
   }
-#undef P2_AX
   if (SUM) {
     dd rsum = block_reduce_dd(acc);
     if (threadIdx.x == 0) {
@@ -577,6 +646,17 @@ static int pcsi(double* X, const double* B) {
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
   const bool blocking = !G.no_pcsi_blocking;
+  // tensor maps of the staged tiles (X and Q for both buffers); without TMA the kernel stages with cp.async
+  PopTmap tmXb[2], tmQb[2], tmC, tmB, tmN, tmE, tmNE;
+  bool use_tma = blocking && !G.no_tma;
+  if (use_tma) {
+    const BtView bv = bt_view();
+    use_tma = make_tmap_2d(&tmXb[0], Xb[0], P2_XW, P2_TY + 4) && make_tmap_2d(&tmXb[1], Xb[1], P2_XW, P2_TY + 4) &&
+              make_tmap_2d(&tmQb[0], Qb[0], P2_XW, P2_TY + 2) && make_tmap_2d(&tmQb[1], Qb[1], P2_XW, P2_TY + 2) &&
+              make_tmap_2d(&tmC, bv.C, P2_XW, P2_TY + 2) && make_tmap_2d(&tmB, B, P2_XW, P2_TY + 2) &&
+              make_tmap_2d(&tmN, bv.N, P2_XW, P2_TY + 3) && make_tmap_2d(&tmE, bv.E, P2_XW, P2_TY + 2) &&
+              make_tmap_2d(&tmNE, bv.NE, P2_XW, P2_TY + 3);
+  }
 #ifndef POP_EMUL
   if (blocking) {
     const int smem2 = (int)(sizeof(double) * P2_SMEM_DOUBLES);
@@ -602,6 +682,10 @@ static int pcsi(double* X, const double* B) {
       a.partials = G.d_partials_big;
       a.do_ew = do_ew; a.do_tripole = do_tp; a.je0 = G.je - 1; a.nxg = G.nxg;
       a.iglob = G.d_iglob; a.jglob = G.d_jglob;
+      a.use_tma = use_tma ? 1 : 0;
+      if (use_tma) {
+        a.tmX = tmXb[cur]; a.tmQ = tmQb[cur]; a.tmC = tmC; a.tmB = tmB; a.tmN = tmN; a.tmE = tmE; a.tmNE = tmNE;
+      }
       const size_t smem2 = sizeof(double) * P2_SMEM_DOUBLES;
       {
         // CUDA-event sample of the pass kernel alone (every 8th pass; the solver timers are otherwise off)
