@@ -265,7 +265,16 @@ extern "C" int pop_init(const pop_config* cfg) {
   cudaDeviceProp prop;
   POP_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   G.sm_count = prop.multiProcessorCount;
-  if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  POP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio_greatest));
+  if (!G.stream2) {
+    // low priority: its CTAs take the slots the main stream's kernels leave free (tails, launch gaps)
+    POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream2, cudaStreamNonBlocking, prio_least));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
+  }
+  G.no_overlap = getenv("POP_B200_NO_OVERLAP") != nullptr && getenv("POP_B200_NO_OVERLAP")[0] == '1';
   POP_REQUIRE(cfg->ns_boundary_type != POP_BNDY_TRIPOLE || cfg->ew_boundary_type == POP_BNDY_CYCLIC,
               "pop_init: a tripole grid needs a cyclic east-west boundary");
   POP_CHECK_CUDA(cudaMalloc(&G.d_iglob, sizeof(int) * G.nxb));
@@ -308,6 +317,7 @@ extern "C" int pop_init(const pop_config* cfg) {
 
 extern "C" int pop_finalize(void) {
   if (G.stream) cudaStreamSynchronize(G.stream);
+  if (G.stream2) cudaStreamSynchronize(G.stream2);
   p2p_teardown();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();

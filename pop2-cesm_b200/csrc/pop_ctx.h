@@ -58,6 +58,11 @@ struct Ctx {
   std::vector<int> i_glob, j_glob;
   int *d_iglob = nullptr, *d_jglob = nullptr;  // device copies
   cudaStream_t stream = nullptr;
+  // side stream: the velocity finish (impvmixu + barotropic-mean removal) of step n runs here, concurrently
+  // with the barotropic solve on `stream` (the solve only needs ZX,ZY of the column kernel)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy
   // rotating time indices (prognostic.F90:63-68)
@@ -251,7 +256,8 @@ int init_barotropic_dev();
 int barotropic_driver_dev();
 // drivers (pop_step.cu)
 int dhdt_dev();
-int baroclinic_driver_dev();
+int baroclinic_driver_dev(bool defer_finish = false);  // defer_finish: the caller launches momentum_finish
+int momentum_finish_new();                            // the deferred velocity finish on UVEL/VVEL(newtime)
 int baroclinic_correct_adjust_dev();
 int step_dev(int ts_type);
 // grid (pop_grid.cu)

@@ -6,6 +6,7 @@
 // The reference loops over blocks and levels on the host and calls one operator per slab; here each
 // driver is a short sequence of fused column kernels plus the halo updates the reference issues at
 // the same points of the step.
+#include <utility>
 #include "pop_dev.cuh"
 
 // ------------------------------------------------------------------ dhdt
@@ -42,7 +43,12 @@ int dhdt_dev() {
 }
 
 // ------------------------------------------------------------------ baroclinic_driver
-int baroclinic_driver_dev() {
+int momentum_finish_new() {
+  return momentum_finish(fld_t("UVEL", G.newtime), fld_t("VVEL", G.newtime), fld_t("UVEL", G.oldtime),
+                         fld_t("VVEL", G.oldtime));
+}
+
+int baroclinic_driver_dev(bool defer_finish) {
   ScopedTimer tm("BAROCLINIC");
   const int o = G.oldtime, c = G.curtime, n_ = G.newtime, mx = G.mixtime;
   const bool pavg = G.cfg.lpressure_avg && G.leapfrogts;
@@ -79,8 +85,11 @@ int baroclinic_driver_dev() {
     io.SMF = fld("SMF"); io.DHU = fld("DHU");
     io.UNEW = fld_t("UVEL", n_); io.VNEW = fld_t("VVEL", n_); io.ZX = fld("ZX"); io.ZY = fld("ZY");
     io.WUK = nullptr;
-    POP_TRY(momentum_column(MO_FULL, 0, io));
-    POP_TRY(momentum_finish(io.UNEW, io.VNEW, io.UOLD, io.VOLD));
+    {
+      ScopedTimer t3("MOMENTUM_COLUMN");
+      POP_TRY(momentum_column(MO_FULL, 0, io));
+    }
+    if (!defer_finish) POP_TRY(momentum_finish(io.UNEW, io.VNEW, io.UOLD, io.VOLD));
   }
   return POP_SUCCESS;
 }
@@ -251,11 +260,24 @@ int step_dev(int ts_type) {
   POP_TRY(set_timestep(ts_type));
   const int km = G.km;
   POP_TRY(dhdt_dev());
-  POP_TRY(baroclinic_driver_dev());
+  const bool overlap = !G.no_overlap;
+  POP_TRY(baroclinic_driver_dev(overlap));
+  if (overlap) {
+    // fork: the velocity finish only touches UVEL/VVEL(new), which nothing reads before the halo updates
+    // below; the barotropic solve and the tracer corrector proceed on the main stream meanwhile
+    POP_CHECK_CUDA(cudaEventRecord(G.ev_fork, G.stream));
+    POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_fork, 0));
+    std::swap(G.stream, G.stream2);
+    const int rc = momentum_finish_new();
+    std::swap(G.stream, G.stream2);
+    POP_TRY(rc);
+    POP_CHECK_CUDA(cudaEventRecord(G.ev_join, G.stream2));
+  }
   POP_TRY(halo_update(fld("ZX"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));  // step_mod.F90:405-417
   POP_TRY(halo_update(fld("ZY"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
   POP_TRY(barotropic_driver_dev());
   POP_TRY(baroclinic_correct_adjust_dev());
+  if (overlap) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));  // join
   const int n_ = G.newtime, c = G.curtime, o = G.oldtime;
   // step_mod.F90:467-560
   POP_TRY(halo_update(fld_t("UBTROP", n_), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
