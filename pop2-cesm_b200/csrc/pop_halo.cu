@@ -178,9 +178,36 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
                 int ghostN, double* __restrict__ toS, double* __restrict__ toN,
                 unsigned long long* flagAtS, unsigned long long* flagAtN, const double* __restrict__ fromS,
                 const double* __restrict__ fromN, volatile unsigned long long* myFlags,
-                unsigned long long seq, unsigned int* counter, int* err) {
+                unsigned long long seq, unsigned int* counter, int* err, int fuse_ew, int fuse_tripole, int nyb,
+                int je0, const int* __restrict__ iglob, const int* __restrict__ jglob) {
   const size_t n = (size_t)nz * 2 * nxg;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // centre scalars: the east-west wrap of the rows this rank owns and the tripole fold only read physical
+  // cells and only write ghost cells, so they ride along before the wait (halo_center_scalar_local)
+  if (fuse_ew || fuse_tripole) {
+    const size_t n_ew = fuse_ew ? (size_t)nz * nyb * 4 : 0;
+    const size_t n_tp = fuse_tripole ? (size_t)nz * 2 * nxb : 0;
+    for (size_t p = t0; p < n_ew + n_tp; p += stride) {
+      if (p < n_ew) {
+        const int c = (int)(p % 4), j = (int)((p / 4) % nyb);
+        const size_t z = p / ((size_t)4 * nyb);
+        if (j < POP_NGHOST || j >= nyb - POP_NGHOST || jglob[j] <= 0) continue;  // ghost rows: see the pull
+        double* row = a + z * n2 + (size_t)j * nxb;
+        if (c < 2) row[c] = row[nxb - 4 + c];
+        else row[nxb - 4 + c] = row[c];
+      } else {
+        const size_t t = p - n_ew;
+        const int i = (int)(t % nxb), r = (int)((t / nxb) % 2);
+        const size_t z = t / ((size_t)2 * nxb);
+        int is = nxg - iglob[i] + 1;
+        if (is == 0) is = nxg;
+        if (is >= 1 && is <= nxg) {
+          double* az = a + z * n2;
+          az[(size_t)(je0 + 1 + r) * nxb + i] = az[(size_t)(je0 - r) * nxb + (POP_NGHOST - 1 + is)];
+        }
+      }
+    }
+  }
   // ---- push
   for (size_t p = t0; p < n; p += stride) {
     const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
@@ -215,8 +242,24 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
     const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
     const size_t z = p / ((size_t)2 * nxg);
     double* az = a + z * n2 + POP_NGHOST + ig;
-    if (fromS) az[(size_t)(ghostS + r) * nxb] = __ldcv(fromS + p);
-    if (fromN) az[(size_t)(ghostN + r) * nxb] = __ldcv(fromN + p);
+    if (fromS) {
+      const double v = __ldcv(fromS + p);
+      double* row = az + (size_t)(ghostS + r) * nxb;
+      row[0] = v;
+      if (fuse_ew) {  // east-west ghost columns of the received row
+        if (ig < POP_NGHOST) row[nxg] = v;
+        else if (ig >= nxg - POP_NGHOST) row[-nxg] = v;
+      }
+    }
+    if (fromN) {
+      const double v = __ldcv(fromN + p);
+      double* row = az + (size_t)(ghostN + r) * nxb;
+      row[0] = v;
+      if (fuse_ew) {
+        if (ig < POP_NGHOST) row[nxg] = v;
+        else if (ig >= nxg - POP_NGHOST) row[-nxg] = v;
+      }
+    }
   }
 }
 #endif
@@ -390,9 +433,13 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
       unsigned grid = ew_grid(msg);
       const unsigned wave = (unsigned)G.sm_count * 2;  // one resident wave (<= 8 CTAs of 256 threads fit per SM)
       if (grid > wave) grid = wave;
+      const bool cs = (loc == POP_LOC_CENTER && kind == POP_KIND_SCALAR);
+      const int f_ew = (cs && ew == POP_BNDY_CYCLIC) ? 1 : 0;
+      const int f_tp = (cs && ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1 && !rows_only) ? 1 : 0;
       POP_LAUNCH(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
                  toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter,
-                 G.p2p_err);
+                 G.p2p_err, f_ew, f_tp, nyb, G.je - 1, G.d_iglob, G.d_jglob);
+      if (cs) return pop_post_launch("halo_update");  // wrap and fold were fused into the exchange
     } else {
     const size_t msg_d = (msg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
     POP_TRY(ensure_halo_buffers(msg_d));
