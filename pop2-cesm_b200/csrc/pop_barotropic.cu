@@ -646,6 +646,18 @@ static int pcsi(double* X, const double* B) {
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
   const bool blocking = !G.no_pcsi_blocking;
+  // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
+  // and a host round trip on every rank, so its verdict is read one check period LATER, when it has long
+  // arrived; X_m of the check is kept in a snapshot, and when a check turns out to have converged the answer
+  // is that snapshot and numIterations is that m -- the same bits as stopping immediately, a few passes late.
+  const bool lagged = (G.nranks > 1) && !(getenv("POP_B200_SYNC_CHECKS") && getenv("POP_B200_SYNC_CHECKS")[0] == '1');
+  double* snap[2] = {W + 4 * G.n2, W + 5 * G.n2};
+  struct { bool valid; int m, slot; } pend = {false, 0, 0};
+  const double* result = nullptr;
+  if (lagged && !G.ev_chk[0]) {
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_chk[0], cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_chk[1], cudaEventDisableTiming));
+  }
   // tensor maps of the staged tiles (X and Q for both buffers); without TMA the kernel stages with cp.async
   PopTmap tmXb[2], tmQb[2], tmC, tmB, tmN, tmE, tmNE;
   bool use_tma = blocking && !G.no_tma;
@@ -719,18 +731,42 @@ static int pcsi(double* X, const double* B) {
       adv = a.advance;
       nblk = nblk1;
     }
-    if (check) {
+    if (check && !lagged) {
       POP_TRY(reduce_finish_n(1, RED_POST_RR, &rr, G.d_partials_big, nblk));
       if (rr < G.convergenceCriterion) {
         G.numIterations = m;
         break;
       }
+    } else if (check) {
+      if (pend.valid) {  // verdict of the previous check
+        POP_CHECK_CUDA(cudaEventSynchronize(G.ev_chk[pend.slot]));
+        rr = G.h_sums[2 + pend.slot];
+        if (rr < G.convergenceCriterion) {
+          G.numIterations = pend.m;
+          result = snap[pend.slot];
+          break;
+        }
+      }
+      const int slot = pend.valid ? (pend.slot ^ 1) : 0;
+      POP_TRY(reduce_finish_n(1, RED_POST_RR, nullptr, G.d_partials_big, nblk));
+      POP_CHECK_CUDA(cudaMemcpyAsync(G.h_sums + 2 + slot, G.d_sums, sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+      POP_CHECK_CUDA(cudaMemcpyAsync(snap[slot], Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+      POP_CHECK_CUDA(cudaEventRecord(G.ev_chk[slot], G.stream));
+      pend.valid = true; pend.m = m; pend.slot = slot;
     }
     if (adv) cur ^= 1;
     m += (adv > 0) ? adv : 1;
   }
-  // the answer is X_m of the last residual evaluation
-  POP_CHECK_CUDA(cudaMemcpyAsync(X, Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  if (lagged && !result && pend.valid) {  // the loop ran out: the last check may still have converged
+    POP_CHECK_CUDA(cudaEventSynchronize(G.ev_chk[pend.slot]));
+    rr = G.h_sums[2 + pend.slot];
+    if (rr < G.convergenceCriterion) {
+      G.numIterations = pend.m;
+      result = snap[pend.slot];
+    }
+  }
+  // the answer is X_m of the converged (or last) residual evaluation
+  POP_CHECK_CUDA(cudaMemcpyAsync(X, result ? result : Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   G.rmsResidual = sqrt(rr * G.residualNorm);
   return pop_post_launch("PCSI");  // PCSI returns silently when not converged (:1828-1830)
 }

@@ -62,6 +62,7 @@ struct Ctx {
   // with the barotropic solve on `stream` (the solve only needs ZX,ZY of the column kernel)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy
