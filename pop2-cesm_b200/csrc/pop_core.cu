@@ -308,6 +308,7 @@ extern "C" int pop_init(const pop_config* cfg) {
   memset(&G.vc, 0, sizeof(G.vc));
   G.launches = 0;
   G.no_tma = getenv("POP_B200_NO_TMA") != nullptr && getenv("POP_B200_NO_TMA")[0] == '1';
+  G.no_fast_tracer = getenv("POP_B200_NO_FAST_TRACER") != nullptr && getenv("POP_B200_NO_FAST_TRACER")[0] == '1';
   G.no_pcsi_blocking = getenv("POP_B200_NO_PCSI_BLOCKING") != nullptr && getenv("POP_B200_NO_PCSI_BLOCKING")[0] == '1';
   G.timers.clear();
   G.grid_set = false;
@@ -500,6 +501,18 @@ bool make_tmap(PopTmap* out, const double* field, int nlev) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+bool make_tmap_box(PopTmap* out, const double* field, int nlev, int boxw, int boxh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc || !field || (G.nxb % 2) != 0 || (boxw % 2) != 0 || boxw > 256 || boxh > 256) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)G.nxb, (cuuint64_t)G.nyb, (cuuint64_t)nlev};
+  cuuint64_t strides[2] = {(cuuint64_t)G.nxb * 8, (cuuint64_t)G.n2 * 8};
+  cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&out->m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)field, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh) {
   // encoded as a one-level 3-d tensor (the form the column kernels use): box boxw x boxh x 1
   EncodeTiledFn enc = get_encode();
@@ -518,6 +531,12 @@ bool make_tmap(PopTmap* out, const double* field, int nlev) {
   if (!field || (G.nxb % 2) != 0) return false;
   out->p = field; out->nx = G.nxb; out->ny = G.nyb; out->nz = nlev;
   out->bw = POP_TW; out->bh = POP_TH;
+  return true;
+}
+bool make_tmap_box(PopTmap* out, const double* field, int nlev, int boxw, int boxh) {
+  if (!field || (G.nxb % 2) != 0 || (boxw % 2) != 0) return false;
+  out->p = field; out->nx = G.nxb; out->ny = G.nyb; out->nz = nlev;
+  out->bw = boxw; out->bh = boxh;
   return true;
 }
 bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh) {

@@ -435,6 +435,261 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
   }
 }
 
+// =====================================================================================
+// Fast path of tracer_update for the production configuration of the leapfrog step: a pair of
+// centred-advection tracers, implicit vertical mixing, TMIX == TOLD != TCUR, even nx_block.
+// Same arithmetic, operation for operation, as tracer_column_kernel<TR_FULL> (which stays the
+// general path and the reference for every other option); what changes is where the operands
+// come from:
+//   * every per-level input, VDC included, arrives by TMA in a 3-deep mbarrier ring, so the level
+//     loop issues no global loads at all (only the two output stores);
+//   * the k-invariant stencil coefficients of a thread's own column, its neighbours' KMT and its
+//     area factor live in registers;
+//   * the flux velocities UTE/VTN and the first del4 Laplacian are built once per tile point per
+//     level (ring-1 tiles) instead of once per use.
+// =====================================================================================
+struct TracerFastArgs {
+  GridView g;
+  const double *STF, *TFW, *DH, *POLD, *PCUR;
+  double* OUT;
+  int n0;                      // first tracer (0-based) of the pair
+  int vdc_lev0[NTC], vdc_kstr;  // VDC level of tracer m at level k: vdc_lev0[m] + k*vdc_kstr
+  int lvariable_hmixt, varthick, predictor;
+  double ah;
+  PopTmap tm_tcur, tm_tmix, tm_u, tm_v, tm_vdc;
+};
+#define TF_NS 3
+#define TF_STAGE (6 * POP_TN + NTC * POP_NTHREADS)  // tc[2], tm[2], u, v halo tiles + vdc[2] column tiles
+#define TF_FIXED 11                                  // ring-1 tiles: dtn dts dte dtw ahf dyu dxu ute vtn d2[2]
+template <bool DEL4>
+__global__ void __launch_bounds__(POP_NTHREADS, 2)
+tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
+  POP_DYN_SMEM(smem_raw);
+  double* s_stage = (double*)smem_raw;  // [TF_NS][TF_STAGE]
+  double* s_dtn = s_stage + TF_NS * TF_STAGE;
+  double* s_dts = s_dtn + POP_T1N;
+  double* s_dte = s_dts + POP_T1N;
+  double* s_dtw = s_dte + POP_T1N;
+  double* s_ahf = s_dtw + POP_T1N;
+  double* s_dyu = s_ahf + POP_T1N;
+  double* s_dxu = s_dyu + POP_T1N;
+  double* s_ute = s_dxu + POP_T1N;
+  double* s_vtn = s_ute + POP_T1N;
+  double* s_d2 = s_vtn + POP_T1N;  // [NTC][T1N]
+  int* s_kmt = (int*)(s_d2 + NTC * POP_T1N);  // halo tile (TIX)
+  uint64_t* s_bar = (uint64_t*)(s_kmt + POP_TN);
+
+  const GridView& g = a.g;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * POP_BX + tx;
+  const int i0 = (g.ib - 1) + blockIdx.x * POP_BX, j0 = (g.jb - 1) + blockIdx.y * POP_BY;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = (i <= g.ie - 1) && (j <= g.je - 1);
+  const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
+  const int km = g.km, nxb = g.nxb, nyb = g.nyb;
+
+  auto issue = [&](int kk) {
+    const int sl = (kk - 1) % TF_NS;
+    double* st = s_stage + (size_t)sl * TF_STAGE;
+    mbar_expect_tx(&s_bar[sl], (uint32_t)(6 * POP_TILE_BYTES + NTC * POP_NTHREADS * 8));
+#pragma unroll
+    for (int m = 0; m < NTC; m++) {
+      const int z = (a.n0 + m) * km + (kk - 1);
+      tma_load_tile(st + m * POP_TN, &a.tm_tcur, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
+      tma_load_tile(st + (NTC + m) * POP_TN, &a.tm_tmix, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
+      tma_load_tile(st + 6 * POP_TN + m * POP_NTHREADS, &a.tm_vdc, i0, j0, a.vdc_lev0[m] + kk * a.vdc_kstr,
+                    &s_bar[sl]);
+    }
+    tma_load_tile(st + 4 * POP_TN, &a.tm_u, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
+    tma_load_tile(st + 5 * POP_TN, &a.tm_v, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
+  };
+  if (tid == 0) {
+    for (int sl = 0; sl < TF_NS; sl++) mbar_init(&s_bar[sl], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int kk = 1; kk <= km && kk <= TF_NS; kk++) issue(kk);
+
+  // ---- k-invariant staging (ring-1 coefficient tiles, KMT halo tile)
+  tile_load_i(s_kmt, g.KMT, i0, j0, nxb, nyb, -2, POP_BX + 1, -2, POP_BY + 1, tid);
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int p = tid + s * POP_NTHREADS;
+    if (p < POP_T1N) {
+      const int jj = p / POP_T1W - 1, ii = p % POP_T1W - 1;
+      const int gi = i0 + ii, gj = j0 + jj;
+      const bool in = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb);
+      const size_t qq = (size_t)gj * nxb + gi;
+      s_dtn[p] = in ? g.DTN[qq] : 0.0;
+      s_dts[p] = in ? g.DTS[qq] : 0.0;
+      s_dte[p] = in ? g.DTE[qq] : 0.0;
+      s_dtw[p] = in ? g.DTW[qq] : 0.0;
+      s_ahf[p] = (in && DEL4 && a.lvariable_hmixt) ? g.AHF[qq] : 0.0;
+      s_dyu[p] = in ? g.DYU[qq] : 0.0;
+      s_dxu[p] = in ? g.DXU[qq] : 0.0;
+    }
+  }
+  const int o1 = TIX1(tx, ty), oT = TIX(tx, ty);
+  __syncthreads();
+  // own column: registers (from the staged tiles, which are zero outside the block, so that threads whose
+  // column lies beyond the physical domain still rebuild D2 of their ghost cell with the right masks)
+  const int kmt = s_kmt[oT];
+  const int k_n = s_kmt[oT + POP_TW], k_s = s_kmt[oT - POP_TW], k_e = s_kmt[oT + 1], k_w = s_kmt[oT - 1];
+  const int kmn = k_n < kmt ? k_n : kmt, kms = k_s < kmt ? k_s : kmt;  // kmX = min(KMT, KMT of that neighbour)
+  const int kme = k_e < kmt ? k_e : kmt, kmw = k_w < kmt ? k_w : kmt;
+  const double o_dtn = s_dtn[o1], o_dts = s_dts[o1], o_dte = s_dte[o1], o_dtw = s_dtw[o1], o_ahf = s_ahf[o1];
+  const double tarea_r = active ? g.TAREA_R[q] : 0.0;
+  // per-level intermediates of level kk from its stage: UTE, VTN (advection.F90:2031-2060) and, for
+  // del4, D2 = AHF*L(TMIX) (hmix_del4.F90:1025-1046) on the ring-1 tile
+  auto pre = [&](int kk, const double* st) {
+    const double* su = st + 4 * POP_TN;
+    const double* sv = st + 5 * POP_TN;
+    // own point
+    s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] + su[oT - POP_TW] * s_dyu[o1 - POP_T1W]);
+    s_vtn[o1] = 0.5 * (sv[oT] * s_dxu[o1] + sv[oT - 1] * s_dxu[o1 - 1]);
+    // the west column of UTE and the south row of VTN
+    if (tid < POP_BY) {
+      const int t1 = TIX1(-1, tid), tt = TIX(-1, tid);
+      s_ute[t1] = 0.5 * (su[tt] * s_dyu[t1] + su[tt - POP_TW] * s_dyu[t1 - POP_T1W]);
+    } else if (tid >= 32 && tid < 32 + POP_BX) {
+      const int t1 = TIX1(tid - 32, -1), tt = TIX(tid - 32, -1);
+      s_vtn[t1] = 0.5 * (sv[tt] * s_dxu[t1] + sv[tt - 1] * s_dxu[t1 - 1]);
+    }
+    if (DEL4) {
+      {  // own point: coefficients from registers
+        const double cn = (kk <= kmn) ? o_dtn : 0.0, cs = (kk <= kms) ? o_dts : 0.0;
+        const double ce = (kk <= kme) ? o_dte : 0.0, cw = (kk <= kmw) ? o_dtw : 0.0;
+        const double cc = -(cn + cs + ce + cw);
+#pragma unroll
+        for (int m = 0; m < NTC; m++) {
+          const double* t = st + (NTC + m) * POP_TN + oT;
+          const double v = cc * t[0] + cn * t[POP_TW] + cs * t[-POP_TW] + ce * t[1] + cw * t[-1];
+          s_d2[m * POP_T1N + o1] = a.lvariable_hmixt ? o_ahf * v : v;
+        }
+      }
+      constexpr int NRING = 2 * POP_T1W + 2 * POP_BY;  // the ring around the CTA's columns
+      if (tid < NRING) {
+        int ii, jj;
+        if (tid < 2 * POP_T1W) { ii = tid % POP_T1W - 1; jj = (tid < POP_T1W) ? -1 : POP_BY; }
+        else { const int t = tid - 2 * POP_T1W; ii = (t < POP_BY) ? -1 : POP_BX; jj = t % POP_BY; }
+        const int t1 = TIX1(ii, jj), tt = TIX(ii, jj);
+        const int kc = s_kmt[tt];
+        const double cn = (kk <= s_kmt[tt + POP_TW] && kk <= kc) ? s_dtn[t1] : 0.0;
+        const double cs = (kk <= s_kmt[tt - POP_TW] && kk <= kc) ? s_dts[t1] : 0.0;
+        const double ce = (kk <= s_kmt[tt + 1] && kk <= kc) ? s_dte[t1] : 0.0;
+        const double cw = (kk <= s_kmt[tt - 1] && kk <= kc) ? s_dtw[t1] : 0.0;
+        const double cc = -(cn + cs + ce + cw);
+#pragma unroll
+        for (int m = 0; m < NTC; m++) {
+          const double* t = st + (NTC + m) * POP_TN + tt;
+          const double v = cc * t[0] + cn * t[POP_TW] + cs * t[-POP_TW] + ce * t[1] + cw * t[-1];
+          s_d2[m * POP_T1N + t1] = a.lvariable_hmixt ? s_ahf[t1] * v : v;
+        }
+      }
+    }
+  };
+  // ---- carried state
+  double wtk = 0.0, tc_m[NTC], told_c[NTC], vtf[NTC];
+  mbar_wait(&s_bar[0], 0u);
+  __syncthreads();  // invariants staged
+#pragma unroll
+  for (int m = 0; m < NTC; m++) {
+    tc_m[m] = 0.0;
+    vtf[m] = 0.0;
+    told_c[m] = s_stage[(NTC + m) * POP_TN + oT];  // TOLD (== TMIX) at level 1
+  }
+  if (active) wtk = a.DH[q];
+  pre(1, s_stage);
+  __syncthreads();
+
+  for (int k = 1; k <= km; k++) {
+    const int slot = (k - 1) % TF_NS;
+    const double* st = s_stage + (size_t)slot * TF_STAGE;
+    const bool have_next = (k < km);
+    const int nslot = k % TF_NS;
+    const double* nst = s_stage + (size_t)nslot * TF_STAGE;
+    if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)((k / TF_NS) & 1));
+    if (active) {
+      const double ute = s_ute[o1], utw = s_ute[o1 - 1], vtn = s_vtn[o1], vts = s_vtn[o1 - POP_T1W];
+      double wtkb = 0.0;
+      if (k < km) {
+        const double FC = (vtn - vts + ute - utw) * tarea_r;
+        wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
+      }
+      const double cn = (k <= kmn) ? o_dtn : 0.0, cs = (k <= kms) ? o_dts : 0.0;
+      const double ce = (k <= kme) ? o_dte : 0.0, cw = (k <= kmw) ? o_dtw : 0.0;
+      const double cc = -(cn + cs + ce + cw);
+#pragma unroll
+      for (int m = 0; m < NTC; m++) {
+        const int n = a.n0 + m;
+        const size_t lev = ((size_t)n * km + (k - 1)) * n2 + q;
+        // ---- horizontal mixing
+        double hd;
+        if (DEL4) {
+          const double* d = s_d2 + m * POP_T1N + o1;
+          hd = a.ah * (cc * d[0] + cn * d[POP_T1W] + cs * d[-POP_T1W] + ce * d[1] + cw * d[-1]);
+        } else {
+          const double* t = st + (NTC + m) * POP_TN + oT;
+          hd = a.ah * (cc * t[0] + cn * t[POP_TW] + cs * t[-POP_TW] + ce * t[1] + cw * t[-1]);
+        }
+        // ---- centred advection: advection.F90:2243-2301
+        const double* tc = st + m * POP_TN + oT;
+        const double T = tc[0];
+        const double Tp = (k < km) ? nst[m * POP_TN + oT] : 0.0;
+        double L = 0.5 *
+                   ((vtn - vts + ute - utw) * T + vtn * tc[POP_TW] - vts * tc[-POP_TW] + ute * tc[1] - utw * tc[-1]) *
+                   tarea_r;
+        if (k == 1) {
+          if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
+        } else {
+          L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+        }
+        if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+        tc_m[m] = T;
+        // ---- vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
+        const double vdc = st[6 * POP_TN + m * POP_NTHREADS + tid];
+        const double told_p = (k < km) ? nst[(NTC + m) * POP_TN + oT] : told_c[m];
+        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
+        const double VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
+        const double vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        vtf[m] = VTFB;
+        told_c[m] = told_p;
+        // ---- tracer_update: baroclinic.F90:1993-2300 (implicit vertical mixing)
+        double FT = 0.0 + hd;
+        FT = FT - L;
+        FT = FT + vd;
+        if (k == 1 && a.varthick) FT = FT + c_vc.dzr[1] * a.TFW[(size_t)n * n2 + q];
+        FT = FT + 0.0;
+        double* out = a.OUT + lev;
+        if (a.predictor && k == 1 && n < 2) {
+          if (kmt > 0) *out = c_vc.c2dtt[1] * FT - 2.0 * T * (a.PCUR[q] - a.POLD[q]) / (POP_GRAV * c_vc.dz[1]);
+        } else {
+          *out = (k <= kmt) ? c_vc.c2dtt[k] * FT : 0.0;
+        }
+      }
+      wtk = wtkb;
+    }
+    __syncthreads();  // every thread is done with ring slot k and with the intermediates of level k
+    if (tid == 0 && k + TF_NS <= km) issue(k + TF_NS);
+    if (have_next) {
+      pre(k + 1, nst);
+      __syncthreads();
+    }
+  }
+}
+
+static int launch_tracer_fast(const TracerFastArgs& a, bool del4) {
+  void (*kfn)(const TracerFastArgs) = del4 ? tracer_fast_kernel<true> : tracer_fast_kernel<false>;
+  const size_t smem = sizeof(double) * ((size_t)TF_NS * TF_STAGE + (size_t)TF_FIXED * POP_T1N) + sizeof(int) * POP_TN +
+                      8 * TF_NS;
+#ifndef POP_EMUL
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+  POP_LAUNCH(kfn, col_grid(G.nxg, G.ny_local), col_block(), smem, a);
+  return POP_SUCCESS;
+}
+
 static size_t tracer_smem_bytes(bool tma) {
   const int ns = tma ? TR_NS : 1;
   return sizeof(double) * POP_TN * (ns * (2 * NTC + 2) + 7 + (tma ? 2 : 1) * NTC) + sizeof(int) * POP_TN + 8 * TR_NS;
@@ -495,6 +750,28 @@ int tracer_column(int mode, int k, const TracerIO& io) {
     }
     switch (mode) {
       case TR_FULL: {
+        // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
+        const bool fast_ok = !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+                             a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
+        if (fast_ok) {
+          TracerFastArgs f;
+          memset(&f, 0, sizeof(f));
+          f.g = a.g; f.STF = a.STF; f.TFW = a.TFW; f.DH = a.DH; f.POLD = a.POLD; f.PCUR = a.PCUR; f.OUT = a.OUT;
+          f.n0 = n0; f.lvariable_hmixt = a.lvariable_hmixt; f.varthick = a.varthick; f.predictor = a.predictor;
+          f.ah = a.ah;
+          f.vdc_kstr = (G.vdc_nk == 1) ? 0 : 1;
+          for (int m = 0; m < NTC; m++) {
+            const int n = n0 + m;
+            const int mt2 = (n + 1 < G.vdc_nd) ? n + 1 : G.vdc_nd;
+            f.vdc_lev0[m] = (mt2 - 1) * G.vdc_nk + ((G.vdc_nk == 1) ? 0 : -G.vdc_k0);
+          }
+          if (make_tmap(&f.tm_tcur, a.TCUR, G.km * G.nt) && make_tmap(&f.tm_tmix, a.TMIX, G.km * G.nt) &&
+              make_tmap(&f.tm_u, a.UCUR, G.km) && make_tmap(&f.tm_v, a.VCUR, G.km) &&
+              make_tmap_box(&f.tm_vdc, a.g.VDC, G.vdc_nk * G.vdc_nd, POP_BX, POP_BY)) {
+            POP_TRY(launch_tracer_fast(f, del4));
+            break;
+          }
+        }
         const bool tma = !G.no_tma && make_tmap(&a.tm_tcur, a.TCUR, G.km * G.nt) &&
                          make_tmap(&a.tm_tmix, a.TMIX, G.km * G.nt) && make_tmap(&a.tm_u, a.UCUR, G.km) &&
                          make_tmap(&a.tm_v, a.VCUR, G.km);
