@@ -396,7 +396,7 @@ pcsi_iter_kernel(const PcsiArgs a) {
 // ghost rows owned by a neighbouring rank hold that rank's bits two cells deep.  One 2-level halo
 // update of (X,Q) follows every pass (P > 1: one strip exchange per two iterations).
 #define P2_TX 64
-#define P2_TY 12
+#define P2_TY 10
 #define P2_NT 256
 // every staged tile starts two cells west of the tile (an even column: TMA needs the first element of a
 // box on a 16-byte boundary) and is P2_XW wide; X, N, NE start two rows south, the others one row south
@@ -427,7 +427,7 @@ __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__
   }
 }
 template <bool SUM>
-__global__ void __launch_bounds__(P2_NT, 3)
+__global__ void __launch_bounds__(P2_NT, 4)
 pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   POP_DYN_SMEM(smem_raw);
   double* sX = (double*)smem_raw;  // X_m              rows j0-2 .. j0+TY+1
@@ -445,6 +445,16 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   const int tid = threadIdx.x;
   // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA):
   // seven TMA box copies issued by one thread (no per-element instructions), or per-thread cp.async
+  // check passes: the mask values of this thread's cells are requested before the wait for the tiles
+  double msk[(P2_TY + 2 + 3) / 4 + 1];
+  if (SUM) {
+    const int r0p = -1 + ((tid / P2_TX) * (P2_TY + 2)) / (P2_NT / P2_TX);
+#pragma unroll
+    for (int t = 0; t < (P2_TY + 2 + 3) / 4 + 1; t++) {
+      const int gjm = j0 + r0p + t, gim = i0 + tid % P2_TX;
+      msk[t] = (r0p + t >= 0 && r0p + t < P2_TY && bt_physical(v, gim, gjm)) ? ldg(v.mask + (size_t)gjm * nxb + gim) : 0.0;
+    }
+  }
   if (a.use_tma) {
     if (tid == 0) {
       mbar_init(s_bar, 1);
@@ -532,8 +542,7 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
           const double ax = c * xc1 + n * xp1 + n_s * xm1 + e * xc2 + ew * xc0 + ne * xp2 + ne_s * xm2 + nw * xp0 +
                             ne_sw * xm0;
           const double r = sB[o1] - ax;
-          if (SUM && jj >= 0 && jj < P2_TY && bt_physical(v, gi, gj))
-            acc = dd_add_d(acc, (r * r) * ldg(v.mask + (size_t)gj * nxb + gi));
+          if (SUM && jj >= 0 && jj < P2_TY && bt_physical(v, gi, gj)) acc = dd_add_d(acc, (r * r) * msk[jj - r0]);
           const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
           qv = a.om1 * (r * a0r) + a.c11 * sQ[o1];
           x1 = xc1 + qv;
