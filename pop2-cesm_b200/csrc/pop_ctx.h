@@ -30,6 +30,9 @@ struct VertConst {
   double c2dtt[POP_KMAX + 2], afac_t[POP_KMAX + 2], afac_u[POP_KMAX + 2];
   double pressz[POP_KMAX + 2], tmin[POP_KMAX + 2], tmax[POP_KMAX + 2], smin[POP_KMAX + 2];
   double smax[POP_KMAX + 2], bouss[POP_KMAX + 2];
+  // pressure-dependent MWJF coefficient sets of each level (state_mod.F90:433-452), evaluated once on the host
+  double eos_n0t0[POP_KMAX + 2], eos_n0t2[POP_KMAX + 2], eos_n1t0[POP_KMAX + 2];
+  double eos_d0t0[POP_KMAX + 2], eos_d0t1[POP_KMAX + 2], eos_d0t3[POP_KMAX + 2];
   double hfac_t[POP_KMAX + 2], hfac_u[POP_KMAX + 2];  // dz(k)/c2dtt(k), dz(k)/c2dtu (vertical_mix.F90:1240,1755)
   double talfzp[POP_KMAX + 2], tbetzp[POP_KMAX + 2], tgamzp[POP_KMAX + 2];
   double talfzm[POP_KMAX + 2], tbetzm[POP_KMAX + 2], tdelzm[POP_KMAX + 2];

@@ -11,7 +11,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
-#include "pop_dev.cuh"
+#include "pop_state.cuh"
 
 namespace {
 typedef std::vector<double> HV;
@@ -204,6 +204,8 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   // ---- state tables (state_mod.F90:1040-1063) and Boussinesq correction (pressure_grad.F90:168-175)
   for (int k = 1; k <= km; k++) {
     vc.pressz[k] = pressure(vc.zt[k] * 0.01);
+    mwjf_level_coefficients(vc.pressz[k], &vc.eos_n0t0[k], &vc.eos_n0t2[k], &vc.eos_n1t0[k], &vc.eos_d0t0[k],
+                            &vc.eos_d0t1[k], &vc.eos_d0t3[k]);
     if (c.state_itype == POP_STATE_MWJF) { vc.tmin[k] = -2.0; vc.tmax[k] = 999.0; vc.smin[k] = 0.0; vc.smax[k] = 0.999; }
     else { vc.tmin[k] = -2.0; vc.tmax[k] = 40.0; vc.smin[k] = 0.0; vc.smax[k] = 0.042; }
     vc.bouss[k] = c.lbouss_correct

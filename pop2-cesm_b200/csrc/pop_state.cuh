@@ -27,6 +27,18 @@ struct StateOpt {
   int itype, range;
 };
 
+// host: the pressure-dependent coefficient sets of level kk, p = 10*pressz(kk) (state_mod.F90:420-452)
+inline void mwjf_level_coefficients(double pressz, double* n0t0, double* n0t2, double* n1t0, double* d0t0,
+                                    double* d0t1, double* d0t3) {
+  const double p = 10.0 * pressz;
+  *n0t0 = mwjfnp0s0t0 + p * (mwjfnp1s0t0 + p * mwjfnp2s0t0);
+  *n0t2 = mwjfnp0s0t2 + p * (mwjfnp1s0t2 + p * mwjfnp2s0t2);
+  *n1t0 = mwjfnp0s1t0 + p * mwjfnp1s1t0;
+  *d0t0 = mwjfdp0s0t0 + p * mwjfdp1s0t0;
+  *d0t1 = mwjfdp0s0t1 + (p * p * p) * mwjfdp3s0t1;
+  *d0t3 = mwjfdp0s0t3 + (p * p) * mwjfdp2s0t3;
+}
+
 // one cell of `state` at pressure level kk; any output pointer may be null
 __device__ __forceinline__ void state_cell(StateOpt o, int kk, double T, double S, double* rho,
                                            double* rhofull, double* drhodt, double* drhods) {
@@ -37,18 +49,19 @@ __device__ __forceinline__ void state_cell(StateOpt o, int kk, double T, double 
     if (drhods) *drhods = bet;
     return;
   }
-  const double p = 10.0 * c_vc.pressz[kk];
-  const double n0t0 = mwjfnp0s0t0 + p * (mwjfnp1s0t0 + p * mwjfnp2s0t0);
+  // the six pressure-dependent sets come from per-level tables (mwjf_level_coefficients below, same
+  // expressions evaluated once per level on the host)
+  const double n0t0 = c_vc.eos_n0t0[kk];
   const double n0t1 = mwjfnp0s0t1;
-  const double n0t2 = mwjfnp0s0t2 + p * (mwjfnp1s0t2 + p * mwjfnp2s0t2);
+  const double n0t2 = c_vc.eos_n0t2[kk];
   const double n0t3 = mwjfnp0s0t3;
-  const double n1t0 = mwjfnp0s1t0 + p * mwjfnp1s1t0;
+  const double n1t0 = c_vc.eos_n1t0[kk];
   const double n1t1 = mwjfnp0s1t1;
   const double n2t0 = mwjfnp0s2t0;
-  const double d0t0 = mwjfdp0s0t0 + p * mwjfdp1s0t0;
-  const double d0t1 = mwjfdp0s0t1 + (p * p * p) * mwjfdp3s0t1;
+  const double d0t0 = c_vc.eos_d0t0[kk];
+  const double d0t1 = c_vc.eos_d0t1[kk];
   const double d0t2 = mwjfdp0s0t2;
-  const double d0t3 = mwjfdp0s0t3 + (p * p) * mwjfdp2s0t3;
+  const double d0t3 = c_vc.eos_d0t3[kk];
   const double d0t4 = mwjfdp0s0t4;
   const double d1t0 = mwjfdp0s1t0, d1t1 = mwjfdp0s1t1, d1t3 = mwjfdp0s1t3;
   const double dqt0 = mwjfdp0sqt0, dqt2 = mwjfdp0sqt2;
