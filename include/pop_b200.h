@@ -168,7 +168,7 @@ int pop_impvmixt(double* TNEW, const double* TOLD, const double* PSFC, int nfirs
 int pop_impvmixt_correct(double* TNEW, const double* PSFC, const double* RHS, int nfirst,
                          int nlast, const pop_block* blk);
 int pop_impvmixu(double* UNEW, double* VNEW, const pop_block* blk);
-/* vertical_mix.F90:518 (const / rich; GIVEN is a no-op) */
+/* vertical_mix.F90:518: const (vmix_const.F90:144), rich (vmix_rich.F90:179, full cells); GIVEN is a no-op */
 int pop_vmix_coeffs(int k, const double* TMIX, const double* UMIX, const double* VMIX,
                     const double* RHOMIX, const pop_block* blk);
 /* state_mod.F90:258: optional outputs are nullable */

@@ -295,8 +295,11 @@ extern "C" int pop_init(const pop_config* cfg) {
               "pop_init: hmix_tracer_itype=%d not supported (del2, del4)", cfg->hmix_tracer_itype);
   POP_REQUIRE(cfg->hmix_momentum_itype == POP_HMIX_DEL2 || cfg->hmix_momentum_itype == POP_HMIX_DEL4,
               "pop_init: hmix_momentum_itype=%d not supported", cfg->hmix_momentum_itype);
-  POP_REQUIRE(cfg->vmix_itype == POP_VMIX_CONST || cfg->vmix_itype == POP_VMIX_GIVEN,
-              "pop_init: vmix_itype=%d is not implemented (const, given)", cfg->vmix_itype);
+  POP_REQUIRE(cfg->vmix_itype == POP_VMIX_CONST || cfg->vmix_itype == POP_VMIX_GIVEN ||
+                  cfg->vmix_itype == POP_VMIX_RICH,
+              "pop_init: vmix_itype=%d is not implemented (const, rich, given)", cfg->vmix_itype);
+  POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH || cfg->implicit_vertical_mix,
+              "pop_init: vmix_itype=rich needs implicit_vertical_mix (the coefficients of all levels are built before the column kernels)");
   POP_TRY(alloc_all_fields());
   POP_TRY(reduce_alloc());
   POP_TRY(p2p_setup());

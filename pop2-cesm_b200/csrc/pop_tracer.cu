@@ -963,6 +963,75 @@ __global__ void vmix_const_kernel(StateOpt o, const double* __restrict__ TMIX, c
   VVC[c] = vvc;
 }
 
+// Richardson-number dependent coefficients (vmix_rich.F90:179-414, full cells).  The reference walks k
+// and carries UTK/VTK (velocities averaged to T points) from the previous level; here every (point,
+// level) is independent: both levels are averaged on the fly (same four-point weights AT0=ATS=ATW=ATSW
+// = 1/4, grid.F90:2908-2928, zero on the first row and column like ugrid_to_tgrid, grid.F90:3297-3355).
+struct RichArgs {
+  StateOpt o;
+  const double *TMIX, *UMIX, *VMIX, *RHOMIX;
+  const int *KMT, *KMU;
+  const double *AU0, *AUN, *AUE, *AUNE;
+  double *VDC, *VVC, *RICH;
+  int nxb, nyb, km, k0;
+  size_t n2;
+  double bckgrnd_vdc, bckgrnd_vvc, rich_mix, convect_diff, convect_visc;
+  int convection_diff;
+};
+__device__ __forceinline__ double u2t(const double* __restrict__ AU, int i, int j, int nxb) {
+  if (i == 0 || j == 0) return 0.0;
+  const size_t q = (size_t)j * nxb + i;
+  return 0.25 * AU[q] + 0.25 * AU[q - nxb] + 0.25 * AU[q - 1] + 0.25 * AU[q - nxb - 1];
+}
+__global__ void vmix_rich_t_kernel(RichArgs a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = a.k0 + blockIdx.y;
+  if (q >= a.n2) return;
+  const int i = (int)(q % a.nxb), j = (int)(q / a.nxb);
+  const int kp1 = (k + 1 < a.km) ? k + 1 : a.km;
+  const size_t c = (size_t)(k - 1) * a.n2, cp = (size_t)(kp1 - 1) * a.n2;
+  const double critnu = a.convection_diff ? a.convect_diff : (0.25 * c_vc.dz[k] * c_vc.dzw[k]) / c_vc.c2dtt[k];
+  double rich = 0.0, vdc = 0.0;
+  if (k < a.KMT[q]) {
+    const double utk = u2t(a.UMIX + c, i, j, a.nxb), utkp = u2t(a.UMIX + cp, i, j, a.nxb);
+    const double vtk = u2t(a.VMIX + c, i, j, a.nxb), vtkp = u2t(a.VMIX + cp, i, j, a.nxb);
+    double rhok;
+    state_cell(a.o, kp1, a.TMIX[c + q], a.TMIX[(size_t)a.km * a.n2 + c + q], &rhok, nullptr, nullptr, nullptr);
+    rich = -POP_GRAV * c_vc.dzw[k] * (rhok - a.RHOMIX[cp + q]) /
+           ((utk - utkp) * (utk - utkp) + (vtk - vtkp) * (vtk - vtkp) + 1.0e-10);
+    const double d = 1.0 + 5.0 * rich;
+    const double v = a.bckgrnd_vdc + (a.bckgrnd_vvc + a.rich_mix / (d * d)) / d;
+    vdc = (critnu < v) ? critnu : v;
+  }
+  if (rich < 0.0) vdc = critnu;
+  a.RICH[c + q] = rich;
+  a.VDC[c + q] = vdc;
+}
+__global__ void vmix_rich_u_kernel(RichArgs a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = a.k0 + blockIdx.y;
+  if (q >= a.n2) return;
+  const int i = (int)(q % a.nxb), j = (int)(q / a.nxb);
+  const size_t c = (size_t)(k - 1) * a.n2;
+  double critnu = a.convection_diff ? a.convect_diff : (0.25 * c_vc.dz[k] * c_vc.dzw[k]) / c_vc.c2dtt[k];
+  if (a.convection_diff) critnu = a.convect_visc;
+  double richu = 0.0;  // tgrid_to_ugrid: zero on the last row and column (grid.F90:3403-3415)
+  if (i < a.nxb - 1 && j < a.nyb - 1) {
+    const double* R = a.RICH + c;
+    richu = a.AU0[q] * R[q] + a.AUN[q] * R[q + a.nxb] + a.AUE[q] * R[q + 1] + a.AUNE[q] * R[q + a.nxb + 1];
+  }
+  double vvc = 0.0;
+  if (k < a.KMU[q]) {
+    const double d = 1.0 + 5.0 * richu;
+    const double v = a.bckgrnd_vvc + a.rich_mix / (d * d);
+    vvc = (critnu < v) ? critnu : v;
+  } else {
+    richu = 0.0;
+  }
+  if (richu < 0.0) vvc = critnu;
+  a.VVC[c + q] = vvc;
+}
+
 int vmix_coeffs_dev(int k0, int k1, const double* TMIX, const double* UMIX, const double* VMIX,
                     const double* RHOMIX) {
   (void)UMIX; (void)VMIX; (void)RHOMIX;
@@ -978,6 +1047,23 @@ int vmix_coeffs_dev(int k0, int k1, const double* TMIX, const double* UMIX, cons
     dim3 grid(ew_grid(G.n2), (unsigned)(k1 - k0 + 1), 1);
     POP_LAUNCH(vmix_const_kernel, grid, POP_EW_THREADS, 0, o, TMIX, fldi("KMT"), fld("VDC"), fld("VVC"),
                G.n2, G.km, k0, c.const_vdc, c.const_vvc, c.convect_diff, vvconv);
+    return pop_post_launch("vmix_coeffs");
+  }
+  if (c.vmix_itype == POP_VMIX_RICH) {  // vmix_rich.F90:179-414 (full cells)
+    POP_REQUIRE(G.vdc_nk == G.km && G.vvc_nk == G.km, "vmix_coeffs(rich) needs implicit vertical mixing");
+    POP_REQUIRE(k0 >= 1 && k1 <= G.km && k0 <= k1, "vmix_coeffs: bad level range %d..%d", k0, k1);
+    ScopedTimer tm("VMIX_COEFFICIENTS_RICH");
+    StateOpt o{c.state_itype, c.state_range_iopt};
+    RichArgs a;
+    a.o = o; a.TMIX = TMIX; a.UMIX = UMIX; a.VMIX = VMIX; a.RHOMIX = RHOMIX; a.KMT = fldi("KMT"); a.KMU = fldi("KMU");
+    a.AU0 = fld("AU0"); a.AUN = fld("AUN"); a.AUE = fld("AUE"); a.AUNE = fld("AUNE");
+    a.VDC = fld("VDC"); a.VVC = fld("VVC"); a.RICH = fld("WORK3D_E");
+    a.nxb = G.nxb; a.nyb = G.nyb; a.km = G.km; a.k0 = k0; a.n2 = G.n2;
+    a.bckgrnd_vdc = c.bckgrnd_vdc; a.bckgrnd_vvc = c.bckgrnd_vvc; a.rich_mix = c.rich_mix;
+    a.convection_diff = c.convection_diff; a.convect_diff = c.convect_diff; a.convect_visc = c.convect_visc;
+    dim3 grid(ew_grid(G.n2), (unsigned)(k1 - k0 + 1), 1);
+    POP_LAUNCH(vmix_rich_t_kernel, grid, POP_EW_THREADS, 0, a);
+    POP_LAUNCH(vmix_rich_u_kernel, grid, POP_EW_THREADS, 0, a);
     return pop_post_launch("vmix_coeffs");
   }
   POP_REQUIRE(false, "vmix_coeffs: vmix_itype=%d is not implemented", c.vmix_itype);

@@ -41,6 +41,11 @@ CASES = {
     # gx flavour: upwind3 advection, pcg, extra passive tracer, cyclic north-south, no convective diffusion
     "upwind3_pcg": dict(nx=40, ny=32, km=7, nt=3, seed=23, ns=c.BNDY_CYCLIC, tadvect=c.TADVECT_UPWIND3,
                         solver_choice=c.SOLVER_PCG, convection_diff=0),
+    # config 1 flavour (input_templates/test_pop2_in): Richardson-number vertical mixing, pcg, del2, centred advection
+    "rich_pcg": dict(nx=48, ny=32, km=8, seed=25, vmix_itype=c.VMIX_RICH, solver_choice=c.SOLVER_PCG,
+                     convergence_criterion=1e-12),
+    "rich_noconv_chrongear": dict(nx=40, ny=32, km=7, seed=26, vmix_itype=c.VMIX_RICH, convection_diff=0,
+                                  convergence_criterion=1e-12),
     # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
     "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
                              lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),
@@ -180,3 +185,22 @@ def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypa
         assert o.step(ts) == 0
     assert o.solver_diag()[0] == res["blocked"][0][-1]
     assert relerr(res["blocked"][1], oracle_global(o, "PSURF", c.TIME_CUR)) <= 2.0e-12
+
+
+def test_config1_shape_test_grid_options():
+    """BASELINE.json config 1: the reference's own CPU-runnable case (input_templates/test_pop2_in and
+    test_domain_size.F90: 192 x 128 x 20, 16 x 16 blocks, cyclic/closed, pcg + diagonal preconditioner,
+    Richardson-number vertical mixing, centred advection, del2, MWJF 'enforce', pressure averaging,
+    Boussinesq correction) -- the oracle runs it in the reference's multi-block layout, the library as
+    one strip; synthetic bathymetry and fields of the same shape (no input files exist in the image)."""
+    cs = make_case(192, 128, 20, seed=111, vmix_itype=c.VMIX_RICH, solver_choice=c.SOLVER_PCG,
+                   convergence_criterion=1e-12, dtt=3600.0)
+    o, p = load_oracle(cs, block_size=(16, 16)), load_pop(cs)
+    try:
+        for i, ts in enumerate([c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG]):
+            assert o.step(ts) == 0
+            p.step(ts)
+            assert o.solver_diag()[0] == p.solvers_get_diagnostics()[0]
+        compare(o, p, 3.0e-12, "config 1 shape")
+    finally:
+        p.finalize()
