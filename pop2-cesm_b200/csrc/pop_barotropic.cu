@@ -70,7 +70,7 @@ bt_stencil_kernel(BtView v, double* __restrict__ V0, const double* __restrict__ 
   const size_t n = (size_t)v.nxb * v.nyb;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
        q += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(q % v.nxb), j = (int)(q / v.nxb);
+    const int j = (int)((unsigned)q / (unsigned)v.nxb), i = (int)((unsigned)q - (unsigned)j * (unsigned)v.nxb);  // n < 2^32
     const bool phys = bt_physical(v, i, j);
     const double m = phys ? v.mask[q] : 0.0;
     if (OP == BT_APPLY) {

@@ -14,8 +14,8 @@
 #endif
 
 int reduce_alloc() {
-  G.red_blocks = 2 * G.sm_count;
-  if (G.red_blocks > 1024) G.red_blocks = 1024;
+  G.red_blocks = 8 * G.sm_count;  // fixed grid of every reduction: 8 CTAs of 256 threads per SM (full occupancy)
+  if (G.red_blocks > 2048) G.red_blocks = 2048;
   cudaFree(G.d_partials);
   cudaFree(G.d_sums);
   cudaFree(G.d_local);
