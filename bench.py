@@ -377,7 +377,8 @@ def run_pop(args):
         passes = sum(iters) / 2.0
         kern["PCSI_PASS2_KERNEL"] = {"ms_per_launch": per, "calls": tm["PCSI_PASS2_KERNEL"][1], "launches_per_run": passes,
                                      "GBs": 72.0 * pts / (per * 1e-3) / 1e9, "share_of_step": per * passes / ms,
-                                     "note": "every 16th launch timed; share = sampled mean x launches"}
+                                     "note": "every 16th launch timed, uniformly over the solve (early passes share the GPU with "
+                                             "the velocity-finish kernel on the side stream); share = sampled mean x launches"}
     traffic = ncu_traffic()
     for n in kern:
         unit = pts if n == "PCSI_PASS2_KERNEL" else local_cells

@@ -686,7 +686,7 @@ static int pcsi(double* X, const double* B) {
   }
 #endif
   int cur = 0;  // (X_m, Q_m) live in (Xb[cur], Qb[cur])
-  int m = 1;
+  int m = 1, npass = 0;
   while (m <= maxIt) {
     const bool check = (m % freq == 0) && (m >= start);
     const bool next_is_check = ((m + 1) % freq == 0) && (m + 1 >= start);
@@ -709,8 +709,9 @@ static int pcsi(double* X, const double* B) {
       }
       const size_t smem2 = sizeof(double) * P2_SMEM_DOUBLES;
       {
-        // CUDA-event sample of the pass kernel alone (every 8th pass; the solver timers are otherwise off)
-        const bool sample = (!check && (m % 16) == 1);
+        // CUDA-event sample of the pass kernel alone (every 16th pass, uniformly over the solve; the solver
+        // timers are otherwise off)
+        const bool sample = (!check && (npass++ % 16) == 8);
         if (sample) G.timer_suppress--;
         {
           ScopedTimer tk("PCSI_PASS2_KERNEL");
