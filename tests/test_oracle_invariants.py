@@ -1,0 +1,156 @@
+"""CPU: invariants that pin the parts of the oracle for which the reference tree holds no golden data
+(SURVEY 8c): symmetry and negative definiteness of the barotropic operator, the residual of the
+tridiagonal solves against an independently assembled matrix, the solver's reported residual against the
+convergence criterion, constant preservation of the advection operator (flux form + comp_flux_vel), and the
+biharmonic operator as two passes of the harmonic one."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from parity import *  # noqa: F401,F403
+
+ci, vp = C.c_int, C.c_void_p
+GRAV = 980.6
+
+
+def _case(**kw):
+    base = dict(seed=5)
+    base.update(kw)
+    cs = make_case(40, 32, 7, **base)
+    return cs, load_oracle(cs)
+
+
+def test_btrop_operator_is_symmetric_and_negative_definite():
+    cs, o = _case(ns=c.BNDY_CYCLIC)
+    o.set_timestep(c.TS_LEAPFROG)
+    osig(o.L, "o_solvers_prep", [], ci)()
+    f_b = osig(o.L, "o_btrop_operator", [vp, vp, ci])
+    rng = np.random.default_rng(1)
+    mask = o.view("mMaskTropic", 1)[0]
+
+    def vec():
+        g = rng.standard_normal((cs.ny, cs.nx)) * (cs.kmt > 0)
+        a = np.zeros((o.nyb, o.nxb))
+        a[2:-2, 2:-2] = g
+        A = np.ascontiguousarray(a[None])
+        o.halo_array(A, c.LOC_CENTER, c.KIND_SCALAR, 0.0)
+        return A[0]
+
+    x, y = vec(), vec()
+    ax, ay = np.zeros_like(x), np.zeros_like(x)
+    f_b(op(ax), op(x), 0)
+    f_b(op(ay), op(y), 0)
+    dot = lambda u, w: float(np.sum((u * w * mask)[2:-2, 2:-2]))
+    assert abs(dot(x, ay) - dot(ax, y)) <= 1e-12 * max(abs(dot(x, ay)), 1e-300)
+    assert dot(x, ax) < 0.0 and dot(y, ay) < 0.0      # -(div H grad) - diagonal: negative definite on ocean points
+
+
+def test_tridiagonal_solves_satisfy_their_matrix():
+    cs, o = _case(given_vmix=True)
+    o.set_timestep(c.TS_LEAPFROG)
+    km, nt = o.km, o.nt
+    To = o.view("TRACER", c.TIME_OLD, (nt, km))[0].copy()
+    Ps = o.view("PSURF", c.TIME_CUR)[0].copy()
+    VDC = o.view("VDC", 0, o.inner_shape("VDC"))[0]          # (2, km+2, nyb, nxb), level index 0..km+1
+    kmt = o.view("KMT", 1, (), np.int32)[0]
+    rng = np.random.default_rng(2)
+    rhs = np.ascontiguousarray(rng.standard_normal(To.shape) * 1e-3)
+    x = rhs.copy()
+    osig(o.L, "o_impvmixt", [vp, vp, vp, ci, ci, ci])(op(x), op(To), op(Ps), 1, nt, 0)
+    dz = cs.dz
+    dzw = np.concatenate([[0.5 * dz[0]], 0.5 * (dz[:-1] + dz[1:])])   # dzw(0..km-1): between k and k+1 is dzw[k]
+    c2dtt = 2.0 * cs.cfg.dtt
+    worst = 0.0
+    for n in range(nt):
+        slot = min(n, 1)
+        for (j, i) in [(5, 7), (12, 20), (20, 31), (25, 11), (9, 3)]:
+            K = kmt[j, i]
+            if K < 2:
+                continue
+            # (h_k + A_k + A_{k-1}) f_k - A_k f_{k+1} - A_{k-1} f_{k-1} = h_k rhs_k,  A_k = VDC(k)/dzw(k), A_K = 0
+            A = np.array([VDC[slot, k + 1, j, i] / dzw[k + 1] for k in range(K)])  # A[k]: between level k+1 and k+2 (1-based)
+            A[K - 1] = 0.0
+            h = dz[:K] / c2dtt
+            h[0] = dz[0] / c2dtt + Ps[j, i] / (GRAV * c2dtt)
+            hr = dz[:K] / c2dtt
+            f = x[n, :K, j, i] - To[n, :K, j, i]
+            res = np.zeros(K)
+            for k in range(K):
+                up = A[k - 1] if k > 0 else 0.0
+                res[k] = (h[k] + A[k] + up) * f[k] - (A[k] * f[k + 1] if k + 1 < K else 0.0) - (up * f[k - 1] if k > 0 else 0.0) \
+                         - hr[k] * rhs[n, k, j, i]
+            scale = np.max(np.abs(hr * rhs[n, :K, j, i])) + 1e-300
+            worst = max(worst, np.max(np.abs(res)) / scale)
+    assert worst <= 1e-10, worst
+
+
+@pytest.mark.parametrize("solver", [c.SOLVER_PCG, c.SOLVER_CHRONGEAR, c.SOLVER_PCSI])
+def test_solver_meets_its_convergence_criterion(solver):
+    cs, o = _case(solver_choice=solver, convergence_criterion=1e-12, given_vmix=True)
+    for ts in (c.TS_EULER, c.TS_LEAPFROG):
+        assert o.step(ts) == 0
+        its, rms = o.solver_diag()
+        assert 0 < its < cs.cfg.max_iterations
+        assert rms <= 1e-12        # rmsResidual = sqrt(rr * residualNorm) < convergenceCriterion (POP_SolversMod.F90:895-906)
+
+
+def test_advection_preserves_a_constant_tracer():
+    """L(1) = 0 by construction of WTKB: with T == const the advective tendency cancels to rounding (closed
+    column: the fluxes through the top (rigid lid) and the bottom vanish)."""
+    cs, o = _case(sfc_layer_type=c.SFC_RIGID)
+    km, nt = o.km, o.nt
+    U = o.view("UVEL", c.TIME_CUR, (km,))[0].copy()
+    V = o.view("VVEL", c.TIME_CUR, (km,))[0].copy()
+    kmt = o.view("KMT", 1, (), np.int32)[0]
+    T = np.zeros((nt, km, o.nyb, o.nxb))
+    for k in range(km):
+        T[:, k] = 3.5 * (kmt > k)
+    T = np.ascontiguousarray(T)
+    f_a = osig(o.L, "o_advt", [ci, vp, vp, vp, vp, vp, vp, ci])
+    WTK = np.zeros((o.nyb, o.nxb))
+    speed = max(np.abs(U).max(), np.abs(V).max())
+    for k in range(1, km + 1):
+        L = np.zeros((nt, o.nyb, o.nxb))
+        f_a(k, op(L), op(WTK), op(T), op(T), op(U), op(V), 0)
+        inner = (kmt[3:-3, 3:-3] >= k)
+        # interior ocean cells whose four neighbours are ocean at this level see T == const everywhere
+        ok = inner & (kmt[3:-3, 2:-4] >= k) & (kmt[3:-3, 4:-2] >= k) & (kmt[2:-4, 3:-3] >= k) & (kmt[4:-2, 3:-3] >= k)
+        ok &= (kmt[3:-3, 3:-3] > k)   # not the bottom cell of the column: there WTKB = 0 closes the column instead
+        if ok.any():
+            assert np.max(np.abs(L[0, 3:-3, 3:-3][ok])) <= 1e-12 * 3.5 * speed / cs.dz.min()
+
+
+def test_del4_is_two_passes_of_the_del2_stencil():
+    """hdifft_del4 = ah * L(AHF * L(T)) with the same masked 5-point weights as hdifft_del2 (ah = 1): compare
+    on cells whose whole 2-ring is ocean and where AHF == 1 (constant coefficient)."""
+    kw = dict(hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=0, lvariable_hmixu=0, ah=-2.0, am=-2.0)
+    cs4, o4 = _case(**kw)
+    T = o4.view("TRACER", c.TIME_CUR, (o4.nt, o4.km))[0].copy()
+    kmt = o4.view("KMT", 1, (), np.int32)[0]
+    f_h = osig(o4.L, "o_hdifft", [ci, vp, vp, vp, vp, ci])
+    k = 2
+    H4 = np.zeros((o4.nt, o4.nyb, o4.nxb))
+    f_h(k, op(H4), op(T), None, None, 0)
+    cs2, o2 = _case(hmix_tracer_itype=c.HMIX_DEL2, ah=1.0)
+    f_h2 = osig(o2.L, "o_hdifft", [ci, vp, vp, vp, vp, ci])
+    L1 = np.zeros((o2.nt, o2.nyb, o2.nxb))
+    f_h2(k, op(L1), op(T), None, None, 0)                    # L(T) on the physical cells
+    T2 = T.copy()
+    T2[:, k - 1] = 0.0
+    T2[:, k - 1, 2:-2, 2:-2] = L1[:, 2:-2, 2:-2]
+    A = np.ascontiguousarray(T2[:, k - 1][None].reshape(1, o2.nt, o2.nyb, o2.nxb))
+    o2.halo_array(A, c.LOC_CENTER, c.KIND_SCALAR, 0.0)
+    T2[:, k - 1] = A[0]
+    L2 = np.zeros((o2.nt, o2.nyb, o2.nxb))
+    f_h2(k, op(L2), op(np.ascontiguousarray(T2)), None, None, 0)
+    ocean = (kmt >= k)
+    deep = ocean.copy()
+    for dj in range(-2, 3):
+        for di in range(-2, 3):
+            deep &= np.roll(np.roll(ocean, dj, 0), di, 1)
+    deep[:4] = deep[-4:] = False
+    deep[:, :4] = deep[:, -4:] = False
+    assert deep.sum() > 20
+    ref = -2.0 * L2[0][deep]
+    assert np.max(np.abs(H4[0][deep] - ref)) <= 1e-11 * np.max(np.abs(ref))
