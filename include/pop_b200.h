@@ -43,7 +43,8 @@ enum { POP_SFC_VARTHICK = 1, POP_SFC_RIGID = 2, POP_SFC_OLDFREE = 3 };/* grid.F9
 enum { POP_STATE_MWJF = 2, POP_STATE_LINEAR = 4 };                    /* state_mod.F90:66-70 */
 enum { POP_STATE_RANGE_IGNORE = 1, POP_STATE_RANGE_ENFORCE = 3 };     /* state_mod.F90:79-82 */
 enum { POP_SOLVER_PCG = 1, POP_SOLVER_CHRONGEAR = 2, POP_SOLVER_PCSI = 3 };
-enum { POP_TS_LEAPFROG = 1, POP_TS_EULER = 2, POP_TS_AVG = 3 };       /* step_mod.F90:302-320,663 */
+enum { POP_TS_LEAPFROG = 1, POP_TS_EULER = 2, POP_TS_AVG = 3,       /* step_mod.F90:302-320,663 */
+       POP_TS_ROBERT = 4 };  /* leapfrog step closed by the Robert-Asselin-Williams filter, step_mod.F90:798,919-1354 */
 enum { POP_TIME_OLD = 0, POP_TIME_CUR = 1, POP_TIME_NEW = 2 };        /* prognostic.F90:63-68 */
 
 #define POP_MAX_NT 64
@@ -88,6 +89,8 @@ typedef struct pop_config {
   double dtt;
   /* ranks */
   int rank, nranks, device;
+  /* time_manager_nml: Robert filter coefficients (time_management.F90:461-464,897-898; Williams 2009) */
+  double robert_alpha, robert_nu;
 } pop_config;
 
 /* block descriptor handed to slab routines: mirrors `type block`, source/blocks.F90:30-39 */

@@ -520,7 +520,7 @@ static void alloc_state(void) {
 
 /* step_mod.F90:302-320 */
 void oracle_set_timestep(int ts_type) {
-  M.leapfrogts = (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_AVG);
+  M.leapfrogts = (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_AVG || ts_type == POP_TS_ROBERT);
   M.f_euler_ts = (ts_type == POP_TS_EULER);
   M.avg_ts = (ts_type == POP_TS_AVG);
   M.mix_pass = 0;

@@ -475,6 +475,156 @@ int o_barotropic_driver(void) {
 }
 
 /* step: step_mod.F90:296-626, 634-640, 663-832 */
+/* step_RF: step_mod.F90:919-1354 (variable-thickness surface layer, no ice formation, no passive-tracer
+   resets, no marginal seas: MASK_TRBUDGET(k) = RCALCT_OPEN_OCEAN_3D(k) = (KMT >= k), init_step :1570-1600).
+   Called with the three time levels of a completed leapfrog step; ends with the time-level rotation. */
+static void o_step_rf(void) {
+  const int km = M.km, nt = M.nt;
+  const int o = M.oldtime, c = M.curtime, n_ = M.newtime;
+  const size_t n2t = M.n2 * (size_t)NB, n3t = M.n3 * (size_t)NB;
+  const double rc = 0.5 * M.cfg.robert_nu * M.cfg.robert_alpha;            /* time_management.F90:897-898 */
+  const double rn = 0.5 * M.cfg.robert_nu * (M.cfg.robert_alpha - 1.0);
+  const int nonzero_new = !(rn == 0.0);
+  const double dz1 = M.dz[1];
+  if (!M.rf_ready) { /* init_step :1558-1600 */
+    M.STORE_RF = (double*)calloc(n3t * nt, sizeof(double));
+    M.bgtarea_t_k = (double*)calloc(km + 2, sizeof(double));
+    double* mk = (double*)malloc(sizeof(double) * n2t);
+    M.rf_volume_2_km = 0.0;
+    for (int k = 1; k <= km; k++) {
+      for (size_t q = 0; q < n2t; q++) mk[q] = (M.KMT[q] >= k) ? 1.0 : 0.0;
+      M.bgtarea_t_k[k] = oracle_global_sum(M.TAREA, POP_LOC_CENTER, mk);
+      if (k >= 2) M.rf_volume_2_km = M.rf_volume_2_km + M.bgtarea_t_k[k] * M.dz[k];
+    }
+    free(mk);
+    for (int n = 0; n < POP_MAX_NT; n++) { M.rf_S_prev[n] = 0.0; M.rf_S_prev_valid[n] = 0; }
+    M.rf_ready = 1;
+  }
+#define RF2(F) for (size_t q = 0; q < n2t; q++) { double w = F[o][q] + F[n_][q] - 2.0 * F[c][q]; \
+                 if (nonzero_new) { F[n_][q] = F[n_][q] + rn * w; } \
+                 F[c][q] = F[c][q] + rc * w; }
+  RF2(M.UBTROP) RF2(M.VBTROP) RF2(M.GRADPX) RF2(M.GRADPY)
+#undef RF2
+  for (size_t q = 0; q < n3t; q++) {
+    double w = M.UVEL[o][q] + M.UVEL[n_][q] - 2.0 * M.UVEL[c][q];
+    if (nonzero_new) M.UVEL[n_][q] = M.UVEL[n_][q] + rn * w;
+    M.UVEL[c][q] = M.UVEL[c][q] + rc * w;
+    w = M.VVEL[o][q] + M.VVEL[n_][q] - 2.0 * M.VVEL[c][q];
+    if (nonzero_new) M.VVEL[n_][q] = M.VVEL[n_][q] + rn * w;
+    M.VVEL[c][q] = M.VVEL[c][q] + rc * w;
+  }
+  double* WORKN = (double*)calloc(n2t * nt, sizeof(double)); /* [n][block][..] for the n-field sum */
+  double rf_Svol[POP_MAX_NT], sums[POP_MAX_NT];
+  double* mask1 = (double*)malloc(sizeof(double) * n2t);
+  for (size_t q = 0; q < n2t; q++) mask1[q] = (M.KMT[q] >= 1) ? 1.0 : 0.0;
+  /* tracers, vertical interior :1031-1066 */
+  for (int b = 0; b < NB; b++) {
+    double *To = B4(M.TRACER[o], b), *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+    double* S = M.STORE_RF + (size_t)b * M.n3 * nt;
+    const int* KMT = M.KMT + (size_t)b * M.n2;
+    for (int n = 1; n <= nt; n++) {
+      double* W = WORKN + ((size_t)(n - 1) * NB + b) * M.n2;
+      for (int k = 2; k <= km; k++) {
+        double *s = KN4(S, k, n), *to = KN4(To, k, n), *tc = KN4(Tc, k, n), *tn = KN4(Tn, k, n);
+        for (size_t q = 0; q < M.n2; q++) {
+          s[q] = to[q] + tn[q] - 2.0 * tc[q];
+          if (nonzero_new) tn[q] = tn[q] + rn * s[q];
+          tc[q] = tc[q] + rc * s[q];
+          W[q] = W[q] + M.dz[k] * ((KMT[q] >= k) ? 1.0 : 0.0) * s[q];
+        }
+      }
+      for (size_t q = 0; q < M.n2; q++) W[q] = B2(M.TAREA, b)[q] * W[q];
+    }
+  }
+  for (int n = 0; n < nt; n++) rf_Svol[n] = oracle_global_sum(WORKN + (size_t)n * n2t, POP_LOC_CENTER, NULL);
+  /* surface tracers and PSURF :1070-1146 */
+  for (int b = 0; b < NB; b++) {
+    double *To = B4(M.TRACER[o], b), *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+    double* S = M.STORE_RF + (size_t)b * M.n3 * nt;
+    const double *Po = B2(M.PSURF[o], b), *Pc = B2(M.PSURF[c], b), *Pn = B2(M.PSURF[n_], b);
+    for (int n = 1; n <= nt; n++) {
+      double* W = WORKN + ((size_t)(n - 1) * NB + b) * M.n2;
+      double *s = KN4(S, 1, n), *to = KN4(To, 1, n), *tc = KN4(Tc, 1, n), *tn = KN4(Tn, 1, n);
+      for (size_t q = 0; q < M.n2; q++) {
+        s[q] = (dz1 + Po[q] / O_GRAV) * to[q] + (dz1 + Pn[q] / O_GRAV) * tn[q] - 2.0 * (dz1 + Pc[q] / O_GRAV) * tc[q];
+        if (nonzero_new) tn[q] = (dz1 + Pn[q] / O_GRAV) * tn[q] + rn * s[q];
+        tc[q] = (dz1 + Pc[q] / O_GRAV) * tc[q] + rc * s[q];
+        W[q] = B2(M.TAREA, b)[q] * B2(mask1, b)[q] * s[q];
+      }
+    }
+  }
+  for (int n = 0; n < nt; n++) rf_Svol[n] = rf_Svol[n] + oracle_global_sum(WORKN + (size_t)n * n2t, POP_LOC_CENTER, NULL);
+  double* WORKB = (double*)malloc(sizeof(double) * n2t);
+  double* WB2 = (double*)malloc(sizeof(double) * n2t);
+  for (size_t q = 0; q < n2t; q++) {
+    WORKB[q] = M.PSURF[o][q] + M.PSURF[n_][q] - 2.0 * M.PSURF[c][q];
+    if (nonzero_new) M.PSURF[n_][q] = M.PSURF[n_][q] + rn * WORKB[q];
+    M.PSURF[c][q] = M.PSURF[c][q] + rc * WORKB[q];
+    WB2[q] = WORKB[q] * M.TAREA[q];
+  }
+  double rf_sump = oracle_global_sum(WB2, POP_LOC_CENTER, mask1);
+  rf_sump = rf_sump / M.bgtarea_t_k[1];
+  for (int b = 0; b < NB; b++) {
+    double *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+    double *Pc = B2(M.PSURF[c], b), *Pn = B2(M.PSURF[n_], b);
+    for (size_t q = 0; q < M.n2; q++) {
+      const double w2 = (B2(mask1, b)[q] != 0.0) ? rf_sump : 0.0;
+      if (nonzero_new) Pn[q] = Pn[q] - rn * w2;
+      Pc[q] = Pc[q] - rc * w2;
+    }
+    for (int n = 1; n <= nt; n++) {
+      double *tc = KN4(Tc, 1, n), *tn = KN4(Tn, 1, n);
+      for (size_t q = 0; q < M.n2; q++) {
+        if (nonzero_new) tn[q] = tn[q] / (dz1 + Pn[q] / O_GRAV);
+        tc[q] = tc[q] / (dz1 + Pc[q] / O_GRAV);
+      }
+    }
+  }
+  /* conservation adjustment :1160-1205 */
+  for (size_t q = 0; q < n2t; q++) WORKB[q] = M.TAREA[q] * (dz1 + M.PSURF[c][q] / O_GRAV);
+  const double rf_volume_total_cur = M.rf_volume_2_km + oracle_global_sum(WORKB, POP_LOC_CENTER, mask1);
+  const double rf_ocean_norm = M.rf_volume_2_km + oracle_global_sum(WORKB, POP_LOC_CENTER, mask1); /* open ocean == ocean */
+  (void)rf_volume_total_cur;
+  for (int n = 1; n <= nt; n++) {
+    const double rf_S = rf_Svol[n - 1] / rf_ocean_norm;
+    double factor;
+    if (!M.rf_S_prev_valid[n - 1] || nonzero_new) factor = rf_S;
+    else factor = 0.5 * (rf_S + M.rf_S_prev[n - 1]);
+    const double f_new = factor * rn, f_cur = factor * rc;
+    for (int b = 0; b < NB; b++) {
+      double *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+      const int* KMT = M.KMT + (size_t)b * M.n2;
+      for (int k = 1; k <= km; k++) {
+        double *tc = KN4(Tc, k, n), *tn = KN4(Tn, k, n);
+        for (size_t q = 0; q < M.n2; q++) {
+          const double m3 = (KMT[q] >= k) ? 1.0 : 0.0;
+          if (nonzero_new) tn[q] = tn[q] - f_new * m3;
+          tc[q] = tc[q] - f_cur * m3;
+        }
+      }
+    }
+    sums[n - 1] = rf_S;
+  }
+  /* :1230-1290 */
+  memcpy(M.FW_OLD, M.FW, sizeof(double) * n2t);
+  for (int b = 0; b < NB; b++) {
+    double *Tc = B4(M.TRACER[c], b), *Tn = B4(M.TRACER[n_], b);
+    for (int k = 1; k <= km; k++) {
+      o_state(k, k, KN4(Tc, k, 1), KN4(Tc, k, 2), b, K3(B3(M.RHO[c], b), k), NULL, NULL, NULL);
+      o_state(k, k, KN4(Tn, k, 1), KN4(Tn, k, 2), b, K3(B3(M.RHO[n_], b), k), NULL, NULL, NULL);
+    }
+  }
+  for (size_t q = 0; q < n2t; q++)
+    M.PGUESS[q] = 3.0 * (M.PSURF[n_][q] - M.PSURF[c][q]) + M.PSURF[o][q];
+  int tmptime = M.oldtime;
+  M.oldtime = M.curtime;
+  M.curtime = M.newtime;
+  M.newtime = tmptime;
+  if (!nonzero_new)
+    for (int n = 0; n < nt; n++) { M.rf_S_prev[n] = sums[n]; M.rf_S_prev_valid[n] = 1; }
+  free(WORKN); free(mask1); free(WORKB); free(WB2);
+}
+
 int oracle_step(int ts_type) {
   double t0 = o_now(), t1;
   const int km = M.km, nt = M.nt;
@@ -511,7 +661,9 @@ int oracle_step(int ts_type) {
   /* PGUESS: step_mod.F90:634-640 */
   for (size_t q = 0; q < M.n2 * (size_t)NB; q++)
     M.PGUESS[q] = 3.0 * (M.PSURF[M.newtime][q] - M.PSURF[M.curtime][q]) + M.PSURF[M.oldtime][q];
-  if (M.avg_ts) {
+  if (ts_type == POP_TS_ROBERT) {
+    o_step_rf();
+  } else if (M.avg_ts) {
     /* averaging step: step_mod.F90:663-796 */
     const int o = M.oldtime, c = M.curtime;
     size_t n2t = M.n2 * (size_t)NB, n3t = M.n3 * (size_t)NB;

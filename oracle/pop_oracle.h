@@ -82,6 +82,10 @@ typedef struct {
   /* barotropic */
   int *CHECKER, *CONSTNT;
   double rcheck, rconst;
+  /* Robert filter (step_mod.F90:81-103,1558-1600): S terms, budget areas, previous conservation factors */
+  double *STORE_RF, *bgtarea_t_k;
+  double rf_volume_2_km, rf_S_prev[POP_MAX_NT];
+  int rf_ready, rf_S_prev_valid[POP_MAX_NT];
   /* work */
   double *DH, *DHU, *ZX, *ZY;
   /* timers (seconds), indices below */

@@ -18,7 +18,7 @@ SFC_VARTHICK, SFC_RIGID, SFC_OLDFREE = 1, 2, 3
 STATE_MWJF, STATE_LINEAR = 2, 4
 STATE_RANGE_IGNORE, STATE_RANGE_ENFORCE = 1, 3
 SOLVER_PCG, SOLVER_CHRONGEAR, SOLVER_PCSI = 1, 2, 3
-TS_LEAPFROG, TS_EULER, TS_AVG = 1, 2, 3
+TS_LEAPFROG, TS_EULER, TS_AVG, TS_ROBERT = 1, 2, 3, 4
 TIME_OLD, TIME_CUR, TIME_NEW = 0, 1, 2
 
 
@@ -50,6 +50,7 @@ class PopConfig(C.Structure):
         ("convergence_criterion", C.c_double), ("lanczos_convergence_criterion", C.c_double),
         ("dtt", C.c_double),
         ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
+        ("robert_alpha", C.c_double), ("robert_nu", C.c_double),
     ]
 
 
@@ -85,7 +86,7 @@ def make_config(**kw):
         solver_choice=SOLVER_CHRONGEAR, max_iterations=1000, convergence_check_freq=10,
         convergence_check_start=60, max_lanczos_step=20,
         convergence_criterion=1.0e-13, lanczos_convergence_criterion=0.1,
-        dtt=3600.0, rank=0, nranks=1, device=0,
+        dtt=3600.0, rank=0, nranks=1, device=0, robert_alpha=0.53, robert_nu=0.20,
     )
     tadv = kw.pop("tadvect", TADVECT_CENTERED)
     d.update(kw)

@@ -153,6 +153,8 @@ extern "C" void pop_config_defaults(pop_config* c) {
   c->lanczos_convergence_criterion = 0.1;
   c->dtt = 3600.0;
   c->nranks = 1;
+  c->robert_alpha = 0.53;  // time_management.F90:461-462 (Williams 2009)
+  c->robert_nu = 0.20;
 }
 
 // ------------------------------------------------------------------ lifecycle
@@ -391,7 +393,7 @@ int upload_vert_const() {
 // step_mod.F90:302-320
 int set_timestep(int ts_type) {
   POP_REQUIRE(G.grid_set, "pop_set_timestep: grid not set");
-  bool leap = (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_AVG);
+  bool leap = (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_AVG || ts_type == POP_TS_ROBERT);
   bool changed = (leap != G.leapfrogts) || G.vc.c2dtt[1] == 0.0;
   G.leapfrogts = leap;
   G.f_euler_ts = (ts_type == POP_TS_EULER);

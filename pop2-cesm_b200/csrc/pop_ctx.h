@@ -75,6 +75,11 @@ struct Ctx {
   double dtt = 0, dtu = 0, dtp = 0, c2dtu = 0, c2dtp = 0, beta = 0;
   double alpha = 1.0 / 3.0, theta = 0.5, gamma = 1.0 - 2.0 * (1.0 / 3.0);
   bool leapfrogts = true, f_euler_ts = false, avg_ts = false;
+  // Robert filter state (step_mod.F90:81-103, init_step :1558-1600)
+  bool rf_ready = false;
+  double rf_volume_2_km = 0, rf_bgtarea1 = 0;
+  double rf_S_prev[POP_MAX_NT] = {0};
+  bool rf_S_prev_valid[POP_MAX_NT] = {false};
   // hmix / misc scalars
   double ah = 0, am = 0, uarea_equator = 0;
   int vdc_nk = 0, vdc_k0 = 1, vdc_nd = 1, vvc_nk = 0;

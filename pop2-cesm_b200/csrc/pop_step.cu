@@ -252,9 +252,195 @@ __global__ void avg_tracer_kernel(double* __restrict__ To, double* __restrict__ 
   Tc[c] = 0.5 * (tc + Tn[c]);
 }
 
+// ------------------------------------------------------------------ Robert-Asselin-Williams filter
+// step_RF, step_mod.F90:919-1354, for the configuration this library covers (variable-thickness surface
+// layer, no ice formation, no passive-tracer resets, no marginal seas, so that MASK_TRBUDGET(k) and
+// RCALCT_OPEN_OCEAN_3D(k) are both (KMT >= k), init_step :1570-1600). STORE_RF is a diagnostic-only array
+// in the reference; here the S terms live in registers and only their column integrals reach memory.
+__global__ void rf_filter_kernel(double* __restrict__ Fo, double* __restrict__ Fc, double* __restrict__ Fn,
+                                 size_t n, double rc, double rn, int nonzero_new) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double fc = Fc[q], fn = Fn[q];
+  const double w = Fo[q] + fn - 2.0 * fc;
+  if (nonzero_new) Fn[q] = fn + rn * w;
+  Fc[q] = fc + rc * w;
+}
+struct RfTracer {
+  const double *To, *Po, *Pc, *Pn, *TAREA, *RCALCT;
+  double *Tc, *Tn, *WI, *WS;  // WI/WS: (n2, nt) interior / surface volume-weighted S
+  const int* KMT;
+  size_t n2, n3;
+  double rc, rn, dz1;
+  int km, nonzero_new;
+};
+// one thread per (column, tracer): levels 2..km (:1031-1066) then the thickness-weighted surface (:1070-1094)
+__global__ void rf_tracer_kernel(RfTracer a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n2) return;
+  const int n = blockIdx.y;
+  const size_t base = (size_t)n * a.n3 + q;
+  const int kmt = a.KMT[q];
+  double w = 0.0;
+  for (int k = 2; k <= a.km; k++) {
+    const size_t c = base + (size_t)(k - 1) * a.n2;
+    const double tc = a.Tc[c], tn = a.Tn[c];
+    const double s = a.To[c] + tn - 2.0 * tc;
+    if (a.nonzero_new) a.Tn[c] = tn + a.rn * s;
+    a.Tc[c] = tc + a.rc * s;
+    w = w + c_vc.dz[k] * ((kmt >= k) ? 1.0 : 0.0) * s;
+  }
+  const double tarea = a.TAREA[q];
+  a.WI[(size_t)n * a.n2 + q] = tarea * w;
+  const double ho = a.dz1 + a.Po[q] / POP_GRAV, hc = a.dz1 + a.Pc[q] / POP_GRAV, hn = a.dz1 + a.Pn[q] / POP_GRAV;
+  const double tc = a.Tc[base], tn = a.Tn[base];
+  const double s = ho * a.To[base] + hn * tn - 2.0 * hc * tc;
+  if (a.nonzero_new) a.Tn[base] = hn * tn + a.rn * s;
+  a.Tc[base] = hc * tc + a.rc * s;
+  a.WS[(size_t)n * a.n2 + q] = tarea * a.RCALCT[q] * s;
+}
+// PSURF filter (:1099-1112); WB = S_p * TAREA for the conservation term
+__global__ void rf_psurf_kernel(const double* __restrict__ Po, double* __restrict__ Pc, double* __restrict__ Pn,
+                                const double* __restrict__ TAREA, double* __restrict__ WB, size_t n,
+                                double rc, double rn, int nonzero_new) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double pc = Pc[q], pn = Pn[q];
+  const double w = Po[q] + pn - 2.0 * pc;
+  if (nonzero_new) Pn[q] = pn + rn * w;
+  Pc[q] = pc + rc * w;
+  WB[q] = w * TAREA[q];
+}
+struct RfSurface {
+  double *Pc, *Pn, *Tc, *Tn, *WB;
+  const double *TAREA, *RCALCT;
+  size_t n2, n3;
+  double rc, rn, dz1, rf_sump;
+  int nt, nonzero_new;
+};
+// PSURF conservation term, surface tracers back from tracer*thickness (:1120-1141), surface volume (:1160)
+__global__ void rf_surface_kernel(RfSurface a) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n2) return;
+  const double w2 = (a.RCALCT[q] != 0.0) ? a.rf_sump : 0.0;
+  double pn = a.Pn[q];
+  if (a.nonzero_new) { pn = pn - a.rn * w2; a.Pn[q] = pn; }
+  const double pc = a.Pc[q] - a.rc * w2;
+  a.Pc[q] = pc;
+  const double hn = a.dz1 + pn / POP_GRAV, hc = a.dz1 + pc / POP_GRAV;
+  for (int n = 0; n < a.nt; n++) {
+    const size_t c = (size_t)n * a.n3 + q;
+    if (a.nonzero_new) a.Tn[c] = a.Tn[c] / hn;
+    a.Tc[c] = a.Tc[c] / hc;
+  }
+  a.WB[q] = a.TAREA[q] * hc;
+}
+struct RfConserve {
+  double f_new[POP_MAX_NT], f_cur[POP_MAX_NT];
+};
+// conservation adjustment at all levels (:1193-1205)
+__global__ void rf_conserve_kernel(double* __restrict__ Tc, double* __restrict__ Tn, const int* __restrict__ KMT,
+                                   size_t n2, int km, int nonzero_new, const POP_GRID_CONSTANT RfConserve f) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  const int z = blockIdx.y;  // 0 .. nt*km-1
+  const int n = z / km, k = z % km + 1;
+  const double m3 = (KMT[q] >= k) ? 1.0 : 0.0;
+  const size_t c = (size_t)z * n2 + q;
+  if (nonzero_new) Tn[c] = Tn[c] - f.f_new[n] * m3;
+  Tc[c] = Tc[c] - f.f_cur[n] * m3;
+}
+__global__ void rf_levelmask_kernel(double* __restrict__ mk, const int* __restrict__ KMT, size_t n, int k) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) mk[q] = (KMT[q] >= k) ? 1.0 : 0.0;
+}
+
+static int step_rf_dev() {
+  ScopedTimer tm("ROBERT_FILTER");
+  POP_REQUIRE(G.cfg.sfc_layer_type == POP_SFC_VARTHICK,
+              "pop_step: the Robert filter needs sfc_layer_type varthick (step_mod.F90:1150-1154)");
+  const int km = G.km, nt = G.nt;
+  const int o = G.oldtime, c = G.curtime, n_ = G.newtime;
+  const double rc = 0.5 * G.cfg.robert_nu * G.cfg.robert_alpha;  // time_management.F90:897-898
+  const double rn = 0.5 * G.cfg.robert_nu * (G.cfg.robert_alpha - 1.0);
+  const int nonzero_new = !(rn == 0.0);
+  const double dz1 = G.vc.dz[1];
+  if (!G.rf_ready) {  // init_step, step_mod.F90:1558-1600
+    G.rf_volume_2_km = 0.0;
+    for (int k = 1; k <= km; k++) {
+      double area = 0.0;
+      POP_LAUNCH(rf_levelmask_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("W2A"), fldi("KMT"), G.n2, k);
+      POP_TRY(global_sum_dev(fld("TAREA"), 1, 0, POP_LOC_CENTER, fld("W2A"), &area));
+      if (k == 1) G.rf_bgtarea1 = area;
+      else G.rf_volume_2_km = G.rf_volume_2_km + area * G.vc.dz[k];
+    }
+    for (int n = 0; n < POP_MAX_NT; n++) { G.rf_S_prev[n] = 0.0; G.rf_S_prev_valid[n] = false; }
+    G.rf_ready = true;
+  }
+  for (const char* f : {"UBTROP", "VBTROP", "GRADPX", "GRADPY"})
+    POP_LAUNCH(rf_filter_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld_t(f, o), fld_t(f, c), fld_t(f, n_), G.n2,
+               rc, rn, nonzero_new);
+  for (const char* f : {"UVEL", "VVEL"})
+    POP_LAUNCH(rf_filter_kernel, ew_grid(G.n3), POP_EW_THREADS, 0, fld_t(f, o), fld_t(f, c), fld_t(f, n_), G.n3,
+               rc, rn, nonzero_new);
+  RfTracer a;
+  a.To = fld_t("TRACER", o); a.Tc = fld_t("TRACER", c); a.Tn = fld_t("TRACER", n_);
+  a.Po = fld_t("PSURF", o); a.Pc = fld_t("PSURF", c); a.Pn = fld_t("PSURF", n_);
+  a.TAREA = fld("TAREA"); a.RCALCT = fld("RCALCT"); a.KMT = fldi("KMT");
+  a.WI = fld("AUX"); a.WS = fld("RHS1");
+  a.n2 = G.n2; a.n3 = G.n3; a.rc = rc; a.rn = rn; a.dz1 = dz1; a.km = km; a.nonzero_new = nonzero_new;
+  POP_LAUNCH(rf_tracer_kernel, dim3(ew_grid(G.n2), (unsigned)nt, 1), POP_EW_THREADS, 0, a);
+  double rf_Svol[POP_MAX_NT], tmp[POP_RED_NF];
+  for (int n0 = 0; n0 < nt; n0 += POP_RED_NF) {  // :1066 and :1096
+    const int nf = (nt - n0 < POP_RED_NF) ? nt - n0 : POP_RED_NF;
+    POP_TRY(global_sum_dev(a.WI + (size_t)n0 * G.n2, nf, G.n2, POP_LOC_CENTER, nullptr, tmp));
+    for (int f = 0; f < nf; f++) rf_Svol[n0 + f] = tmp[f];
+    POP_TRY(global_sum_dev(a.WS + (size_t)n0 * G.n2, nf, G.n2, POP_LOC_CENTER, nullptr, tmp));
+    for (int f = 0; f < nf; f++) rf_Svol[n0 + f] = rf_Svol[n0 + f] + tmp[f];
+  }
+  double *Pc = fld_t("PSURF", c), *Pn = fld_t("PSURF", n_);
+  POP_LAUNCH(rf_psurf_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, a.Po, Pc, Pn, a.TAREA, fld("W2A"), G.n2, rc, rn,
+             nonzero_new);
+  double rf_sump = 0.0;
+  POP_TRY(global_sum_dev(fld("W2A"), 1, 0, POP_LOC_CENTER, a.RCALCT, &rf_sump));  // :1116-1118
+  rf_sump = rf_sump / G.rf_bgtarea1;
+  RfSurface s;
+  s.Pc = Pc; s.Pn = Pn; s.Tc = a.Tc; s.Tn = a.Tn; s.WB = fld("W2A"); s.TAREA = a.TAREA; s.RCALCT = a.RCALCT;
+  s.n2 = G.n2; s.n3 = G.n3; s.rc = rc; s.rn = rn; s.dz1 = dz1; s.rf_sump = rf_sump; s.nt = nt;
+  s.nonzero_new = nonzero_new;
+  POP_LAUNCH(rf_surface_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, s);
+  double sfc_vol = 0.0;
+  POP_TRY(global_sum_dev(fld("W2A"), 1, 0, POP_LOC_CENTER, a.RCALCT, &sfc_vol));  // :1162-1171
+  const double rf_ocean_norm = G.rf_volume_2_km + sfc_vol;
+  RfConserve f;
+  double rf_S[POP_MAX_NT];
+  for (int n = 0; n < nt; n++) {  // :1173-1187
+    rf_S[n] = rf_Svol[n] / rf_ocean_norm;
+    const double factor =
+        (!G.rf_S_prev_valid[n] || nonzero_new) ? rf_S[n] : 0.5 * (rf_S[n] + G.rf_S_prev[n]);
+    f.f_new[n] = factor * rn;
+    f.f_cur[n] = factor * rc;
+  }
+  POP_LAUNCH(rf_conserve_kernel, dim3(ew_grid(G.n2), (unsigned)(km * nt), 1), POP_EW_THREADS, 0, a.Tc, a.Tn, a.KMT,
+             G.n2, km, nonzero_new, f);
+  // :1230-1290
+  POP_CHECK_CUDA(cudaMemcpyAsync(fld("FW_OLD"), fld("FW"), sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  POP_TRY(state_3d(a.Tc, fld_t("RHO", c)));
+  POP_TRY(state_3d(a.Tn, fld_t("RHO", n_)));
+  POP_LAUNCH(pguess_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("PGUESS"), Pn, Pc, a.Po, G.n2);  // :1305-1311
+  const int t = G.oldtime;
+  G.oldtime = G.curtime;
+  G.curtime = G.newtime;
+  G.newtime = t;
+  if (!nonzero_new)
+    for (int n = 0; n < nt; n++) { G.rf_S_prev[n] = rf_S[n]; G.rf_S_prev_valid[n] = true; }
+  return pop_post_launch("step_RF");
+}
+
 int step_dev(int ts_type) {
   POP_REQUIRE(G.grid_set, "pop_step: grid not set");
-  POP_REQUIRE(ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER || ts_type == POP_TS_AVG,
+  POP_REQUIRE(ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER || ts_type == POP_TS_AVG ||
+                  ts_type == POP_TS_ROBERT,
               "pop_step: unknown time-step type %d (matsuno steps are not supported)", ts_type);
   ScopedTimer tm("STEP");
   POP_TRY(set_timestep(ts_type));
@@ -293,7 +479,9 @@ int step_dev(int ts_type) {
   }
   POP_LAUNCH(pguess_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("PGUESS"), fld_t("PSURF", n_),
              fld_t("PSURF", c), fld_t("PSURF", o), G.n2);  // step_mod.F90:634-640
-  if (G.avg_ts) {
+  if (ts_type == POP_TS_ROBERT) {
+    POP_TRY(step_rf_dev());  // step_mod.F90:798-802
+  } else if (G.avg_ts) {
     for (const char* f : {"UBTROP", "VBTROP", "GRADPX", "GRADPY"})
       POP_LAUNCH(avg_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld_t(f, o), fld_t(f, c), fld_t(f, n_), G.n2);
     POP_LAUNCH(avg_fw_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("FW_OLD"), fld("FW"), G.n2);

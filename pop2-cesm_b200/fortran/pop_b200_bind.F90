@@ -30,7 +30,8 @@ module pop_b200_bind
                                  POP_B200_LOC_NFACE  = 3, POP_B200_LOC_EFACE    = 4
    integer (c_int), parameter :: POP_B200_KIND_SCALAR = 1, POP_B200_KIND_VECTOR = 2, &
                                  POP_B200_KIND_ANGLE  = 3
-   integer (c_int), parameter :: POP_B200_TS_LEAPFROG = 1, POP_B200_TS_EULER = 2, POP_B200_TS_AVG = 3
+   integer (c_int), parameter :: POP_B200_TS_LEAPFROG = 1, POP_B200_TS_EULER = 2, POP_B200_TS_AVG = 3, &
+                                 POP_B200_TS_ROBERT = 4
    integer (c_int), parameter :: POP_B200_TIME_OLD = 0, POP_B200_TIME_CUR = 1, POP_B200_TIME_NEW = 2
 
    ! mirrors struct pop_config (include/pop_b200.h); filled from the namelist variables the
@@ -62,6 +63,7 @@ module pop_b200_bind
       real (c_double) :: convergence_criterion, lanczos_convergence_criterion
       real (c_double) :: dtt
       integer (c_int) :: rank, nranks, device
+      real (c_double) :: robert_alpha, robert_nu
    end type pop_config
 
    ! mirrors struct pop_block = `type block` of blocks.F90:30-39

@@ -45,7 +45,7 @@ def main():
     elif which == "cyclic_pcg":
         kw.update(ns=c.BNDY_CYCLIC, solver_choice=c.SOLVER_PCG, tadvect=c.TADVECT_UPWIND3, nt=3)
     cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
-    steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG]
+    steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG, c.TS_ROBERT]
     ref = None
     if rank == 0:
         ref = run(cs, c.copy_config(cs.cfg, rank=0, nranks=1, device=0), None, steps)

@@ -70,6 +70,35 @@ def test_step_sequence_matches_oracle(name):
         p.finalize()
 
 
+@pytest.mark.parametrize("name,alpha", [("del2_chrongear", 0.53), ("tripole_del4_pcsi", 0.53), ("upwind3_pcg", 1.0)])
+def test_robert_filter_steps_match_oracle(name, alpha):
+    """Leapfrog steps closed by the Robert-Asselin-Williams filter (step_RF, step_mod.F90:919-1354).
+    alpha = 0.53 filters both the new and the current level; alpha = 1 (plain Robert-Asselin) only the
+    current one and averages the conservation factor with the previous step's (:1176-1182)."""
+    kw = dict(CASES[name])
+    cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), robert_alpha=alpha, **kw)
+    o, p = load_oracle(cs), load_pop(cs)
+    try:
+        for i, ts in enumerate([c.TS_EULER, c.TS_ROBERT, c.TS_ROBERT, c.TS_ROBERT]):
+            assert o.step(ts) == 0
+            p.step(ts)
+            assert o.solver_diag()[0] == p.solvers_get_diagnostics()[0]
+            compare(o, p, RTOL_1STEP * (i + 1), "%s robert step %d" % (name, i))
+    finally:
+        p.finalize()
+
+
+def test_robert_filter_needs_variable_thickness_surface_layer():
+    cs = make_case(32, 24, 6, seed=3, sfc_layer_type=c.SFC_RIGID)
+    p = load_pop(cs)
+    try:
+        p.step(c.TS_EULER)
+        with pytest.raises(Exception, match="varthick"):
+            p.step(c.TS_ROBERT)
+    finally:
+        p.finalize()
+
+
 def test_ten_steps_stay_within_solver_tolerance():
     cs = make_case(48, 36, 8, seed=31, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=900.0)
     o, p = load_oracle(cs), load_pop(cs)

@@ -127,7 +127,7 @@ def test_del4_is_two_passes_of_the_del2_stencil():
     kw = dict(hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=0, lvariable_hmixu=0, ah=-2.0, am=-2.0)
     cs4, o4 = _case(**kw)
     T = o4.view("TRACER", c.TIME_CUR, (o4.nt, o4.km))[0].copy()
-    kmt = o4.view("KMT", 1, (), np.int32)[0]
+    kmt = o4.view("KMT", 1, (), np.int32)[0].copy()      # the oracle is re-initialised below: no views into its memory
     f_h = osig(o4.L, "o_hdifft", [ci, vp, vp, vp, vp, ci])
     k = 2
     H4 = np.zeros((o4.nt, o4.nyb, o4.nxb))
@@ -154,3 +154,45 @@ def test_del4_is_two_passes_of_the_del2_stencil():
     assert deep.sum() > 20
     ref = -2.0 * L2[0][deep]
     assert np.max(np.abs(H4[0][deep] - ref)) <= 1e-11 * np.max(np.abs(ref))
+
+
+def _content(o, cs, tlev):
+    """volume integrals of the tracers (variable-thickness surface layer) and the area integral of PSURF
+    over the physical ocean cells of time level tlev"""
+    T = oracle_global(o, "TRACER", tlev).reshape(o.nt, o.km, cs.ny, cs.nx)
+    P = oracle_global(o, "PSURF", tlev).reshape(cs.ny, cs.nx)
+    tarea = oracle_global(o, "TAREA", 0).reshape(cs.ny, cs.nx)
+    dz = np.asarray(cs.dz, dtype=np.float64)
+    lev = np.arange(1, o.km + 1)[:, None, None]
+    thick = np.broadcast_to(dz[:, None, None], (o.km, cs.ny, cs.nx)).copy()
+    thick[0] = dz[0] + P / GRAV
+    vol = tarea[None] * thick * (cs.kmt[None] >= lev)
+    return [float(np.sum(vol * T[n])) for n in range(o.nt)], float(np.sum(tarea * (cs.kmt >= 1) * P)), float(np.sum(vol))
+
+
+@pytest.mark.parametrize("alpha", [0.53, 1.0])
+def test_robert_filter_conserves_tracer_content_and_mean_surface_pressure(alpha):
+    """step_RF's conservation terms (step_mod.F90:1114-1205): filtering changes the values of the current and
+    new levels but neither their volume-integrated tracer content nor the area mean of PSURF, so a leapfrog
+    step closed by the filter and a plain leapfrog step from the same state agree in those integrals."""
+    res = {}
+    for ts in (c.TS_LEAPFROG, c.TS_ROBERT):
+        cs, o = _case(ns=c.BNDY_TRIPOLE, robert_alpha=alpha, convergence_criterion=1e-13)
+        assert o.step(c.TS_EULER) == 0 and o.step(ts) == 0
+        res[ts] = [_content(o, cs, t) for t in (c.TIME_OLD, c.TIME_CUR)]   # = (cur, new) of the step just taken
+        fields = {t: oracle_global(o, "TRACER", t).copy() for t in (c.TIME_OLD, c.TIME_CUR)}
+        if ts == c.TS_LEAPFROG:
+            plain = fields
+    for lvl in (0, 1):
+        (ta, pa, va), (tb, pb, vb) = res[c.TS_LEAPFROG][lvl], res[c.TS_ROBERT][lvl]
+        if alpha == 1.0 and lvl == 1:      # plain Robert-Asselin leaves the new level untouched
+            assert np.array_equal(plain[c.TIME_CUR], fields[c.TIME_CUR])
+        # the reference normalises by the CURRENT level's volume (:1162-1171, "placeholder for
+        # lrf_nonzero_newtime; this is not correct" :1178), so the new level is conserved only as far as the
+        # two surface volumes agree
+        tol = 1e-12 if lvl == 0 else 1e-9
+        for n in range(len(ta)):
+            assert abs(ta[n] - tb[n]) <= tol * abs(ta[n]), (lvl, n, ta[n], tb[n])
+        assert abs(pa - pb) <= 1e-12 * max(abs(pa), va * 1e-6)
+    # ... while the fields themselves did change at the filtered level
+    assert not np.array_equal(plain[c.TIME_OLD], fields[c.TIME_OLD])
