@@ -391,6 +391,7 @@ void* o_alloc_i(size_t n) {
   return p;
 }
 void oracle_finalize(void) {
+  o_gm_reset();
   for (int i = 0; i < g_nptr; i++) free(g_ptrs[i]);
   g_nptr = 0;
   free(M.ib); free(M.ie); free(M.jb); free(M.je); free(M.iblk); free(M.jblk); free(M.active);

@@ -95,6 +95,7 @@ int oracle_set_grid(const double* ULAT_G, const double* HTN_G, const double* HTE
                     const double* DYU_G, const double* DXT_G, const double* DYT_G,
                     const int* KMT_G, const double* dz_in) {
   const int nxb = M.nxb, nyb = M.nyb;
+  M.TLAT = D2ALLOC();
   M.ULAT = D2ALLOC(); M.HTN = D2ALLOC(); M.HTE = D2ALLOC(); M.HUS = D2ALLOC(); M.HUW = D2ALLOC();
   M.DXU = D2ALLOC(); M.DYU = D2ALLOC(); M.DXT = D2ALLOC(); M.DYT = D2ALLOC();
   M.DXUR = D2ALLOC(); M.DYUR = D2ALLOC(); M.DXTR = D2ALLOC(); M.DYTR = D2ALLOC();
@@ -551,7 +552,7 @@ void* oracle_field(const char* name, int tlev) {
   F("DH", M.DH); F("DHU", M.DHU); F("ZX", M.ZX); F("ZY", M.ZY);
   F("KMT", M.KMT); F("KMU", M.KMU); F("KMTN", M.KMTN); F("KMTS", M.KMTS); F("KMTE", M.KMTE);
   F("KMTW", M.KMTW); F("KMTEE", M.KMTEE); F("KMTNN", M.KMTNN);
-  F("ULAT", M.ULAT); F("HTN", M.HTN); F("HTE", M.HTE); F("HUS", M.HUS); F("HUW", M.HUW);
+  F("TLAT", M.TLAT); F("ULAT", M.ULAT); F("HTN", M.HTN); F("HTE", M.HTE); F("HUS", M.HUS); F("HUW", M.HUW);
   F("DXU", M.DXU); F("DYU", M.DYU); F("DXT", M.DXT); F("DYT", M.DYT);
   F("DXUR", M.DXUR); F("DYUR", M.DYUR); F("DXTR", M.DXTR); F("DYTR", M.DYTR);
   F("UAREA", M.UAREA); F("TAREA", M.TAREA); F("UAREA_R", M.UAREA_R); F("TAREA_R", M.TAREA_R);
@@ -576,5 +577,5 @@ void* oracle_field(const char* name, int tlev) {
   F("talfzp", M.talfzp); F("tbetzp", M.tbetzp); F("tgamzp", M.tgamzp);
   F("talfzm", M.talfzm); F("tbetzm", M.tbetzm); F("tdelzm", M.tdelzm);
 #undef F
-  return NULL;
+  return o_gm_field(name);
 }

@@ -530,11 +530,11 @@ void o_hdifft_gm(int k, double* HDTK, const double* TMIX, const double* UMIX, co
 void o_hdifft(int k, double* HDTK, const double* TMIX, const double* UMIX, const double* VMIX,
               int b) {
   double t0 = o_now();
-  (void)UMIX; (void)VMIX;
   memset(HDTK, 0, sizeof(double) * M.n2 * M.nt);
   switch (M.cfg.hmix_tracer_itype) {
     case POP_HMIX_DEL2: hdifft_del2(k, HDTK, TMIX, b); break;
     case POP_HMIX_DEL4: hdifft_del4(k, HDTK, TMIX, b); break;
+    case POP_HMIX_GM: o_hdifft_gm(k, HDTK, TMIX, UMIX, VMIX, b); break;
     default: break;
   }
   M.timer[OT_HDIFFT] += o_now() - t0;

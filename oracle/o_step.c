@@ -15,6 +15,7 @@
 #include "pop_oracle.h"
 
 void* o_alloc_i(size_t n);
+void* o_alloc_d(size_t n);
 #define NXB (M.nxb)
 #define NYB (M.nyb)
 #define NB (M.nblocks)
@@ -153,6 +154,7 @@ static void clinic(int k, double* FX, double* FY, double* WUK, const double* UCU
 int o_baroclinic_driver(void) {
   const int km = M.km, nt = M.nt;
   const int o = M.oldtime, c = M.curtime, n_ = M.newtime, mx = M.mixtime;
+  o_gm_begin_step();
 #pragma omp parallel for schedule(dynamic)
   for (int b = 0; b < NB; b++) {
     double* WTK = tmp2();
@@ -487,8 +489,8 @@ static void o_step_rf(void) {
   const int nonzero_new = !(rn == 0.0);
   const double dz1 = M.dz[1];
   if (!M.rf_ready) { /* init_step :1558-1600 */
-    M.STORE_RF = (double*)calloc(n3t * nt, sizeof(double));
-    M.bgtarea_t_k = (double*)calloc(km + 2, sizeof(double));
+    M.STORE_RF = (double*)o_alloc_d(n3t * nt);
+    M.bgtarea_t_k = (double*)o_alloc_d(km + 2);
     double* mk = (double*)malloc(sizeof(double) * n2t);
     M.rf_volume_2_km = 0.0;
     for (int k = 1; k <= km; k++) {

@@ -38,6 +38,7 @@ typedef struct {
   /* vertical grid (index 0..km+1 where the reference has 0:km) */
   double *dz, *dzw, *dzr, *dz2r, *dzwr, *c2dz, *zt, *zw;
   /* horizontal grid, each [nblocks][nyb][nxb] */
+  double *TLAT; /* T-point latitude (radians): input, only GM reads it (FCORT, grid.F90:1159) */
   double *ULAT, *HTN, *HTE, *HUS, *HUW, *DXU, *DYU, *DXT, *DYT;
   double *DXUR, *DYUR, *DXTR, *DYTR, *UAREA, *TAREA, *UAREA_R, *TAREA_R;
   double *HU, *HUR, *HT, *FCOR, *RCALCT, *RCALCU;
@@ -122,6 +123,12 @@ void oracle_gather(double* glob, const double* src, int nz);
 void oracle_gather_i4(int* glob, const int* src);
 int oracle_distribution_cartesian(int nprocs, int nbx, int nby, const int* work, int* loc);
 int oracle_block_info(int b, int* out8, int* iglob, int* jglob);
+
+/* ---- GM (o_gm.c) ---- */
+void o_gm_reset(void);
+void o_gm_begin_step(void);
+void* o_gm_field(const char* name);
+int o_gm_cancellation(void);
 
 /* ---- grid + init (o_grid.c) ---- */
 int oracle_set_grid(const double* ULAT, const double* HTN, const double* HTE, const double* HUS,

@@ -49,6 +49,7 @@ def horiz_grid(nx, ny, tripole=False, lat0=-78.0, lat1=87.0):
     tlat_deg = lat0 + (j - 0.5) * dlat          # T rows
     one = np.ones((ny, nx))
     ULAT = (ulat_deg * rad)[:, None] * one
+    TLAT = (tlat_deg * rad)[:, None] * one      # only GM reads it (Coriolis parameter at T points)
     HTN = RADIUS * dlon * rad * np.cos(ulat_deg * rad)[:, None] * one
     HTE = RADIUS * dlat * rad * one
     HUS = RADIUS * dlon * rad * np.cos(tlat_deg * rad)[:, None] * one
@@ -60,7 +61,7 @@ def horiz_grid(nx, ny, tripole=False, lat0=-78.0, lat1=87.0):
     if tripole:
         DYU[-1, :] = HTE[-1, :]
     return {k: np.ascontiguousarray(v) for k, v in dict(
-        ULAT=ULAT, HTN=HTN, HTE=HTE, HUS=HUS, HUW=HUW, DXU=DXU, DYU=DYU, DXT=DXT, DYT=DYT).items()}
+        TLAT=TLAT, ULAT=ULAT, HTN=HTN, HTE=HTE, HUS=HUS, HUW=HUW, DXU=DXU, DYU=DYU, DXT=DXT, DYT=DYT).items()}
 
 
 def _lowwave(nx, ny, rng, nmodes=6, periodic_j=False):

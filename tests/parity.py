@@ -71,6 +71,9 @@ def load_oracle(cs, block_size=None):
             o.halo(name, t, loc, kind)
         o.state_all(t)
         o.grad_psurf(t)
+    if cfg.hmix_tracer_itype == c.HMIX_GM:
+        o.scatter("TLAT", 0, cs.grid["TLAT"])
+        o.halo("TLAT", 0, c.LOC_CENTER, c.KIND_SCALAR)
     o.scatter("PGUESS", c.TIME_CUR, cs.state["PSURF_cur"])
     o.halo("PGUESS", c.TIME_CUR, c.LOC_CENTER, c.KIND_SCALAR)
     for name in ("STF", "SMF", "FW", "FW_OLD", "TFW"):
@@ -101,6 +104,9 @@ def load_pop(cs, cfg=None, comm_id=None):
         p.grad(1, p.dptr("GRADPX", t), p.dptr("GRADPY", t), p.dptr("PSURF", t))
         p.halo_field("GRADPX", t, c.LOC_NECORNER, c.KIND_VECTOR)
         p.halo_field("GRADPY", t, c.LOC_NECORNER, c.KIND_VECTOR)
+    if p.cfg.hmix_tracer_itype == c.HMIX_GM:
+        p.scatter("TLAT", 0, cs.grid["TLAT"])
+        p.halo_field("TLAT", 0, c.LOC_CENTER, c.KIND_SCALAR)
     p.scatter("PGUESS", 0, cs.state["PSURF_cur"])
     p.halo_field("PGUESS", 0, c.LOC_CENTER, c.KIND_SCALAR)
     for name in ("STF", "SMF", "FW", "FW_OLD", "TFW"):
