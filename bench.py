@@ -59,6 +59,11 @@ def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
               convergence_criterion=1.0e-13, max_lanczos_step=100, lanczos_convergence_criterion=0.15,
               dtt=dt, rank=rank, nranks=nranks, device=device,
               tadvect=c.TADVECT_CENTERED)
+    if workload == "gx1v7":
+        # BASELINE config 3: GM/Redi tracer mixing (constant kappa 0.8e7, hmix_gm.F90:407-428), Laplacian momentum
+        # mixing (the reference's gx1 anisotropic viscosity is outside SURVEY section 8), KPP-shaped given coefficients, P-CSI
+        kw.update(hmix_tracer_itype=c.HMIX_GM, hmix_momentum_itype=c.HMIX_DEL2, lvariable_hmixt=0, lvariable_hmixu=0,
+                  ah=0.8e7, am=0.6e8)
     if block:
         kw.update(block_size_x=block[0], block_size_y=block[1])
     return c.make_config(**kw), vg
@@ -272,6 +277,9 @@ def run_pop(args):
     grid, dz, kmt, kmu = static_inputs(args.workload)
     p = P.api.Pop(cfg, comm_id)
     p.set_grid(grid, kmt, dz)
+    if cfg.hmix_tracer_itype == c.HMIX_GM:
+        p.scatter("TLAT", 0, grid["TLAT"])
+        p.halo_field("TLAT", 0, c.LOC_CENTER, c.KIND_SCALAR)
     F = Fields(torch, nx, ny, km, dz, kmt, kmu, p.rows(), dev)
     fill_pop(p, F, nt)
     del F
@@ -401,8 +409,11 @@ def run_pop(args):
         "value": cells * K / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (seeded analytic fields + hash noise, synthetic bathymetry)",
-        "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt del4(variable) given-KPP-shaped-vmix "
-                               "PCSI/diagonal 1e-13 dt=%gs full-cells, 1x%d j-strips" % (args.workload, nx, ny, km, nt, cfg.dtt, world),
+        "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt %s given-KPP-shaped-vmix "
+                               "PCSI/diagonal 1e-13 dt=%gs full-cells, 1x%d j-strips"
+                               % (args.workload, nx, ny, km, nt,
+                                  "GM(const kappa, notanh)+del2u" if cfg.hmix_tracer_itype == c.HMIX_GM else "del4(variable)",
+                                  cfg.dtt, world),
                    "l2": "inputs larger than L2 (state is %.0f GB; no explicit flush)" % (cells * 8 * (3 * nt + 9 + 3) / 1e9),
                    "solver_iterations_per_step": iters, "ocean_cell_updates_per_s": ocean * K / (ms * 1e-3)},
         "roofline": roof,
@@ -429,6 +440,9 @@ def oracle_setup(sample, nt):
     grid, dz, kmt, kmu = static_inputs(sample)
     o = O.Oracle(cfg)
     o.set_grid(grid, kmt, dz)
+    if cfg.hmix_tracer_itype == c.HMIX_GM:
+        o.scatter("TLAT", 0, grid["TLAT"])
+        o.halo("TLAT", 0, c.LOC_CENTER, c.KIND_SCALAR)
     F = Fields(np, nx, ny, km, dz, kmt, kmu, slice(0, ny))
     for lev, t in (("cur", c.TIME_CUR), ("old", c.TIME_OLD)):
         T = np.stack([np.stack([F.tracer(n, k, lev) for k in range(1, km + 1)]) for n in range(nt)])
@@ -454,7 +468,7 @@ def oracle_setup(sample, nt):
 def cpu_baseline(args, steps):
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    sample = "tiny" if args.workload == "tiny" else "tx_sample"
+    sample = args.workload if args.workload in ("tiny", "gx1v7") else "tx_sample"
     o, cells = oracle_setup(sample, args.nt)
     assert o.step(c.TS_EULER) == 0
     t0 = time.perf_counter()
@@ -474,7 +488,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    sample = "tiny" if args.workload == "tiny" else "tx_sample"
+    sample = args.workload if args.workload in ("tiny", "gx1v7") else "tx_sample"
     o, cells = oracle_setup(sample, args.nt)
     W, K = max(args.warmup, 1), args.steps
     W, K = min(W, 2), min(K, 5)     # bounded: ~6 s per step on 8 cores
@@ -487,11 +501,13 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     nx, ny, km = WORKLOADS[sample][:3]
     val = cells * K / dt
-    desc = ("%d leapfrog steps of the tx0.1v3 configuration on a %dx%dx%d sub-grid, all host cores (OpenMP over 60x40 "
-            "blocks)" % (K, nx, ny, km))
+    desc = ("%d leapfrog steps of the %s configuration on a %dx%dx%d %s, all host cores (OpenMP over 60x40 "
+            "blocks)" % (K, args.workload, nx, ny, km, "grid" if sample == args.workload else "sub-grid"))
     cfg, _ = make_cfg(args.workload, args.nt)
     print(json.dumps({
-        "impl": "reference", "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)",
+        "impl": "reference",
+        "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)" if args.workload == "tx0.1v3"
+                  else "cell-updates/s, full baroclinic+barotropic step",
         "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (same seeded fields as the GPU arm)",

@@ -64,7 +64,8 @@ typedef struct pop_config {
   double ah, am;
   int lvariable_hmixt, lvariable_hmixu;
   int lauto_hmixt, lauto_hmixu;
-  /* hmix_gm_nml (constant kappa, notanh slope control) */
+  /* hmix_gm_nml (hmix_gm.F90:407-428): constant kappa_isop (ah_gm) / kappa_thic (ah_bolus), slope_control 'notanh',
+     use_const_ah_bkg_srfbl = .true., ah_bkg_bottom = 0, transition_layer_on = .false.; needs the field "TLAT" */
   double ah_gm, ah_bolus, ah_bkg_srfbl, slm_r, slm_b;
   /* vertical_mix_nml */
   int vmix_itype, implicit_vertical_mix;

@@ -123,9 +123,15 @@ static int find_field(const char* what, const char* name, int tlev, DevField** f
   *f = &G.fields[key];
   return POP_SUCCESS;
 }
+// caller-supplied inputs that GM caches (pop_gm.cu)
+static void note_field_written(const char* name) {
+  if (!strcmp(name, "TLAT")) G.gm_dirty = true;
+  if (!strcmp(name, "VDC")) G.gm_vdc_dirty = true;
+}
 extern "C" int pop_set_field(const char* name, int tlev, const void* host) {
   DevField* f;
   POP_TRY(find_field("pop_set_field", name, tlev, &f));
+  note_field_written(name);
   POP_REQUIRE(host != nullptr, "pop_set_field: null host pointer");
   POP_CHECK_CUDA(cudaMemcpyAsync(f->p, host, f->elems * (f->is_int ? sizeof(int) : sizeof(double)), cudaMemcpyHostToDevice, G.stream));
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
@@ -156,6 +162,7 @@ static int strip_copy(DevField* f, void* host, bool to_device, int z0, int nz) {
 extern "C" int pop_scatter_field(const char* name, int tlev, const void* host_strip) {
   DevField* f;
   POP_TRY(find_field("pop_scatter_field", name, tlev, &f));
+  note_field_written(name);
   POP_REQUIRE(host_strip != nullptr, "pop_scatter_field: null host pointer");
   POP_TRY(strip_copy(f, (void*)host_strip, true, 0, f->nz));
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
@@ -164,6 +171,7 @@ extern "C" int pop_scatter_field(const char* name, int tlev, const void* host_st
 extern "C" int pop_scatter_field_levels(const char* name, int tlev, int z0, int nz, const void* strip) {
   DevField* f;
   POP_TRY(find_field("pop_scatter_field_levels", name, tlev, &f));
+  note_field_written(name);
   POP_REQUIRE(strip != nullptr && z0 >= 0 && nz >= 1 && z0 + nz <= f->nz,
               "pop_scatter_field_levels: bad level range %d..%d of %d", z0, z0 + nz - 1, f->nz);
   POP_TRY(strip_copy(f, (void*)strip, true, z0, nz));
@@ -227,6 +235,16 @@ extern "C" int pop_hdifft(int k, double* HDTK, const double* TMIX, const double*
   io.TCUR = io.TMIX;
   io.TOLD = io.TMIX;
   io.TNEW = s.inout("h_hdtk", HDTK, G.n2 * G.nt, false);
+  if (s.ok && G.cfg.hmix_tracer_itype == POP_HMIX_GM) {
+    // hdifft_gm must be called with k = 1,2,3,...: the k == 1 call does the work of every level (slopes,
+    // diffusivities, VDC += VDC_GM, tendency), later calls hand out their level (hmix_gm.F90:1109)
+    POP_REQUIRE(k >= 1 && k <= G.km, "hdifft: k=%d out of range", k);
+    if (k == 1) POP_TRY(gm_tendency_dev(io.TMIX));
+    for (int n = 0; n < G.nt; n++)
+      POP_CHECK_CUDA(cudaMemcpyAsync(io.TNEW + (size_t)n * G.n2, fld("GM_HDT") + ((size_t)n * G.km + (k - 1)) * G.n2,
+                                     sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+    return s.finish(POP_SUCCESS);
+  }
   return s.finish(s.ok ? tracer_column(TR_HDIFFT, k, io) : POP_FAIL);
 }
 

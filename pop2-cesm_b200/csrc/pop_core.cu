@@ -204,6 +204,7 @@ static int alloc_all_fields() {
   POP_TRY(alloc_field("VVC", G.vvc_nk, false));
   // work: Thomas E coefficients; momentum Thomas E
   POP_TRY(alloc_field("WORK3D_E", km, false));
+  if (c.hmix_tracer_itype == POP_HMIX_GM) POP_TRY(gm_alloc_fields());
   return POP_SUCCESS;
 }
 
@@ -293,8 +294,11 @@ extern "C" int pop_init(const pop_config* cfg) {
     else if (cfg->tadvect_itype[n] == POP_TADVECT_CENTERED) G.use_centered = true;
     else POP_REQUIRE(false, "pop_init: tadvect_itype[%d]=%d not supported", n, cfg->tadvect_itype[n]);
   }
-  POP_REQUIRE(cfg->hmix_tracer_itype == POP_HMIX_DEL2 || cfg->hmix_tracer_itype == POP_HMIX_DEL4,
-              "pop_init: hmix_tracer_itype=%d not supported (del2, del4)", cfg->hmix_tracer_itype);
+  POP_REQUIRE(cfg->hmix_tracer_itype == POP_HMIX_DEL2 || cfg->hmix_tracer_itype == POP_HMIX_DEL4 ||
+                  cfg->hmix_tracer_itype == POP_HMIX_GM,
+              "pop_init: hmix_tracer_itype=%d not supported (del2, del4, gm)", cfg->hmix_tracer_itype);
+  POP_REQUIRE(cfg->hmix_tracer_itype != POP_HMIX_GM || cfg->implicit_vertical_mix,
+              "pop_init: implicit vertical mixing must be used with GM horiz mixing (hmix_gm.F90:1192-1194)");
   POP_REQUIRE(cfg->hmix_momentum_itype == POP_HMIX_DEL2 || cfg->hmix_momentum_itype == POP_HMIX_DEL4,
               "pop_init: hmix_momentum_itype=%d not supported", cfg->hmix_momentum_itype);
   POP_REQUIRE(cfg->vmix_itype == POP_VMIX_CONST || cfg->vmix_itype == POP_VMIX_GIVEN ||

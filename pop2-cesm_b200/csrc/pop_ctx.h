@@ -80,6 +80,8 @@ struct Ctx {
   double rf_volume_2_km = 0, rf_bgtarea1 = 0;
   double rf_S_prev[POP_MAX_NT] = {0};
   bool rf_S_prev_valid[POP_MAX_NT] = {false};
+  // GM (pop_gm.cu): RBR/metric ratios need rebuilding (TLAT or the grid changed); VDC_BASE needs re-saving
+  bool gm_dirty = true, gm_vdc_dirty = true, gm_force_general = false;
   // hmix / misc scalars
   double ah = 0, am = 0, uarea_equator = 0;
   int vdc_nk = 0, vdc_k0 = 1, vdc_nd = 1, vvc_nk = 0;
@@ -232,6 +234,10 @@ int reduce_reserve_partials(int nblocks);  // sizes G.d_partials_big for POP_RED
 int state_slab(int k, int kk, const double* T, const double* S, double* RHOOUT, double* RHOFULL,
                double* DRHODT, double* DRHODS, size_t n);
 int state_3d(const double* TRACER, double* RHO);
+// GM (pop_gm.cu)
+int gm_alloc_fields();
+int gm_begin_step();
+int gm_tendency_dev(const double* TMIX);  // fills the field GM_HDT (nxb,nyb,km,nt), adds VDC_GM to VDC
 // tracer path (pop_tracer.cu)
 enum { TR_FULL = 0, TR_ADVT = 1, TR_HDIFFT = 2, TR_VDIFFT = 3 };
 struct TracerIO {

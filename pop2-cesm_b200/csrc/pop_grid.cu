@@ -447,6 +447,7 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   }
   G.grid_set = true;
   G.rf_ready = false;  // budget areas depend on KMT/TAREA
+  G.gm_dirty = true;
   POP_TRY(set_timestep(POP_TS_LEAPFROG));
   POP_TRY(upload_vert_const());
   POP_TRY(solvers_init_dev());

@@ -53,6 +53,7 @@ int baroclinic_driver_dev(bool defer_finish) {
   const int o = G.oldtime, c = G.curtime, n_ = G.newtime, mx = G.mixtime;
   const bool pavg = G.cfg.lpressure_avg && G.leapfrogts;
   const bool varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
+  POP_TRY(gm_begin_step());
   POP_TRY(vmix_coeffs_dev(1, G.km, fld_t("TRACER", mx), fld_t("UVEL", mx), fld_t("VVEL", mx), fld_t("RHO", mx)));
   {
     ScopedTimer t2("TRACER_UPDATE");

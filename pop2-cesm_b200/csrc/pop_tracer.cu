@@ -26,6 +26,7 @@ struct TracerArgs {
   double* OUT;   // FULL: TRACER(new) (nxb,nyb,km,nt); slab modes: (nxb,nyb,nt)
   double* WTK;   // slab modes: carried vertical velocity at the top of level k (in/out)
   double *VTF, *AUX;  // slab modes: carried fluxes (nxb,nyb,nt)
+  const double* HDT;  // GM: precomputed horizontal-mixing tendency (nxb,nyb,km,nt), pop_gm.cu; else null
   int k0, k1;    // level range (1-based, inclusive)
   int n0, nn;    // tracers n0 .. n0+nn-1 (0-based)
   int adv[NTC];  // advection scheme of each tracer of this pass
@@ -266,7 +267,8 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       // ---- horizontal mixing
       double hd = 0.0;
       if (DO_HMIX) {
-        if (DEL4) hd = a.ah * lap5(cc5, s_d2 + m * POP_TN, tx, ty);
+        if (a.HDT) hd = a.HDT[lev];
+        else if (DEL4) hd = a.ah * lap5(cc5, s_d2 + m * POP_TN, tx, ty);
         else {
           hd = a.ah * lap5(cc5, s_tm + m * POP_TN, tx, ty);
         }
@@ -729,6 +731,12 @@ int tracer_column(int mode, int k, const TracerIO& io) {
   a.VTF = fld("VTF");
   a.AUX = fld("AUX");
   a.hmix = G.cfg.hmix_tracer_itype;
+  const bool gm = (a.hmix == POP_HMIX_GM);
+  if (gm) {
+    POP_REQUIRE(mode == TR_FULL, "tracer_column: GM tendencies come from gm_tendency_dev");
+    POP_TRY(gm_tendency_dev(io.TMIX));  // hdifft_gm for every level; also VDC += VDC_GM before the column kernel reads VDC
+    a.HDT = fld("GM_HDT");
+  }
   a.lvariable_hmixt = G.cfg.lvariable_hmixt;
   a.varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
   a.implicit_vmix = G.cfg.implicit_vertical_mix;
@@ -751,7 +759,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
     switch (mode) {
       case TR_FULL: {
         // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
-        const bool fast_ok = !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+        const bool fast_ok = !gm && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
                              a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
         if (fast_ok) {
           TracerFastArgs f;

@@ -44,6 +44,9 @@ def main():
         kw.update(convergence_criterion=1e-12)
     elif which == "cyclic_pcg":
         kw.update(ns=c.BNDY_CYCLIC, solver_choice=c.SOLVER_PCG, tadvect=c.TADVECT_UPWIND3, nt=3)
+    elif which == "gm":
+        kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM, ah_bolus=0.5e7, slm_b=0.2, given_vmix=True, nt=3,
+                  solver_choice=c.SOLVER_PCSI, dtt=1800.0)
     cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
     steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG, c.TS_ROBERT]
     ref = None

@@ -15,7 +15,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("which", ["pcsi", "chrongear", "cyclic_pcg"])
+@pytest.mark.parametrize("which", ["pcsi", "chrongear", "cyclic_pcg", "gm"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_strips_are_bitwise_the_single_strip_run(which, world):
     if _ngpu() < world:

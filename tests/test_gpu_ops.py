@@ -34,6 +34,11 @@ def get_case(key):
     if key == "del2":
         cs = make_case(40, 28, 7, nt=3, seed=11, given_vmix=True,
                        tadvect=[c.TADVECT_CENTERED, c.TADVECT_UPWIND3, c.TADVECT_CENTERED])
+    elif key == "gm":          # gx1v7 flavour: GM with the terms that cancel dropped (ah == ah_bolus)
+        cs = make_case(40, 28, 7, nt=3, seed=13, hmix_tracer_itype=c.HMIX_GM, given_vmix=True)
+    elif key == "gm_general":  # general skew-flux form: different thickness diffusivity and slope limits
+        cs = make_case(36, 24, 6, nt=3, seed=14, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM,
+                       ah_gm=0.6e7, ah_bolus=0.4e7, ah_bkg_srfbl=0.5e7, slm_r=0.3, slm_b=0.2)
     else:
         cs = make_case(36, 24, 6, nt=2, seed=12, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
                        hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21,
@@ -116,6 +121,32 @@ def test_hdifft_advt_vdifft(which):
         p.vdifft(k, vq, To, STF)
         assert np.array_equal(phys(vo), phys(vq)), ("vdifft", k)
     assert np.abs(phys(lo)).max() >= 0.0 and np.abs(phys(ho)).max() > 0.0
+
+
+@pytest.mark.parametrize("which", ["gm", "gm_general"])
+def test_hdifft_gm_slabs_and_vdc_side_effect(which):
+    """hdifft with hmix_tracer_itype = GM (hmix_gm.F90:1102-2219 after tracer_diffs_and_isopyc_slopes), called
+    k = 1,2,3,... like the reference: every level's tendency and the VDC the calls leave behind are bit-exact."""
+    cs, o, p = get_case(which)
+    To = fields(o, c.TIME_OLD)[0]
+    nt, km = o.nt, o.km
+    f_h = osig(o.L, "o_hdifft", [ci, vp, vp, vp, vp, ci])
+    shape = o.inner_shape("VDC")
+    v0 = o.view("VDC", 0, shape)[0].copy()
+    assert np.array_equal(v0, p.get_padded("VDC", 0).reshape(v0.shape))
+    big = 0.0
+    for k in range(1, km + 1):
+        ho, hp = np.zeros((nt, o.nyb, o.nxb)), np.zeros((nt, o.nyb, o.nxb))
+        f_h(k, op(ho), op(To), None, None, 0)
+        p.hdifft(k, hp, To)
+        assert np.array_equal(phys(ho), phys(hp)), ("hdifft_gm", k)
+        big = max(big, np.abs(phys(ho)).max())
+    assert big > 0.0
+    v1o, v1p = o.view("VDC", 0, shape)[0], p.get_padded("VDC", 0).reshape(v0.shape)
+    assert np.array_equal(phys(v1o), phys(v1p))
+    assert (phys(v1o) - phys(v0)).max() > 0.0                   # VDC_GM was added
+    o.view("VDC", 0, shape)[0][...] = v0                        # leave the case as it was found
+    p.set_padded("VDC", 0, v0)
 
 
 @pytest.mark.parametrize("which", ["del2", "del4"])

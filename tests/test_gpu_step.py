@@ -46,6 +46,13 @@ CASES = {
                      convergence_criterion=1e-12),
     "rich_noconv_chrongear": dict(nx=40, ny=32, km=7, seed=26, vmix_itype=c.VMIX_RICH, convection_diff=0,
                                   convergence_criterion=1e-12),
+    # gx1v7 flavour (BASELINE config 3): GM/Redi tracer mixing, KPP-shaped given coefficients, P-CSI, extra tracer
+    "gm_pcsi": dict(nx=48, ny=36, km=8, nt=3, seed=27, hmix_tracer_itype=c.HMIX_GM, given_vmix=True,
+                    solver_choice=c.SOLVER_PCSI, dtt=1800.0),
+    # GM in its general skew-flux form (ah_bolus != ah, slm_b != slm_r) on the tripole grid, convective diffusion
+    "gm_general_tripole": dict(nx=40, ny=32, km=7, nt=2, seed=28, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM,
+                               ah_gm=0.6e7, ah_bolus=0.4e7, ah_bkg_srfbl=0.5e7, slm_b=0.2,
+                               convergence_criterion=1e-12),
     # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
     "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
                              lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),
