@@ -7,12 +7,14 @@
 //
 // The reference keeps TX/TY/TZ, RX/RY, SLX/SLY, SF_SLX/SF_SLY, KAPPA_ISOP/KAPPA_THIC/HOR_DIFF as block arrays
 // (about 26*km + 3*km*nt 2-d fields) that every k pass re-reads. Here two kernels do the work:
-//   gm_column_kernel  one thread per column (physical cells + the first ghost ring) marches k once: density
-//                     gradients, the eight quarter-cell slopes of each level, tapers and diffusivities, and the
-//                     VDC side effect (VDC += VDC_GM); only slopes (8/level) and diffusivities (4-6/level) reach HBM
-//   gm_flux_kernel    one thread per (physical column, tracer) marches k with FZTOP in a register: tracer
-//                     differences are rebuilt from TMIX, face fluxes FX/FY and the vertical flux are formed and
+//   gm_column_kernel  one thread per (column, level) over the physical cells + the first ghost ring: density
+//                     gradients, the quarter-cell slopes either side of the interface below the level, tapers and
+//                     diffusivities, and the VDC side effect (VDC += VDC_GM); only slopes (8/level) and
+//                     diffusivities (4-6/level) reach HBM
+//   gm_flux_kernel    one thread per (physical column, level), tracers looped inside: tracer differences are rebuilt from TMIX,
+//                     face fluxes FX/FY and the vertical fluxes through the top and bottom faces are formed and
 //                     differenced in registers; only the tendency GTK reaches HBM
+// Nothing is carried between levels (FZTOP is re-evaluated where it is needed), so all levels run in parallel.
 // Every expression keeps the reference's operand order (-fmad=false), so the tendency is bit-identical to the
 // oracle's slab-by-slab restatement.
 #include <cmath>
@@ -109,168 +111,210 @@ __device__ __forceinline__ void gm_level(const GmArgs& a, size_t q, int kk, int 
   L->salt = s0;
 }
 
-__global__ void __launch_bounds__(128) gm_column_kernel(const GmArgs a) {
+// One thread per (column, level): nothing is carried from level to level (each interface needs the density
+// differences of its two levels only), so the km levels of a column run in parallel -- a gx1v7-sized strip has
+// only 1.2e5 columns, far too few to fill 148 SMs with one thread per column. Thread (q, kk) owns the interface
+// below level kk: the bottom half of level kk, the top half of level kk+1 and VDC_GM(kk); it evaluates the level
+// differences of kk and kk+1 (the EOS derivatives of a level are thus evaluated twice, by threads kk-1 and kk).
+__global__ void __launch_bounds__(128, 8) gm_column_kernel(const GmArgs a) {
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;  // 0-based, first ghost ring included
   const int j = 1 + blockIdx.y;
+  const int kk = 1 + blockIdx.z;
   const GridView& g = a.g;
   if (i > g.nxb - 2 || j > g.nyb - 2) return;
   const size_t n2 = g.n2, nxb = g.nxb, q = (size_t)j * nxb + i;
   const int km = g.km;
   const int kmt = g.KMT[q], kmte = g.KMT[q + 1], kmtw = g.KMT[q - 1], kmtn = g.KMT[q + nxb], kmts = g.KMT[q - nxb];
   const double rbr = a.RBR[q], dxt = a.DXT[q], dyt = a.DYT[q];
-  const double hyx = a.HYX[q], hyxw = a.HYX[q - 1], hxy = a.HXY[q], hxys = a.HXY[q - nxb];
-  const double tarea_r = g.TAREA_R[q];
-  GmLevel L;
-  gm_level(a, q, 1, kmt, kmte, kmtw, kmtn, kmts, &L);
   double s[4] = {0.0, 0.0, 0.0, 0.0};
-  gm_half(a, q, KTP, 1, kmt, s, rbr, dxt, dyt);  // the top half of level 1 has no slopes
-  for (int kk = 1; kk <= km; kk++) {
-    if (kk < km) {
-      const double KMASK = (kk < kmt) ? 1.0 : 0.0;
-      const double tdn = a.TMIX[(size_t)kk * n2 + q];
-      const double tempn = (-2.0 > tdn) ? -2.0 : tdn;
-      const double tz2 = L.salt - a.TMIX[((size_t)km + kk) * n2 + q];
-      const double tzp = L.temp - tempn;
-      double rz = L.drdt * tzp + L.drds * tz2;  // :302-303
-      rz = (rz < -GM_EPS2) ? rz : -GM_EPS2;
+  if (kk == 1) gm_half(a, q, KTP, 1, kmt, s, rbr, dxt, dyt);  // the top half of level 1 has no slopes
+  if (kk == km) {                                             // nor has the bottom half of level km
+    gm_half(a, q, KBT, km, kmt, s, rbr, dxt, dyt);
+    return;
+  }
+  const double hyx = a.HYX[q], hyxw = a.HYX[q - 1], hxy = a.HXY[q], hxys = a.HXY[q - nxb];
+  GmLevel L;
+  gm_level(a, q, kk, kmt, kmte, kmtw, kmtn, kmts, &L);
+  const double KMASK = (kk < kmt) ? 1.0 : 0.0;
+  const double tdn = a.TMIX[(size_t)kk * n2 + q];
+  const double tempn = (-2.0 > tdn) ? -2.0 : tdn;
+  const double tz2 = L.salt - a.TMIX[((size_t)km + kk) * n2 + q];
+  const double tzp = L.temp - tempn;
+  double rz = L.drdt * tzp + L.drds * tz2;  // :302-303
+  rz = (rz < -GM_EPS2) ? rz : -GM_EPS2;
 #pragma unroll
-      for (int d = 0; d < 4; d++) s[d] = KMASK * L.rx[d] / rz;
-      const double kib = gm_half(a, q, KBT, kk, kmt, s, rbr, dxt, dyt);
-      const double vb = hyx * (s[XE] * s[XE]) + hyxw * (s[XW] * s[XW]) + hxy * (s[YN] * s[YN]) + hxys * (s[YS] * s[YS]);
-      gm_level(a, q, kk + 1, kmt, kmte, kmtw, kmtn, kmts, &L);
-      double rz1 = L.drdt * tzp + L.drds * tz2;  // :388-390
-      rz1 = (rz1 < -GM_EPS2) ? rz1 : -GM_EPS2;
+  for (int d = 0; d < 4; d++) s[d] = KMASK * L.rx[d] / rz;
+  const double kib = gm_half(a, q, KBT, kk, kmt, s, rbr, dxt, dyt);
+  const double vb = hyx * (s[XE] * s[XE]) + hyxw * (s[XW] * s[XW]) + hxy * (s[YN] * s[YN]) + hxys * (s[YS] * s[YS]);
+  gm_level(a, q, kk + 1, kmt, kmte, kmtw, kmtn, kmts, &L);
+  double rz1 = L.drdt * tzp + L.drds * tz2;  // :388-390
+  rz1 = (rz1 < -GM_EPS2) ? rz1 : -GM_EPS2;
 #pragma unroll
-      for (int d = 0; d < 4; d++) s[d] = (kk + 1 <= kmt) ? L.rx[d] / rz1 : 0.0;
-      const double kit = gm_half(a, q, KTP, kk + 1, kmt, s, rbr, dxt, dyt);
-      const double vt = hyx * (s[XE] * s[XE]) + hyxw * (s[XW] * s[XW]) + hxy * (s[YN] * s[YN]) + hxys * (s[YS] * s[YS]);
-      // effective vertical diffusion coefficient, VDC += VDC_GM (:1725-1743)
-      const double W = c_vc.dzw[kk] * KMASK * tarea_r *
-                       (c_vc.dz[kk] * 0.25 * kib * vb + c_vc.dz[kk + 1] * 0.25 * kit * vt);
-      for (int n = 0; n < g.vdc_nd; n++) {
-        double* v = a.VDC + ((size_t)n * g.vdc_nk + (kk - g.vdc_k0)) * n2 + q;
-        *v = *v + W;
-      }
-    } else {
-      s[0] = s[1] = s[2] = s[3] = 0.0;
-      gm_half(a, q, KBT, km, kmt, s, rbr, dxt, dyt);
-    }
+  for (int d = 0; d < 4; d++) s[d] = (kk + 1 <= kmt) ? L.rx[d] / rz1 : 0.0;
+  const double kit = gm_half(a, q, KTP, kk + 1, kmt, s, rbr, dxt, dyt);
+  const double vt = hyx * (s[XE] * s[XE]) + hyxw * (s[XW] * s[XW]) + hxy * (s[YN] * s[YN]) + hxys * (s[YS] * s[YS]);
+  // effective vertical diffusion coefficient, VDC += VDC_GM (:1725-1743)
+  const double W = c_vc.dzw[kk] * KMASK * g.TAREA_R[q] *
+                   (c_vc.dz[kk] * 0.25 * kib * vb + c_vc.dz[kk + 1] * 0.25 * kit * vt);
+  for (int n = 0; n < g.vdc_nd; n++) {
+    double* v = a.VDC + ((size_t)n * g.vdc_nk + (kk - g.vdc_k0)) * n2 + q;
+    *v = *v + W;
   }
 }
 
-// flux through the face between cell qa and its east (stride 1) / north (stride nxb) neighbour qb at level k,
-// tracer n: FX or FY of hdifft_gm (:1765-1896). da/db: slope direction stored at qa (east/north) and qb (west/south).
-__device__ __forceinline__ double gm_face(const GmArgs& a, const double* Tn, size_t qa, size_t qb, int da, int db,
-                                          double H, int k, int kp1) {
-  const size_t n2 = a.g.n2;
+// ---- face fluxes FX / FY of hdifft_gm (:1765-1896). The diffusivity sums and the skew coefficients of a face
+// do not depend on the tracer: they are formed once per (column, level) and applied to every tracer.
+struct GmFace {
+  double C, m, W;          // CX or CY, its 0/1 mask, the eight-term diffusivity sum WORK3 / WORK4
+  double W1, W2, W3, W4;   // general form only: KAPPA_ISOP*slope*dz - SF_slope at (qa,top) (qa,bottom) (qb,top) (qb,bottom)
+};
+// face between cell qa and its east (qb = qa+1) / north (qb = qa+nxb) neighbour; da/db: slope direction stored
+// at qa (east/north) and at qb (west/south)
+template <bool CANCEL>
+__device__ __forceinline__ GmFace gm_face_coef(const GmArgs& a, size_t qa, size_t qb, int da, int db, double H, int k) {
+  GmFace f;
   const int ka = a.g.KMT[qa], kb = a.g.KMT[qb];
   const bool open = (k <= ka && k <= kb);
-  const double C = open ? H * 0.25 : 0.0;
-  const double m = open ? 1.0 : 0.0;
+  f.C = open ? H * 0.25 : 0.0;
+  f.m = open ? 1.0 : 0.0;
   const size_t ot = k2_ix(a, KTP, k), ob = k2_ix(a, KBT, k);
-  const double W = a.KI[ot + qa] + a.HD[ot + qa] + a.KI[ob + qa] + a.HD[ob + qa] + a.KI[ot + qb] + a.HD[ot + qb] +
-                   a.KI[ob + qb] + a.HD[ob + qb];
-  const double* Tk = Tn + (size_t)(k - 1) * n2;
-  const double tx = m * (Tk[qb] - Tk[qa]);
-  double F = c_vc.dz[k] * C * tx * W;
-  if (!a.cancel) {
+  const double kiat = a.KI[ot + qa], kiab = a.KI[ob + qa], kibt = a.KI[ot + qb], kibb = a.KI[ob + qb];
+  f.W = kiat + a.HD[ot + qa] + kiab + a.HD[ob + qa] + kibt + a.HD[ot + qb] + kibb + a.HD[ob + qb];
+  f.W1 = f.W2 = f.W3 = f.W4 = 0.0;
+  if (!CANCEL) {
     const double dzk = c_vc.dz[k];
-    const double sfat = (k <= ka) ? a.KT[ot + qa] * a.SL[sl_ix(a, da, KTP, k) + qa] * dzk : 0.0;
-    const double sfab = (k <= ka) ? a.KT[ob + qa] * a.SL[sl_ix(a, da, KBT, k) + qa] * dzk : 0.0;
-    const double sfbt = (k <= kb) ? a.KT[ot + qb] * a.SL[sl_ix(a, db, KTP, k) + qb] * dzk : 0.0;
-    const double sfbb = (k <= kb) ? a.KT[ob + qb] * a.SL[sl_ix(a, db, KBT, k) + qb] * dzk : 0.0;
-    const double W1 = a.KI[ot + qa] * a.SL[sl_ix(a, da, KTP, k) + qa] * dzk - sfat;
-    const double W2 = a.KI[ob + qa] * a.SL[sl_ix(a, da, KBT, k) + qa] * dzk - sfab;
-    const double W3 = a.KI[ot + qb] * a.SL[sl_ix(a, db, KTP, k) + qb] * dzk - sfbt;
-    const double W4 = a.KI[ob + qb] * a.SL[sl_ix(a, db, KBT, k) + qb] * dzk - sfbb;
+    const double sat = a.SL[sl_ix(a, da, KTP, k) + qa], sab = a.SL[sl_ix(a, da, KBT, k) + qa];
+    const double sbt = a.SL[sl_ix(a, db, KTP, k) + qb], sbb = a.SL[sl_ix(a, db, KBT, k) + qb];
+    const double sfat = (k <= ka) ? a.KT[ot + qa] * sat * dzk : 0.0;  // SF_SLX / SF_SLY (:1682-1700)
+    const double sfab = (k <= ka) ? a.KT[ob + qa] * sab * dzk : 0.0;
+    const double sfbt = (k <= kb) ? a.KT[ot + qb] * sbt * dzk : 0.0;
+    const double sfbb = (k <= kb) ? a.KT[ob + qb] * sbb * dzk : 0.0;
+    f.W1 = kiat * sat * dzk - sfat;
+    f.W2 = kiab * sab * dzk - sfab;
+    f.W3 = kibt * sbt * dzk - sfbt;
+    f.W4 = kibb * sbb * dzk - sfbb;
+  }
+  return f;
+}
+template <bool CANCEL>
+__device__ __forceinline__ double gm_face_flux(const GmArgs& a, const GmFace& f, const double* Tn, size_t qa, size_t qb,
+                                               int k, int kp1) {
+  const size_t n2 = a.g.n2;
+  const double* Tk = Tn + (size_t)(k - 1) * n2;
+  const double tx = f.m * (Tk[qb] - Tk[qa]);
+  double F = c_vc.dz[k] * f.C * tx * f.W;
+  if (!CANCEL) {
     // TZ(:,:,k) = TMIX(k-1) - TMIX(k), zero at k = 1 (hmix_gm_submeso_share.F90:296-297, hmix_gm.F90:1849-1850)
     const double* Tm = Tk - n2;
     const double* Tp = Tn + (size_t)(kp1 - 1) * n2;
     const double tza = (k >= 2) ? Tm[qa] - Tk[qa] : 0.0, tzb = (k >= 2) ? Tm[qb] - Tk[qb] : 0.0;
     const double tzpa = (kp1 >= 2) ? (Tp - n2)[qa] - Tp[qa] : 0.0, tzpb = (kp1 >= 2) ? (Tp - n2)[qb] - Tp[qb] : 0.0;
-    F = F - C * (W1 * tza + W2 * tzpa + W3 * tzb + W4 * tzpb);
+    F = F - f.C * (f.W1 * tza + f.W2 * tzpa + f.W3 * tzb + f.W4 * tzpb);
   }
   return F;
 }
 
-__global__ void __launch_bounds__(128) gm_flux_kernel(const GmArgs a) {
+// ---- vertical flux through the bottom face of level k < km (:1911-2040): tracer-independent part ...
+struct GmFz {
+  double KMASK, kib, kit1, sb[4], st[4], fb[4], ft[4];
+};
+template <bool CANCEL>
+__device__ __forceinline__ GmFz gm_fz_coef(const GmArgs& a, size_t q, int k, int kmt) {
+  GmFz c;
+  const int kp1 = k + 1;
+  c.KMASK = (k < kmt) ? 1.0 : 0.0;
+  const size_t ob = k2_ix(a, KBT, k) + q, ot1 = k2_ix(a, KTP, kp1) + q;
+  c.kib = a.KI[ob];
+  c.kit1 = a.KI[ot1];
+#pragma unroll
+  for (int d = 0; d < 4; d++) {
+    c.sb[d] = a.SL[sl_ix(a, d, KBT, k) + q];
+    c.st[d] = a.SL[sl_ix(a, d, KTP, kp1) + q];
+    c.fb[d] = c.ft[d] = 0.0;
+  }
+  if (!CANCEL) {
+    const double ktb = a.KT[ob], ktt1 = a.KT[ot1];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      c.fb[d] = (k <= kmt) ? ktb * c.sb[d] * c_vc.dz[k] : 0.0;
+      c.ft[d] = (kp1 <= kmt) ? ktt1 * c.st[d] * c_vc.dz[kp1] : 0.0;
+    }
+  }
+  return c;
+}
+// ... and its application to the tracer differences t0 (level k) and t1 (level k+1), ordered TX(i), TX(i-1), TY(j), TY(j-1)
+template <bool CANCEL>
+__device__ __forceinline__ double gm_fz_eval(const GmArgs& a, const GmFz& c, int k, const double* t0, const double* t1,
+                                             double hyx, double hyxw, double hxy, double hxys) {
+  const double dz_bottom = c_vc.dz[k + 1];
+  if (!CANCEL) {  // :1917-1986
+    double w3 = 0.0;
+    w3 = w3 + (c_vc.dz[k] * c.kib *
+               (c.sb[XE] * hyx * t0[XE] + c.sb[YN] * hxy * t0[YN] + c.sb[XW] * hyxw * t0[XW] + c.sb[YS] * hxys * t0[YS]));
+    w3 = w3 + (c.fb[XE] * hyx * t0[XE] + c.fb[YN] * hxy * t0[YN] + c.fb[XW] * hyxw * t0[XW] + c.fb[YS] * hxys * t0[YS]);
+    w3 = w3 + (dz_bottom * c.kit1 *
+               (c.st[XE] * hyx * t1[XE] + c.st[YN] * hxy * t1[YN] + c.st[XW] * hyxw * t1[XW] + c.st[YS] * hxys * t1[YS]));
+    w3 = w3 + (1.0 * (c.ft[XE] * hyx * t1[XE] + c.ft[YN] * hxy * t1[YN] + c.ft[XW] * hyxw * t1[XW] +
+                      c.ft[YS] * hxys * t1[YS]));
+    return -c.KMASK * 0.25 * w3;
+  }
+  // cancellation_occurs :1990-2033
+  double w3 = (c_vc.dz[k] * c.kib *
+               (c.sb[XE] * hyx * t0[XE] + c.sb[YN] * hxy * t0[YN] + c.sb[XW] * hyxw * t0[XW] + c.sb[YS] * hxys * t0[YS]));
+  w3 = w3 + (dz_bottom * c.kit1 *
+             (c.st[XE] * hyx * t1[XE] + c.st[YN] * hxy * t1[YN] + c.st[XW] * hyxw * t1[XW] + c.st[YS] * hxys * t1[YS]));
+  return -c.KMASK * 0.5 * w3;
+}
+
+// One thread per (physical column, level); the tracers are looped inside so that the diffusivities and slopes
+// are read once. FZTOP of the reference (the flux through the top face, carried from the k-1 call) is
+// re-evaluated by the thread that needs it: same expression, same bits.
+template <bool CANCEL>
+__global__ void __launch_bounds__(128, CANCEL ? 4 : 3) gm_flux_kernel(const GmArgs a) {
   const GridView& g = a.g;
   const int i = (g.ib - 1) + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = (g.jb - 1) + blockIdx.y;
-  const int n = blockIdx.z;
+  const int km = g.km, k = 1 + (int)blockIdx.z;
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t n2 = g.n2, nxb = g.nxb, q = (size_t)j * nxb + i, qw = q - 1, qs = q - nxb;
-  const int km = g.km;
   const int kmt = g.KMT[q], kmte = g.KMT[q + 1], kmtw = g.KMT[qw], kmtn = g.KMT[q + nxb], kmts = g.KMT[qs];
   const double hyx = a.HYX[q], hyxw = a.HYX[qw], hxy = a.HXY[q], hxys = a.HXY[qs];
-  const double tarea_r = g.TAREA_R[q];
-  const double* Tn = a.TMIX + (size_t)n * km * n2;
-  double* out = a.HDT + (size_t)n * km * n2 + q;
-  double fztop = 0.0;  // zero flux B.C. at the surface (:1664)
-  for (int k = 1; k <= km; k++) {
-    const int kp1 = (k == km) ? k : k + 1;
-    const double fxe = gm_face(a, Tn, q, q + 1, XE, XW, hyx, k, kp1);
-    const double fxw = gm_face(a, Tn, qw, q, XE, XW, hyxw, k, kp1);
-    const double fyn = gm_face(a, Tn, q, q + nxb, YN, YS, hxy, k, kp1);
-    const double fys = gm_face(a, Tn, qs, q, YN, YS, hxys, k, kp1);
+  const double scale_r = g.TAREA_R[q];
+  const int kp1 = (k == km) ? k : k + 1;
+  const GmFace fe = gm_face_coef<CANCEL>(a, q, q + 1, XE, XW, hyx, k), fw = gm_face_coef<CANCEL>(a, qw, q, XE, XW, hyxw, k);
+  const GmFace fn = gm_face_coef<CANCEL>(a, q, q + nxb, YN, YS, hxy, k), fs = gm_face_coef<CANCEL>(a, qs, q, YN, YS, hxys, k);
+  GmFz ct, cb;
+  if (k > 1) ct = gm_fz_coef<CANCEL>(a, q, k - 1, kmt);
+  if (k < km) cb = gm_fz_coef<CANCEL>(a, q, k, kmt);
+  for (int n = 0; n < g.nt; n++) {
+    const double* Tn = a.TMIX + (size_t)n * km * n2;
+    const double fxe = gm_face_flux<CANCEL>(a, fe, Tn, q, q + 1, k, kp1), fxw = gm_face_flux<CANCEL>(a, fw, Tn, qw, q, k, kp1);
+    const double fyn = gm_face_flux<CANCEL>(a, fn, Tn, q, q + nxb, k, kp1), fys = gm_face_flux<CANCEL>(a, fs, Tn, qs, q, k, kp1);
+    // masked tracer differences of levels k-1, k, k+1: TX(i), TX(i-1), TY(j), TY(j-1)
+    double t[3][4];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      const int kk = k - 1 + l;
+      if (kk < 1 || kk > km) continue;
+      const double* T = Tn + (size_t)(kk - 1) * n2;
+      const double me = (kk <= kmt && kk <= kmte) ? 1.0 : 0.0, mw = (kk <= kmtw && kk <= kmt) ? 1.0 : 0.0;
+      const double mn = (kk <= kmt && kk <= kmtn) ? 1.0 : 0.0, ms = (kk <= kmts && kk <= kmt) ? 1.0 : 0.0;
+      const double t0 = T[q];
+      t[l][XE] = me * (T[q + 1] - t0);
+      t[l][XW] = mw * (t0 - T[qw]);
+      t[l][YN] = mn * (T[q + nxb] - t0);
+      t[l][YS] = ms * (t0 - T[qs]);
+    }
+    // zero flux B.C. at the surface (:1664); FZTOP = fz of the level above otherwise (:2036, :2065)
+    const double fztop = (k == 1) ? 0.0 : gm_fz_eval<CANCEL>(a, ct, k - 1, t[0], t[1], hyx, hyxw, hxy, hxys);
     double G;
     if (k < km) {
-      const double KMASK = (k < kmt) ? 1.0 : 0.0;
-      const double dz_bottom = c_vc.dz[kp1];
-      // tracer differences at levels k and k+1 (TX(i), TY(j), TX(i-1), TY(j-1))
-      double t[2][4];
-#pragma unroll
-      for (int l = 0; l < 2; l++) {
-        const int kk = k + l;
-        const double* T = Tn + (size_t)(kk - 1) * n2;
-        const double me = (kk <= kmt && kk <= kmte) ? 1.0 : 0.0, mw = (kk <= kmtw && kk <= kmt) ? 1.0 : 0.0;
-        const double mn = (kk <= kmt && kk <= kmtn) ? 1.0 : 0.0, ms = (kk <= kmts && kk <= kmt) ? 1.0 : 0.0;
-        const double t0 = T[q];
-        t[l][XE] = me * (T[q + 1] - t0);
-        t[l][XW] = mw * (t0 - T[qw]);
-        t[l][YN] = mn * (T[q + nxb] - t0);
-        t[l][YS] = ms * (t0 - T[qs]);
-      }
-      const size_t ob = k2_ix(a, KBT, k) + q, ot1 = k2_ix(a, KTP, kp1) + q;
-      const double kib = a.KI[ob], kit1 = a.KI[ot1];
-      double sb[4], st[4];
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        sb[d] = a.SL[sl_ix(a, d, KBT, k) + q];
-        st[d] = a.SL[sl_ix(a, d, KTP, kp1) + q];
-      }
-      double fz;
-      if (!a.cancel) {  // :1917-1986
-        const double ktb = a.KT[ob], ktt1 = a.KT[ot1];
-        double fb[4], ft[4];
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-          fb[d] = (k <= kmt) ? ktb * sb[d] * c_vc.dz[k] : 0.0;
-          ft[d] = (kp1 <= kmt) ? ktt1 * st[d] * c_vc.dz[kp1] : 0.0;
-        }
-        double w3 = 0.0;
-        w3 = w3 + (c_vc.dz[k] * kib *
-                   (sb[XE] * hyx * t[0][XE] + sb[YN] * hxy * t[0][YN] + sb[XW] * hyxw * t[0][XW] + sb[YS] * hxys * t[0][YS]));
-        w3 = w3 + (fb[XE] * hyx * t[0][XE] + fb[YN] * hxy * t[0][YN] + fb[XW] * hyxw * t[0][XW] + fb[YS] * hxys * t[0][YS]);
-        w3 = w3 + (dz_bottom * kit1 *
-                   (st[XE] * hyx * t[1][XE] + st[YN] * hxy * t[1][YN] + st[XW] * hyxw * t[1][XW] + st[YS] * hxys * t[1][YS]));
-        w3 = w3 + (1.0 * (ft[XE] * hyx * t[1][XE] + ft[YN] * hxy * t[1][YN] + ft[XW] * hyxw * t[1][XW] +
-                          ft[YS] * hxys * t[1][YS]));
-        fz = -KMASK * 0.25 * w3;
-      } else {  // :1990-2033
-        double w3 = (c_vc.dz[k] * kib *
-                     (sb[XE] * hyx * t[0][XE] + sb[YN] * hxy * t[0][YN] + sb[XW] * hyxw * t[0][XW] + sb[YS] * hxys * t[0][YS]));
-        w3 = w3 + (dz_bottom * kit1 *
-                   (st[XE] * hyx * t[1][XE] + st[YN] * hxy * t[1][YN] + st[XW] * hyxw * t[1][XW] + st[YS] * hxys * t[1][YS]));
-        fz = -KMASK * 0.5 * w3;
-      }
-      G = (fxe - fxw + fyn - fys + fztop - fz) * c_vc.dzr[k] * tarea_r;
-      fztop = fz;
+      const double fz = gm_fz_eval<CANCEL>(a, cb, k, t[1], t[2], hyx, hyxw, hxy, hxys);
+      G = (fxe - fxw + fyn - fys + fztop - fz) * c_vc.dzr[k] * scale_r;
     } else {
-      G = (fxe - fxw + fyn - fys + fztop) * c_vc.dzr[k] * tarea_r;
-      fztop = 0.0;
+      G = (fxe - fxw + fyn - fys + fztop) * c_vc.dzr[k] * scale_r;
     }
-    out[(size_t)(k - 1) * n2] = G;
+    a.HDT[((size_t)n * km + (k - 1)) * n2 + q] = G;
   }
 }
 
@@ -353,9 +397,10 @@ int gm_tendency_dev(const double* TMIX) {
   a.cancel = !(a.diff_tapering || c.ah_gm != c.ah_bolus);       // :970-983
   if (G.gm_force_general) a.cancel = 0;
   const int nt = 128;
-  dim3 g1((unsigned)((G.nxb - 2 + nt - 1) / nt), (unsigned)(G.nyb - 2), 1);
+  dim3 g1((unsigned)((G.nxb - 2 + nt - 1) / nt), (unsigned)(G.nyb - 2), (unsigned)G.km);
   POP_LAUNCH(gm_column_kernel, g1, nt, 0, a);
-  dim3 g2((unsigned)((G.ie - G.ib + 1 + nt - 1) / nt), (unsigned)(G.je - G.jb + 1), (unsigned)G.nt);
-  POP_LAUNCH(gm_flux_kernel, g2, nt, 0, a);
+  dim3 g2((unsigned)((G.ie - G.ib + 1 + nt - 1) / nt), (unsigned)(G.je - G.jb + 1), (unsigned)G.km);
+  if (a.cancel) POP_LAUNCH(gm_flux_kernel<true>, g2, nt, 0, a);
+  else POP_LAUNCH(gm_flux_kernel<false>, g2, nt, 0, a);
   return pop_post_launch("hdifft_gm");
 }
