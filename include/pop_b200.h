@@ -92,6 +92,9 @@ typedef struct pop_config {
   int rank, nranks, device;
   /* time_manager_nml: Robert filter coefficients (time_management.F90:461-464,897-898; Williams 2009) */
   double robert_alpha, robert_nu;
+  /* vertical_mix_nml: convection_diff = 0 is convection_type = 'adjustment' with nconvad passes of convad
+     (vertical_mix.F90:239,1888-2027; the reference default is 2). 0 passes = no convective adjustment. */
+  int nconvad;
 } pop_config;
 
 /* block descriptor handed to slab routines: mirrors `type block`, source/blocks.F90:30-39 */

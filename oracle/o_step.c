@@ -327,7 +327,29 @@ void o_baroclinic_correct_adjust(void) {
         }
       }
     }
-    /* convad: convection_type = 'diffusion' -> immediate return (vertical_mix.F90:1925) */
+    /* convad (vertical_mix.F90:1888-2027): convection_type = 'diffusion' -> immediate return (:1925); otherwise
+       nconvad passes over the odd, then the even level pairs; dttxcel = 1 so dztxcel(k) = dz(k)/1,
+       dzwxcel(k) = 1/(dztxcel(k) + dztxcel(k+1)) (time_management.F90:1005-1010) */
+    if (!M.cfg.convection_diff && M.cfg.nconvad > 0) {
+      double *RHOK = tmp2(), *RHOKP = tmp2();
+      for (int nc = 1; nc <= M.cfg.nconvad; nc++)
+        for (int ks = 1; ks <= 2; ks++)
+          for (int k = ks; k <= km - 1; k += 2) {
+            o_state(k, k + 1, KN4(Tn, k, 1), KN4(Tn, k, 2), b, RHOK, NULL, NULL, NULL);
+            o_state(k + 1, k + 1, KN4(Tn, k + 1, 1), KN4(Tn, k + 1, 2), b, RHOKP, NULL, NULL, NULL);
+            const double dztk = M.dz[k] / 1.0, dztk1 = M.dz[k + 1] / 1.0;
+            const double dzwx = 1.0 / (dztk + dztk1);
+            for (int n = 1; n <= nt; n++) {
+              double *tk = KN4(Tn, k, n), *tk1 = KN4(Tn, k + 1, n);
+              for (size_t q = 0; q < M.n2; q++)
+                if (RHOK[q] > RHOKP[q] && k < KMT[q]) {
+                  tk[q] = dzwx * (dztk * tk[q] + dztk1 * tk1[q]);
+                  tk1[q] = tk[q];
+                }
+            }
+          }
+      free(RHOK); free(RHOKP);
+    }
     for (int k = 1; k <= km; k++)
       o_state(k, k, KN4(Tn, k, 1), KN4(Tn, k, 2), b, K3(B3(M.RHO[n_], b), k), NULL, NULL, NULL);
   }

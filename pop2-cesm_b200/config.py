@@ -51,6 +51,7 @@ class PopConfig(C.Structure):
         ("dtt", C.c_double),
         ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
         ("robert_alpha", C.c_double), ("robert_nu", C.c_double),
+        ("nconvad", C.c_int),
     ]
 
 
@@ -86,7 +87,7 @@ def make_config(**kw):
         solver_choice=SOLVER_CHRONGEAR, max_iterations=1000, convergence_check_freq=10,
         convergence_check_start=60, max_lanczos_step=20,
         convergence_criterion=1.0e-13, lanczos_convergence_criterion=0.1,
-        dtt=3600.0, rank=0, nranks=1, device=0, robert_alpha=0.53, robert_nu=0.20,
+        dtt=3600.0, rank=0, nranks=1, device=0, robert_alpha=0.53, robert_nu=0.20, nconvad=0,
     )
     tadv = kw.pop("tadvect", TADVECT_CENTERED)
     d.update(kw)

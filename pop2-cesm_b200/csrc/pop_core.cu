@@ -155,6 +155,7 @@ extern "C" void pop_config_defaults(pop_config* c) {
   c->nranks = 1;
   c->robert_alpha = 0.53;  // time_management.F90:461-462 (Williams 2009)
   c->robert_nu = 0.20;
+  c->nconvad = 0;
 }
 
 // ------------------------------------------------------------------ lifecycle

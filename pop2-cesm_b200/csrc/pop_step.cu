@@ -8,6 +8,7 @@
 // the same points of the step.
 #include <utility>
 #include "pop_dev.cuh"
+#include "pop_state.cuh"
 
 // ------------------------------------------------------------------ dhdt
 __global__ void dhdt_kernel(double* __restrict__ DH, const double* __restrict__ Pc,
@@ -95,6 +96,36 @@ int baroclinic_driver_dev(bool defer_finish) {
   return POP_SUCCESS;
 }
 
+// convad (vertical_mix.F90:1888-2027): nconvad passes over the odd, then the even level pairs of a column; a pair
+// that is statically unstable after adiabatic displacement is mixed to its thickness-weighted mean. One thread
+// per column: the passes are sequential in k by construction. dttxcel = 1 (time_management.F90:1005-1010).
+__global__ void convad_kernel(StateOpt so, double* T, const int* __restrict__ KMT, size_t n2, int km,
+                              int nt, int nconvad) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  const int kmt = KMT[q];
+  double* S = T + (size_t)km * n2;
+  for (int nc = 1; nc <= nconvad; nc++)
+    for (int ks = 1; ks <= 2; ks++)
+      for (int k = ks; k <= km - 1; k += 2) {
+        if (!(k < kmt)) break;  // nothing below the bottom is touched (the where mask), k only grows
+        const size_t c = (size_t)(k - 1) * n2 + q, c1 = c + n2;
+        double rhok, rhokp;
+        state_cell(so, k + 1, T[c], S[c], &rhok, nullptr, nullptr, nullptr);
+        state_cell(so, k + 1, T[c1], S[c1], &rhokp, nullptr, nullptr, nullptr);
+        if (rhok > rhokp) {
+          const double dztk = c_vc.dz[k] / 1.0, dztk1 = c_vc.dz[k + 1] / 1.0;
+          const double dzwx = 1.0 / (dztk + dztk1);
+          for (int n = 0; n < nt; n++) {
+            double* t = T + (size_t)n * km * n2;
+            const double v = dzwx * (dztk * t[c] + dztk1 * t[c1]);
+            t[c] = v;
+            t[c1] = v;
+          }
+        }
+      }
+}
+
 // ------------------------------------------------------------------ baroclinic_correct_adjust
 struct SfcArgs {
   double *Tn;
@@ -162,6 +193,9 @@ int baroclinic_correct_adjust_dev() {
     }
   }
   // convad: convection_type = 'diffusion' returns immediately (vertical_mix.F90:1925)
+  if (!G.cfg.convection_diff && G.cfg.nconvad > 0)
+    POP_LAUNCH(convad_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, StateOpt{G.cfg.state_itype, G.cfg.state_range_iopt}, Tn,
+               fldi("KMT"), G.n2, G.km, G.nt, G.cfg.nconvad);
   POP_TRY(state_3d(Tn, fld_t("RHO", n_)));  // baroclinic.F90:1476-1482
   return pop_post_launch("baroclinic_correct_adjust");
 }

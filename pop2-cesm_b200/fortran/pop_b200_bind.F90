@@ -64,6 +64,7 @@ module pop_b200_bind
       real (c_double) :: dtt
       integer (c_int) :: rank, nranks, device
       real (c_double) :: robert_alpha, robert_nu
+      integer (c_int) :: nconvad
    end type pop_config
 
    ! mirrors struct pop_block = `type block` of blocks.F90:30-39

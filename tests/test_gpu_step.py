@@ -53,6 +53,8 @@ CASES = {
     "gm_general_tripole": dict(nx=40, ny=32, km=7, nt=2, seed=28, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM,
                                ah_gm=0.6e7, ah_bolus=0.4e7, ah_bkg_srfbl=0.5e7, slm_b=0.2,
                                convergence_criterion=1e-12),
+    # convection_type = 'adjustment': two convad passes (vertical_mix.F90:1888-2027) instead of convective diffusion
+    "convad_chrongear": dict(nx=40, ny=32, km=8, nt=3, seed=29, convection_diff=0, nconvad=2, convergence_criterion=1e-12),
     # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
     "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
                              lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),

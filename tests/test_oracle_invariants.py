@@ -196,3 +196,22 @@ def test_robert_filter_conserves_tracer_content_and_mean_surface_pressure(alpha)
         assert abs(pa - pb) <= 1e-12 * max(abs(pa), va * 1e-6)
     # ... while the fields themselves did change at the filtered level
     assert not np.array_equal(plain[c.TIME_OLD], fields[c.TIME_OLD])
+
+
+def test_convective_adjustment_mixes_unstable_pairs_and_conserves_column_content():
+    """convad (vertical_mix.F90:1888-2027): pairs that are statically unstable are replaced by their thickness-weighted
+    mean, so the dz-weighted column integral of every tracer is unchanged."""
+    new = {}
+    for nconvad in (0, 2):
+        cs, o = _case(nt=3, convection_diff=0, nconvad=nconvad, convergence_criterion=1e-13)
+        assert o.step(c.TS_EULER) == 0
+        new[nconvad] = oracle_global(o, "TRACER", c.TIME_CUR).reshape(o.nt, o.km, cs.ny, cs.nx).copy()
+    a, b = new[0], new[2]
+    changed = np.any(a != b, axis=(0,))
+    assert changed.sum() > 50                                       # the synthetic state has unstable pairs
+    dz = np.asarray(cs.dz)[None, :, None, None]
+    lev = np.arange(1, cs.km + 1)[None, :, None, None]
+    w = dz * (lev <= cs.kmt[None, None])
+    ia, ib = np.sum(a * w, axis=1), np.sum(b * w, axis=1)
+    assert np.max(np.abs(ia - ib)) <= 1e-12 * np.max(np.abs(ia))
+    assert np.all(b[:, :, cs.kmt == 0] == 0.0)
