@@ -20,7 +20,7 @@ def test_cuda_path_matches_golden(name):
     p = load_pop(MG.build_case(name))
     try:
         its = []
-        for ts in MG.STEPS:
+        for ts in MG.steps_of(name):
             p.step(ts)
             its.append(p.solvers_get_diagnostics()[0])
         assert its == g["solver_iterations"].tolist()

@@ -16,7 +16,7 @@ def test_oracle_matches_golden(name):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     o = load_oracle(MG.build_case(name))
     its = []
-    for ts in MG.STEPS:
+    for ts in MG.steps_of(name):
         assert o.step(ts) == 0
         its.append(o.solver_diag()[0])
     assert its == g["solver_iterations"].tolist()
