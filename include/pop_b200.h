@@ -196,6 +196,13 @@ int pop_halo_update_3d_r8(double* array, int nz, int fieldLoc, int fieldKind, do
 int pop_halo_update_4d_r8(double* array, int nz, int nt, int fieldLoc, int fieldKind,
                           double fillValue);
 int pop_halo_update_2d_i4(int* array, int fieldLoc, int fieldKind, int fillValue);
+/* the other members of the generic POP_HaloUpdate interface (mpi/POP_HaloMod.F90:79-89: 2DR4 :2078, 3DR4 :3218,
+   3DI4 :3670, 4DR4 :4592, 4DI4 :5062) */
+int pop_halo_update_3d_i4(int* array, int nz, int fieldLoc, int fieldKind, int fillValue);
+int pop_halo_update_4d_i4(int* array, int nz, int nt, int fieldLoc, int fieldKind, int fillValue);
+int pop_halo_update_2d_r4(float* array, int fieldLoc, int fieldKind, float fillValue);
+int pop_halo_update_3d_r4(float* array, int nz, int fieldLoc, int fieldKind, float fillValue);
+int pop_halo_update_4d_r4(float* array, int nz, int nt, int fieldLoc, int fieldKind, float fillValue);
 int pop_global_sum_2d_r8(const double* array, int fieldLoc, const double* mMask, double* sum);
 int pop_global_sum_nfields_2d_r8(const double* array, int nfields, int fieldLoc,
                                  const double* mMask, double* sums);

@@ -28,7 +28,8 @@ SYMBOLS = [
     "pop_impvmixt_correct", "pop_impvmixu", "pop_vmix_coeffs", "pop_state", "pop_solvers_run",
     "pop_solvers_diagonal", "pop_solvers_get_diagnostics", "pop_btrop_operator", "pop_solvers_prep",
     "pop_solvers_get_eigs", "pop_halo_update_2d_r8", "pop_halo_update_3d_r8",
-    "pop_halo_update_4d_r8", "pop_halo_update_2d_i4", "pop_global_sum_2d_r8",
+    "pop_halo_update_4d_r8", "pop_halo_update_2d_i4", "pop_halo_update_3d_i4", "pop_halo_update_4d_i4",
+    "pop_halo_update_2d_r4", "pop_halo_update_3d_r4", "pop_halo_update_4d_r4", "pop_global_sum_2d_r8",
     "pop_global_sum_nfields_2d_r8", "pop_dhdt", "pop_baroclinic_driver", "pop_barotropic_driver",
     "pop_baroclinic_correct_adjust", "pop_step", "pop_step_coupled", "pop_kernel_launch_count",
     "pop_timer_get", "pop_timers_reset", "pop_timers_enable", "pop_sync", "pop_stream",
@@ -88,6 +89,11 @@ def lib():
         L.pop_halo_update_3d_r8.argtypes = [vp, ci, ci, ci, cd]
         L.pop_halo_update_4d_r8.argtypes = [vp, ci, ci, ci, ci, cd]
         L.pop_halo_update_2d_i4.argtypes = [vp, ci, ci, ci]
+        L.pop_halo_update_3d_i4.argtypes = [vp, ci, ci, ci, ci]
+        L.pop_halo_update_4d_i4.argtypes = [vp, ci, ci, ci, ci, ci]
+        L.pop_halo_update_2d_r4.argtypes = [vp, ci, ci, C.c_float]
+        L.pop_halo_update_3d_r4.argtypes = [vp, ci, ci, ci, C.c_float]
+        L.pop_halo_update_4d_r4.argtypes = [vp, ci, ci, ci, ci, C.c_float]
         L.pop_global_sum_2d_r8.argtypes = [vp, ci, vp, C.POINTER(cd)]
         L.pop_global_sum_nfields_2d_r8.argtypes = [vp, ci, ci, vp, vp]
         L.pop_step.argtypes = [ci]
@@ -281,9 +287,14 @@ class Pop:
     def halo_update(self, array, fieldLoc, fieldKind, fillValue=0.0):
         """POP_HaloUpdate on a padded local array (nyb,nxb) / (nz,nyb,nxb) / (nt,nz,nyb,nxb)."""
         a = array
-        if a.dtype == np.int32:
-            assert a.ndim == 2
-            self._ck(self.L.pop_halo_update_2d_i4(_p(a), fieldLoc, fieldKind, int(fillValue)))
+        if a.dtype in (np.int32, np.float32):      # POP_HaloUpdate{2D,3D,4D}{I4,R4}
+            sfx, fv = ("i4", int(fillValue)) if a.dtype == np.int32 else ("r4", float(fillValue))
+            if a.ndim == 2:
+                self._ck(getattr(self.L, "pop_halo_update_2d_" + sfx)(_p(a), fieldLoc, fieldKind, fv))
+            elif a.ndim == 3:
+                self._ck(getattr(self.L, "pop_halo_update_3d_" + sfx)(_p(a), a.shape[0], fieldLoc, fieldKind, fv))
+            else:
+                self._ck(getattr(self.L, "pop_halo_update_4d_" + sfx)(_p(a), a.shape[1], a.shape[0], fieldLoc, fieldKind, fv))
         elif a.ndim == 2:
             self._ck(self.L.pop_halo_update_2d_r8(_p(a), fieldLoc, fieldKind, float(fillValue)))
         elif a.ndim == 3:

@@ -456,6 +456,42 @@ extern "C" int pop_halo_update_2d_i4(int* array, int fieldLoc, int fieldKind, in
   int* a = s.inout("hl_a", array, G.n2, true);
   return s.finish(s.ok ? halo_update_i4(a, 1, fieldLoc, fieldKind, fillValue) : POP_FAIL);
 }
+// the remaining members of the POP_HaloUpdate generic interface (mpi/POP_HaloMod.F90:79-89): 3-d/4-d integer and
+// 2-d/3-d/4-d single-precision arrays; the same kernels instantiated for the element type
+extern "C" int pop_halo_update_3d_i4(int* array, int nz, int fieldLoc, int fieldKind, int fillValue) {
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: not initialized");
+  POP_REQUIRE(nz >= 1, "POP_HaloUpdate: nz=%d", nz);
+  Stage s;
+  int* a = s.inout("hl_a", array, G.n2 * nz, true);
+  return s.finish(s.ok ? halo_update_i4(a, nz, fieldLoc, fieldKind, fillValue) : POP_FAIL);
+}
+extern "C" int pop_halo_update_4d_i4(int* array, int nz, int nt, int fieldLoc, int fieldKind, int fillValue) {
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: not initialized");
+  POP_REQUIRE(nz >= 1 && nt >= 1, "POP_HaloUpdate: nz=%d nt=%d", nz, nt);
+  Stage s;
+  int* a = s.inout("hl_a", array, G.n2 * nz * nt, true);
+  return s.finish(s.ok ? halo_update_i4(a, nz * nt, fieldLoc, fieldKind, fillValue) : POP_FAIL);
+}
+extern "C" int pop_halo_update_2d_r4(float* array, int fieldLoc, int fieldKind, float fillValue) {
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: not initialized");
+  Stage s;
+  float* a = s.inout("hl_a", array, G.n2, true);
+  return s.finish(s.ok ? halo_update_r4(a, 1, fieldLoc, fieldKind, fillValue) : POP_FAIL);
+}
+extern "C" int pop_halo_update_3d_r4(float* array, int nz, int fieldLoc, int fieldKind, float fillValue) {
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: not initialized");
+  POP_REQUIRE(nz >= 1, "POP_HaloUpdate: nz=%d", nz);
+  Stage s;
+  float* a = s.inout("hl_a", array, G.n2 * nz, true);
+  return s.finish(s.ok ? halo_update_r4(a, nz, fieldLoc, fieldKind, fillValue) : POP_FAIL);
+}
+extern "C" int pop_halo_update_4d_r4(float* array, int nz, int nt, int fieldLoc, int fieldKind, float fillValue) {
+  POP_REQUIRE(G.initialized, "POP_HaloUpdate: not initialized");
+  POP_REQUIRE(nz >= 1 && nt >= 1, "POP_HaloUpdate: nz=%d nt=%d", nz, nt);
+  Stage s;
+  float* a = s.inout("hl_a", array, G.n2 * nz * nt, true);
+  return s.finish(s.ok ? halo_update_r4(a, nz * nt, fieldLoc, fieldKind, fillValue) : POP_FAIL);
+}
 extern "C" int pop_global_sum_nfields_2d_r8(const double* array, int nfields, int fieldLoc,
                                             const double* mMask, double* sums) {
   POP_REQUIRE(G.initialized, "POP_GlobalSum: not initialized");

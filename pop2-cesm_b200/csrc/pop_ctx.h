@@ -206,6 +206,7 @@ int set_timestep(int ts_type);
 // halo (pop_halo.cu)
 int halo_update(double* a, int nz, int loc, int kind, double fill);
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill);
+int halo_update_r4(float* a, int nz, int loc, int kind, float fill);
 int halo_rows_only(double* a, int nz);
 int comm_init(int rank, int nranks, const char* id128);
 int comm_unique_id(char* id128);

@@ -514,3 +514,6 @@ int halo_rows_only(double* a, int nz) {
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill) {
   return halo_update_t<int>(a, nz, loc, kind, fill);
 }
+int halo_update_r4(float* a, int nz, int loc, int kind, float fill) {
+  return halo_update_t<float>(a, nz, loc, kind, fill);
+}

@@ -362,6 +362,51 @@ module pop_b200_bind
          integer (c_int) :: ierr
       end function
 
+      ! mpi/POP_HaloMod.F90:3670,5062   POP_HaloUpdate3DI4, POP_HaloUpdate4DI4
+      function pop_halo_update_3d_i4(array, nz, fieldLoc, fieldKind, fillValue) &
+               bind(C, name='pop_halo_update_3d_i4') result(ierr)
+         import :: c_int
+         integer (c_int), intent(inout) :: array(*)
+         integer (c_int), value :: nz, fieldLoc, fieldKind, fillValue
+         integer (c_int) :: ierr
+      end function
+
+      function pop_halo_update_4d_i4(array, nz, nt, fieldLoc, fieldKind, fillValue) &
+               bind(C, name='pop_halo_update_4d_i4') result(ierr)
+         import :: c_int
+         integer (c_int), intent(inout) :: array(*)
+         integer (c_int), value :: nz, nt, fieldLoc, fieldKind, fillValue
+         integer (c_int) :: ierr
+      end function
+
+      ! mpi/POP_HaloMod.F90:2078,3218,4592   POP_HaloUpdate2DR4, POP_HaloUpdate3DR4, POP_HaloUpdate4DR4
+      function pop_halo_update_2d_r4(array, fieldLoc, fieldKind, fillValue) &
+               bind(C, name='pop_halo_update_2d_r4') result(ierr)
+         import :: c_int, c_float
+         real (c_float), intent(inout) :: array(*)
+         integer (c_int), value :: fieldLoc, fieldKind
+         real (c_float), value :: fillValue
+         integer (c_int) :: ierr
+      end function
+
+      function pop_halo_update_3d_r4(array, nz, fieldLoc, fieldKind, fillValue) &
+               bind(C, name='pop_halo_update_3d_r4') result(ierr)
+         import :: c_int, c_float
+         real (c_float), intent(inout) :: array(*)
+         integer (c_int), value :: nz, fieldLoc, fieldKind
+         real (c_float), value :: fillValue
+         integer (c_int) :: ierr
+      end function
+
+      function pop_halo_update_4d_r4(array, nz, nt, fieldLoc, fieldKind, fillValue) &
+               bind(C, name='pop_halo_update_4d_r4') result(ierr)
+         import :: c_int, c_float
+         real (c_float), intent(inout) :: array(*)
+         integer (c_int), value :: nz, nt, fieldLoc, fieldKind
+         real (c_float), value :: fillValue
+         integer (c_int) :: ierr
+      end function
+
       ! mpi/POP_ReductionsMod.F90:144   POP_GlobalSum(array,dist,fieldLoc,errorCode,mMask)
       function pop_global_sum_2d_r8(array, fieldLoc, mMask, total) &
                bind(C, name='pop_global_sum_2d_r8') result(ierr)
