@@ -45,7 +45,8 @@ WORKLOADS = {
     "gx1v7": (320, 384, 60, "gx1v7", 3600.0),
     "tx_sample": (1200, 800, 62, "tx0.1v3", 864.0),     # bounded CPU sample of the tx0.1v3 workload
     "tiny": (120, 80, 12, "stretched", 2880.0),
-    "tx_strip8": (3600, 300, 62, "tx0.1v3", 288.0),     # one of the 8 strips of tx0.1v3 as a single-GPU problem (tuning aid)
+    "tx_strip8": (3600, 300, 62, "tx0.1v3", 288.0),
+    "tx_2strips": (3600, 600, 62, "tx0.1v3", 288.0),    # two such strips: the 8-GPU per-rank size on 2 GPUs (exchange-latency tuning aid)     # one of the 8 strips of tx0.1v3 as a single-GPU problem (tuning aid)
 }
 
 

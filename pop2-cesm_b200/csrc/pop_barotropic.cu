@@ -731,7 +731,9 @@ static int pcsi(double* X, const double* B) {
       a.om = csomga; a.c1 = csy * csomga - 1.0;
       a.advance = (m < maxIt) ? 1 : 0;
       a.partials = G.d_partials_big;
-      a.map_ghost = (G.nranks == 1) ? 1 : 0;
+      // one rank: the pass itself fills the ghost cells it can map to a source cell (east-west wrap, tripole
+      // fold); north-south cyclic rows come from the halo update like the rows of a neighbouring strip
+      a.map_ghost = (G.nranks == 1 && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC) ? 1 : 0;
       a.do_ew = do_ew; a.do_tripole = do_tp;
       a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
       if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid1, PC_TX * PC_TY, 0, a);

@@ -433,7 +433,8 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   // the operator weights are derived from HU one row/column beyond each cell: on the outermost ghost row
   // of a strip that neighbour does not exist locally, so take the owner's values (the two-iteration
   // P-CSI pass evaluates the operator on the first ghost ring and must reproduce the owner's bits)
-  if (G.nranks > 1)
+  // (a cyclic north-south boundary on one rank is the same situation: the strip is its own neighbour)
+  if (G.nranks > 1 || c.ns_boundary_type == POP_BNDY_CYCLIC)
     for (const char* w : {"btropWgtNE", "btropWgtEast", "btropWgtNorth", "centerWgtClinicIndep"})
       POP_TRY(halo_rows_only(fld(w), 1));
   for (const char* w : {"BT_R", "BT_S", "BT_Q", "BT_Z", "BT_AZ", "BT_A0R"}) POP_TRY(alloc_field(w, 1, false));

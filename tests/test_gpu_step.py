@@ -225,6 +225,53 @@ def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypa
     assert relerr(res["blocked"][1], oracle_global(o, "PSURF", c.TIME_CUR)) <= 2.0e-12
 
 
+@pytest.mark.parametrize("flags", [("POP_B200_NO_TMA",), ("POP_B200_NO_FAST_TRACER",), ("POP_B200_NO_OVERLAP",),
+                                   ("POP_B200_NO_TMA", "POP_B200_NO_OVERLAP")])
+def test_staging_and_overlap_variants_are_bitwise_identical(monkeypatch, flags):
+    """The TMA-staged kernels, the specialised leapfrog tracer kernel and the side-stream overlap of the velocity
+    finish are optimisations of one computation: switching each off (the paths odd extents and old drivers take)
+    must not change a single bit, on a grid with partial edge tiles."""
+    cs = make_case(104, 52, 6, seed=72, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                   hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21,
+                   given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
+    res = []
+    for on in (False, True):
+        for f in flags:
+            monkeypatch.setenv(f, "1" if on else "0")
+        p = load_pop(cs)
+        try:
+            for ts in (c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG):
+                p.step(ts)
+            res.append({n: pop_global(p, n, c.TIME_CUR) for n in PROG})
+        finally:
+            p.finalize()
+    for n in PROG:
+        assert np.array_equal(res[0][n], res[1][n]), n
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nx=45, ny=33, km=5, seed=73, convergence_criterion=1e-12),                      # odd nx: no TMA descriptors
+    dict(nx=37, ny=29, km=3, seed=74, ns=c.BNDY_CYCLIC, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
+         ah=-3.0e21, am=-27.0e21, solver_choice=c.SOLVER_PCSI, dtt=600.0, nt=3),        # minimum depth, odd extents
+    dict(nx=72, ny=30, km=4, seed=76, ns=c.BNDY_CYCLIC, solver_choice=c.SOLVER_PCSI, dtt=600.0),   # P-CSI across a cyclic north-south seam
+    dict(nx=33, ny=8, km=4, seed=75, hmix_tracer_itype=c.HMIX_GM, given_vmix=True, convergence_criterion=1e-12),  # one tile row
+])
+def test_ragged_extents_match_oracle(kw):
+    """Extents that are not multiples of any tile size, odd nx (the non-TMA staging paths), the minimum km = 3 and a
+    strip thinner than one tile: same parity bar as the regular cases."""
+    kw = dict(kw)
+    cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
+    o, p = load_oracle(cs), load_pop(cs)
+    try:
+        for i, ts in enumerate([c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG]):
+            assert o.step(ts) == 0
+            p.step(ts)
+            assert o.solver_diag()[0] == p.solvers_get_diagnostics()[0]
+            compare(o, p, RTOL_1STEP * (i + 1), "ragged step %d" % i)
+    finally:
+        p.finalize()
+
+
 def test_config1_shape_test_grid_options():
     """BASELINE.json config 1: the reference's own CPU-runnable case (input_templates/test_pop2_in and
     test_domain_size.F90: 192 x 128 x 20, 16 x 16 blocks, cyclic/closed, pcg + diagonal preconditioner,
