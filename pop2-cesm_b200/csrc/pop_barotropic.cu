@@ -396,7 +396,12 @@ pcsi_iter_kernel(const PcsiArgs a) {
 // ghost rows owned by a neighbouring rank hold that rank's bits two cells deep.  One 2-level halo
 // update of (X,Q) follows every pass (P > 1: one strip exchange per two iterations).
 #define P2_TX 64
+#ifndef P2_TY
 #define P2_TY 10
+#endif
+#ifndef P2_MINB
+#define P2_MINB 4
+#endif
 #define P2_NT 256
 // every staged tile starts two cells west of the tile (an even column: TMA needs the first element of a
 // box on a 16-byte boundary) and is P2_XW wide; X, N, NE start two rows south, the others one row south
@@ -427,7 +432,7 @@ __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__
   }
 }
 template <bool SUM>
-__global__ void __launch_bounds__(P2_NT, 4)
+__global__ void __launch_bounds__(P2_NT, P2_MINB)
 pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   POP_DYN_SMEM(smem_raw);
   double* sX = (double*)smem_raw;  // X_m              rows j0-2 .. j0+TY+1
