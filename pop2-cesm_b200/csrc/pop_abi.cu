@@ -146,16 +146,17 @@ extern "C" int pop_get_field(const char* name, int tlev, void* host) {
   return POP_SUCCESS;
 }
 // physical strip (nx_global x ny_local x nz) <-> padded block; ghost cells are not touched
-static int strip_copy(DevField* f, void* host, bool to_device, int z0, int nz) {
+static int strip_copy(DevField* f, void* host, bool to_device, int z0, int nz, cudaStream_t st = nullptr) {
   const size_t es = f->is_int ? sizeof(int) : sizeof(double);
+  if (!st) st = G.stream;
   for (int z = z0; z < z0 + nz; z++) {
     char* d = (char*)f->p + ((size_t)z * G.n2 + (size_t)POP_NGHOST * G.nxb + POP_NGHOST) * es;
     char* h = (char*)host + (size_t)(z - z0) * G.nxg * G.ny_local * es;
     // cudaMemcpyDefault: the strip may live in host (pageable / pinned) or device memory
     if (to_device)
-      POP_CHECK_CUDA(cudaMemcpy2DAsync(d, G.nxb * es, h, G.nxg * es, G.nxg * es, G.ny_local, cudaMemcpyDefault, G.stream));
+      POP_CHECK_CUDA(cudaMemcpy2DAsync(d, G.nxb * es, h, G.nxg * es, G.nxg * es, G.ny_local, cudaMemcpyDefault, st));
     else
-      POP_CHECK_CUDA(cudaMemcpy2DAsync(h, G.nxg * es, d, G.nxb * es, G.nxg * es, G.ny_local, cudaMemcpyDefault, G.stream));
+      POP_CHECK_CUDA(cudaMemcpy2DAsync(h, G.nxg * es, d, G.nxb * es, G.nxg * es, G.ny_local, cudaMemcpyDefault, st));
   }
   return POP_SUCCESS;
 }
@@ -529,28 +530,87 @@ extern "C" int pop_step(int ts_type) {
 }
 
 // One coupled step from HOST buffers: surface forcing in, surface state out (physical strips).
+// ---- coupled step: the surface forcing comes in from host buffers, the new surface state goes out to a host
+// buffer, the 3-d state never leaves HBM. STF (read by the first kernel of the step) is copied on the main stream;
+// SMF, SHF_QSW and FW follow on the copy stream while the tracer kernel runs, and the step waits for them just
+// before their first reader. PSURF leaves as soon as the barotropic solve has produced it, SST/SSS as soon as the
+// corrector has; only U1/V1 (final after the barotropic mean is added back, at the very end) are copied after the
+// step. Averaging and Robert-filtered steps rewrite the output level at the end, so everything leaves after the step.
+int coupled_wait_forcing() {
+  if (!G.cio.forcing_pending) return POP_SUCCESS;
+  POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_cp_in, 0));
+  G.cio.forcing_pending = false;
+  return POP_SUCCESS;
+}
+int coupled_after_barotropic() {
+  if (!G.cio.out || !G.cio.early) return POP_SUCCESS;
+  DevField* f;
+  const size_t strip = (size_t)G.nxg * G.ny_local;
+  POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_a, G.stream));
+  POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_cp, G.ev_cp_a, 0));
+  POP_TRY(find_field("pop_step_coupled", "PSURF", POP_TIME_NEW, &f));
+  POP_TRY(strip_copy(f, G.cio.out + 2 * strip, false, 0, 1, G.stream_cp));
+  G.cio.psurf_sent = true;
+  return POP_SUCCESS;
+}
+int coupled_after_corrector() {
+  if (!G.cio.out || !G.cio.early) return POP_SUCCESS;
+  DevField* f;
+  const size_t strip = (size_t)G.nxg * G.ny_local;
+  POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_b, G.stream));
+  POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_cp, G.ev_cp_b, 0));
+  POP_TRY(find_field("pop_step_coupled", "TRACER", POP_TIME_NEW, &f));
+  POP_TRY(strip_copy(f, G.cio.out, false, 0, 1, G.stream_cp));              // SST
+  POP_TRY(strip_copy(f, G.cio.out + strip, false, G.km, 1, G.stream_cp));   // SSS
+  G.cio.ts_sent = true;
+  return POP_SUCCESS;
+}
+
 extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SMF, const double* SHF_QSW,
                                 const double* FW, double* sfc_out) {
   POP_TRY(check_ready("pop_step_coupled", nullptr, false));
   DevField* f;
   if (STF) { POP_TRY(find_field("pop_step_coupled", "STF", 0, &f)); POP_TRY(strip_copy(f, (void*)STF, true, 0, G.nt)); }
-  if (SMF) { POP_TRY(find_field("pop_step_coupled", "SMF", 0, &f)); POP_TRY(strip_copy(f, (void*)SMF, true, 0, 2)); }
-  if (SHF_QSW) { POP_TRY(find_field("pop_step_coupled", "SHF_QSW", 0, &f)); POP_TRY(strip_copy(f, (void*)SHF_QSW, true, 0, 1)); }
-  if (FW) { POP_TRY(find_field("pop_step_coupled", "FW", 0, &f)); POP_TRY(strip_copy(f, (void*)FW, true, 0, 1)); }
-  POP_TRY(step_dev(ts_type));
+  const bool side = !G.no_overlap && (SMF || SHF_QSW || FW);
+  cudaStream_t st_in = side ? G.stream_cp : G.stream;
+  if (SMF) { POP_TRY(find_field("pop_step_coupled", "SMF", 0, &f)); POP_TRY(strip_copy(f, (void*)SMF, true, 0, 2, st_in)); }
+  if (SHF_QSW) { POP_TRY(find_field("pop_step_coupled", "SHF_QSW", 0, &f)); POP_TRY(strip_copy(f, (void*)SHF_QSW, true, 0, 1, st_in)); }
+  if (FW) { POP_TRY(find_field("pop_step_coupled", "FW", 0, &f)); POP_TRY(strip_copy(f, (void*)FW, true, 0, 1, st_in)); }
+  if (side) {
+    POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_in, G.stream_cp));
+    G.cio.forcing_pending = true;
+  }
+  G.cio.out = sfc_out;
+  G.cio.early = sfc_out && !G.no_overlap && (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER);
+  G.cio.psurf_sent = G.cio.ts_sent = false;
+  const int rc = step_dev(ts_type);
+  const bool psurf_sent = G.cio.psurf_sent, ts_sent = G.cio.ts_sent;
+  G.cio.out = nullptr;
+  G.cio.early = false;
+  if (rc != POP_SUCCESS) {
+    if (G.cio.forcing_pending) { cudaStreamSynchronize(G.stream_cp); G.cio.forcing_pending = false; }
+    cudaStreamSynchronize(G.stream_cp);
+    return rc;
+  }
+  POP_TRY(coupled_wait_forcing());  // a step that never reached the wait (cannot happen today) must not leave copies behind
   if (sfc_out) {
     // after the step the freshly computed level is `cur` (or the averaged `cur` on an averaging step)
     const size_t strip = (size_t)G.nxg * G.ny_local;
     POP_TRY(find_field("pop_step_coupled", "TRACER", POP_TIME_CUR, &f));
-    POP_TRY(strip_copy(f, sfc_out, false, 0, 1));               // SST
-    POP_TRY(strip_copy(f, sfc_out + strip, false, G.km, 1));    // SSS
-    POP_TRY(find_field("pop_step_coupled", "PSURF", POP_TIME_CUR, &f));
-    POP_TRY(strip_copy(f, sfc_out + 2 * strip, false, 0, 1));
+    if (!ts_sent) {
+      POP_TRY(strip_copy(f, sfc_out, false, 0, 1));               // SST
+      POP_TRY(strip_copy(f, sfc_out + strip, false, G.km, 1));    // SSS
+    }
+    if (!psurf_sent) {
+      POP_TRY(find_field("pop_step_coupled", "PSURF", POP_TIME_CUR, &f));
+      POP_TRY(strip_copy(f, sfc_out + 2 * strip, false, 0, 1));
+    }
     POP_TRY(find_field("pop_step_coupled", "UVEL", POP_TIME_CUR, &f));
     POP_TRY(strip_copy(f, sfc_out + 3 * strip, false, 0, 1));
     POP_TRY(find_field("pop_step_coupled", "VVEL", POP_TIME_CUR, &f));
     POP_TRY(strip_copy(f, sfc_out + 4 * strip, false, 0, 1));
   }
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream_cp));
   return POP_SUCCESS;
 }

@@ -278,6 +278,12 @@ extern "C" int pop_init(const pop_config* cfg) {
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
   }
+  if (!G.stream_cp) {
+    POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream_cp, cudaStreamNonBlocking, prio_least));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_in, cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_a, cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_b, cudaEventDisableTiming));
+  }
   G.no_overlap = getenv("POP_B200_NO_OVERLAP") != nullptr && getenv("POP_B200_NO_OVERLAP")[0] == '1';
   POP_REQUIRE(cfg->ns_boundary_type != POP_BNDY_TRIPOLE || cfg->ew_boundary_type == POP_BNDY_CYCLIC,
               "pop_init: a tripole grid needs a cyclic east-west boundary");
@@ -329,6 +335,7 @@ extern "C" int pop_init(const pop_config* cfg) {
 extern "C" int pop_finalize(void) {
   if (G.stream) cudaStreamSynchronize(G.stream);
   if (G.stream2) cudaStreamSynchronize(G.stream2);
+  if (G.stream_cp) cudaStreamSynchronize(G.stream_cp);
   p2p_teardown();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();

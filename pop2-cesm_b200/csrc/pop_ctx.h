@@ -67,6 +67,16 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
+  // pop_step_coupled: host<->device copies of the surface forcing / surface state on their own stream, overlapped
+  // with the step (pop_abi.cu); the step calls the three hooks below at the points where the data are needed / final
+  cudaStream_t stream_cp = nullptr;
+  cudaEvent_t ev_cp_in = nullptr, ev_cp_a = nullptr, ev_cp_b = nullptr;
+  struct {
+    bool forcing_pending = false;  // SMF/SHF_QSW/FW still in flight on stream_cp
+    double* out = nullptr;         // host buffer of the surface state, or null
+    bool early = false;            // outputs may leave as soon as they are final (not on averaging / filtered steps)
+    bool psurf_sent = false, ts_sent = false;
+  } cio;
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy
   // rotating time indices (prognostic.F90:63-68)
@@ -236,6 +246,10 @@ int state_slab(int k, int kk, const double* T, const double* S, double* RHOOUT, 
                double* DRHODT, double* DRHODS, size_t n);
 int state_3d(const double* TRACER, double* RHO);
 // GM (pop_gm.cu)
+// hooks of the overlapped coupled step (pop_abi.cu); no-ops outside pop_step_coupled
+int coupled_wait_forcing();      // before the first reader of SMF / SHF_QSW / FW
+int coupled_after_barotropic();  // PSURF(new) is final
+int coupled_after_corrector();   // T,S(new) of the physical cells are final
 int gm_alloc_fields();
 int gm_begin_step();
 int gm_tendency_dev(const double* TMIX);  // fills the field GM_HDT (nxb,nyb,km,nt), adds VDC_GM to VDC

@@ -78,6 +78,7 @@ int baroclinic_driver_dev(bool defer_finish) {
     POP_TRY(halo_update(fld_t("TRACER", n_), 2 * G.km, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
     POP_TRY(state_3d(fld_t("TRACER", n_), fld_t("RHO", n_)));  // baroclinic.F90:981-985
   }
+  POP_TRY(coupled_wait_forcing());  // SMF is first read by the momentum kernel
   {
     ScopedTimer t2("CLINIC");
     MomentumIO io;
@@ -497,7 +498,9 @@ int step_dev(int ts_type) {
   POP_TRY(halo_update(fld("ZX"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));  // step_mod.F90:405-417
   POP_TRY(halo_update(fld("ZY"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
   POP_TRY(barotropic_driver_dev());
+  POP_TRY(coupled_after_barotropic());
   POP_TRY(baroclinic_correct_adjust_dev());
+  POP_TRY(coupled_after_corrector());
   if (overlap) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));  // join
   const int n_ = G.newtime, c = G.curtime, o = G.oldtime;
   // step_mod.F90:467-560

@@ -173,22 +173,38 @@ def test_conservation_constant_preservation_and_masking():
 
 
 def test_step_coupled_host_buffers_match_resident_step():
-    cs = make_case(40, 32, 6, seed=61)
+    """pop_step_coupled (forcing in from host buffers, surface state out to a host buffer, copies overlapped with the
+    step on their own stream) against the resident step fed the same forcing, with forcing that CHANGES every step
+    (a copy that arrived late or an output that left early would show) and every kind of time step."""
+    cs = make_case(72, 40, 6, seed=61, ns=c.BNDY_TRIPOLE, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
+    steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG, c.TS_ROBERT, c.TS_LEAPFROG]
+    rng = np.random.default_rng(5)
+    ocean, oceanu = (cs.kmt > 0), (cs.kmu > 0)
+    forcing = [dict(STF=np.ascontiguousarray(1.0e-4 * rng.standard_normal((cs.nt, cs.ny, cs.nx)) * ocean),
+                    SMF=np.ascontiguousarray(0.5 * rng.standard_normal((2, cs.ny, cs.nx)) * oceanu),
+                    SHF_QSW=np.ascontiguousarray(1.0e-3 * rng.standard_normal((cs.ny, cs.nx)) * ocean),
+                    FW=np.ascontiguousarray(1.0e-6 * rng.standard_normal((cs.ny, cs.nx)) * ocean)) for _ in steps]
+    ref = []
     p = load_pop(cs)
     try:
-        p.step(c.TS_EULER)
-        ref = {n: pop_global(p, n, c.TIME_CUR) for n in ("TRACER", "PSURF", "UVEL", "VVEL")}
+        for ts, f in zip(steps, forcing):
+            for name in ("STF", "SMF", "SHF_QSW", "FW"):
+                p.scatter(name, 0, f[name])
+            p.step(ts)
+            ref.append({n: pop_global(p, n, c.TIME_CUR) for n in ("TRACER", "PSURF", "UVEL", "VVEL")})
     finally:
         p.finalize()
     p = load_pop(cs)
     try:
-        out = np.zeros((5, cs.ny, cs.nx))
-        f = cs.forcing
-        p.step_coupled(c.TS_EULER, np.ascontiguousarray(f["STF"]), np.ascontiguousarray(f["SMF"]),
-                       np.zeros((cs.ny, cs.nx)), np.ascontiguousarray(f["FW"]), out)
-        assert np.array_equal(out[0], ref["TRACER"][0]) and np.array_equal(out[1], ref["TRACER"][cs.km])
-        assert np.array_equal(out[2], ref["PSURF"][0])
-        assert np.array_equal(out[3], ref["UVEL"][0]) and np.array_equal(out[4], ref["VVEL"][0])
+        for i, (ts, f) in enumerate(zip(steps, forcing)):
+            out = np.full((5, cs.ny, cs.nx), np.nan)
+            p.step_coupled(ts, f["STF"], f["SMF"], f["SHF_QSW"], f["FW"], out)
+            r = ref[i]
+            assert np.array_equal(out[0], r["TRACER"][0]) and np.array_equal(out[1], r["TRACER"][cs.km]), i
+            assert np.array_equal(out[2], r["PSURF"][0]), i
+            assert np.array_equal(out[3], r["UVEL"][0]) and np.array_equal(out[4], r["VVEL"][0]), i
+            # the resident state is the same too
+            assert np.array_equal(pop_global(p, "TRACER", c.TIME_CUR), r["TRACER"]), i
     finally:
         p.finalize()
 
