@@ -333,6 +333,8 @@ struct PcsiArgs {
 template <bool SUM>
 __global__ void __launch_bounds__(PC_TX * PC_TY, 8)
 pcsi_iter_kernel(const PcsiArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const BtView& v = a.v;
   const int tx = threadIdx.x % PC_TX, ty = threadIdx.x / PC_TX;
   const int i = blockIdx.x * PC_TX + tx, j = blockIdx.y * PC_TY + ty;
@@ -434,6 +436,8 @@ __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__
 template <bool SUM>
 __global__ void __launch_bounds__(P2_NT, P2_MINB)
 pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
+  pdl_wait();
+  pdl_trigger();
   POP_DYN_SMEM(smem_raw);
   double* sX = (double*)smem_raw;  // X_m              rows j0-2 .. j0+TY+1
   double* sX1 = sX + P2_N_X;       // X_{m+1}          rows j0-1 .. j0+TY
@@ -720,8 +724,8 @@ static int pcsi(double* X, const double* B) {
         if (sample) G.timer_suppress--;
         {
           ScopedTimer tk("PCSI_PASS2_KERNEL");
-          if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, grid2, P2_NT, smem2, a);
-          else POP_LAUNCH(pcsi_iter2_kernel<false>, grid2, P2_NT, smem2, a);
+          if (check) POP_LAUNCH_PDL(pcsi_iter2_kernel<true>, grid2, P2_NT, smem2, a);
+          else POP_LAUNCH_PDL(pcsi_iter2_kernel<false>, grid2, P2_NT, smem2, a);
         }
         if (sample) G.timer_suppress++;
       }
@@ -741,8 +745,8 @@ static int pcsi(double* X, const double* B) {
       a.map_ghost = (G.nranks == 1 && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC) ? 1 : 0;
       a.do_ew = do_ew; a.do_tripole = do_tp;
       a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
-      if (check) POP_LAUNCH(pcsi_iter_kernel<true>, grid1, PC_TX * PC_TY, 0, a);
-      else POP_LAUNCH(pcsi_iter_kernel<false>, grid1, PC_TX * PC_TY, 0, a);
+      if (check) POP_LAUNCH_PDL(pcsi_iter_kernel<true>, grid1, PC_TX * PC_TY, 0, a);
+      else POP_LAUNCH_PDL(pcsi_iter_kernel<false>, grid1, PC_TX * PC_TY, 0, a);
       if (a.advance && !a.map_ghost)
         POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = a.advance;

@@ -285,6 +285,12 @@ extern "C" int pop_init(const pop_config* cfg) {
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_b, cudaEventDisableTiming));
   }
   G.no_overlap = getenv("POP_B200_NO_OVERLAP") != nullptr && getenv("POP_B200_NO_OVERLAP")[0] == '1';
+  // programmatic dependent launch pays when the per-rank kernels are short (A/B in profiles/r1_ncu_summary.md: -7 %
+  // solver time on a 3600x300 strip, +1 % on the full 3600x2400 grid where the early CTAs compete with the
+  // overlapped velocity-finish kernel): on for strips up to 2.5 M points, POP_B200_PDL=1 / POP_B200_NO_PDL=1 override
+  G.no_pdl = (size_t)G.nxg * (size_t)(G.nyg / G.nranks) > 2500000;
+  if (getenv("POP_B200_PDL") != nullptr && getenv("POP_B200_PDL")[0] == '1') G.no_pdl = false;
+  if (getenv("POP_B200_NO_PDL") != nullptr && getenv("POP_B200_NO_PDL")[0] == '1') G.no_pdl = true;
   POP_REQUIRE(cfg->ns_boundary_type != POP_BNDY_TRIPOLE || cfg->ew_boundary_type == POP_BNDY_CYCLIC,
               "pop_init: a tripole grid needs a cyclic east-west boundary");
   POP_CHECK_CUDA(cudaMalloc(&G.d_iglob, sizeof(int) * G.nxb));

@@ -10,6 +10,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 #include "../../include/pop_b200.h"
@@ -67,6 +68,7 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
+  bool no_pdl = false;      // POP_B200_NO_PDL=1: plain stream-ordered launches in the P-CSI loop
   // pop_step_coupled: host<->device copies of the surface forcing / surface state on their own stream, overlapped
   // with the step (pop_abi.cu); the step calls the three hooks below at the points where the data are needed / final
   cudaStream_t stream_cp = nullptr;
@@ -182,6 +184,32 @@ bool resolve_name(const char* name, int tlev, std::string* out);
     kernel<<<(grid), (block), (smem), G.stream>>>(__VA_ARGS__);       \
     G.launches++;                                                     \
   } while (0)
+#endif
+// launches of the P-CSI loop (pass kernel <-> ghost fill / strip exchange, ~600 dependent launches per step): the
+// next kernel's launch overlaps the tail of the previous one (programmatic dependent launch); see pdl_wait()
+#ifndef POP_EMUL
+template <typename... KArgs, typename... Args>
+inline void pop_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define POP_LAUNCH_PDL(kernel, grid, block, smem, ...)                                              \
+  do {                                                                                              \
+    if (G.no_pdl) kernel<<<(grid), (block), (smem), G.stream>>>(__VA_ARGS__);                       \
+    else pop_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), G.stream, __VA_ARGS__);    \
+    G.launches++;                                                                                   \
+  } while (0)
+#else
+#define POP_LAUNCH_PDL POP_LAUNCH
 #endif
 int pop_post_launch(const char* what);  // cudaGetLastError -> POP error
 

@@ -136,6 +136,8 @@ template <typename T>
 __global__ void halo_center_scalar_local(T* __restrict__ a, int nz, int nxb, int nyb, size_t n2, int nxg,
                                          int do_ew, int do_tripole, int je0,
                                          const int* __restrict__ iglob, const int* __restrict__ jglob) {
+  pdl_wait();
+  pdl_trigger();
   const size_t n_ew = do_ew ? (size_t)nz * nyb * 4 : 0;
   const size_t n_tp = do_tripole ? (size_t)nz * 2 * nxb : 0;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_ew + n_tp;
@@ -180,6 +182,8 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
                 const double* __restrict__ fromN, volatile unsigned long long* myFlags,
                 unsigned long long seq, unsigned int* counter, int* err, int fuse_ew, int fuse_tripole, int nyb,
                 int je0, const int* __restrict__ iglob, const int* __restrict__ jglob) {
+  pdl_wait();
+  pdl_trigger();
   const size_t n = (size_t)nz * 2 * nxg;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // centre scalars: the east-west wrap of the rows this rank owns and the tripole fold only read physical
@@ -436,7 +440,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
       const bool cs = (loc == POP_LOC_CENTER && kind == POP_KIND_SCALAR);
       const int f_ew = (cs && ew == POP_BNDY_CYCLIC) ? 1 : 0;
       const int f_tp = (cs && ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1 && !rows_only) ? 1 : 0;
-      POP_LAUNCH(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
+      POP_LAUNCH_PDL(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
                  toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter,
                  G.p2p_err, f_ew, f_tp, nyb, G.je - 1, G.d_iglob, G.d_jglob);
       if (cs) return pop_post_launch("halo_update");  // wrap and fold were fused into the exchange
@@ -471,7 +475,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
     const int do_ew = (ew == POP_BNDY_CYCLIC) ? 1 : 0, do_tp = tripole_here ? 1 : 0;
     const size_t n = (do_ew ? (size_t)nz * nyb * 4 : 0) + (do_tp ? (size_t)nz * 2 * nxb : 0);
     if (n > 0)
-      POP_LAUNCH(halo_center_scalar_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb,
+      POP_LAUNCH_PDL(halo_center_scalar_local<T>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, nxb,
                  nyb, n2, nxg, do_ew, do_tp, G.je - 1, G.d_iglob, G.d_jglob);
     return pop_post_launch("halo_update");
   }
