@@ -422,6 +422,9 @@ struct Pcsi2Args {
   int do_ew, do_tripole, je0, nxg;
   const int *iglob, *jglob;
   int use_tma;
+  // tile rows of this launch: rowsel 0 -> blockIdx.y + row0; rowsel 1 -> the first and the last tile row (the rows a
+  // neighbouring strip needs), launched ahead of the interior so that the exchange overlaps the interior tiles
+  int rowsel, row0, nty;
   PopTmap tmX, tmC, tmB, tmQ, tmN, tmE, tmNE;  // 2-d tensor maps with the box of each staged tile
 };
 // cooperative asynchronous staging of a w x h window of a 2-d field (origin gi0,gj0; zero outside)
@@ -450,7 +453,8 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   uint64_t* s_bar = (uint64_t*)(sNE + P2_N_2);
   const BtView& v = a.v;
   const int nxb = v.nxb, nyb = v.nyb;
-  const int i0 = POP_NGHOST + blockIdx.x * P2_TX, j0 = POP_NGHOST + blockIdx.y * P2_TY;  // 0-based tile origin
+  const int trow = a.rowsel ? (blockIdx.y == 0 ? 0 : a.nty - 1) : (int)blockIdx.y + a.row0;
+  const int i0 = POP_NGHOST + blockIdx.x * P2_TX, j0 = POP_NGHOST + trow * P2_TY;  // 0-based tile origin
   const int tid = threadIdx.x;
   // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA):
   // seven TMA box copies issued by one thread (no per-element instructions), or per-thread cp.async
@@ -622,7 +626,7 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   if (SUM) {
     dd rsum = block_reduce_dd(acc);
     if (threadIdx.x == 0) {
-      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t b = (size_t)trow * gridDim.x + blockIdx.x;  // global tile index: the sum order does not depend on the split
       a.partials[b * 2] = rsum.hi;
       a.partials[b * 2 + 1] = rsum.lo;
     }
@@ -664,6 +668,9 @@ static int pcsi(double* X, const double* B) {
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
   const bool blocking = !G.no_pcsi_blocking;
+  // opt-in (POP_B200_OVERLAP_EXCHANGE=1): boundary tile rows first, strip exchange concurrent with the interior tiles
+  const bool xover = blocking && G.overlap_exchange && G.nranks > 1 && G.p2p_on && grid2.y >= 3 &&
+                     G.cfg.ew_boundary_type == POP_BNDY_CYCLIC;
   // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
   // and a host round trip on every rank, so its verdict is read one check period LATER, when it has long
   // arrived; X_m of the check is kept in a snapshot, and when a check turns out to have converged the answer
@@ -713,10 +720,31 @@ static int pcsi(double* X, const double* B) {
       a.do_ew = do_ew; a.do_tripole = do_tp; a.je0 = G.je - 1; a.nxg = G.nxg;
       a.iglob = G.d_iglob; a.jglob = G.d_jglob;
       a.use_tma = use_tma ? 1 : 0;
+      a.rowsel = 0; a.row0 = 0; a.nty = (int)grid2.y;
       if (use_tma) {
         a.tmX = tmXb[cur]; a.tmQ = tmQb[cur]; a.tmC = tmC; a.tmB = tmB; a.tmN = tmN; a.tmE = tmE; a.tmNE = tmNE;
       }
       const size_t smem2 = sizeof(double) * P2_SMEM_DOUBLES;
+      if (xover) {
+        // boundary tile rows first; their rows go to the neighbours on the exchange stream while the interior tiles run
+        a.rowsel = 1;
+        if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, dim3(grid2.x, 2, 1), P2_NT, smem2, a);
+        else POP_LAUNCH(pcsi_iter2_kernel<false>, dim3(grid2.x, 2, 1), P2_NT, smem2, a);
+        POP_CHECK_CUDA(cudaEventRecord(G.ev_xb, G.stream));
+        a.rowsel = 0; a.row0 = 1;
+        if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, dim3(grid2.x, grid2.y - 2, 1), P2_NT, smem2, a);
+        else POP_LAUNCH(pcsi_iter2_kernel<false>, dim3(grid2.x, grid2.y - 2, 1), P2_NT, smem2, a);
+        POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_x, G.ev_xb, 0));
+        std::swap(G.stream, G.stream_x);
+        const int rcx = halo_exchange_rows(Xb[cur ^ 1], 2);
+        std::swap(G.stream, G.stream_x);
+        POP_TRY(rcx);
+        POP_CHECK_CUDA(cudaEventRecord(G.ev_xx, G.stream_x));
+        POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_xx, 0));
+        POP_TRY(halo_ew_own_rows(Xb[cur ^ 1], 2));  // east-west ghost columns of the rows the interior tiles wrote
+        adv = 2;
+        nblk = nblk2;
+      } else {
       {
         // CUDA-event sample of the pass kernel alone (every 16th pass, uniformly over the solve; the solver
         // timers are otherwise off)
@@ -732,6 +760,7 @@ static int pcsi(double* X, const double* B) {
       POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = 2;
       nblk = nblk2;
+      }
     } else {
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
       PcsiArgs a;

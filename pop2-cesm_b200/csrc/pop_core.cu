@@ -271,13 +271,22 @@ extern "C" int pop_init(const pop_config* cfg) {
   G.sm_count = prop.multiProcessorCount;
   int prio_least = 0, prio_greatest = 0;
   POP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-  if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio_greatest));
+  // with the opt-in exchange overlap: exchange stream > main stream > side streams (lower number = higher priority)
+  const bool want_x = getenv("POP_B200_OVERLAP_EXCHANGE") != nullptr && getenv("POP_B200_OVERLAP_EXCHANGE")[0] == '1';
+  const int prio_main = (want_x && prio_least - prio_greatest >= 2) ? prio_greatest + 1 : prio_greatest;
+  if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio_main));
   if (!G.stream2) {
     // low priority: its CTAs take the slots the main stream's kernels leave free (tails, launch gaps)
     POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream2, cudaStreamNonBlocking, prio_least));
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
   }
+  if (!G.stream_x) {
+    POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream_x, cudaStreamNonBlocking, prio_greatest));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_xb, cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_xx, cudaEventDisableTiming));
+  }
+  G.overlap_exchange = getenv("POP_B200_OVERLAP_EXCHANGE") != nullptr && getenv("POP_B200_OVERLAP_EXCHANGE")[0] == '1';
   if (!G.stream_cp) {
     POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream_cp, cudaStreamNonBlocking, prio_least));
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_in, cudaEventDisableTiming));
@@ -342,6 +351,7 @@ extern "C" int pop_finalize(void) {
   if (G.stream) cudaStreamSynchronize(G.stream);
   if (G.stream2) cudaStreamSynchronize(G.stream2);
   if (G.stream_cp) cudaStreamSynchronize(G.stream_cp);
+  if (G.stream_x) cudaStreamSynchronize(G.stream_x);
   p2p_teardown();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();

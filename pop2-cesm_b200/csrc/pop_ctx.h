@@ -68,6 +68,9 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
+  bool overlap_exchange = false;  // POP_B200_OVERLAP_EXCHANGE=1 (opt-in): P-CSI boundary tiles first, exchange under the interior
+  cudaStream_t stream_x = nullptr;
+  cudaEvent_t ev_xb = nullptr, ev_xx = nullptr;
   bool no_pdl = false;      // POP_B200_NO_PDL=1: plain stream-ordered launches in the P-CSI loop
   // pop_step_coupled: host<->device copies of the surface forcing / surface state on their own stream, overlapped
   // with the step (pop_abi.cu); the step calls the three hooks below at the points where the data are needed / final
@@ -246,6 +249,8 @@ int halo_update(double* a, int nz, int loc, int kind, double fill);
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill);
 int halo_update_r4(float* a, int nz, int loc, int kind, float fill);
 int halo_rows_only(double* a, int nz);
+int halo_exchange_rows(double* a, int nz);  // peer-memory exchange of centre-scalar rows without the wrap of own rows
+int halo_ew_own_rows(double* a, int nz);    // the deferred east-west wrap
 int comm_init(int rank, int nranks, const char* id128);
 int comm_unique_id(char* id128);
 int comm_finalize();

@@ -188,8 +188,8 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // centre scalars: the east-west wrap of the rows this rank owns and the tripole fold only read physical
   // cells and only write ghost cells, so they ride along before the wait (halo_center_scalar_local)
-  if (fuse_ew || fuse_tripole) {
-    const size_t n_ew = fuse_ew ? (size_t)nz * nyb * 4 : 0;
+  if ((fuse_ew & 1) || fuse_tripole) {  // fuse_ew bit 0: wrap of the rows this rank owns; any bit: wrap of the pulled rows
+    const size_t n_ew = (fuse_ew & 1) ? (size_t)nz * nyb * 4 : 0;
     const size_t n_tp = fuse_tripole ? (size_t)nz * 2 * nxb : 0;
     for (size_t p = t0; p < n_ew + n_tp; p += stride) {
       if (p < n_ew) {
@@ -404,8 +404,10 @@ static int ensure_halo_buffers(size_t elems) {  // elems: doubles per message
   return POP_SUCCESS;
 }
 
+// xmode 1: the north-south exchange only (peer-memory path, centre scalars): neighbours' rows + their east-west ghost
+// columns + the tripole fold, but NOT the east-west wrap of the rows this rank owns (halo_ew_own_rows does that later)
 template <typename T>
-static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only = false) {
+static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only = false, int xmode = 0) {
   (void)fill;  // no eliminated land blocks in the strip decomposition: nothing receives fillValue
   POP_REQUIRE(G.initialized, "POP_HaloUpdate: library not initialized");
   POP_REQUIRE(a != nullptr && nz >= 1, "POP_HaloUpdate: bad array");
@@ -438,7 +440,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
       const unsigned wave = (unsigned)G.sm_count * 2;  // one resident wave (<= 8 CTAs of 256 threads fit per SM)
       if (grid > wave) grid = wave;
       const bool cs = (loc == POP_LOC_CENTER && kind == POP_KIND_SCALAR);
-      const int f_ew = (cs && ew == POP_BNDY_CYCLIC) ? 1 : 0;
+      const int f_ew = (cs && ew == POP_BNDY_CYCLIC) ? (xmode == 1 ? 2 : 1) : 0;
       const int f_tp = (cs && ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1 && !rows_only) ? 1 : 0;
       POP_LAUNCH_PDL(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
                  toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter,
@@ -514,6 +516,16 @@ int halo_update(double* a, int nz, int loc, int kind, double fill) {
 // arrays that were derived locally exact copies of the owner's values two ghost rows deep
 int halo_rows_only(double* a, int nz) {
   return halo_update_t<double>(a, nz, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0, true);
+}
+int halo_exchange_rows(double* a, int nz) {
+  POP_REQUIRE(G.nranks > 1 && G.p2p_on, "halo_exchange_rows: needs the peer-memory path");
+  return halo_update_t<double>(a, nz, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0, false, 1);
+}
+int halo_ew_own_rows(double* a, int nz) {
+  const size_t n = (size_t)nz * G.nyb * 4;
+  POP_LAUNCH(halo_center_scalar_local<double>, ew_grid(n) < 4096 ? ew_grid(n) : 4096, POP_EW_THREADS, 0, a, nz, G.nxb,
+             G.nyb, G.n2, G.nxg, 1, 0, G.je - 1, G.d_iglob, G.d_jglob);
+  return pop_post_launch("halo_ew_own_rows");
 }
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill) {
   return halo_update_t<int>(a, nz, loc, kind, fill);
