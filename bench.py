@@ -43,6 +43,7 @@ WORKLOADS = {
     # name: (nx, ny, km, vertical grid, dt[s])
     "tx0.1v3": (3600, 2400, 62, "tx0.1v3", 288.0),
     "gx1v7": (320, 384, 60, "gx1v7", 3600.0),
+    "gx3v7": (100, 116, 60, "gx3v7", 7200.0),          # BASELINE config 2: upwind3 + del2 + implicit vmix
     "tx_sample": (1200, 800, 62, "tx0.1v3", 864.0),     # bounded CPU sample of the tx0.1v3 workload
     "tiny": (120, 80, 12, "stretched", 2880.0),
     "tx_strip8": (3600, 300, 62, "tx0.1v3", 288.0),
@@ -65,6 +66,13 @@ def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
         # mixing (the reference's gx1 anisotropic viscosity is outside SURVEY section 8), KPP-shaped given coefficients, P-CSI
         kw.update(hmix_tracer_itype=c.HMIX_GM, hmix_momentum_itype=c.HMIX_DEL2, lvariable_hmixt=0, lvariable_hmixu=0,
                   ah=0.8e7, am=0.6e8)
+    if workload == "gx3v7":
+        # BASELINE config 2: third-order upwind advection (the gx production default), Laplacian mixing
+        # ah = 1.0e7 (namelist_defaults_pop.xml:1863), constant vertical mixing coefficients applied implicitly,
+        # ChronGear (the gx3 production solver), dt = 86400/12 s
+        kw.update(hmix_tracer_itype=c.HMIX_DEL2, hmix_momentum_itype=c.HMIX_DEL2, lvariable_hmixt=0, lvariable_hmixu=0,
+                  ah=1.0e7, am=1.0e8, vmix_itype=c.VMIX_CONST, vdc_kdim_halo=0, vdc_ndim=1,
+                  solver_choice=c.SOLVER_CHRONGEAR, tadvect=c.TADVECT_UPWIND3, ns_boundary_type=c.BNDY_CLOSED)
     if block:
         kw.update(block_size_x=block[0], block_size_y=block[1])
     return c.make_config(**kw), vg
@@ -142,13 +150,15 @@ class Fields:
 
 def static_inputs(workload):
     nx, ny, km, vg, _ = WORKLOADS[workload]
+    tripole = workload != "gx3v7"
     # metrics: analytic lat-lon, -78..+75 deg: cos(75 deg) = 0.26 bounds the cell aspect ratio like the real
     # displaced-pole tx0.1v3 grid (dx_min ~ dx_eq/4); going to 87 deg would make the elliptic system 4x stiffer
-    grid = syn.horiz_grid(nx, ny, tripole=True, lat0=-78.0, lat1=75.0)
+    grid = syn.horiz_grid(nx, ny, tripole=tripole, lat0=-78.0, lat1=75.0)
     dz = syn.vert_grid(vg, km)
     kmt = syn.bathymetry(nx, ny, km, 20240611 + 4)
-    kmt[-3:, :] = np.minimum(kmt[-3:, :], kmt[-3:, ::-1])
-    kmu = syn.kmu_from_kmt(kmt, ew_cyclic=True, ns_type=c.BNDY_TRIPOLE)
+    if tripole:
+        kmt[-3:, :] = np.minimum(kmt[-3:, :], kmt[-3:, ::-1])
+    kmu = syn.kmu_from_kmt(kmt, ew_cyclic=True, ns_type=c.BNDY_TRIPOLE if tripole else c.BNDY_CLOSED)
     return grid, dz, kmt, kmu
 
 
@@ -188,18 +198,20 @@ def fill_pop(p, F, nt):
     a = a.contiguous() if F.xp is not np else a
     p.scatter_levels("PGUESS", 0, 0, 1, ptr(a))
     p.halo_field("PGUESS", 0, c.LOC_CENTER, c.KIND_SCALAR)
-    for d in range(2):
-        for kk in range(km + 2):
-            a = F.vdc(d, kk)
+    if p.cfg.vmix_itype == c.VMIX_GIVEN:
+        for d in range(2):
+            for kk in range(km + 2):
+                a = F.vdc(d, kk)
+                a = a.contiguous() if F.xp is not np else a
+                p.scatter_levels("VDC", 0, d * (km + 2) + kk, 1, ptr(a))
+        for k in range(1, km + 1):
+            a = F.vvc(k)
             a = a.contiguous() if F.xp is not np else a
-            p.scatter_levels("VDC", 0, d * (km + 2) + kk, 1, ptr(a))
-    for k in range(1, km + 1):
-        a = F.vvc(k)
-        a = a.contiguous() if F.xp is not np else a
-        p.scatter_levels("VVC", 0, k - 1, 1, ptr(a))
-    p.halo_field("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
-    p.halo_field("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
-    p.solvers_prep()
+            p.scatter_levels("VVC", 0, k - 1, 1, ptr(a))
+        p.halo_field("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
+        p.halo_field("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
+    if p.cfg.solver_choice == c.SOLVER_PCSI:
+        p.solvers_prep()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -357,6 +369,7 @@ def run_pop(args):
     cells = float(nx) * ny * km
     ocean = float(np.sum(kmt))
     p_nxb, p_nyb = p.nxb, p.nyb
+    checksum = state_checksum(p)     # collective: every rank takes part
     p.finalize()
     if rank != 0:
         return
@@ -425,21 +438,43 @@ def run_pop(args):
                 "ms_per_step": ms_e2e / K, "api": "pop_step_coupled (host forcing in, host surface state out)"},
         "gpu_launches": launches, "clocks": sampler.summary(),
     }
+    out["state_checksum"] = checksum
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, steps=2)
+        base, check = cpu_baseline(args, steps=2, check=not args.no_check)
+        out["cpu_baseline"] = base
+        if check is not None:
+            out["parity_check"] = check
     print(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (test infrastructure) timed on the host cores on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def oracle_setup(sample, nt):
+def state_checksum(p):
+    """decomposition-independent fingerprint of the prognostic state after the last timed step: the global sum of every
+    level of T, S, U, V and of PSURF (each the correctly rounded exact sum: double-double accumulation in a fixed
+    order, pop_reduce.cu), added up exactly (math.fsum).  Equal hex strings at N = 1, 2, 4, 8 mean equal bits."""
+    n2 = p.nxb * p.nyb
+    out = {}
+    for name, nz, loc in (("T", p.km, c.LOC_CENTER), ("S", p.km, c.LOC_CENTER), ("UVEL", p.km, c.LOC_NECORNER),
+                          ("VVEL", p.km, c.LOC_NECORNER), ("PSURF", 1, c.LOC_CENTER)):
+        fld = "TRACER" if name in ("T", "S") else name
+        base = p.dptr(fld, c.TIME_CUR) + (8 * n2 * p.km if name == "S" else 0)
+        sums = [p.global_sum(base + 8 * n2 * k, loc) for k in range(nz)]
+        out[name] = float(math.fsum(sums)).hex()
+    return out
+
+
+def oracle_setup(sample, nt, threads):
     from oracle import oracle as O
     O.build()
+    so = O.build_fast()          # -O3 -march=native copy built on THIS host (SURVEY 8d); same sources, same IEEE arithmetic
     nx, ny, km, vg, dt = WORKLOADS[sample]
-    cfg, _ = make_cfg(sample, nt, block=(60, 40))
+    cfg, _ = make_cfg(sample, nt, block=(60, 40) if nx % 60 == 0 and ny % 40 == 0 else (nx // 4, ny // 4))
     grid, dz, kmt, kmu = static_inputs(sample)
-    o = O.Oracle(cfg)
+    o = O.Oracle(cfg, so)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the team size is set explicitly and read back
+    used = o.set_threads(threads)
     o.set_grid(grid, kmt, dz)
     if cfg.hmix_tracer_itype == c.HMIX_GM:
         o.scatter("TLAT", 0, grid["TLAT"])
@@ -458,29 +493,87 @@ def oracle_setup(sample, nt):
         o.grad_psurf(t)
     o.scatter("PGUESS", c.TIME_CUR, F.psurf("cur"))
     o.halo("PGUESS", c.TIME_CUR, c.LOC_CENTER, c.KIND_SCALAR)
-    o.scatter("VDC", 0, np.stack([np.stack([F.vdc(d, kk) for kk in range(km + 2)]) for d in range(2)]))
-    o.halo("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
-    o.scatter("VVC", 0, np.stack([F.vvc(k) for k in range(1, km + 1)]))
-    o.halo("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
-    assert o.solvers_prep() == 0
-    return o, float(nx) * ny * km
+    if cfg.vmix_itype == c.VMIX_GIVEN:
+        o.scatter("VDC", 0, np.stack([np.stack([F.vdc(d, kk) for kk in range(km + 2)]) for d in range(2)]))
+        o.halo("VDC", 0, c.LOC_CENTER, c.KIND_SCALAR)
+        o.scatter("VVC", 0, np.stack([F.vvc(k) for k in range(1, km + 1)]))
+        o.halo("VVC", 0, c.LOC_NECORNER, c.KIND_SCALAR)
+    if cfg.solver_choice == c.SOLVER_PCSI:
+        assert o.solvers_prep() == 0
+    return o, float(nx) * ny * km, used, cfg
 
 
-def cpu_baseline(args, steps):
+CHECK_FIELDS = ("TRACER", "UVEL", "VVEL", "RHO", "PSURF", "UBTROP", "VBTROP")
+
+
+def compare_fields(o, p):
+    """field-max and pointwise relative error (absolute floor 1e-3 of the field maximum) and zero-mask equality of the
+    current time level, oracle vs library"""
+    worst, worst_pt, masks_equal, nonid = 0.0, 0.0, True, 0
+    for name in CHECK_FIELDS:
+        a = o.gather(name, c.TIME_CUR).reshape(-1, o.cfg.ny_global, o.cfg.nx_global)
+        b = p.gather(name, c.TIME_CUR)
+        d = np.abs(a - b)
+        s = float(np.max(np.abs(a)))
+        if s > 0.0:
+            worst = max(worst, float(d.max()) / s)
+            worst_pt = max(worst_pt, float(np.max(d / np.maximum(np.abs(a), 1.0e-3 * s))))
+        masks_equal = masks_equal and bool(np.array_equal(a == 0.0, b == 0.0))
+        nonid += int(np.count_nonzero(d))
+    return worst, worst_pt, masks_equal, nonid
+
+
+def cpu_sample_name(workload):
+    return workload if workload in ("tiny", "gx1v7", "gx3v7") else "tx_sample"
+
+
+def cpu_baseline(args, steps, check):
+    """The CPU oracle on the bounded sample of the workload, all host cores: a forward-Euler step, one leapfrog step, then
+    `steps` timed leapfrog steps.  With check: the library advances the same sample next to it (a second, small instance
+    after the benchmark instance has been finalised) and every step is compared -- the parity gate at the benchmark
+    configuration (tx0.1v3 options and vertical grid at 1200 x 800 x 62)."""
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    sample = args.workload if args.workload in ("tiny", "gx1v7") else "tx_sample"
-    o, cells = oracle_setup(sample, args.nt)
-    assert o.step(c.TS_EULER) == 0
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        assert o.step(c.TS_LEAPFROG) == 0
-    dt = time.perf_counter() - t0
+    sample = cpu_sample_name(args.workload)
+    o, cells, used, cfg = oracle_setup(sample, args.nt, cores)
+    p = None
+    result = None
+    if check:
+        grid, dz, kmt, kmu = static_inputs(sample)
+        pcfg, _ = make_cfg(sample, args.nt)
+        p = P.api.Pop(pcfg, None)
+        p.set_grid(grid, kmt, dz)
+        if pcfg.hmix_tracer_itype == c.HMIX_GM:
+            p.scatter("TLAT", 0, grid["TLAT"])
+            p.halo_field("TLAT", 0, c.LOC_CENTER, c.KIND_SCALAR)
+        fill_pop(p, Fields(np, pcfg.nx_global, pcfg.ny_global, pcfg.km, dz, kmt, kmu, slice(0, pcfg.ny_global)), args.nt)
+        result = {"workload": "%s %dx%dx%d (same options and vertical grid as the timed workload)"
+                              % ((sample,) + WORKLOADS[sample][:3]),
+                  "steps": [], "rtol_per_step": 1.0e-12, "ok": True}
+    dt = 0.0
+    for i, ts in enumerate([c.TS_EULER, c.TS_LEAPFROG] + [c.TS_LEAPFROG] * steps):
+        t0 = time.perf_counter()
+        assert o.step(ts) == 0
+        if i >= 2:
+            dt += time.perf_counter() - t0
+        if p is not None:
+            p.step(ts)
+            it_o, it_p = o.solver_diag()[0], p.solvers_get_diagnostics()[0]
+            e, ept, masks, nonid = compare_fields(o, p)
+            okay = (it_o == it_p) and masks and e <= 1.0e-12 * (i + 1)
+            result["steps"].append({"relerr_fieldmax": e, "relerr_pointwise_floor1e-3": ept, "zero_masks_equal": masks,
+                                    "solver_iterations": [it_o, it_p], "cells_not_bit_identical": nonid, "ok": okay})
+            result["ok"] = result["ok"] and okay
+    if p is not None:
+        p.finalize()
     nx, ny, km = WORKLOADS[sample][:3]
-    return {"value": cells * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-            "sample": "%d leapfrog steps of the same configuration on a %dx%dx%d sub-grid (60x40 blocks, OpenMP over "
-                      "blocks); CPU oracle = C restatement of the reference (the Fortran reference cannot be built here)"
-                      % (steps, nx, ny, km), "s_per_step": dt / steps}
+    base = {"value": cells * steps / dt, "unit": "cell-updates/s", "cores": used, "kind": "port",
+            "sample": "%d leapfrog steps of the same configuration on a %dx%dx%d %s (%dx%d blocks, OpenMP over blocks and "
+                      "solver loops, %d threads; oracle built -O3 -march=native on this host); CPU oracle = C restatement of "
+                      "the reference (the Fortran reference cannot be built here)"
+                      % (steps, nx, ny, km, "grid" if sample == args.workload else "sub-grid (1/9 of the timed grid: a full "
+                         "tx0.1v3 oracle step takes minutes)", cfg.block_size_x, cfg.block_size_y, used),
+            "s_per_step": dt / steps}
+    return base, result
 
 
 def run_reference(args):
@@ -488,11 +581,10 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    sample = args.workload if args.workload in ("tiny", "gx1v7") else "tx_sample"
-    o, cells = oracle_setup(sample, args.nt)
+    sample = cpu_sample_name(args.workload)
+    o, cells, used, cfg = oracle_setup(sample, args.nt, cores)
     W, K = max(args.warmup, 1), args.steps
-    W, K = min(W, 2), min(K, 5)     # bounded: ~6 s per step on 8 cores
+    W, K = min(W, 2), min(K, 5)     # bounded: a few seconds per step
     assert o.step(c.TS_EULER) == 0
     for _ in range(W - 1):
         assert o.step(c.TS_LEAPFROG) == 0
@@ -502,9 +594,13 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     nx, ny, km = WORKLOADS[sample][:3]
     val = cells * K / dt
-    desc = ("%d leapfrog steps of the %s configuration on a %dx%dx%d %s, all host cores (OpenMP over 60x40 "
-            "blocks)" % (K, args.workload, nx, ny, km, "grid" if sample == args.workload else "sub-grid"))
-    cfg, _ = make_cfg(args.workload, args.nt)
+    same = sample == args.workload
+    desc = ("%d leapfrog steps of the %s configuration on a %dx%dx%d %s, %d OpenMP threads (blocks of %dx%d; oracle built "
+            "-O3 -march=native on this host)" % (K, args.workload, nx, ny, km, "grid" if same else "sub-grid", used,
+                                                 cfg.block_size_x, cfg.block_size_y))
+    why = "" if same else (" -- same options, vertical grid and per-cell work as the GPU arm but 1/9 of its horizontal extent "
+                           "and dt scaled with dx (864 s): a full 3600x2400x62 oracle step takes minutes, the contract "
+                           "asks for a bounded sample; cell-updates/s is per-cell, so the ratio is indicative")
     print(json.dumps({
         "impl": "reference",
         "metric": "cell-updates/s, full baroclinic+barotropic step (tx0.1v3 shape)" if args.workload == "tx0.1v3"
@@ -512,8 +608,9 @@ def run_reference(args):
         "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (same seeded fields as the GPU arm)",
-        "config": {"workload": "%s configuration, bounded CPU sample %dx%dx%d nt=%d" % (args.workload, nx, ny, km, args.nt)},
-        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": {"workload": "%s configuration, bounded CPU sample %dx%dx%d nt=%d%s" % (args.workload, nx, ny, km, args.nt, why),
+                   "same_config": same, "omp_threads": used},
+        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": used, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "kind=port: the reference is Fortran (no compiler in this image); this is its C restatement oracle/",
     }))
@@ -528,6 +625,7 @@ def main():
     ap.add_argument("--workload", default="tx0.1v3", choices=list(WORKLOADS))
     ap.add_argument("--nt", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle-vs-library parity check of the CPU sample")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: device-resident timed region only")
     args = ap.parse_args()
     if args.impl == "reference":

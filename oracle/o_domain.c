@@ -21,6 +21,15 @@ double o_now(void) {
 }
 double oracle_timer(int id) { return (id >= 0 && id < OT_N) ? M.timer[id] : 0.0; }
 void oracle_timers_reset(void) { memset(M.timer, 0, sizeof(M.timer)); }
+/* OpenMP team size of the block loops (bench.py sets it explicitly: torchrun exports OMP_NUM_THREADS=1) */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_get_max_threads(void) { return 1; }
+#endif
 
 static void* zalloc(size_t n, size_t sz) {
   void* p = calloc(n ? n : 1, sz);
@@ -124,6 +133,7 @@ static inline int owner(int ig, int jg, int* il, int* jl) {
     const int nxb = M.nxb, nyb = M.nyb, nxg = M.cfg.nx_global, nyg = M.cfg.ny_global;             \
     const int tripole = (M.cfg.ns_boundary_type == POP_BNDY_TRIPOLE);                             \
     /* regular copies: physical source cells only, so update order is irrelevant */              \
+    _Pragma("omp parallel for schedule(static) if (nxg * nyg > 100000)")                        \
     for (int b = 0; b < M.nblocks; b++) {                                                         \
       if (!M.active[b]) continue;                                                                 \
       T* ab = a + (size_t)b * bstride;                                                            \
@@ -231,6 +241,8 @@ void oracle_halo_4d(double* a, int nz, int nt, int loc, int kind, double fill) {
 double oracle_global_sum(const double* a, int loc, const double* mask) {
   double localSum = 0.0;
   int tripole = (M.cfg.ns_boundary_type == POP_BNDY_TRIPOLE);
+  double* part = (double*)calloc(M.nblocks, sizeof(double));
+#pragma omp parallel for schedule(static) if (M.nblocks * M.n2 > 100000)
   for (int b = 0; b < M.nblocks; b++) {
     if (!M.active[b]) continue;
     const double* ab = B2(a, b);
@@ -246,14 +258,19 @@ double oracle_global_sum(const double* a, int loc, const double* mask) {
         if (ig[i - 1] > M.cfg.nx_global / 2)
           blockSum = blockSum - (mb ? ab[IX2(i, j)] * mb[IX2(i, j)] : ab[IX2(i, j)]);
     }
-    localSum = localSum + blockSum;
+    part[b] = blockSum;
   }
+  for (int b = 0; b < M.nblocks; b++) /* block order, as the serial loop */
+    if (M.active[b]) localSum = localSum + part[b];
+  free(part);
   return localSum;
 }
 /* POP_GlobalSumNfields2DR8 (:823): array(nxb,nyb,nfields,nblocks) */
 void oracle_global_sum_n(const double* a, int nf, int loc, const double* mask, double* out) {
   (void)loc;
   for (int f = 0; f < nf; f++) out[f] = 0.0;
+  double* part = (double*)calloc((size_t)M.nblocks * nf, sizeof(double));
+#pragma omp parallel for schedule(static) if (M.nblocks * M.n2 > 100000)
   for (int b = 0; b < M.nblocks; b++) {
     if (!M.active[b]) continue;
     for (int f = 0; f < nf; f++) {
@@ -263,9 +280,13 @@ void oracle_global_sum_n(const double* a, int nf, int loc, const double* mask, d
       for (int j = M.jb[b]; j <= M.je[b]; j++)
         for (int i = M.ib[b]; i <= M.ie[b]; i++)
           blockSum = blockSum + (mb ? ab[IX2(i, j)] * mb[IX2(i, j)] : ab[IX2(i, j)]);
-      out[f] = out[f] + blockSum;
+      part[(size_t)b * nf + f] = blockSum;
     }
   }
+  for (int b = 0; b < M.nblocks; b++)
+    if (M.active[b])
+      for (int f = 0; f < nf; f++) out[f] = out[f] + part[(size_t)b * nf + f];
+  free(part);
 }
 
 /* scatter physical cells of a global (nx_global, ny_global [,nz]) array; ghost cells untouched */

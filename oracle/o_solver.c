@@ -4,6 +4,8 @@
  * :1110-1151; POP_SolversRun :327-495 (clinic == tropic distribution, redistribution = copy);
  * pcg :1200-1503; PCSI :1510-1835; ChronGear :1841-2266; btropOperator :2376-2431;
  * PcsiLanczos :2699-2990; ratqr :3122-3222.  Diagonal preconditioner only.
+ * Block loops and element-wise loops run as OpenMP teams (the reference threads the same loops over blocks,
+ * POP_SolversMod.F90 "!$OMP PARALLEL DO PRIVATE(iblock)"); every global sum is combined in block order.
  */
 #include <math.h>
 #include <stdio.h>
@@ -84,6 +86,7 @@ static int pcg(double* X, const double* B) {
   const int maxIt = M.cfg.max_iterations, freq = M.cfg.convergence_check_freq;
   double *R = vec(), *S = vec(), *Q = vec(), *work0 = vec(), *work1 = vec();
   double eta0, eta1, rr = 0.0;
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (int b = 0; b < NB; b++) {
     o_btrop_operator(S, X, b);
     for (size_t q = 0; q < M.n2; q++) {
@@ -95,11 +98,13 @@ static int pcg(double* X, const double* B) {
   eta0 = 1.0;
   M.numIterations = maxIt;
   for (int m = 1; m <= maxIt; m++) {
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) {
       work1[q] = (M.btropWgtCenter[q] != 0.0) ? R[q] / M.btropWgtCenter[q] : 0.0;
       work0[q] = R[q] * work1[q];
     }
     eta1 = gsum(work0);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       for (size_t q = 0; q < M.n2; q++) B2(S, b)[q] = B2(work1, b)[q] + B2(S, b)[q] * (eta1 / eta0);
       o_btrop_operator(Q, S, b);
@@ -108,6 +113,7 @@ static int pcg(double* X, const double* B) {
     halo(Q);
     eta0 = eta1;
     eta1 = eta0 / gsum(work0);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       for (size_t q = 0; q < M.n2; q++) {
         B2(X, b)[q] = B2(X, b)[q] + eta1 * B2(S, b)[q];
@@ -145,12 +151,15 @@ static int chrongear(double* X, const double* B) {
   (void)cgRho;
   M.numIterations = maxIt;
   set_a0r(A0R);
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (int b = 0; b < NB; b++) {
     o_btrop_operator(S, X, b);
     for (size_t q = 0; q < M.n2; q++) B2(R, b)[q] = B2(B, b)[q] - B2(S, b)[q];
   }
   halo(R);
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (size_t q = 0; q < NTOT; q++) Z[q] = R[q] * A0R[q];
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (int b = 0; b < NB; b++) {
     double *W1 = WORKN + ((size_t)b * 2) * M.n2, *W2 = W1 + M.n2;
     for (size_t q = 0; q < M.n2; q++) {
@@ -165,13 +174,16 @@ static int chrongear(double* X, const double* B) {
   cgRhoOld = sumN[0];
   cgSigma = sumN[1];
   cgAlpha = cgRhoOld / cgSigma;
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (size_t q = 0; q < NTOT; q++) {
     X[q] = X[q] + cgAlpha * S[q];
     R[q] = R[q] - cgAlpha * Q[q];
   }
   for (int m = 1; m <= maxIt; m++) {
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) Z[q] = R[q] * A0R[q];
     halo(Z);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       double *W1 = WORKN + ((size_t)b * 2) * M.n2, *W2 = W1 + M.n2;
       o_btrop_operator(AZ, Z, b);
@@ -187,6 +199,7 @@ static int chrongear(double* X, const double* B) {
     cgSigma = cgDelta - (cgBeta * cgBeta) * cgSigma;
     cgAlpha = cgRho / cgSigma;
     cgRhoOld = cgRho;
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       for (size_t q = 0; q < M.n2; q++) {
         B2(S, b)[q] = B2(Z, b)[q] + cgBeta * B2(S, b)[q];
@@ -228,15 +241,18 @@ static int pcsi(double* X, const double* B) {
   double csbeta = (M.PcsiMaxEigs + M.PcsiMinEigs) / (M.PcsiMaxEigs - M.PcsiMinEigs);
   double csy = csbeta / csalpha;
   double csomga = 2.0 / csy;
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (int b = 0; b < NB; b++) {
     o_btrop_operator(S, X, b);
     for (size_t q = 0; q < M.n2; q++) B2(R, b)[q] = B2(B, b)[q] - B2(S, b)[q];
   }
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (size_t q = 0; q < NTOT; q++) {
     R[q] = R[q] * A0R[q];
     Q[q] = (1.0 / csy) * R[q];
   }
   halo(Q);
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (int b = 0; b < NB; b++) {
     for (size_t q = 0; q < M.n2; q++) B2(X, b)[q] = B2(X, b)[q] + B2(Q, b)[q];
     o_btrop_operator(S, X, b);
@@ -246,9 +262,11 @@ static int pcsi(double* X, const double* B) {
   M.numIterations = maxIt;
   for (int m = 1; m <= maxIt; m++) {
     csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) R[q] = R[q] * A0R[q];
     halo(R);
     int check = (m % freq == 0) && (m >= start);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       for (size_t q = 0; q < M.n2; q++) {
         B2(Q, b)[q] = csomga * B2(R, b)[q] + (csy * csomga - 1.0) * B2(Q, b)[q];
@@ -336,10 +354,13 @@ static int pcsi_lanczos(void) {
   double csa, csb, csc, mineig, u, v;
   int rc = 0;
   set_a0r(A0R);
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (size_t q = 0; q < NTOT; q++) { R[q] = 1.0; Q[q] = 0.0; Q1[q] = 0.0; }
+  _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
   for (size_t q = 0; q < NTOT; q++) { S[q] = R[q] * A0R[q]; WORK[q] = S[q] * R[q]; }
   csc = -gsum(WORK);
   if (csc > 0.0) {
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) Q[q] = (1 / sqrt(csc)) * R[q];
   } else {
     rc = -1;
@@ -350,8 +371,10 @@ static int pcsi_lanczos(void) {
   M.lanczos_steps = 0;
   for (int m = 1; m <= maxstep; m++) {
     M.lanczos_steps = m;
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) P[q] = Q[q] * A0R[q];
     halo(P);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (int b = 0; b < NB; b++) {
       o_btrop_operator(WORK1, P, b);
       for (size_t q = 0; q < M.n2; q++) {
@@ -360,8 +383,10 @@ static int pcsi_lanczos(void) {
       }
     }
     csa = -gsum(WORK);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) R[q] = R[q] - csa * Q[q];
     halo(R);
+    _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
     for (size_t q = 0; q < NTOT; q++) { S[q] = R[q] * A0R[q]; WORK[q] = S[q] * R[q]; }
     csc = -gsum(WORK);
     csb = sqrt(csc);
@@ -373,6 +398,7 @@ static int pcsi_lanczos(void) {
       u = (u > c) ? u : c;
     }
     if (csb != 0.0) {
+      _Pragma("omp parallel for schedule(static) if (NTOT > 100000)")
       for (size_t q = 0; q < NTOT; q++) { Q1[q] = Q[q]; Q[q] = (1 / csb) * R[q]; }
     } else {
       rc = -1;

@@ -24,13 +24,36 @@ def build():
     subprocess.check_call(["make", "-s", "-C", HERE], stdout=subprocess.DEVNULL)
 
 
-def lib():
+def build_fast():
+    """TIMING copy (bench.py only): -O3 -march=native, built on the host it runs on; the file name carries a
+    hash of that host's CPU model and flags so that a copy built elsewhere is never loaded."""
+    import hashlib
+    try:
+        info = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        info = [os.uname().machine]
+    tag = hashlib.sha1("".join(info).encode()).hexdigest()[:10]
+    so = os.path.join(HERE, "libpop_oracle_fast_%s.so" % tag)
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
+        subprocess.check_call(["make", "-s", "-C", HERE, "fast", "FAST_SO=" + so], stdout=subprocess.DEVNULL)
+    return so
+
+
+_LIBS = {}
+
+
+def lib(so=None):
+    """the checker build by default; bench.py passes the path of its timing copy (each shared object has its own
+    model state, so both can live in one process)"""
     global _LIB
-    if _LIB is None:
-        so = os.path.join(HERE, "libpop_oracle.so")
+    so = so or os.path.join(HERE, "libpop_oracle.so")
+    if so not in _LIBS:
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)
+        L.oracle_get_max_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_field.restype = C.c_void_p
         L.oracle_field.argtypes = [C.c_char_p, C.c_int]
         L.oracle_global_sum.restype = C.c_double
@@ -45,8 +68,10 @@ def lib():
         L.oracle_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_gather_i4.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_set_grid.argtypes = [C.c_void_p] * 11
-        _LIB = L
-    return _LIB
+        _LIBS[so] = L
+        if so.endswith("libpop_oracle.so"):
+            _LIB = L
+    return _LIBS[so]
 
 
 def _p(a):
@@ -56,8 +81,8 @@ def _p(a):
 class Oracle:
     """One oracle model instance (the C side is a singleton, like the Fortran modules)."""
 
-    def __init__(self, cfg):
-        self.L = lib()
+    def __init__(self, cfg, so=None):
+        self.L = lib(so)
         self.cfg = cfg
         assert self.L.oracle_init(C.byref(cfg)) == 0
         nb = C.c_int.in_dll(self.L, "M")  # not used; sizes come from cfg
@@ -205,3 +230,8 @@ class Oracle:
 
     def timer(self, i):
         return self.L.oracle_timer(i)
+
+    def set_threads(self, n):
+        """OpenMP team size of the block loops; returns the size actually in effect"""
+        self.L.oracle_set_threads(int(n))
+        return self.L.oracle_get_max_threads()

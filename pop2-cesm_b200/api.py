@@ -303,6 +303,10 @@ class Pop:
             self._ck(self.L.pop_halo_update_4d_r8(_p(a), a.shape[1], a.shape[0], fieldLoc, fieldKind, float(fillValue)))
 
     def global_sum(self, array, fieldLoc, mMask=None):
+        if isinstance(array, (int, np.integer)):   # device pointer of one padded 2-d field
+            s = C.c_double()
+            self._ck(self.L.pop_global_sum_2d_r8(_p(array), fieldLoc, _p(mMask), C.byref(s)))
+            return s.value
         a = np.ascontiguousarray(array, dtype=np.float64)
         if a.ndim == 2:
             s = C.c_double()

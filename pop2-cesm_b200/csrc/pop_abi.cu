@@ -573,6 +573,11 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
   if (STF) { POP_TRY(find_field("pop_step_coupled", "STF", 0, &f)); POP_TRY(strip_copy(f, (void*)STF, true, 0, G.nt)); }
   const bool side = !G.no_overlap && (SMF || SHF_QSW || FW);
   cudaStream_t st_in = side ? G.stream_cp : G.stream;
+  if (side) {
+    // the copy stream must not overwrite SMF / FW while kernels of a previous (unsynchronised) pop_step still read them
+    POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_a, G.stream));
+    POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_cp, G.ev_cp_a, 0));
+  }
   if (SMF) { POP_TRY(find_field("pop_step_coupled", "SMF", 0, &f)); POP_TRY(strip_copy(f, (void*)SMF, true, 0, 2, st_in)); }
   if (SHF_QSW) { POP_TRY(find_field("pop_step_coupled", "SHF_QSW", 0, &f)); POP_TRY(strip_copy(f, (void*)SHF_QSW, true, 0, 1, st_in)); }
   if (FW) { POP_TRY(find_field("pop_step_coupled", "FW", 0, &f)); POP_TRY(strip_copy(f, (void*)FW, true, 0, 1, st_in)); }

@@ -294,6 +294,9 @@ extern "C" int pop_init(const pop_config* cfg) {
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cp_b, cudaEventDisableTiming));
   }
   G.no_overlap = getenv("POP_B200_NO_OVERLAP") != nullptr && getenv("POP_B200_NO_OVERLAP")[0] == '1';
+  G.finish_mode = G.no_overlap ? 2 : 0;
+  if (!G.no_overlap && getenv("POP_B200_OVERLAP_FINISH") != nullptr && getenv("POP_B200_OVERLAP_FINISH")[0] == '1')
+    G.finish_mode = 1;
   // programmatic dependent launch pays when the per-rank kernels are short (A/B in profiles/r1_ncu_summary.md: -7 %
   // solver time on a 3600x300 strip, +1 % on the full 3600x2400 grid where the early CTAs compete with the
   // overlapped velocity-finish kernel): on for strips up to 2.5 M points, POP_B200_PDL=1 / POP_B200_NO_PDL=1 override

@@ -68,6 +68,10 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
+  // velocity finish (impvmixu + Uold + mean removal + mask): 0 = one kernel after the barotropic solve that also adds
+  // UBTROP/VBTROP(new) (default); 1 = on the side stream under the solve, separate add-barotropic kernel
+  // (POP_B200_OVERLAP_FINISH=1, the round-1 layout); 2 = inside baroclinic_driver (POP_B200_NO_OVERLAP=1)
+  int finish_mode = 0;
   bool overlap_exchange = false;  // POP_B200_OVERLAP_EXCHANGE=1 (opt-in): P-CSI boundary tiles first, exchange under the interior
   cudaStream_t stream_x = nullptr;
   cudaEvent_t ev_xb = nullptr, ev_xx = nullptr;
@@ -307,7 +311,10 @@ struct MomentumIO {
   double* WUK;                    // slab modes: carried (in/out)
 };
 int momentum_column(int mode, int k, const MomentumIO& io);
-int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD);
+// UB/VB: also add the barotropic velocity (step_mod.F90:581-592) except on array row bt_skip_row (0-based; the tripole
+// seam row, which the NE-corner halo update symmetrises non-linearly: the caller adds there after the halo update)
+int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD, const double* UB = nullptr,
+                    const double* VB = nullptr, int bt_skip_row = -1);
 int grad_dev(int k, double* GX, double* GY, const double* F);
 int div_dev(int k, double* D, const double* UX, const double* UY);
 // barotropic + solver (pop_barotropic.cu)
@@ -321,7 +328,7 @@ int barotropic_driver_dev();
 // drivers (pop_step.cu)
 int dhdt_dev();
 int baroclinic_driver_dev(bool defer_finish = false);  // defer_finish: the caller launches momentum_finish
-int momentum_finish_new();                            // the deferred velocity finish on UVEL/VVEL(newtime)
+int momentum_finish_new(bool add_barotropic);         // the deferred velocity finish on UVEL/VVEL(newtime)
 int baroclinic_correct_adjust_dev();
 int step_dev(int ts_type);
 // grid (pop_grid.cu)

@@ -518,13 +518,24 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
 // =====================================================================================
 // impvmixu + velocity finish
 // =====================================================================================
-// Same layout as impvmixt (pop_tracer.cu): E(k) in shared memory, F1/F2 streamed in place through
-// UNEW/VNEW, loads issued one chunk of MF_CH levels ahead of the recurrence.
+// Same layout as impvmixt (pop_tracer.cu): one thread per column, 128 columns per CTA, E(k) in shared memory,
+// running level pointers, loads issued one chunk ahead of the recurrence, one reciprocal refinement shared by the
+// three quotients of a level (div_by).  Passes over the column:
+//   1 (down) forward elimination: reads RHS u,v and VVC, leaves F1,F2 in place
+//   2 (up)   back substitution fused with U = Uold + dU: the E(k) slot of a finished level is recycled for U(k),
+//            V(k) goes back to its (L2-resident) place
+//   3 (down) vertical means in the reference's summation order (U from shared memory)
+//   4 (down) mean removal + KMU mask [+ UBTROP/VBTROP(new): the `add barotropic` pass of step_mod.F90:581-592
+//            when the caller runs this kernel after the barotropic solve]
+// so DRAM sees RHS u,v, VVC, Uold, Vold in and U,V out (56 B/cell, 72 with the fused barotropic add that used to be
+// a 32 B/cell kernel of its own).
 #define MF_CH 8
+#define MF_BCH 4
 #define MF_THREADS 128
 __global__ void __launch_bounds__(MF_THREADS, 3)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
-                       const double* __restrict__ UOLD, const double* __restrict__ VOLD, double c2dtu,
+                       const double* __restrict__ UOLD, const double* __restrict__ VOLD,
+                       const double* __restrict__ UB, const double* __restrict__ VB, int bt_skip_row,
                        int implicit_vmix, int finish) {
   POP_DYN_SMEM(smem_raw);
   double* sE = (double*)smem_raw + threadIdx.x;
@@ -532,133 +543,215 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   const int j = (g.jb - 1) + blockIdx.y;
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
+  const int n2i = (int)n2;
   const int km = g.km, kmu = g.KMU[q];
   double* Un = UNEW + q;
   double* Vn = VNEW + q;
-  const double* VVCq = g.VVC + q;
-  const size_t vstr = (g.vvc_nk == 1) ? 0 : n2;
+  const int vstr = (g.vvc_nk == 1) ? 0 : n2i;
+  const size_t top = (size_t)(km - 1) * n2;
   if (implicit_vmix) {
-    double A, B, C, D, F1, F2;
+    double A, B, C, F1, F2;
     {
       const double hfac = c_vc.hfac_u[1];
-      A = c_vc.afac_u[1] * VVCq[0];
-      D = hfac + A;
-      const double e = A / D;
+      A = c_vc.afac_u[1] * g.VVC[q];
+      const RcpD rd = rcp_prepare(hfac + A);
+      const double e = div_by(A, rd);
       sE[0] = e;
       B = hfac * e;
-      F1 = hfac * Un[0] / D;
-      F2 = hfac * Vn[0] / D;
+      F1 = div_by(hfac * Un[0], rd);
+      F2 = div_by(hfac * Vn[0], rd);
       Un[0] = F1;
       Vn[0] = F2;
     }
+    const double* pc = g.VVC + q + vstr;  // next level to load (level 2)
+    const double* pu = Un + n2i;
+    const double* pv = Vn + n2i;
+    double* su = Un + n2i;                // next level to store
+    double* sv = Vn + n2i;
+    int nld = km - 1;
     double uv[MF_CH], vv[MF_CH], cv[MF_CH], un[MF_CH], vn[MF_CH], cn[MF_CH];
 #pragma unroll
-    for (int c = 0; c < MF_CH; c++) {
-      const int k = 2 + c;
-      const bool in = (k <= km);
-      cv[c] = in ? VVCq[(size_t)(k - 1) * vstr] : 0.0;
-      uv[c] = in ? Un[(size_t)(k - 1) * n2] : 0.0;
-      vv[c] = in ? Vn[(size_t)(k - 1) * n2] : 0.0;
-    }
-    for (int kb = 2; kb <= km; kb += MF_CH) {
+    for (int c = 0; c < MF_CH; c++) { uv[c] = 0.0; vv[c] = 0.0; cv[c] = 0.0; un[c] = 0.0; vn[c] = 0.0; cn[c] = 0.0; }
+    auto load_fwd = [&](double* cc, double* uu, double* ww) {
+      if (nld >= MF_CH) {
 #pragma unroll
-      for (int c = 0; c < MF_CH; c++) {
-        const int k = kb + MF_CH + c;
-        const bool in = (k <= km);
-        cn[c] = in ? VVCq[(size_t)(k - 1) * vstr] : 0.0;
-        un[c] = in ? Un[(size_t)(k - 1) * n2] : 0.0;
-        vn[c] = in ? Vn[(size_t)(k - 1) * n2] : 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < MF_CH; c++) {
-        const int k = kb + c;
-        if (k <= km) {
-          const double hfac = c_vc.hfac_u[k];
-          C = A;
-          A = c_vc.afac_u[k] * cv[c];
-          if (k < kmu) D = hfac + A + B;
-          else if (k == kmu) D = hfac + B;
-          if (k <= kmu) {
-            const double e = A / D;
-            sE[(size_t)(k - 1) * MF_THREADS] = e;
-            B = (hfac + B) * e;
-            F1 = (hfac * uv[c] + C * F1) / D;
-            F2 = (hfac * vv[c] + C * F2) / D;
-          } else {
-            F1 = 0.0;
-            F2 = 0.0;
-          }
-          Un[(size_t)(k - 1) * n2] = F1;
-          Vn[(size_t)(k - 1) * n2] = F2;
+        for (int c = 0; c < MF_CH; c++) {
+          cc[c] = *pc; uu[c] = *pu; ww[c] = *pv;
+          pc += vstr; pu += n2i; pv += n2i;
         }
-      }
+        nld -= MF_CH;
+      } else {
 #pragma unroll
-      for (int c = 0; c < MF_CH; c++) { cv[c] = cn[c]; uv[c] = un[c]; vv[c] = vn[c]; }
-    }
-    // back substitution: only levels k < kmu change; F1,F2 = F(km)
-#pragma unroll
-    for (int c = 0; c < MF_CH; c++) {
-      const int k = km - 1 - c;
-      uv[c] = (k >= 1) ? Un[(size_t)(k - 1) * n2] : 0.0;
-      vv[c] = (k >= 1) ? Vn[(size_t)(k - 1) * n2] : 0.0;
-    }
-    for (int kt = km - 1; kt >= 1; kt -= MF_CH) {
-#pragma unroll
-      for (int c = 0; c < MF_CH; c++) {
-        const int k = kt - MF_CH - c;
-        un[c] = (k >= 1) ? Un[(size_t)(k - 1) * n2] : 0.0;
-        vn[c] = (k >= 1) ? Vn[(size_t)(k - 1) * n2] : 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < MF_CH; c++) {
-        const int k = kt - c;
-        if (k >= 1) {
-          double f1 = uv[c], f2 = vv[c];
-          if (k < kmu) {
-            const double e = sE[(size_t)(k - 1) * MF_THREADS];
-            f1 = f1 + e * F1;
-            f2 = f2 + e * F2;
-            Un[(size_t)(k - 1) * n2] = f1;
-            Vn[(size_t)(k - 1) * n2] = f2;
+        for (int c = 0; c < MF_CH; c++)
+          if (c < nld) {
+            cc[c] = *pc; uu[c] = *pu; ww[c] = *pv;
+            pc += vstr; pu += n2i; pv += n2i;
           }
-          F1 = f1;
-          F2 = f2;
-        }
+        nld = 0;
       }
+    };
+    auto fwd_level = [&](int k, double vvc, double ru, double rw) {
+      const double hfac = c_vc.hfac_u[k];
+      C = A;
+      A = c_vc.afac_u[k] * vvc;
+      if (k <= kmu) {
+        const RcpD rd = rcp_prepare((k < kmu) ? hfac + A + B : hfac + B);
+        const double e = div_by(A, rd);
+        sE[(k - 1) * MF_THREADS] = e;
+        B = (hfac + B) * e;
+        F1 = div_by(hfac * ru + C * F1, rd);
+        F2 = div_by(hfac * rw + C * F2, rd);
+      } else {
+        F1 = 0.0;
+        F2 = 0.0;
+      }
+      *su = F1;
+      *sv = F2;
+      su += n2i;
+      sv += n2i;
+    };
+    auto fwd_chunk = [&](int kb, const double* cc, const double* uu, const double* ww) {
+      if (kb + MF_CH - 1 <= km) {
 #pragma unroll
-      for (int c = 0; c < MF_CH; c++) { uv[c] = un[c]; vv[c] = vn[c]; }
+        for (int c = 0; c < MF_CH; c++) fwd_level(kb + c, cc[c], uu[c], ww[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < MF_CH; c++)
+          if (kb + c <= km) fwd_level(kb + c, cc[c], uu[c], ww[c]);
+      }
+    };
+    load_fwd(cv, uv, vv);
+    for (int kb = 2; kb <= km; kb += 2 * MF_CH) {  // two register sets, no copies
+      load_fwd(cn, un, vn);
+      fwd_chunk(kb, cv, uv, vv);
+      if (kb + MF_CH <= km) {
+        load_fwd(cv, uv, vv);
+        fwd_chunk(kb + MF_CH, cn, un, vn);
+      }
+    }
+    // ---- back substitution (only levels k < kmu change; F1,F2 = F(km)), fused with U = Uold + dU when finishing
+    if (finish) {
+      const double u = UOLD[top + q] + F1, v = VOLD[top + q] + F2;
+      sE[(km - 1) * MF_THREADS] = u;
+      Vn[top] = v;
+    }
+    const double* qu = Un + top - n2i;  // next level to load (km-1), going up
+    const double* qv = Vn + top - n2i;
+    const double* qo = finish ? UOLD + q + top - n2i : Un;
+    const double* qp = finish ? VOLD + q + top - n2i : Vn;
+    double* tu = Un + top - n2i;        // next level to store
+    double* tv = Vn + top - n2i;
+    nld = km - 1;
+    double f1[MF_BCH], f2[MF_BCH], o1[MF_BCH], o2[MF_BCH], g1[MF_BCH], g2[MF_BCH], p1[MF_BCH], p2[MF_BCH];
+#pragma unroll
+    for (int c = 0; c < MF_BCH; c++) { f1[c] = f2[c] = o1[c] = o2[c] = g1[c] = g2[c] = p1[c] = p2[c] = 0.0; }
+    auto load_bwd = [&](double* a1, double* a2, double* b1, double* b2) {
+      if (nld >= MF_BCH) {
+#pragma unroll
+        for (int c = 0; c < MF_BCH; c++) {
+          a1[c] = *qu; a2[c] = *qv;
+          qu -= n2i; qv -= n2i;
+          if (finish) { b1[c] = *qo; b2[c] = *qp; qo -= n2i; qp -= n2i; }
+        }
+        nld -= MF_BCH;
+      } else {
+#pragma unroll
+        for (int c = 0; c < MF_BCH; c++)
+          if (c < nld) {
+            a1[c] = *qu; a2[c] = *qv;
+            qu -= n2i; qv -= n2i;
+            if (finish) { b1[c] = *qo; b2[c] = *qp; qo -= n2i; qp -= n2i; }
+          }
+        nld = 0;
+      }
+    };
+    auto bwd_level = [&](int k, double a1, double a2, double b1, double b2) {
+      if (k < kmu) {
+        const double e = sE[(k - 1) * MF_THREADS];
+        a1 = a1 + e * F1;
+        a2 = a2 + e * F2;
+        if (!finish) { *tu = a1; *tv = a2; }
+      }
+      F1 = a1;
+      F2 = a2;
+      if (finish) {
+        sE[(k - 1) * MF_THREADS] = b1 + a1;  // U(k); E(k) is not needed any more
+        *tv = b2 + a2;
+      }
+      tu -= n2i;
+      tv -= n2i;
+    };
+    auto bwd_chunk = [&](int kt, const double* a1, const double* a2, const double* b1, const double* b2) {
+      if (kt - MF_BCH + 1 >= 1) {
+#pragma unroll
+        for (int c = 0; c < MF_BCH; c++) bwd_level(kt - c, a1[c], a2[c], b1[c], b2[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < MF_BCH; c++)
+          if (kt - c >= 1) bwd_level(kt - c, a1[c], a2[c], b1[c], b2[c]);
+      }
+    };
+    load_bwd(f1, f2, o1, o2);
+    for (int kt = km - 1; kt >= 1; kt -= 2 * MF_BCH) {
+      load_bwd(g1, g2, p1, p2);
+      bwd_chunk(kt, f1, f2, o1, o2);
+      if (kt - MF_BCH >= 1) {
+        load_bwd(f1, f2, o1, o2);
+        bwd_chunk(kt - MF_BCH, g1, g2, p1, p2);
+      }
+    }
+    if (!finish) return;
+  } else {
+    if (!finish) return;
+    // explicit vertical mixing: U = Uold + dU (baroclinic.F90:1077-1080)
+    const double* po = UOLD + q;
+    const double* pp = VOLD + q;
+    double* tv = Vn;
+    const double* pu = Un;
+#pragma unroll 4
+    for (int k = 1; k <= km; k++) {
+      sE[(k - 1) * MF_THREADS] = *po + *pu;
+      *tv = *pp + *tv;
+      po += n2i; pp += n2i; pu += n2i; tv += n2i;
     }
   }
-  if (!finish) return;
-  // U = Uold + dU ; remove the vertical mean ; KMU mask (baroclinic.F90:1077-1129)
+  // ---- remove the vertical mean, KMU mask (baroclinic.F90:1085-1129) [+ barotropic velocity, step_mod.F90:581-592]
   const double hur = g.HUR[q];
   double w1 = 0.0, w2 = 0.0;
+  {
+    const double* pv = Vn;
 #pragma unroll 8
-  for (int k = 1; k <= km; k++) {
-    const size_t o = (size_t)(k - 1) * n2;
-    const double u = UOLD[o + q] + Un[o], v = VOLD[o + q] + Vn[o];
-    Un[o] = u;
-    Vn[o] = v;
-    w1 = w1 + u * c_vc.dz[k];
-    w2 = w2 + v * c_vc.dz[k];
+    for (int k = 1; k <= km; k++) {
+      w1 = w1 + sE[(k - 1) * MF_THREADS] * c_vc.dz[k];
+      w2 = w2 + *pv * c_vc.dz[k];
+      pv += n2i;
+    }
   }
   w1 = w1 * hur;
   w2 = w2 * hur;
+  const bool addbt = (UB != nullptr) && (j != bt_skip_row);
+  const double ub = addbt ? UB[q] : 0.0, vb = addbt ? VB[q] : 0.0;
+  {
+    double* tu = Un;
+    double* tv = Vn;
 #pragma unroll 8
-  for (int k = 1; k <= km; k++) {
-    const size_t o = (size_t)(k - 1) * n2;
-    if (k <= kmu) {
-      Un[o] = Un[o] - w1;
-      Vn[o] = Vn[o] - w2;
-    } else {
-      Un[o] = 0.0;
-      Vn[o] = 0.0;
+    for (int k = 1; k <= km; k++) {
+      double u = 0.0, v = 0.0;
+      if (k <= kmu) {
+        u = sE[(k - 1) * MF_THREADS] - w1;
+        v = *tv - w2;
+        if (addbt) { u = u + ub; v = v + vb; }
+      }
+      *tu = u;
+      *tv = v;
+      tu += n2i;
+      tv += n2i;
     }
   }
 }
 
-static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD,
-                         int implicit_vmix, int finish) {
+static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD, const double* UB,
+                         const double* VB, int bt_skip_row, int implicit_vmix, int finish) {
   GridView g = grid_view();
   dim3 block(MF_THREADS, 1, 1), grid((unsigned)((G.nxg + MF_THREADS - 1) / MF_THREADS), (unsigned)G.ny_local, 1);
   const size_t smem = sizeof(double) * MF_THREADS * (size_t)G.km;
@@ -666,17 +759,19 @@ static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const d
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
-  POP_LAUNCH(momentum_finish_kernel, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, G.c2dtu, implicit_vmix, finish);
+  POP_LAUNCH(momentum_finish_kernel, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, implicit_vmix,
+             finish);
   return pop_post_launch("momentum_finish");
 }
 
 int impvmixu_dev(double* UNEW, double* VNEW) {
   ScopedTimer tm("VMIX_MOMENTUM_IMPLICIT");
-  return launch_finish(UNEW, VNEW, nullptr, nullptr, 1, 0);
+  return launch_finish(UNEW, VNEW, nullptr, nullptr, nullptr, nullptr, -1, 1, 0);
 }
-int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD) {
+int momentum_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD, const double* UB,
+                    const double* VB, int bt_skip_row) {
   ScopedTimer tm("MOMENTUM_FINISH");
-  return launch_finish(UNEW, VNEW, UOLD, VOLD, G.cfg.implicit_vertical_mix, 1);
+  return launch_finish(UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, G.cfg.implicit_vertical_mix, 1);
 }
 
 // =====================================================================================

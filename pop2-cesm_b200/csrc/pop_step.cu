@@ -44,9 +44,14 @@ int dhdt_dev() {
 }
 
 // ------------------------------------------------------------------ baroclinic_driver
-int momentum_finish_new() {
+// array row (0-based) of the tripole seam on the rank that owns it, else -1
+static int tripole_seam_row() {
+  return (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? G.je - 1 : -1;
+}
+int momentum_finish_new(bool add_barotropic) {
   return momentum_finish(fld_t("UVEL", G.newtime), fld_t("VVEL", G.newtime), fld_t("UVEL", G.oldtime),
-                         fld_t("VVEL", G.oldtime));
+                         fld_t("VVEL", G.oldtime), add_barotropic ? fld_t("UBTROP", G.newtime) : nullptr,
+                         add_barotropic ? fld_t("VBTROP", G.newtime) : nullptr, tripole_seam_row());
 }
 
 int baroclinic_driver_dev(bool defer_finish) {
@@ -204,10 +209,10 @@ int baroclinic_correct_adjust_dev() {
 // ------------------------------------------------------------------ step
 __global__ void add_barotropic_kernel(double* __restrict__ U, double* __restrict__ V,
                                       const double* __restrict__ UB, const double* __restrict__ VB,
-                                      const int* __restrict__ KMU, size_t n2) {
-  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                      const int* __restrict__ KMU, size_t n2, size_t q0, size_t nq) {
+  const size_t q = q0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y + 1;
-  if (q >= n2) return;
+  if (q >= q0 + nq) return;
   if (k <= KMU[q]) {
     const size_t c = (size_t)(k - 1) * n2 + q;
     U[c] = U[c] + UB[q];
@@ -482,15 +487,18 @@ int step_dev(int ts_type) {
   POP_TRY(set_timestep(ts_type));
   const int km = G.km;
   POP_TRY(dhdt_dev());
-  const bool overlap = !G.no_overlap;
-  POP_TRY(baroclinic_driver_dev(overlap));
+  // Velocity finish (impvmixu + Uold + vertical-mean removal + KMU mask, baroclinic.F90:1067-1129): nothing reads
+  // UVEL/VVEL(new) before the halo updates below, so by default it runs as ONE kernel after the barotropic solve and
+  // adds UBTROP/VBTROP(new) in its last pass (the reference's separate add at step_mod.F90:581-592; ghost cells get
+  // the same bits through the halo update, which copies / sign-flips sums exactly as it copies the addends)
+  const bool overlap = (G.finish_mode == 1), fused = (G.finish_mode == 0);
+  POP_TRY(baroclinic_driver_dev(overlap || fused));
   if (overlap) {
-    // fork: the velocity finish only touches UVEL/VVEL(new), which nothing reads before the halo updates
-    // below; the barotropic solve and the tracer corrector proceed on the main stream meanwhile
+    // fork: the barotropic solve and the tracer corrector proceed on the main stream meanwhile
     POP_CHECK_CUDA(cudaEventRecord(G.ev_fork, G.stream));
     POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_fork, 0));
     std::swap(G.stream, G.stream2);
-    const int rc = momentum_finish_new();
+    const int rc = momentum_finish_new(false);
     std::swap(G.stream, G.stream2);
     POP_TRY(rc);
     POP_CHECK_CUDA(cudaEventRecord(G.ev_join, G.stream2));
@@ -499,6 +507,7 @@ int step_dev(int ts_type) {
   POP_TRY(halo_update(fld("ZY"), 1, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
   POP_TRY(barotropic_driver_dev());
   POP_TRY(coupled_after_barotropic());
+  if (fused) POP_TRY(momentum_finish_new(true));
   POP_TRY(baroclinic_correct_adjust_dev());
   POP_TRY(coupled_after_corrector());
   if (overlap) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));  // join
@@ -510,10 +519,15 @@ int step_dev(int ts_type) {
   POP_TRY(halo_update(fld_t("VVEL", n_), km, POP_LOC_NECORNER, POP_KIND_VECTOR, 0.0));
   POP_TRY(halo_update(fld_t("RHO", n_), km, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
   POP_TRY(halo_update(fld_t("TRACER", n_), km * G.nt, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
-  {  // step_mod.F90:581-592
+  if (!fused) {  // step_mod.F90:581-592
     dim3 grid(ew_grid(G.n2), (unsigned)km, 1);
     POP_LAUNCH(add_barotropic_kernel, grid, POP_EW_THREADS, 0, fld_t("UVEL", n_), fld_t("VVEL", n_),
-               fld_t("UBTROP", n_), fld_t("VBTROP", n_), fldi("KMU"), G.n2);
+               fld_t("UBTROP", n_), fld_t("VBTROP", n_), fldi("KMU"), G.n2, (size_t)0, G.n2);
+  } else if (tripole_seam_row() >= 0) {  // the seam row, symmetrised by the halo updates above, gets its add now
+    dim3 grid(ew_grid((size_t)G.nxb), (unsigned)km, 1);
+    POP_LAUNCH(add_barotropic_kernel, grid, POP_EW_THREADS, 0, fld_t("UVEL", n_), fld_t("VVEL", n_),
+               fld_t("UBTROP", n_), fld_t("VBTROP", n_), fldi("KMU"), G.n2, (size_t)tripole_seam_row() * G.nxb,
+               (size_t)G.nxb);
   }
   POP_LAUNCH(pguess_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, fld("PGUESS"), fld_t("PSURF", n_),
              fld_t("PSURF", c), fld_t("PSURF", o), G.n2);  // step_mod.F90:634-640

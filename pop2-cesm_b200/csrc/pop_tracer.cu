@@ -811,7 +811,11 @@ int tracer_column(int mode, int k, const TracerIO& io) {
 // right-hand side F(k) is streamed in place through the output array (it is re-read by the back
 // substitution while still L2-resident), and every global load of a chunk of IV_CH levels is issued
 // one chunk ahead of the (division-bound) recurrence that consumes it, so the dependent chain never
-// waits on DRAM.  Registers stay small, so 3 CTAs are resident per SM.
+// waits on DRAM.  Level addresses are running pointers (one IMAD.WIDE per level and array; the first
+// version recomputed (k-1)*n2 in 64 bits per access, which was half of the kernel's instructions:
+// profiles/r1_ncu_summary.md), full chunks carry no bounds predicates, and the two quotients of a level
+// share one reciprocal refinement (div_by: the compiler's own division sequence, bit-identical).
+// ncu (profiles/): 12 warps/SM (E(k) footprint), HBM-bound target 64 B/cell for two tracers.
 #define IV_CH 8
 #define IV_THREADS 128
 template <bool CORRECT>
@@ -825,103 +829,149 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
   const int j = (g.jb - 1) + blockIdx.y;
   if (i > g.ie - 1 || j > g.je - 1) return;
   const size_t q = (size_t)j * g.nxb + i, n2 = g.n2;
+  const int n2i = (int)n2;  // elements per level (< 2^31): the level stride of every running pointer
   const int km = g.km, kmt = g.KMT[q];
   const double hfac1 = c_vc.hfac_t[1];
   const double H1 = varthick ? hfac1 + PSFC[q] / (POP_GRAV * c_vc.c2dtt[1]) : hfac1;
+  const int vstr = (g.vdc_nk == 1) ? 0 : n2i;
   for (int n = nfirst; n <= nlast; n++) {  // 1-based tracer index
     const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
-    // VDC(:,:,k,mt2) = VDCq[(k - vdc_k0) * n2] (a single level when vdc_nk == 1)
-    const double* VDCq = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q;
-    const size_t vstr = (g.vdc_nk == 1) ? 0 : n2;
-    const size_t voff = (g.vdc_nk == 1) ? (size_t)(1 - g.vdc_k0) * n2 : (size_t)(0 - g.vdc_k0) * n2;  // + k*vstr
+    // VDC(:,:,k,mt2) = VDC1[(k-1) * vstr] (a single level when vdc_nk == 1)
+    const double* VDC1 = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q + (size_t)(1 - g.vdc_k0) * n2;
     double* Tn = TNEW + (size_t)(n - 1) * km * n2 + q;
-    const double* To = CORRECT ? nullptr : TOLD + (size_t)(n - 1) * km * n2 + q;
+    const double* Bs = CORRECT ? Tn : TOLD + (size_t)(n - 1) * km * n2 + q;  // what the solution is added to
     double* Fb = CORRECT ? FB + q : Tn;
-    double A, B, C, D, Fm;
+    double A, B, C, Fm;
     {
-      A = c_vc.afac_t[1] * VDCq[voff + vstr];
-      D = H1 + A;
-      const double e = A / D;
+      A = c_vc.afac_t[1] * VDC1[0];
+      const RcpD rd = rcp_prepare(H1 + A);
+      const double e = div_by(A, rd);
       sE[0] = e;
       B = H1 * e;
       const double R1 = CORRECT ? RHS[(size_t)(n - 1) * n2 + q] : Tn[0];
-      Fm = hfac1 * R1 / D;
+      Fm = div_by(hfac1 * R1, rd);
       Fb[0] = Fm;
     }
     // ---- forward elimination, levels 2..km in chunks; loads of chunk c+1 are in flight during chunk c
+    const double* pv = VDC1 + vstr;  // VDC of the next level to load (level 2)
+    const double* pr = Tn + n2i;     // right-hand side of the next level to load
+    double* pf = Fb + n2i;           // F of the next level to store
+    int nld = km - 1;                // levels not loaded yet
     double rv[IV_CH], vv[IV_CH], rn[IV_CH], vn[IV_CH];
 #pragma unroll
-    for (int c = 0; c < IV_CH; c++) {
-      const int k = 2 + c;
-      vv[c] = (k <= km) ? VDCq[voff + (size_t)k * vstr] : 0.0;
-      rv[c] = (!CORRECT && k <= km) ? Tn[(size_t)(k - 1) * n2] : 0.0;
-    }
-    for (int kb = 2; kb <= km; kb += IV_CH) {
+    for (int c = 0; c < IV_CH; c++) { rv[c] = 0.0; vv[c] = 0.0; rn[c] = 0.0; vn[c] = 0.0; }
+    auto load_fwd = [&](double* v, double* r) {
+      if (nld >= IV_CH) {
 #pragma unroll
-      for (int c = 0; c < IV_CH; c++) {
-        const int k = kb + IV_CH + c;
-        vn[c] = (k <= km) ? VDCq[voff + (size_t)k * vstr] : 0.0;
-        rn[c] = (!CORRECT && k <= km) ? Tn[(size_t)(k - 1) * n2] : 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < IV_CH; c++) {
-        const int k = kb + c;
-        if (k <= km) {
-          C = A;
-          A = c_vc.afac_t[k] * vv[c];
-          const double hfac = c_vc.hfac_t[k];
-          double F;
-          if (k > kmt) {
-            F = 0.0;
-          } else {
-            if (k == kmt) D = hfac + B;
-            else D = hfac + A + B;
-            const double e = A / D;
-            sE[(size_t)(k - 1) * IV_THREADS] = e;
-            B = (hfac + B) * e;
-            if (CORRECT) F = C * Fm / D;
-            else F = (hfac * rv[c] + C * Fm) / D;
-          }
-          Fb[(size_t)(k - 1) * n2] = F;
-          Fm = F;
+        for (int c = 0; c < IV_CH; c++) {
+          v[c] = *pv;
+          pv += vstr;
+          if (!CORRECT) { r[c] = *pr; pr += n2i; }
         }
-      }
+        nld -= IV_CH;
+      } else {
 #pragma unroll
-      for (int c = 0; c < IV_CH; c++) { vv[c] = vn[c]; rv[c] = rn[c]; }
+        for (int c = 0; c < IV_CH; c++)
+          if (c < nld) {
+            v[c] = *pv;
+            pv += vstr;
+            if (!CORRECT) { r[c] = *pr; pr += n2i; }
+          }
+        nld = 0;
+      }
+    };
+    auto fwd_level = [&](int k, double vdc, double rhs) {
+      C = A;
+      A = c_vc.afac_t[k] * vdc;
+      const double hfac = c_vc.hfac_t[k];
+      double F;
+      if (k > kmt) {
+        F = 0.0;
+      } else {
+        const RcpD rd = rcp_prepare((k == kmt) ? hfac + B : hfac + A + B);
+        const double e = div_by(A, rd);
+        sE[(k - 1) * IV_THREADS] = e;
+        B = (hfac + B) * e;
+        F = CORRECT ? div_by(C * Fm, rd) : div_by(hfac * rhs + C * Fm, rd);
+      }
+      *pf = F;
+      pf += n2i;
+      Fm = F;
+    };
+    auto fwd_chunk = [&](int kb, const double* v, const double* r) {
+      if (kb + IV_CH - 1 <= km) {
+#pragma unroll
+        for (int c = 0; c < IV_CH; c++) fwd_level(kb + c, v[c], r[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < IV_CH; c++)
+          if (kb + c <= km) fwd_level(kb + c, v[c], r[c]);
+      }
+    };
+    load_fwd(vv, rv);
+    for (int kb = 2; kb <= km; kb += 2 * IV_CH) {  // two register sets, no copies
+      load_fwd(vn, rn);
+      fwd_chunk(kb, vv, rv);
+      if (kb + IV_CH <= km) {
+        load_fwd(vv, rv);
+        fwd_chunk(kb + IV_CH, vn, rn);
+      }
     }
     // ---- back substitution + final update, levels km..1 in chunks (Fm = F(km))
     double Fp = Fm;
-    {
-      double* t = Tn + (size_t)(km - 1) * n2;
-      const double base = CORRECT ? *t : To[(size_t)(km - 1) * n2];
-      *t = base + Fp;
-    }
-    // chunk covers levels kt, kt-1, ..., kt-IV_CH+1
+    const size_t top = (size_t)(km - 1) * n2;
+    Tn[top] = Bs[top] + Fp;
+    const double* qf = Fb + top - n2i;  // F of the next level to load (level km-1), going up
+    const double* qb = Bs + top - n2i;
+    double* qt = Tn + top - n2i;        // next level to store
+    nld = km - 1;
+    auto load_bwd = [&](double* f, double* b) {
+      if (nld >= IV_CH) {
 #pragma unroll
-    for (int c = 0; c < IV_CH; c++) {
-      const int k = km - 1 - c;
-      rv[c] = (k >= 1) ? Fb[(size_t)(k - 1) * n2] : 0.0;
-      vv[c] = (k >= 1) ? (CORRECT ? Tn[(size_t)(k - 1) * n2] : To[(size_t)(k - 1) * n2]) : 0.0;
-    }
-    for (int kt = km - 1; kt >= 1; kt -= IV_CH) {
-#pragma unroll
-      for (int c = 0; c < IV_CH; c++) {
-        const int k = kt - IV_CH - c;
-        rn[c] = (k >= 1) ? Fb[(size_t)(k - 1) * n2] : 0.0;
-        vn[c] = (k >= 1) ? (CORRECT ? Tn[(size_t)(k - 1) * n2] : To[(size_t)(k - 1) * n2]) : 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < IV_CH; c++) {
-        const int k = kt - c;
-        if (k >= 1) {
-          double F = rv[c];
-          if (k < kmt) F = F + sE[(size_t)(k - 1) * IV_THREADS] * Fp;
-          Tn[(size_t)(k - 1) * n2] = vv[c] + F;
-          Fp = F;
+        for (int c = 0; c < IV_CH; c++) {
+          f[c] = *qf;
+          b[c] = *qb;
+          qf -= n2i;
+          qb -= n2i;
         }
-      }
+        nld -= IV_CH;
+      } else {
 #pragma unroll
-      for (int c = 0; c < IV_CH; c++) { rv[c] = rn[c]; vv[c] = vn[c]; }
+        for (int c = 0; c < IV_CH; c++)
+          if (c < nld) {
+            f[c] = *qf;
+            b[c] = *qb;
+            qf -= n2i;
+            qb -= n2i;
+          }
+        nld = 0;
+      }
+    };
+    auto bwd_level = [&](int k, double f, double b) {
+      double F = f;
+      if (k < kmt) F = F + sE[(k - 1) * IV_THREADS] * Fp;
+      *qt = b + F;
+      qt -= n2i;
+      Fp = F;
+    };
+    auto bwd_chunk = [&](int kt, const double* f, const double* b) {
+      if (kt - IV_CH + 1 >= 1) {
+#pragma unroll
+        for (int c = 0; c < IV_CH; c++) bwd_level(kt - c, f[c], b[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < IV_CH; c++)
+          if (kt - c >= 1) bwd_level(kt - c, f[c], b[c]);
+      }
+    };
+    load_bwd(rv, vv);
+    for (int kt = km - 1; kt >= 1; kt -= 2 * IV_CH) {
+      load_bwd(rn, vn);
+      bwd_chunk(kt, rv, vv);
+      if (kt - IV_CH >= 1) {
+        load_bwd(rv, vv);
+        bwd_chunk(kt - IV_CH, rn, vn);
+      }
     }
   }
 }

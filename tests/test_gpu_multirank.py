@@ -16,7 +16,7 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("which", ["pcsi", "chrongear", "cyclic_pcg", "gm"])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_strips_are_bitwise_the_single_strip_run(which, world):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
