@@ -190,7 +190,11 @@ int pop_btrop_operator(double* AX, const double* X, int bid);
 int pop_solvers_prep(void); /* POP_SolversPrep: Lanczos eigenvalue bounds for PCSI */
 int pop_solvers_get_eigs(double* mineig, double* maxeig);
 
-/* ---- communication (mpi/POP_HaloMod.F90:1732,2766,4122; mpi/POP_ReductionsMod.F90:144,823) ---- */
+/* ---- communication (mpi/POP_HaloMod.F90:1732,2766,4122; mpi/POP_ReductionsMod.F90:144,823) ----
+   fillValue: the reference writes it into ghost cells that face an ELIMINATED land block (POP_HaloMod.F90:1911-1913).
+   The strip decomposition of this library eliminates no blocks, so no ghost cell ever receives it; ghost cells on a
+   closed boundary are left untouched exactly as in the reference (no message targets them).  The argument is kept for
+   the reference's signature and has no effect. */
 int pop_halo_update_2d_r8(double* array, int fieldLoc, int fieldKind, double fillValue);
 int pop_halo_update_3d_r8(double* array, int nz, int fieldLoc, int fieldKind, double fillValue);
 int pop_halo_update_4d_r8(double* array, int nz, int nt, int fieldLoc, int fieldKind,
@@ -214,8 +218,10 @@ int pop_barotropic_driver(void);                  /* barotropic.F90:267 */
 int pop_baroclinic_correct_adjust(void);          /* baroclinic.F90:1217 */
 int pop_step(int ts_type);                        /* step_mod.F90:126 */
 /* end-to-end step used by a coupled host: uploads this step's surface forcing from HOST
-   buffers (STF nt fields, SMF 2 fields, SHF_QSW, FW; physical strips), advances one step,
-   returns the new surface state (SST, SSS, PSURF, U1, V1: physical strips) to HOST buffers. */
+   buffers (STF nt fields, SMF 2 fields, FW; physical strips), advances one step,
+   returns the new surface state (SST, SSS, PSURF, U1, V1: physical strips) to HOST buffers.
+   SHF_QSW is accepted for the coupler's argument list but IGNORED (may be NULL): penetrative short-wave absorption
+   (add_sw_absorb, baroclinic.F90:2176) is not part of this path, so no kernel reads it and it is not copied. */
 int pop_step_coupled(int ts_type, const double* STF, const double* SMF, const double* SHF_QSW,
                      const double* FW, double* sfc_out /* 5 strips */);
 

@@ -236,11 +236,69 @@ void oracle_halo_4d(double* a, int nz, int nt, int loc, int kind, double fill) {
   M.timer[OT_HALO] += o_now() - t0;
 }
 
+/* The reference's REPRODUCIBLE build (mpi/POP_ReductionsMod.F90:279-283, :357-363) accumulates blockSum and
+   localSum in real(r16), reduces in r16 and rounds once to r8: the result is the correctly rounded exact sum and
+   does not depend on the block decomposition or the summation order.  oracle_set_reproducible(1) selects that
+   branch; the 113-bit accumulator is restated as a double-double (106 bits, error-free TwoSum), which rounds to the
+   same r8 value unless the exact sum lies within ~n * 2^-106 of a rounding boundary.  Products array*mask are formed
+   in r8 first, as in the Fortran expression. */
+static int g_repro = 0;
+void oracle_set_reproducible(int on) { g_repro = on ? 1 : 0; }
+int oracle_get_reproducible(void) { return g_repro; }
+typedef struct { double hi, lo; } odd;
+static inline odd odd_add_d(odd a, double b) {
+  double s = a.hi + b;
+  double bb = s - a.hi;
+  double e = (a.hi - (s - bb)) + (b - bb);
+  e += a.lo;
+  double hi = s + e;
+  double lo = e - (hi - s);
+  odd r = {hi, lo};
+  return r;
+}
+static inline odd odd_add(odd a, odd b) {
+  double s = a.hi + b.hi;
+  double bb = s - a.hi;
+  double e = (a.hi - (s - bb)) + (b.hi - bb);
+  e += a.lo + b.lo;
+  double hi = s + e;
+  double lo = e - (hi - s);
+  odd r = {hi, lo};
+  return r;
+}
+/* one block's contribution in r16-equivalent precision (tripole de-duplication included) */
+static odd block_sum_repro(const double* ab, const double* mb, int b, int loc) {
+  odd acc = {0.0, 0.0};
+  for (int j = M.jb[b]; j <= M.je[b]; j++)
+    for (int i = M.ib[b]; i <= M.ie[b]; i++)
+      acc = odd_add_d(acc, mb ? ab[IX2(i, j)] * mb[IX2(i, j)] : ab[IX2(i, j)]);
+  if (M.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && M.jblk[b] == M.nby &&
+      (loc == POP_LOC_NFACE || loc == POP_LOC_NECORNER)) {
+    int j = M.je[b];
+    const int* ig = M.i_glob + (size_t)b * M.nxb;
+    for (int i = M.ib[b]; i <= M.ie[b]; i++)
+      if (ig[i - 1] > M.cfg.nx_global / 2)
+        acc = odd_add_d(acc, -(mb ? ab[IX2(i, j)] * mb[IX2(i, j)] : ab[IX2(i, j)]));
+  }
+  return acc;
+}
+
 /* POP_GlobalSum2DR8: mpi/POP_ReductionsMod.F90:255-353 (per-block sums, j outer / i inner,
    tripole de-duplication :312-341, then the sum over blocks in block order) */
 double oracle_global_sum(const double* a, int loc, const double* mask) {
   double localSum = 0.0;
   int tripole = (M.cfg.ns_boundary_type == POP_BNDY_TRIPOLE);
+  if (g_repro) {
+    odd* pr = (odd*)calloc(M.nblocks, sizeof(odd));
+#pragma omp parallel for schedule(static) if (M.nblocks * M.n2 > 100000)
+    for (int b = 0; b < M.nblocks; b++)
+      if (M.active[b]) pr[b] = block_sum_repro(B2(a, b), mask ? B2(mask, b) : NULL, b, loc);
+    odd tot = {0.0, 0.0};
+    for (int b = 0; b < M.nblocks; b++)
+      if (M.active[b]) tot = odd_add(tot, pr[b]);
+    free(pr);
+    return tot.hi + tot.lo;
+  }
   double* part = (double*)calloc(M.nblocks, sizeof(double));
 #pragma omp parallel for schedule(static) if (M.nblocks * M.n2 > 100000)
   for (int b = 0; b < M.nblocks; b++) {
@@ -267,8 +325,18 @@ double oracle_global_sum(const double* a, int loc, const double* mask) {
 }
 /* POP_GlobalSumNfields2DR8 (:823): array(nxb,nyb,nfields,nblocks) */
 void oracle_global_sum_n(const double* a, int nf, int loc, const double* mask, double* out) {
-  (void)loc;
   for (int f = 0; f < nf; f++) out[f] = 0.0;
+  if (g_repro) {
+    for (int f = 0; f < nf; f++) {
+      odd tot = {0.0, 0.0};
+      for (int b = 0; b < M.nblocks; b++)
+        if (M.active[b])
+          tot = odd_add(tot, block_sum_repro(a + ((size_t)b * nf + f) * M.n2, mask ? B2(mask, b) : NULL, b, POP_LOC_CENTER));
+      out[f] = tot.hi + tot.lo;
+    }
+    (void)loc;
+    return;
+  }
   double* part = (double*)calloc((size_t)M.nblocks * nf, sizeof(double));
 #pragma omp parallel for schedule(static) if (M.nblocks * M.n2 > 100000)
   for (int b = 0; b < M.nblocks; b++) {

@@ -231,6 +231,10 @@ class Oracle:
     def timer(self, i):
         return self.L.oracle_timer(i)
 
+    def set_reproducible(self, on=True):
+        """the reference's REPRODUCIBLE build: global sums accumulated in real(r16) and rounded once"""
+        self.L.oracle_set_reproducible(1 if on else 0)
+
     def set_threads(self, n):
         """OpenMP team size of the block loops; returns the size actually in effect"""
         self.L.oracle_set_threads(int(n))

@@ -76,9 +76,13 @@ struct Stage {
           rc = POP_FAIL;
         }
     if (!outs.empty() || rc != POP_SUCCESS) cudaStreamSynchronize(G.stream);
+    // multi-rank: a peer-memory exchange that timed out inside this call must surface here, not at the next pop_step
+    if (rc == POP_SUCCESS && G.p2p_on) rc = p2p_check();
     return rc;
   }
 };
+// the drivers that exchange halos without going through Stage
+static int with_p2p_check(int rc) { return (rc == POP_SUCCESS && G.p2p_on) ? p2p_check() : rc; }
 
 int check_ready(const char* what, const pop_block* blk, bool need_blk) {
   POP_REQUIRE(G.initialized, "%s: pop_init has not been called", what);
@@ -100,7 +104,7 @@ extern "C" int pop_set_grid(const double* ULAT, const double* HTN, const double*
                             const double* DYT, const int* KMT, const double* dz) {
   POP_REQUIRE(G.initialized, "pop_set_grid: pop_init has not been called");
   POP_REQUIRE(ULAT && HTN && HTE && HUS && HUW && DXU && DYU && DXT && DYT && KMT && dz, "pop_set_grid: null argument");
-  return set_grid_host(ULAT, HTN, HTE, HUS, HUW, DXU, DYU, DXT, DYT, KMT, dz);
+  return with_p2p_check(set_grid_host(ULAT, HTN, HTE, HUS, HUW, DXU, DYU, DXT, DYT, KMT, dz));
 }
 
 // ------------------------------------------------------------------ field access
@@ -514,15 +518,15 @@ extern "C" int pop_dhdt(void) {
 }
 extern "C" int pop_baroclinic_driver(void) {
   POP_TRY(check_ready("baroclinic_driver", nullptr, false));
-  return baroclinic_driver_dev();
+  return with_p2p_check(baroclinic_driver_dev());
 }
 extern "C" int pop_barotropic_driver(void) {
   POP_TRY(check_ready("barotropic_driver", nullptr, false));
-  return barotropic_driver_dev();
+  return with_p2p_check(barotropic_driver_dev());
 }
 extern "C" int pop_baroclinic_correct_adjust(void) {
   POP_TRY(check_ready("baroclinic_correct_adjust", nullptr, false));
-  return baroclinic_correct_adjust_dev();
+  return with_p2p_check(baroclinic_correct_adjust_dev());
 }
 extern "C" int pop_step(int ts_type) {
   POP_TRY(check_ready("step", nullptr, false));
@@ -571,7 +575,10 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
   POP_TRY(check_ready("pop_step_coupled", nullptr, false));
   DevField* f;
   if (STF) { POP_TRY(find_field("pop_step_coupled", "STF", 0, &f)); POP_TRY(strip_copy(f, (void*)STF, true, 0, G.nt)); }
-  const bool side = !G.no_overlap && (SMF || SHF_QSW || FW);
+  // SHF_QSW is part of the coupler's forcing set but nothing on this path consumes it (penetrative short-wave
+  // absorption, add_sw_absorb, is outside SURVEY section 8): it is accepted and ignored -- not copied, not counted
+  (void)SHF_QSW;
+  const bool side = !G.no_overlap && (SMF || FW);
   cudaStream_t st_in = side ? G.stream_cp : G.stream;
   if (side) {
     // the copy stream must not overwrite SMF / FW while kernels of a previous (unsynchronised) pop_step still read them
@@ -579,7 +586,6 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
     POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_cp, G.ev_cp_a, 0));
   }
   if (SMF) { POP_TRY(find_field("pop_step_coupled", "SMF", 0, &f)); POP_TRY(strip_copy(f, (void*)SMF, true, 0, 2, st_in)); }
-  if (SHF_QSW) { POP_TRY(find_field("pop_step_coupled", "SHF_QSW", 0, &f)); POP_TRY(strip_copy(f, (void*)SHF_QSW, true, 0, 1, st_in)); }
   if (FW) { POP_TRY(find_field("pop_step_coupled", "FW", 0, &f)); POP_TRY(strip_copy(f, (void*)FW, true, 0, 1, st_in)); }
   if (side) {
     POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_in, G.stream_cp));

@@ -61,8 +61,14 @@ FORCING_LOC = {"STF": (c.LOC_CENTER, c.KIND_SCALAR), "TFW": (c.LOC_CENTER, c.KIN
                "SMF": (c.LOC_NECORNER, c.KIND_VECTOR)}
 
 
-def load_oracle(cs, block_size=None):
+def load_oracle(cs, block_size=None, reproducible=False):
+    """reproducible: the reference's REPRODUCIBLE build (global sums accumulated in real(r16), rounded once:
+    mpi/POP_ReductionsMod.F90:279-283,357-363).  The library's sums are double-double with one final rounding as well,
+    so in that mode every solver scalar -- and with it the whole step -- must agree BIT FOR BIT, whatever the block
+    decomposition.  With the default r8 sums the two sides differ by the rounding of the dot products (1e-12 bar)."""
+    from oracle import oracle as _O
     cfg = cs.cfg if block_size is None else c.copy_config(cs.cfg, block_size_x=block_size[0], block_size_y=block_size[1])
+    _O.lib().oracle_set_reproducible(1 if reproducible else 0)
     o = Oracle(cfg)
     o.set_grid(cs.grid, cs.kmt, cs.dz)
     for lev, t in LEVELS:
