@@ -43,6 +43,7 @@ enum { POP_SFC_VARTHICK = 1, POP_SFC_RIGID = 2, POP_SFC_OLDFREE = 3 };/* grid.F9
 enum { POP_STATE_MWJF = 2, POP_STATE_LINEAR = 4 };                    /* state_mod.F90:66-70 */
 enum { POP_STATE_RANGE_IGNORE = 1, POP_STATE_RANGE_ENFORCE = 3 };     /* state_mod.F90:79-82 */
 enum { POP_SOLVER_PCG = 1, POP_SOLVER_CHRONGEAR = 2, POP_SOLVER_PCSI = 3 };
+enum { POP_PRECOND_DIAGONAL = 0, POP_PRECOND_EVP = 1 };               /* POP_SolversMod.F90:120-126 */
 enum { POP_TS_LEAPFROG = 1, POP_TS_EULER = 2, POP_TS_AVG = 3,       /* step_mod.F90:302-320,663 */
        POP_TS_ROBERT = 4 };  /* leapfrog step closed by the Robert-Asselin-Williams filter, step_mod.F90:798,919-1354 */
 enum { POP_TIME_OLD = 0, POP_TIME_CUR = 1, POP_TIME_NEW = 2 };        /* prognostic.F90:63-68 */
@@ -95,6 +96,10 @@ typedef struct pop_config {
   /* vertical_mix_nml: convection_diff = 0 is convection_type = 'adjustment' with nconvad passes of convad
      (vertical_mix.F90:239,1888-2027; the reference default is 2). 0 passes = no convective adjustment. */
   int nconvad;
+  /* solvers: preconditionerChoice (POP_SolversMod.F90:120-126,709-722). 'diagonal' or 'evp' (the block preconditioner
+     of Hu et al.: 8 x 8 sub-blocks inverted by error-vector propagation, :2273-2369,2434-2696; production default
+     outside gx3v7, namelist_defaults_pop.xml:262-263); 'file' is not supported. */
+  int preconditioner_choice;
 } pop_config;
 
 /* block descriptor handed to slab routines: mirrors `type block`, source/blocks.F90:30-39 */
@@ -189,6 +194,10 @@ int pop_solvers_get_diagnostics(int* iterationCount, double* residual);
 int pop_btrop_operator(double* AX, const double* X, int bid);
 int pop_solvers_prep(void); /* POP_SolversPrep: Lanczos eigenvalue bounds for PCSI */
 int pop_solvers_get_eigs(double* mineig, double* maxeig);
+/* EVP preconditioner set-up (POP_SolversPrep :252-292, EvpPre :2434-2506): number of sub-blocks of this rank's block,
+   how many of them fall back to the diagonal (landIndx = 1), and the largest max|rinv*rin - I| of the influence-matrix
+   inverses -- the quantity the reference checks against 1e-8 (:2594-2614; pop_solvers_prep fails above that bound) */
+int pop_solvers_get_evp_diagnostics(int* subBlocks, int* landSubBlocks, double* maxInverseError);
 
 /* ---- communication (mpi/POP_HaloMod.F90:1732,2766,4122; mpi/POP_ReductionsMod.F90:144,823) ----
    fillValue: the reference writes it into ghost cells that face an ELIMINATED land block (POP_HaloMod.F90:1911-1913).

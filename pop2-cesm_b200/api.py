@@ -27,7 +27,7 @@ SYMBOLS = [
     "pop_gradp", "pop_grad", "pop_div", "pop_vdifft", "pop_vdiffu", "pop_impvmixt",
     "pop_impvmixt_correct", "pop_impvmixu", "pop_vmix_coeffs", "pop_state", "pop_solvers_run",
     "pop_solvers_diagonal", "pop_solvers_get_diagnostics", "pop_btrop_operator", "pop_solvers_prep",
-    "pop_solvers_get_eigs", "pop_halo_update_2d_r8", "pop_halo_update_3d_r8",
+    "pop_solvers_get_eigs", "pop_solvers_get_evp_diagnostics", "pop_halo_update_2d_r8", "pop_halo_update_3d_r8",
     "pop_halo_update_4d_r8", "pop_halo_update_2d_i4", "pop_halo_update_3d_i4", "pop_halo_update_4d_i4",
     "pop_halo_update_2d_r4", "pop_halo_update_3d_r4", "pop_halo_update_4d_r4", "pop_global_sum_2d_r8",
     "pop_global_sum_nfields_2d_r8", "pop_dhdt", "pop_baroclinic_driver", "pop_barotropic_driver",
@@ -85,6 +85,7 @@ def lib():
         L.pop_solvers_get_diagnostics.argtypes = [C.POINTER(ci), C.POINTER(cd)]
         L.pop_btrop_operator.argtypes = [vp, vp, ci]
         L.pop_solvers_get_eigs.argtypes = [C.POINTER(cd), C.POINTER(cd)]
+        L.pop_solvers_get_evp_diagnostics.argtypes = [C.POINTER(ci), C.POINTER(ci), C.POINTER(cd)]
         L.pop_halo_update_2d_r8.argtypes = [vp, ci, ci, cd]
         L.pop_halo_update_3d_r8.argtypes = [vp, ci, ci, ci, cd]
         L.pop_halo_update_4d_r8.argtypes = [vp, ci, ci, ci, ci, cd]
@@ -280,6 +281,12 @@ class Pop:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.pop_solvers_get_eigs(C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def solvers_get_evp_diagnostics(self):
+        """(sub-blocks, sub-blocks on the diagonal fallback, max |rinv*rin - I|) of the EVP set-up"""
+        n, nl, e = C.c_int(), C.c_int(), C.c_double()
+        self._ck(self.L.pop_solvers_get_evp_diagnostics(C.byref(n), C.byref(nl), C.byref(e)))
+        return n.value, nl.value, e.value
 
     def btrop_operator(self, AX, X):
         self._ck(self.L.pop_btrop_operator(_p(AX), _p(X), 1))

@@ -18,6 +18,7 @@ SFC_VARTHICK, SFC_RIGID, SFC_OLDFREE = 1, 2, 3
 STATE_MWJF, STATE_LINEAR = 2, 4
 STATE_RANGE_IGNORE, STATE_RANGE_ENFORCE = 1, 3
 SOLVER_PCG, SOLVER_CHRONGEAR, SOLVER_PCSI = 1, 2, 3
+PRECOND_DIAGONAL, PRECOND_EVP = 0, 1
 TS_LEAPFROG, TS_EULER, TS_AVG, TS_ROBERT = 1, 2, 3, 4
 TIME_OLD, TIME_CUR, TIME_NEW = 0, 1, 2
 
@@ -52,6 +53,7 @@ class PopConfig(C.Structure):
         ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
         ("robert_alpha", C.c_double), ("robert_nu", C.c_double),
         ("nconvad", C.c_int),
+        ("preconditioner_choice", C.c_int),
     ]
 
 
@@ -88,6 +90,7 @@ def make_config(**kw):
         convergence_check_start=60, max_lanczos_step=20,
         convergence_criterion=1.0e-13, lanczos_convergence_criterion=0.1,
         dtt=3600.0, rank=0, nranks=1, device=0, robert_alpha=0.53, robert_nu=0.20, nconvad=0,
+        preconditioner_choice=PRECOND_DIAGONAL,
     )
     tadv = kw.pop("tadvect", TADVECT_CENTERED)
     d.update(kw)

@@ -427,6 +427,9 @@ extern "C" int pop_solvers_prep(void) {
   POP_TRY(check_ready("POP_SolversPrep", nullptr, false));
   return solvers_prep_dev();
 }
+extern "C" int pop_solvers_get_evp_diagnostics(int* subBlocks, int* landSubBlocks, double* maxInverseError) {
+  return solvers_evp_diagnostics(subBlocks, landSubBlocks, maxInverseError);
+}
 extern "C" int pop_solvers_get_eigs(double* mineig, double* maxeig) {
   if (mineig) *mineig = G.pcsiMinEigs;
   if (maxeig) *maxeig = G.pcsiMaxEigs;

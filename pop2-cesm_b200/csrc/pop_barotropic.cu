@@ -132,7 +132,8 @@ enum {
   EW_SCALE,       // V0 = s0 * V1
   EW_AXPY,        // V0 = V0 - s0*V1
   EW_SET,         // V0 = s0
-  EW_LZ_SHIFT     // Q1(V0) = Q(V1) ; Q(V1) = s0*R(V2)
+  EW_LZ_SHIFT,    // Q1(V0) = Q(V1) ; Q(V1) = s0*R(V2)
+  EW_DOT          // sum V0*V1 (masked, physical cells)
 };
 struct EwArgs {
   double *V0, *V1, *V2, *V3, *V4, *V5, *V6;
@@ -202,9 +203,12 @@ bt_ew_kernel(BtView v, EwArgs a, const SolverScalars* __restrict__ sc, double* _
     } else if (OP == EW_LZ_SHIFT) {
       a.V0[q] = a.V1[q];
       a.V1[q] = a.s0 * a.V2[q];
+    } else if (OP == EW_DOT) {
+      const int i = (int)(q % v.nxb), j = (int)(q / v.nxb);
+      if (bt_physical(v, i, j)) acc[0] = dd_add_d(acc[0], (a.V0[q] * a.V1[q]) * v.mask[q]);
     }
   }
-  if (OP == EW_PCG_W1 || OP == EW_LZ_SR) bt_store_partials(acc, 1, partials, red_blocks);
+  if (OP == EW_PCG_W1 || OP == EW_LZ_SR || OP == EW_DOT) bt_store_partials(acc, 1, partials, red_blocks);
 }
 
 #define BT_ST(OP, V0, V1, V2, V3, s0, want)                                                            \
@@ -259,6 +263,322 @@ static int refresh_center() {  // POP_SolversRun :390-391 / POP_SolversPrep: btr
   return POP_SUCCESS;
 }
 
+
+// ------------------------------------------------------------------ EVP block preconditioner
+// preconditionerChoice = 'evp' (POP_SolversMod.F90: EvpBlockPartition :2992-3040, EvpPre :2434-2506,
+// ExplicitBlockEvpPre :2508-2616, inverse :3042-3120, ExplicitEvp :2618-2696, preconditioner :2273-2369, the EVP
+// part of POP_SolversPrep :252-292).  The block is cut into sub-blocks of at most 8 x 8 cells; a sub-block without
+// land inverts the five-point operator (centre + corner weights) exactly by error-vector propagation: march
+// north-east from a zero south/west edge, read the error arriving at the north/east frame, correct the edge with
+// the influence matrix, march again; sub-blocks with land use the diagonal of prep time.
+//   Set-up (once per pop_solvers_prep, host): the influence matrices are 15 x 15 inverses per sub-block, sequential
+// arithmetic of ~10 k operations each -- built on the host from the weights as they are at prep time, uploaded
+// TRANSPOSED (element-major, sub-block fastest) so that the apply kernel's loads coalesce.
+//   Apply (every iteration, device): one thread per sub-block; the full 10 x 10 case is unrolled with the marching
+// rows in registers, ragged edge sub-blocks take the generic path.  Traffic per application: X in, PX out, and per
+// 64 cells 3 x 100 coefficient values + 225 influence values = 66 B/cell.
+#define EVP_BS 8
+#define EVP_LD (EVP_BS + 2)
+#define EVP_L (2 * EVP_BS - 1)
+struct EvpDev {
+  bool ready = false;
+  int xnb = 0, ynb = 0, nsub = 0;
+  std::vector<int> xidx, yidx;        // EvpXbidx(1:xnb+1), EvpYbidx(1:ynb+1) ([0] unused)
+  int *d_xidx = nullptr, *d_yidx = nullptr, *d_land = nullptr;
+  double *d_cc = nullptr, *d_ne = nullptr, *d_ine = nullptr, *d_icc = nullptr, *d_rinv = nullptr;  // [elem][nsub]
+  double selfcheck = 0.0;
+  int nland = 0;
+};
+static EvpDev EV;
+static bool use_evp() { return G.cfg.preconditioner_choice == POP_PRECOND_EVP; }
+
+static void evp_partition(int m, int mm, int* mb_out, std::vector<int>* mdi) {
+  const int mb = (m - 3) / mm + 1;
+  mdi->assign(mb + 2, 0);
+  (*mdi)[1] = 2;
+  if (mb == 1) {
+    (*mdi)[mb + 1] = m;
+  } else {
+    for (int i = 1; i <= mb - 2; i++) (*mdi)[i + 1] = 2 + i * mm;
+    (*mdi)[mb] = ((*mdi)[mb - 1] + m) / 2;
+    (*mdi)[mb + 1] = m;
+  }
+  *mb_out = mb;
+}
+#define HF2(a, i, j) (a)[((j)-1) * EVP_LD + ((i)-1)]
+// inverse :3042-3120 (Doolittle LU without pivoting); a is destroyed; cinv(i,k) at [(k-1)*n + (i-1)]
+static void evp_inverse_host(std::vector<double>& a, std::vector<double>& cinv, int n) {
+  std::vector<double> Lm((size_t)n * n, 0.0), Um((size_t)n * n, 0.0), bv(n + 1, 0.0), d(n + 1, 0.0), x(n + 1, 0.0);
+  auto A = [&](int i, int j) -> double& { return a[(size_t)(j - 1) * n + (i - 1)]; };
+  auto Lx = [&](int i, int j) -> double& { return Lm[(size_t)(j - 1) * n + (i - 1)]; };
+  auto Ux = [&](int i, int j) -> double& { return Um[(size_t)(j - 1) * n + (i - 1)]; };
+  for (int k = 1; k <= n - 1; k++)
+    for (int i = k + 1; i <= n; i++) {
+      const double coeff = A(i, k) / A(k, k);
+      Lx(i, k) = coeff;
+      for (int j = k + 1; j <= n; j++) A(i, j) = A(i, j) - coeff * A(k, j);
+    }
+  for (int i = 1; i <= n; i++) Lx(i, i) = 1.0;
+  for (int j = 1; j <= n; j++)
+    for (int i = 1; i <= j; i++) Ux(i, j) = A(i, j);
+  for (int k = 1; k <= n; k++) {
+    bv[k] = 1.0;
+    d[1] = bv[1];
+    for (int i = 2; i <= n; i++) {
+      d[i] = bv[i];
+      for (int j = 1; j <= i - 1; j++) d[i] = d[i] - Lx(i, j) * d[j];
+    }
+    x[n] = d[n] / Ux(n, n);
+    for (int i = n - 1; i >= 1; i--) {
+      x[i] = d[i];
+      for (int j = n; j >= i + 1; j--) x[i] = x[i] - Ux(i, j) * x[j];
+      x[i] = x[i] / Ux(i, i);
+    }
+    for (int i = 1; i <= n; i++) cinv[(size_t)(k - 1) * n + (i - 1)] = x[i];
+    bv[k] = 0.0;
+  }
+}
+// ExplicitBlockEvpPre :2508-2616; rinv(k,j) at [(j-1)*EVP_L + (k-1)]; returns max|rinv*rin - I|
+static double evp_block_pre_host(const double* cc, const double* ne, double* rinv, int n, int m) {
+  const int nm = n + m - 5;
+  double y[EVP_LD * EVP_LD];
+  std::vector<double> rin((size_t)nm * nm, 0.0), work, rtmp((size_t)nm * nm, 0.0);
+  auto RIN = [&](int i, int j) -> double& { return rin[(size_t)(j - 1) * nm + (i - 1)]; };
+  memset(y, 0, sizeof(y));
+  for (int pass = 0; pass < 2; pass++) {
+    const int cnt = pass == 0 ? m - 2 : n - 3;
+    for (int ii = 1; ii <= cnt; ii++) {
+      if (pass == 0) HF2(y, 2, m - ii) = 1.0;
+      else HF2(y, ii + 2, 2) = 1.0;
+      for (int j = 2; j <= m - 1; j++)
+        for (int i = 2; i <= n - 1; i++)
+          HF2(y, i + 1, j + 1) = (-HF2(cc, i, j) * HF2(y, i, j) - HF2(ne, i, j - 1) * HF2(y, i + 1, j - 1) -
+                                  HF2(ne, i - 1, j) * HF2(y, i - 1, j + 1) - HF2(ne, i - 1, j - 1) * HF2(y, i - 1, j - 1)) /
+                                 HF2(ne, i, j);
+      const int row = pass == 0 ? ii : m - 2 + ii;
+      for (int i = 1; i <= n - 2; i++) RIN(row, i) = -HF2(y, i + 2, m);
+      for (int j = 1; j <= m - 3; j++) RIN(row, n - 2 + j) = -HF2(y, n, m - j);
+      if (pass == 0) HF2(y, 2, m - ii) = 0.0;
+      else HF2(y, ii + 2, 2) = 0.0;
+    }
+  }
+  work = rin;
+  evp_inverse_host(work, rtmp, nm);
+  double maxvalr = 0.0;
+  for (int j = 1; j <= nm; j++)
+    for (int i = 1; i <= nm; i++) {
+      double w = 0.0;
+      for (int k = 1; k <= nm; k++) w = w + rtmp[(size_t)(k - 1) * nm + (i - 1)] * RIN(k, j);
+      if (i == j) w = w - 1.0;
+      if (fabs(w) > maxvalr) maxvalr = fabs(w);
+    }
+  for (int j = 1; j <= nm; j++)
+    for (int k = 1; k <= nm; k++) rinv[(size_t)(j - 1) * EVP_L + (k - 1)] = rtmp[(size_t)(j - 1) * nm + (k - 1)];
+  return maxvalr;
+}
+
+static int evp_prep_dev() {
+  const int nxb = G.nxb, nyb = G.nyb;
+  if (!EV.ready) {
+    evp_partition(nxb - 2, EVP_BS, &EV.xnb, &EV.xidx);
+    evp_partition(nyb - 2, EVP_BS, &EV.ynb, &EV.yidx);
+    EV.nsub = EV.xnb * EV.ynb;
+    const size_t ns = (size_t)EV.nsub;
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_xidx, sizeof(int) * EV.xidx.size()));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_yidx, sizeof(int) * EV.yidx.size()));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_land, sizeof(int) * ns));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_cc, sizeof(double) * ns * EVP_LD * EVP_LD));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_ne, sizeof(double) * ns * EVP_LD * EVP_LD));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_ine, sizeof(double) * ns * EVP_LD * EVP_LD));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_icc, sizeof(double) * ns * EVP_LD * EVP_LD));
+    POP_CHECK_CUDA(cudaMalloc(&EV.d_rinv, sizeof(double) * ns * EVP_L * EVP_L));
+    POP_CHECK_CUDA(cudaMemcpy(EV.d_xidx, EV.xidx.data(), sizeof(int) * EV.xidx.size(), cudaMemcpyHostToDevice));
+    POP_CHECK_CUDA(cudaMemcpy(EV.d_yidx, EV.yidx.data(), sizeof(int) * EV.yidx.size(), cudaMemcpyHostToDevice));
+    EV.ready = true;
+  }
+  const size_t ns = (size_t)EV.nsub, n2 = G.n2;
+  std::vector<double> C(n2), NE(n2);
+  POP_CHECK_CUDA(cudaMemcpyAsync(C.data(), fld("btropWgtCenter"), sizeof(double) * n2, cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaMemcpyAsync(NE.data(), fld("btropWgtNE"), sizeof(double) * n2, cudaMemcpyDeviceToHost, G.stream));
+  POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  // element-major copies: a[e * nsub + s]
+  std::vector<double> cc(ns * EVP_LD * EVP_LD, 0.0), ne(ns * EVP_LD * EVP_LD, 0.0), ine(ns * EVP_LD * EVP_LD, 0.0),
+      icc(ns * EVP_LD * EVP_LD, 0.0), rinv(ns * EVP_L * EVP_L, 0.0);
+  std::vector<int> land(ns, 0);
+  double worst = 0.0;
+  int bad = 0;
+  EV.nland = 0;
+  double ecc[EVP_LD * EVP_LD], ene[EVP_LD * EVP_LD], er[EVP_L * EVP_L];
+  for (int j = 1; j <= EV.ynb; j++) {
+    const int js = EV.yidx[j] - 1, je = EV.yidx[j + 1], lm = je - js + 1;
+    for (int i = 1; i <= EV.xnb; i++) {
+      const int is = EV.xidx[i] - 1, ie = EV.xidx[i + 1], ln = ie - is + 1;
+      const size_t sb = (size_t)(j - 1) * EV.xnb + (i - 1);
+      memset(ecc, 0, sizeof(ecc));
+      memset(ene, 0, sizeof(ene));
+      // cc = btropWgtCenter(2:nx1, 2:ny1): element (ii,jj) of the sub-block is 0-based array cell (is+ii-1, js+jj-1)
+      for (int jj = 1; jj <= lm; jj++)
+        for (int ii = 1; ii <= ln; ii++) {
+          const size_t q = (size_t)(js + jj - 1) * nxb + (is + ii - 1);
+          HF2(ecc, ii, jj) = C[q];
+          HF2(ene, ii, jj) = NE[q];
+        }
+      int iland = 0;
+      double mn = fabs(HF2(ene, 2, 2));
+      for (int jj = 2; jj <= lm - 1; jj++)
+        for (int ii = 2; ii <= ln - 1; ii++) mn = fabs(HF2(ene, ii, jj)) < mn ? fabs(HF2(ene, ii, jj)) : mn;
+      if (mn == 0.0) iland = 1;
+      if (is + 2 < G.ib || ie - 1 > G.ie) iland = 2;
+      if (js + 2 < G.jb || je - 1 > G.je) iland = 3;
+      memset(er, 0, sizeof(er));
+      if (iland > 0) {
+        land[sb] = 1;
+        EV.nland++;
+      } else {
+        const double chk = evp_block_pre_host(ecc, ene, er, ln, lm);
+        worst = chk > worst ? chk : worst;
+        if (chk > 1.0e-8) bad++;
+      }
+      for (int e = 0; e < EVP_LD * EVP_LD; e++) {
+        cc[(size_t)e * ns + sb] = ecc[e];
+        ne[(size_t)e * ns + sb] = ene[e];
+        if (ecc[e] != 0.0) icc[(size_t)e * ns + sb] = 1.0 / ecc[e];
+        if (ene[e] != 0.0) ine[(size_t)e * ns + sb] = 1.0 / ene[e];
+      }
+      for (int e = 0; e < EVP_L * EVP_L; e++) rinv[(size_t)e * ns + sb] = er[e];
+    }
+  }
+  EV.selfcheck = worst;
+  POP_REQUIRE(bad == 0, "POP_EXPLICITPRE: error in computing the inverse, error > 1.0e-8 (%g) in %d sub-blocks; check EVP "
+              "sub-block size", worst, bad);  // POP_SolversMod.F90:2606-2614
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_land, land.data(), sizeof(int) * ns, cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_cc, cc.data(), sizeof(double) * cc.size(), cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_ne, ne.data(), sizeof(double) * ne.size(), cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_ine, ine.data(), sizeof(double) * ine.size(), cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_icc, icc.data(), sizeof(double) * icc.size(), cudaMemcpyHostToDevice));
+  POP_CHECK_CUDA(cudaMemcpy(EV.d_rinv, rinv.data(), sizeof(double) * rinv.size(), cudaMemcpyHostToDevice));
+  return POP_SUCCESS;
+}
+void evp_release() {
+  cudaFree(EV.d_xidx); cudaFree(EV.d_yidx); cudaFree(EV.d_land); cudaFree(EV.d_cc); cudaFree(EV.d_ne);
+  cudaFree(EV.d_ine); cudaFree(EV.d_icc); cudaFree(EV.d_rinv);
+  EV = EvpDev();
+}
+
+struct EvpArgs {
+  int nxb, xnb, ynb, nsub;
+  const int *xidx, *yidx, *land;
+  const double *cc, *ne, *ine, *icc, *rinv;
+  const double* X;
+  double* PX;
+};
+// ExplicitEvp (:2618-2696) for one sub-block.  N, M > 0: compile-time extents (everything unrolled, y in registers);
+// N = M = 0: run-time extents n, m.  Element (i,j) (1-based) of a coefficient array is a[((j-1)*EVP_LD + (i-1)) * ns].
+template <int N, int M>
+__device__ __forceinline__ void evp_solve(const EvpArgs& a, int sb, int is, int js, int n_rt, int m_rt) {
+  const int n = N ? N : n_rt, m = M ? M : m_rt;
+  const int nm = n + m - 5;
+  const size_t ns = (size_t)a.nsub;
+  const double* cc = a.cc + sb;
+  const double* ne = a.ne + sb;
+  const double* ine = a.ine + sb;
+  const double* rinv = a.rinv + sb;
+#define CF(p, i, j) ldg((p) + (size_t)(((j)-1) * EVP_LD + ((i)-1)) * ns)
+#define YY(i, j) y[((j)-1) * EVP_LD + ((i)-1)]
+  const double* X = a.X + (size_t)(js - 1) * a.nxb + (is - 1);  // X(is,js): sub-block element (1,1), 1-based array indices
+  double y[EVP_LD * EVP_LD];
+#pragma unroll
+  for (int e = 0; e < EVP_LD * EVP_LD; e++) y[e] = 0.0;
+#pragma unroll
+  for (int j = 2; j <= (M ? M : EVP_LD) - 1; j++)
+    if (j <= m - 1) {
+#pragma unroll
+      for (int i = 2; i <= (N ? N : EVP_LD) - 1; i++)
+        if (i <= n - 1)
+          YY(i + 1, j + 1) = (ldg(X + (size_t)(j - 1) * a.nxb + (i - 1)) - CF(cc, i, j) * YY(i, j) -
+                              CF(ne, i, j - 1) * YY(i + 1, j - 1) - CF(ne, i - 1, j) * YY(i - 1, j + 1) -
+                              CF(ne, i - 1, j - 1) * YY(i - 1, j - 1)) * CF(ine, i, j);
+    }
+  double r[EVP_L];
+#pragma unroll
+  for (int q = 1; q <= EVP_L; q++) {
+    double v = 0.0;
+    if (q <= n - 2) v = YY((N ? q + 2 : q + 2), m);                       // r(1:n-2) = y(3:n, m)
+    else if (q <= nm) v = YY(n, m - 1 - (q - (n - 1)));                  // r(n-1:nm) = y(n, m-1:3:-1)
+    r[q - 1] = v;
+  }
+#pragma unroll
+  for (int j = 1; j <= EVP_LD - 2; j++)
+    if (j <= m - 2) {
+      double acc = YY(2, m - j);
+#pragma unroll
+      for (int k = 1; k <= EVP_L; k++)
+        if (k <= nm) acc = acc + ldg(rinv + (size_t)((j - 1) * EVP_L + (k - 1)) * ns) * r[k - 1];
+      YY(2, m - j) = acc;
+    }
+#pragma unroll
+  for (int i = 1; i <= EVP_LD - 3; i++)
+    if (i <= n - 3) {
+      double acc = YY(i + 2, 2);
+#pragma unroll
+      for (int k = 1; k <= EVP_L; k++)
+        if (k <= nm) acc = acc + ldg(rinv + (size_t)((m - 2 + i - 1) * EVP_L + (k - 1)) * ns) * r[k - 1];
+      YY(i + 2, 2) = acc;
+    }
+#pragma unroll
+  for (int j = 2; j <= (M ? M : EVP_LD) - 2; j++)
+    if (j <= m - 2) {
+#pragma unroll
+      for (int i = 2; i <= (N ? N : EVP_LD) - 2; i++)
+        if (i <= n - 2)
+          YY(i + 1, j + 1) = (ldg(X + (size_t)(j - 1) * a.nxb + (i - 1)) - CF(cc, i, j) * YY(i, j) -
+                              CF(ne, i, j - 1) * YY(i + 1, j - 1) - CF(ne, i - 1, j) * YY(i - 1, j + 1) -
+                              CF(ne, i - 1, j - 1) * YY(i - 1, j - 1)) * CF(ine, i, j);
+    }
+  double* PX = a.PX + (size_t)(js - 1) * a.nxb + (is - 1);
+#pragma unroll
+  for (int j = 2; j <= (M ? M : EVP_LD) - 1; j++)
+    if (j <= m - 1) {
+#pragma unroll
+      for (int i = 2; i <= (N ? N : EVP_LD) - 1; i++)
+        if (i <= n - 1) PX[(size_t)(j - 1) * a.nxb + (i - 1)] = YY(i, j);
+    }
+#undef CF
+#undef YY
+}
+__global__ void __launch_bounds__(128)
+evp_apply_kernel(const EvpArgs a) {
+  const int sb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sb >= a.nsub) return;
+  const int bi = sb % a.xnb + 1, bj = sb / a.xnb + 1;
+  // preconditioner :2333-2342: the frame of the sub-block in array indices (1-based)
+  const int is = a.xidx[bi], ie = a.xidx[bi + 1] + 1, js = a.yidx[bj], je = a.yidx[bj + 1] + 1;
+  const int ln = ie - is + 1, lm = je - js + 1;
+  if (a.land[sb]) {
+    const size_t ns = (size_t)a.nsub;
+    for (int jj = 2; jj <= lm - 1; jj++)
+      for (int ii = 2; ii <= ln - 1; ii++) {
+        const size_t q = (size_t)(js + jj - 2) * a.nxb + (is + ii - 2);
+        a.PX[q] = ldg(a.X + q) * ldg(a.icc + (size_t)((jj - 1) * EVP_LD + (ii - 1)) * ns + sb);
+      }
+    return;
+  }
+  if (ln == EVP_LD && lm == EVP_LD) evp_solve<EVP_LD, EVP_LD>(a, sb, is, js, ln, lm);
+  else evp_solve<0, 0>(a, sb, is, js, ln, lm);
+}
+// PX = (PC) X on the sub-block interiors, 0 elsewhere (PX(:,:,bid) = 0 first, :2309)
+static int precond_apply(double* PX, const double* X) {
+  POP_REQUIRE(EV.ready, "POP_Solvers: the EVP preconditioner needs pop_solvers_prep (POP_SolversPrep) first");
+  POP_CHECK_CUDA(cudaMemsetAsync(PX, 0, sizeof(double) * G.n2, G.stream));
+  EvpArgs a;
+  a.nxb = G.nxb; a.xnb = EV.xnb; a.ynb = EV.ynb; a.nsub = EV.nsub;
+  a.xidx = EV.d_xidx; a.yidx = EV.d_yidx; a.land = EV.d_land;
+  a.cc = EV.d_cc; a.ne = EV.d_ne; a.ine = EV.d_ine; a.icc = EV.d_icc; a.rinv = EV.d_rinv;
+  a.X = X; a.PX = PX;
+  POP_LAUNCH(evp_apply_kernel, (unsigned)((EV.nsub + 127) / 128), 128, 0, a);
+  return POP_SUCCESS;
+}
+
 // ------------------------------------------------------------------ ChronGear :1841-2266
 static int chrongear(double* X, const double* B) {
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq;
@@ -266,20 +586,28 @@ static int chrongear(double* X, const double* B) {
          *A0R = fld("BT_A0R");
   double rr = 0.0;
   G.numIterations = maxIt;
+  const bool evp = use_evp();
   BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
   POP_TRY(bt_halo(R));
-  BT_ST(BT_CG_ZS, Z, R, A0R, S, 0.0, 0);
+  if (evp) {  // :2009-2033: Z = (PC) r, halo update, S = Z
+    POP_TRY(precond_apply(Z, R));
+    POP_TRY(bt_halo(Z));
+    POP_CHECK_CUDA(cudaMemcpyAsync(S, Z, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  } else {
+    BT_ST(BT_CG_ZS, Z, R, A0R, S, 0.0, 0);
+  }
   BT_ST(BT_CG_QSUM, Q, S, R, Z, 0.0, 1);
   POP_TRY(bt_halo(Q));
   POP_TRY(reduce_finish(2, RED_POST_CG_INIT, nullptr));
   bt_ew<EW_CG_UPDATE0>(X, R, S, Q);
-  bt_ew<EW_MUL>(Z, R, A0R);
+  if (evp) POP_TRY(precond_apply(Z, R));
+  else bt_ew<EW_MUL>(Z, R, A0R);
   for (int m = 1; m <= maxIt; m++) {
     POP_TRY(bt_halo(Z));
     BT_ST(BT_CG_AZSUM, AZ, Z, R, (double*)nullptr, 0.0, 1);
     POP_TRY(reduce_finish(2, RED_POST_CG_ITER, nullptr));
     const bool check = (m % freq == 0);
-    bt_ew<EW_CG_UPDATE>(X, R, S, Q, Z, AZ, A0R, 0.0, 0.0, check ? 0 : 1);
+    bt_ew<EW_CG_UPDATE>(X, R, S, Q, Z, AZ, A0R, 0.0, 0.0, (check || evp) ? 0 : 1);
     if (check) {
       BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 1);
       POP_TRY(bt_halo(R));
@@ -288,8 +616,9 @@ static int chrongear(double* X, const double* B) {
         G.numIterations = m;
         break;
       }
-      bt_ew<EW_MUL>(Z, R, A0R);
+      if (!evp) bt_ew<EW_MUL>(Z, R, A0R);
     }
+    if (evp) POP_TRY(precond_apply(Z, R));
   }
   G.rmsResidual = sqrt(rr * G.residualNorm);
   POP_TRY(pop_post_launch("ChronGear"));
@@ -633,7 +962,46 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   }
 }
 
+// PCSI with usePreconditioner (:1651-1659, :1734-1742): the preconditioner couples the cells of a sub-block, so the
+// residual goes through memory: evp_apply -> halo -> (Q, X) update -> residual, four launches per iteration.
+static int pcsi_evp(double* X, const double* B) {
+  const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
+            start = G.cfg.convergence_check_start;
+  double *R = fld("BT_R"), *PR = fld("BT_S"), *Q = fld("BT_Q");
+  double rr = 0.0;
+  const double csalpha = 2.0 / (G.pcsiMaxEigs - G.pcsiMinEigs);
+  const double csbeta = (G.pcsiMaxEigs + G.pcsiMinEigs) / (G.pcsiMaxEigs - G.pcsiMinEigs);
+  const double csy = csbeta / csalpha;
+  double csomga = 2.0 / csy;
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  POP_TRY(precond_apply(PR, R));
+  bt_ew<EW_SCALE>(Q, PR, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0 / csy);
+  POP_TRY(bt_halo(Q));
+  bt_ew<EW_ADD>(X, Q);
+  BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, 0);
+  POP_TRY(bt_halo(R));
+  G.numIterations = maxIt;
+  for (int m = 1; m <= maxIt; m++) {
+    csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
+    POP_TRY(precond_apply(PR, R));
+    POP_TRY(bt_halo(PR));
+    bt_ew<EW_PCSI_QX>(Q, X, PR, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
+    const bool check = (m % freq == 0) && (m >= start);
+    BT_ST(BT_RESID, R, X, B, (double*)nullptr, 0.0, check ? 1 : 0);
+    if (check) {
+      POP_TRY(reduce_finish(1, RED_POST_RR, &rr));
+      if (rr < G.convergenceCriterion) {
+        G.numIterations = m;
+        break;
+      }
+    }
+  }
+  G.rmsResidual = sqrt(rr * G.residualNorm);
+  return pop_post_launch("PCSI/EVP");
+}
+
 static int pcsi(double* X, const double* B) {
+  if (use_evp()) return pcsi_evp(X, B);
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
             start = G.cfg.convergence_check_start;
   double *R = fld("BT_R"), *A0R = fld("BT_A0R");
@@ -836,7 +1204,13 @@ static int pcg(double* X, const double* B) {
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   G.numIterations = maxIt;
   for (int m = 1; m <= maxIt; m++) {
-    bt_ew<EW_PCG_W1>(W1, R, fld("btropWgtCenter"));
+    if (use_evp()) {  // :1310-1345
+      POP_TRY(precond_apply(W1, R));
+      bt_ew<EW_DOT>(R, W1);
+      POP_TRY(bt_halo(W1));
+    } else {
+      bt_ew<EW_PCG_W1>(W1, R, fld("btropWgtCenter"));
+    }
     POP_TRY(reduce_finish(1, RED_POST_PCG_ETA1, nullptr));
     bt_ew<EW_PCG_S>(S, W1);
     BT_ST(BT_PCG_AS, Q, S, (const double*)nullptr, (double*)nullptr, 0.0, 1);
@@ -917,7 +1291,13 @@ static int pcsi_lanczos() {
   bt_ew<EW_SET>(R, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.0);
   bt_ew<EW_SET>(Q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0);
   bt_ew<EW_SET>(Q1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0);
-  bt_ew<EW_LZ_SR>(S, R, A0R);
+  const bool evp = use_evp();
+  if (evp) {
+    POP_TRY(precond_apply(S, R));
+    bt_ew<EW_DOT>(S, R);
+  } else {
+    bt_ew<EW_LZ_SR>(S, R, A0R);
+  }
   POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
   csc = -sum;
   POP_REQUIRE(csc > 0.0, "PcsiLanczos: preconditioned operator is not negative definite (csc=%g)", csc);
@@ -928,14 +1308,20 @@ static int pcsi_lanczos() {
   G.lanczosSteps = 0;
   for (int m = 1; m <= maxstep; m++) {
     G.lanczosSteps = m;
-    bt_ew<EW_MUL>(P, Q, A0R);
+    if (evp) POP_TRY(precond_apply(P, Q));
+    else bt_ew<EW_MUL>(P, Q, A0R);
     POP_TRY(bt_halo(P));
     BT_ST(BT_LZ_AP, R, P, Q1, (double*)nullptr, csb, 1);
     POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
     csa = -sum;
     bt_ew<EW_AXPY>(R, Q, nullptr, nullptr, nullptr, nullptr, nullptr, csa);
     POP_TRY(bt_halo(R));
-    bt_ew<EW_LZ_SR>(S, R, A0R);
+    if (evp) {
+      POP_TRY(precond_apply(S, R));
+      bt_ew<EW_DOT>(S, R);
+    } else {
+      bt_ew<EW_LZ_SR>(S, R, A0R);
+    }
     POP_TRY(reduce_finish(1, RED_POST_NONE, &sum));
     csc = -sum;
     csb = sqrt(csc);
@@ -965,7 +1351,15 @@ static int pcsi_lanczos() {
 
 int solvers_prep_dev() {
   POP_TRY(refresh_center());
+  if (use_evp()) POP_TRY(evp_prep_dev());  // POP_SolversPrep :252-292, before the Lanczos estimate that uses it
   if (G.cfg.solver_choice == POP_SOLVER_PCSI) return pcsi_lanczos();
+  return POP_SUCCESS;
+}
+int solvers_evp_diagnostics(int* nsub, int* nland, double* selfcheck) {
+  POP_REQUIRE(EV.ready, "POP_SolversGetEvpDiagnostics: the EVP preconditioner has not been prepared");
+  if (nsub) *nsub = EV.nsub;
+  if (nland) *nland = EV.nland;
+  if (selfcheck) *selfcheck = EV.selfcheck;
   return POP_SUCCESS;
 }
 

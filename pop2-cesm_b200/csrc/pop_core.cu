@@ -156,6 +156,7 @@ extern "C" void pop_config_defaults(pop_config* c) {
   c->robert_alpha = 0.53;  // time_management.F90:461-462 (Williams 2009)
   c->robert_nu = 0.20;
   c->nconvad = 0;
+  c->preconditioner_choice = POP_PRECOND_DIAGONAL;
 }
 
 // ------------------------------------------------------------------ lifecycle
@@ -329,6 +330,8 @@ extern "C" int pop_init(const pop_config* cfg) {
   POP_REQUIRE(cfg->vmix_itype == POP_VMIX_CONST || cfg->vmix_itype == POP_VMIX_GIVEN ||
                   cfg->vmix_itype == POP_VMIX_RICH,
               "pop_init: vmix_itype=%d is not implemented (const, rich, given)", cfg->vmix_itype);
+  POP_REQUIRE(cfg->preconditioner_choice == POP_PRECOND_DIAGONAL || cfg->preconditioner_choice == POP_PRECOND_EVP,
+              "pop_init: unknown preconditioner choice %d (diagonal, evp)", cfg->preconditioner_choice);
   POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH || cfg->implicit_vertical_mix,
               "pop_init: vmix_itype=rich needs implicit_vertical_mix (the coefficients of all levels are built before the column kernels)");
   POP_TRY(alloc_all_fields());
@@ -356,6 +359,7 @@ extern "C" int pop_finalize(void) {
   if (G.stream_cp) cudaStreamSynchronize(G.stream_cp);
   if (G.stream_x) cudaStreamSynchronize(G.stream_x);
   p2p_teardown();
+  evp_release();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();
   for (auto& kv : G.stage) cudaFree(kv.second.first);

@@ -320,6 +320,8 @@ int div_dev(int k, double* D, const double* UX, const double* UY);
 // barotropic + solver (pop_barotropic.cu)
 int solvers_init_dev();
 int solvers_prep_dev();
+int solvers_evp_diagnostics(int* nsub, int* nland, double* selfcheck);
+void evp_release();
 int solvers_diagonal_dev(const double* diagCorr);
 int solvers_run_dev(double* X, const double* B);
 int btrop_operator_dev(double* AX, const double* X);

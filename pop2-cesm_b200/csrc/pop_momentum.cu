@@ -529,10 +529,26 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
 //            when the caller runs this kernel after the barotropic solve]
 // so DRAM sees RHS u,v, VVC, Uold, Vold in and U,V out (56 B/cell, 72 with the fused barotropic add that used to be
 // a 32 B/cell kernel of its own).
-#define MF_CH 8
-#define MF_BCH 4
+#ifndef MF_CH
+#define MF_CH 4    // levels per chunk, forward sweep (three arrays)
+#endif
+#ifndef MF_NB
+#define MF_NB 4    // register ring depth, forward sweep
+#endif
+#ifndef MF_BCH
+#define MF_BCH 2   // levels per chunk, backward sweep (four arrays)
+#endif
+#ifndef MF_BNB
+#define MF_BNB 4
+#endif
+#ifndef MF_MINB
+#define MF_MINB 3
+#endif
+#ifndef MF_PD
+#define MF_PD 16   // L2 prefetch distance in levels (0: off)
+#endif
 #define MF_THREADS 128
-__global__ void __launch_bounds__(MF_THREADS, 3)
+__global__ void __launch_bounds__(MF_THREADS, MF_MINB)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
                        const double* __restrict__ UOLD, const double* __restrict__ VOLD,
                        const double* __restrict__ UB, const double* __restrict__ VB, int bt_skip_row,
@@ -569,11 +585,22 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
     double* su = Un + n2i;                // next level to store
     double* sv = Vn + n2i;
     int nld = km - 1;
-    double uv[MF_CH], vv[MF_CH], cv[MF_CH], un[MF_CH], vn[MF_CH], cn[MF_CH];
+    double ub[MF_NB][MF_CH], wb[MF_NB][MF_CH], cb[MF_NB][MF_CH];  // ring of chunk buffers
 #pragma unroll
-    for (int c = 0; c < MF_CH; c++) { uv[c] = 0.0; vv[c] = 0.0; cv[c] = 0.0; un[c] = 0.0; vn[c] = 0.0; cn[c] = 0.0; }
+    for (int s = 0; s < MF_NB; s++)
+#pragma unroll
+      for (int c = 0; c < MF_CH; c++) { ub[s][c] = 0.0; wb[s][c] = 0.0; cb[s][c] = 0.0; }
+    const ptrdiff_t pdc = (ptrdiff_t)MF_PD * vstr, pdn = (ptrdiff_t)MF_PD * n2i;
     auto load_fwd = [&](double* cc, double* uu, double* ww) {
       if (nld >= MF_CH) {
+        if (MF_PD && nld >= MF_CH + MF_PD) {
+#pragma unroll
+          for (int c = 0; c < MF_CH; c++) {
+            if (vstr) prefetch_l2(pc + pdc + (ptrdiff_t)c * vstr);
+            prefetch_l2(pu + pdn + (ptrdiff_t)c * n2i);
+            prefetch_l2(pv + pdn + (ptrdiff_t)c * n2i);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < MF_CH; c++) {
           cc[c] = *pc; uu[c] = *pu; ww[c] = *pv;
@@ -620,16 +647,22 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
           if (kb + c <= km) fwd_level(kb + c, cc[c], uu[c], ww[c]);
       }
     };
-    load_fwd(cv, uv, vv);
-    for (int kb = 2; kb <= km; kb += 2 * MF_CH) {  // two register sets, no copies
-      load_fwd(cn, un, vn);
-      fwd_chunk(kb, cv, uv, vv);
-      if (kb + MF_CH <= km) {
-        load_fwd(cv, uv, vv);
-        fwd_chunk(kb + MF_CH, cn, un, vn);
-      }
+#pragma unroll
+    for (int s = 0; s < MF_NB - 1; s++) load_fwd(cb[s], ub[s], wb[s]);
+    for (int kb = 2; kb <= km; kb += MF_NB * MF_CH) {
+#pragma unroll
+      for (int s = 0; s < MF_NB; s++)
+        if (kb + s * MF_CH <= km) {
+          load_fwd(cb[(s + MF_NB - 1) % MF_NB], ub[(s + MF_NB - 1) % MF_NB], wb[(s + MF_NB - 1) % MF_NB]);
+          fwd_chunk(kb + s * MF_CH, cb[s], ub[s], wb[s]);
+        }
     }
     // ---- back substitution (only levels k < kmu change; F1,F2 = F(km)), fused with U = Uold + dU when finishing
+    if (MF_PD && finish) {
+#pragma unroll
+      for (int c = 1; c <= MF_PD; c++)
+        if (c < km) { prefetch_l2(UOLD + q + top - (size_t)c * n2); prefetch_l2(VOLD + q + top - (size_t)c * n2); }
+    }
     if (finish) {
       const double u = UOLD[top + q] + F1, v = VOLD[top + q] + F2;
       sE[(km - 1) * MF_THREADS] = u;
@@ -642,11 +675,20 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
     double* tu = Un + top - n2i;        // next level to store
     double* tv = Vn + top - n2i;
     nld = km - 1;
-    double f1[MF_BCH], f2[MF_BCH], o1[MF_BCH], o2[MF_BCH], g1[MF_BCH], g2[MF_BCH], p1[MF_BCH], p2[MF_BCH];
+    double f1[MF_BNB][MF_BCH], f2[MF_BNB][MF_BCH], o1[MF_BNB][MF_BCH], o2[MF_BNB][MF_BCH];
 #pragma unroll
-    for (int c = 0; c < MF_BCH; c++) { f1[c] = f2[c] = o1[c] = o2[c] = g1[c] = g2[c] = p1[c] = p2[c] = 0.0; }
+    for (int s = 0; s < MF_BNB; s++)
+#pragma unroll
+      for (int c = 0; c < MF_BCH; c++) { f1[s][c] = 0.0; f2[s][c] = 0.0; o1[s][c] = 0.0; o2[s][c] = 0.0; }
     auto load_bwd = [&](double* a1, double* a2, double* b1, double* b2) {
       if (nld >= MF_BCH) {
+        if (MF_PD && finish && nld >= MF_BCH + MF_PD) {  // Uold, Vold are touched for the first time on the way up
+#pragma unroll
+          for (int c = 0; c < MF_BCH; c++) {
+            prefetch_l2(qo - pdn - (ptrdiff_t)c * n2i);
+            prefetch_l2(qp - pdn - (ptrdiff_t)c * n2i);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < MF_BCH; c++) {
           a1[c] = *qu; a2[c] = *qv;
@@ -691,14 +733,16 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
           if (kt - c >= 1) bwd_level(kt - c, a1[c], a2[c], b1[c], b2[c]);
       }
     };
-    load_bwd(f1, f2, o1, o2);
-    for (int kt = km - 1; kt >= 1; kt -= 2 * MF_BCH) {
-      load_bwd(g1, g2, p1, p2);
-      bwd_chunk(kt, f1, f2, o1, o2);
-      if (kt - MF_BCH >= 1) {
-        load_bwd(f1, f2, o1, o2);
-        bwd_chunk(kt - MF_BCH, g1, g2, p1, p2);
-      }
+#pragma unroll
+    for (int s = 0; s < MF_BNB - 1; s++) load_bwd(f1[s], f2[s], o1[s], o2[s]);
+    for (int kt = km - 1; kt >= 1; kt -= MF_BNB * MF_BCH) {
+#pragma unroll
+      for (int s = 0; s < MF_BNB; s++)
+        if (kt - s * MF_BCH >= 1) {
+          load_bwd(f1[(s + MF_BNB - 1) % MF_BNB], f2[(s + MF_BNB - 1) % MF_BNB], o1[(s + MF_BNB - 1) % MF_BNB],
+                   o2[(s + MF_BNB - 1) % MF_BNB]);
+          bwd_chunk(kt - s * MF_BCH, f1[s], f2[s], o1[s], o2[s]);
+        }
     }
     if (!finish) return;
   } else {

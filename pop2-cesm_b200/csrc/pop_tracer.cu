@@ -816,10 +816,21 @@ int tracer_column(int mode, int k, const TracerIO& io) {
 // profiles/r1_ncu_summary.md), full chunks carry no bounds predicates, and the two quotients of a level
 // share one reciprocal refinement (div_by: the compiler's own division sequence, bit-identical).
 // ncu (profiles/): 12 warps/SM (E(k) footprint), HBM-bound target 64 B/cell for two tracers.
-#define IV_CH 8
+#ifndef IV_CH
+#define IV_CH 4   // levels per chunk
+#endif
+#ifndef IV_NB
+#define IV_NB 4   // register ring depth: IV_NB - 1 chunks of loads are in flight ahead of the recurrence
+#endif
+#ifndef IV_MINB
+#define IV_MINB 3
+#endif
+#ifndef IV_PD
+#define IV_PD 16  // L2 prefetch distance in levels (0: off)
+#endif
 #define IV_THREADS 128
 template <bool CORRECT>
-__global__ void __launch_bounds__(IV_THREADS, 3)
+__global__ void __launch_bounds__(IV_THREADS, IV_MINB)
 impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict__ TOLD,
                 const double* __restrict__ PSFC, const double* __restrict__ RHS, double* FB,
                 int nfirst, int nlast, int varthick) {
@@ -857,11 +868,21 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
     const double* pr = Tn + n2i;     // right-hand side of the next level to load
     double* pf = Fb + n2i;           // F of the next level to store
     int nld = km - 1;                // levels not loaded yet
-    double rv[IV_CH], vv[IV_CH], rn[IV_CH], vn[IV_CH];
+    double rb[IV_NB][IV_CH], vb[IV_NB][IV_CH];  // ring of chunk buffers (static indices after unrolling)
 #pragma unroll
-    for (int c = 0; c < IV_CH; c++) { rv[c] = 0.0; vv[c] = 0.0; rn[c] = 0.0; vn[c] = 0.0; }
+    for (int s = 0; s < IV_NB; s++)
+#pragma unroll
+      for (int c = 0; c < IV_CH; c++) { rb[s][c] = 0.0; vb[s][c] = 0.0; }
+    const ptrdiff_t pdv = (ptrdiff_t)IV_PD * vstr, pdn = (ptrdiff_t)IV_PD * n2i;
     auto load_fwd = [&](double* v, double* r) {
       if (nld >= IV_CH) {
+        if (IV_PD && nld >= IV_CH + IV_PD) {  // the chunk IV_PD levels further down exists: pull it into L2
+#pragma unroll
+          for (int c = 0; c < IV_CH; c++) {
+            if (vstr) prefetch_l2(pv + pdv + (ptrdiff_t)c * vstr);
+            if (!CORRECT) prefetch_l2(pr + pdn + (ptrdiff_t)c * n2i);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < IV_CH; c++) {
           v[c] = *pv;
@@ -908,18 +929,24 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
           if (kb + c <= km) fwd_level(kb + c, v[c], r[c]);
       }
     };
-    load_fwd(vv, rv);
-    for (int kb = 2; kb <= km; kb += 2 * IV_CH) {  // two register sets, no copies
-      load_fwd(vn, rn);
-      fwd_chunk(kb, vv, rv);
-      if (kb + IV_CH <= km) {
-        load_fwd(vv, rv);
-        fwd_chunk(kb + IV_CH, vn, rn);
-      }
+#pragma unroll
+    for (int s = 0; s < IV_NB - 1; s++) load_fwd(vb[s], rb[s]);
+    for (int kb = 2; kb <= km; kb += IV_NB * IV_CH) {
+#pragma unroll
+      for (int s = 0; s < IV_NB; s++)
+        if (kb + s * IV_CH <= km) {
+          load_fwd(vb[(s + IV_NB - 1) % IV_NB], rb[(s + IV_NB - 1) % IV_NB]);
+          fwd_chunk(kb + s * IV_CH, vb[s], rb[s]);
+        }
     }
     // ---- back substitution + final update, levels km..1 in chunks (Fm = F(km))
     double Fp = Fm;
     const size_t top = (size_t)(km - 1) * n2;
+    if (IV_PD && !CORRECT) {
+#pragma unroll
+      for (int c = 0; c < IV_PD; c++)
+        if (c < km) prefetch_l2(Bs + top - (size_t)c * n2);
+    }
     Tn[top] = Bs[top] + Fp;
     const double* qf = Fb + top - n2i;  // F of the next level to load (level km-1), going up
     const double* qb = Bs + top - n2i;
@@ -927,6 +954,10 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
     nld = km - 1;
     auto load_bwd = [&](double* f, double* b) {
       if (nld >= IV_CH) {
+        if (IV_PD && !CORRECT && nld >= IV_CH + IV_PD) {  // TOLD is touched for the first time on the way up
+#pragma unroll
+          for (int c = 0; c < IV_CH; c++) prefetch_l2(qb - pdn - (ptrdiff_t)c * n2i);
+        }
 #pragma unroll
         for (int c = 0; c < IV_CH; c++) {
           f[c] = *qf;
@@ -964,14 +995,15 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
           if (kt - c >= 1) bwd_level(kt - c, f[c], b[c]);
       }
     };
-    load_bwd(rv, vv);
-    for (int kt = km - 1; kt >= 1; kt -= 2 * IV_CH) {
-      load_bwd(rn, vn);
-      bwd_chunk(kt, rv, vv);
-      if (kt - IV_CH >= 1) {
-        load_bwd(rv, vv);
-        bwd_chunk(kt - IV_CH, rn, vn);
-      }
+#pragma unroll
+    for (int s = 0; s < IV_NB - 1; s++) load_bwd(rb[s], vb[s]);
+    for (int kt = km - 1; kt >= 1; kt -= IV_NB * IV_CH) {
+#pragma unroll
+      for (int s = 0; s < IV_NB; s++)
+        if (kt - s * IV_CH >= 1) {
+          load_bwd(rb[(s + IV_NB - 1) % IV_NB], vb[(s + IV_NB - 1) % IV_NB]);
+          bwd_chunk(kt - s * IV_CH, rb[s], vb[s]);
+        }
     }
   }
 }

@@ -65,6 +65,7 @@ module pop_b200_bind
       integer (c_int) :: rank, nranks, device
       real (c_double) :: robert_alpha, robert_nu
       integer (c_int) :: nconvad
+      integer (c_int) :: preconditioner_choice
    end type pop_config
 
    ! mirrors struct pop_block = `type block` of blocks.F90:30-39
@@ -322,6 +323,15 @@ module pop_b200_bind
 
       function pop_solvers_prep() bind(C, name='pop_solvers_prep') result(ierr)
          import :: c_int
+         integer (c_int) :: ierr
+      end function
+
+      ! EVP preconditioner set-up diagnostics (EvpPre, POP_SolversMod.F90:2434-2506; self-check :2594-2614)
+      function pop_solvers_get_evp_diagnostics(subBlocks, landSubBlocks, maxInverseError) &
+               bind(C, name='pop_solvers_get_evp_diagnostics') result(ierr)
+         import :: c_int, c_double
+         integer (c_int), intent(out) :: subBlocks, landSubBlocks
+         real (c_double), intent(out) :: maxInverseError
          integer (c_int) :: ierr
       end function
 
