@@ -545,7 +545,7 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
 #define MF_MINB 3
 #endif
 #ifndef MF_PD
-#define MF_PD 16   // L2 prefetch distance in levels (0: off)
+#define MF_PD 8    // L2 prefetch distance in levels (0: off)
 #endif
 #define MF_THREADS 128
 __global__ void __launch_bounds__(MF_THREADS, MF_MINB)
@@ -584,16 +584,18 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
     const double* pv = Vn + n2i;
     double* su = Un + n2i;                // next level to store
     double* sv = Vn + n2i;
-    int nld = km - 1;
+    const int nfull = (km - 1) / MF_CH;   // full chunks of the forward sweep
+    int nld = nfull;                      // chunks not loaded yet
     double ub[MF_NB][MF_CH], wb[MF_NB][MF_CH], cb[MF_NB][MF_CH];  // ring of chunk buffers
 #pragma unroll
     for (int s = 0; s < MF_NB; s++)
 #pragma unroll
       for (int c = 0; c < MF_CH; c++) { ub[s][c] = 0.0; wb[s][c] = 0.0; cb[s][c] = 0.0; }
     const ptrdiff_t pdc = (ptrdiff_t)MF_PD * vstr, pdn = (ptrdiff_t)MF_PD * n2i;
+    int kpf = 2 + MF_PD;  // level the next forward L2 prefetch targets
     auto load_fwd = [&](double* cc, double* uu, double* ww) {
-      if (nld >= MF_CH) {
-        if (MF_PD && nld >= MF_CH + MF_PD) {
+      if (nld > 0) {
+        if (MF_PD && kpf + MF_CH - 1 <= km) {
 #pragma unroll
           for (int c = 0; c < MF_CH; c++) {
             if (vstr) prefetch_l2(pc + pdc + (ptrdiff_t)c * vstr);
@@ -601,20 +603,13 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
             prefetch_l2(pv + pdn + (ptrdiff_t)c * n2i);
           }
         }
+        kpf += MF_CH;
 #pragma unroll
         for (int c = 0; c < MF_CH; c++) {
           cc[c] = *pc; uu[c] = *pu; ww[c] = *pv;
           pc += vstr; pu += n2i; pv += n2i;
         }
-        nld -= MF_CH;
-      } else {
-#pragma unroll
-        for (int c = 0; c < MF_CH; c++)
-          if (c < nld) {
-            cc[c] = *pc; uu[c] = *pu; ww[c] = *pv;
-            pc += vstr; pu += n2i; pv += n2i;
-          }
-        nld = 0;
+        nld--;
       }
     };
     auto fwd_level = [&](int k, double vvc, double ru, double rw) {
@@ -637,28 +632,26 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
       su += n2i;
       sv += n2i;
     };
-    auto fwd_chunk = [&](int kb, const double* cc, const double* uu, const double* ww) {
-      if (kb + MF_CH - 1 <= km) {
-#pragma unroll
-        for (int c = 0; c < MF_CH; c++) fwd_level(kb + c, cc[c], uu[c], ww[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < MF_CH; c++)
-          if (kb + c <= km) fwd_level(kb + c, cc[c], uu[c], ww[c]);
-      }
-    };
 #pragma unroll
     for (int s = 0; s < MF_NB - 1; s++) load_fwd(cb[s], ub[s], wb[s]);
-    for (int kb = 2; kb <= km; kb += MF_NB * MF_CH) {
+    int k = 2;
+    for (int ch = 0; ch < nfull; ch += MF_NB) {
 #pragma unroll
       for (int s = 0; s < MF_NB; s++)
-        if (kb + s * MF_CH <= km) {
+        if (ch + s < nfull) {
           load_fwd(cb[(s + MF_NB - 1) % MF_NB], ub[(s + MF_NB - 1) % MF_NB], wb[(s + MF_NB - 1) % MF_NB]);
-          fwd_chunk(kb + s * MF_CH, cb[s], ub[s], wb[s]);
+#pragma unroll
+          for (int c = 0; c < MF_CH; c++) fwd_level(k + c, cb[s][c], ub[s][c], wb[s][c]);
+          k += MF_CH;
         }
     }
+    for (; k <= km; k++) {  // the last (km-1) % MF_CH levels
+      const double vvc = *pc, ru = *pu, rw = *pv;
+      pc += vstr; pu += n2i; pv += n2i;
+      fwd_level(k, vvc, ru, rw);
+    }
     // ---- back substitution (only levels k < kmu change; F1,F2 = F(km)), fused with U = Uold + dU when finishing
-    if (MF_PD && finish) {
+    if (MF_PD && finish) {  // Uold, Vold are touched for the first time on the way up
 #pragma unroll
       for (int c = 1; c <= MF_PD; c++)
         if (c < km) { prefetch_l2(UOLD + q + top - (size_t)c * n2); prefetch_l2(VOLD + q + top - (size_t)c * n2); }
@@ -674,42 +667,36 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
     const double* qp = finish ? VOLD + q + top - n2i : Vn;
     double* tu = Un + top - n2i;        // next level to store
     double* tv = Vn + top - n2i;
-    nld = km - 1;
+    const int nfullb = (km - 1) / MF_BCH;
+    nld = nfullb;
+    kpf = km - 1 - MF_PD;
     double f1[MF_BNB][MF_BCH], f2[MF_BNB][MF_BCH], o1[MF_BNB][MF_BCH], o2[MF_BNB][MF_BCH];
 #pragma unroll
     for (int s = 0; s < MF_BNB; s++)
 #pragma unroll
       for (int c = 0; c < MF_BCH; c++) { f1[s][c] = 0.0; f2[s][c] = 0.0; o1[s][c] = 0.0; o2[s][c] = 0.0; }
     auto load_bwd = [&](double* a1, double* a2, double* b1, double* b2) {
-      if (nld >= MF_BCH) {
-        if (MF_PD && finish && nld >= MF_BCH + MF_PD) {  // Uold, Vold are touched for the first time on the way up
+      if (nld > 0) {
+        if (MF_PD && finish && kpf - MF_BCH + 1 >= 1) {
 #pragma unroll
           for (int c = 0; c < MF_BCH; c++) {
             prefetch_l2(qo - pdn - (ptrdiff_t)c * n2i);
             prefetch_l2(qp - pdn - (ptrdiff_t)c * n2i);
           }
         }
+        kpf -= MF_BCH;
 #pragma unroll
         for (int c = 0; c < MF_BCH; c++) {
           a1[c] = *qu; a2[c] = *qv;
           qu -= n2i; qv -= n2i;
           if (finish) { b1[c] = *qo; b2[c] = *qp; qo -= n2i; qp -= n2i; }
         }
-        nld -= MF_BCH;
-      } else {
-#pragma unroll
-        for (int c = 0; c < MF_BCH; c++)
-          if (c < nld) {
-            a1[c] = *qu; a2[c] = *qv;
-            qu -= n2i; qv -= n2i;
-            if (finish) { b1[c] = *qo; b2[c] = *qp; qo -= n2i; qp -= n2i; }
-          }
-        nld = 0;
+        nld--;
       }
     };
-    auto bwd_level = [&](int k, double a1, double a2, double b1, double b2) {
-      if (k < kmu) {
-        const double e = sE[(k - 1) * MF_THREADS];
+    auto bwd_level = [&](int kk, double a1, double a2, double b1, double b2) {
+      if (kk < kmu) {
+        const double e = sE[(kk - 1) * MF_THREADS];
         a1 = a1 + e * F1;
         a2 = a2 + e * F2;
         if (!finish) { *tu = a1; *tv = a2; }
@@ -717,32 +704,31 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
       F1 = a1;
       F2 = a2;
       if (finish) {
-        sE[(k - 1) * MF_THREADS] = b1 + a1;  // U(k); E(k) is not needed any more
+        sE[(kk - 1) * MF_THREADS] = b1 + a1;  // U(k); E(k) is not needed any more
         *tv = b2 + a2;
       }
       tu -= n2i;
       tv -= n2i;
     };
-    auto bwd_chunk = [&](int kt, const double* a1, const double* a2, const double* b1, const double* b2) {
-      if (kt - MF_BCH + 1 >= 1) {
-#pragma unroll
-        for (int c = 0; c < MF_BCH; c++) bwd_level(kt - c, a1[c], a2[c], b1[c], b2[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < MF_BCH; c++)
-          if (kt - c >= 1) bwd_level(kt - c, a1[c], a2[c], b1[c], b2[c]);
-      }
-    };
 #pragma unroll
     for (int s = 0; s < MF_BNB - 1; s++) load_bwd(f1[s], f2[s], o1[s], o2[s]);
-    for (int kt = km - 1; kt >= 1; kt -= MF_BNB * MF_BCH) {
+    k = km - 1;
+    for (int ch = 0; ch < nfullb; ch += MF_BNB) {
 #pragma unroll
       for (int s = 0; s < MF_BNB; s++)
-        if (kt - s * MF_BCH >= 1) {
+        if (ch + s < nfullb) {
           load_bwd(f1[(s + MF_BNB - 1) % MF_BNB], f2[(s + MF_BNB - 1) % MF_BNB], o1[(s + MF_BNB - 1) % MF_BNB],
                    o2[(s + MF_BNB - 1) % MF_BNB]);
-          bwd_chunk(kt - s * MF_BCH, f1[s], f2[s], o1[s], o2[s]);
+#pragma unroll
+          for (int c = 0; c < MF_BCH; c++) bwd_level(k - c, f1[s][c], f2[s][c], o1[s][c], o2[s][c]);
+          k -= MF_BCH;
         }
+    }
+    for (; k >= 1; k--) {
+      const double a1 = *qu, a2 = *qv, b1 = finish ? *qo : 0.0, b2 = finish ? *qp : 0.0;
+      qu -= n2i; qv -= n2i;
+      if (finish) { qo -= n2i; qp -= n2i; }
+      bwd_level(k, a1, a2, b1, b2);
     }
     if (!finish) return;
   } else {

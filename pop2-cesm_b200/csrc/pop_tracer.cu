@@ -826,7 +826,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
 #define IV_MINB 3
 #endif
 #ifndef IV_PD
-#define IV_PD 16  // L2 prefetch distance in levels (0: off)
+#define IV_PD 8   // L2 prefetch distance in levels (0: off)
 #endif
 #define IV_THREADS 128
 template <bool CORRECT>
@@ -863,42 +863,37 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
       Fm = div_by(hfac1 * R1, rd);
       Fb[0] = Fm;
     }
-    // ---- forward elimination, levels 2..km in chunks; loads of chunk c+1 are in flight during chunk c
+    // ---- forward elimination, levels 2..km: full chunks of IV_CH levels through the register ring (loads IV_NB-1
+    // chunks ahead, L2 prefetch IV_PD levels ahead), then the < IV_CH remaining levels one by one
     const double* pv = VDC1 + vstr;  // VDC of the next level to load (level 2)
     const double* pr = Tn + n2i;     // right-hand side of the next level to load
     double* pf = Fb + n2i;           // F of the next level to store
-    int nld = km - 1;                // levels not loaded yet
+    const int nfull = (km - 1) / IV_CH;  // full chunks of either sweep
+    int nld = nfull;                     // chunks not loaded yet
     double rb[IV_NB][IV_CH], vb[IV_NB][IV_CH];  // ring of chunk buffers (static indices after unrolling)
 #pragma unroll
     for (int s = 0; s < IV_NB; s++)
 #pragma unroll
       for (int c = 0; c < IV_CH; c++) { rb[s][c] = 0.0; vb[s][c] = 0.0; }
     const ptrdiff_t pdv = (ptrdiff_t)IV_PD * vstr, pdn = (ptrdiff_t)IV_PD * n2i;
+    int kpf = 2 + IV_PD;  // level the next forward L2 prefetch targets
     auto load_fwd = [&](double* v, double* r) {
-      if (nld >= IV_CH) {
-        if (IV_PD && nld >= IV_CH + IV_PD) {  // the chunk IV_PD levels further down exists: pull it into L2
+      if (nld > 0) {
+        if (IV_PD && kpf + IV_CH - 1 <= km) {
 #pragma unroll
           for (int c = 0; c < IV_CH; c++) {
             if (vstr) prefetch_l2(pv + pdv + (ptrdiff_t)c * vstr);
             if (!CORRECT) prefetch_l2(pr + pdn + (ptrdiff_t)c * n2i);
           }
         }
+        kpf += IV_CH;
 #pragma unroll
         for (int c = 0; c < IV_CH; c++) {
           v[c] = *pv;
           pv += vstr;
           if (!CORRECT) { r[c] = *pr; pr += n2i; }
         }
-        nld -= IV_CH;
-      } else {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++)
-          if (c < nld) {
-            v[c] = *pv;
-            pv += vstr;
-            if (!CORRECT) { r[c] = *pr; pr += n2i; }
-          }
-        nld = 0;
+        nld--;
       }
     };
     auto fwd_level = [&](int k, double vdc, double rhs) {
@@ -919,30 +914,29 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
       pf += n2i;
       Fm = F;
     };
-    auto fwd_chunk = [&](int kb, const double* v, const double* r) {
-      if (kb + IV_CH - 1 <= km) {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++) fwd_level(kb + c, v[c], r[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++)
-          if (kb + c <= km) fwd_level(kb + c, v[c], r[c]);
-      }
-    };
 #pragma unroll
     for (int s = 0; s < IV_NB - 1; s++) load_fwd(vb[s], rb[s]);
-    for (int kb = 2; kb <= km; kb += IV_NB * IV_CH) {
+    int k = 2;
+    for (int ch = 0; ch < nfull; ch += IV_NB) {
 #pragma unroll
       for (int s = 0; s < IV_NB; s++)
-        if (kb + s * IV_CH <= km) {
+        if (ch + s < nfull) {
           load_fwd(vb[(s + IV_NB - 1) % IV_NB], rb[(s + IV_NB - 1) % IV_NB]);
-          fwd_chunk(kb + s * IV_CH, vb[s], rb[s]);
+#pragma unroll
+          for (int c = 0; c < IV_CH; c++) fwd_level(k + c, vb[s][c], rb[s][c]);
+          k += IV_CH;
         }
     }
-    // ---- back substitution + final update, levels km..1 in chunks (Fm = F(km))
+    for (; k <= km; k++) {  // the last (km-1) % IV_CH levels
+      const double vdc = *pv, rhs = CORRECT ? 0.0 : *pr;
+      pv += vstr;
+      pr += n2i;
+      fwd_level(k, vdc, rhs);
+    }
+    // ---- back substitution + final update, levels km..1 (Fm = F(km)): the same ring going up
     double Fp = Fm;
     const size_t top = (size_t)(km - 1) * n2;
-    if (IV_PD && !CORRECT) {
+    if (IV_PD && !CORRECT) {  // TOLD is touched for the first time on the way up
 #pragma unroll
       for (int c = 0; c < IV_PD; c++)
         if (c < km) prefetch_l2(Bs + top - (size_t)c * n2);
@@ -951,13 +945,15 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
     const double* qf = Fb + top - n2i;  // F of the next level to load (level km-1), going up
     const double* qb = Bs + top - n2i;
     double* qt = Tn + top - n2i;        // next level to store
-    nld = km - 1;
+    nld = nfull;
+    kpf = km - 1 - IV_PD;               // level the next backward L2 prefetch targets
     auto load_bwd = [&](double* f, double* b) {
-      if (nld >= IV_CH) {
-        if (IV_PD && !CORRECT && nld >= IV_CH + IV_PD) {  // TOLD is touched for the first time on the way up
+      if (nld > 0) {
+        if (IV_PD && !CORRECT && kpf - IV_CH + 1 >= 1) {
 #pragma unroll
           for (int c = 0; c < IV_CH; c++) prefetch_l2(qb - pdn - (ptrdiff_t)c * n2i);
         }
+        kpf -= IV_CH;
 #pragma unroll
         for (int c = 0; c < IV_CH; c++) {
           f[c] = *qf;
@@ -965,45 +961,34 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
           qf -= n2i;
           qb -= n2i;
         }
-        nld -= IV_CH;
-      } else {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++)
-          if (c < nld) {
-            f[c] = *qf;
-            b[c] = *qb;
-            qf -= n2i;
-            qb -= n2i;
-          }
-        nld = 0;
+        nld--;
       }
     };
-    auto bwd_level = [&](int k, double f, double b) {
+    auto bwd_level = [&](int kk, double f, double b) {
       double F = f;
-      if (k < kmt) F = F + sE[(k - 1) * IV_THREADS] * Fp;
+      if (kk < kmt) F = F + sE[(kk - 1) * IV_THREADS] * Fp;
       *qt = b + F;
       qt -= n2i;
       Fp = F;
     };
-    auto bwd_chunk = [&](int kt, const double* f, const double* b) {
-      if (kt - IV_CH + 1 >= 1) {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++) bwd_level(kt - c, f[c], b[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < IV_CH; c++)
-          if (kt - c >= 1) bwd_level(kt - c, f[c], b[c]);
-      }
-    };
 #pragma unroll
     for (int s = 0; s < IV_NB - 1; s++) load_bwd(rb[s], vb[s]);
-    for (int kt = km - 1; kt >= 1; kt -= IV_NB * IV_CH) {
+    k = km - 1;
+    for (int ch = 0; ch < nfull; ch += IV_NB) {
 #pragma unroll
       for (int s = 0; s < IV_NB; s++)
-        if (kt - s * IV_CH >= 1) {
+        if (ch + s < nfull) {
           load_bwd(rb[(s + IV_NB - 1) % IV_NB], vb[(s + IV_NB - 1) % IV_NB]);
-          bwd_chunk(kt - s * IV_CH, rb[s], vb[s]);
+#pragma unroll
+          for (int c = 0; c < IV_CH; c++) bwd_level(k - c, rb[s][c], vb[s][c]);
+          k -= IV_CH;
         }
+    }
+    for (; k >= 1; k--) {
+      const double f = *qf, b2 = *qb;
+      qf -= n2i;
+      qb -= n2i;
+      bwd_level(k, f, b2);
     }
   }
 }
