@@ -51,6 +51,10 @@ WORKLOADS = {
 }
 
 
+PRECOND = {"diagonal": 0, "evp": 1}
+_PRECOND_CHOICE = ["diagonal"]   # set from --precond
+
+
 def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
     nx, ny, km, vg, dt = WORKLOADS[workload]
     scale = 3600.0 / nx   # biharmonic coefficients scale with dx^3 (hmix_del4.F90 lauto rule ~ 1/nx)
@@ -73,6 +77,7 @@ def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
         kw.update(hmix_tracer_itype=c.HMIX_DEL2, hmix_momentum_itype=c.HMIX_DEL2, lvariable_hmixt=0, lvariable_hmixu=0,
                   ah=1.0e7, am=1.0e8, vmix_itype=c.VMIX_CONST, vdc_kdim_halo=0, vdc_ndim=1,
                   solver_choice=c.SOLVER_CHRONGEAR, tadvect=c.TADVECT_UPWIND3, ns_boundary_type=c.BNDY_CLOSED)
+    kw.update(preconditioner_choice=PRECOND[_PRECOND_CHOICE[0]])
     if block:
         kw.update(block_size_x=block[0], block_size_y=block[1])
     return c.make_config(**kw), vg
@@ -336,7 +341,7 @@ def run_pop(args):
     if args.no_e2e:      # profiling runs (tools/ncu_kernels.sh): device-resident region only, no JSON contract
         p.finalize()
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms / K, "launches": launches,
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / K, "launches": launches, "solver_iterations": iters,
                               "phases_ms_per_step": {n: tm[n][0] / K for n in tm}}))
         return
     # ---- timed region 2: end to end through pop_step_coupled with pinned host buffers
@@ -424,10 +429,10 @@ def run_pop(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (seeded analytic fields + hash noise, synthetic bathymetry)",
         "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt %s given-KPP-shaped-vmix "
-                               "PCSI/diagonal 1e-13 dt=%gs full-cells, 1x%d j-strips"
+                               "PCSI/%s 1e-13 dt=%gs full-cells, 1x%d j-strips"
                                % (args.workload, nx, ny, km, nt,
                                   "GM(const kappa, notanh)+del2u" if cfg.hmix_tracer_itype == c.HMIX_GM else "del4(variable)",
-                                  cfg.dtt, world),
+                                  args.precond, cfg.dtt, world),
                    "l2": "inputs larger than L2 (state is %.0f GB; no explicit flush)" % (cells * 8 * (3 * nt + 9 + 3) / 1e9),
                    "solver_iterations_per_step": iters, "ocean_cell_updates_per_s": ocean * K / (ms * 1e-3)},
         "roofline": roof,
@@ -633,10 +638,13 @@ def main():
     ap.add_argument("--impl", default="pop", choices=["pop", "reference"])
     ap.add_argument("--workload", default="tx0.1v3", choices=list(WORKLOADS))
     ap.add_argument("--nt", type=int, default=2)
+    ap.add_argument("--precond", default="diagonal", choices=list(PRECOND),
+                    help="barotropic preconditioner: diagonal (timed default) or evp (the reference's production default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle-vs-library parity check of the CPU sample")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: device-resident timed region only")
     args = ap.parse_args()
+    _PRECOND_CHOICE[0] = args.precond
     if args.impl == "reference":
         run_reference(args)
     else:
