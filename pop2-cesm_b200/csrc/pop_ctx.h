@@ -149,6 +149,9 @@ struct Ctx {
   bool no_pcsi_blocking = false;  // POP_B200_NO_PCSI_BLOCKING=1: one P-CSI iteration per pass (debugging aid)
   bool no_fast_tracer = false;  // POP_B200_NO_FAST_TRACER=1: always the general tracer column kernel
   bool no_tma = false;  // POP_B200_NO_TMA=1: force the plain-load column kernels (debugging aid)
+  // POP_B200_THOMAS_TMA=1: the TMA-staged Thomas kernels (opt-in: measured slower than the register-ring kernels,
+  // 33.6 vs 20.2 ms for the two tracer solves at tx0.1v3 -- profiles/r2_ncu_summary.md)
+  bool thomas_tma = false;
 };
 
 extern Ctx G;

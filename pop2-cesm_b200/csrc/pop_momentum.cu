@@ -780,10 +780,243 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   }
 }
 
+// ---- the velocity finish with the operands staged by TMA (opt-in, POP_B200_THOMAS_TMA=1; bit-identical, measured slower:
+// 14.3 vs 11.5 ms at tx0.1v3) ---
+// Same passes as above; the level rows of the CTA's 128 columns (VVC and the two right-hand sides on the way down,
+// Uold and Vold on the way up) arrive as 128 x 1 x 1 TMA boxes in an MTS-deep shared-memory ring filled by one elected
+// thread across the sweep boundary; F1,F2 are re-read from L2 by plain loads one chunk ahead.
+// Shared memory per CTA: km + 3*MTS*MTC KB (62 + 48 KB): two CTAs per SM.
+#ifndef MTC
+#define MTC 4
+#endif
+#ifndef MTS
+#define MTS 4
+#endif
+struct MfTmaArgs {
+  GridView g;
+  double *UNEW, *VNEW;
+  const double *UOLD, *VOLD, *UB, *VB;
+  int bt_skip_row;
+  PopTmap tmU, tmV, tmUo, tmVo, tmC;  // UNEW, VNEW, UOLD, VOLD (nxb,nyb,km); VVC (nxb,nyb,vvc_nk)
+};
+__global__ void __launch_bounds__(MF_THREADS, 2)
+momentum_finish_tma_kernel(const POP_GRID_CONSTANT MfTmaArgs a) {
+  POP_DYN_SMEM(smem_raw);
+  const GridView& g = a.g;
+  const int km = g.km, tid = threadIdx.x;
+  double* sEb = (double*)smem_raw;
+  double* ring = sEb + (size_t)km * MF_THREADS;  // [MTS][MTC][3][MF_THREADS]
+  uint64_t* bar = (uint64_t*)(ring + (size_t)MTS * MTC * 3 * MF_THREADS);
+  double* sE = sEb + tid;
+  const int i0 = (g.ib - 1) + blockIdx.x * MF_THREADS;
+  const int j = (g.jb - 1) + blockIdx.y;
+  const int i = i0 + tid;
+  const bool active = (i <= g.ie - 1);
+  const size_t n2 = g.n2;
+  const int n2i = (int)n2;
+  const size_t q = (size_t)j * g.nxb + (active ? i : i0);
+  const int kmu = active ? g.KMU[q] : 0;
+  double* Un = a.UNEW + q;
+  double* Vn = a.VNEW + q;
+  const size_t top = (size_t)(km - 1) * n2;
+  const int nch = (km - 1 + MTC - 1) / MTC;
+  const int total = 2 * nch;
+  auto issue = [&](int gi) {
+    const int slot = gi % MTS;
+    double* st = ring + (size_t)slot * MTC * 3 * MF_THREADS;
+    if (gi < nch) {
+      const int k0 = 2 + gi * MTC;
+      const int nl = (km - k0 + 1 < MTC) ? km - k0 + 1 : MTC;
+      mbar_expect_tx(&bar[slot], (uint32_t)(nl * 3 * MF_THREADS * 8));
+      for (int c = 0; c < nl; c++) {
+        const int k = k0 + c;
+        tma_load_tile(st + (size_t)(c * 3) * MF_THREADS, &a.tmC, i0, j, (g.vvc_nk == 1) ? 0 : k - 1, &bar[slot]);
+        tma_load_tile(st + (size_t)(c * 3 + 1) * MF_THREADS, &a.tmU, i0, j, k - 1, &bar[slot]);
+        tma_load_tile(st + (size_t)(c * 3 + 2) * MF_THREADS, &a.tmV, i0, j, k - 1, &bar[slot]);
+      }
+    } else {
+      const int k0 = km - 1 - (gi - nch) * MTC;
+      const int nl = (k0 < MTC) ? k0 : MTC;
+      mbar_expect_tx(&bar[slot], (uint32_t)(nl * 2 * MF_THREADS * 8));
+      for (int c = 0; c < nl; c++) {
+        tma_load_tile(st + (size_t)(c * 3) * MF_THREADS, &a.tmUo, i0, j, k0 - c - 1, &bar[slot]);
+        tma_load_tile(st + (size_t)(c * 3 + 1) * MF_THREADS, &a.tmVo, i0, j, k0 - c - 1, &bar[slot]);
+      }
+    }
+  };
+  if (tid == 0) {
+    for (int sl = 0; sl < MTS; sl++) mbar_init(&bar[sl], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int gi = 0; gi < MTS && gi < total; gi++) issue(gi);
+  int gc = 0;
+  auto next_chunk = [&]() {
+    __syncthreads();
+    if (tid == 0 && gc + MTS < total) issue(gc + MTS);
+    gc++;
+  };
+  double A = 0.0, B = 0.0, C = 0.0, F1 = 0.0, F2 = 0.0;
+  if (active) {
+    const double hfac = c_vc.hfac_u[1];
+    A = c_vc.afac_u[1] * g.VVC[q];
+    const RcpD rd = rcp_prepare(hfac + A);
+    const double e = div_by(A, rd);
+    sE[0] = e;
+    B = hfac * e;
+    F1 = div_by(hfac * Un[0], rd);
+    F2 = div_by(hfac * Vn[0], rd);
+    Un[0] = F1;
+    Vn[0] = F2;
+  }
+  // ---- forward elimination
+  {
+    double* su = Un + n2i;
+    double* sv = Vn + n2i;
+    for (int r = 0; r < nch; r++) {
+      const double* st = ring + (size_t)(gc % MTS) * MTC * 3 * MF_THREADS + tid;
+      mbar_wait(&bar[gc % MTS], (uint32_t)((gc / MTS) & 1));
+      const int k0 = 2 + r * MTC;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < MTC; c++) {
+          const int k = k0 + c;
+          if (k <= km) {
+            const double vvc = st[(size_t)(c * 3) * MF_THREADS];
+            const double ru = st[(size_t)(c * 3 + 1) * MF_THREADS], rw = st[(size_t)(c * 3 + 2) * MF_THREADS];
+            const double hfac = c_vc.hfac_u[k];
+            C = A;
+            A = c_vc.afac_u[k] * vvc;
+            if (k <= kmu) {
+              const RcpD rd = rcp_prepare((k < kmu) ? hfac + A + B : hfac + B);
+              const double e = div_by(A, rd);
+              sE[(size_t)(k - 1) * MF_THREADS] = e;
+              B = (hfac + B) * e;
+              F1 = div_by(hfac * ru + C * F1, rd);
+              F2 = div_by(hfac * rw + C * F2, rd);
+            } else {
+              F1 = 0.0;
+              F2 = 0.0;
+            }
+            *su = F1;
+            *sv = F2;
+            su += n2i;
+            sv += n2i;
+          }
+        }
+      }
+      next_chunk();
+    }
+  }
+  // ---- back substitution fused with U = Uold + dU (U(k) recycles the E(k) slot, V(k) goes back in place)
+  if (active) {
+    const double u = a.UOLD[top + q] + F1, v = a.VOLD[top + q] + F2;
+    sE[(size_t)(km - 1) * MF_THREADS] = u;
+    Vn[top] = v;
+  }
+  {
+    const double* qu = Un + top - n2i;  // F1, F2 of the next level to load (km-1), going up
+    const double* qv = Vn + top - n2i;
+    double* tv = Vn + top - n2i;
+    double fa1[MTC], fa2[MTC], fn1[MTC], fn2[MTC];
+#pragma unroll
+    for (int c = 0; c < MTC; c++) { fa1[c] = fa2[c] = fn1[c] = fn2[c] = 0.0; }
+    int kl = km - 1;
+    auto load_f = [&](double* f1, double* f2) {
+#pragma unroll
+      for (int c = 0; c < MTC; c++)
+        if (active && kl - c >= 1) { f1[c] = qu[-(ptrdiff_t)c * n2i]; f2[c] = qv[-(ptrdiff_t)c * n2i]; }
+      qu -= (ptrdiff_t)MTC * n2i;
+      qv -= (ptrdiff_t)MTC * n2i;
+      kl -= MTC;
+    };
+    load_f(fa1, fa2);
+    for (int r = 0; r < nch; r++) {
+      const double* st = ring + (size_t)(gc % MTS) * MTC * 3 * MF_THREADS + tid;
+      load_f(fn1, fn2);
+      mbar_wait(&bar[gc % MTS], (uint32_t)((gc / MTS) & 1));
+      const int k0 = km - 1 - r * MTC;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < MTC; c++) {
+          const int k = k0 - c;
+          if (k >= 1) {
+            double a1 = fa1[c], a2 = fa2[c];
+            if (k < kmu) {
+              const double e = sE[(size_t)(k - 1) * MF_THREADS];
+              a1 = a1 + e * F1;
+              a2 = a2 + e * F2;
+            }
+            F1 = a1;
+            F2 = a2;
+            sE[(size_t)(k - 1) * MF_THREADS] = st[(size_t)(c * 3) * MF_THREADS] + a1;
+            *tv = st[(size_t)(c * 3 + 1) * MF_THREADS] + a2;
+            tv -= n2i;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MTC; c++) { fa1[c] = fn1[c]; fa2[c] = fn2[c]; }
+      next_chunk();
+    }
+  }
+  if (!active) return;
+  // ---- remove the vertical mean, KMU mask [+ barotropic velocity]
+  const double hur = g.HUR[q];
+  double w1 = 0.0, w2 = 0.0;
+  {
+    const double* pv = Vn;
+#pragma unroll 8
+    for (int k = 1; k <= km; k++) {
+      w1 = w1 + sE[(size_t)(k - 1) * MF_THREADS] * c_vc.dz[k];
+      w2 = w2 + *pv * c_vc.dz[k];
+      pv += n2i;
+    }
+  }
+  w1 = w1 * hur;
+  w2 = w2 * hur;
+  const bool addbt = (a.UB != nullptr) && (j != a.bt_skip_row);
+  const double ub = addbt ? a.UB[q] : 0.0, vb = addbt ? a.VB[q] : 0.0;
+  {
+    double* tu = Un;
+    double* tv = Vn;
+#pragma unroll 8
+    for (int k = 1; k <= km; k++) {
+      double u = 0.0, v = 0.0;
+      if (k <= kmu) {
+        u = sE[(size_t)(k - 1) * MF_THREADS] - w1;
+        v = *tv - w2;
+        if (addbt) { u = u + ub; v = v + vb; }
+      }
+      *tu = u;
+      *tv = v;
+      tu += n2i;
+      tv += n2i;
+    }
+  }
+}
+
 static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const double* VOLD, const double* UB,
                          const double* VB, int bt_skip_row, int implicit_vmix, int finish) {
   GridView g = grid_view();
   dim3 block(MF_THREADS, 1, 1), grid((unsigned)((G.nxg + MF_THREADS - 1) / MF_THREADS), (unsigned)G.ny_local, 1);
+  if (implicit_vmix && finish && !G.no_tma && G.thomas_tma) {
+    MfTmaArgs ta;
+    if (make_tmap_box(&ta.tmU, UNEW, G.km, MF_THREADS, 1) && make_tmap_box(&ta.tmV, VNEW, G.km, MF_THREADS, 1) &&
+        make_tmap_box(&ta.tmUo, UOLD, G.km, MF_THREADS, 1) && make_tmap_box(&ta.tmVo, VOLD, G.km, MF_THREADS, 1) &&
+        make_tmap_box(&ta.tmC, g.VVC, g.vvc_nk, MF_THREADS, 1)) {
+      ta.g = g; ta.UNEW = UNEW; ta.VNEW = VNEW; ta.UOLD = UOLD; ta.VOLD = VOLD; ta.UB = UB; ta.VB = VB;
+      ta.bt_skip_row = bt_skip_row;
+      const size_t smem_t = sizeof(double) * MF_THREADS * ((size_t)G.km + (size_t)MTS * MTC * 3) + 8 * MTS + 16;
+#ifndef POP_EMUL
+      POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+      POP_LAUNCH(momentum_finish_tma_kernel, grid, block, smem_t, ta);
+      return pop_post_launch("momentum_finish");
+    }
+  }
   const size_t smem = sizeof(double) * MF_THREADS * (size_t)G.km;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -993,6 +993,187 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
   }
 }
 
+// ---- the same solve with the operands staged by TMA (opt-in, POP_B200_THOMAS_TMA=1: the north_star's "warp-cooperative
+// path"; bit-identical, but measured SLOWER than the register-ring kernel above on B200: with E(k) and the ring in shared
+// memory only 8 warps fit per SM, and the per-chunk barrier + mbarrier wait cost more than the DRAM latency they hide) --
+// A warp owns 32 neighbouring columns, a CTA 128 (one 1 KB run per level and array).  One elected thread streams the
+// level rows of the CTA -- VDC and the right-hand side on the way down, the field the solution is added to on the way
+// up -- as 128 x 1 x 1 TMA boxes into a TVS-deep shared-memory ring, chunk by chunk, across the sweep and tracer
+// boundaries (the whole sequence of chunks is known up front), with one mbarrier per ring slot; the recurrence reads
+// its operands from shared memory with immediate offsets: no address arithmetic, no scoreboard wait on DRAM in the
+// dependent chain.  E(k) stays in shared memory, F streams through the output array as before (re-read from L2 by
+// plain loads one chunk ahead: a TMA read of lines this CTA has just written would need a cross-proxy fence).
+// Shared memory per CTA: km + 2*TVS*TVC KB (62 + 40 KB): two CTAs per SM.
+#ifndef TVC
+#define TVC 4   // levels per chunk
+#endif
+#ifndef TVS
+#define TVS 5   // ring slots
+#endif
+struct IvTmaArgs {
+  GridView g;
+  double* TNEW;
+  const double *TOLD, *PSFC, *RHS;
+  double* FB;
+  int nfirst, nlast, varthick;
+  PopTmap tmT, tmO, tmV;  // TNEW, TOLD (nxb, nyb, km*nt); VDC (nxb, nyb, vdc_nd*vdc_nk): boxes of IV_THREADS x 1 x 1
+};
+template <bool CORRECT>
+__global__ void __launch_bounds__(IV_THREADS, 2)
+impvmixt_tma_kernel(const POP_GRID_CONSTANT IvTmaArgs a) {
+  POP_DYN_SMEM(smem_raw);
+  const GridView& g = a.g;
+  const int km = g.km, tid = threadIdx.x;
+  double* sEb = (double*)smem_raw;                       // E(k): [km][IV_THREADS]
+  double* ring = sEb + (size_t)km * IV_THREADS;          // [TVS][TVC][2][IV_THREADS]
+  uint64_t* bar = (uint64_t*)(ring + (size_t)TVS * TVC * 2 * IV_THREADS);
+  double* sE = sEb + tid;
+  const int i0 = (g.ib - 1) + blockIdx.x * IV_THREADS;
+  const int j = (g.jb - 1) + blockIdx.y;
+  const int i = i0 + tid;
+  const bool active = (i <= g.ie - 1);
+  const size_t n2 = g.n2;
+  const int n2i = (int)n2;
+  const size_t q = (size_t)j * g.nxb + (active ? i : i0);
+  const int kmt = active ? g.KMT[q] : 0;
+  const double hfac1 = c_vc.hfac_t[1];
+  const double H1 = a.varthick ? hfac1 + a.PSFC[q] / (POP_GRAV * c_vc.c2dtt[1]) : hfac1;
+  const int nch = (km - 1 + TVC - 1) / TVC;   // chunks per sweep (levels 2..km down, km-1..1 up)
+  const int ntr = a.nlast - a.nfirst + 1;
+  const int total = ntr * 2 * nch;            // chunks of the whole kernel, in the order they are consumed
+  // ---- producer (thread 0): chunk gi of the sequence -> ring slot gi % TVS
+  auto issue = [&](int gi) {
+    const int tr = gi / (2 * nch), r = gi % (2 * nch);
+    const int n = a.nfirst + tr;  // 1-based tracer
+    const int slot = gi % TVS;
+    double* st = ring + (size_t)slot * TVC * 2 * IV_THREADS;
+    if (r < nch) {  // way down: levels k0 .. k0+TVC-1
+      const int k0 = 2 + r * TVC;
+      const int nl = (km - k0 + 1 < TVC) ? km - k0 + 1 : TVC;
+      mbar_expect_tx(&bar[slot], (uint32_t)(nl * (CORRECT ? 1 : 2) * IV_THREADS * 8));
+      const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
+      for (int c = 0; c < nl; c++) {
+        const int k = k0 + c;
+        const int zv = (mt2 - 1) * g.vdc_nk + ((g.vdc_nk == 1) ? 0 : k - g.vdc_k0);
+        tma_load_tile(st + (size_t)(c * 2) * IV_THREADS, &a.tmV, i0, j, zv, &bar[slot]);
+        if (!CORRECT) tma_load_tile(st + (size_t)(c * 2 + 1) * IV_THREADS, &a.tmT, i0, j, (n - 1) * km + (k - 1), &bar[slot]);
+      }
+    } else {        // way up: levels k0, k0-1, ...
+      const int k0 = km - 1 - (r - nch) * TVC;
+      const int nl = (k0 < TVC) ? k0 : TVC;
+      mbar_expect_tx(&bar[slot], (uint32_t)(nl * IV_THREADS * 8));
+      for (int c = 0; c < nl; c++)
+        tma_load_tile(st + (size_t)(c * 2) * IV_THREADS, CORRECT ? &a.tmT : &a.tmO, i0, j, (n - 1) * km + (k0 - c - 1),
+                      &bar[slot]);
+    }
+  };
+  if (tid == 0) {
+    for (int sl = 0; sl < TVS; sl++) mbar_init(&bar[sl], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int gi = 0; gi < TVS && gi < total; gi++) issue(gi);
+  int gc = 0;  // chunk being consumed
+  auto next_chunk = [&]() {  // every thread is done with the slot of chunk gc: refill it, move on
+    __syncthreads();
+    if (tid == 0 && gc + TVS < total) issue(gc + TVS);
+    gc++;
+  };
+  for (int n = a.nfirst; n <= a.nlast; n++) {
+    const int mt2 = (n < g.vdc_nd) ? n : g.vdc_nd;
+    const double* VDC1 = g.VDC + (size_t)(mt2 - 1) * g.vdc_nk * n2 + q + (size_t)(1 - g.vdc_k0) * n2;
+    double* Tn = a.TNEW + (size_t)(n - 1) * km * n2 + q;
+    double* Fb = CORRECT ? a.FB + q : Tn;
+    double A = 0.0, B = 0.0, C = 0.0, Fm = 0.0;
+    if (active) {
+      A = c_vc.afac_t[1] * VDC1[0];
+      const RcpD rd = rcp_prepare(H1 + A);
+      const double e = div_by(A, rd);
+      sE[0] = e;
+      B = H1 * e;
+      const double R1 = CORRECT ? a.RHS[(size_t)(n - 1) * n2 + q] : Tn[0];
+      Fm = div_by(hfac1 * R1, rd);
+      Fb[0] = Fm;
+    }
+    // ---- forward elimination
+    double* pf = Fb + n2i;  // F of the next level to store
+    for (int r = 0; r < nch; r++) {
+      const double* st = ring + (size_t)(gc % TVS) * TVC * 2 * IV_THREADS + tid;
+      mbar_wait(&bar[gc % TVS], (uint32_t)((gc / TVS) & 1));
+      const int k0 = 2 + r * TVC;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < TVC; c++) {
+          const int k = k0 + c;
+          if (k <= km) {
+            const double vdc = st[(size_t)(c * 2) * IV_THREADS];
+            const double rhs = CORRECT ? 0.0 : st[(size_t)(c * 2 + 1) * IV_THREADS];
+            C = A;
+            A = c_vc.afac_t[k] * vdc;
+            const double hfac = c_vc.hfac_t[k];
+            double F;
+            if (k > kmt) {
+              F = 0.0;
+            } else {
+              const RcpD rd = rcp_prepare((k == kmt) ? hfac + B : hfac + A + B);
+              const double e = div_by(A, rd);
+              sE[(size_t)(k - 1) * IV_THREADS] = e;
+              B = (hfac + B) * e;
+              F = CORRECT ? div_by(C * Fm, rd) : div_by(hfac * rhs + C * Fm, rd);
+            }
+            *pf = F;
+            pf += n2i;
+            Fm = F;
+          }
+        }
+      }
+      next_chunk();
+    }
+    // ---- back substitution + final update (Fm = F(km))
+    double Fp = Fm;
+    const size_t top = (size_t)(km - 1) * n2;
+    const double* Bs = CORRECT ? Tn : a.TOLD + (size_t)(n - 1) * km * n2 + q;
+    if (active) Tn[top] = Bs[top] + Fp;
+    const double* qf = Fb + top - n2i;  // F of the next level to load (km-1), going up: plain loads, L2-resident
+    double* qt = Tn + top - n2i;        // next level to store
+    double fa[TVC], fn[TVC];
+#pragma unroll
+    for (int c = 0; c < TVC; c++) { fa[c] = 0.0; fn[c] = 0.0; }
+    int kl = km - 1;  // next level to load F of
+    auto load_f = [&](double* f) {
+#pragma unroll
+      for (int c = 0; c < TVC; c++)
+        if (active && kl - c >= 1) f[c] = qf[-(ptrdiff_t)c * n2i];
+      qf -= (ptrdiff_t)TVC * n2i;
+      kl -= TVC;
+    };
+    load_f(fa);
+    for (int r = 0; r < nch; r++) {
+      const double* st = ring + (size_t)(gc % TVS) * TVC * 2 * IV_THREADS + tid;
+      load_f(fn);
+      mbar_wait(&bar[gc % TVS], (uint32_t)((gc / TVS) & 1));
+      const int k0 = km - 1 - r * TVC;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < TVC; c++) {
+          const int k = k0 - c;
+          if (k >= 1) {
+            double F = fa[c];
+            if (k < kmt) F = F + sE[(size_t)(k - 1) * IV_THREADS] * Fp;
+            *qt = st[(size_t)(c * 2) * IV_THREADS] + F;
+            qt -= n2i;
+            Fp = F;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < TVC; c++) fa[c] = fn[c];
+      next_chunk();
+    }
+  }
+}
+
 int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const double* RHS, int nfirst,
                  int nlast, int correct) {
   if (nfirst > nlast || nfirst > G.nt) return POP_SUCCESS;  // vertical_mix.F90:1232
@@ -1002,6 +1183,26 @@ int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const dou
   const int varthick = (G.cfg.sfc_layer_type == POP_SFC_VARTHICK);
   dim3 block(IV_THREADS, 1, 1), grid((unsigned)((G.nxg + IV_THREADS - 1) / IV_THREADS), (unsigned)G.ny_local, 1);
   double* FB = fld("WORK3D_E");
+  // TMA-staged path (needs an even row pitch; TOLD is only dereferenced by the predictor form)
+  IvTmaArgs ta;
+  const bool tma = !G.no_tma && G.thomas_tma && make_tmap_box(&ta.tmT, TNEW, G.km * G.nt, IV_THREADS, 1) &&
+                   (correct || make_tmap_box(&ta.tmO, TOLD, G.km * G.nt, IV_THREADS, 1)) &&
+                   make_tmap_box(&ta.tmV, g.VDC, g.vdc_nd * g.vdc_nk, IV_THREADS, 1);
+  if (tma) {
+    ta.g = g; ta.TNEW = TNEW; ta.TOLD = TOLD; ta.PSFC = PSFC; ta.RHS = RHS; ta.FB = FB;
+    ta.nfirst = nfirst; ta.nlast = nlast; ta.varthick = varthick;
+    if (correct) ta.tmO = ta.tmT;
+    const size_t smem = sizeof(double) * IV_THREADS * ((size_t)G.km + (size_t)TVS * TVC * 2) + 8 * TVS + 16;
+    auto kc = impvmixt_tma_kernel<true>;
+    auto kp = impvmixt_tma_kernel<false>;
+#ifndef POP_EMUL
+    POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
+    if (correct) POP_LAUNCH(kc, grid, block, smem, ta);
+    else POP_LAUNCH(kp, grid, block, smem, ta);
+    return pop_post_launch("impvmixt");
+  }
   const size_t smem = sizeof(double) * IV_THREADS * (size_t)G.km;
   auto kc = impvmixt_kernel<true>;
   auto kp = impvmixt_kernel<false>;
