@@ -53,6 +53,7 @@ WORKLOADS = {
 
 PRECOND = {"diagonal": 0, "evp": 1}
 _PRECOND_CHOICE = ["diagonal"]   # set from --precond
+_PBC = [False]                   # set from --pbc: partial bottom cells (the production setting of tx0.1v3)
 
 
 def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
@@ -77,7 +78,7 @@ def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
         kw.update(hmix_tracer_itype=c.HMIX_DEL2, hmix_momentum_itype=c.HMIX_DEL2, lvariable_hmixt=0, lvariable_hmixu=0,
                   ah=1.0e7, am=1.0e8, vmix_itype=c.VMIX_CONST, vdc_kdim_halo=0, vdc_ndim=1,
                   solver_choice=c.SOLVER_CHRONGEAR, tadvect=c.TADVECT_UPWIND3, ns_boundary_type=c.BNDY_CLOSED)
-    kw.update(preconditioner_choice=PRECOND[_PRECOND_CHOICE[0]])
+    kw.update(preconditioner_choice=PRECOND[_PRECOND_CHOICE[0]], partial_bottom_cells=1 if _PBC[0] else 0)
     if block:
         kw.update(block_size_x=block[0], block_size_y=block[1])
     return c.make_config(**kw), vg
@@ -165,6 +166,14 @@ def static_inputs(workload):
         kmt[-3:, :] = np.minimum(kmt[-3:, :], kmt[-3:, ::-1])
     kmu = syn.kmu_from_kmt(kmt, ew_cyclic=True, ns_type=c.BNDY_TRIPOLE if tripole else c.BNDY_CLOSED)
     return grid, dz, kmt, kmu
+
+
+def bottom_cells(workload, kmt, dz):
+    """DZBC for --pbc: a seeded fraction (0.25 .. 1) of the full thickness of every column's bottom level"""
+    d = syn.bottom_cells(kmt, dz, 20240611 + 40)
+    if workload != "gx3v7":
+        d[-3:, :] = np.minimum(d[-3:, :], d[-3:, ::-1])
+    return d
 
 
 def fill_pop(p, F, nt):
@@ -294,6 +303,8 @@ def run_pop(args):
     nx, ny, km = cfg.nx_global, cfg.ny_global, cfg.km
     grid, dz, kmt, kmu = static_inputs(args.workload)
     p = P.api.Pop(cfg, comm_id)
+    if cfg.partial_bottom_cells:
+        p.set_bottom_cells(bottom_cells(args.workload, kmt, dz))
     p.set_grid(grid, kmt, dz)
     if cfg.hmix_tracer_itype == c.HMIX_GM:
         p.scatter("TLAT", 0, grid["TLAT"])
@@ -429,10 +440,10 @@ def run_pop(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (seeded analytic fields + hash noise, synthetic bathymetry)",
         "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt %s given-KPP-shaped-vmix "
-                               "PCSI/%s 1e-13 dt=%gs full-cells, 1x%d j-strips"
+                               "PCSI/%s 1e-13 dt=%gs %s, 1x%d j-strips"
                                % (args.workload, nx, ny, km, nt,
                                   "GM(const kappa, notanh)+del2u" if cfg.hmix_tracer_itype == c.HMIX_GM else "del4(variable)",
-                                  args.precond, cfg.dtt, world),
+                                  args.precond, cfg.dtt, "partial-bottom-cells" if args.pbc else "full-cells", world),
                    "l2": "inputs larger than L2 (state is %.0f GB; no explicit flush)" % (cells * 8 * (3 * nt + 9 + 3) / 1e9),
                    "solver_iterations_per_step": iters, "ocean_cell_updates_per_s": ocean * K / (ms * 1e-3)},
         "roofline": roof,
@@ -483,6 +494,8 @@ def oracle_setup(sample, nt, threads, reproducible=False):
     o = O.Oracle(cfg, so)
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the team size is set explicitly and read back
     used = o.set_threads(threads)
+    if cfg.partial_bottom_cells:
+        o.set_bottom_cells(bottom_cells(sample, kmt, dz))
     o.set_grid(grid, kmt, dz)
     if cfg.hmix_tracer_itype == c.HMIX_GM:
         o.scatter("TLAT", 0, grid["TLAT"])
@@ -551,6 +564,8 @@ def cpu_baseline(args, steps, check):
         grid, dz, kmt, kmu = static_inputs(sample)
         pcfg, _ = make_cfg(sample, args.nt)
         p = P.api.Pop(pcfg, None)
+        if pcfg.partial_bottom_cells:
+            p.set_bottom_cells(bottom_cells(sample, kmt, dz))
         p.set_grid(grid, kmt, dz)
         if pcfg.hmix_tracer_itype == c.HMIX_GM:
             p.scatter("TLAT", 0, grid["TLAT"])
@@ -640,11 +655,15 @@ def main():
     ap.add_argument("--nt", type=int, default=2)
     ap.add_argument("--precond", default="diagonal", choices=list(PRECOND),
                     help="barotropic preconditioner: diagonal (timed default) or evp (the reference's production default)")
+    ap.add_argument("--pbc", action="store_true",
+                    help="partial bottom cells (namelist_defaults_pop.xml:122: the production setting of tx0.1v3); the timed "
+                         "default is full cells, the primary variant of SURVEY 8d config 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle-vs-library parity check of the CPU sample")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: device-resident timed region only")
     args = ap.parse_args()
     _PRECOND_CHOICE[0] = args.precond
+    _PBC[0] = args.pbc
     if args.impl == "reference":
         run_reference(args)
     else:

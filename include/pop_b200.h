@@ -131,6 +131,10 @@ int pop_local_shape(int* nx_block, int* ny_block, int* j_start_global, int* ny_l
    field location the reference uses (grid.F90:1420-1520), and derives every other grid array
    (grid.F90:587-647,786-803,978-1041,2537-2596,2882-2932; hmix_del2/del4 init; advection init;
    POP_SolversInit). */
+/* partial bottom cells (grid_nml partial_bottom_cells, grid.F90:917-960): DZBC = thickness (cm) of the bottom cell of
+   every column, this rank's physical strip -- what the reference reads from bottom_cell_file (read_bottom_cell,
+   grid.F90:2116).  Call BEFORE pop_set_grid, which derives DZT, DZU, HT, HU and HUR from it. */
+int pop_set_bottom_cells(const double* DZBC);
 int pop_set_grid(const double* ULAT, const double* HTN, const double* HTE, const double* HUS,
                  const double* HUW, const double* DXU, const double* DYU, const double* DXT,
                  const double* DYT, const int* KMT, const double* dz /* km, cm */);

@@ -90,6 +90,16 @@ static void init_del2t_or_del4t(void);
 static void init_advection(void);
 static void alloc_state(void);
 
+/* read_bottom_cell (grid.F90:2116-2172): DZBC scattered as a centre scalar */
+static double* g_dzbc_global = NULL;
+int oracle_set_bottom_cells(const double* DZBC_G) {
+  size_t n = (size_t)M.cfg.nx_global * M.cfg.ny_global;
+  free(g_dzbc_global);
+  g_dzbc_global = (double*)malloc(sizeof(double) * n);
+  memcpy(g_dzbc_global, DZBC_G, sizeof(double) * n);
+  return 0;
+}
+
 int oracle_set_grid(const double* ULAT_G, const double* HTN_G, const double* HTE_G,
                     const double* HUS_G, const double* HUW_G, const double* DXU_G,
                     const double* DYU_G, const double* DXT_G, const double* DYT_G,
@@ -195,16 +205,54 @@ int oracle_set_grid(const double* ULAT_G, const double* HTN_G, const double* HTE
       }
   }
   oracle_halo_2d_i4(M.KMU, POP_LOC_NECORNER, POP_KIND_SCALAR, 0);
-  /* HT, HU, HUR: grid.F90:1024-1041 (full cells) ; landmasks :2537-2596 */
+  if (PBC) { /* grid.F90:917-966: DZT = dz except the bottom cell, DZU = min of the four surrounding DZT */
+    if (!g_dzbc_global) return -1;
+    M.DZBC = D2ALLOC();
+    oracle_scatter_2d(M.DZBC, g_dzbc_global, POP_LOC_CENTER, POP_KIND_SCALAR);
+    size_t n3p = M.n2 * (size_t)(M.km + 2);
+    M.DZT = (double*)calloc(n3p * M.nblocks, sizeof(double));
+    M.DZU = (double*)calloc(n3p * M.nblocks, sizeof(double));
+    for (int b = 0; b < M.nblocks; b++) {
+      const int* KMT = M.KMT + (size_t)b * M.n2;
+      for (int k = 1; k <= M.km; k++) {
+        double *T = DZT3(b, k), *U = DZU3(b, k);
+        for (size_t q = 0; q < M.n2; q++) T[q] = (KMT[q] == k) ? B2(M.DZBC, b)[q] : M.dz[k];
+        for (int j = 1; j <= nyb - 1; j++)
+          for (int i = 1; i <= nxb - 1; i++) {
+            double m = T[IX2(i, j)];
+            if (T[IX2(i + 1, j)] < m) m = T[IX2(i + 1, j)];
+            if (T[IX2(i, j + 1)] < m) m = T[IX2(i, j + 1)];
+            if (T[IX2(i + 1, j + 1)] < m) m = T[IX2(i + 1, j + 1)];
+            U[IX2(i, j)] = m;
+          }
+      }
+    }
+    /* POP_HaloUpdate(DZU, NEcorner, scalar) over the levels 0:km+1; the halo works on [nblocks][nz] slabs */
+    oracle_halo_3d(M.DZU, M.km + 2, POP_LOC_NECORNER, POP_KIND_SCALAR, 0.0);
+  }
+  /* HT, HU, HUR: grid.F90:1001-1041 ; landmasks :2537-2596 */
   for (int b = 0; b < M.nblocks; b++) {
     const int *KMT = M.KMT + (size_t)b * M.n2, *KMU = M.KMU + (size_t)b * M.n2;
     for (int j = 1; j <= nyb; j++)
       for (int i = 1; i <= nxb; i++) {
         size_t q = IX2(i, j);
         int kt = KMT[q], ku = KMU[q];
-        B2(M.HT, b)[q] = (kt >= 1 && kt <= M.km) ? M.zw[kt] : 0.0;
-        B2(M.HU, b)[q] = (ku >= 1 && ku <= M.km) ? M.zw[ku] : 0.0;
-        B2(M.HUR, b)[q] = (ku >= 1 && ku <= M.km) ? 1.0 / M.zw[ku] : 0.0;
+        if (PBC) { /* :1001-1022 */
+          B2(M.HT, b)[q] = (kt >= 1 && kt <= M.km) ? M.zw[kt - 1] + DZT3(b, kt)[q] : 0.0;
+          if (ku >= 1 && ku <= M.km) {
+            B2(M.HU, b)[q] = M.zw[ku - 1] + DZU3(b, ku)[q];
+            B2(M.HUR, b)[q] = 1.0 / B2(M.HU, b)[q];
+          } else {
+            B2(M.HU, b)[q] = 0.0;
+            B2(M.HUR, b)[q] = 0.0;
+          }
+          for (int k = 1; k <= M.km; k++)
+            if (k > ku) DZU3(b, k)[q] = M.dz[k]; /* to prevent divide by zero */
+        } else {
+          B2(M.HT, b)[q] = (kt >= 1 && kt <= M.km) ? M.zw[kt] : 0.0;
+          B2(M.HU, b)[q] = (ku >= 1 && ku <= M.km) ? M.zw[ku] : 0.0;
+          B2(M.HUR, b)[q] = (ku >= 1 && ku <= M.km) ? 1.0 / M.zw[ku] : 0.0;
+        }
         B2(M.RCALCT, b)[q] = (kt >= 1) ? 1.0 : 0.0;
         B2(M.RCALCU, b)[q] = (ku >= 1) ? 1.0 : 0.0;
         (M.KMTN + (size_t)b * M.n2)[q] = eoi(KMT, i, j + 1);
@@ -557,6 +605,7 @@ void* oracle_field(const char* name, int tlev) {
   F("DXUR", M.DXUR); F("DYUR", M.DYUR); F("DXTR", M.DXTR); F("DYTR", M.DYTR);
   F("UAREA", M.UAREA); F("TAREA", M.TAREA); F("UAREA_R", M.UAREA_R); F("TAREA_R", M.TAREA_R);
   F("HU", M.HU); F("HUR", M.HUR); F("HT", M.HT); F("FCOR", M.FCOR);
+  F("DZT", M.DZT); F("DZU", M.DZU); F("DZBC", M.DZBC);
   F("RCALCT", M.RCALCT); F("RCALCU", M.RCALCU);
   F("AU0", M.AU0); F("AUN", M.AUN); F("AUE", M.AUE); F("AUNE", M.AUNE);
   F("KXU", M.KXU); F("KYU", M.KYU);

@@ -217,6 +217,20 @@ void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* 
     return;
   }
   const double *U = K3(UUU, k), *V = K3(VVV, k), *DYU = B2(M.DYU, b), *DXU = B2(M.DXU, b);
+  if (PBC) { /* :2040-2066: the flux velocities carry the thickness of the U cells */
+    const double* DZU = DZU3(b, k);
+#define UD_(i, j) (U[IX2(i, j)] * DYU[IX2(i, j)] * DZU[IX2(i, j)])
+#define VD_(i, j) (V[IX2(i, j)] * DXU[IX2(i, j)] * DZU[IX2(i, j)])
+    for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+      for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
+        UTE[IX2(i, j)] = 0.5 * (UD_(i, j) + UD_(i, j - 1));
+        UTW[IX2(i, j)] = 0.5 * (UD_(i - 1, j) + UD_(i - 1, j - 1));
+        VTN[IX2(i, j)] = 0.5 * (VD_(i, j) + VD_(i - 1, j));
+        VTS[IX2(i, j)] = 0.5 * (VD_(i, j - 1) + VD_(i - 1, j - 1));
+      }
+#undef UD_
+#undef VD_
+  } else
   for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
     for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
       UTE[IX2(i, j)] = 0.5 * (U[IX2(i, j)] * DYU[IX2(i, j)] + U[IX2(i, j - 1)] * DYU[IX2(i, j - 1)]);
@@ -229,7 +243,8 @@ void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* 
     const double* TR = B2(M.TAREA_R, b);
     for (size_t q = 0; q < M.n2; q++) {
       double FC = (VTN[q] - VTS[q] + UTE[q] - UTW[q]) * TR[q];
-      WTKB[q] = (k < KMT[q]) ? WTK[q] + M.dz[k] * FC : 0.0;
+      if (PBC) WTKB[q] = (k < KMT[q]) ? WTK[q] + FC : 0.0; /* :2110-2111 */
+      else WTKB[q] = (k < KMT[q]) ? WTK[q] + M.dz[k] * FC : 0.0;
     }
   } else {
     memset(WTKB, 0, sizeof(double) * M.n2);
@@ -250,16 +265,20 @@ static void advt_centered(int k, double* LTK, const double* TRCR, const double* 
                     VTN[IX2(i, j)] * T[IX2(i, j + 1)] - VTN[IX2(i, j - 1)] * T[IX2(i, j - 1)] +
                     UTE[IX2(i, j)] * T[IX2(i + 1, j)] - UTE[IX2(i - 1, j)] * T[IX2(i - 1, j)]) *
                    TR[IX2(i, j)];
+    const double* DZT = PBC ? DZT3(b, k) : NULL;
+    if (PBC) PHYS2(b) L[IX2(i, j)] = L[IX2(i, j)] / DZT[IX2(i, j)]; /* :2223-2238 */
     if (k == 1) {
       if (M.cfg.sfc_layer_type != POP_SFC_VARTHICK)
         for (size_t q = 0; q < M.n2; q++) L[q] = L[q] + M.dzr[k] * WTK[q] * T[q];
     } else {
       const double* Tm = KN4(TRCR, k - 1, n);
-      for (size_t q = 0; q < M.n2; q++) L[q] = L[q] + M.dz2r[k] * WTK[q] * (Tm[q] + T[q]);
+      if (PBC) for (size_t q = 0; q < M.n2; q++) L[q] = L[q] + 0.5 / DZT[q] * WTK[q] * (Tm[q] + T[q]); /* :2278-2280 */
+      else for (size_t q = 0; q < M.n2; q++) L[q] = L[q] + M.dz2r[k] * WTK[q] * (Tm[q] + T[q]);
     }
     if (k < M.km) {
       const double* Tp = KN4(TRCR, k + 1, n);
-      for (size_t q = 0; q < M.n2; q++) L[q] = L[q] - M.dz2r[k] * WTKB[q] * (T[q] + Tp[q]);
+      if (PBC) for (size_t q = 0; q < M.n2; q++) L[q] = L[q] - 0.5 / DZT[q] * WTKB[q] * (T[q] + Tp[q]);
+      else for (size_t q = 0; q < M.n2; q++) L[q] = L[q] - M.dz2r[k] * WTKB[q] * (T[q] + Tp[q]);
     }
   }
 }
@@ -410,6 +429,24 @@ void o_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, con
                *UR = B2(M.UAREA_R, b), *KXU = B2(M.KXU, b), *KYU = B2(M.KYU, b);
   const int* KMU = M.KMU + (size_t)b * M.n2;
   double *UUE = tmp2(), *UUW = tmp2(), *VUN = tmp2(), *VUS = tmp2(), *WUKB = tmp2();
+  const double* DZU = PBC ? DZU3(b, k) : NULL;
+  if (PBC) { /* :1245-1303 */
+#define UD_(i, j) (U[IX2(i, j)] * DYU[IX2(i, j)] * DZU[IX2(i, j)])
+#define VD_(i, j) (V[IX2(i, j)] * DXU[IX2(i, j)] * DZU[IX2(i, j)])
+    for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+      for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
+        UUW[IX2(i, j)] = 0.25 * (UD_(i, j) + UD_(i - 1, j)) +
+                         0.125 * (UD_(i, j - 1) + UD_(i - 1, j - 1) + UD_(i, j + 1) + UD_(i - 1, j + 1));
+        UUE[IX2(i, j)] = 0.25 * (UD_(i + 1, j) + UD_(i, j)) +
+                         0.125 * (UD_(i + 1, j - 1) + UD_(i, j - 1) + UD_(i + 1, j + 1) + UD_(i, j + 1));
+        VUS[IX2(i, j)] = 0.25 * (VD_(i, j) + VD_(i, j - 1)) +
+                         0.125 * (VD_(i - 1, j) + VD_(i - 1, j - 1) + VD_(i + 1, j) + VD_(i + 1, j - 1));
+        VUN[IX2(i, j)] = 0.25 * (VD_(i, j + 1) + VD_(i, j)) +
+                         0.125 * (VD_(i - 1, j + 1) + VD_(i - 1, j) + VD_(i + 1, j + 1) + VD_(i + 1, j));
+      }
+#undef UD_
+#undef VD_
+  } else
   for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
     for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
       UUW[IX2(i, j)] = 0.25 * (U[IX2(i, j)] * DYU[IX2(i, j)] + U[IX2(i - 1, j)] * DYU[IX2(i - 1, j)]) +
@@ -425,8 +462,10 @@ void o_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, con
                        0.125 * (V[IX2(i - 1, j + 1)] * DXU[IX2(i - 1, j + 1)] + V[IX2(i - 1, j)] * DXU[IX2(i - 1, j)] +
                                 V[IX2(i + 1, j + 1)] * DXU[IX2(i + 1, j + 1)] + V[IX2(i + 1, j)] * DXU[IX2(i + 1, j)]);
     }
-  for (size_t q = 0; q < M.n2; q++)
-    WUKB[q] = WUK[q] + M.c2dz[k] * 0.5 * (VUN[q] - VUS[q] + UUE[q] - UUW[q]) * UR[q];
+  for (size_t q = 0; q < M.n2; q++) {
+    if (PBC) WUKB[q] = WUK[q] + (VUN[q] - VUS[q] + UUE[q] - UUW[q]) * UR[q]; /* :1352-1353 */
+    else WUKB[q] = WUK[q] + M.c2dz[k] * 0.5 * (VUN[q] - VUS[q] + UUE[q] - UUW[q]) * UR[q];
+  }
   memset(LUK, 0, sizeof(double) * M.n2);
   memset(LVK, 0, sizeof(double) * M.n2);
   PHYS2(b) {
@@ -437,6 +476,10 @@ void o_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, con
     LVK[IX2(i, j)] = 0.5 * (cc * V[IX2(i, j)] + VUS[IX2(i, j + 1)] * V[IX2(i, j + 1)] -
                             VUS[IX2(i, j)] * V[IX2(i, j - 1)] + UUW[IX2(i + 1, j)] * V[IX2(i + 1, j)] -
                             UUW[IX2(i, j)] * V[IX2(i - 1, j)]) * UR[IX2(i, j)];
+    if (PBC) { /* :1381-1405: ... * UAREA_R / DZU */
+      LUK[IX2(i, j)] = LUK[IX2(i, j)] / DZU[IX2(i, j)];
+      LVK[IX2(i, j)] = LVK[IX2(i, j)] / DZU[IX2(i, j)];
+    }
   }
   if (k == 1) {
     for (size_t q = 0; q < M.n2; q++) {
@@ -446,15 +489,25 @@ void o_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, con
   } else {
     const double *Um = K3(UUU, k - 1), *Vm = K3(VVV, k - 1);
     for (size_t q = 0; q < M.n2; q++) {
-      LUK[q] = LUK[q] + M.dz2r[k] * WUK[q] * (Um[q] + U[q]);
-      LVK[q] = LVK[q] + M.dz2r[k] * WUK[q] * (Vm[q] + V[q]);
+      if (PBC) { /* :1443-1447 */
+        LUK[q] = LUK[q] + 0.5 / DZU[q] * WUK[q] * (Um[q] + U[q]);
+        LVK[q] = LVK[q] + 0.5 / DZU[q] * WUK[q] * (Vm[q] + V[q]);
+      } else {
+        LUK[q] = LUK[q] + M.dz2r[k] * WUK[q] * (Um[q] + U[q]);
+        LVK[q] = LVK[q] + M.dz2r[k] * WUK[q] * (Vm[q] + V[q]);
+      }
     }
   }
   if (k < M.km) {
     const double *Up = K3(UUU, k + 1), *Vp = K3(VVV, k + 1);
     for (size_t q = 0; q < M.n2; q++) {
-      LUK[q] = LUK[q] - M.dz2r[k] * WUKB[q] * (U[q] + Up[q]);
-      LVK[q] = LVK[q] - M.dz2r[k] * WUKB[q] * (V[q] + Vp[q]);
+      if (PBC) { /* :1462-1466 */
+        LUK[q] = LUK[q] - 0.5 / DZU[q] * WUKB[q] * (U[q] + Up[q]);
+        LVK[q] = LVK[q] - 0.5 / DZU[q] * WUKB[q] * (V[q] + Vp[q]);
+      } else {
+        LUK[q] = LUK[q] - M.dz2r[k] * WUKB[q] * (U[q] + Up[q]);
+        LVK[q] = LVK[q] - M.dz2r[k] * WUKB[q] * (V[q] + Vp[q]);
+      }
     }
   }
   PHYS2(b) {
@@ -478,6 +531,29 @@ static void tracer_coeffs(int k, int b, double* CC, double* CN, double* CS, doub
   const int *KMT = M.KMT + (size_t)b * M.n2, *KMTN = M.KMTN + (size_t)b * M.n2,
             *KMTS = M.KMTS + (size_t)b * M.n2, *KMTE = M.KMTE + (size_t)b * M.n2,
             *KMTW = M.KMTW + (size_t)b * M.n2;
+  if (PBC) { /* hmix_del2.F90:1034-1062 / hmix_del4.F90:964-988: the face is as thick as the thinner of its two cells */
+    const double* DZT = DZT3(b, k);
+    memset(CN, 0, sizeof(double) * M.n2); memset(CS, 0, sizeof(double) * M.n2);
+    memset(CE, 0, sizeof(double) * M.n2); memset(CW, 0, sizeof(double) * M.n2);
+#define MIN_(a, c) ((a) < (c) ? (a) : (c))
+    for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+      for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
+        size_t q = IX2(i, j);
+        CN[q] = B2(M.DTN, b)[q] * MIN_(DZT[q], DZT[IX2(i, j + 1)]) / DZT[q];
+        CS[q] = B2(M.DTS, b)[q] * MIN_(DZT[q], DZT[IX2(i, j - 1)]) / DZT[q];
+        CE[q] = B2(M.DTE, b)[q] * MIN_(DZT[q], DZT[IX2(i + 1, j)]) / DZT[q];
+        CW[q] = B2(M.DTW, b)[q] * MIN_(DZT[q], DZT[IX2(i - 1, j)]) / DZT[q];
+      }
+#undef MIN_
+    for (size_t q = 0; q < M.n2; q++) {
+      if (!(k <= KMTN[q] && k <= KMT[q])) CN[q] = 0.0;
+      if (!(k <= KMTS[q] && k <= KMT[q])) CS[q] = 0.0;
+      if (!(k <= KMTE[q] && k <= KMT[q])) CE[q] = 0.0;
+      if (!(k <= KMTW[q] && k <= KMT[q])) CW[q] = 0.0;
+      CC[q] = -(CN[q] + CS[q] + CE[q] + CW[q]);
+    }
+    return;
+  }
   for (size_t q = 0; q < M.n2; q++) {
     CN[q] = (k <= KMTN[q] && k <= KMT[q]) ? B2(M.DTN, b)[q] : 0.0;
     CS[q] = (k <= KMTS[q] && k <= KMT[q]) ? B2(M.DTS, b)[q] : 0.0;
@@ -565,6 +641,22 @@ void o_hdiffu(int k, double* HDUK, double* HDVK, const double* UMIXK, const doub
   for (size_t q = 0; q < M.n2; q++) CC[q] = DUC[q] + DUM[q];
   memset(HDUK, 0, sizeof(double) * M.n2);
   memset(HDVK, 0, sizeof(double) * M.n2);
+  double *PN = NULL, *PS = NULL, *PE = NULL, *PW = NULL;
+  if (PBC) { /* hmix_del2.F90:852-863, hmix_del4.F90:683-694: neighbour weights scaled by min(DZU)/DZU */
+    const double* DZU = DZU3(b, k);
+    PN = tmp2(); PS = tmp2(); PE = tmp2(); PW = tmp2();
+#define MIN_(a, c) ((a) < (c) ? (a) : (c))
+    for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+      for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
+        size_t q = IX2(i, j);
+        PN[q] = DUN[q] * MIN_(DZU[IX2(i, j + 1)], DZU[q]) / DZU[q];
+        PS[q] = DUS[q] * MIN_(DZU[IX2(i, j - 1)], DZU[q]) / DZU[q];
+        PE[q] = DUE[q] * MIN_(DZU[IX2(i + 1, j)], DZU[q]) / DZU[q];
+        PW[q] = DUW[q] * MIN_(DZU[IX2(i - 1, j)], DZU[q]) / DZU[q];
+      }
+#undef MIN_
+    DUN = PN; DUS = PS; DUE = PE; DUW = PW;
+  }
   if (M.cfg.hmix_momentum_itype == POP_HMIX_DEL2) {
     PHYS2(b) {
       HDUK[IX2(i, j)] = M.am * mom_stencil(CC, DUN, DUS, DUE, DUW, DMC, DMN, DMS, DME, DMW, UMIXK, VMIXK, i, j, +1);
@@ -592,6 +684,7 @@ void o_hdiffu(int k, double* HDUK, double* HDVK, const double* UMIXK, const doub
   for (size_t q = 0; q < M.n2; q++)
     if (k > KMU[q]) { HDUK[q] = 0.0; HDVK[q] = 0.0; }
   free(CC);
+  if (PBC) { free(PN); free(PS); free(PE); free(PW); }
   M.timer[OT_HDIFFU] += o_now() - t0;
 }
 
@@ -618,6 +711,14 @@ void o_vdifft(int k, double* VDTK, const double* TOLD, const double* STF, int b)
     double* VD = VDTK + (size_t)(n - 1) * M.n2;
     if (k == 1)
       for (size_t q = 0; q < M.n2; q++) VTF[q] = (KMT[q] >= 1) ? S[q] : 0.0;
+    if (PBC) { /* :790-803 */
+      const double *DZT = DZT3(b, k), *DZTp = DZT3(b, kp1);
+      for (size_t q = 0; q < M.n2; q++) {
+        double VTFB = (KMT[q] > k) ? VDC[q] * (T[q] - Tp[q]) / (0.5 * (DZT[q] + DZTp[q])) : 0.0;
+        VD[q] = (k <= KMT[q]) ? (VTF[q] - VTFB) / DZT[q] : 0.0;
+        VTF[q] = VTFB;
+      }
+    } else
     for (size_t q = 0; q < M.n2; q++) {
       double VTFB = (KMT[q] > k) ? VDC[q] * (T[q] - Tp[q]) * M.dzwr[k] : 0.0;
       VD[q] = (k <= KMT[q]) ? (VTF[q] - VTFB) * M.dzr[k] : 0.0;
@@ -639,6 +740,14 @@ void o_vdiffu(int k, double* VDUK, double* VDVK, const double* UOLD, const doubl
       VUF[q] = (KMU[q] >= 1) ? SMF[q] : 0.0;
       VVF[q] = (KMU[q] >= 1) ? SMF[M.n2 + q] : 0.0;
     }
+  if (PBC) { /* :946-958: kp1 = min(k+1, km), so at k = km WORK = p5*DZU(km) */
+    const double *DZU = DZU3(b, k), *DZUp = DZU3(b, kp1);
+    for (size_t q = 0; q < M.n2; q++) {
+      double W = (k < M.km) ? 0.5 * (DZU[q] + DZUp[q]) : 0.5 * DZUp[q];
+      VUFB[q] = VVC[q] * (U[q] - Up[q]) / W;
+      VVFB[q] = VVC[q] * (V[q] - Vp[q]) / W;
+    }
+  } else
   for (size_t q = 0; q < M.n2; q++) {
     VUFB[q] = VVC[q] * (U[q] - Up[q]) * M.dzwr[k];
     VVFB[q] = VVC[q] * (V[q] - Vp[q]) * M.dzwr[k];
@@ -652,8 +761,14 @@ void o_vdiffu(int k, double* VDUK, double* VDVK, const double* UOLD, const doubl
     }
   }
   for (size_t q = 0; q < M.n2; q++) {
-    VDUK[q] = (k <= KMU[q]) ? (VUF[q] - VUFB[q]) * M.dzr[k] : 0.0;
-    VDVK[q] = (k <= KMU[q]) ? (VVF[q] - VVFB[q]) * M.dzr[k] : 0.0;
+    if (PBC) { /* :991-995 */
+      const double* DZU = DZU3(b, k);
+      VDUK[q] = (k <= KMU[q]) ? (VUF[q] - VUFB[q]) / DZU[q] : 0.0;
+      VDVK[q] = (k <= KMU[q]) ? (VVF[q] - VVFB[q]) / DZU[q] : 0.0;
+    } else {
+      VDUK[q] = (k <= KMU[q]) ? (VUF[q] - VUFB[q]) * M.dzr[k] : 0.0;
+      VDVK[q] = (k <= KMU[q]) ? (VVF[q] - VVFB[q]) * M.dzr[k] : 0.0;
+    }
     VUF[q] = VUFB[q];
     VVF[q] = VVFB[q];
   }
@@ -694,16 +809,22 @@ static void impvmixt_common(double* TNEW, const double* TOLD, const double* PSFC
       PHYS2(b) {
         size_t q = IX2(i, j);
         C[q] = A[q];
-        A[q] = M.afac_t[k] * VDC[q];
+        double hf = hfac_t[k];
+        if (PBC) { /* :1280-1286 / :1577-1582: DZT(k+1) is read at k = km too (DZT is dimensioned 0:km+1) */
+          A[q] = M.cfg.aidif * VDC[q] / (0.5 * (DZT3(b, k)[q] + DZT3(b, k + 1)[q]));
+          hf = DZT3(b, k)[q] / M.c2dtt[k];
+        } else {
+          A[q] = M.afac_t[k] * VDC[q];
+        }
         if (k > KMT[q]) {
           K3(F, k)[q] = 0.0;
         } else {
-          if (k == KMT[q]) D[q] = hfac_t[k] + B[q];
-          else D[q] = hfac_t[k] + A[q] + B[q];
+          if (k == KMT[q]) D[q] = hf + B[q];
+          else D[q] = hf + A[q] + B[q];
           K3(E, k)[q] = A[q] / D[q];
-          B[q] = (hfac_t[k] + B[q]) * K3(E, k)[q];
+          B[q] = (hf + B[q]) * K3(E, k)[q];
           if (correct) K3(F, k)[q] = C[q] * K3(F, k - 1)[q] / D[q];
-          else K3(F, k)[q] = (hfac_t[k] * Rk[q] + C[q] * K3(F, k - 1)[q]) / D[q];
+          else K3(F, k)[q] = (hf * Rk[q] + C[q] * K3(F, k - 1)[q]) / D[q];
         }
       }
     }
@@ -757,17 +878,23 @@ void o_impvmixu(double* UNEW, double* VNEW, int b) {
     PHYS2(b) {
       size_t q = IX2(i, j);
       C[q] = A[q];
-      A[q] = M.afac_u[k] * VVC[q];
+      double hf = hfac_u[k];
+      if (PBC) { /* :1777-1784 */
+        hf = DZU3(b, k)[q] / M.c2dtu;
+        A[q] = M.cfg.aidif * VVC[q] / (0.5 * (DZU3(b, k)[q] + DZU3(b, k + 1)[q]));
+      } else {
+        A[q] = M.afac_u[k] * VVC[q];
+      }
       if (k < KMU[q]) {
-        D[q] = hfac_u[k] + A[q] + B[q];
+        D[q] = hf + A[q] + B[q];
       } else if (k == KMU[q]) {
-        D[q] = hfac_u[k] + B[q];
+        D[q] = hf + B[q];
       }
       if (k <= KMU[q]) {
         K3(E, k)[q] = A[q] / D[q];
-        B[q] = (hfac_u[k] + B[q]) * K3(E, k)[q];
-        K3(F1, k)[q] = (hfac_u[k] * K3(UNEW, k)[q] + C[q] * K3(F1, k - 1)[q]) / D[q];
-        K3(F2, k)[q] = (hfac_u[k] * K3(VNEW, k)[q] + C[q] * K3(F2, k - 1)[q]) / D[q];
+        B[q] = (hf + B[q]) * K3(E, k)[q];
+        K3(F1, k)[q] = (hf * K3(UNEW, k)[q] + C[q] * K3(F1, k - 1)[q]) / D[q];
+        K3(F2, k)[q] = (hf * K3(VNEW, k)[q] + C[q] * K3(F2, k - 1)[q]) / D[q];
       } else {
         K3(F1, k)[q] = 0.0;
         K3(F2, k)[q] = 0.0;

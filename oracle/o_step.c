@@ -221,6 +221,13 @@ int o_baroclinic_driver(void) {
       } else {
         for (size_t q = 0; q < M.n2; q++) { Uk[q] = M.c2dtu * FX[q]; Vk[q] = M.c2dtu * FY[q]; }
       }
+      if (PBC) { /* baroclinic.F90:1037-1039 */
+        const double* DZU = DZU3(b, k);
+        for (size_t q = 0; q < M.n2; q++) {
+          ZX[q] = ZX[q] + FX[q] * DZU[q];
+          ZY[q] = ZY[q] + FY[q] * DZU[q];
+        }
+      } else
       for (size_t q = 0; q < M.n2; q++) {
         ZX[q] = ZX[q] + FX[q] * M.dz[k];
         ZY[q] = ZY[q] + FY[q] * M.dz[k];
@@ -236,8 +243,9 @@ int o_baroclinic_driver(void) {
     memset(WORK2, 0, sizeof(double) * M.n2);
     for (int k = 1; k <= km; k++)
       for (size_t q = 0; q < M.n2; q++) {
-        WORK1[q] = WORK1[q] + K3(Un, k)[q] * M.dz[k];
-        WORK2[q] = WORK2[q] + K3(Vn, k)[q] * M.dz[k];
+        const double dzk = PBC ? DZU3(b, k)[q] : M.dz[k]; /* baroclinic.F90:1097-1107 */
+        WORK1[q] = WORK1[q] + K3(Un, k)[q] * dzk;
+        WORK2[q] = WORK2[q] + K3(Vn, k)[q] * dzk;
       }
     for (size_t q = 0; q < M.n2; q++) { WORK1[q] = WORK1[q] * HUR[q]; WORK2[q] = WORK2[q] * HUR[q]; }
     for (int k = 1; k <= km; k++)
@@ -343,7 +351,12 @@ void o_baroclinic_correct_adjust(void) {
               double *tk = KN4(Tn, k, n), *tk1 = KN4(Tn, k + 1, n);
               for (size_t q = 0; q < M.n2; q++)
                 if (RHOK[q] > RHOKP[q] && k < KMT[q]) {
-                  tk[q] = dzwx * (dztk * tk[q] + dztk1 * tk1[q]);
+                  if (PBC) { /* vertical_mix.F90:1960-1968 (dttxcel = 1) */
+                    const double a = DZT3(b, k)[q] / 1.0, c_ = DZT3(b, k + 1)[q] / 1.0;
+                    tk[q] = 1.0 / (a + c_) * (a * tk[q] + c_ * tk1[q]);
+                  } else {
+                    tk[q] = dzwx * (dztk * tk[q] + dztk1 * tk1[q]);
+                  }
                   tk1[q] = tk[q];
                 }
             }

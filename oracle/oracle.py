@@ -187,6 +187,11 @@ class Oracle:
         return self.L.oracle_global_sum(_p(arr), loc, _p(mask))
 
     # ---- model setup
+    def set_bottom_cells(self, dzbc):
+        """partial bottom cells: global (ny, nx) thickness of the bottom cell of every column; before set_grid"""
+        a = np.ascontiguousarray(dzbc, dtype=np.float64)
+        assert self.L.oracle_set_bottom_cells(_p(a)) == 0
+
     def set_grid(self, grid, kmt, dz):
         args = [np.ascontiguousarray(grid[k], dtype=np.float64) for k in
                 ("ULAT", "HTN", "HTE", "HUS", "HUW", "DXU", "DYU", "DXT", "DYT")]

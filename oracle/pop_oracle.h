@@ -45,6 +45,9 @@ typedef struct {
   double *AU0, *AUN, *AUE, *AUNE, *AT0, *ATS, *ATW, *ATSW;
   double *KXU, *KYU;
   int *KMT, *KMU, *KMTN, *KMTS, *KMTE, *KMTW, *KMTEE, *KMTNN;
+  /* partial bottom cells (grid.F90:917-960): DZBC input (thickness of the bottom cell of each column), DZT / DZU
+     [nblocks][0:km+1][nyb][nxb] */
+  double *DZBC, *DZT, *DZU;
   double uarea_equator;
   /* hmix coefficients (hmix_del2.F90 / hmix_del4.F90 init) */
   double *DTN, *DTS, *DTE, *DTW, *AHF;
@@ -98,6 +101,10 @@ enum { OT_STEP = 0, OT_BAROCLINIC, OT_BAROTROPIC, OT_HALO, OT_ADVT, OT_HDIFFT, O
 
 extern omodel M;
 
+/* partial-bottom-cell thickness of level k (0..km+1) of block b */
+#define PBC (M.cfg.partial_bottom_cells)
+#define DZT3(b, k) (M.DZT + ((size_t)(b) * (M.km + 2) + (k)) * M.n2)
+#define DZU3(b, k) (M.DZU + ((size_t)(b) * (M.km + 2) + (k)) * M.n2)
 /* index macros: 1-based like the reference */
 #define IX2(i, j) ((size_t)((j)-1) * M.nxb + ((i)-1))
 #define B2(a, b) ((a) + (size_t)(b)*M.n2)                               /* block b (0-based) of 2-d field */
@@ -131,6 +138,7 @@ void* o_gm_field(const char* name);
 int o_gm_cancellation(void);
 
 /* ---- grid + init (o_grid.c) ---- */
+int oracle_set_bottom_cells(const double* DZBC_G); /* before oracle_set_grid when partial_bottom_cells */
 int oracle_set_grid(const double* ULAT, const double* HTN, const double* HTE, const double* HUS,
                     const double* HUW, const double* DXU, const double* DYU, const double* DXT,
                     const double* DYT, const int* KMT, const double* dz);

@@ -21,7 +21,7 @@ _LIB = None
 # every symbol include/pop_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
     "pop_last_error", "pop_config_defaults", "pop_init", "pop_finalize", "pop_is_initialized",
-    "pop_comm_unique_id", "pop_comm_init", "pop_get_block", "pop_local_shape", "pop_set_grid",
+    "pop_comm_unique_id", "pop_comm_init", "pop_get_block", "pop_local_shape", "pop_set_bottom_cells", "pop_set_grid",
     "pop_device_ptr", "pop_field_size", "pop_set_field", "pop_get_field", "pop_scatter_field",
     "pop_gather_field", "pop_scatter_field_levels", "pop_set_timestep", "pop_advt", "pop_advu", "pop_hdifft", "pop_hdiffu",
     "pop_gradp", "pop_grad", "pop_div", "pop_vdifft", "pop_vdiffu", "pop_impvmixt",
@@ -176,6 +176,12 @@ class Pop:
         kmt_s = np.ascontiguousarray(kmt[r], dtype=np.int32)
         dz = np.ascontiguousarray(dz, dtype=np.float64)
         self._ck(self.L.pop_set_grid(*[_p(a) for a in arrs], _p(kmt_s), _p(dz)))
+
+    def set_bottom_cells(self, dzbc):
+        """partial bottom cells: GLOBAL (ny, nx) thickness of the bottom cell; this rank's rows are passed on"""
+        a = np.ascontiguousarray(np.asarray(dzbc, dtype=np.float64)[self.rows(), :])
+        self.L.pop_set_bottom_cells.argtypes = [C.c_void_p]
+        self._ck(self.L.pop_set_bottom_cells(_p(a)))
 
     def field_levels(self, name):
         return self.L.pop_field_size(name.encode()) // (self.nxb * self.nyb)

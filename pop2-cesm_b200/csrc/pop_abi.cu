@@ -99,6 +99,13 @@ int check_ready(const char* what, const pop_block* blk, bool need_blk) {
 extern "C" int pop_comm_unique_id(char id128[128]) { return comm_unique_id(id128); }
 extern "C" int pop_comm_init(int rank, int nranks, const char id128[128]) { return comm_init(rank, nranks, id128); }
 
+extern "C" int pop_set_bottom_cells(const double* DZBC) {
+  POP_REQUIRE(G.initialized, "pop_set_bottom_cells: pop_init has not been called");
+  POP_REQUIRE(G.cfg.partial_bottom_cells, "pop_set_bottom_cells: partial_bottom_cells is off in pop_config");
+  POP_REQUIRE(DZBC != nullptr, "pop_set_bottom_cells: null argument");
+  G.dzbc_strip.assign(DZBC, DZBC + (size_t)G.nxg * G.ny_local);
+  return POP_SUCCESS;
+}
 extern "C" int pop_set_grid(const double* ULAT, const double* HTN, const double* HTE, const double* HUS,
                             const double* HUW, const double* DXU, const double* DYU, const double* DXT,
                             const double* DYT, const int* KMT, const double* dz) {

@@ -233,7 +233,16 @@ extern "C" int pop_init(const pop_config* cfg) {
   POP_REQUIRE(G.nt >= 2 && G.nt <= POP_MAX_NT, "pop_init: nt=%d out of range", G.nt);
   POP_REQUIRE(G.nyg % G.nranks == 0, "pop_init: ny_global=%d not divisible by nranks=%d", G.nyg,
               G.nranks);
-  POP_REQUIRE(!cfg->partial_bottom_cells, "pop_init: partial bottom cells are not implemented");
+  if (cfg->partial_bottom_cells) {
+    // partial bottom cells are built for the option set of the tx0.1v3 production configuration and its neighbours:
+    // centred advection, del2 / del4 mixing, const / given vertical mixing coefficients
+    for (int n = 0; n < cfg->nt; n++)
+      POP_REQUIRE(cfg->tadvect_itype[n] == POP_TADVECT_CENTERED,
+                  "pop_init: partial_bottom_cells needs centred advection (tracer %d uses upwind3, whose vertical "
+                  "interpolation weights become 3-d with partial cells: not built)", n + 1);
+    POP_REQUIRE(cfg->hmix_tracer_itype != POP_HMIX_GM, "pop_init: partial_bottom_cells with GM is not built");
+    POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH, "pop_init: partial_bottom_cells with vmix 'rich' is not built");
+  }
   POP_REQUIRE(G.nranks == 1 || G.nccl_comm != nullptr,
               "pop_init: nranks=%d but pop_comm_init was not called", G.nranks);
   G.ny_local = G.nyg / G.nranks;
@@ -476,6 +485,8 @@ GridView grid_view() {
   GV(TALFXM); GV(TBETXM); GV(TDELXM); GV(TALFYM); GV(TBETYM); GV(TDELYM);
   GV(VDC); GV(VVC);
 #undef GV
+  if (G.cfg.partial_bottom_cells) { g.DZT = fld("DZT"); g.DZU = fld("DZU"); }
+  g.aidif = G.cfg.aidif;
   g.vdc_nk = G.vdc_nk; g.vdc_k0 = G.vdc_k0; g.vdc_nd = G.vdc_nd; g.vvc_nk = G.vvc_nk;
   return g;
 }

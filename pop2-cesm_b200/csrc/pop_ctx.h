@@ -60,6 +60,7 @@ struct Ctx {
   int nxb = 0, nyb = 0, ib = 3, ie = 0, jb = 3, je = 0;  // 1-based like the reference
   size_t n2 = 0, n3 = 0;
   std::vector<int> i_glob, j_glob;
+  std::vector<double> dzbc_strip;  // pop_set_bottom_cells: thickness of the bottom cell, physical strip
   int *d_iglob = nullptr, *d_jglob = nullptr;  // device copies
   cudaStream_t stream = nullptr;
   // side stream: the velocity finish (impvmixu + barotropic-mean removal) of step n runs here, concurrently
@@ -245,6 +246,10 @@ struct GridView {
   const double *TALFXM, *TBETXM, *TDELXM, *TALFYM, *TBETYM, *TDELYM;
   const double *VDC, *VVC;
   int vdc_nk, vdc_k0, vdc_nd, vvc_nk;
+  // partial bottom cells (grid.F90:917-960): thickness of the T / U cells, levels 0..km+1 (level k at + k*n2); null
+  // when partial_bottom_cells is off
+  const double *DZT, *DZU;
+  double aidif;  // vertical_mix_nml aidif (afac = aidif/dzw is rebuilt per cell with partial bottom cells)
 };
 GridView grid_view();
 

@@ -173,13 +173,52 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   POP_TRY(halo_update_i4(fldi("KMU"), 1, POP_LOC_NECORNER, POP_KIND_SCALAR, 0));
   POP_CHECK_CUDA(cudaMemcpyAsync(KMU.data(), fldi("KMU"), n2 * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
-  // ---- HT, HU, HUR, masks: grid.F90:1024-1041
+  // ---- partial bottom cells: DZT, DZU (grid.F90:917-966)
+  const bool pbc = G.cfg.partial_bottom_cells != 0;
+  HV DZT, DZU;
+  if (pbc) {
+    POP_REQUIRE(G.dzbc_strip.size() == (size_t)G.nxg * G.ny_local,
+                "pop_set_grid: partial_bottom_cells needs pop_set_bottom_cells (DZBC) first");
+    HV DZBC;
+    POP_TRY(scatter_halo("DZBC", G.dzbc_strip.data(), POP_LOC_CENTER, DZBC));
+    DZT.assign(n2 * (size_t)(km + 2), 0.0);
+    DZU.assign(n2 * (size_t)(km + 2), 0.0);
+    for (int k = 1; k <= km; k++) {
+      double *T = DZT.data() + (size_t)k * n2, *U = DZU.data() + (size_t)k * n2;
+      for (size_t q = 0; q < n2; q++) T[q] = (KMT[q] == k) ? DZBC[q] : vc.dz[k];
+      for (int j = 1; j <= nyb - 1; j++)
+        for (int i = 1; i <= nxb - 1; i++) {
+          double m = T[IX(i, j)];
+          if (T[IX(i + 1, j)] < m) m = T[IX(i + 1, j)];
+          if (T[IX(i, j + 1)] < m) m = T[IX(i, j + 1)];
+          if (T[IX(i + 1, j + 1)] < m) m = T[IX(i + 1, j + 1)];
+          U[IX(i, j)] = m;
+        }
+    }
+    POP_TRY(put("DZU", DZU));
+    POP_TRY(halo_update(fld("DZU"), km + 2, POP_LOC_NECORNER, POP_KIND_SCALAR, 0.0));
+    POP_TRY(get("DZU", DZU));
+  }
+  // ---- HT, HU, HUR, masks: grid.F90:1001-1041
   HV HT(n2), HU(n2), HUR(n2), RCALCT(n2), RCALCU(n2), FCOR(n2);
   for (size_t q = 0; q < n2; q++) {
     const int kt = KMT[q], ku = KMU[q];
+    if (pbc) {
+      HT[q] = (kt >= 1 && kt <= km) ? vc.zw[kt - 1] + DZT[(size_t)kt * n2 + q] : 0.0;
+      if (ku >= 1 && ku <= km) {
+        HU[q] = vc.zw[ku - 1] + DZU[(size_t)ku * n2 + q];
+        HUR[q] = 1.0 / HU[q];
+      } else {
+        HU[q] = 0.0;
+        HUR[q] = 0.0;
+      }
+      for (int k = 1; k <= km; k++)
+        if (k > ku) DZU[(size_t)k * n2 + q] = vc.dz[k];  // "to prevent divide by zero", grid.F90:1013
+    } else {
     HT[q] = (kt >= 1 && kt <= km) ? vc.zw[kt] : 0.0;
     HU[q] = (ku >= 1 && ku <= km) ? vc.zw[ku] : 0.0;
     HUR[q] = (ku >= 1 && ku <= km) ? 1.0 / vc.zw[ku] : 0.0;
+    }
     RCALCT[q] = (kt >= 1) ? 1.0 : 0.0;
     RCALCU[q] = (ku >= 1) ? 1.0 : 0.0;
     FCOR[q] = 2.0 * POP_OMEGA * sin(ULAT[q]);  // grid.F90:1146
@@ -424,6 +463,7 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   POP_TRY(put("UAREA", UAREA)); POP_TRY(put("UAREA_R", UAREA_R)); POP_TRY(put("TAREA", TAREA));
   POP_TRY(put("TAREA_R", TAREA_R)); POP_TRY(put("AU0", AU0)); POP_TRY(put("AUN", AUN)); POP_TRY(put("AUE", AUE));
   POP_TRY(put("AUNE", AUNE)); POP_TRY(put("HT", HT)); POP_TRY(put("HU", HU)); POP_TRY(put("HUR", HUR));
+  if (pbc) { POP_TRY(put("DZT", DZT)); POP_TRY(put("DZU", DZU)); }
   POP_TRY(put("RCALCT", RCALCT)); POP_TRY(put("RCALCU", RCALCU)); POP_TRY(put("FCOR", FCOR));
   POP_TRY(put("KXU", KXU)); POP_TRY(put("KYU", KYU));
   POP_TRY(put("btropWgtNE", WNE)); POP_TRY(put("btropWgtEast", WE)); POP_TRY(put("btropWgtNorth", WN));

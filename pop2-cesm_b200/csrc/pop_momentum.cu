@@ -33,14 +33,28 @@ struct MomCoefTiles {  // ring-1 tiles; DMS = -DMN and DMW = -DME exactly (hmix_
 };
 // 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*.
 // R1 = true: A and B are ring-1 tiles (TIX1); false: halo tiles of a pipeline stage (TIX).
+// dzu (partial bottom cells, hmix_del2.F90:852-863 / hmix_del4.F90:683-694): level k of DZU at the stencil centre
+// (array index gq, row pitch nxb), or null; inb: the centre and its four neighbours lie inside the padded block
 template <bool R1>
 __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const double* A, const double* B,
-                                              int ii, int jj, bool plus) {
+                                              int ii, int jj, bool plus, const double* dzu = nullptr, size_t gq = 0,
+                                              int nxb = 0, bool inb = false) {
   const int q = TIX1(ii, jj);
   const int o = R1 ? q : TIX(ii, jj);
   constexpr int W = R1 ? POP_T1W : POP_TW;
-  const double s1 = c.cc[q] * A[o] + c.dun[q] * A[o + W] + c.dus[q] * A[o - W] + c.due[q] * A[o + 1] +
-                    c.duw[q] * A[o - 1];
+  double dn = c.dun[q], ds = c.dus[q], de = c.due[q], dw = c.duw[q];
+  if (dzu) {
+    if (inb) {
+      const double z = dzu[gq];
+      dn = dn * fmin(dzu[gq + nxb], z) / z;
+      ds = ds * fmin(dzu[gq - nxb], z) / z;
+      de = de * fmin(dzu[gq + 1], z) / z;
+      dw = dw * fmin(dzu[gq - 1], z) / z;
+    } else {
+      dn = ds = de = dw = 0.0;
+    }
+  }
+  const double s1 = c.cc[q] * A[o] + dn * A[o + W] + ds * A[o - W] + de * A[o + 1] + dw * A[o - 1];
   const double s2 = c.dmc[q] * B[o] + c.dmn[q] * B[o + W] + (-c.dmn[q]) * B[o - W] + c.dme[q] * B[o + 1] +
                     (-c.dme[q]) * B[o - 1];
   return plus ? (s1 + s2) : (s1 - s2);
@@ -199,13 +213,22 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       const int p = tid + s * POP_NTHREADS;
       if (p < POP_T1N) {
         const int jj = p / POP_T1W - 1, ii = p % POP_T1W - 1;
+        const int gi = i0 + ii, gj = j0 + jj;
+        const bool inb = (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2);
+        const size_t gq = (size_t)gj * nxb + gi;
+        const double* dzu = g.DZU ? g.DZU + (size_t)kk * n2 : nullptr;
         if (DO_ADV) {
           s_ud[p] = uc[TIX(ii, jj)] * r_dyu[s];
           s_vd[p] = vc[TIX(ii, jj)] * r_dxu[s];
+          if (dzu) {  // advection.F90:1245-1303: (U*DYU)*DZU
+            const double z = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb) ? dzu[gq] : 0.0;
+            s_ud[p] = s_ud[p] * z;
+            s_vd[p] = s_vd[p] * z;
+          }
         }
         if (DO_HMIX && DEL4) {
-          double d2u = mom_stencil<false>(ct, um, vm, ii, jj, true);
-          double d2v = mom_stencil<false>(ct, vm, um, ii, jj, false);
+          double d2u = mom_stencil<false>(ct, um, vm, ii, jj, true, dzu, gq, nxb, inb);
+          double d2v = mom_stencil<false>(ct, vm, um, ii, jj, false, dzu, gq, nxb, inb);
           if (a.lvariable_hmixu) {
             if (kk <= s_kmu[p]) { d2u = s_amf[p] * d2u; d2v = s_amf[p] * d2v; }
             else { d2u = 0.0; d2v = 0.0; }
@@ -274,6 +297,9 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)(((k + 1 - a.k0) / NS) & 1));
     if (active) {
     double fx = 0.0, fy = 0.0;
+    const bool pbc = (g.DZU != nullptr);
+    const double* dzu_k = pbc ? g.DZU + (size_t)k * n2 : nullptr;
+    const double dzu_c = pbc ? dzu_k[q] : 0.0;  // thickness of this U cell
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
     // ---- advu: advection.F90:1307-1491
     double luk = 0.0, lvk = 0.0;
@@ -286,15 +312,23 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       const double vun = 0.25 * (VD(0, 1) + VD(0, 0)) + 0.125 * (VD(-1, 1) + VD(-1, 0) + VD(1, 1) + VD(1, 0));
 #undef UD
 #undef VD
-      const double wukb = wuk + c_vc.c2dz[k] * 0.5 * (vun - vus + uue - uuw) * uarea_r;
+      const double wukb = pbc ? wuk + (vun - vus + uue - uuw) * uarea_r  // advection.F90:1352-1353
+                              : wuk + c_vc.c2dz[k] * 0.5 * (vun - vus + uue - uuw) * uarea_r;
       const double cc = vun - vus + uue - uuw;  // VUS(i,j+1) - VUS(i,j) + UUW(i+1,j) - UUW(i,j)
       luk = 0.5 * (cc * U + vun * s_uc[TIX(tx, ty + 1)] - vus * s_uc[TIX(tx, ty - 1)] +
                    uue * s_uc[TIX(tx + 1, ty)] - uuw * s_uc[TIX(tx - 1, ty)]) * uarea_r;
       lvk = 0.5 * (cc * V + vun * s_vc[TIX(tx, ty + 1)] - vus * s_vc[TIX(tx, ty - 1)] +
                    uue * s_vc[TIX(tx + 1, ty)] - uuw * s_vc[TIX(tx - 1, ty)]) * uarea_r;
+      if (pbc) {  // :1381-1405
+        luk = luk / dzu_c;
+        lvk = lvk / dzu_c;
+      }
       if (k == 1) {
         luk = luk + c_vc.dzr[k] * wuk * U;
         lvk = lvk + c_vc.dzr[k] * wuk * V;
+      } else if (pbc) {  // :1443-1447
+        luk = luk + 0.5 / dzu_c * wuk * (u_m + U);
+        lvk = lvk + 0.5 / dzu_c * wuk * (v_m + V);
       } else {
         luk = luk + c_vc.dz2r[k] * wuk * (u_m + U);
         lvk = lvk + c_vc.dz2r[k] * wuk * (v_m + V);
@@ -302,8 +336,13 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       if (k < km) {
         const double Up = have_next ? n_uc[TIX(tx, ty)] : a.UCUR[lev + n2 + q];
         const double Vp = have_next ? n_vc[TIX(tx, ty)] : a.VCUR[lev + n2 + q];
-        luk = luk - c_vc.dz2r[k] * wukb * (U + Up);
-        lvk = lvk - c_vc.dz2r[k] * wukb * (V + Vp);
+        if (pbc) {  // :1462-1466
+          luk = luk - 0.5 / dzu_c * wukb * (U + Up);
+          lvk = lvk - 0.5 / dzu_c * wukb * (V + Vp);
+        } else {
+          luk = luk - c_vc.dz2r[k] * wukb * (U + Up);
+          lvk = lvk - c_vc.dz2r[k] * wukb * (V + Vp);
+        }
       }
       if (k <= kmu) {
         luk = luk + U * V * kyu - (V * V) * kxu;
@@ -350,11 +389,11 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     double hdu = 0.0, hdv = 0.0;
     if (DO_HMIX) {
       if (DEL4) {
-        hdu = a.am * mom_stencil<true>(ct, s_d2u, s_d2v, tx, ty, true);
-        hdv = a.am * mom_stencil<true>(ct, s_d2v, s_d2u, tx, ty, false);
+        hdu = a.am * mom_stencil<true>(ct, s_d2u, s_d2v, tx, ty, true, dzu_k, q, nxb, true);
+        hdv = a.am * mom_stencil<true>(ct, s_d2v, s_d2u, tx, ty, false, dzu_k, q, nxb, true);
       } else {
-        hdu = a.am * mom_stencil<false>(ct, um, vm, tx, ty, true);
-        hdv = a.am * mom_stencil<false>(ct, vm, um, tx, ty, false);
+        hdu = a.am * mom_stencil<false>(ct, um, vm, tx, ty, true, dzu_k, q, nxb, true);
+        hdv = a.am * mom_stencil<false>(ct, vm, um, tx, ty, false, dzu_k, q, nxb, true);
       }
       if (k > kmu) { hdu = 0.0; hdv = 0.0; }
     }
@@ -373,15 +412,28 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         vuf = (kmu >= 1) ? a.SMF[q] : 0.0;
         vvf = (kmu >= 1) ? a.SMF[n2 + q] : 0.0;
       }
-      double vufb = vvc * (uo_c - uo_p) * c_vc.dzwr[k];
-      double vvfb = vvc * (vo_c - vo_p) * c_vc.dzwr[k];
+      double vufb, vvfb;
+      if (pbc) {  // vertical_mix.F90:946-958: kp1 = min(k+1, km)
+        const double zp = g.DZU[(size_t)((k < km) ? k + 1 : km) * n2 + q];
+        const double W = (k < km) ? 0.5 * (dzu_c + zp) : 0.5 * zp;
+        vufb = vvc * (uo_c - uo_p) / W;
+        vvfb = vvc * (vo_c - vo_p) / W;
+      } else {
+        vufb = vvc * (uo_c - uo_p) * c_vc.dzwr[k];
+        vvfb = vvc * (vo_c - vo_p) * c_vc.dzwr[k];
+      }
       if (k == kmu) {
         const double vmag = a.bottom_drag * sqrt(uo_c * uo_c + vo_c * vo_c);
         vufb = vmag * uo_c;
         vvfb = vmag * vo_c;
       }
-      vdu = (k <= kmu) ? (vuf - vufb) * c_vc.dzr[k] : 0.0;
-      vdv = (k <= kmu) ? (vvf - vvfb) * c_vc.dzr[k] : 0.0;
+      if (pbc) {  // :991-995
+        vdu = (k <= kmu) ? (vuf - vufb) / dzu_c : 0.0;
+        vdv = (k <= kmu) ? (vvf - vvfb) / dzu_c : 0.0;
+      } else {
+        vdu = (k <= kmu) ? (vuf - vufb) * c_vc.dzr[k] : 0.0;
+        vdv = (k <= kmu) ? (vvf - vvfb) * c_vc.dzr[k] : 0.0;
+      }
       vuf = vufb;
       vvf = vvfb;
     }
@@ -421,8 +473,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       }
       a.OUT1[lev + q] = un;
       a.OUT2[lev + q] = vn;
-      zx = zx + fx * c_vc.dz[k];
-      zy = zy + fy * c_vc.dz[k];
+      zx = zx + fx * (pbc ? dzu_c : c_vc.dz[k]);  // baroclinic.F90:1037-1043
+      zy = zy + fy * (pbc ? dzu_c : c_vc.dz[k]);
     }
     uo_c = uo_p;
     vo_c = vo_p;
@@ -552,7 +604,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MINB)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
                        const double* __restrict__ UOLD, const double* __restrict__ VOLD,
                        const double* __restrict__ UB, const double* __restrict__ VB, int bt_skip_row,
-                       int implicit_vmix, int finish) {
+                       int implicit_vmix, int finish, double c2dtu) {
   POP_DYN_SMEM(smem_raw);
   double* sE = (double*)smem_raw + threadIdx.x;
   const int i = (g.ib - 1) + blockIdx.x * MF_THREADS + threadIdx.x;
@@ -612,10 +664,18 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
         nld--;
       }
     };
+    const double* DZUq = g.DZU ? g.DZU + q : nullptr;  // partial bottom cells: vertical_mix.F90:1777-1784
     auto fwd_level = [&](int k, double vvc, double ru, double rw) {
-      const double hfac = c_vc.hfac_u[k];
+      double hfac;
       C = A;
-      A = c_vc.afac_u[k] * vvc;
+      if (DZUq) {
+        const double zk = DZUq[(size_t)k * n2];
+        hfac = zk / c2dtu;
+        A = g.aidif * vvc / (0.5 * (zk + DZUq[(size_t)(k + 1) * n2]));
+      } else {
+        hfac = c_vc.hfac_u[k];
+        A = c_vc.afac_u[k] * vvc;
+      }
       if (k <= kmu) {
         const RcpD rd = rcp_prepare((k < kmu) ? hfac + A + B : hfac + B);
         const double e = div_by(A, rd);
@@ -748,7 +808,18 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   // ---- remove the vertical mean, KMU mask (baroclinic.F90:1085-1129) [+ barotropic velocity, step_mod.F90:581-592]
   const double hur = g.HUR[q];
   double w1 = 0.0, w2 = 0.0;
-  {
+  if (g.DZU) {  // baroclinic.F90:1097-1107
+    const double* pv = Vn;
+    const double* pz = g.DZU + q + n2;
+#pragma unroll 4
+    for (int k = 1; k <= km; k++) {
+      const double dzk = *pz;
+      w1 = w1 + sE[(k - 1) * MF_THREADS] * dzk;
+      w2 = w2 + *pv * dzk;
+      pv += n2i;
+      pz += n2i;
+    }
+  } else {
     const double* pv = Vn;
 #pragma unroll 8
     for (int k = 1; k <= km; k++) {
@@ -1001,7 +1072,7 @@ static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const d
                          const double* VB, int bt_skip_row, int implicit_vmix, int finish) {
   GridView g = grid_view();
   dim3 block(MF_THREADS, 1, 1), grid((unsigned)((G.nxg + MF_THREADS - 1) / MF_THREADS), (unsigned)G.ny_local, 1);
-  if (implicit_vmix && finish && !G.no_tma && G.thomas_tma) {
+  if (implicit_vmix && finish && !G.no_tma && G.thomas_tma && !G.cfg.partial_bottom_cells) {
     MfTmaArgs ta;
     if (make_tmap_box(&ta.tmU, UNEW, G.km, MF_THREADS, 1) && make_tmap_box(&ta.tmV, VNEW, G.km, MF_THREADS, 1) &&
         make_tmap_box(&ta.tmUo, UOLD, G.km, MF_THREADS, 1) && make_tmap_box(&ta.tmVo, VOLD, G.km, MF_THREADS, 1) &&
@@ -1023,7 +1094,7 @@ static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const d
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
   POP_LAUNCH(momentum_finish_kernel, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, implicit_vmix,
-             finish);
+             finish, G.c2dtu);
   return pop_post_launch("momentum_finish");
 }
 

@@ -106,7 +106,7 @@ int baroclinic_driver_dev(bool defer_finish) {
 // that is statically unstable after adiabatic displacement is mixed to its thickness-weighted mean. One thread
 // per column: the passes are sequential in k by construction. dttxcel = 1 (time_management.F90:1005-1010).
 __global__ void convad_kernel(StateOpt so, double* T, const int* __restrict__ KMT, size_t n2, int km,
-                              int nt, int nconvad) {
+                              int nt, int nconvad, const double* __restrict__ DZT) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n2) return;
   const int kmt = KMT[q];
@@ -120,7 +120,11 @@ __global__ void convad_kernel(StateOpt so, double* T, const int* __restrict__ KM
         state_cell(so, k + 1, T[c], S[c], &rhok, nullptr, nullptr, nullptr);
         state_cell(so, k + 1, T[c1], S[c1], &rhokp, nullptr, nullptr, nullptr);
         if (rhok > rhokp) {
-          const double dztk = c_vc.dz[k] / 1.0, dztk1 = c_vc.dz[k + 1] / 1.0;
+          double dztk = c_vc.dz[k] / 1.0, dztk1 = c_vc.dz[k + 1] / 1.0;
+          if (DZT) {  // partial bottom cells: vertical_mix.F90:1960-1968
+            dztk = DZT[(size_t)k * n2 + q] / 1.0;
+            dztk1 = DZT[(size_t)(k + 1) * n2 + q] / 1.0;
+          }
           const double dzwx = 1.0 / (dztk + dztk1);
           for (int n = 0; n < nt; n++) {
             double* t = T + (size_t)n * km * n2;
@@ -201,7 +205,8 @@ int baroclinic_correct_adjust_dev() {
   // convad: convection_type = 'diffusion' returns immediately (vertical_mix.F90:1925)
   if (!G.cfg.convection_diff && G.cfg.nconvad > 0)
     POP_LAUNCH(convad_kernel, ew_grid(G.n2), POP_EW_THREADS, 0, StateOpt{G.cfg.state_itype, G.cfg.state_range_iopt}, Tn,
-               fldi("KMT"), G.n2, G.km, G.nt, G.cfg.nconvad);
+               fldi("KMT"), G.n2, G.km, G.nt, G.cfg.nconvad,
+               G.cfg.partial_bottom_cells ? (const double*)fld("DZT") : (const double*)nullptr);
   POP_TRY(state_3d(Tn, fld_t("RHO", n_)));  // baroclinic.F90:1476-1482
   return pop_post_launch("baroclinic_correct_adjust");
 }

@@ -40,16 +40,32 @@ struct TracerArgs {
 struct Coef5 {
   double cc, cn, cs, ce, cw;
 };
+// dzt: level k of DZT (partial bottom cells: hmix_del2.F90:1034-1062, hmix_del4.F90:964-988 -- a face is as thick as
+// the thinner of its two cells) or null; gq/nxb: array index of the tile point and the row pitch; inb: the point and
+// its four neighbours lie inside the padded block
 __device__ __forceinline__ Coef5 tracer_coef(const int* s_kmt, const double* s_dtn, const double* s_dts,
                                              const double* s_dte, const double* s_dtw, int ii, int jj,
-                                             int k) {
+                                             int k, const double* dzt = nullptr, size_t gq = 0, int nxb = 0,
+                                             bool inb = false) {
   const int q = TIX(ii, jj);
   const int kmt = s_kmt[q];
   Coef5 c;
-  c.cn = (k <= s_kmt[TIX(ii, jj + 1)] && k <= kmt) ? s_dtn[q] : 0.0;
-  c.cs = (k <= s_kmt[TIX(ii, jj - 1)] && k <= kmt) ? s_dts[q] : 0.0;
-  c.ce = (k <= s_kmt[TIX(ii + 1, jj)] && k <= kmt) ? s_dte[q] : 0.0;
-  c.cw = (k <= s_kmt[TIX(ii - 1, jj)] && k <= kmt) ? s_dtw[q] : 0.0;
+  double dn = s_dtn[q], ds = s_dts[q], de = s_dte[q], dw = s_dtw[q];
+  if (dzt) {
+    if (inb) {
+      const double z = dzt[gq];
+      dn = dn * fmin(z, dzt[gq + nxb]) / z;
+      ds = ds * fmin(z, dzt[gq - nxb]) / z;
+      de = de * fmin(z, dzt[gq + 1]) / z;
+      dw = dw * fmin(z, dzt[gq - 1]) / z;
+    } else {
+      dn = ds = de = dw = 0.0;
+    }
+  }
+  c.cn = (k <= s_kmt[TIX(ii, jj + 1)] && k <= kmt) ? dn : 0.0;
+  c.cs = (k <= s_kmt[TIX(ii, jj - 1)] && k <= kmt) ? ds : 0.0;
+  c.ce = (k <= s_kmt[TIX(ii + 1, jj)] && k <= kmt) ? de : 0.0;
+  c.cw = (k <= s_kmt[TIX(ii - 1, jj)] && k <= kmt) ? dw : 0.0;
   c.cc = -(c.cn + c.cs + c.ce + c.cw);
   return c;
 }
@@ -170,7 +186,10 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
     constexpr int w = POP_BX + 2, npts = w * (POP_BY + 2);
     for (int p = tid; p < npts; p += POP_NTHREADS) {
       const int jj = p / w - 1, ii = p % w - 1;
-      const Coef5 c = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, ii, jj, kk);
+      const int gi = i0 + ii, gj = j0 + jj;
+      const Coef5 c = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, ii, jj, kk,
+                                  g.DZT ? g.DZT + (size_t)kk * n2 : nullptr, (size_t)gj * nxb + gi, nxb,
+                                  gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2);
 #pragma unroll
       for (int m = 0; m < NTC; m++) {
         if (m >= a.nn) continue;
@@ -241,22 +260,35 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
     if (active) {
     // ---- flux velocities and the vertical velocity at the bottom of the level
     double ute = 0.0, utw = 0.0, vtn = 0.0, vts = 0.0, wtkb = 0.0;
+    const bool pbc = (g.DZT != nullptr);
+    const double dzt_c = pbc ? g.DZT[(size_t)k * n2 + q] : 0.0;  // thickness of this cell
     if (DO_ADV) {
 #define UD(di, dj) (s_u[TIX(tx + (di), ty + (dj))] * s_dyu[TIX(tx + (di), ty + (dj))])
 #define VD(di, dj) (s_v[TIX(tx + (di), ty + (dj))] * s_dxu[TIX(tx + (di), ty + (dj))])
+      if (pbc) {  // advection.F90:2040-2066: the flux velocities carry the thickness of the U cells
+        const double* zu = g.DZU + (size_t)k * n2 + q;
+        const double z00 = zu[0], z0m = zu[-(ptrdiff_t)nxb], zm0 = zu[-1], zmm = zu[-(ptrdiff_t)nxb - 1];
+        ute = 0.5 * (UD(0, 0) * z00 + UD(0, -1) * z0m);
+        utw = 0.5 * (UD(-1, 0) * zm0 + UD(-1, -1) * zmm);
+        vtn = 0.5 * (VD(0, 0) * z00 + VD(-1, 0) * zm0);
+        vts = 0.5 * (VD(0, -1) * z0m + VD(-1, -1) * zmm);
+      } else {
       ute = 0.5 * (UD(0, 0) + UD(0, -1));
       utw = 0.5 * (UD(-1, 0) + UD(-1, -1));
       vtn = 0.5 * (VD(0, 0) + VD(-1, 0));
       vts = 0.5 * (VD(0, -1) + VD(-1, -1));
+      }
 #undef UD
 #undef VD
       if (k < km) {
         const double FC = (vtn - vts + ute - utw) * tarea_r;
-        wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
+        if (pbc) wtkb = (k < kmt) ? wtk + FC : 0.0;  // :2110-2111
+        else wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
       }
     }
     Coef5 cc5;
-    if (DO_HMIX) cc5 = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, tx, ty, k);
+    if (DO_HMIX) cc5 = tracer_coef(s_kmt, s_dtn, s_dts, s_dte, s_dtw, tx, ty, k, pbc ? g.DZT + (size_t)k * n2 : nullptr, q,
+                                   nxb, true);
 
 #pragma unroll
     for (int m = 0; m < NTC; m++) {
@@ -283,12 +315,17 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
               ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
                ute * tc[TIX(tx + 1, ty)] - utw * tc[TIX(tx - 1, ty)]) *
               tarea_r;
+          if (pbc) L = L / dzt_c;  // :2223-2238
           if (k == 1) {
             if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
           } else {
-            L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+            if (pbc) L = L + 0.5 / dzt_c * wtk * (tc_m[m] + T);  // :2278-2280
+            else L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
           }
-          if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+          if (k < km) {
+            if (pbc) L = L - 0.5 / dzt_c * wtkb * (T + Tp);
+            else L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+          }
         } else if (UPW) {  // upwind3: advection.F90:2387-2476 + hupw3 :2543-2672
           const double CE = ute * tarea_r, CW = -utw * tarea_r, CN = vtn * tarea_r, CS = -vts * tarea_r;
           const double CEw = utw * tarea_rw;  // CE(i-1,j) = UTE(i-1,j)*TAREA_R(i-1,j)
@@ -374,8 +411,15 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
         const double told_p = (k < km) ? ((have_next && told_is_mix) ? n_tm[m * POP_TN + TIX(tx, ty)] : a.TOLD[lev + n2])
                                        : told_c[m];
         if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
-        const double VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
-        vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        double VTFB;
+        if (pbc) {  // vertical_mix.F90:790-803
+          const double dzt_p = g.DZT[(size_t)((k < km) ? k + 1 : km) * n2 + q];
+          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) / (0.5 * (dzt_c + dzt_p)) : 0.0;
+          vd = (k <= kmt) ? (vtf[m] - VTFB) / dzt_c : 0.0;
+        } else {
+          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
+          vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        }
         vtf[m] = VTFB;
         told_c[m] = told_p;
       }
@@ -759,7 +803,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
     switch (mode) {
       case TR_FULL: {
         // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
-        const bool fast_ok = !gm && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+        const bool fast_ok = !gm && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
                              a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
         if (fast_ok) {
           TracerFastArgs f;
@@ -896,10 +940,18 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
         nld--;
       }
     };
+    const double* DZTq = g.DZT ? g.DZT + q : nullptr;  // partial bottom cells: vertical_mix.F90:1279-1286, :1577-1582
     auto fwd_level = [&](int k, double vdc, double rhs) {
       C = A;
-      A = c_vc.afac_t[k] * vdc;
-      const double hfac = c_vc.hfac_t[k];
+      double hfac;
+      if (DZTq) {  // level 1 keeps the full-cell A and hfac (:1263-1269); DZT(k+1) is read at k = km too
+        const double zk = DZTq[(size_t)k * n2];
+        A = g.aidif * vdc / (0.5 * (zk + DZTq[(size_t)(k + 1) * n2]));
+        hfac = zk / c_vc.c2dtt[k];
+      } else {
+        A = c_vc.afac_t[k] * vdc;
+        hfac = c_vc.hfac_t[k];
+      }
       double F;
       if (k > kmt) {
         F = 0.0;
@@ -1185,7 +1237,7 @@ int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const dou
   double* FB = fld("WORK3D_E");
   // TMA-staged path (needs an even row pitch; TOLD is only dereferenced by the predictor form)
   IvTmaArgs ta;
-  const bool tma = !G.no_tma && G.thomas_tma && make_tmap_box(&ta.tmT, TNEW, G.km * G.nt, IV_THREADS, 1) &&
+  const bool tma = !G.no_tma && G.thomas_tma && !G.cfg.partial_bottom_cells && make_tmap_box(&ta.tmT, TNEW, G.km * G.nt, IV_THREADS, 1) &&
                    (correct || make_tmap_box(&ta.tmO, TOLD, G.km * G.nt, IV_THREADS, 1)) &&
                    make_tmap_box(&ta.tmV, g.VDC, g.vdc_nd * g.vdc_nk, IV_THREADS, 1);
   if (tma) {

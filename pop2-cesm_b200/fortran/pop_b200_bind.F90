@@ -120,6 +120,13 @@ module pop_b200_bind
       end function
 
       ! ---------------------------------------------------------------- grid + fields
+      ! grid.F90:2116 read_bottom_cell -> DZBC (physical strip); before pop_set_grid when partial_bottom_cells
+      function pop_set_bottom_cells(DZBC) bind(C, name='pop_set_bottom_cells') result(ierr)
+         import :: c_int, c_double
+         real (c_double), intent(in) :: DZBC(*)
+         integer (c_int) :: ierr
+      end function
+
       function pop_set_grid(ULAT, HTN, HTE, HUS, HUW, DXU, DYU, DXT, DYT, KMT, dz) &
                bind(C, name='pop_set_grid') result(ierr)
          import :: c_int, c_double

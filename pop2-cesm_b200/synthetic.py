@@ -91,6 +91,15 @@ def bathymetry(nx, ny, km, seed, land_frac_thresh=0.12, south_land_rows=2, flat=
     return np.ascontiguousarray(kmt)
 
 
+def bottom_cells(kmt, dz, seed, fmin=0.25):
+    """DZBC(ny,nx): thickness of the bottom cell of every column for partial bottom cells (grid.F90:917-940): a seeded
+    fraction fmin..1 of the full thickness of level KMT; land columns get dz(1) (never used: KMT == k is false)."""
+    rng = np.random.default_rng(seed)
+    frac = fmin + (1.0 - fmin) * rng.uniform(0.0, 1.0, kmt.shape)
+    full = np.where(kmt > 0, dz[np.maximum(kmt, 1) - 1], dz[0])
+    return np.ascontiguousarray(np.where(kmt > 0, frac * full, dz[0]))
+
+
 def kmu_from_kmt(kmt, ew_cyclic=True, ns_type=0):
     """KMU = min of the 4 surrounding KMT (source/grid.F90:978-985) on the global grid."""
     ny, nx = kmt.shape

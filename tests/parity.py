@@ -30,6 +30,11 @@ def make_case(nx, ny, km, nt=2, seed=1, ns=c.BNDY_CLOSED, ew=c.BNDY_CYCLIC, vgri
     if tripole:  # mirror-symmetric bathymetry on the top rows
         cs.kmt[-3:, :] = np.minimum(cs.kmt[-3:, :], cs.kmt[-3:, ::-1])
     cs.kmu = syn.kmu_from_kmt(cs.kmt, ew_cyclic=(ew == c.BNDY_CYCLIC), ns_type=ns)
+    cs.dzbc = None
+    if cs.cfg.partial_bottom_cells:
+        cs.dzbc = syn.bottom_cells(cs.kmt, cs.dz, seed + 11)
+        if tripole:
+            cs.dzbc[-3:, :] = np.minimum(cs.dzbc[-3:, :], cs.dzbc[-3:, ::-1])
     cs.state = syn.state(nx, ny, km, nt, cs.dz, cs.kmt, cs.kmu, seed + 100)
     rng = np.random.default_rng(seed + 7)
     cs.state["UBTROP_cur"] = 2.0 * rng.standard_normal((ny, nx)) * (cs.kmu > 0)
@@ -70,6 +75,8 @@ def load_oracle(cs, block_size=None, reproducible=False):
     cfg = cs.cfg if block_size is None else c.copy_config(cs.cfg, block_size_x=block_size[0], block_size_y=block_size[1])
     _O.lib().oracle_set_reproducible(1 if reproducible else 0)
     o = Oracle(cfg)
+    if cs.dzbc is not None:
+        o.set_bottom_cells(cs.dzbc)
     o.set_grid(cs.grid, cs.kmt, cs.dz)
     for lev, t in LEVELS:
         for name, loc, kind in FIELDS:
@@ -98,6 +105,8 @@ def load_oracle(cs, block_size=None, reproducible=False):
 def load_pop(cs, cfg=None, comm_id=None):
     api = P.api
     p = api.Pop(cfg if cfg is not None else cs.cfg, comm_id)
+    if cs.dzbc is not None:
+        p.set_bottom_cells(cs.dzbc)
     p.set_grid(cs.grid, cs.kmt, cs.dz)
     n2 = p.nxb * p.nyb
     for lev, t in LEVELS:

@@ -36,6 +36,12 @@ def get_case(key):
                        tadvect=[c.TADVECT_CENTERED, c.TADVECT_UPWIND3, c.TADVECT_CENTERED])
     elif key == "gm":          # gx1v7 flavour: GM with the terms that cancel dropped (ah == ah_bolus)
         cs = make_case(40, 28, 7, nt=3, seed=13, hmix_tracer_itype=c.HMIX_GM, given_vmix=True)
+    elif key == "pbc":         # partial bottom cells: every operator takes its DZT / DZU branch (del4, given coefficients)
+        cs = make_case(36, 24, 7, nt=3, seed=15, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                       hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21,
+                       am=-27.0e21, given_vmix=True, partial_bottom_cells=1)
+    elif key == "pbc_del2":
+        cs = make_case(40, 28, 7, nt=2, seed=16, given_vmix=True, partial_bottom_cells=1)
     elif key == "gm_general":  # general skew-flux form: different thickness diffusivity and slope limits
         cs = make_case(36, 24, 6, nt=3, seed=14, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM,
                        ah_gm=0.6e7, ah_bolus=0.4e7, ah_bkg_srfbl=0.5e7, slm_r=0.3, slm_b=0.2)
@@ -66,8 +72,15 @@ def fields(o, t):
     return T, U, V, R
 
 
-def test_grid_masks_and_metrics_bit_exact(case_del4):
-    cs, o, p = case_del4
+@pytest.mark.parametrize("which", ["del4", "pbc"])
+def test_grid_masks_and_metrics_bit_exact(which):
+    cs, o, p = get_case(which)
+    if which == "pbc":   # grid.F90:917-1022: DZT, DZU (levels 0..km+1), and the depths built from them
+        for n in ("DZT", "DZU"):
+            a = o.view(n, 1, (o.km + 2,))[0]
+            assert np.array_equal(a, p.get_padded(n, 1).reshape(a.shape)), n
+        for n in ("HU", "HUR", "HT"):
+            assert np.array_equal(o.view(n, 1)[0], p.get_padded(n, 1)[0]), n
     for n in ("KMT", "KMU", "CHECKER", "CONSTNT"):
         assert np.array_equal(o.view(n, 1, (), np.int32)[0], p.get_padded(n, 1, np.int32)[0]), n
     for n in ("DXU", "DYU", "TAREA_R", "UAREA_R", "HUR", "FCOR", "AU0", "AUNE", "KXU", "KYU", "DTN", "DTS", "DTE",
@@ -94,7 +107,7 @@ def test_state_mwjf_all_outputs(case_del2):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("which", ["del2", "del4"])
+@pytest.mark.parametrize("which", ["del2", "del4", "pbc", "pbc_del2"])
 def test_hdifft_advt_vdifft(which):
     cs, o, p = get_case(which)
     Tc, Uc, Vc, _ = fields(o, c.TIME_CUR)
@@ -149,7 +162,7 @@ def test_hdifft_gm_slabs_and_vdc_side_effect(which):
     p.set_padded("VDC", 0, v0)
 
 
-@pytest.mark.parametrize("which", ["del2", "del4"])
+@pytest.mark.parametrize("which", ["del2", "del4", "pbc", "pbc_del2"])
 def test_advu_hdiffu_gradp_vdiffu(which):
     cs, o, p = get_case(which)
     _, Uc, Vc, Rc = fields(o, c.TIME_CUR)
@@ -186,8 +199,9 @@ def test_advu_hdiffu_gradp_vdiffu(which):
         assert np.array_equal(phys(a1), phys(b1)) and np.array_equal(phys(a2), phys(b2)), ("vdiffu", k)
 
 
-def test_impvmix_tridiagonal_solves(case_del2):
-    cs, o, p = case_del2
+@pytest.mark.parametrize("which", ["del2", "pbc"])
+def test_impvmix_tridiagonal_solves(which):
+    cs, o, p = get_case(which)
     Tc = fields(o, c.TIME_CUR)[0]
     To, Uo, Vo, _ = fields(o, c.TIME_OLD)
     Ps = o.view("PSURF", c.TIME_CUR)[0].copy()

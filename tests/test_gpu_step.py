@@ -60,6 +60,18 @@ CASES = {
                                convergence_criterion=1e-12),
     # convection_type = 'adjustment': two convad passes (vertical_mix.F90:1888-2027) instead of convective diffusion
     "convad_chrongear": dict(nx=40, ny=32, km=8, nt=3, seed=29, convection_diff=0, nconvad=2, convergence_criterion=1e-12),
+    # partial bottom cells (grid.F90:917-1022 and the DZT/DZU branches of every operator): the production variant of
+    # config 4 (tripole, variable del4, KPP-shaped coefficients, P-CSI) ...
+    "pbc_tripole_del4_pcsi": dict(nx=48, ny=36, km=8, seed=32, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                                  hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21,
+                                  am=-27.0e21, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0,
+                                  partial_bottom_cells=1),
+    # ... with del2 mixing, const coefficients, an extra tracer and convective adjustment ...
+    "pbc_del2_convad_chrongear": dict(nx=40, ny=32, km=8, nt=3, seed=33, convection_diff=0, nconvad=2,
+                                      convergence_criterion=1e-12, partial_bottom_cells=1),
+    # ... and with explicit vertical mixing (vdifft / vdiffu carry the cell thicknesses)
+    "pbc_explicit_vmix": dict(nx=40, ny=32, km=6, seed=34, implicit_vertical_mix=0, convection_diff=0,
+                              partial_bottom_cells=1),
     # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
     "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
                              lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),

@@ -215,3 +215,30 @@ def test_convective_adjustment_mixes_unstable_pairs_and_conserves_column_content
     ia, ib = np.sum(a * w, axis=1), np.sum(b * w, axis=1)
     assert np.max(np.abs(ia - ib)) <= 1e-12 * np.max(np.abs(ia))
     assert np.all(b[:, :, cs.kmt == 0] == 0.0)
+
+
+def test_partial_bottom_cells_conserve_tracer_content():
+    """Partial bottom cells (grid.F90:917-1022; DZT/DZU branches of comp_flux_vel, advt_centered, hdifft, vdifft,
+    impvmixt): with a rigid lid, closed/cyclic boundaries and no surface fluxes the flux form conserves the volume
+    integral of every tracer, the volumes being TAREA * DZT -- which only holds if every branch uses the cell
+    thicknesses consistently (faces as thick as the thinner neighbour, vertical fluxes over the local distances)."""
+    cs = make_case(64, 40, 10, nt=3, seed=51, sfc_layer_type=c.SFC_RIGID, lpressure_avg=0, given_vmix=True,
+                   partial_bottom_cells=1)
+    for f in ("STF", "TFW"):
+        cs.forcing[f][:] = 0.0
+    o = load_oracle(cs, block_size=(16, 20))
+    lev = np.arange(1, cs.km + 1)[:, None, None]
+    dzt = np.where(lev == cs.kmt[None], cs.dzbc[None], cs.dz[:, None, None])
+    vol = (lev <= cs.kmt[None]) * dzt * (cs.grid["DXT"] * cs.grid["DYT"])[None]
+    told = oracle_global(o, "TRACER", c.TIME_OLD).reshape(3, cs.km, cs.ny, cs.nx)
+    assert o.step(c.TS_EULER) == 0
+    t = oracle_global(o, "TRACER", c.TIME_CUR).reshape(3, cs.km, cs.ny, cs.nx)
+    for n in range(3):
+        before, after = np.sum(told[n] * vol), np.sum(t[n] * vol)
+        assert abs(after - before) <= 1.0e-12 * np.sum(np.abs(told[n]) * vol), (n, before, after)
+    # the depths follow the partial cells: HU = zw(KMU-1) + DZU(KMU) <= zw(KMU), HT likewise (grid.F90:1001-1015)
+    zw = np.concatenate([[0.0], np.cumsum(cs.dz)])
+    ht = oracle_global(o, "HT", 1)[0]
+    ocean = cs.kmt > 0
+    assert np.all(ht[ocean] <= zw[cs.kmt[ocean]] + 1e-9) and np.all(ht[ocean] > zw[cs.kmt[ocean] - 1])
+    np.testing.assert_array_equal(ht[ocean], zw[cs.kmt[ocean] - 1] + cs.dzbc[ocean])
