@@ -66,7 +66,7 @@ __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const doubl
 // intermediates UD = U*DYU, VD = V*DXU and, for del4, D2U/D2V = AMF*L(U,V) of level k), then the CTA
 // rebuilds those intermediates for level k+1 from the stage that has already landed.  The products
 // and the first Laplacian are thus computed once per tile point instead of once per stencil use.
-template <int MODE, bool DEL4, bool TMA>
+template <int MODE, bool DEL4, bool TMA, bool PBC>
 __global__ void __launch_bounds__(POP_NTHREADS, 2)
 momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   POP_DYN_SMEM(smem_raw);
@@ -216,11 +216,11 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         const int gi = i0 + ii, gj = j0 + jj;
         const bool inb = (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2);
         const size_t gq = (size_t)gj * nxb + gi;
-        const double* dzu = g.DZU ? g.DZU + (size_t)kk * n2 : nullptr;
+        const double* dzu = PBC ? g.DZU + (size_t)kk * n2 : nullptr;
         if (DO_ADV) {
           s_ud[p] = uc[TIX(ii, jj)] * r_dyu[s];
           s_vd[p] = vc[TIX(ii, jj)] * r_dxu[s];
-          if (dzu) {  // advection.F90:1245-1303: (U*DYU)*DZU
+          if (PBC) {  // advection.F90:1245-1303: (U*DYU)*DZU
             const double z = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb) ? dzu[gq] : 0.0;
             s_ud[p] = s_ud[p] * z;
             s_vd[p] = s_vd[p] * z;
@@ -297,7 +297,7 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)(((k + 1 - a.k0) / NS) & 1));
     if (active) {
     double fx = 0.0, fy = 0.0;
-    const bool pbc = (g.DZU != nullptr);
+    constexpr bool pbc = PBC;  // partial bottom cells: g.DZU is set
     const double* dzu_k = pbc ? g.DZU + (size_t)k * n2 : nullptr;
     const double dzu_c = pbc ? dzu_k[q] : 0.0;  // thickness of this U cell
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
@@ -505,8 +505,14 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
 template <int MODE>
 static int launch_momentum(const MomentumArgs& a, bool del4, bool tma) {
   void (*kfn)(const MomentumArgs) = nullptr;
-  if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true> : momentum_column_kernel<MODE, false, true>;
-  else kfn = del4 ? momentum_column_kernel<MODE, true, false> : momentum_column_kernel<MODE, false, false>;
+  const bool pbc = (a.g.DZU != nullptr);
+  if (pbc) {
+    if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true, true> : momentum_column_kernel<MODE, false, true, true>;
+    else kfn = del4 ? momentum_column_kernel<MODE, true, false, true> : momentum_column_kernel<MODE, false, false, true>;
+  } else {
+    if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true, false> : momentum_column_kernel<MODE, false, true, false>;
+    else kfn = del4 ? momentum_column_kernel<MODE, true, false, false> : momentum_column_kernel<MODE, false, false, false>;
+  }
   const int ns = tma ? MO_NS : 1;
   const size_t smem = sizeof(double) * ((size_t)POP_TN * ns * MOM_STAGE_TILES + (size_t)POP_T1N * MOM_FIXED_TILES) +
                       sizeof(int) * POP_T1N + 8 * MO_NS;

@@ -47,10 +47,27 @@ def main():
     elif which == "gm":
         kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM, ah_bolus=0.5e7, slm_b=0.2, given_vmix=True, nt=3,
                   solver_choice=c.SOLVER_PCSI, dtt=1800.0)
+    elif which == "pbc":   # partial bottom cells, the production variant of config 4
+        kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
+                  lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21, given_vmix=True,
+                  solver_choice=c.SOLVER_PCSI, dtt=600.0, partial_bottom_cells=1)
+    elif which == "evp":   # EVP is block-local: the strips are compared with the oracle run on the same 1 x P blocks
+        kw.update(ns=c.BNDY_TRIPOLE, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=7200.0,
+                  preconditioner_choice=c.PRECOND_EVP, max_lanczos_step=100, lanczos_convergence_criterion=0.15)
     cs = make_case(kw.pop("nx"), kw.pop("ny"), kw.pop("km"), **kw)
     steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_AVG, c.TS_LEAPFROG, c.TS_ROBERT]
+    if which == "evp":
+        steps = [c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG]
     ref = None
-    if rank == 0:
+    if rank == 0 and which == "evp":
+        # reference = the oracle in its REPRODUCIBLE (r16-sum) build on the same decomposition: bit-identical expected
+        o = load_oracle(cs, block_size=(cs.nx, cs.ny // world), reproducible=True)
+        its = []
+        for ts in steps:
+            assert o.step(ts) == 0
+            its.append(o.solver_diag()[0])
+        ref = (its, {n: oracle_global(o, n, c.TIME_CUR) for n in FIELDS_CMP}, None)
+    elif rank == 0:
         ref = run(cs, c.copy_config(cs.cfg, rank=0, nranks=1, device=0), None, steps)
     dist.barrier()
     obj = [P.api.Pop.unique_id() if rank == 0 else None]

@@ -1,4 +1,5 @@
-"""N > 1 GPUs: the strip-decomposed run (one process per GPU) is bitwise the single-GPU run.
+"""N > 1 GPUs: the strip-decomposed run (one process per GPU) is bitwise the single-GPU run (for the block-local EVP
+preconditioner: bitwise the oracle in its REPRODUCIBLE build on the same 1 x P blocks).
 Needs >= 2 GPUs (gpurun --gpus 2); skipped on the single-GPU box."""
 import os
 import subprocess
@@ -15,7 +16,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("which", ["pcsi", "chrongear", "cyclic_pcg", "gm"])
+@pytest.mark.parametrize("which", ["pcsi", "chrongear", "cyclic_pcg", "gm", "pbc", "evp"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_strips_are_bitwise_the_single_strip_run(which, world):
     if _ngpu() < world:

@@ -276,11 +276,13 @@ def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypa
 
 
 @pytest.mark.parametrize("flags", [("POP_B200_NO_TMA",), ("POP_B200_NO_FAST_TRACER",), ("POP_B200_NO_OVERLAP",),
-                                   ("POP_B200_NO_TMA", "POP_B200_NO_OVERLAP")])
+                                   ("POP_B200_NO_TMA", "POP_B200_NO_OVERLAP"), ("POP_B200_OVERLAP_FINISH",),
+                                   ("POP_B200_THOMAS_TMA",)])
 def test_staging_and_overlap_variants_are_bitwise_identical(monkeypatch, flags):
-    """The TMA-staged kernels, the specialised leapfrog tracer kernel and the side-stream overlap of the velocity
-    finish are optimisations of one computation: switching each off (the paths odd extents and old drivers take)
-    must not change a single bit, on a grid with partial edge tiles."""
+    """The TMA-staged kernels, the specialised leapfrog tracer kernel, the placement of the velocity finish (fused after
+    the barotropic solve with the barotropic add, inside baroclinic_driver, or on a side stream under the solve) and the
+    opt-in TMA-staged Thomas kernels are variants of one computation: switching between them must not change a single
+    bit, on a tripole grid with partial edge tiles."""
     cs = make_case(104, 52, 6, seed=72, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
                    hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21,
                    given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
