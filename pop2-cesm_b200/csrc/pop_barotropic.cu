@@ -754,6 +754,9 @@ struct Pcsi2Args {
   // tile rows of this launch: rowsel 0 -> blockIdx.y + row0; rowsel 1 -> the first and the last tile row (the rows a
   // neighbouring strip needs), launched ahead of the interior so that the exchange overlaps the interior tiles
   int rowsel, row0, nty;
+  // deep strips (see pcsi()): rows above jw_max are not written by the tile pass; with `deep` the ghost cells that have
+  // a source cell in this strip (east-west wrap, tripole fold) are written together with their source
+  int deep, jw_max;
   PopTmap tmX, tmC, tmB, tmQ, tmN, tmE, tmNE;  // 2-d tensor maps with the box of each staged tile
 };
 // cooperative asynchronous staging of a w x h window of a 2-d field (origin gi0,gj0; zero outside)
@@ -856,7 +859,8 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
     x1 = ldg(X + q) + (a.om1 * (r * a0r) + a.c11 * ldg(a.Q + q));
   };
   const bool edge_cta = (i0 + P2_TX + 1 >= nxb - POP_NGHOST) || (i0 - 1 < POP_NGHOST) || (j0 - 1 < POP_NGHOST) ||
-                        (j0 + P2_TY >= nyb - POP_NGHOST);  // the tile + ring touches ghost cells of the block
+                        (j0 + P2_TY >= nyb - POP_NGHOST) ||  // the tile + ring touches ghost cells of the block
+                        (a.do_tripole && j0 + P2_TY > a.je0);  // ... or the fold rows of a deep strip
   // ---- iteration m on the tile + ring: rows -1 .. TY split over the strips
   {
     constexpr int NR1 = P2_TY + 2;
@@ -937,15 +941,33 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
       const double c = sC[o1], n = sN[o1 + P2_XW], e = sE[oX], ew = sE[oX - 1];
       const double ne = sNE[oX + P2_XW], nw = sNE[oX + P2_XW - 1];
       const int gj = j0 + jj;
-      if (gi <= nxb - POP_NGHOST - 1 && gj <= nyb - POP_NGHOST - 1) {
+      if (gi <= nxb - POP_NGHOST - 1 && gj <= a.jw_max) {
         const double ax = c * xc1 + n * xp1 + n_s * xm1 + e * xc2 + ew * xc0 + ne * xp2 + ne_s * xm2 + nw * xp0 +
                           ne_sw * xm0;
         const double r = sB[o1] - ax;
         const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
         const double qv = a.om2 * (r * a0r) + a.c12 * sQ[o1];
+        const double xv = xc1 + qv;
         const size_t q = (size_t)gj * nxb + gi;
         a.Qn[q] = qv;
-        a.Xn[q] = xc1 + qv;
+        a.Xn[q] = xv;
+        if (a.deep) {  // the copies a halo update would make of this cell
+          const int nxg = nxb - 2 * POP_NGHOST;
+          if (a.do_ew && a.jglob[gj] > 0) {
+            if (gi < 2 * POP_NGHOST) { a.Qn[q + nxg] = qv; a.Xn[q + nxg] = xv; }
+            else if (gi >= nxg) { a.Qn[q - nxg] = qv; a.Xn[q - nxg] = xv; }
+          }
+          if (a.do_tripole && gj >= a.je0 - (POP_NGHOST - 1)) {
+            const int t = a.nxg - a.iglob[gi] + 1;  // global column of the fold row cell this one is the source of
+            const size_t qr = (size_t)(2 * a.je0 + 1 - gj) * nxb;
+            a.Qn[qr + POP_NGHOST - 1 + t] = qv;
+            a.Xn[qr + POP_NGHOST - 1 + t] = xv;
+            if (a.do_ew) {
+              if (t <= POP_NGHOST) { a.Qn[qr + nxb - POP_NGHOST - 1 + t] = qv; a.Xn[qr + nxb - POP_NGHOST - 1 + t] = xv; }
+              else if (t > a.nxg - POP_NGHOST) { a.Qn[qr + t - (a.nxg - POP_NGHOST) - 1] = qv; a.Xn[qr + t - (a.nxg - POP_NGHOST) - 1] = xv; }
+            }
+          }
+        }
       }
       xm0 = xc0; xm1 = xc1; xm2 = xc2;
       xc0 = xp0; xc1 = xp1; xc2 = xp2;
@@ -1000,6 +1022,58 @@ static int pcsi_evp(double* X, const double* B) {
   return pop_post_launch("PCSI/EVP");
 }
 
+// ---- deep strips (P > 1) ------------------------------------------------------------------------------------
+// On P strips every pass used to be followed by a strip exchange (a peer-memory kernel with a flag round trip): at
+// 1/8 of the tx0.1 grid the exchange cost more than the pass.  The iteration therefore runs on private copies of
+// its ten arrays whose strips carry `gd` ghost rows on either side instead of two: after an exchange all gd rows
+// hold the owner's bits, and every iteration makes one more ghost row stale (the pass recomputes the ghost rows
+// redundantly, bit for bit what their owner computes), so ONE exchange serves gd iterations.  Ghost cells with a
+// source in the same strip (east-west wrap, tripole fold) are written by the pass itself.  gd = 2 + a multiple of
+// the tile height keeps the tiles -- and with them the order of the residual sum -- those of the plain layout.
+struct DeepBt {
+  double* buf = nullptr;  // levels: C N E NE mask B X0 Q0 X1 Q1 snap0 snap1
+  int* jglob = nullptr;
+  int gd = 0, nyd = 0;
+  size_t n2d = 0;
+};
+static DeepBt DB;
+enum { DL_C = 0, DL_N, DL_E, DL_NE, DL_MASK, DL_B, DL_X0, DL_Q0, DL_X1, DL_Q1, DL_SNAP0, DL_SNAP1, DL_COUNT };
+void deep_release() {
+  cudaFree(DB.buf);
+  cudaFree(DB.jglob);
+  DB = DeepBt();
+}
+static int deep_prepare(int gd) {
+  if (DB.buf && DB.gd == gd && DB.nyd == G.ny_local + 2 * gd) return POP_SUCCESS;
+  deep_release();
+  DB.gd = gd;
+  DB.nyd = G.ny_local + 2 * gd;
+  DB.n2d = (size_t)G.nxb * DB.nyd;
+  POP_CHECK_CUDA(cudaMalloc(&DB.buf, sizeof(double) * DB.n2d * DL_COUNT));
+  POP_CHECK_CUDA(cudaMemset(DB.buf, 0, sizeof(double) * DB.n2d * DL_COUNT));
+  std::vector<int> jg(DB.nyd);
+  for (int j = 0; j < DB.nyd; j++) {  // as j_glob of the strip (pop_core.cu), gd rows deep
+    int v = G.j0 + j - gd;
+    if (v < 1) v = 0;
+    else if (v > G.nyg) v = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE) ? -v : 0;
+    jg[j] = v;
+  }
+  POP_CHECK_CUDA(cudaMalloc(&DB.jglob, sizeof(int) * DB.nyd));
+  POP_CHECK_CUDA(cudaMemcpy(DB.jglob, jg.data(), sizeof(int) * DB.nyd, cudaMemcpyHostToDevice));
+  return POP_SUCCESS;
+}
+// plain strip (nyb rows) -> rows gd-2 .. of a deep level, and back
+static int deep_load(int level, const double* src) {
+  POP_CHECK_CUDA(cudaMemcpyAsync(DB.buf + level * DB.n2d + (size_t)(DB.gd - POP_NGHOST) * G.nxb, src, sizeof(double) * G.n2,
+                                 cudaMemcpyDeviceToDevice, G.stream));
+  return POP_SUCCESS;
+}
+static int deep_store(double* dst, const double* deep_level) {
+  POP_CHECK_CUDA(cudaMemcpyAsync(dst, deep_level + (size_t)(DB.gd - POP_NGHOST) * G.nxb, sizeof(double) * G.n2,
+                                 cudaMemcpyDeviceToDevice, G.stream));
+  return POP_SUCCESS;
+}
+
 static int pcsi(double* X, const double* B) {
   if (use_evp()) return pcsi_evp(X, B);
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
@@ -1029,22 +1103,54 @@ static int pcsi(double* X, const double* B) {
   // the other pair starts as a copy so that cells no pass writes (closed-boundary ghost rows) agree
   POP_CHECK_CUDA(cudaMemcpyAsync(Xb[1], Xb[0], sizeof(double) * 2 * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   G.numIterations = maxIt;
-  const dim3 grid1((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((G.nyb + PC_TY - 1) / PC_TY), 1);
-  const dim3 grid2((unsigned)((G.nxg + P2_TX - 1) / P2_TX), (unsigned)((G.ny_local + P2_TY - 1) / P2_TY), 1);
+  const bool blocking = !G.no_pcsi_blocking;
+  // deep strips: see DeepBt.  Needs the peer-memory exchange, a closed or tripole north-south boundary and strips
+  // at least gd rows high; gd is rounded to 2 + k * tile height.
+  int gd = G.deep_halo >= POP_NGHOST + P2_TY ? POP_NGHOST + (G.deep_halo - POP_NGHOST) / P2_TY * P2_TY : 0;
+  const bool deep = blocking && gd > 0 && G.ny_local >= gd && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC &&
+                    ((G.nranks > 1 && G.p2p_on && (size_t)8 * gd * G.nxg <= G.p2p_cap) || (G.nranks == 1 && G.deep_force));
+  BtView view = bt_view();
+  const int* jglob = G.d_jglob;
+  int nyv = G.nyb;        // rows of the arrays the passes work on
+  int je0 = G.je - 1;     // 0-based last physical row
+  size_t n2v = G.n2;
+  double* snap[2] = {W + 4 * G.n2, W + 5 * G.n2};
+  int valid = 0;          // deep: ghost rows that still hold the owner's bits
+  if (deep) {
+    if (getenv("POP_B200_TRACE")) fprintf(stderr, "[pop_b200] rank %d: P-CSI on deep strips, %d ghost rows\n", G.rank, gd);
+    POP_TRY(deep_prepare(gd));
+    nyv = DB.nyd; n2v = DB.n2d; je0 = gd + G.ny_local - 1; jglob = DB.jglob;
+    const double* srcs[8] = {view.C, view.N, view.E, view.NE, view.mask, B, Xb[0], Qb[0]};
+    for (int l = 0; l < 8; l++) POP_TRY(deep_load(l, srcs[l]));
+    POP_TRY(halo_exchange_deep(DB.buf, 8, gd, DB.n2d));
+    POP_CHECK_CUDA(cudaMemcpyAsync(DB.buf + DL_X1 * DB.n2d, DB.buf + DL_X0 * DB.n2d, sizeof(double) * 2 * DB.n2d,
+                                   cudaMemcpyDeviceToDevice, G.stream));
+    view.nyb = DB.nyd; view.jb = gd + 1;
+    view.C = DB.buf + DL_C * DB.n2d; view.N = DB.buf + DL_N * DB.n2d; view.E = DB.buf + DL_E * DB.n2d;
+    view.NE = DB.buf + DL_NE * DB.n2d; view.mask = DB.buf + DL_MASK * DB.n2d;
+    B = DB.buf + DL_B * DB.n2d;
+    Xb[0] = DB.buf + DL_X0 * DB.n2d; Qb[0] = DB.buf + DL_Q0 * DB.n2d;
+    Xb[1] = DB.buf + DL_X1 * DB.n2d; Qb[1] = DB.buf + DL_Q1 * DB.n2d;
+    snap[0] = DB.buf + DL_SNAP0 * DB.n2d; snap[1] = DB.buf + DL_SNAP1 * DB.n2d;
+    valid = gd;
+  }
+  // rows the tile pass may write: on the last strip the rows above the top physical row belong to the fold (or are
+  // closed-boundary zeros)
+  const int jw_max = (deep && G.rank == G.nranks - 1) ? je0 : nyv - POP_NGHOST - 1;
+  const dim3 grid1((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((nyv + PC_TY - 1) / PC_TY), 1);
+  const dim3 grid2((unsigned)((G.nxg + P2_TX - 1) / P2_TX), (unsigned)((nyv - 2 * POP_NGHOST + P2_TY - 1) / P2_TY), 1);
   const int nblk1 = (int)(grid1.x * grid1.y), nblk2 = (int)(grid2.x * grid2.y);
   POP_TRY(reduce_reserve_partials(nblk1 > nblk2 ? nblk1 : nblk2));
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
-  const bool blocking = !G.no_pcsi_blocking;
   // opt-in (POP_B200_OVERLAP_EXCHANGE=1): boundary tile rows first, strip exchange concurrent with the interior tiles
-  const bool xover = blocking && G.overlap_exchange && G.nranks > 1 && G.p2p_on && grid2.y >= 3 &&
+  const bool xover = !deep && blocking && G.overlap_exchange && G.nranks > 1 && G.p2p_on && grid2.y >= 3 &&
                      G.cfg.ew_boundary_type == POP_BNDY_CYCLIC;
   // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
   // and a host round trip on every rank, so its verdict is read one check period LATER, when it has long
   // arrived; X_m of the check is kept in a snapshot, and when a check turns out to have converged the answer
   // is that snapshot and numIterations is that m -- the same bits as stopping immediately, a few passes late.
   const bool lagged = (G.nranks > 1) && !(getenv("POP_B200_SYNC_CHECKS") && getenv("POP_B200_SYNC_CHECKS")[0] == '1');
-  double* snap[2] = {W + 4 * G.n2, W + 5 * G.n2};
   struct { bool valid; int m, slot; } pend = {false, 0, 0};
   const double* result = nullptr;
   if (lagged && !G.ev_chk[0]) {
@@ -1055,12 +1161,12 @@ static int pcsi(double* X, const double* B) {
   PopTmap tmXb[2], tmQb[2], tmC, tmB, tmN, tmE, tmNE;
   bool use_tma = blocking && !G.no_tma;
   if (use_tma) {
-    const BtView bv = bt_view();
-    use_tma = make_tmap_2d(&tmXb[0], Xb[0], P2_XW, P2_TY + 4) && make_tmap_2d(&tmXb[1], Xb[1], P2_XW, P2_TY + 4) &&
-              make_tmap_2d(&tmQb[0], Qb[0], P2_XW, P2_TY + 2) && make_tmap_2d(&tmQb[1], Qb[1], P2_XW, P2_TY + 2) &&
-              make_tmap_2d(&tmC, bv.C, P2_XW, P2_TY + 2) && make_tmap_2d(&tmB, B, P2_XW, P2_TY + 2) &&
-              make_tmap_2d(&tmN, bv.N, P2_XW, P2_TY + 3) && make_tmap_2d(&tmE, bv.E, P2_XW, P2_TY + 2) &&
-              make_tmap_2d(&tmNE, bv.NE, P2_XW, P2_TY + 3);
+    const BtView& bv = view;
+    use_tma = make_tmap_2d(&tmXb[0], Xb[0], P2_XW, P2_TY + 4, nyv) && make_tmap_2d(&tmXb[1], Xb[1], P2_XW, P2_TY + 4, nyv) &&
+              make_tmap_2d(&tmQb[0], Qb[0], P2_XW, P2_TY + 2, nyv) && make_tmap_2d(&tmQb[1], Qb[1], P2_XW, P2_TY + 2, nyv) &&
+              make_tmap_2d(&tmC, bv.C, P2_XW, P2_TY + 2, nyv) && make_tmap_2d(&tmB, B, P2_XW, P2_TY + 2, nyv) &&
+              make_tmap_2d(&tmN, bv.N, P2_XW, P2_TY + 3, nyv) && make_tmap_2d(&tmE, bv.E, P2_XW, P2_TY + 2, nyv) &&
+              make_tmap_2d(&tmNE, bv.NE, P2_XW, P2_TY + 3, nyv);
   }
 #ifndef POP_EMUL
   if (blocking) {
@@ -1077,16 +1183,21 @@ static int pcsi(double* X, const double* B) {
     int adv;  // iterations this pass advances X by
     int nblk;
     if (blocking && m + 2 <= maxIt && !next_is_check) {
+      if (deep && valid < 2) {  // the next pass consumes two ghost rows
+        POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
+        valid = gd;
+      }
       Pcsi2Args a;
-      a.v = bt_view();
+      a.v = view;
+      a.deep = deep ? 1 : 0; a.jw_max = jw_max;
       a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[cur ^ 1]; a.Qn = Qb[cur ^ 1];
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
       a.om1 = csomga; a.c11 = csy * csomga - 1.0;
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+2}
       a.om2 = csomga; a.c12 = csy * csomga - 1.0;
       a.partials = G.d_partials_big;
-      a.do_ew = do_ew; a.do_tripole = do_tp; a.je0 = G.je - 1; a.nxg = G.nxg;
-      a.iglob = G.d_iglob; a.jglob = G.d_jglob;
+      a.do_ew = do_ew; a.do_tripole = do_tp; a.je0 = je0; a.nxg = G.nxg;
+      a.iglob = G.d_iglob; a.jglob = jglob;
       a.use_tma = use_tma ? 1 : 0;
       a.rowsel = 0; a.row0 = 0; a.nty = (int)grid2.y;
       if (use_tma) {
@@ -1125,26 +1236,32 @@ static int pcsi(double* X, const double* B) {
         }
         if (sample) G.timer_suppress++;
       }
-      POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+      if (deep) valid -= 2;
+      else POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = 2;
       nblk = nblk2;
       }
     } else {
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
+      if (deep && valid < 1) {
+        POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
+        valid = gd;
+      }
       PcsiArgs a;
-      a.v = bt_view();
+      a.v = view;
       a.X = Xb[cur]; a.Xn = Xb[cur ^ 1]; a.Q = Qb[cur]; a.Qn = Qb[cur ^ 1]; a.B = B;
       a.om = csomga; a.c1 = csy * csomga - 1.0;
       a.advance = (m < maxIt) ? 1 : 0;
       a.partials = G.d_partials_big;
       // one rank: the pass itself fills the ghost cells it can map to a source cell (east-west wrap, tripole
       // fold); north-south cyclic rows come from the halo update like the rows of a neighbouring strip
-      a.map_ghost = (G.nranks == 1 && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC) ? 1 : 0;
+      a.map_ghost = (deep || (G.nranks == 1 && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC)) ? 1 : 0;
       a.do_ew = do_ew; a.do_tripole = do_tp;
-      a.je0 = G.je - 1; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = G.d_jglob;
+      a.je0 = je0; a.nxg = G.nxg; a.iglob = G.d_iglob; a.jglob = jglob;
       if (check) POP_LAUNCH_PDL(pcsi_iter_kernel<true>, grid1, PC_TX * PC_TY, 0, a);
       else POP_LAUNCH_PDL(pcsi_iter_kernel<false>, grid1, PC_TX * PC_TY, 0, a);
-      if (a.advance && !a.map_ghost)
+      if (deep) valid -= a.advance;
+      else if (a.advance && !a.map_ghost)
         POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = a.advance;
       nblk = nblk1;
@@ -1168,7 +1285,7 @@ static int pcsi(double* X, const double* B) {
       const int slot = pend.valid ? (pend.slot ^ 1) : 0;
       POP_TRY(reduce_finish_n(1, RED_POST_RR, nullptr, G.d_partials_big, nblk));
       POP_CHECK_CUDA(cudaMemcpyAsync(G.h_sums + 2 + slot, G.d_sums, sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-      POP_CHECK_CUDA(cudaMemcpyAsync(snap[slot], Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+      POP_CHECK_CUDA(cudaMemcpyAsync(snap[slot], Xb[cur], sizeof(double) * n2v, cudaMemcpyDeviceToDevice, G.stream));
       POP_CHECK_CUDA(cudaEventRecord(G.ev_chk[slot], G.stream));
       pend.valid = true; pend.m = m; pend.slot = slot;
     }
@@ -1184,7 +1301,12 @@ static int pcsi(double* X, const double* B) {
     }
   }
   // the answer is X_m of the converged (or last) residual evaluation
-  POP_CHECK_CUDA(cudaMemcpyAsync(X, result ? result : Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  if (deep) {  // physical rows back to the caller's strip; its ghost cells as a halo update leaves them
+    POP_TRY(deep_store(X, result ? result : Xb[cur]));
+    POP_TRY(bt_halo(X));
+  } else {
+    POP_CHECK_CUDA(cudaMemcpyAsync(X, result ? result : Xb[cur], sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  }
   G.rmsResidual = sqrt(rr * G.residualNorm);
   return pop_post_launch("PCSI");  // PCSI returns silently when not converged (:1828-1830)
 }

@@ -310,7 +310,12 @@ extern "C" int pop_init(const pop_config* cfg) {
   // programmatic dependent launch pays when the per-rank kernels are short (A/B in profiles/r1_ncu_summary.md: -7 %
   // solver time on a 3600x300 strip, +1 % on the full 3600x2400 grid where the early CTAs compete with the
   // overlapped velocity-finish kernel): on for strips up to 2.5 M points, POP_B200_PDL=1 / POP_B200_NO_PDL=1 override
-  G.no_pdl = (size_t)G.nxg * (size_t)(G.nyg / G.nranks) > 2500000;
+  // (round 2: with the velocity finish after the solve nothing competes any more, and the full grid gains 3 % too)
+  G.no_pdl = (G.finish_mode == 1) && (size_t)G.nxg * (size_t)(G.nyg / G.nranks) > 2500000;
+  G.deep_halo = 12;
+  if (const char* e = getenv("POP_B200_DEEP_HALO")) G.deep_halo = atoi(e);
+  if (getenv("POP_B200_NO_DEEP_HALO") != nullptr && getenv("POP_B200_NO_DEEP_HALO")[0] == '1') G.deep_halo = 0;
+  G.deep_force = getenv("POP_B200_DEEP_HALO_FORCE") != nullptr && getenv("POP_B200_DEEP_HALO_FORCE")[0] == '1';
   if (getenv("POP_B200_PDL") != nullptr && getenv("POP_B200_PDL")[0] == '1') G.no_pdl = false;
   if (getenv("POP_B200_NO_PDL") != nullptr && getenv("POP_B200_NO_PDL")[0] == '1') G.no_pdl = true;
   POP_REQUIRE(cfg->ns_boundary_type != POP_BNDY_TRIPOLE || cfg->ew_boundary_type == POP_BNDY_CYCLIC,
@@ -370,6 +375,7 @@ extern "C" int pop_finalize(void) {
   if (G.stream_x) cudaStreamSynchronize(G.stream_x);
   p2p_teardown();
   evp_release();
+  deep_release();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();
   for (auto& kv : G.stage) cudaFree(kv.second.first);
@@ -565,11 +571,11 @@ bool make_tmap_box(PopTmap* out, const double* field, int nlev, int boxw, int bo
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
-bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh) {
+bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh, int nrows) {
   // encoded as a one-level 3-d tensor (the form the column kernels use): box boxw x boxh x 1
   EncodeTiledFn enc = get_encode();
   if (!enc || !field || (G.nxb % 2) != 0 || (boxw % 2) != 0 || boxw > 256 || boxh > 256) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)G.nxb, (cuuint64_t)G.nyb, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)G.nxb, (cuuint64_t)(nrows > 0 ? nrows : G.nyb), 1};
   cuuint64_t strides[2] = {(cuuint64_t)G.nxb * 8, (cuuint64_t)G.n2 * 8};
   cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -591,9 +597,9 @@ bool make_tmap_box(PopTmap* out, const double* field, int nlev, int boxw, int bo
   out->bw = boxw; out->bh = boxh;
   return true;
 }
-bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh) {
+bool make_tmap_2d(PopTmap* out, const double* field, int boxw, int boxh, int nrows) {
   if (!field || (G.nxb % 2) != 0 || (boxw % 2) != 0) return false;
-  out->p = field; out->nx = G.nxb; out->ny = G.nyb; out->nz = 1;
+  out->p = field; out->nx = G.nxb; out->ny = nrows > 0 ? nrows : G.nyb; out->nz = 1;
   out->bw = boxw; out->bh = boxh;
   return true;
 }

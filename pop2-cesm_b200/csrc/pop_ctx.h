@@ -74,6 +74,10 @@ struct Ctx {
   // (POP_B200_OVERLAP_FINISH=1, the round-1 layout); 2 = inside baroclinic_driver (POP_B200_NO_OVERLAP=1)
   int finish_mode = 0;
   bool overlap_exchange = false;  // POP_B200_OVERLAP_EXCHANGE=1 (opt-in): P-CSI boundary tiles first, exchange under the interior
+  // P-CSI on deep strips (P > 1): ghost depth in rows (0: off; POP_B200_DEEP_HALO=<rows>, POP_B200_NO_DEEP_HALO=1);
+  // deep_force (POP_B200_DEEP_HALO_FORCE=1) runs the deep layout on one rank too (test aid)
+  int deep_halo = 12;
+  bool deep_force = false;
   cudaStream_t stream_x = nullptr;
   cudaEvent_t ev_xb = nullptr, ev_xx = nullptr;
   bool no_pdl = false;      // POP_B200_NO_PDL=1: plain stream-ordered launches in the P-CSI loop
@@ -261,6 +265,7 @@ int halo_update(double* a, int nz, int loc, int kind, double fill);
 int halo_update_i4(int* a, int nz, int loc, int kind, int fill);
 int halo_update_r4(float* a, int nz, int loc, int kind, float fill);
 int halo_rows_only(double* a, int nz);
+int halo_exchange_deep(double* a, int nz, int gd, size_t n2d);  // strip exchange of the solver's deep strips
 int halo_exchange_rows(double* a, int nz);  // peer-memory exchange of centre-scalar rows without the wrap of own rows
 int halo_ew_own_rows(double* a, int nz);    // the deferred east-west wrap
 int comm_init(int rank, int nranks, const char* id128);
@@ -330,6 +335,7 @@ int solvers_init_dev();
 int solvers_prep_dev();
 int solvers_evp_diagnostics(int* nsub, int* nland, double* selfcheck);
 void evp_release();
+void deep_release();
 int solvers_diagonal_dev(const double* diagCorr);
 int solvers_run_dev(double* X, const double* B);
 int btrop_operator_dev(double* AX, const double* X);

@@ -193,11 +193,12 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
                 unsigned long long* flagAtS, unsigned long long* flagAtN, const double* __restrict__ fromS,
                 const double* __restrict__ fromN, volatile unsigned long long* myFlags,
                 unsigned long long seq, unsigned int* counter, int* err, int fuse_ew, int fuse_tripole, int nyb,
-                int je0, const int* __restrict__ iglob, const int* __restrict__ jglob, long long spin_limit) {
+                int je0, const int* __restrict__ iglob, const int* __restrict__ jglob, long long spin_limit, int nr) {
+  // nr: rows per side and level (2 for a halo update; the ghost depth of the solver's deep strips otherwise)
   __shared__ int s_ok;
   pdl_wait();
   pdl_trigger();
-  const size_t n = (size_t)nz * 2 * nxg;
+  const size_t n = (size_t)nz * nr * nxg;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // centre scalars: the east-west wrap of the rows this rank owns and the tripole fold only read physical
   // cells and only write ghost cells, so they ride along before the wait (halo_center_scalar_local)
@@ -227,8 +228,8 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
   }
   // ---- push
   for (size_t p = t0; p < n; p += stride) {
-    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
-    const size_t z = p / ((size_t)2 * nxg);
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % nr);
+    const size_t z = p / ((size_t)nr * nxg);
     const double* az = a + z * n2 + POP_NGHOST + ig;
     if (toS) toS[p] = az[(size_t)(rowS + r) * nxb];
     if (toN) toN[p] = az[(size_t)(rowN + r) * nxb];
@@ -258,8 +259,8 @@ halo_p2p_kernel(double* __restrict__ a, int nz, int nxb, size_t n2, int nxg, int
   if (!s_ok) return;  // timed out: leave the ghost rows alone rather than consume a stale mailbox
   // ---- pull
   for (size_t p = t0; p < n; p += stride) {
-    const int ig = (int)(p % nxg), r = (int)((p / nxg) % 2);
-    const size_t z = p / ((size_t)2 * nxg);
+    const int ig = (int)(p % nxg), r = (int)((p / nxg) % nr);
+    const size_t z = p / ((size_t)nr * nxg);
     double* az = a + z * n2 + POP_NGHOST + ig;
     if (fromS) {
       const double v = __ldcv(fromS + p);
@@ -333,6 +334,8 @@ int p2p_setup() {
   const int north = (G.rank < G.nranks - 1) ? G.rank + 1 : (ns == POP_BNDY_CYCLIC ? 0 : -1);
   const int nzmax = G.km * G.nt > G.km + 2 ? G.km * G.nt : G.km + 2;
   G.p2p_cap = (size_t)nzmax * 2 * G.nxg;
+  // the solver's deep strips exchange eight levels of deep_halo rows at a time (pop_barotropic.cu)
+  if (G.deep_halo > 0 && (size_t)8 * G.deep_halo * G.nxg > G.p2p_cap) G.p2p_cap = (size_t)8 * G.deep_halo * G.nxg;
   const size_t bytes = (4 * G.p2p_cap + 2) * sizeof(double);
   // every step below is collective; a rank that fails still takes part and the verdict is agreed with a
   // min-reduction so that all ranks choose the same path
@@ -478,7 +481,7 @@ static int halo_update_t(T* a, int nz, int loc, int kind, T fill, bool rows_only
       const int f_tp = (cs && ns == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1 && !rows_only) ? 1 : 0;
       POP_LAUNCH_PDL(halo_p2p_kernel, grid, POP_EW_THREADS, 0, (double*)a, nz, nxb, n2, nxg, G.jb - 1, G.je - 2, 0, G.je,
                  toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter,
-                 G.p2p_err, f_ew, f_tp, nyb, G.je - 1, G.d_iglob, G.d_jglob, p2p_spin_cycles());
+                 G.p2p_err, f_ew, f_tp, nyb, G.je - 1, G.d_iglob, G.d_jglob, p2p_spin_cycles(), 2);
       if (cs) return pop_post_launch("halo_update");  // wrap and fold were fused into the exchange
     } else {
     const size_t msg_d = (msg * sizeof(T) + sizeof(double) - 1) / sizeof(double);
@@ -554,6 +557,42 @@ int halo_rows_only(double* a, int nz) {
 int halo_exchange_rows(double* a, int nz) {
   POP_REQUIRE(G.nranks > 1 && G.p2p_on, "halo_exchange_rows: needs the peer-memory path");
   return halo_update_t<double>(a, nz, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0, false, 1);
+}
+// Strip exchange of the solver's deep strips (pop_barotropic.cu): `a` holds nz levels of nyd = ny_local + 2*gd rows
+// (level stride n2d); the gd ghost rows on either side receive the neighbour's gd outermost physical rows, east-west
+// ghost columns included.  Same mailboxes, flags and sequence numbers as the two-row exchange.
+int halo_exchange_deep(double* a, int nz, int gd, size_t n2d) {
+  if (G.nranks <= 1) return POP_SUCCESS;  // no neighbour strips (the single-rank test mode of the deep layout)
+#ifndef POP_EMUL
+  const int ns = G.cfg.ns_boundary_type;
+  POP_REQUIRE(G.p2p_on && ns != POP_BNDY_CYCLIC, "halo_exchange_deep: needs the peer-memory path");
+  const size_t msg = (size_t)nz * gd * G.nxg;
+  POP_REQUIRE(msg <= G.p2p_cap, "halo_exchange_deep: message exceeds the mailbox");
+  ScopedTimer tm("HALO");
+  const int south = (G.rank > 0) ? G.rank - 1 : -1, north = (G.rank < G.nranks - 1) ? G.rank + 1 : -1;
+  const unsigned long long seq = ++G.p2p_seq;
+  const size_t par = (size_t)(seq & 1ull);
+  double* mb = G.p2p_mbox;
+  unsigned long long* myFlags = (unsigned long long*)(mb + 4 * G.p2p_cap);
+  double* toS = south >= 0 ? G.p2p_peerS + (par * 2 + 1) * G.p2p_cap : nullptr;
+  double* toN = north >= 0 ? G.p2p_peerN + (par * 2 + 0) * G.p2p_cap : nullptr;
+  unsigned long long* fS = south >= 0 ? (unsigned long long*)(G.p2p_peerS + 4 * G.p2p_cap) + 1 : nullptr;
+  unsigned long long* fN = north >= 0 ? (unsigned long long*)(G.p2p_peerN + 4 * G.p2p_cap) + 0 : nullptr;
+  const double* fromS = south >= 0 ? mb + (par * 2 + 0) * G.p2p_cap : nullptr;
+  const double* fromN = north >= 0 ? mb + (par * 2 + 1) * G.p2p_cap : nullptr;
+  unsigned grid = ew_grid(msg);
+  const unsigned wave = (unsigned)G.sm_count * 2;
+  if (grid > wave) grid = wave;
+  const int f_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 2 : 0;  // wrap of the pulled rows only
+  const int nyd = G.ny_local + 2 * gd;
+  POP_LAUNCH_PDL(halo_p2p_kernel, grid, POP_EW_THREADS, 0, a, nz, G.nxb, n2d, G.nxg, gd, G.ny_local, 0, gd + G.ny_local,
+                 toS, toN, fS, fN, fromS, fromN, (volatile unsigned long long*)myFlags, seq, G.p2p_counter, G.p2p_err,
+                 f_ew, 0, nyd, gd + G.ny_local - 1, G.d_iglob, G.d_jglob, p2p_spin_cycles(), gd);
+  return pop_post_launch("halo_exchange_deep");
+#else
+  (void)a; (void)nz; (void)gd; (void)n2d;
+  POP_REQUIRE(false, "halo_exchange_deep: more than one rank in the emulator build");
+#endif
 }
 int halo_ew_own_rows(double* a, int nz) {
   const size_t n = (size_t)nz * G.nyb * 4;

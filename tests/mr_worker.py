@@ -36,6 +36,10 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     which = sys.argv[1] if len(sys.argv) > 1 else "pcsi"
     kw = dict(nx=96, ny=64, km=6, seed=81)
+    if which in ("pcsi22", "pcsi_plain"):
+        # the P-CSI passes run on deep strips by default (12 ghost rows); also 22 rows deep, and the plain layout
+        os.environ.update({"POP_B200_DEEP_HALO": "22"} if which == "pcsi22" else {"POP_B200_NO_DEEP_HALO": "1"})
+        which = "pcsi"
     if which == "pcsi":
         kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
                   lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21, given_vmix=True,

@@ -275,6 +275,34 @@ def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypa
     assert relerr(res["blocked"][1], oracle_global(o, "PSURF", c.TIME_CUR)) <= 2.0e-12
 
 
+@pytest.mark.parametrize("ns,ny,depth", [(c.BNDY_TRIPOLE, 90, "12"), (c.BNDY_TRIPOLE, 87, "22"), (c.BNDY_CLOSED, 64, "12")])
+def test_pcsi_deep_strip_layout_is_bitwise_the_plain_solver(monkeypatch, ns, ny, depth):
+    """The P-CSI passes of the multi-rank solver run on strips with a deep ghost zone (one strip exchange per `depth`
+    iterations instead of one per pass; ghost cells with a source in the same strip -- east-west wrap, tripole fold --
+    written by the pass itself).  POP_B200_DEEP_HALO_FORCE runs that layout on one rank, where everything but the peer
+    exchange is exercised: same bits, same iteration counts as the plain layout."""
+    cs = make_case(200, ny, 5, seed=73, ns=ns, hmix_tracer_itype=c.HMIX_DEL4,
+                   hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21,
+                   given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
+    res = {}
+    monkeypatch.setenv("POP_B200_DEEP_HALO", depth)
+    for tag, env in (("plain", "0"), ("deep", "1")):
+        monkeypatch.setenv("POP_B200_DEEP_HALO_FORCE", env)
+        p = load_pop(cs)
+        try:
+            its = []
+            for ts in (c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG):
+                p.step(ts)
+                its.append(p.solvers_get_diagnostics()[0])
+            res[tag] = (its, {n: pop_global(p, n, c.TIME_CUR) for n in PROG})
+        finally:
+            p.finalize()
+    assert res["plain"][0] == res["deep"][0]
+    assert min(res["plain"][0]) >= 60
+    for n in PROG:
+        assert np.array_equal(res["plain"][1][n], res["deep"][1][n]), n
+
+
 @pytest.mark.parametrize("flags", [("POP_B200_NO_TMA",), ("POP_B200_NO_FAST_TRACER",), ("POP_B200_NO_OVERLAP",),
                                    ("POP_B200_NO_TMA", "POP_B200_NO_OVERLAP"), ("POP_B200_OVERLAP_FINISH",),
                                    ("POP_B200_THOMAS_TMA",)])
