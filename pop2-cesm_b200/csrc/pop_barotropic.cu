@@ -1031,13 +1031,13 @@ static int pcsi_evp(double* X, const double* B) {
 // source in the same strip (east-west wrap, tripole fold) are written by the pass itself.  gd = 2 + a multiple of
 // the tile height keeps the tiles -- and with them the order of the residual sum -- those of the plain layout.
 struct DeepBt {
-  double* buf = nullptr;  // levels: C N E NE mask B X0 Q0 X1 Q1 snap0 snap1
+  double* buf = nullptr;  // levels: C N E NE mask B X0 Q0 X1 Q1 X2 Q2
   int* jglob = nullptr;
   int gd = 0, nyd = 0;
   size_t n2d = 0;
 };
 static DeepBt DB;
-enum { DL_C = 0, DL_N, DL_E, DL_NE, DL_MASK, DL_B, DL_X0, DL_Q0, DL_X1, DL_Q1, DL_SNAP0, DL_SNAP1, DL_COUNT };
+enum { DL_C = 0, DL_N, DL_E, DL_NE, DL_MASK, DL_B, DL_X0, DL_Q0, DL_X1, DL_Q1, DL_X2, DL_Q2, DL_COUNT };
 void deep_release() {
   cudaFree(DB.buf);
   cudaFree(DB.jglob);
@@ -1079,8 +1079,8 @@ static int pcsi(double* X, const double* B) {
   const int maxIt = G.cfg.max_iterations, freq = G.cfg.convergence_check_freq,
             start = G.cfg.convergence_check_start;
   double *R = fld("BT_R"), *A0R = fld("BT_A0R");
-  double* W = fld("BT_PCSI");  // [X0, Q0, X1, Q1]: (X,Q) pairs are 2-level fields for the halo pass
-  double *Xb[2] = {W, W + 2 * G.n2}, *Qb[2] = {W + G.n2, W + 3 * G.n2};
+  double* W = fld("BT_PCSI");  // [X0, Q0, X1, Q1, X2, Q2]: (X,Q) pairs are 2-level fields for the halo pass
+  double *Xb[3] = {W, W + 2 * G.n2, W + 4 * G.n2}, *Qb[3] = {W + G.n2, W + 3 * G.n2, W + 5 * G.n2};
   double rr = 0.0;
   const double csalpha = 2.0 / (G.pcsiMaxEigs - G.pcsiMinEigs);
   const double csbeta = (G.pcsiMaxEigs + G.pcsiMinEigs) / (G.pcsiMaxEigs - G.pcsiMinEigs);
@@ -1100,8 +1100,9 @@ static int pcsi(double* X, const double* B) {
   csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));
   POP_CHECK_CUDA(cudaMemcpyAsync(Xb[0], X, sizeof(double) * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   bt_ew<EW_PCSI_QX>(Q, Xb[0], R, nullptr, nullptr, nullptr, nullptr, csomga, csy * csomga - 1.0);
-  // the other pair starts as a copy so that cells no pass writes (closed-boundary ghost rows) agree
+  // the other pairs start as copies so that cells no pass writes (closed-boundary ghost rows) agree
   POP_CHECK_CUDA(cudaMemcpyAsync(Xb[1], Xb[0], sizeof(double) * 2 * G.n2, cudaMemcpyDeviceToDevice, G.stream));
+  POP_CHECK_CUDA(cudaMemcpyAsync(Xb[2], Xb[0], sizeof(double) * 2 * G.n2, cudaMemcpyDeviceToDevice, G.stream));
   G.numIterations = maxIt;
   const bool blocking = !G.no_pcsi_blocking;
   // deep strips: see DeepBt.  Needs the peer-memory exchange, a closed or tripole north-south boundary and strips
@@ -1113,25 +1114,24 @@ static int pcsi(double* X, const double* B) {
   const int* jglob = G.d_jglob;
   int nyv = G.nyb;        // rows of the arrays the passes work on
   int je0 = G.je - 1;     // 0-based last physical row
-  size_t n2v = G.n2;
-  double* snap[2] = {W + 4 * G.n2, W + 5 * G.n2};
   int valid = 0;          // deep: ghost rows that still hold the owner's bits
   if (deep) {
     if (getenv("POP_B200_TRACE")) fprintf(stderr, "[pop_b200] rank %d: P-CSI on deep strips, %d ghost rows\n", G.rank, gd);
     POP_TRY(deep_prepare(gd));
-    nyv = DB.nyd; n2v = DB.n2d; je0 = gd + G.ny_local - 1; jglob = DB.jglob;
+    nyv = DB.nyd; je0 = gd + G.ny_local - 1; jglob = DB.jglob;
     const double* srcs[8] = {view.C, view.N, view.E, view.NE, view.mask, B, Xb[0], Qb[0]};
     for (int l = 0; l < 8; l++) POP_TRY(deep_load(l, srcs[l]));
     POP_TRY(halo_exchange_deep(DB.buf, 8, gd, DB.n2d));
-    POP_CHECK_CUDA(cudaMemcpyAsync(DB.buf + DL_X1 * DB.n2d, DB.buf + DL_X0 * DB.n2d, sizeof(double) * 2 * DB.n2d,
-                                   cudaMemcpyDeviceToDevice, G.stream));
+    for (int l = DL_X1; l <= DL_X2; l += 2)
+      POP_CHECK_CUDA(cudaMemcpyAsync(DB.buf + l * DB.n2d, DB.buf + DL_X0 * DB.n2d, sizeof(double) * 2 * DB.n2d,
+                                     cudaMemcpyDeviceToDevice, G.stream));
     view.nyb = DB.nyd; view.jb = gd + 1;
     view.C = DB.buf + DL_C * DB.n2d; view.N = DB.buf + DL_N * DB.n2d; view.E = DB.buf + DL_E * DB.n2d;
     view.NE = DB.buf + DL_NE * DB.n2d; view.mask = DB.buf + DL_MASK * DB.n2d;
     B = DB.buf + DL_B * DB.n2d;
     Xb[0] = DB.buf + DL_X0 * DB.n2d; Qb[0] = DB.buf + DL_Q0 * DB.n2d;
     Xb[1] = DB.buf + DL_X1 * DB.n2d; Qb[1] = DB.buf + DL_Q1 * DB.n2d;
-    snap[0] = DB.buf + DL_SNAP0 * DB.n2d; snap[1] = DB.buf + DL_SNAP1 * DB.n2d;
+    Xb[2] = DB.buf + DL_X2 * DB.n2d; Qb[2] = DB.buf + DL_Q2 * DB.n2d;
     valid = gd;
   }
   // rows the tile pass may write: on the last strip the rows above the top physical row belong to the fold (or are
@@ -1148,21 +1148,29 @@ static int pcsi(double* X, const double* B) {
                      G.cfg.ew_boundary_type == POP_BNDY_CYCLIC;
   // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
   // and a host round trip on every rank, so its verdict is read one check period LATER, when it has long
-  // arrived; X_m of the check is kept in a snapshot, and when a check turns out to have converged the answer
-  // is that snapshot and numIterations is that m -- the same bits as stopping immediately, a few passes late.
-  const bool lagged = (G.nranks > 1) && !(getenv("POP_B200_SYNC_CHECKS") && getenv("POP_B200_SYNC_CHECKS")[0] == '1');
-  struct { bool valid; int m, slot; } pend = {false, 0, 0};
+  // arrived; X_m of the check is kept (its buffer pair sits out of the rotation), and when a check turns out to have
+  // converged the answer is that X_m and numIterations is that m -- the same bits as stopping immediately, a few
+  // passes late.
+  // (POP_B200_SYNC_CHECKS=1: immediate verdicts on P ranks too; POP_B200_LAGGED_CHECKS=1: lagged on one rank, a test aid)
+  const bool lagged = ((G.nranks > 1) && !(getenv("POP_B200_SYNC_CHECKS") && getenv("POP_B200_SYNC_CHECKS")[0] == '1')) ||
+                      (getenv("POP_B200_LAGGED_CHECKS") && getenv("POP_B200_LAGGED_CHECKS")[0] == '1');
+  struct { bool valid; int m, slot, buf; } pend = {false, 0, 0, -1};
   const double* result = nullptr;
   if (lagged && !G.ev_chk[0]) {
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_chk[0], cudaEventDisableTiming));
     POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_chk[1], cudaEventDisableTiming));
+    POP_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_chk_go, cudaEventDisableTiming));
+    int lo = 0, hi = 0;
+    POP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream_chk, cudaStreamNonBlocking, hi));
   }
   // tensor maps of the staged tiles (X and Q for both buffers); without TMA the kernel stages with cp.async
-  PopTmap tmXb[2], tmQb[2], tmC, tmB, tmN, tmE, tmNE;
+  PopTmap tmXb[3], tmQb[3], tmC, tmB, tmN, tmE, tmNE;
   bool use_tma = blocking && !G.no_tma;
   if (use_tma) {
     const BtView& bv = view;
     use_tma = make_tmap_2d(&tmXb[0], Xb[0], P2_XW, P2_TY + 4, nyv) && make_tmap_2d(&tmXb[1], Xb[1], P2_XW, P2_TY + 4, nyv) &&
+              make_tmap_2d(&tmXb[2], Xb[2], P2_XW, P2_TY + 4, nyv) && make_tmap_2d(&tmQb[2], Qb[2], P2_XW, P2_TY + 2, nyv) &&
               make_tmap_2d(&tmQb[0], Qb[0], P2_XW, P2_TY + 2, nyv) && make_tmap_2d(&tmQb[1], Qb[1], P2_XW, P2_TY + 2, nyv) &&
               make_tmap_2d(&tmC, bv.C, P2_XW, P2_TY + 2, nyv) && make_tmap_2d(&tmB, B, P2_XW, P2_TY + 2, nyv) &&
               make_tmap_2d(&tmN, bv.N, P2_XW, P2_TY + 3, nyv) && make_tmap_2d(&tmE, bv.E, P2_XW, P2_TY + 2, nyv) &&
@@ -1175,7 +1183,10 @@ static int pcsi(double* X, const double* B) {
     POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)pcsi_iter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   }
 #endif
-  int cur = 0;  // (X_m, Q_m) live in (Xb[cur], Qb[cur])
+  // (X_m, Q_m) live in pair `cur`, a pass writes pair `nxt`.  With lagged checks X_m of a check must outlive its
+  // verdict: the pair is simply retired from the rotation until then (`held`: at most one at a time besides the one
+  // whose verdict is being awaited), so three pairs suffice and nothing is copied.
+  int cur = 0, nxt = 1, held = -1;
   int m = 1, npass = 0;
   while (m <= maxIt) {
     const bool check = (m % freq == 0) && (m >= start);
@@ -1183,6 +1194,7 @@ static int pcsi(double* X, const double* B) {
     int adv;  // iterations this pass advances X by
     int nblk;
     if (blocking && m + 2 <= maxIt && !next_is_check) {
+      if (check && lagged && pend.valid) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_chk[pend.slot], 0));
       if (deep && valid < 2) {  // the next pass consumes two ghost rows
         POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
         valid = gd;
@@ -1190,7 +1202,7 @@ static int pcsi(double* X, const double* B) {
       Pcsi2Args a;
       a.v = view;
       a.deep = deep ? 1 : 0; a.jw_max = jw_max;
-      a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[cur ^ 1]; a.Qn = Qb[cur ^ 1];
+      a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[nxt]; a.Qn = Qb[nxt];
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
       a.om1 = csomga; a.c11 = csy * csomga - 1.0;
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+2}
@@ -1215,12 +1227,12 @@ static int pcsi(double* X, const double* B) {
         else POP_LAUNCH(pcsi_iter2_kernel<false>, dim3(grid2.x, grid2.y - 2, 1), P2_NT, smem2, a);
         POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_x, G.ev_xb, 0));
         std::swap(G.stream, G.stream_x);
-        const int rcx = halo_exchange_rows(Xb[cur ^ 1], 2);
+        const int rcx = halo_exchange_rows(Xb[nxt], 2);
         std::swap(G.stream, G.stream_x);
         POP_TRY(rcx);
         POP_CHECK_CUDA(cudaEventRecord(G.ev_xx, G.stream_x));
         POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_xx, 0));
-        POP_TRY(halo_ew_own_rows(Xb[cur ^ 1], 2));  // east-west ghost columns of the rows the interior tiles wrote
+        POP_TRY(halo_ew_own_rows(Xb[nxt], 2));  // east-west ghost columns of the rows the interior tiles wrote
         adv = 2;
         nblk = nblk2;
       } else {
@@ -1237,19 +1249,20 @@ static int pcsi(double* X, const double* B) {
         if (sample) G.timer_suppress++;
       }
       if (deep) valid -= 2;
-      else POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+      else POP_TRY(halo_update(Xb[nxt], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = 2;
       nblk = nblk2;
       }
     } else {
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
+      if (check && lagged && pend.valid) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_chk[pend.slot], 0));
       if (deep && valid < 1) {
         POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
         valid = gd;
       }
       PcsiArgs a;
       a.v = view;
-      a.X = Xb[cur]; a.Xn = Xb[cur ^ 1]; a.Q = Qb[cur]; a.Qn = Qb[cur ^ 1]; a.B = B;
+      a.X = Xb[cur]; a.Xn = Xb[nxt]; a.Q = Qb[cur]; a.Qn = Qb[nxt]; a.B = B;
       a.om = csomga; a.c1 = csy * csomga - 1.0;
       a.advance = (m < maxIt) ? 1 : 0;
       a.partials = G.d_partials_big;
@@ -1262,7 +1275,7 @@ static int pcsi(double* X, const double* B) {
       else POP_LAUNCH_PDL(pcsi_iter_kernel<false>, grid1, PC_TX * PC_TY, 0, a);
       if (deep) valid -= a.advance;
       else if (a.advance && !a.map_ghost)
-        POP_TRY(halo_update(Xb[cur ^ 1], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+        POP_TRY(halo_update(Xb[nxt], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = a.advance;
       nblk = nblk1;
     }
@@ -1278,18 +1291,30 @@ static int pcsi(double* X, const double* B) {
         rr = G.h_sums[2 + pend.slot];
         if (rr < G.convergenceCriterion) {
           G.numIterations = pend.m;
-          result = snap[pend.slot];
+          result = Xb[pend.buf];
           break;
         }
       }
+      // the sum over tiles and ranks, the all-gather and the copy of the verdict to the host run on their own
+      // stream beside the following passes; X_m stays where it is (its pair leaves the rotation)
       const int slot = pend.valid ? (pend.slot ^ 1) : 0;
-      POP_TRY(reduce_finish_n(1, RED_POST_RR, nullptr, G.d_partials_big, nblk));
-      POP_CHECK_CUDA(cudaMemcpyAsync(G.h_sums + 2 + slot, G.d_sums, sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-      POP_CHECK_CUDA(cudaMemcpyAsync(snap[slot], Xb[cur], sizeof(double) * n2v, cudaMemcpyDeviceToDevice, G.stream));
-      POP_CHECK_CUDA(cudaEventRecord(G.ev_chk[slot], G.stream));
-      pend.valid = true; pend.m = m; pend.slot = slot;
+      POP_CHECK_CUDA(cudaEventRecord(G.ev_chk_go, G.stream));
+      POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_chk, G.ev_chk_go, 0));
+      std::swap(G.stream, G.stream_chk);
+      int rcc = reduce_finish_n(1, RED_POST_RR, nullptr, G.d_partials_big, nblk);
+      if (rcc == POP_SUCCESS &&
+          (cudaMemcpyAsync(G.h_sums + 2 + slot, G.d_sums, sizeof(double), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess ||
+           cudaEventRecord(G.ev_chk[slot], G.stream) != cudaSuccess))
+        rcc = POP_FAIL;
+      std::swap(G.stream, G.stream_chk);
+      POP_REQUIRE(rcc == POP_SUCCESS, "PCSI: convergence check could not be queued");
+      pend.valid = true; pend.m = m; pend.slot = slot; pend.buf = cur;
     }
-    if (adv) cur ^= 1;
+    if (adv) {  // rotate: the pair just read is free again unless a pending check holds it
+      const int old = cur;
+      cur = nxt;
+      nxt = (pend.valid && pend.buf == old) ? 3 - old - cur : old;
+    }
     m += (adv > 0) ? adv : 1;
   }
   if (lagged && !result && pend.valid) {  // the loop ran out: the last check may still have converged
@@ -1297,7 +1322,7 @@ static int pcsi(double* X, const double* B) {
     rr = G.h_sums[2 + pend.slot];
     if (rr < G.convergenceCriterion) {
       G.numIterations = pend.m;
-      result = snap[pend.slot];
+      result = Xb[pend.buf];
     }
   }
   // the answer is X_m of the converged (or last) residual evaluation

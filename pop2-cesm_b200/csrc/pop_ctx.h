@@ -68,6 +68,8 @@ struct Ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks
+  cudaEvent_t ev_chk_go = nullptr;
+  cudaStream_t stream_chk = nullptr;           // ... whose reductions run beside the passes
   bool no_overlap = false;  // POP_B200_NO_OVERLAP=1
   // velocity finish (impvmixu + Uold + mean removal + mask): 0 = one kernel after the barotropic solve that also adds
   // UBTROP/VBTROP(new) (default); 1 = on the side stream under the solve, separate add-barotropic kernel

@@ -478,7 +478,7 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
     for (const char* w : {"btropWgtNE", "btropWgtEast", "btropWgtNorth", "centerWgtClinicIndep"})
       POP_TRY(halo_rows_only(fld(w), 1));
   for (const char* w : {"BT_R", "BT_S", "BT_Q", "BT_Z", "BT_AZ", "BT_A0R"}) POP_TRY(alloc_field(w, 1, false));
-  POP_TRY(alloc_field("BT_PCSI", 6, false));  // [X0, Q0, X1, Q1] of the fused PCSI passes + 2 check snapshots
+  POP_TRY(alloc_field("BT_PCSI", 6, false));  // three (X, Q) pairs of the fused PCSI passes (two in rotation, one held by a pending check)
   // vmix_const init: VVC = const_vvc, VDC = const_vdc
   if (c.vmix_itype == POP_VMIX_CONST) {
     HV v((size_t)G.vdc_nk * G.vdc_nd * n2, c.const_vdc);

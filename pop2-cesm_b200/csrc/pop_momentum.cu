@@ -606,6 +606,7 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
 #define MF_PD 8    // L2 prefetch distance in levels (0: off)
 #endif
 #define MF_THREADS 128
+template <bool PBC>
 __global__ void __launch_bounds__(MF_THREADS, MF_MINB)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
                        const double* __restrict__ UOLD, const double* __restrict__ VOLD,
@@ -670,11 +671,11 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
         nld--;
       }
     };
-    const double* DZUq = g.DZU ? g.DZU + q : nullptr;  // partial bottom cells: vertical_mix.F90:1777-1784
+    const double* DZUq = PBC ? g.DZU + q : nullptr;  // partial bottom cells: vertical_mix.F90:1777-1784
     auto fwd_level = [&](int k, double vvc, double ru, double rw) {
       double hfac;
       C = A;
-      if (DZUq) {
+      if (PBC) {
         const double zk = DZUq[(size_t)k * n2];
         hfac = zk / c2dtu;
         A = g.aidif * vvc / (0.5 * (zk + DZUq[(size_t)(k + 1) * n2]));
@@ -814,7 +815,7 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
   // ---- remove the vertical mean, KMU mask (baroclinic.F90:1085-1129) [+ barotropic velocity, step_mod.F90:581-592]
   const double hur = g.HUR[q];
   double w1 = 0.0, w2 = 0.0;
-  if (g.DZU) {  // baroclinic.F90:1097-1107
+  if (PBC) {  // baroclinic.F90:1097-1107
     const double* pv = Vn;
     const double* pz = g.DZU + q + n2;
 #pragma unroll 4
@@ -1095,11 +1096,12 @@ static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const d
     }
   }
   const size_t smem = sizeof(double) * MF_THREADS * (size_t)G.km;
+  auto kfn = g.DZU ? momentum_finish_kernel<true> : momentum_finish_kernel<false>;
 #ifndef POP_EMUL
-  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)momentum_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
-  POP_LAUNCH(momentum_finish_kernel, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, implicit_vmix,
+  POP_LAUNCH(kfn, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, implicit_vmix,
              finish, G.c2dtu);
   return pop_post_launch("momentum_finish");
 }

@@ -873,7 +873,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
 #define IV_PD 8   // L2 prefetch distance in levels (0: off)
 #endif
 #define IV_THREADS 128
-template <bool CORRECT>
+template <bool CORRECT, bool PBC>
 __global__ void __launch_bounds__(IV_THREADS, IV_MINB)
 impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict__ TOLD,
                 const double* __restrict__ PSFC, const double* __restrict__ RHS, double* FB,
@@ -940,11 +940,11 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
         nld--;
       }
     };
-    const double* DZTq = g.DZT ? g.DZT + q : nullptr;  // partial bottom cells: vertical_mix.F90:1279-1286, :1577-1582
+    const double* DZTq = PBC ? g.DZT + q : nullptr;  // partial bottom cells: vertical_mix.F90:1279-1286, :1577-1582
     auto fwd_level = [&](int k, double vdc, double rhs) {
       C = A;
       double hfac;
-      if (DZTq) {  // level 1 keeps the full-cell A and hfac (:1263-1269); DZT(k+1) is read at k = km too
+      if (PBC) {  // level 1 keeps the full-cell A and hfac (:1263-1269); DZT(k+1) is read at k = km too
         const double zk = DZTq[(size_t)k * n2];
         A = g.aidif * vdc / (0.5 * (zk + DZTq[(size_t)(k + 1) * n2]));
         hfac = zk / c_vc.c2dtt[k];
@@ -1256,8 +1256,9 @@ int impvmixt_dev(double* TNEW, const double* TOLD, const double* PSFC, const dou
     return pop_post_launch("impvmixt");
   }
   const size_t smem = sizeof(double) * IV_THREADS * (size_t)G.km;
-  auto kc = impvmixt_kernel<true>;
-  auto kp = impvmixt_kernel<false>;
+  const bool pbc = (g.DZT != nullptr);
+  auto kc = pbc ? impvmixt_kernel<true, true> : impvmixt_kernel<true, false>;
+  auto kp = pbc ? impvmixt_kernel<false, true> : impvmixt_kernel<false, false>;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)(correct ? kc : kp), cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -286,8 +286,11 @@ def test_pcsi_deep_strip_layout_is_bitwise_the_plain_solver(monkeypatch, ns, ny,
                    given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
     res = {}
     monkeypatch.setenv("POP_B200_DEEP_HALO", depth)
-    for tag, env in (("plain", "0"), ("deep", "1")):
+    for tag, env in (("plain", "0"), ("deep", "1"), ("lagged", "0")):
         monkeypatch.setenv("POP_B200_DEEP_HALO_FORCE", env)
+        # the multi-rank solver also reads the verdict of a convergence check one check period late (X_m of the check
+        # is kept aside meanwhile): same answer, same iteration count
+        monkeypatch.setenv("POP_B200_LAGGED_CHECKS", "1" if tag != "plain" else "0")
         p = load_pop(cs)
         try:
             its = []
@@ -297,10 +300,11 @@ def test_pcsi_deep_strip_layout_is_bitwise_the_plain_solver(monkeypatch, ns, ny,
             res[tag] = (its, {n: pop_global(p, n, c.TIME_CUR) for n in PROG})
         finally:
             p.finalize()
-    assert res["plain"][0] == res["deep"][0]
+    assert res["plain"][0] == res["deep"][0] == res["lagged"][0]
     assert min(res["plain"][0]) >= 60
     for n in PROG:
         assert np.array_equal(res["plain"][1][n], res["deep"][1][n]), n
+        assert np.array_equal(res["plain"][1][n], res["lagged"][1][n]), n
 
 
 @pytest.mark.parametrize("flags", [("POP_B200_NO_TMA",), ("POP_B200_NO_FAST_TRACER",), ("POP_B200_NO_OVERLAP",),
