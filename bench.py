@@ -54,6 +54,8 @@ WORKLOADS = {
 PRECOND = {"diagonal": 0, "evp": 1}
 _PRECOND_CHOICE = ["diagonal"]   # set from --precond
 _PBC = [False]                   # set from --pbc: partial bottom cells (the production setting of tx0.1v3)
+_PASSIVE_ADV = ["centered"]      # set from --passive-advect: scheme of tracers 3..nt (BASELINE config 5: lw_lim)
+TADV = {"centered": c.TADVECT_CENTERED, "upwind3": c.TADVECT_UPWIND3, "lw_lim": c.TADVECT_LW_LIM}
 
 
 def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
@@ -79,6 +81,11 @@ def make_cfg(workload, nt, rank=0, nranks=1, device=0, block=None):
                   ah=1.0e7, am=1.0e8, vmix_itype=c.VMIX_CONST, vdc_kdim_halo=0, vdc_ndim=1,
                   solver_choice=c.SOLVER_CHRONGEAR, tadvect=c.TADVECT_UPWIND3, ns_boundary_type=c.BNDY_CLOSED)
     kw.update(preconditioner_choice=PRECOND[_PRECOND_CHOICE[0]], partial_bottom_cells=1 if _PBC[0] else 0)
+    if _PASSIVE_ADV[0] != "centered" and nt > 2:
+        # the ecosystem (MARBL) tracers of the production runs are advected with lw_lim (positive-definite enough for
+        # concentrations), TEMP and SALT keep the scheme of the workload
+        base = kw["tadvect"]
+        kw["tadvect"] = [base, base] + [TADV[_PASSIVE_ADV[0]]] * (nt - 2)
     if block:
         kw.update(block_size_x=block[0], block_size_y=block[1])
     return c.make_config(**kw), vg
@@ -439,9 +446,10 @@ def run_pop(args):
         "value": cells * K / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (seeded analytic fields + hash noise, synthetic bathymetry)",
-        "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt %s given-KPP-shaped-vmix "
+        "config": {"workload": "%s %dx%dx%d nt=%d tripole centered-advt%s %s given-KPP-shaped-vmix "
                                "PCSI/%s 1e-13 dt=%gs %s, 1x%d j-strips"
                                % (args.workload, nx, ny, km, nt,
+                                  "(+%d passive on %s)" % (nt - 2, args.passive_advect) if (args.passive_advect != "centered" and nt > 2) else "",
                                   "GM(const kappa, notanh)+del2u" if cfg.hmix_tracer_itype == c.HMIX_GM else "del4(variable)",
                                   args.precond, cfg.dtt, "partial-bottom-cells" if args.pbc else "full-cells", world),
                    "l2": "inputs larger than L2 (state is %.0f GB; no explicit flush)" % (cells * 8 * (3 * nt + 9 + 3) / 1e9),
@@ -655,6 +663,8 @@ def main():
     ap.add_argument("--nt", type=int, default=2)
     ap.add_argument("--precond", default="diagonal", choices=list(PRECOND),
                     help="barotropic preconditioner: diagonal (timed default) or evp (the reference's production default)")
+    ap.add_argument("--passive-advect", default="centered", choices=list(TADV),
+                    help="advection scheme of the passive tracers 3..nt (config 5: lw_lim, advection.F90:2684-3280)")
     ap.add_argument("--pbc", action="store_true",
                     help="partial bottom cells (namelist_defaults_pop.xml:122: the production setting of tx0.1v3); the timed "
                          "default is full cells, the primary variant of SURVEY 8d config 4")
@@ -664,6 +674,7 @@ def main():
     args = ap.parse_args()
     _PRECOND_CHOICE[0] = args.precond
     _PBC[0] = args.pbc
+    _PASSIVE_ADV[0] = args.passive_advect
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -35,7 +35,7 @@ enum { POP_KIND_SCALAR = 1, POP_KIND_VECTOR = 2, POP_KIND_ANGLE = 3 };
 /* boundary types of create_blocks (source/blocks.F90:181-257) */
 enum { POP_BNDY_CLOSED = 0, POP_BNDY_CYCLIC = 1, POP_BNDY_TRIPOLE = 2 };
 /* option ids */
-enum { POP_TADVECT_CENTERED = 1, POP_TADVECT_UPWIND3 = 2 };          /* advection.F90:112-115 */
+enum { POP_TADVECT_CENTERED = 1, POP_TADVECT_UPWIND3 = 2, POP_TADVECT_LW_LIM = 3 };  /* advection.F90:73-76 */
 enum { POP_HMIX_DEL2 = 1, POP_HMIX_DEL4 = 2, POP_HMIX_GM = 3 };         /* horizontal_mix.F90 */
 enum { POP_VMIX_CONST = 1, POP_VMIX_RICH = 2, POP_VMIX_GIVEN = 3 };   /* vertical_mix.F90:393-419;
                                    GIVEN = KPP-shaped VDC(0:km+1,2)/VVC(km) supplied by the caller */
@@ -158,9 +158,13 @@ int pop_scatter_field_levels(const char* name, int tlev, int z0, int nz, const v
 int pop_set_timestep(int ts_type);
 
 /* ---- slab operators: reference argument lists. ---- */
-/* advection.F90:1577 */
+/* advection.F90:1577 (tracers with tadvect_itype = lw_lim: call pop_comp_flux_vel_ghost once per step first, and
+   levels in ascending order) */
 int pop_advt(int k, double* LTK, double* WTK, const double* TMIX, const double* TRCR,
              const double* UUU, const double* VVV, const pop_block* blk);
+/* advection.F90:1014 comp_flux_vel_ghost(DH, errorCode): flux velocities of UVEL/VVEL(curtime) of every level with
+   halo-updated ghost cells, for the lw_lim scheme; DH (nx_block, ny_block) host or device; no-op without lw_lim */
+int pop_comp_flux_vel_ghost(const double* DH);
 /* advection.F90:1127 */
 int pop_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, const double* VVV,
              const pop_block* blk);

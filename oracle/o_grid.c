@@ -298,6 +298,43 @@ static void init_advection(void) {
   for (int n = 0; n < M.nt; n++)
     if (M.cfg.tadvect_itype[n] == POP_TADVECT_UPWIND3) use_upwind3 = 1;
   M.AUX = o_alloc_d(M.n2 * M.nt * M.nblocks);
+  M.use_lw_lim = 0;
+  for (int n = 0; n < M.nt; n++)
+    if (M.cfg.tadvect_itype[n] == POP_TADVECT_LW_LIM) M.use_lw_lim = 1;
+  if (M.use_lw_lim) { /* advection.F90:566-694 */
+    const int kk = PBC ? km : 1;
+    M.p5_dz_ph_r = o_alloc_d(km + 2);
+    M.p5_DXT_ph_R = D2ALLOC(); M.p5_DYT_ph_R = D2ALLOC();
+    M.UTE_to_UVEL_E = o_alloc_d(M.n2 * kk * M.nblocks);
+    M.VTN_to_VVEL_N = o_alloc_d(M.n2 * kk * M.nblocks);
+    M.UTE_jbm2 = o_alloc_d((size_t)nxb * km * M.nblocks); M.WTKB_jbm2 = o_alloc_d((size_t)nxb * km * M.nblocks);
+    M.WTKB_jep2 = o_alloc_d((size_t)nxb * km * M.nblocks);
+    M.WTKB_ibm2 = o_alloc_d((size_t)nyb * km * M.nblocks); M.WTKB_iep2 = o_alloc_d((size_t)nyb * km * M.nblocks);
+    M.FLUX_VEL_prev = o_alloc_d(M.n2 * 5 * M.nblocks);
+    for (int k = 1; k <= km - 1; k++) M.p5_dz_ph_r[k] = 1.0 / (M.dz[k] + M.dz[k + 1]);
+    M.p5_dz_ph_r[km] = 0.5 / M.dz[km];
+    for (int b = 0; b < M.nblocks; b++) {
+      const double *DXT = B2(M.DXT, b), *DYT = B2(M.DYT, b), *HTE = B2(M.HTE, b), *HTN = B2(M.HTN, b);
+      for (int j = M.jb[b] - 2; j <= M.je[b] + 2; j++)
+        for (int i = M.ib[b] - 2; i <= M.ie[b] + 1; i++) {
+          B2(M.p5_DXT_ph_R, b)[IX2(i, j)] = 1.0 / (DXT[IX2(i, j)] + DXT[IX2(i + 1, j)]);
+          for (int k = 1; k <= kk; k++) {
+            double* E = M.UTE_to_UVEL_E + ((size_t)b * kk + (k - 1)) * M.n2;
+            if (PBC) E[IX2(i, j)] = 1.0 / HTE[IX2(i, j)] / fmin(DZT3(b, k)[IX2(i, j)], DZT3(b, k)[IX2(i + 1, j)]);
+            else E[IX2(i, j)] = 1.0 / HTE[IX2(i, j)];
+          }
+        }
+      for (int j = M.jb[b] - 2; j <= M.je[b] + 1; j++)
+        for (int i = M.ib[b]; i <= M.ie[b]; i++) {
+          B2(M.p5_DYT_ph_R, b)[IX2(i, j)] = 1.0 / (DYT[IX2(i, j)] + DYT[IX2(i, j + 1)]);
+          for (int k = 1; k <= kk; k++) {
+            double* N = M.VTN_to_VVEL_N + ((size_t)b * kk + (k - 1)) * M.n2;
+            if (PBC) N[IX2(i, j)] = 1.0 / HTN[IX2(i, j)] / fmin(DZT3(b, k)[IX2(i, j)], DZT3(b, k)[IX2(i, j + 1)]);
+            else N[IX2(i, j)] = 1.0 / HTN[IX2(i, j)];
+          }
+        }
+    }
+  }
   if (!use_upwind3) return;
   M.talfzp = o_alloc_d(km + 2); M.tbetzp = o_alloc_d(km + 2); M.tgamzp = o_alloc_d(km + 2);
   M.talfzm = o_alloc_d(km + 2); M.tbetzm = o_alloc_d(km + 2); M.tdelzm = o_alloc_d(km + 2);

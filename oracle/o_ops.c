@@ -217,11 +217,12 @@ void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* 
     return;
   }
   const double *U = K3(UUU, k), *V = K3(VVV, k), *DYU = B2(M.DYU, b), *DXU = B2(M.DXU, b);
+  const int jend = M.use_lw_lim ? M.je[b] + 2 : M.je[b] + 1; /* :2036 */
   if (PBC) { /* :2040-2066: the flux velocities carry the thickness of the U cells */
     const double* DZU = DZU3(b, k);
 #define UD_(i, j) (U[IX2(i, j)] * DYU[IX2(i, j)] * DZU[IX2(i, j)])
 #define VD_(i, j) (V[IX2(i, j)] * DXU[IX2(i, j)] * DZU[IX2(i, j)])
-    for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+    for (int j = M.jb[b] - 1; j <= jend; j++)
       for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
         UTE[IX2(i, j)] = 0.5 * (UD_(i, j) + UD_(i, j - 1));
         UTW[IX2(i, j)] = 0.5 * (UD_(i - 1, j) + UD_(i - 1, j - 1));
@@ -231,13 +232,21 @@ void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* 
 #undef UD_
 #undef VD_
   } else
-  for (int j = M.jb[b] - 1; j <= M.je[b] + 1; j++)
+  for (int j = M.jb[b] - 1; j <= jend; j++)
     for (int i = M.ib[b] - 1; i <= M.ie[b] + 1; i++) {
       UTE[IX2(i, j)] = 0.5 * (U[IX2(i, j)] * DYU[IX2(i, j)] + U[IX2(i, j - 1)] * DYU[IX2(i, j - 1)]);
       UTW[IX2(i, j)] = 0.5 * (U[IX2(i - 1, j)] * DYU[IX2(i - 1, j)] + U[IX2(i - 1, j - 1)] * DYU[IX2(i - 1, j - 1)]);
       VTN[IX2(i, j)] = 0.5 * (V[IX2(i, j)] * DXU[IX2(i, j)] + V[IX2(i - 1, j)] * DXU[IX2(i - 1, j)]);
       VTS[IX2(i, j)] = 0.5 * (V[IX2(i, j - 1)] * DXU[IX2(i, j - 1)] + V[IX2(i - 1, j - 1)] * DXU[IX2(i - 1, j - 1)]);
     }
+  if (M.use_lw_lim) { /* :2086-2092: the outermost ghost cells come from comp_flux_vel_ghost */
+    const int jb2 = M.jb[b] - 2, ib2 = M.ib[b] - 2;
+    const double* ute_s = M.UTE_jbm2 + ((size_t)b * M.km + (k - 1)) * NXB;
+    for (int i = 1; i <= NXB; i++) UTE[IX2(i, jb2)] = ute_s[i - 1];
+    for (int i = 2; i <= NXB; i++) UTW[IX2(i, jb2)] = UTE[IX2(i - 1, jb2)];
+    for (int j = 1; j <= NYB; j++) UTE[IX2(ib2, j)] = UTW[IX2(ib2 + 1, j)];
+    for (int i = 1; i <= NXB; i++) VTN[IX2(i, jb2)] = VTS[IX2(i, jb2 + 1)];
+  }
   if (k < M.km) {
     const int* KMT = M.KMT + (size_t)b * M.n2;
     const double* TR = B2(M.TAREA_R, b);
@@ -245,6 +254,13 @@ void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* 
       double FC = (VTN[q] - VTS[q] + UTE[q] - UTW[q]) * TR[q];
       if (PBC) WTKB[q] = (k < KMT[q]) ? WTK[q] + FC : 0.0; /* :2110-2111 */
       else WTKB[q] = (k < KMT[q]) ? WTK[q] + M.dz[k] * FC : 0.0;
+    }
+    if (M.use_lw_lim) { /* :2116-2121 */
+      const size_t sx = ((size_t)b * M.km + (k - 1)) * NXB, sy = ((size_t)b * M.km + (k - 1)) * NYB;
+      for (int i = 1; i <= NXB; i++) WTKB[IX2(i, M.jb[b] - 2)] = M.WTKB_jbm2[sx + i - 1];
+      for (int i = 1; i <= NXB; i++) WTKB[IX2(i, M.je[b] + 2)] = M.WTKB_jep2[sx + i - 1];
+      for (int j = 1; j <= NYB; j++) WTKB[IX2(M.ib[b] - 2, j)] = M.WTKB_ibm2[sy + j - 1];
+      for (int j = 1; j <= NYB; j++) WTKB[IX2(M.ie[b] + 2, j)] = M.WTKB_iep2[sy + j - 1];
     }
   } else {
     memset(WTKB, 0, sizeof(double) * M.n2);
@@ -401,14 +417,312 @@ static void advt_upwind3(int k, double* LTK, const double* TRCR, const double* W
   free(FVN); free(FVS); free(FUE); free(FUW); free(AZM); free(DZM); free(TE); free(TN); free(AUXB);
 }
 
-/* advt: advection.F90:1577-1730 (centered + upwind3; lw_lim is a "next" row) */
+/* comp_flux_vel_ghost: advection.F90:1014-1120.  Flux velocities of every level with halo-updated ghost cells; the
+   rows / columns two cells outside the physical domain are kept for comp_flux_vel. */
+void o_comp_flux_vel_ghost(void) {
+  if (!M.use_lw_lim) return;
+  const int nb = M.nblocks, km = M.km, c = M.curtime;
+  const size_t nall = M.n2 * nb;
+  double *UTE = (double*)calloc(nall, sizeof(double)), *UTW = (double*)calloc(nall, sizeof(double)),
+         *VTN = (double*)calloc(nall, sizeof(double)), *VTS = (double*)calloc(nall, sizeof(double)),
+         *WTK = (double*)calloc(nall, sizeof(double)), *WTKB = (double*)calloc(nall, sizeof(double));
+  for (int k = 1; k <= km; k++) {
+    for (int b = 0; b < nb; b++) {
+      if (!M.active[b]) continue;
+      if (k == 1) memcpy(B2(WTK, b), B2(M.DH, b), sizeof(double) * M.n2);
+      else memcpy(B2(WTK, b), B2(WTKB, b), sizeof(double) * M.n2);
+      o_comp_flux_vel(k, B3(M.UVEL[c], b), B3(M.VVEL[c], b), B2(WTK, b), B2(UTE, b), B2(UTW, b), B2(VTN, b),
+                      B2(VTS, b), B2(WTKB, b), b);
+    }
+    oracle_halo_2d(UTE, POP_LOC_EFACE, POP_KIND_VECTOR, 0.0);
+    oracle_halo_2d(WTKB, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0);
+    for (int b = 0; b < nb; b++) {
+      if (!M.active[b]) continue;
+      const size_t sx = ((size_t)b * km + (k - 1)) * NXB, sy = ((size_t)b * km + (k - 1)) * NYB;
+      const double *E = B2(UTE, b), *W = B2(WTKB, b);
+      for (int i = 1; i <= NXB; i++) {
+        M.UTE_jbm2[sx + i - 1] = E[IX2(i, M.jb[b] - 2)];
+        M.WTKB_jbm2[sx + i - 1] = W[IX2(i, M.jb[b] - 2)];
+        M.WTKB_jep2[sx + i - 1] = W[IX2(i, M.je[b] + 2)];
+      }
+      for (int j = 1; j <= NYB; j++) {
+        M.WTKB_ibm2[sy + j - 1] = W[IX2(M.ib[b] - 2, j)];
+        M.WTKB_iep2[sy + j - 1] = W[IX2(M.ie[b] + 2, j)];
+      }
+    }
+  }
+  free(UTE); free(UTW); free(VTN); free(VTS); free(WTK); free(WTKB);
+}
+
+/* lw_lim: advection.F90:2832-3280.  Second-order forward-in-time scheme with one-dimensional flux limiters:
+   z, then x (on the z-updated field), then y (on the z- and x-updated field). */
+static void lw_lim(int k, double adv_dt, const double* UVEL_E_dt, const double* VVEL_N_dt, double* XOUT,
+                   const double* X, const double* WTK, const double* WTKB, const double* WTKBp1, double* AUXB,
+                   const double* CN, const double* CS, const double* CE, const double* CW, const double* KMASKE,
+                   const double* KMASKN, double* TRACER_E, double* TRACER_N, int b) {
+  const int km = M.km, ib = M.ib[b], ie = M.ie[b], jb = M.jb[b], je = M.je[b];
+  const int* KMT = M.KMT + (size_t)b * M.n2;
+  const double *DXT = B2(M.DXT, b), *DYT = B2(M.DYT, b), *PX = B2(M.p5_DXT_ph_R, b), *PY = B2(M.p5_DYT_ph_R, b);
+  const double adv_dt_r = 1.0 / adv_dt;
+  double *DIV = tmp2(), *XSTAR = tmp2(), *MU_z = tmp2(), *LW_z = tmp2(), *MU_x = tmp2(), *LW_x = tmp2(),
+         *MU_y = tmp2(), *LW_y = tmp2();
+  /* ---- tracer-independent coefficients, :2911-2975 */
+  if (PBC) {
+    const double *Zk = DZT3(b, k), *Zp = DZT3(b, k + 1), *Zm = DZT3(b, k - 1);
+    const double* Zpp = (k + 2 <= km + 1) ? DZT3(b, k + 2) : NULL;
+    for (int j = jb - 2; j <= je + 2; j++)
+      for (int i = ib - 2; i <= ie + 2; i++) {
+        const size_t q = IX2(i, j);
+        if (WTKB[q] > 0.0) {
+          LW_z[q] = (Zp[q] - adv_dt * WTKB[q]) / (Zk[q] + Zp[q]);
+          if (WTKBp1[q] > 0.0) MU_z[q] = (Zp[q] * adv_dt_r - WTKBp1[q]) / WTKB[q];
+          else if (WTKBp1[q] < 0.0)
+            MU_z[q] = -WTKBp1[q] / WTKB[q] * (Zp[q] + adv_dt * WTKBp1[q]) / (Zp[q] + Zpp[q]);
+          else MU_z[q] = 0.0;
+        } else if (WTKB[q] < 0.0) {
+          LW_z[q] = (Zk[q] + adv_dt * WTKB[q]) / (Zk[q] + Zp[q]);
+          if (WTK[q] < 0.0) MU_z[q] = -(Zk[q] * adv_dt_r + WTK[q]) / WTKB[q];
+          else if (WTK[q] > 0.0) MU_z[q] = -WTK[q] / WTKB[q] * (Zk[q] - adv_dt * WTK[q]) / (Zm[q] + Zk[q]);
+          else MU_z[q] = 0.0;
+        }
+      }
+  } else {
+    const double dzk_div_dt = M.dz[k] * adv_dt_r;
+    const double dzkp1_div_dt = (k < km) ? M.dz[k + 1] * adv_dt_r : 0.0;
+    const double work1 = M.dz[k] * M.p5_dz_ph_r[k];
+    const double work2 = (k < km) ? M.dz[k + 1] * M.p5_dz_ph_r[k] : 0.0;
+    const double work3 = adv_dt * M.p5_dz_ph_r[k];
+    for (int j = jb - 2; j <= je + 2; j++)
+      for (int i = ib - 2; i <= ie + 2; i++) {
+        const size_t q = IX2(i, j);
+        if (WTKB[q] > 0.0) {
+          LW_z[q] = work2 - work3 * WTKB[q];
+          if (WTKBp1[q] > 0.0) MU_z[q] = (dzkp1_div_dt - WTKBp1[q]) / WTKB[q];
+          else if (WTKBp1[q] < 0.0)
+            MU_z[q] = -WTKBp1[q] / WTKB[q] * (M.dz[k + 1] + adv_dt * WTKBp1[q]) * M.p5_dz_ph_r[k + 1];
+          else MU_z[q] = 0.0;
+        } else if (WTKB[q] < 0.0) {
+          LW_z[q] = work1 + work3 * WTKB[q];
+          if (WTK[q] < 0.0) MU_z[q] = -(dzk_div_dt + WTK[q]) / WTKB[q];
+          else if (WTK[q] > 0.0) MU_z[q] = -WTK[q] / WTKB[q] * (M.dz[k] - adv_dt * WTK[q]) * M.p5_dz_ph_r[k - 1];
+          else MU_z[q] = 0.0;
+        }
+      }
+  }
+  /* :2977-3015 */
+  for (int j = jb - 2; j <= je + 2; j++) {
+    int i = ib - 2;
+    if (UVEL_E_dt[IX2(i, j)] < 0.0) LW_x[IX2(i, j)] = (DXT[IX2(i + 1, j)] + UVEL_E_dt[IX2(i, j)]) * PX[IX2(i, j)];
+    for (i = ib - 1; i <= ie; i++) {
+      const size_t q = IX2(i, j);
+      if (UVEL_E_dt[q] > 0.0) {
+        LW_x[q] = (DXT[q] - UVEL_E_dt[q]) * PX[q];
+        if (UVEL_E_dt[IX2(i - 1, j)] > 0.0) MU_x[q] = (DXT[q] - UVEL_E_dt[IX2(i - 1, j)]) / UVEL_E_dt[q];
+        else MU_x[q] = 0.0;
+      } else if (UVEL_E_dt[q] < 0.0) {
+        LW_x[q] = (DXT[IX2(i + 1, j)] + UVEL_E_dt[q]) * PX[q];
+        if (UVEL_E_dt[IX2(i + 1, j)] < 0.0) MU_x[q] = -(DXT[IX2(i + 1, j)] + UVEL_E_dt[IX2(i + 1, j)]) / UVEL_E_dt[q];
+        else MU_x[q] = 0.0;
+      } else {
+        LW_x[q] = DXT[q] * PX[q];
+      }
+    }
+    i = ie + 1;
+    if (UVEL_E_dt[IX2(i, j)] > 0.0) LW_x[IX2(i, j)] = (DXT[IX2(i, j)] - UVEL_E_dt[IX2(i, j)]) * PX[IX2(i, j)];
+    for (i = ib - 1; i <= ie; i++) {
+      const size_t q = IX2(i, j);
+      if (UVEL_E_dt[q] > 0.0 && UVEL_E_dt[IX2(i - 1, j)] < 0.0)
+        MU_x[q] = -UVEL_E_dt[IX2(i - 1, j)] / UVEL_E_dt[q] * LW_x[IX2(i - 1, j)];
+      if (UVEL_E_dt[q] < 0.0 && UVEL_E_dt[IX2(i + 1, j)] > 0.0)
+        MU_x[q] = -UVEL_E_dt[IX2(i + 1, j)] / UVEL_E_dt[q] * LW_x[IX2(i + 1, j)];
+    }
+  }
+  /* :3017-3061 */
+  for (int i = ib; i <= ie; i++)
+    if (VVEL_N_dt[IX2(i, jb - 2)] < 0.0)
+      LW_y[IX2(i, jb - 2)] = (DYT[IX2(i, jb - 1)] + VVEL_N_dt[IX2(i, jb - 2)]) * PY[IX2(i, jb - 2)];
+  for (int j = jb - 1; j <= je; j++)
+    for (int i = ib; i <= ie; i++) {
+      const size_t q = IX2(i, j);
+      if (VVEL_N_dt[q] > 0.0) {
+        LW_y[q] = (DYT[q] - VVEL_N_dt[q]) * PY[q];
+        if (VVEL_N_dt[IX2(i, j - 1)] > 0.0) MU_y[q] = (DYT[q] - VVEL_N_dt[IX2(i, j - 1)]) / VVEL_N_dt[q];
+        else MU_y[q] = 0.0;
+      } else if (VVEL_N_dt[q] < 0.0) {
+        LW_y[q] = (DYT[IX2(i, j + 1)] + VVEL_N_dt[q]) * PY[q];
+        if (VVEL_N_dt[IX2(i, j + 1)] < 0.0) MU_y[q] = -(DYT[IX2(i, j + 1)] + VVEL_N_dt[IX2(i, j + 1)]) / VVEL_N_dt[q];
+        else MU_y[q] = 0.0;
+      } else {
+        LW_y[q] = DYT[q] * PY[q];
+      }
+    }
+  for (int i = ib; i <= ie; i++)
+    if (VVEL_N_dt[IX2(i, je + 1)] > 0.0)
+      LW_y[IX2(i, je + 1)] = (DYT[IX2(i, je + 1)] - VVEL_N_dt[IX2(i, je + 1)]) * PY[IX2(i, je + 1)];
+  for (int j = jb - 1; j <= je; j++)
+    for (int i = ib; i <= ie; i++) {
+      const size_t q = IX2(i, j);
+      if (VVEL_N_dt[q] > 0.0 && VVEL_N_dt[IX2(i, j - 1)] < 0.0)
+        MU_y[q] = -VVEL_N_dt[IX2(i, j - 1)] / VVEL_N_dt[q] * LW_y[IX2(i, j - 1)];
+      if (VVEL_N_dt[q] < 0.0 && VVEL_N_dt[IX2(i, j + 1)] > 0.0)
+        MU_y[q] = -VVEL_N_dt[IX2(i, j + 1)] / VVEL_N_dt[q] * LW_y[IX2(i, j + 1)];
+    }
+  /* :3063-3067 */
+  for (size_t q = 0; q < M.n2; q++) {
+    if (PBC) DIV[q] = (WTK[q] - WTKB[q]) / DZT3(b, k)[q] + CE[q] + CW[q] + CN[q] + CS[q];
+    else DIV[q] = (WTK[q] - WTKB[q]) * M.dzr[k] + CE[q] + CW[q] + CN[q] + CS[q];
+  }
+  /* ---- tracers, :3073-3274 */
+  for (int n = 1; n <= M.nt; n++) {
+    if (M.cfg.tadvect_itype[n - 1] != POP_TADVECT_LW_LIM) continue;
+    double *TE = TRACER_E + (size_t)(n - 1) * M.n2, *TN = TRACER_N + (size_t)(n - 1) * M.n2,
+           *XO = XOUT + (size_t)(n - 1) * M.n2, *AB = AUXB + (size_t)(n - 1) * M.n2;
+    const double* AUX = M.AUX + ((size_t)b * M.nt + (n - 1)) * M.n2;
+    const double* Xk = KN4(X, k, n);
+    const double* Xp = (k + 1 <= km) ? KN4(X, k + 1, n) : NULL;
+    const double* Xpp = (k + 2 <= km) ? KN4(X, k + 2, n) : NULL;
+    const double* Xm = (k > 1) ? KN4(X, k - 1, n) : NULL;
+    zero_ghost_cells(b, TE); zero_ghost_cells(b, TN); zero_ghost_cells(b, AB);
+    for (int j = jb - 2; j <= je + 2; j++) {
+      for (int i = ib - 2; i <= ie + 2; i++) { /* z, :3096-3149 */
+        const size_t q = IX2(i, j);
+        if (k + 1 <= KMT[q]) {
+          const double dTR = Xp[q] - Xk[q];
+          if (WTKB[q] > 0.0) {
+            AB[q] = WTKB[q] * Xp[q];
+            if (k + 2 <= KMT[q]) {
+              const double dTRp1 = Xpp[q] - Xp[q];
+              if (dTR > 0.0 && dTRp1 > 0.0) AB[q] = WTKB[q] * (Xp[q] - fmin(LW_z[q] * dTR, MU_z[q] * dTRp1));
+              else if (dTR < 0.0 && dTRp1 < 0.0) AB[q] = WTKB[q] * (Xp[q] - fmax(LW_z[q] * dTR, MU_z[q] * dTRp1));
+            }
+          } else if (WTKB[q] < 0.0) {
+            AB[q] = WTKB[q] * Xk[q];
+            if (k > 1) {
+              const double dTRm1 = Xk[q] - Xm[q];
+              if (dTR > 0.0 && dTRm1 > 0.0) AB[q] = WTKB[q] * (Xk[q] + fmin(LW_z[q] * dTR, MU_z[q] * dTRm1));
+              else if (dTR < 0.0 && dTRm1 < 0.0) AB[q] = WTKB[q] * (Xk[q] + fmax(LW_z[q] * dTR, MU_z[q] * dTRm1));
+            }
+          } else {
+            AB[q] = 0.0;
+          }
+        } else {
+          AB[q] = 0.0;
+        }
+        if (PBC) XO[q] = (AUX[q] - AB[q] - (WTK[q] - WTKB[q]) * Xk[q]) / DZT3(b, k)[q];
+        else XO[q] = (AUX[q] - AB[q] - (WTK[q] - WTKB[q]) * Xk[q]) * M.dzr[k];
+        XSTAR[q] = Xk[q] - adv_dt * XO[q];
+      }
+      for (int i = ib - 1; i <= ie; i++) { /* x faces, :3151-3188 */
+        const size_t q = IX2(i, j);
+        const double dTR = (XSTAR[IX2(i + 1, j)] - XSTAR[q]) * KMASKE[q];
+        if (CE[q] > 0.0) {
+          const double dTRm1 = (XSTAR[q] - XSTAR[IX2(i - 1, j)]) * KMASKE[IX2(i - 1, j)];
+          if (dTR > 0.0 && dTRm1 > 0.0) TE[q] = XSTAR[q] + fmin(LW_x[q] * dTR, MU_x[q] * dTRm1);
+          else if (dTR < 0.0 && dTRm1 < 0.0) TE[q] = XSTAR[q] + fmax(LW_x[q] * dTR, MU_x[q] * dTRm1);
+          else TE[q] = XSTAR[q];
+        } else if (CE[q] < 0.0) {
+          const double dTRp1 = (XSTAR[IX2(i + 2, j)] - XSTAR[IX2(i + 1, j)]) * KMASKE[IX2(i + 1, j)];
+          if (dTR > 0.0 && dTRp1 > 0.0) TE[q] = XSTAR[IX2(i + 1, j)] - fmin(LW_x[q] * dTR, MU_x[q] * dTRp1);
+          else if (dTR < 0.0 && dTRp1 < 0.0) TE[q] = XSTAR[IX2(i + 1, j)] - fmax(LW_x[q] * dTR, MU_x[q] * dTRp1);
+          else TE[q] = XSTAR[IX2(i + 1, j)];
+        } else {
+          TE[q] = XSTAR[q] + LW_x[q] * dTR;
+        }
+      }
+    }
+    for (int j = jb - 2; j <= je + 2; j++) /* x update, :3205-3213 */
+      for (int i = ib; i <= ie; i++) {
+        const size_t q = IX2(i, j);
+        const double work1 = CE[q] * TE[q] + CW[q] * TE[IX2(i - 1, j)] - (CE[q] + CW[q]) * Xk[q];
+        XO[q] = XO[q] + work1;
+        XSTAR[q] = XSTAR[q] - adv_dt * work1;
+      }
+    for (int j = jb - 1; j <= je; j++) /* y faces, :3220-3256 */
+      for (int i = ib; i <= ie; i++) {
+        const size_t q = IX2(i, j);
+        const double dTR = (XSTAR[IX2(i, j + 1)] - XSTAR[q]) * KMASKN[q];
+        if (CN[q] > 0.0) {
+          const double dTRm1 = (XSTAR[q] - XSTAR[IX2(i, j - 1)]) * KMASKN[IX2(i, j - 1)];
+          if (dTR > 0.0 && dTRm1 > 0.0) TN[q] = XSTAR[q] + fmin(LW_y[q] * dTR, MU_y[q] * dTRm1);
+          else if (dTR < 0.0 && dTRm1 < 0.0) TN[q] = XSTAR[q] + fmax(LW_y[q] * dTR, MU_y[q] * dTRm1);
+          else TN[q] = XSTAR[q];
+        } else if (CN[q] < 0.0) {
+          const double dTRp1 = (XSTAR[IX2(i, j + 2)] - XSTAR[IX2(i, j + 1)]) * KMASKN[IX2(i, j + 1)];
+          if (dTR > 0.0 && dTRp1 > 0.0) TN[q] = XSTAR[IX2(i, j + 1)] - fmin(LW_y[q] * dTR, MU_y[q] * dTRp1);
+          else if (dTR < 0.0 && dTRp1 < 0.0) TN[q] = XSTAR[IX2(i, j + 1)] - fmax(LW_y[q] * dTR, MU_y[q] * dTRp1);
+          else TN[q] = XSTAR[IX2(i, j + 1)];
+        } else {
+          TN[q] = XSTAR[q] + LW_y[q] * dTR;
+        }
+      }
+    for (int j = jb - 1; j <= je; j++) /* y update + divergence term, :3263-3272 */
+      for (int i = ib; i <= ie; i++) {
+        const size_t q = IX2(i, j);
+        XO[q] = XO[q] + CN[q] * TN[q] + CS[q] * TN[IX2(i, j - 1)] - (CN[q] + CS[q] - DIV[q]) * Xk[q];
+      }
+  }
+  free(DIV); free(XSTAR); free(MU_z); free(LW_z); free(MU_x); free(LW_x); free(MU_y); free(LW_y);
+}
+
+/* advt_lw_lim: advection.F90:2684-2825 */
+static void advt_lw_lim(int k, double* LTK, const double* TMIX, const double* WTK, const double* WTKB,
+                        const double* WTKBp1, const double* UTE, const double* UTW, const double* VTN,
+                        const double* VTS, int b) {
+  const int kk = PBC ? k : 1;
+  const double adv_dt = M.c2dtt[k];
+  const int *KMT = M.KMT + (size_t)b * M.n2, *KMTE = M.KMTE + (size_t)b * M.n2, *KMTN = M.KMTN + (size_t)b * M.n2;
+  const double* TR = B2(M.TAREA_R, b);
+  const double* E2U = M.UTE_to_UVEL_E + ((size_t)b * (PBC ? M.km : 1) + (kk - 1)) * M.n2;
+  const double* N2V = M.VTN_to_VVEL_N + ((size_t)b * (PBC ? M.km : 1) + (kk - 1)) * M.n2;
+  double *UE = tmp2(), *VN = tmp2(), *FVN = tmp2(), *FVS = tmp2(), *FUE = tmp2(), *FUW = tmp2(), *KE = tmp2(),
+         *KN = tmp2(), *WEFF = tmp2();
+  double *TE = tmp2n(M.nt), *TN = tmp2n(M.nt), *AUXB = tmp2n(M.nt);
+  for (size_t q = 0; q < M.n2; q++) {
+    UE[q] = adv_dt * UTE[q] * E2U[q];
+    VN[q] = adv_dt * VTN[q] * N2V[q];
+    const double w = PBC ? TR[q] / DZT3(b, k)[q] : TR[q];
+    FVN[q] = VTN[q] * w;
+    FVS[q] = -VTS[q] * w;
+    FUE[q] = UTE[q] * w;
+    FUW[q] = -UTW[q] * w;
+    KE[q] = (k <= KMT[q] && k <= KMTE[q]) ? 1.0 : 0.0;
+    KN[q] = (k <= KMT[q] && k <= KMTN[q]) ? 1.0 : 0.0;
+    WEFF[q] = (k == 1 && M.cfg.sfc_layer_type == POP_SFC_VARTHICK) ? 0.0 : WTK[q];
+  }
+  if (k == 1)
+    for (int n = 1; n <= M.nt; n++) {
+      if (M.cfg.tadvect_itype[n - 1] != POP_TADVECT_LW_LIM) continue;
+      double* AUX = M.AUX + ((size_t)b * M.nt + (n - 1)) * M.n2;
+      const double* T = KN4(TMIX, 1, n);
+      for (size_t q = 0; q < M.n2; q++) AUX[q] = WEFF[q] * T[q];
+    }
+  lw_lim(k, adv_dt, UE, VN, LTK, TMIX, WEFF, WTKB, WTKBp1, AUXB, FVN, FVS, FUE, FUW, KE, KN, TE, TN, b);
+  for (int n = 1; n <= M.nt; n++) {
+    if (M.cfg.tadvect_itype[n - 1] != POP_TADVECT_LW_LIM) continue;
+    memcpy(M.AUX + ((size_t)b * M.nt + (n - 1)) * M.n2, AUXB + (size_t)(n - 1) * M.n2, sizeof(double) * M.n2);
+  }
+  free(UE); free(VN); free(FVN); free(FVS); free(FUE); free(FUW); free(KE); free(KN); free(WEFF);
+  free(TE); free(TN); free(AUXB);
+}
+
+/* advt: advection.F90:1577-1963 */
 void o_advt(int k, double* LTK, double* WTK, const double* TMIX, const double* TRCR,
             const double* UUU, const double* VVV, int b) {
-  (void)TMIX;
   double t0 = o_now();
   double *UTE = tmp2(), *UTW = tmp2(), *VTN = tmp2(), *VTS = tmp2(), *WTKB = tmp2();
-  o_comp_flux_vel(k, UUU, VVV, WTK, UTE, UTW, VTN, VTS, WTKB, b);
+  double* FP = M.use_lw_lim ? M.FLUX_VEL_prev + (size_t)b * 5 * M.n2 : NULL;
+  if (k == 1 || !M.use_lw_lim) { /* :1667-1676 */
+    o_comp_flux_vel(k, UUU, VVV, WTK, UTE, UTW, VTN, VTS, WTKB, b);
+  } else {
+    memcpy(UTE, FP, sizeof(double) * M.n2); memcpy(UTW, FP + M.n2, sizeof(double) * M.n2);
+    memcpy(VTN, FP + 2 * M.n2, sizeof(double) * M.n2); memcpy(VTS, FP + 3 * M.n2, sizeof(double) * M.n2);
+    memcpy(WTKB, FP + 4 * M.n2, sizeof(double) * M.n2);
+  }
   memset(LTK, 0, sizeof(double) * M.n2 * M.nt);
+  if (M.use_lw_lim) { /* :1688-1708: flux velocities of level k+1 are kept for the next call */
+    o_comp_flux_vel(k + 1, UUU, VVV, WTKB, FP, FP + M.n2, FP + 2 * M.n2, FP + 3 * M.n2, FP + 4 * M.n2, b);
+    advt_lw_lim(k, LTK, TMIX, WTK, WTKB, FP + 4 * M.n2, UTE, UTW, VTN, VTS, b);
+  }
   int up3 = 0, cen = 0;
   for (int n = 0; n < M.nt; n++) {
     if (M.cfg.tadvect_itype[n] == POP_TADVECT_UPWIND3) up3 = 1;

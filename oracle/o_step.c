@@ -155,6 +155,7 @@ int o_baroclinic_driver(void) {
   const int km = M.km, nt = M.nt;
   const int o = M.oldtime, c = M.curtime, n_ = M.newtime, mx = M.mixtime;
   o_gm_begin_step();
+  o_comp_flux_vel_ghost(); /* baroclinic.F90:667 */
 #pragma omp parallel for schedule(dynamic)
   for (int b = 0; b < NB; b++) {
     double* WTK = tmp2();

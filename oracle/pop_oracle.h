@@ -59,6 +59,12 @@ typedef struct {
   double *TALFXM, *TBETXM, *TDELXM, *TALFYM, *TBETYM, *TDELYM;
   /* state */
   double *pressz, *tmin, *tmax, *smin, *smax, *bouss;
+  /* lw_lim advection (advection.F90:566-694): grid coefficients, flux velocities of the outermost ghost cells
+     (comp_flux_vel_ghost, :1014-1120), flux velocities of level k+1 kept between levels (FLUX_VEL_prev) */
+  int use_lw_lim;
+  double *p5_dz_ph_r, *p5_DXT_ph_R, *p5_DYT_ph_R, *UTE_to_UVEL_E, *VTN_to_VVEL_N; /* the last two: [nblocks][km or 1][n2] */
+  double *UTE_jbm2, *WTKB_jbm2, *WTKB_jep2, *WTKB_ibm2, *WTKB_iep2;               /* [nblocks][km][nxb or nyb] */
+  double *FLUX_VEL_prev;                                                          /* [nblocks][5][n2] */
   /* vertical mixing */
   double *VDC, *VVC; /* VDC: [nblocks][vdc_nd][vdc_nk][nyb][nxb], level offset vdc_k0 */
   int vdc_nk, vdc_k0, vdc_nd, vvc_nk;
@@ -149,6 +155,7 @@ void o_state(int k, int kk, const double* T, const double* S, int b, double* RHO
              double* RHOFULL, double* DRHODT, double* DRHODS);
 void o_comp_flux_vel(int k, const double* UUU, const double* VVV, const double* WTK, double* UTE,
                      double* UTW, double* VTN, double* VTS, double* WTKB, int b);
+void o_comp_flux_vel_ghost(void); /* baroclinic.F90:667 */
 void o_advt(int k, double* LTK, double* WTK, const double* TMIX, const double* TRCR,
             const double* UUU, const double* VVV, int b);
 void o_advu(int k, double* LUK, double* LVK, double* WUK, const double* UUU, const double* VVV,

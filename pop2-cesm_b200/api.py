@@ -23,7 +23,7 @@ SYMBOLS = [
     "pop_last_error", "pop_config_defaults", "pop_init", "pop_finalize", "pop_is_initialized",
     "pop_comm_unique_id", "pop_comm_init", "pop_get_block", "pop_local_shape", "pop_set_bottom_cells", "pop_set_grid",
     "pop_device_ptr", "pop_field_size", "pop_set_field", "pop_get_field", "pop_scatter_field",
-    "pop_gather_field", "pop_scatter_field_levels", "pop_set_timestep", "pop_advt", "pop_advu", "pop_hdifft", "pop_hdiffu",
+    "pop_gather_field", "pop_scatter_field_levels", "pop_set_timestep", "pop_advt", "pop_comp_flux_vel_ghost", "pop_advu", "pop_hdifft", "pop_hdiffu",
     "pop_gradp", "pop_grad", "pop_div", "pop_vdifft", "pop_vdiffu", "pop_impvmixt",
     "pop_impvmixt_correct", "pop_impvmixu", "pop_vmix_coeffs", "pop_state", "pop_solvers_run",
     "pop_solvers_diagonal", "pop_solvers_get_diagnostics", "pop_btrop_operator", "pop_solvers_prep",
@@ -67,6 +67,7 @@ def lib():
         L.pop_comm_init.argtypes = [ci, ci, C.c_char_p]
         bp = C.POINTER(cfgmod.PopBlock)
         L.pop_advt.argtypes = [ci] + [vp] * 6 + [bp]
+        L.pop_comp_flux_vel_ghost.argtypes = [vp]
         L.pop_advu.argtypes = [ci] + [vp] * 5 + [bp]
         L.pop_hdifft.argtypes = [ci] + [vp] * 4 + [bp]
         L.pop_hdiffu.argtypes = [ci] + [vp] * 4 + [bp]
@@ -232,6 +233,10 @@ class Pop:
 
     def advt(self, k, LTK, WTK, TMIX, TRCR, UUU, VVV):
         self._ck(self.L.pop_advt(k, _p(LTK), _p(WTK), _p(TMIX), _p(TRCR), _p(UUU), _p(VVV), self.this_block))
+
+    def comp_flux_vel_ghost(self, DH):
+        """advection.F90:1014: once per step before the first advt level when a tracer uses lw_lim."""
+        self._ck(self.L.pop_comp_flux_vel_ghost(_p(DH)))
 
     def advu(self, k, LUK, LVK, WUK, UUU, VVV):
         self._ck(self.L.pop_advu(k, _p(LUK), _p(LVK), _p(WUK), _p(UUU), _p(VVV), self.this_block))

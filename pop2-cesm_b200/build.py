@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libpop_b200.so")
 SOURCES = ["pop_core.cu", "pop_grid.cu", "pop_halo.cu", "pop_reduce.cu", "pop_state.cu",
-           "pop_tracer.cu", "pop_gm.cu", "pop_momentum.cu", "pop_barotropic.cu", "pop_step.cu", "pop_abi.cu"]
+           "pop_tracer.cu", "pop_lwlim.cu", "pop_gm.cu", "pop_momentum.cu", "pop_barotropic.cu", "pop_step.cu", "pop_abi.cu"]
 HEADERS = ["pop_ctx.h", "pop_dev.cuh", "pop_state.cuh", "../../include/pop_b200.h"]
 
 

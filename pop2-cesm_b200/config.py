@@ -11,7 +11,7 @@ POP_MAX_NT = 64
 LOC_CENTER, LOC_NECORNER, LOC_NFACE, LOC_EFACE = 1, 2, 3, 4
 KIND_SCALAR, KIND_VECTOR, KIND_ANGLE = 1, 2, 3
 BNDY_CLOSED, BNDY_CYCLIC, BNDY_TRIPOLE = 0, 1, 2
-TADVECT_CENTERED, TADVECT_UPWIND3 = 1, 2
+TADVECT_CENTERED, TADVECT_UPWIND3, TADVECT_LW_LIM = 1, 2, 3
 HMIX_DEL2, HMIX_DEL4, HMIX_GM = 1, 2, 3
 VMIX_CONST, VMIX_RICH, VMIX_GIVEN = 1, 2, 3
 SFC_VARTHICK, SFC_RIGID, SFC_OLDFREE = 1, 2, 3

@@ -227,6 +227,10 @@ extern "C" int pop_advt(int k, double* LTK, double* WTK, const double* TMIX, con
   io.TCUR = s.in("a_trcr", TRCR, G.n3 * G.nt);
   io.TMIX = io.TCUR;
   io.TOLD = io.TCUR;
+  if (G.use_lw_lim) {  // lw_lim advects the mix-time field (advection.F90:1704, :2806)
+    POP_REQUIRE(TMIX, "advt: lw_lim needs TMIX");
+    io.TMIX = s.in("a_tmix", TMIX, G.n3 * G.nt);
+  }
   io.UCUR = s.in("a_u", UUU, G.n3);
   io.VCUR = s.in("a_v", VVV, G.n3);
   io.TNEW = s.inout("a_ltk", LTK, G.n2 * G.nt, false);
@@ -525,6 +529,17 @@ extern "C" int pop_global_sum_2d_r8(const double* array, int fieldLoc, const dou
 extern "C" int pop_dhdt(void) {
   POP_TRY(check_ready("dhdt", nullptr, false));
   return dhdt_dev();
+}
+// comp_flux_vel_ghost(DH, errorCode), advection.F90:1014: the flux velocities of UVEL/VVEL(curtime) two cells outside the
+// physical domain, which the lw_lim branch of advt needs.  The fused drivers call it themselves; a host that drives
+// pop_advt level by level calls it once per step before the first level, as baroclinic_driver does (baroclinic.F90:667).
+extern "C" int pop_comp_flux_vel_ghost(const double* DH) {
+  POP_TRY(check_ready("comp_flux_vel_ghost", nullptr, false));
+  if (!G.use_lw_lim) return POP_SUCCESS;  // :1057
+  POP_REQUIRE(DH, "comp_flux_vel_ghost: null DH");
+  double* dh = fld("DH");  // the library's own DH (what pop_dhdt fills) is what the lw_lim kernel reads at the surface
+  if (DH != dh) POP_CHECK_CUDA(cudaMemcpyAsync(dh, DH, sizeof(double) * G.n2, cudaMemcpyDefault, G.stream));
+  return with_p2p_check(lw_flux_prepare_dev(fld_t("UVEL", G.curtime), fld_t("VVEL", G.curtime), dh));
 }
 extern "C" int pop_baroclinic_driver(void) {
   POP_TRY(check_ready("baroclinic_driver", nullptr, false));

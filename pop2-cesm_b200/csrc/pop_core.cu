@@ -235,11 +235,11 @@ extern "C" int pop_init(const pop_config* cfg) {
               G.nranks);
   if (cfg->partial_bottom_cells) {
     // partial bottom cells are built for the option set of the tx0.1v3 production configuration and its neighbours:
-    // centred advection, del2 / del4 mixing, const / given vertical mixing coefficients
+    // centred or lw_lim advection, del2 / del4 mixing, const / given vertical mixing coefficients
     for (int n = 0; n < cfg->nt; n++)
-      POP_REQUIRE(cfg->tadvect_itype[n] == POP_TADVECT_CENTERED,
-                  "pop_init: partial_bottom_cells needs centred advection (tracer %d uses upwind3, whose vertical "
-                  "interpolation weights become 3-d with partial cells: not built)", n + 1);
+      POP_REQUIRE(cfg->tadvect_itype[n] != POP_TADVECT_UPWIND3,
+                  "pop_init: partial_bottom_cells needs centred or lw_lim advection (tracer %d uses upwind3, whose "
+                  "vertical interpolation weights become 3-d with partial cells: not built)", n + 1);
     POP_REQUIRE(cfg->hmix_tracer_itype != POP_HMIX_GM, "pop_init: partial_bottom_cells with GM is not built");
     POP_REQUIRE(cfg->vmix_itype != POP_VMIX_RICH, "pop_init: partial_bottom_cells with vmix 'rich' is not built");
   }
@@ -328,10 +328,13 @@ extern "C" int pop_init(const pop_config* cfg) {
   G.curtime = 1;
   G.newtime = 2;
   G.mixtime = 0;
-  G.use_upwind3 = G.use_centered = false;
+  G.use_upwind3 = G.use_centered = G.use_lw_lim = false;
+  G.lw_flux_ready = false;
+  G.lw_coef_dirty = true;
   for (int n = 0; n < G.nt; n++) {
     if (cfg->tadvect_itype[n] == POP_TADVECT_UPWIND3) G.use_upwind3 = true;
     else if (cfg->tadvect_itype[n] == POP_TADVECT_CENTERED) G.use_centered = true;
+    else if (cfg->tadvect_itype[n] == POP_TADVECT_LW_LIM) G.use_lw_lim = true;
     else POP_REQUIRE(false, "pop_init: tadvect_itype[%d]=%d not supported", n, cfg->tadvect_itype[n]);
   }
   POP_REQUIRE(cfg->hmix_tracer_itype == POP_HMIX_DEL2 || cfg->hmix_tracer_itype == POP_HMIX_DEL4 ||
@@ -376,6 +379,7 @@ extern "C" int pop_finalize(void) {
   p2p_teardown();
   evp_release();
   deep_release();
+  lw_release();
   for (auto& kv : G.fields) cudaFree(kv.second.p);
   G.fields.clear();
   for (auto& kv : G.stage) cudaFree(kv.second.first);

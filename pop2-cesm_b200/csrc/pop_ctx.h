@@ -111,7 +111,9 @@ struct Ctx {
   // hmix / misc scalars
   double ah = 0, am = 0, uarea_equator = 0;
   int vdc_nk = 0, vdc_k0 = 1, vdc_nd = 1, vvc_nk = 0;
-  bool use_upwind3 = false, use_centered = false;
+  bool use_upwind3 = false, use_centered = false, use_lw_lim = false;
+  bool lw_flux_ready = false;  // comp_flux_vel_ghost has run for the current velocities
+  bool lw_coef_dirty = true;   // grid coefficients of lw_lim follow pop_set_grid
   // solver
   double residualNorm = 0, convergenceCriterion = 0, rmsResidual = 0;
   int numIterations = 0;
@@ -338,6 +340,10 @@ int solvers_prep_dev();
 int solvers_evp_diagnostics(int* nsub, int* nland, double* selfcheck);
 void evp_release();
 void deep_release();
+// lw_lim advection (pop_lwlim.cu)
+void lw_release();
+int lw_flux_prepare_dev(const double* U, const double* V, const double* DH);  // comp_flux_vel_ghost
+int lw_lim_dev(const int* slots, const double* TMIX, int k0, int k1);         // L(T) of levels k0..k1 -> LW_LTK
 int solvers_diagonal_dev(const double* diagCorr);
 int solvers_run_dev(double* X, const double* B);
 int btrop_operator_dev(double* AX, const double* X);

@@ -489,6 +489,8 @@ int set_grid_host(const double* ULAT_S, const double* HTN_S, const double* HTE_S
   G.grid_set = true;
   G.rf_ready = false;  // budget areas depend on KMT/TAREA
   G.gm_dirty = true;
+  G.lw_coef_dirty = true;
+  G.lw_flux_ready = false;
   POP_TRY(set_timestep(POP_TS_LEAPFROG));
   POP_TRY(upload_vert_const());
   POP_TRY(solvers_init_dev());

@@ -27,6 +27,7 @@ struct TracerArgs {
   double* WTK;   // slab modes: carried vertical velocity at the top of level k (in/out)
   double *VTF, *AUX;  // slab modes: carried fluxes (nxb,nyb,nt)
   const double* HDT;  // GM: precomputed horizontal-mixing tendency (nxb,nyb,km,nt), pop_gm.cu; else null
+  const double* LWL;  // lw_lim: precomputed advective tendency of the tracers of this pass (nxb,nyb,km,NTC), pop_lwlim.cu
   int k0, k1;    // level range (1-based, inclusive)
   int n0, nn;    // tracers n0 .. n0+nn-1 (0-based)
   int adv[NTC];  // advection scheme of each tracer of this pass
@@ -310,7 +311,9 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       if (DO_ADV) {
         const double T = tc[TIX(tx, ty)];
         const double Tp = (k < km) ? (have_next ? n_tc[m * POP_TN + TIX(tx, ty)] : a.TCUR[lev + n2]) : 0.0;
-        if (a.adv[m] == POP_TADVECT_CENTERED) {  // advection.F90:2243-2301
+        if (a.adv[m] == POP_TADVECT_LW_LIM) {  // advection.F90:2684-3280, computed by lw_lim_kernel
+          L = a.LWL[((size_t)m * km + (k - 1)) * n2 + q];
+        } else if (a.adv[m] == POP_TADVECT_CENTERED) {  // advection.F90:2243-2301
           L = 0.5 *
               ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
                ute * tc[TIX(tx + 1, ty)] - utw * tc[TIX(tx - 1, ty)]) *
@@ -786,6 +789,9 @@ int tracer_column(int mode, int k, const TracerIO& io) {
   a.implicit_vmix = G.cfg.implicit_vertical_mix;
   a.predictor = (a.varthick && G.cfg.lpressure_avg && G.leapfrogts);
   a.ah = G.ah;
+  // lw_lim needs the flux velocities two cells out (comp_flux_vel_ghost, baroclinic.F90:667): the fused driver makes
+  // them here, the slab entry point pop_advt expects pop_comp_flux_vel_ghost to have been called
+  if (mode == TR_FULL && G.use_lw_lim) POP_TRY(lw_flux_prepare_dev(io.UCUR, io.VCUR, io.DH));
   if (mode == TR_FULL) { a.k0 = 1; a.k1 = G.km; }
   else {
     POP_REQUIRE(k >= 1 && k <= G.km, "tracer slab operator: k=%d out of range", k);
@@ -795,15 +801,23 @@ int tracer_column(int mode, int k, const TracerIO& io) {
   for (int n0 = 0; n0 < G.nt; n0 += NTC) {
     a.n0 = n0;
     a.nn = (G.nt - n0 < NTC) ? G.nt - n0 : NTC;
-    bool upw = false;
+    bool upw = false, lwl = false;
+    int lw_slots[NTC];
+    for (int m = 0; m < NTC; m++) lw_slots[m] = -1;
     for (int m = 0; m < a.nn; m++) {
       a.adv[m] = G.cfg.tadvect_itype[n0 + m];
       if (a.adv[m] == POP_TADVECT_UPWIND3) upw = true;
+      if (a.adv[m] == POP_TADVECT_LW_LIM) { lwl = true; lw_slots[m] = n0 + m; }
+    }
+    a.LWL = nullptr;
+    if (lwl && (mode == TR_FULL || mode == TR_ADVT)) {  // X of lw_lim is the mix-time field (advection.F90:2806)
+      POP_TRY(lw_lim_dev(lw_slots, io.TMIX, a.k0, a.k1));
+      a.LWL = fld("LW_LTK");
     }
     switch (mode) {
       case TR_FULL: {
         // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
-        const bool fast_ok = !gm && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+        const bool fast_ok = !gm && !lwl && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
                              a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
         if (fast_ok) {
           TracerFastArgs f;

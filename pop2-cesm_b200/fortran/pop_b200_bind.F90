@@ -170,6 +170,13 @@ module pop_b200_bind
          integer (c_int) :: ierr
       end function
 
+      ! advection.F90:1014   comp_flux_vel_ghost(DH, errorCode)
+      function pop_comp_flux_vel_ghost(DH) bind(C, name='pop_comp_flux_vel_ghost') result(ierr)
+         import :: c_int, c_double
+         real (c_double), intent(in) :: DH(*)
+         integer (c_int) :: ierr
+      end function
+
       ! advection.F90:1127   advu(k,LUK,LVK,WUK,UUU,VVV,this_block)
       function pop_advu(k, LUK, LVK, WUK, UUU, VVV, blk) bind(C, name='pop_advu') result(ierr)
          import :: c_int, c_double, pop_block

@@ -55,6 +55,9 @@ def main():
         kw.update(ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
                   lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21, given_vmix=True,
                   solver_choice=c.SOLVER_PCSI, dtt=600.0, partial_bottom_cells=1)
+    elif which == "lwlim":  # lw_lim advection: flux velocities two cells out cross the strip boundaries (comp_flux_vel_ghost)
+        kw.update(ns=c.BNDY_TRIPOLE, nt=4, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=1800.0,
+                  tadvect=[c.TADVECT_CENTERED, c.TADVECT_CENTERED, c.TADVECT_LW_LIM, c.TADVECT_LW_LIM])
     elif which == "evp":   # EVP is block-local: the strips are compared with the oracle run on the same 1 x P blocks
         kw.update(ns=c.BNDY_TRIPOLE, given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=7200.0,
                   preconditioner_choice=c.PRECOND_EVP, max_lanczos_step=100, lanczos_convergence_criterion=0.15)

@@ -42,6 +42,11 @@ def get_case(key):
                        am=-27.0e21, given_vmix=True, partial_bottom_cells=1)
     elif key == "pbc_del2":
         cs = make_case(40, 28, 7, nt=2, seed=16, given_vmix=True, partial_bottom_cells=1)
+    elif key == "lw_lim":      # limited advection next to the centred scheme, tripole
+        cs = make_case(36, 24, 7, nt=3, seed=17, ns=c.BNDY_TRIPOLE, given_vmix=True,
+                       tadvect=[c.TADVECT_LW_LIM, c.TADVECT_CENTERED, c.TADVECT_LW_LIM])
+    elif key == "pbc_lw_lim":
+        cs = make_case(40, 28, 7, nt=2, seed=18, given_vmix=True, partial_bottom_cells=1, tadvect=c.TADVECT_LW_LIM)
     elif key == "gm_general":  # general skew-flux form: different thickness diffusivity and slope limits
         cs = make_case(36, 24, 6, nt=3, seed=14, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_GM,
                        ah_gm=0.6e7, ah_bolus=0.4e7, ah_bkg_srfbl=0.5e7, slm_r=0.3, slm_b=0.2)
@@ -134,6 +139,33 @@ def test_hdifft_advt_vdifft(which):
         p.vdifft(k, vq, To, STF)
         assert np.array_equal(phys(vo), phys(vq)), ("vdifft", k)
     assert np.abs(phys(lo)).max() >= 0.0 and np.abs(phys(ho)).max() > 0.0
+
+
+@pytest.mark.parametrize("which", ["lw_lim", "pbc_lw_lim"])
+def test_advt_lw_lim_level_by_level(which):
+    """advt with tadvect_itype = lw_lim through the reference's own calling sequence: comp_flux_vel_ghost(DH) once
+    (baroclinic.F90:667), then advt(k) for k = 1..km with WTK carried by the caller (baroclinic.F90:1989-2010).  TMIX
+    (the advected field of lw_lim) differs from TRCR (the advected field of the centred scheme)."""
+    cs, o, p = get_case(which)
+    Tc, Uc, Vc, _ = fields(o, c.TIME_CUR)
+    To = fields(o, c.TIME_OLD)[0]
+    nt, km = o.nt, o.km
+    f_a = osig(o.L, "o_advt", [ci, vp, vp, vp, vp, vp, vp, ci])
+    kmt = o.view("KMT", 1, (), np.int32)[0]
+    DH = np.ascontiguousarray(0.01 * np.sin(np.arange(o.nyb * o.nxb)).reshape(o.nyb, o.nxb) * (kmt > 0))
+    o.view("DH", 0, ())[0][:] = DH
+    osig(o.L, "o_comp_flux_vel_ghost", [])()
+    p.comp_flux_vel_ghost(DH)
+    wo, wp = DH.copy(), DH.copy()
+    seen = 0.0
+    for k in range(1, km + 1):
+        lo, lp = np.zeros((nt, o.nyb, o.nxb)), np.zeros((nt, o.nyb, o.nxb))
+        f_a(k, op(lo), op(wo), op(To), op(Tc), op(Uc), op(Vc), 0)
+        p.advt(k, lp, wp, To, Tc, Uc, Vc)
+        assert np.array_equal(phys(lo), phys(lp)), ("advt", k, np.abs(phys(lo) - phys(lp)).max())
+        assert np.array_equal(phys(wo), phys(wp)), ("WTK", k)
+        seen = max(seen, np.abs(phys(lo)[0]).max())
+    assert seen > 0.0
 
 
 @pytest.mark.parametrize("which", ["gm", "gm_general"])

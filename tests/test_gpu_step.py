@@ -72,6 +72,20 @@ CASES = {
     # ... and with explicit vertical mixing (vdifft / vdiffu carry the cell thicknesses)
     "pbc_explicit_vmix": dict(nx=40, ny=32, km=6, seed=34, implicit_vertical_mix=0, convection_diff=0,
                               partial_bottom_cells=1),
+    # lw_lim advection (advection.F90:2684-3280 + comp_flux_vel_ghost :1014-1120) for every tracer ...
+    "lw_lim_chrongear": dict(nx=48, ny=36, km=8, nt=3, seed=35, tadvect=c.TADVECT_LW_LIM, convergence_criterion=1e-12),
+    # ... mixed with the centred scheme on the tripole grid (config 5: passive tracers on lw_lim) ...
+    "lw_lim_mixed_tripole_pcsi": dict(nx=48, ny=36, km=8, nt=4, seed=36, ns=c.BNDY_TRIPOLE,
+                                      tadvect=[c.TADVECT_CENTERED, c.TADVECT_CENTERED, c.TADVECT_LW_LIM, c.TADVECT_LW_LIM],
+                                      hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1,
+                                      lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21, given_vmix=True,
+                                      solver_choice=c.SOLVER_PCSI, dtt=600.0),
+    # ... mixed with upwind3 (an odd tracer count: a half-filled last pass), cyclic north-south ...
+    "lw_lim_upwind3_cyclic": dict(nx=40, ny=32, km=7, nt=3, seed=37, ns=c.BNDY_CYCLIC,
+                                  tadvect=[c.TADVECT_UPWIND3, c.TADVECT_LW_LIM, c.TADVECT_LW_LIM], solver_choice=c.SOLVER_PCG),
+    # ... and with partial bottom cells
+    "pbc_lw_lim": dict(nx=40, ny=32, km=8, nt=3, seed=38, tadvect=c.TADVECT_LW_LIM, given_vmix=True,
+                       convergence_criterion=1e-12, partial_bottom_cells=1),
     # explicit vertical mixing, rigid-lid-free options off: no pressure averaging, no implicit Coriolis
     "explicit_options": dict(nx=40, ny=32, km=6, seed=24, implicit_vertical_mix=0, convection_diff=0,
                              lpressure_avg=0, impcor=0, lbouss_correct=0, state_range_iopt=c.STATE_RANGE_IGNORE),

@@ -242,3 +242,86 @@ def test_partial_bottom_cells_conserve_tracer_content():
     ocean = cs.kmt > 0
     assert np.all(ht[ocean] <= zw[cs.kmt[ocean]] + 1e-9) and np.all(ht[ocean] > zw[cs.kmt[ocean] - 1])
     np.testing.assert_array_equal(ht[ocean], zw[cs.kmt[ocean] - 1] + cs.dzbc[ocean])
+
+
+def _lw_case(**kw):
+    base = dict(nt=3, seed=61, tadvect=c.TADVECT_LW_LIM, sfc_layer_type=c.SFC_RIGID, lpressure_avg=0, given_vmix=True)
+    base.update(kw)
+    cs = make_case(64, 40, 10, **base)
+    for f in ("STF", "TFW"):
+        cs.forcing[f][:] = 0.0
+    return cs
+
+
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_lw_lim_conserves_tracer_content_and_is_block_independent(pbc):
+    """lw_lim (advection.F90:2684-3280) is in flux form: with a rigid lid and no surface fluxes the volume integral of
+    every tracer is conserved -- across block boundaries too, which needs the flux velocities of the outermost ghost
+    cells (comp_flux_vel_ghost, :1014-1120) to be the neighbouring block's own.  And the answer must not depend on the
+    block decomposition at all: 4 x 2 blocks give the bits of a single block."""
+    cs = _lw_case(partial_bottom_cells=pbc)
+    lev = np.arange(1, cs.km + 1)[:, None, None]
+    dzt = np.where(lev == cs.kmt[None], cs.dzbc[None], cs.dz[:, None, None]) if pbc else cs.dz[:, None, None] + 0 * lev
+    vol = (lev <= cs.kmt[None]) * dzt * (cs.grid["DXT"] * cs.grid["DYT"])[None]
+    res = []
+    for bs in ((16, 20), None):
+        # (REPRODUCIBLE sums: the solver's dot products do not depend on the block order either)
+        o = load_oracle(cs, block_size=bs, reproducible=True) if bs else load_oracle(cs, reproducible=True)
+        told = oracle_global(o, "TRACER", c.TIME_OLD).reshape(3, cs.km, cs.ny, cs.nx).copy()
+        for ts in (c.TS_EULER, c.TS_LEAPFROG):
+            assert o.step(ts) == 0
+        t = oracle_global(o, "TRACER", c.TIME_CUR).reshape(3, cs.km, cs.ny, cs.nx).copy()
+        res.append(t)
+        if bs:
+            o2 = load_oracle(cs, block_size=bs)
+            assert o2.step(c.TS_EULER) == 0
+            t1 = oracle_global(o2, "TRACER", c.TIME_CUR).reshape(3, cs.km, cs.ny, cs.nx)
+            for n in range(3):
+                before, after = np.sum(told[n] * vol), np.sum(t1[n] * vol)
+                assert abs(after - before) <= 1.0e-12 * np.sum(np.abs(told[n]) * vol), (n, before, after)
+    assert np.array_equal(res[0], res[1])
+
+
+def test_lw_lim_limits_where_centered_advection_overshoots():
+    """The one-dimensional flux limiters keep a front between two plateaus within its bounds, where the centred scheme
+    (advection.F90:2139-2306) over- and undershoots: T - dt L(T) of one forward step."""
+    out = {}
+    for scheme in (c.TADVECT_LW_LIM, c.TADVECT_CENTERED):
+        cs = _lw_case(tadvect=scheme, nt=2, flat=True)
+        o = load_oracle(cs)
+        o.L.oracle_set_timestep(c.TS_EULER)
+        km, nt = o.km, o.nt
+        U = o.view("UVEL", c.TIME_CUR, (km,))[0].copy()
+        V = o.view("VVEL", c.TIME_CUR, (km,))[0].copy()
+        # a strong zonal flow with a uniform mass flux U*DYU (no divergence, hence no vertical velocity) that moves the
+        # front a good fraction of a cell: CFL <= 0.3 in x
+        dxt, dyu = o.view("DXT", 1, ())[0], o.view("DYU", 1, ())[0]
+        kmu = o.view("KMU", 1, (), np.int32)[0]
+        dt = cs.cfg.dtt
+        flux = 0.3 * np.min(dxt * dyu) / dt
+        for k in range(km):
+            U[k] = flux / dyu * (kmu > k)
+            V[k] = 0.0
+        o.view("UVEL", c.TIME_CUR, (km,))[0][:] = U
+        o.view("VVEL", c.TIME_CUR, (km,))[0][:] = V
+        kmt = o.view("KMT", 1, (), np.int32)[0]
+        T = np.zeros((nt, km, o.nyb, o.nxb))
+        ii = np.arange(o.nxb)[None, :] * np.ones((o.nyb, 1))
+        for k in range(km):
+            T[:, k] = np.where((ii > 20) & (ii < 40), 1.0, 0.0) * (kmt > k)
+        T = np.ascontiguousarray(T)
+        if scheme == c.TADVECT_LW_LIM:
+            osig(o.L, "o_comp_flux_vel_ghost", [])()
+        f_a = osig(o.L, "o_advt", [ci, vp, vp, vp, vp, vp, vp, ci])
+        WTK = np.zeros((o.nyb, o.nxb))
+        new = np.zeros((km, o.nyb, o.nxb))
+        for k in range(1, km + 1):
+            L = np.zeros((nt, o.nyb, o.nxb))
+            f_a(k, op(L), op(WTK), op(T), op(T), op(U), op(V), 0)
+            new[k - 1] = T[0, k - 1] - dt * L[0]
+        out[scheme] = new[:, 2:-2, 2:-2]
+    lw, cen = out[c.TADVECT_LW_LIM], out[c.TADVECT_CENTERED]
+    assert lw.min() >= -1e-12 and lw.max() <= 1.0 + 1e-12
+    assert cen.min() < -1e-3 and cen.max() > 1.0 + 1e-3        # the unlimited scheme rings
+    assert np.abs(lw - cen).max() > 1e-3
+    assert abs(lw[0].sum() - cen[0].sum()) <= 1e-9 * cen[0].sum()   # both move the same amount of tracer
