@@ -343,7 +343,7 @@ void deep_release();
 // lw_lim advection (pop_lwlim.cu)
 void lw_release();
 int lw_flux_prepare_dev(const double* U, const double* V, const double* DH);  // comp_flux_vel_ghost
-int lw_lim_dev(const int* slots, const double* TMIX, int k0, int k1);         // L(T) of levels k0..k1 -> LW_LTK
+int lw_lim_dev(const int* slots, const double* TMIX, int k0, int k1, double* out, size_t tstride, size_t lstride);
 int solvers_diagonal_dev(const double* diagCorr);
 int solvers_run_dev(double* X, const double* B);
 int btrop_operator_dev(double* AX, const double* X);

@@ -199,7 +199,11 @@ struct LwArgs {
   int nxb, nyb, km, k0, k1;
   size_t n2;
   const double* X;      // TMIX (nxb,nyb,km,nt)
-  double* LTK;          // (nxb,nyb,km,LW_NTC): L(T) of the tracers of this pass
+  // L(T) of tracer n, level k goes to LTK[n * tstride + (k-1) * lstride + q], ocean cells only: the caller's output
+  // array itself (TRACER(new) of the fused driver, the LTK slab of pop_advt), where the column kernel picks it up
+  // before it overwrites the cell with its own result -- no scratch copy of a 4-d field
+  double* LTK;
+  size_t tstride, lstride;
   int n[LW_NTC];        // 0-based tracer index of each slot, -1: slot unused
   const double *UTE3, *VTN3, *WTKB3, *DH, *TAREA_R, *DXT, *DYT, *PX, *PY, *E2U, *N2V, *DZT;
   const int* KMT;
@@ -417,9 +421,9 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
       else DIV = (wtk - wtkb) * c_vc.dzr[k] + CE + CW + CN + CS;
 #pragma unroll
       for (int m = 0; m < LW_NTC; m++) {
-        if (a.n[m] < 0) continue;
+        if (a.n[m] < 0 || k > kmt) continue;
         const double L = xout[m] + CN * s_tn[m][c] + CS * s_tn[m][c - LW_EX] - (CN + CS - DIV) * Xk[m];
-        a.LTK[((size_t)m * km + (k - 1)) * n2 + q] = L;
+        a.LTK[(size_t)a.n[m] * a.tstride + (size_t)(k - 1) * a.lstride + q] = L;
       }
     }
     // ---- next level
@@ -432,14 +436,13 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
   }
 }
 
-// L(T) of levels k0..k1 for the tracers `slots` (0-based indices, -1: unused) into LW_LTK
-int lw_lim_dev(const int* slots, const double* TMIX, int k0, int k1) {
+// L(T) of levels k0..k1 for the tracers `slots` (0-based indices, -1: unused) into `out` (see LwArgs::LTK)
+int lw_lim_dev(const int* slots, const double* TMIX, int k0, int k1, double* out, size_t tstride, size_t lstride) {
   POP_REQUIRE(G.lw_flux_ready, "advt (lw_lim): comp_flux_vel_ghost has not been called for this step");
   ScopedTimer tm("ADVT_LW_LIM");
-  POP_TRY(alloc_field("LW_LTK", G.km * LW_NTC, false));
   LwArgs a;
   a.nxb = G.nxb; a.nyb = G.nyb; a.km = G.km; a.k0 = k0; a.k1 = k1; a.n2 = G.n2;
-  a.X = TMIX; a.LTK = fld("LW_LTK");
+  a.X = TMIX; a.LTK = out; a.tstride = tstride; a.lstride = lstride;
   for (int m = 0; m < LW_NTC; m++) a.n[m] = slots[m];
   a.UTE3 = fld("LW_UTE"); a.VTN3 = fld("LW_VTN"); a.WTKB3 = fld("LW_WTKB"); a.DH = fld("DH");
   a.TAREA_R = fld("TAREA_R"); a.DXT = fld("DXT"); a.DYT = fld("DYT");

@@ -27,7 +27,7 @@ struct TracerArgs {
   double* WTK;   // slab modes: carried vertical velocity at the top of level k (in/out)
   double *VTF, *AUX;  // slab modes: carried fluxes (nxb,nyb,nt)
   const double* HDT;  // GM: precomputed horizontal-mixing tendency (nxb,nyb,km,nt), pop_gm.cu; else null
-  const double* LWL;  // lw_lim: precomputed advective tendency of the tracers of this pass (nxb,nyb,km,NTC), pop_lwlim.cu
+  int lwl;            // lw_lim: the advective tendency of such tracers is waiting in OUT (ocean cells), pop_lwlim.cu
   int k0, k1;    // level range (1-based, inclusive)
   int n0, nn;    // tracers n0 .. n0+nn-1 (0-based)
   int adv[NTC];  // advection scheme of each tracer of this pass
@@ -311,8 +311,8 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
       if (DO_ADV) {
         const double T = tc[TIX(tx, ty)];
         const double Tp = (k < km) ? (have_next ? n_tc[m * POP_TN + TIX(tx, ty)] : a.TCUR[lev + n2]) : 0.0;
-        if (a.adv[m] == POP_TADVECT_LW_LIM) {  // advection.F90:2684-3280, computed by lw_lim_kernel
-          L = a.LWL[((size_t)m * km + (k - 1)) * n2 + q];
+        if (a.adv[m] == POP_TADVECT_LW_LIM) {  // advection.F90:2684-3280, left in the output cell by lw_lim_kernel
+          L = (k <= kmt) ? a.OUT[(MODE == TR_FULL) ? lev : (size_t)n * n2 + q] : 0.0;
         } else if (a.adv[m] == POP_TADVECT_CENTERED) {  // advection.F90:2243-2301
           L = 0.5 *
               ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
@@ -809,10 +809,11 @@ int tracer_column(int mode, int k, const TracerIO& io) {
       if (a.adv[m] == POP_TADVECT_UPWIND3) upw = true;
       if (a.adv[m] == POP_TADVECT_LW_LIM) { lwl = true; lw_slots[m] = n0 + m; }
     }
-    a.LWL = nullptr;
+    a.lwl = 0;
     if (lwl && (mode == TR_FULL || mode == TR_ADVT)) {  // X of lw_lim is the mix-time field (advection.F90:2806)
-      POP_TRY(lw_lim_dev(lw_slots, io.TMIX, a.k0, a.k1));
-      a.LWL = fld("LW_LTK");
+      if (mode == TR_FULL) POP_TRY(lw_lim_dev(lw_slots, io.TMIX, a.k0, a.k1, a.OUT, G.n3, G.n2));
+      else POP_TRY(lw_lim_dev(lw_slots, io.TMIX, a.k0, a.k1, a.OUT, G.n2, 0));
+      a.lwl = 1;
     }
     switch (mode) {
       case TR_FULL: {
