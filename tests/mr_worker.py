@@ -35,7 +35,8 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     which = sys.argv[1] if len(sys.argv) > 1 else "pcsi"
-    kw = dict(nx=96, ny=64, km=6, seed=81)
+    # (8 strips: 16 rows each, so that the deep-strip layout of the P-CSI passes -- 12 ghost rows -- is in play there too)
+    kw = dict(nx=96, ny=64 if world < 8 else 128, km=6, seed=81)
     if which in ("pcsi22", "pcsi_plain"):
         # the P-CSI passes run on deep strips by default (12 ghost rows); also 22 rows deep, and the plain layout
         os.environ.update({"POP_B200_DEEP_HALO": "22"} if which == "pcsi22" else {"POP_B200_NO_DEEP_HALO": "1"})
