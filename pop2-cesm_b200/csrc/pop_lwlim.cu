@@ -223,8 +223,13 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
   __shared__ double s_xs[LW_NTC][LW_NT], s_te[LW_NTC][LW_NT];
   double (*s_tn)[LW_NT] = s_te;  // the north-face values reuse the tile of the east-face values (a barrier apart)
   __shared__ int s_kmt[LW_NT];
+  __shared__ double s_rdt[POP_KMAX + 2], s_p5[POP_KMAX + 2];  // 1 / c2dtt(k); p5_dz_ph_r(k) (:599-600), 0 at k = 0
   const int c = threadIdx.x, ei = c % LW_EX, ej = c / LW_EX;
   const int nxb = a.nxb, nyb = a.nyb, km = a.km;
+  for (int k = c; k <= km + 1; k += LW_NT) {
+    s_rdt[k] = (k >= 1 && k <= km) ? 1.0 / c_vc.c2dtt[k] : 0.0;
+    s_p5[k] = (k >= 1 && k < km) ? 1.0 / (c_vc.dz[k] + c_vc.dz[k + 1]) : ((k == km) ? 0.5 / c_vc.dz[km] : 0.0);
+  }
   const int gi = POP_NGHOST + blockIdx.x * LW_TX - 2 + ei, gj = POP_NGHOST + blockIdx.y * LW_TY - 2 + ej;  // 0-based
   const bool valid = (gi < nxb && gj < nyb);  // gi, gj >= 0 always
   const size_t q = valid ? (size_t)gj * nxb + gi : 0, n2 = a.n2;
@@ -254,13 +259,12 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
   // vertical velocity at the top of level k as lw_lim sees it (:2780-2784)
   auto wtop = [&](int k) { return (k == 1) ? ((a.varthick || !valid) ? 0.0 : a.DH[q]) : wlev(k - 1); };
   auto dzt_at = [&](int k) { return (PBC && valid) ? a.DZT[(size_t)k * n2 + q] : 0.0; };
-  // LW_z, MU_z of the bottom face of level k (:2911-2975) and the limited flux through it (:3096-3137)
-  auto zflux = [&](int k, double wt, double wb, double wbp1, double xm, double xk, double xp, double xpp) {
-    if (!(k + 1 <= kmt)) return 0.0;
-    const double adv_dt = c_vc.c2dtt[k];
-    double lwz = 0.0, muz = 0.0;
+  // LW_z, MU_z of the bottom face of level k (:2911-2975): tracer independent
+  auto zcoef = [&](int k, double wt, double wb, double wbp1, double& lwz, double& muz) {
+    lwz = 0.0; muz = 0.0;
+    if (!(k + 1 <= kmt)) return;
+    const double adv_dt = c_vc.c2dtt[k], adv_dt_r = s_rdt[k];
     if (PBC) {
-      const double adv_dt_r = 1.0 / adv_dt;
       const double zk = dzt_at(k), zp = dzt_at(k + 1);
       if (wb > 0.0) {
         lwz = (zp - adv_dt * wb) / (zk + zp);
@@ -272,21 +276,21 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
         else if (wt > 0.0) muz = -wt / wb * (zk - adv_dt * wt) / (dzt_at(k - 1) + zk);
       }
     } else {
-      const double adv_dt_r = 1.0 / adv_dt;
-      const double p5k = (k < km) ? 1.0 / (c_vc.dz[k] + c_vc.dz[k + 1]) : 0.5 / c_vc.dz[km];
+      const double p5k = s_p5[k];
       if (wb > 0.0) {
         lwz = c_vc.dz[k + 1] * p5k - (adv_dt * p5k) * wb;
         if (wbp1 > 0.0) muz = (c_vc.dz[k + 1] * adv_dt_r - wbp1) / wb;
-        else if (wbp1 < 0.0) {
-          const double p5kp1 = (k + 1 < km) ? 1.0 / (c_vc.dz[k + 1] + c_vc.dz[k + 2]) : 0.5 / c_vc.dz[km];
-          muz = -wbp1 / wb * (c_vc.dz[k + 1] + adv_dt * wbp1) * p5kp1;
-        }
+        else if (wbp1 < 0.0) muz = -wbp1 / wb * (c_vc.dz[k + 1] + adv_dt * wbp1) * s_p5[k + 1];
       } else if (wb < 0.0) {
         lwz = c_vc.dz[k] * p5k + (adv_dt * p5k) * wb;
         if (wt < 0.0) muz = -(c_vc.dz[k] * adv_dt_r + wt) / wb;
-        else if (wt > 0.0) muz = -wt / wb * (c_vc.dz[k] - adv_dt * wt) * ((k > 1) ? 1.0 / (c_vc.dz[k - 1] + c_vc.dz[k]) : 0.0);
+        else if (wt > 0.0) muz = -wt / wb * (c_vc.dz[k] - adv_dt * wt) * s_p5[k - 1];
       }
     }
+  };
+  // the limited flux through that face (:3096-3137)
+  auto zface = [&](int k, double wb, double lwz, double muz, double xm, double xk, double xp, double xpp) {
+    if (!(k + 1 <= kmt)) return 0.0;
     const double dTR = xp - xk;
     if (wb > 0.0) {
       double f = wb * xp;
@@ -307,14 +311,18 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
     return 0.0;
   };
   double wtk = wtop(k0), wtkb = wlev(k0), wtkbp1 = wlev(k0 + 1);
+  __syncthreads();  // s_rdt, s_p5, s_kmt
+  {
+    double lwz0 = 0.0, muz0 = 0.0;
+    if (k0 > 1) zcoef(k0 - 1, wtop(k0 - 1), wtk, wtkb, lwz0, muz0);
 #pragma unroll
-  for (int m = 0; m < LW_NTC; m++) {
-    Xm[m] = level(Xn[m], k0 - 1); Xk[m] = level(Xn[m], k0); Xp[m] = level(Xn[m], k0 + 1); Xpp[m] = level(Xn[m], k0 + 2);
-    // flux through the top face of the first level: WTK_EFF * X at the surface (:2795), else the bottom flux of k0-1
-    if (k0 == 1) aux[m] = wtk * Xk[m];
-    else aux[m] = zflux(k0 - 1, wtop(k0 - 1), wtk, wtkb, level(Xn[m], k0 - 2), Xm[m], Xk[m], Xp[m]);
+    for (int m = 0; m < LW_NTC; m++) {
+      Xm[m] = level(Xn[m], k0 - 1); Xk[m] = level(Xn[m], k0); Xp[m] = level(Xn[m], k0 + 1); Xpp[m] = level(Xn[m], k0 + 2);
+      // flux through the top face of the first level: WTK_EFF * X at the surface (:2795), else the bottom flux of k0-1
+      if (k0 == 1) aux[m] = wtk * Xk[m];
+      else aux[m] = zface(k0 - 1, wtk, lwz0, muz0, level(Xn[m], k0 - 2), Xm[m], Xk[m], Xp[m]);
+    }
   }
-  __syncthreads();
   for (int k = k0; k <= a.k1; k++) {
     const double adv_dt = c_vc.c2dtt[k];
     const size_t l = (size_t)(k - 1) * n2 + q;
@@ -334,9 +342,11 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
     s_lwy[c] = (vn > 0.0) ? (dyt - vn) * py : ((vn < 0.0) ? (dytn + vn) * py : dyt * py);
     // ---- z sweep (:3096-3149)
     double xout[LW_NTC], xs[LW_NTC];
+    double lwz, muz;
+    zcoef(k, wtk, wtkb, wtkbp1, lwz, muz);
 #pragma unroll
     for (int m = 0; m < LW_NTC; m++) {
-      const double auxb = zflux(k, wtk, wtkb, wtkbp1, Xm[m], Xk[m], Xp[m], Xpp[m]);
+      const double auxb = zface(k, wtkb, lwz, muz, Xm[m], Xk[m], Xp[m], Xpp[m]);
       if (PBC) xout[m] = (aux[m] - auxb - (wtk - wtkb) * Xk[m]) / dzk;
       else xout[m] = (aux[m] - auxb - (wtk - wtkb) * Xk[m]) * c_vc.dzr[k];
       if (!valid) xout[m] = 0.0;

@@ -502,6 +502,7 @@ struct TracerFastArgs {
   const double *STF, *TFW, *DH, *POLD, *PCUR;
   double* OUT;
   int n0;                      // first tracer (0-based) of the pair
+  int lw[NTC];                 // tracer m is advected by lw_lim: its L(T) waits in OUT (ocean cells), pop_lwlim.cu
   int vdc_lev0[NTC], vdc_kstr;  // VDC level of tracer m at level k: vdc_lev0[m] + k*vdc_kstr
   int lvariable_hmixt, varthick, predictor;
   double ah;
@@ -638,7 +639,10 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
     }
   };
   // ---- carried state
-  double wtk = 0.0, tc_m[NTC], told_c[NTC], vtf[NTC];
+  double wtk = 0.0, tc_m[NTC], told_c[NTC], vtf[NTC], lw_next[NTC];
+#pragma unroll
+  for (int m = 0; m < NTC; m++)  // lw_lim tendency of level 1 (requested before the first wait)
+    lw_next[m] = (a.lw[m] && active) ? a.OUT[((size_t)(a.n0 + m) * km) * n2 + q] : 0.0;
   mbar_wait(&s_bar[0], 0u);
   __syncthreads();  // invariants staged
 #pragma unroll
@@ -685,15 +689,21 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         const double* tc = st + m * POP_TN + oT;
         const double T = tc[0];
         const double Tp = (k < km) ? nst[m * POP_TN + oT] : 0.0;
-        double L = 0.5 *
-                   ((vtn - vts + ute - utw) * T + vtn * tc[POP_TW] - vts * tc[-POP_TW] + ute * tc[1] - utw * tc[-1]) *
-                   tarea_r;
-        if (k == 1) {
-          if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
+        double L;
+        if (a.lw[m]) {  // lw_lim (advection.F90:2684-3280): computed by lw_lim_kernel, one level requested ahead
+          L = (k <= kmt) ? lw_next[m] : 0.0;
+          if (k < km) lw_next[m] = a.OUT[lev + n2];
         } else {
-          L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+          L = 0.5 *
+              ((vtn - vts + ute - utw) * T + vtn * tc[POP_TW] - vts * tc[-POP_TW] + ute * tc[1] - utw * tc[-1]) *
+              tarea_r;
+          if (k == 1) {
+            if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
+          } else {
+            L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+          }
+          if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
         }
-        if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
         tc_m[m] = T;
         // ---- vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
         const double vdc = st[6 * POP_TN + m * POP_NTHREADS + tid];
@@ -818,12 +828,13 @@ int tracer_column(int mode, int k, const TracerIO& io) {
     switch (mode) {
       case TR_FULL: {
         // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
-        const bool fast_ok = !gm && !lwl && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+        const bool fast_ok = !gm && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
                              a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
         if (fast_ok) {
           TracerFastArgs f;
           memset(&f, 0, sizeof(f));
           f.g = a.g; f.STF = a.STF; f.TFW = a.TFW; f.DH = a.DH; f.POLD = a.POLD; f.PCUR = a.PCUR; f.OUT = a.OUT;
+          for (int m = 0; m < NTC; m++) f.lw[m] = (a.adv[m] == POP_TADVECT_LW_LIM) ? 1 : 0;
           f.n0 = n0; f.lvariable_hmixt = a.lvariable_hmixt; f.varthick = a.varthick; f.predictor = a.predictor;
           f.ah = a.ah;
           f.vdc_kstr = (G.vdc_nk == 1) ? 0 : 1;
