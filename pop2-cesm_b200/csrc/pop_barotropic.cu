@@ -1134,9 +1134,13 @@ static int pcsi(double* X, const double* B) {
     Xb[2] = DB.buf + DL_X2 * DB.n2d; Qb[2] = DB.buf + DL_Q2 * DB.n2d;
     valid = gd;
   }
+  // One strip without a cyclic north-south boundary: every ghost cell of (X,Q) has its source in the strip, so the tile
+  // pass writes the ghost cells itself (as on deep strips) and no halo kernel runs between two passes.
+  const bool self_ghost = deep || (G.nranks == 1 && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC &&
+                                   !(getenv("POP_B200_PCSI_HALO_KERNEL") && getenv("POP_B200_PCSI_HALO_KERNEL")[0] == '1'));
   // rows the tile pass may write: on the last strip the rows above the top physical row belong to the fold (or are
   // closed-boundary zeros)
-  const int jw_max = (deep && G.rank == G.nranks - 1) ? je0 : nyv - POP_NGHOST - 1;
+  const int jw_max = (self_ghost && G.rank == G.nranks - 1) ? je0 : nyv - POP_NGHOST - 1;
   const dim3 grid1((unsigned)((G.nxb + PC_TX - 1) / PC_TX), (unsigned)((nyv + PC_TY - 1) / PC_TY), 1);
   const dim3 grid2((unsigned)((G.nxg + P2_TX - 1) / P2_TX), (unsigned)((nyv - 2 * POP_NGHOST + P2_TY - 1) / P2_TY), 1);
   const int nblk1 = (int)(grid1.x * grid1.y), nblk2 = (int)(grid2.x * grid2.y);
@@ -1201,7 +1205,7 @@ static int pcsi(double* X, const double* B) {
       }
       Pcsi2Args a;
       a.v = view;
-      a.deep = deep ? 1 : 0; a.jw_max = jw_max;
+      a.deep = self_ghost ? 1 : 0; a.jw_max = jw_max;
       a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[nxt]; a.Qn = Qb[nxt];
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
       a.om1 = csomga; a.c11 = csy * csomga - 1.0;
@@ -1249,7 +1253,7 @@ static int pcsi(double* X, const double* B) {
         if (sample) G.timer_suppress++;
       }
       if (deep) valid -= 2;
-      else POP_TRY(halo_update(Xb[nxt], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+      else if (!self_ghost) POP_TRY(halo_update(Xb[nxt], 2, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
       adv = 2;
       nblk = nblk2;
       }

@@ -323,11 +323,26 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
       else aux[m] = zface(k0 - 1, wtk, lwz0, muz0, level(Xn[m], k0 - 2), Xm[m], Xk[m], Xp[m]);
     }
   }
+  // running pointers of the level loop (one add per level and array instead of a 64-bit product per access); the flux
+  // velocities of a level are requested one level ahead
+  const int n2i = (int)n2;
+  const double* pu = a.UTE3 + (size_t)(k0 - 1) * n2 + q;
+  const double* pv = a.VTN3 + (size_t)(k0 - 1) * n2 + q;
+  const double* pw = a.WTKB3 + (size_t)(k0 + 1) * n2 + q;  // WTKB of level k + 2
+  const double* pxn[LW_NTC];
+  double* pl[LW_NTC];
+#pragma unroll
+  for (int m = 0; m < LW_NTC; m++) {
+    pxn[m] = Xn[m] ? Xn[m] + (size_t)(k0 + 2) * n2 : nullptr;  // X of level k + 3
+    pl[m] = (a.n[m] >= 0) ? a.LTK + (size_t)a.n[m] * a.tstride + (size_t)(k0 - 1) * a.lstride + q : nullptr;
+  }
+  double ute_n = valid ? *pu : 0.0, vtn_n = valid ? *pv : 0.0;
   for (int k = k0; k <= a.k1; k++) {
     const double adv_dt = c_vc.c2dtt[k];
-    const size_t l = (size_t)(k - 1) * n2 + q;
     // ---- tracer-independent part of the level
-    const double ute = valid ? a.UTE3[l] : 0.0, vtn = valid ? a.VTN3[l] : 0.0;
+    const double ute = ute_n, vtn = vtn_n;
+    pu += n2i; pv += n2i;
+    if (valid && k < a.k1) { ute_n = *pu; vtn_n = *pv; }
     double e2u = e2u0, n2v = n2v0, wgt = tarea_r, dzk = 0.0;
     if (PBC && valid) {  // :609-617, :659-667, :2761-2768
       dzk = a.DZT[(size_t)k * n2 + q];
@@ -433,14 +448,17 @@ __global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
       for (int m = 0; m < LW_NTC; m++) {
         if (a.n[m] < 0 || k > kmt) continue;
         const double L = xout[m] + CN * s_tn[m][c] + CS * s_tn[m][c - LW_EX] - (CN + CS - DIV) * Xk[m];
-        a.LTK[(size_t)a.n[m] * a.tstride + (size_t)(k - 1) * a.lstride + q] = L;
+        *pl[m] = L;
       }
     }
     // ---- next level
-    wtk = wtkb; wtkb = wtkbp1; wtkbp1 = wlev(k + 2);
+    wtk = wtkb; wtkb = wtkbp1; wtkbp1 = (valid && k + 2 <= km) ? *pw : 0.0;
+    pw += n2i;
 #pragma unroll
     for (int m = 0; m < LW_NTC; m++) {
-      Xm[m] = Xk[m]; Xk[m] = Xp[m]; Xp[m] = Xpp[m]; Xpp[m] = level(Xn[m], k + 3);
+      Xm[m] = Xk[m]; Xk[m] = Xp[m]; Xp[m] = Xpp[m]; Xpp[m] = (pxn[m] && k + 3 <= km) ? *pxn[m] : 0.0;
+      if (pxn[m]) pxn[m] += n2i;
+      if (pl[m]) pl[m] += a.lstride;
     }
     __syncthreads();
   }

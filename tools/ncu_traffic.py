@@ -5,7 +5,7 @@
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMES = {"tracer_fast_kernel": "TRACER_UPDATE", "tracer_column_kernel": "TRACER_UPDATE", "momentum_column_kernel": "MOMENTUM_COLUMN",
-         "impvmixt_kernel<0>": "VMIX_TRACER_IMPLICIT", "impvmixt_kernel<(bool)0>": "VMIX_TRACER_IMPLICIT",
+         "impvmixt_kernel<0": "VMIX_TRACER_IMPLICIT", "impvmixt_kernel<(bool)0": "VMIX_TRACER_IMPLICIT",
          "momentum_finish_kernel": "MOMENTUM_FINISH", "state_3d_kernel": "STATE",
          "pcsi_iter2_kernel<0>": "PCSI_PASS2_KERNEL", "pcsi_iter2_kernel<(bool)0>": "PCSI_PASS2_KERNEL"}
 out = {"_source": "ncu --set full: (dram__bytes_read.sum + dram__bytes_write.sum) / units of the captured launch; tools/ncu_traffic.py " + " ".join(sys.argv[1:])}
