@@ -951,7 +951,7 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
         const size_t q = (size_t)gj * nxb + gi;
         a.Qn[q] = qv;
         a.Xn[q] = xv;
-        if (a.deep) {  // the copies a halo update would make of this cell
+        if (a.deep && edge_cta) {  // the copies a halo update would make of this cell (edge tiles only)
           const int nxg = nxb - 2 * POP_NGHOST;
           if (a.do_ew && a.jglob[gj] > 0) {
             if (gi < 2 * POP_NGHOST) { a.Qn[q + nxg] = qv; a.Xn[q + nxg] = xv; }

@@ -1,0 +1,22 @@
+#!/bin/bash
+# round-2 GPU call 15: P-CSI ghost writes restricted to edge tiles: A/B at full size and gx1v7
+mkdir -p gpurun_out
+run() { tag=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e "$@" > gpurun_out/r2c15_$tag.json 2> gpurun_out/r2c15_$tag.err
+  python - "$tag" <<'PY'
+import json, sys
+v = sys.argv[1]
+try:
+    d = json.loads([l for l in open("gpurun_out/r2c15_%s.json" % v) if l.startswith("{")][-1])
+    ph = d["phases_ms_per_step"]
+    print("%-10s step %.2f  TR %.2f  MOMCOL %.2f  VMIX %.2f  STATE %.2f  FIN %.2f  SOLVER %.2f HALO %.2f iters %s" % (v, d["ms_per_step"], ph["TRACER_UPDATE"], ph["MOMENTUM_COLUMN"], ph["VMIX_TRACER_IMPLICIT"], ph["STATE"], ph["MOMENTUM_FINISH"], ph["SOLVER"], ph.get("HALO", 0), d.get("solver_iterations")))
+except Exception as e:
+    print(v, "FAILED", e); import subprocess; print(subprocess.run(["tail", "-2", "gpurun_out/r2c15_%s.err" % v], capture_output=True, text=True).stdout)
+PY
+}
+run base X=1 --
+run halok POP_B200_PCSI_HALO_KERNEL=1 --
+run base2 X=1 --
+run halok2 POP_B200_PCSI_HALO_KERNEL=1 --
+run gx1 X=1 -- --workload gx1v7
+run gx1halok POP_B200_PCSI_HALO_KERNEL=1 -- --workload gx1v7
