@@ -785,7 +785,9 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
   uint64_t* s_bar = (uint64_t*)(sNE + P2_N_2);
   const BtView& v = a.v;
   const int nxb = v.nxb, nyb = v.nyb;
-  const int trow = a.rowsel ? (blockIdx.y == 0 ? 0 : a.nty - 1) : (int)blockIdx.y + a.row0;
+  // rowsel = E > 0: the E first and the E last tile rows (gridDim.y = 2E)
+  const int trow = a.rowsel ? ((int)blockIdx.y < a.rowsel ? (int)blockIdx.y : a.nty - 2 * a.rowsel + (int)blockIdx.y)
+                            : (int)blockIdx.y + a.row0;
   const int i0 = POP_NGHOST + blockIdx.x * P2_TX, j0 = POP_NGHOST + trow * P2_TY;  // 0-based tile origin
   const int tid = threadIdx.x;
   // ---- every operand of both iterations is requested up front (one exposed memory latency per CTA):
@@ -1148,6 +1150,9 @@ static int pcsi(double* X, const double* B) {
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
   // opt-in (POP_B200_OVERLAP_EXCHANGE=1): boundary tile rows first, strip exchange concurrent with the interior tiles
+  // deep strips: interior tile rows of the pass after an exchange run beside the exchange (POP_B200_NO_DEEP_OVERLAP=1: off)
+  const bool deep_overlap = deep && (G.nranks > 1 || G.deep_force) && grid2.y >= 6 && G.stream_x != nullptr &&
+                            !(getenv("POP_B200_NO_DEEP_OVERLAP") && getenv("POP_B200_NO_DEEP_OVERLAP")[0] == '1');
   const bool xover = !deep && blocking && G.overlap_exchange && G.nranks > 1 && G.p2p_on && grid2.y >= 3 &&
                      G.cfg.ew_boundary_type == POP_BNDY_CYCLIC;
   // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
@@ -1199,8 +1204,23 @@ static int pcsi(double* X, const double* B) {
     int nblk;
     if (blocking && m + 2 <= maxIt && !next_is_check) {
       if (check && lagged && pend.valid) POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_chk[pend.slot], 0));
+      // Deep strips: the pass after an exchange is split.  Only the two outermost tile rows on either side read ghost rows
+      // the exchange rewrites (a tile reads two rows beyond itself), so the interior tile rows run beside the exchange
+      // (on its own high-priority stream, launched first) and the edge rows follow it.
+      bool split = false;
       if (deep && valid < 2) {  // the next pass consumes two ghost rows
-        POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
+        if (deep_overlap) {
+          POP_CHECK_CUDA(cudaEventRecord(G.ev_xb, G.stream));
+          POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_x, G.ev_xb, 0));
+          std::swap(G.stream, G.stream_x);
+          const int rcx = halo_exchange_deep(Xb[cur], 2, gd, DB.n2d);
+          std::swap(G.stream, G.stream_x);
+          POP_TRY(rcx);
+          POP_CHECK_CUDA(cudaEventRecord(G.ev_xx, G.stream_x));
+          split = true;
+        } else {
+          POP_TRY(halo_exchange_deep(Xb[cur], 2, gd, DB.n2d));
+        }
         valid = gd;
       }
       Pcsi2Args a;
@@ -1237,6 +1257,18 @@ static int pcsi(double* X, const double* B) {
         POP_CHECK_CUDA(cudaEventRecord(G.ev_xx, G.stream_x));
         POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_xx, 0));
         POP_TRY(halo_ew_own_rows(Xb[nxt], 2));  // east-west ghost columns of the rows the interior tiles wrote
+        adv = 2;
+        nblk = nblk2;
+      } else if (split) {
+        constexpr int E = 2;
+        a.rowsel = 0; a.row0 = E;
+        if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, dim3(grid2.x, grid2.y - 2 * E, 1), P2_NT, smem2, a);
+        else POP_LAUNCH(pcsi_iter2_kernel<false>, dim3(grid2.x, grid2.y - 2 * E, 1), P2_NT, smem2, a);
+        POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_xx, 0));
+        a.rowsel = E; a.row0 = 0;
+        if (check) POP_LAUNCH(pcsi_iter2_kernel<true>, dim3(grid2.x, 2 * E, 1), P2_NT, smem2, a);
+        else POP_LAUNCH(pcsi_iter2_kernel<false>, dim3(grid2.x, 2 * E, 1), P2_NT, smem2, a);
+        valid -= 2;
         adv = 2;
         nblk = nblk2;
       } else {

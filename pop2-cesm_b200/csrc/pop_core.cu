@@ -283,7 +283,10 @@ extern "C" int pop_init(const pop_config* cfg) {
   POP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   // with the opt-in exchange overlap: exchange stream > main stream > side streams (lower number = higher priority)
   const bool want_x = getenv("POP_B200_OVERLAP_EXCHANGE") != nullptr && getenv("POP_B200_OVERLAP_EXCHANGE")[0] == '1';
-  const int prio_main = (want_x && prio_least - prio_greatest >= 2) ? prio_greatest + 1 : prio_greatest;
+  // (the strip exchange of the solver's deep strips and the convergence-check reductions run on streams of their own that
+  // must get their few CTAs scheduled ahead of the pass kernels: main stream one level below the greatest priority)
+  (void)want_x;
+  const int prio_main = (prio_least - prio_greatest >= 2) ? prio_greatest + 1 : prio_greatest;
   if (!G.stream) POP_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio_main));
   if (!G.stream2) {
     // low priority: its CTAs take the slots the main stream's kernels leave free (tails, launch gaps)
