@@ -413,7 +413,8 @@ def run_pop(args):
                                    "GBs": bpc["CLINIC"] * local_cells / (per * 1e-3) / 1e9,
                                    "share_of_step": tm["MOMENTUM_COLUMN"][0] / ms}
     if "MOMENTUM_FINISH" in kern:
-        kern["MOMENTUM_FINISH"]["note"] = "runs on a side stream concurrently with the barotropic solve"
+        kern["MOMENTUM_FINISH"]["note"] = ("runs after the barotropic solve and adds UBTROP/VBTROP(new) in the same pass "
+                                           "(algorithmic 56 B/cell: RHS u,v, VVC, Uold, Vold in, U, V out; ncu sees 72: V(k) is written and read back)")
     # the P-CSI pass kernel (two iterations per launch): 72 B per 2-d point per launch = X,Q,B and the four
     # operator weights read once, Q and X written once; sampled with CUDA events
     pts = float(p_nxb) * p_nyb
@@ -422,8 +423,8 @@ def run_pop(args):
         passes = sum(iters) / 2.0
         kern["PCSI_PASS2_KERNEL"] = {"ms_per_launch": per, "calls": tm["PCSI_PASS2_KERNEL"][1], "launches_per_run": passes,
                                      "GBs": 72.0 * pts / (per * 1e-3) / 1e9, "share_of_step": per * passes / ms,
-                                     "note": "every 16th launch timed, uniformly over the solve (early passes share the GPU with "
-                                             "the velocity-finish kernel on the side stream); share = sampled mean x launches"}
+                                     "note": "every 16th launch timed with CUDA events, uniformly over the solve; "
+                                             "share = sampled mean x launches"}
     traffic = ncu_traffic()
     for n in kern:
         unit = pts if n == "PCSI_PASS2_KERNEL" else local_cells
