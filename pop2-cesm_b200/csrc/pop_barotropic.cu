@@ -1030,8 +1030,9 @@ static int pcsi_evp(double* X, const double* B) {
 // its ten arrays whose strips carry `gd` ghost rows on either side instead of two: after an exchange all gd rows
 // hold the owner's bits, and every iteration makes one more ghost row stale (the pass recomputes the ghost rows
 // redundantly, bit for bit what their owner computes), so ONE exchange serves gd iterations.  Ghost cells with a
-// source in the same strip (east-west wrap, tripole fold) are written by the pass itself.  gd = 2 + a multiple of
-// the tile height keeps the tiles -- and with them the order of the residual sum -- those of the plain layout.
+// source in the same strip (east-west wrap, tripole fold) are written by the pass itself.  The residual sum is a
+// double-double sum over tiles, i.e. the correctly rounded exact sum whatever the tiling: shifting the tiles by the
+// ghost depth changes neither a bit of the answer nor an iteration count (the tests run depths 8, 12 and 22).
 struct DeepBt {
   double* buf = nullptr;  // levels: C N E NE mask B X0 Q0 X1 Q1 X2 Q2
   int* jglob = nullptr;
@@ -1108,8 +1109,20 @@ static int pcsi(double* X, const double* B) {
   G.numIterations = maxIt;
   const bool blocking = !G.no_pcsi_blocking;
   // deep strips: see DeepBt.  Needs the peer-memory exchange, a closed or tripole north-south boundary and strips
-  // at least gd rows high; gd is rounded to 2 + k * tile height.
-  int gd = G.deep_halo >= POP_NGHOST + P2_TY ? POP_NGHOST + (G.deep_halo - POP_NGHOST) / P2_TY * P2_TY : 0;
+  // at least gd rows high.
+  // Depth: at most deep_halo rows (even: a pass consumes two), and among the depths >= 6 the largest one whose pass
+  // still fits the fewest waves of CTAs -- a 3600 x 300 strip with 12 ghost rows is 1824 tiles on 592 resident CTAs
+  // (3.08 waves: a quarter of the pass is tail), with 6 rows it is 1767 (2.98).  POP_B200_DEEP_HALO_EXACT=1: no search.
+  int gd = (G.deep_halo / 2) * 2;
+  if (gd < 4) gd = 0;
+  if (gd > 6 && !(getenv("POP_B200_DEEP_HALO_EXACT") && getenv("POP_B200_DEEP_HALO_EXACT")[0] == '1')) {
+    const long slots = (long)P2_MINB * G.sm_count, tx = (G.nxg + P2_TX - 1) / P2_TX;
+    auto waves = [&](int d) { return ((long)((G.ny_local + 2 * d - 2 * POP_NGHOST + P2_TY - 1) / P2_TY) * tx + slots - 1) / slots; };
+    int best = gd;
+    for (int d = gd - 2; d >= 6; d -= 2)
+      if (waves(d) < waves(best)) best = d;
+    gd = best;
+  }
   const bool deep = blocking && gd > 0 && G.ny_local >= gd && G.cfg.ns_boundary_type != POP_BNDY_CYCLIC &&
                     ((G.nranks > 1 && G.p2p_on && (size_t)8 * gd * G.nxg <= G.p2p_cap) || (G.nranks == 1 && G.deep_force));
   BtView view = bt_view();

@@ -46,10 +46,11 @@ __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const doubl
   if (dzu) {
     if (inb) {
       const double z = dzu[gq];
-      dn = dn * fmin(dzu[gq + nxb], z) / z;
-      ds = ds * fmin(dzu[gq - nxb], z) / z;
-      de = de * fmin(dzu[gq + 1], z) / z;
-      dw = dw * fmin(dzu[gq - 1], z) / z;
+      const RcpD rz = rcp_prepare(z);  // four IEEE quotients by the same thickness: one reciprocal refinement (div_by)
+      dn = div_by(dn * fmin(dzu[gq + nxb], z), rz);
+      ds = div_by(ds * fmin(dzu[gq - nxb], z), rz);
+      de = div_by(de * fmin(dzu[gq + 1], z), rz);
+      dw = div_by(dw * fmin(dzu[gq - 1], z), rz);
     } else {
       dn = ds = de = dw = 0.0;
     }
@@ -300,6 +301,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     constexpr bool pbc = PBC;  // partial bottom cells: g.DZU is set
     const double* dzu_k = pbc ? g.DZU + (size_t)k * n2 : nullptr;
     const double dzu_c = pbc ? dzu_k[q] : 0.0;  // thickness of this U cell
+    const RcpD rzu = pbc ? rcp_prepare(dzu_c) : RcpD{1.0, 1.0};
+    const double h_dzu = pbc ? div_by(0.5, rzu) : 0.0;  // 0.5 / DZU
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
     // ---- advu: advection.F90:1307-1491
     double luk = 0.0, lvk = 0.0;
@@ -320,15 +323,15 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       lvk = 0.5 * (cc * V + vun * s_vc[TIX(tx, ty + 1)] - vus * s_vc[TIX(tx, ty - 1)] +
                    uue * s_vc[TIX(tx + 1, ty)] - uuw * s_vc[TIX(tx - 1, ty)]) * uarea_r;
       if (pbc) {  // :1381-1405
-        luk = luk / dzu_c;
-        lvk = lvk / dzu_c;
+        luk = div_by(luk, rzu);
+        lvk = div_by(lvk, rzu);
       }
       if (k == 1) {
         luk = luk + c_vc.dzr[k] * wuk * U;
         lvk = lvk + c_vc.dzr[k] * wuk * V;
       } else if (pbc) {  // :1443-1447
-        luk = luk + 0.5 / dzu_c * wuk * (u_m + U);
-        lvk = lvk + 0.5 / dzu_c * wuk * (v_m + V);
+        luk = luk + h_dzu * wuk * (u_m + U);
+        lvk = lvk + h_dzu * wuk * (v_m + V);
       } else {
         luk = luk + c_vc.dz2r[k] * wuk * (u_m + U);
         lvk = lvk + c_vc.dz2r[k] * wuk * (v_m + V);
@@ -337,8 +340,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         const double Up = have_next ? n_uc[TIX(tx, ty)] : a.UCUR[lev + n2 + q];
         const double Vp = have_next ? n_vc[TIX(tx, ty)] : a.VCUR[lev + n2 + q];
         if (pbc) {  // :1462-1466
-          luk = luk - 0.5 / dzu_c * wukb * (U + Up);
-          lvk = lvk - 0.5 / dzu_c * wukb * (V + Vp);
+          luk = luk - h_dzu * wukb * (U + Up);
+          lvk = lvk - h_dzu * wukb * (V + Vp);
         } else {
           luk = luk - c_vc.dz2r[k] * wukb * (U + Up);
           lvk = lvk - c_vc.dz2r[k] * wukb * (V + Vp);
@@ -416,8 +419,9 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       if (pbc) {  // vertical_mix.F90:946-958: kp1 = min(k+1, km)
         const double zp = g.DZU[(size_t)((k < km) ? k + 1 : km) * n2 + q];
         const double W = (k < km) ? 0.5 * (dzu_c + zp) : 0.5 * zp;
-        vufb = vvc * (uo_c - uo_p) / W;
-        vvfb = vvc * (vo_c - vo_p) / W;
+        const RcpD rw = rcp_prepare(W);
+        vufb = div_by(vvc * (uo_c - uo_p), rw);
+        vvfb = div_by(vvc * (vo_c - vo_p), rw);
       } else {
         vufb = vvc * (uo_c - uo_p) * c_vc.dzwr[k];
         vvfb = vvc * (vo_c - vo_p) * c_vc.dzwr[k];
@@ -428,8 +432,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         vvfb = vmag * vo_c;
       }
       if (pbc) {  // :991-995
-        vdu = (k <= kmu) ? (vuf - vufb) / dzu_c : 0.0;
-        vdv = (k <= kmu) ? (vvf - vvfb) / dzu_c : 0.0;
+        vdu = (k <= kmu) ? div_by(vuf - vufb, rzu) : 0.0;
+        vdv = (k <= kmu) ? div_by(vvf - vvfb, rzu) : 0.0;
       } else {
         vdu = (k <= kmu) ? (vuf - vufb) * c_vc.dzr[k] : 0.0;
         vdv = (k <= kmu) ? (vvf - vvfb) * c_vc.dzr[k] : 0.0;

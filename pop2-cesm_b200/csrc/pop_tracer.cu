@@ -55,10 +55,11 @@ __device__ __forceinline__ Coef5 tracer_coef(const int* s_kmt, const double* s_d
   if (dzt) {
     if (inb) {
       const double z = dzt[gq];
-      dn = dn * fmin(z, dzt[gq + nxb]) / z;
-      ds = ds * fmin(z, dzt[gq - nxb]) / z;
-      de = de * fmin(z, dzt[gq + 1]) / z;
-      dw = dw * fmin(z, dzt[gq - 1]) / z;
+      const RcpD rz = rcp_prepare(z);  // four IEEE quotients by the same thickness: one reciprocal refinement (div_by)
+      dn = div_by(dn * fmin(z, dzt[gq + nxb]), rz);
+      ds = div_by(ds * fmin(z, dzt[gq - nxb]), rz);
+      de = div_by(de * fmin(z, dzt[gq + 1]), rz);
+      dw = div_by(dw * fmin(z, dzt[gq - 1]), rz);
     } else {
       dn = ds = de = dw = 0.0;
     }
@@ -263,6 +264,8 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
     double ute = 0.0, utw = 0.0, vtn = 0.0, vts = 0.0, wtkb = 0.0;
     const bool pbc = (g.DZT != nullptr);
     const double dzt_c = pbc ? g.DZT[(size_t)k * n2 + q] : 0.0;  // thickness of this cell
+    const RcpD rzt = pbc ? rcp_prepare(dzt_c) : RcpD{1.0, 1.0};
+    const double h_dzt = pbc ? div_by(0.5, rzt) : 0.0;  // 0.5 / DZT
     if (DO_ADV) {
 #define UD(di, dj) (s_u[TIX(tx + (di), ty + (dj))] * s_dyu[TIX(tx + (di), ty + (dj))])
 #define VD(di, dj) (s_v[TIX(tx + (di), ty + (dj))] * s_dxu[TIX(tx + (di), ty + (dj))])
@@ -318,15 +321,15 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
               ((vtn - vts + ute - utw) * T + vtn * tc[TIX(tx, ty + 1)] - vts * tc[TIX(tx, ty - 1)] +
                ute * tc[TIX(tx + 1, ty)] - utw * tc[TIX(tx - 1, ty)]) *
               tarea_r;
-          if (pbc) L = L / dzt_c;  // :2223-2238
+          if (pbc) L = div_by(L, rzt);  // :2223-2238
           if (k == 1) {
             if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
           } else {
-            if (pbc) L = L + 0.5 / dzt_c * wtk * (tc_m[m] + T);  // :2278-2280
+            if (pbc) L = L + h_dzt * wtk * (tc_m[m] + T);  // :2278-2280
             else L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
           }
           if (k < km) {
-            if (pbc) L = L - 0.5 / dzt_c * wtkb * (T + Tp);
+            if (pbc) L = L - h_dzt * wtkb * (T + Tp);
             else L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
           }
         } else if (UPW) {  // upwind3: advection.F90:2387-2476 + hupw3 :2543-2672
@@ -418,7 +421,7 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
         if (pbc) {  // vertical_mix.F90:790-803
           const double dzt_p = g.DZT[(size_t)((k < km) ? k + 1 : km) * n2 + q];
           VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) / (0.5 * (dzt_c + dzt_p)) : 0.0;
-          vd = (k <= kmt) ? (vtf[m] - VTFB) / dzt_c : 0.0;
+          vd = (k <= kmt) ? div_by(vtf[m] - VTFB, rzt) : 0.0;
         } else {
           VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
           vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;

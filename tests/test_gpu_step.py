@@ -289,7 +289,8 @@ def test_pcsi_two_iterations_per_pass_is_bitwise_the_single_pass_solver(monkeypa
     assert relerr(res["blocked"][1], oracle_global(o, "PSURF", c.TIME_CUR)) <= 2.0e-12
 
 
-@pytest.mark.parametrize("ns,ny,depth", [(c.BNDY_TRIPOLE, 90, "12"), (c.BNDY_TRIPOLE, 87, "22"), (c.BNDY_CLOSED, 64, "12")])
+@pytest.mark.parametrize("ns,ny,depth", [(c.BNDY_TRIPOLE, 90, "12"), (c.BNDY_TRIPOLE, 87, "22"), (c.BNDY_CLOSED, 64, "12"),
+                                         (c.BNDY_TRIPOLE, 90, "8")])
 def test_pcsi_deep_strip_layout_is_bitwise_the_plain_solver(monkeypatch, ns, ny, depth):
     """The P-CSI passes of the multi-rank solver run on strips with a deep ghost zone (one strip exchange per `depth`
     iterations instead of one per pass; ghost cells with a source in the same strip -- east-west wrap, tripole fold --
