@@ -757,6 +757,7 @@ struct Pcsi2Args {
   // deep strips (see pcsi()): rows above jw_max are not written by the tile pass; with `deep` the ghost cells that have
   // a source cell in this strip (east-west wrap, tripole fold) are written together with their source
   int deep, jw_max;
+  int early_const;  // see the kernel head
   PopTmap tmX, tmC, tmB, tmQ, tmN, tmE, tmNE;  // 2-d tensor maps with the box of each staged tile
 };
 // cooperative asynchronous staging of a w x h window of a 2-d field (origin gi0,gj0; zero outside)
@@ -771,7 +772,12 @@ __device__ __forceinline__ void p2_stage(double* dst, const double* __restrict__
 template <bool SUM>
 __global__ void __launch_bounds__(P2_NT, P2_MINB)
 pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
-  pdl_wait();
+  // Programmatic dependent launch: the CTAs of this pass may start while the last wave of the previous pass drains.
+  // What that pass writes (X, Q) must not be touched before pdl_wait(); the five arrays that are constant during the
+  // solve (B and the operator weights) are requested before it (a.early_const: not for the first pass of a solve, whose
+  // predecessors are the kernels that set those arrays up).
+  const bool early = a.use_tma && a.early_const;
+  if (!early) pdl_wait();
   pdl_trigger();
   POP_DYN_SMEM(smem_raw);
   double* sX = (double*)smem_raw;  // X_m              rows j0-2 .. j0+TY+1
@@ -811,15 +817,17 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
     if (tid == 0) {
       constexpr uint32_t bytes = 8u * P2_XW * ((P2_TY + 4) + 4 * (P2_TY + 2) + 2 * (P2_TY + 3));
       mbar_expect_tx(s_bar, bytes);
-      tma_load_box2d(sX, &a.tmX, i0 - 2, j0 - 2, s_bar);
       tma_load_box2d(sC, &a.tmC, i0 - 2, j0 - 1, s_bar);
       tma_load_box2d(sB, &a.tmB, i0 - 2, j0 - 1, s_bar);
-      tma_load_box2d(sQ, &a.tmQ, i0 - 2, j0 - 1, s_bar);
       tma_load_box2d(sE, &a.tmE, i0 - 2, j0 - 1, s_bar);
       tma_load_box2d(sN, &a.tmN, i0 - 2, j0 - 2, s_bar);
       tma_load_box2d(sNE, &a.tmNE, i0 - 2, j0 - 2, s_bar);
+      if (early) pdl_wait();
+      tma_load_box2d(sX, &a.tmX, i0 - 2, j0 - 2, s_bar);
+      tma_load_box2d(sQ, &a.tmQ, i0 - 2, j0 - 1, s_bar);
     }
     mbar_wait(s_bar, 0u);
+    if (early) pdl_wait();  // every thread: the edge tiles read X, Q with plain loads as well, and all write X, Q
   } else {
     p2_stage(sX, a.X, P2_XW, P2_TY + 4, i0 - 2, j0 - 2, nxb, nyb, tid);
     p2_stage(sC, v.C, P2_XW, P2_TY + 2, i0 - 2, j0 - 1, nxb, nyb, tid);
@@ -1110,12 +1118,13 @@ static int pcsi(double* X, const double* B) {
   const bool blocking = !G.no_pcsi_blocking;
   // deep strips: see DeepBt.  Needs the peer-memory exchange, a closed or tripole north-south boundary and strips
   // at least gd rows high.
-  // Depth: at most deep_halo rows (even: a pass consumes two), and among the depths >= 6 the largest one whose pass
-  // still fits the fewest waves of CTAs -- a 3600 x 300 strip with 12 ghost rows is 1824 tiles on 592 resident CTAs
-  // (3.08 waves: a quarter of the pass is tail), with 6 rows it is 1767 (2.98).  POP_B200_DEEP_HALO_EXACT=1: no search.
+  // Depth: deep_halo rows (even: a pass consumes two).  Opt-in POP_B200_DEEP_HALO_WAVES=1: among the depths >= 6 the
+  // largest one whose pass fits the fewest waves of CTAs (a 3600 x 300 strip with 12 ghost rows is 1824 tiles on 592
+  // resident CTAs = 3.08 waves, with 6 rows 1767 = 2.98) -- measured slower: twice the exchanges cost more than the
+  // tail of the fourth wave (profiles/r2_ncu_summary.md section 6).
   int gd = (G.deep_halo / 2) * 2;
   if (gd < 4) gd = 0;
-  if (gd > 6 && !(getenv("POP_B200_DEEP_HALO_EXACT") && getenv("POP_B200_DEEP_HALO_EXACT")[0] == '1')) {
+  if (gd > 6 && getenv("POP_B200_DEEP_HALO_WAVES") && getenv("POP_B200_DEEP_HALO_WAVES")[0] == '1') {
     const long slots = (long)P2_MINB * G.sm_count, tx = (G.nxg + P2_TX - 1) / P2_TX;
     auto waves = [&](int d) { return ((long)((G.ny_local + 2 * d - 2 * POP_NGHOST + P2_TY - 1) / P2_TY) * tx + slots - 1) / slots; };
     int best = gd;
@@ -1163,9 +1172,11 @@ static int pcsi(double* X, const double* B) {
   const int do_ew = (G.cfg.ew_boundary_type == POP_BNDY_CYCLIC) ? 1 : 0;
   const int do_tp = (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) ? 1 : 0;
   // opt-in (POP_B200_OVERLAP_EXCHANGE=1): boundary tile rows first, strip exchange concurrent with the interior tiles
-  // deep strips: interior tile rows of the pass after an exchange run beside the exchange (POP_B200_NO_DEEP_OVERLAP=1: off)
+  // deep strips, opt-in POP_B200_DEEP_OVERLAP=1: interior tile rows of the pass after an exchange run beside the exchange
+  // (bitwise the same; measured no faster: with one exchange per six passes the two extra launches and events cost
+  // what the overlap hides)
   const bool deep_overlap = deep && (G.nranks > 1 || G.deep_force) && grid2.y >= 6 && G.stream_x != nullptr &&
-                            !(getenv("POP_B200_NO_DEEP_OVERLAP") && getenv("POP_B200_NO_DEEP_OVERLAP")[0] == '1');
+                            getenv("POP_B200_DEEP_OVERLAP") && getenv("POP_B200_DEEP_OVERLAP")[0] == '1';
   const bool xover = !deep && blocking && G.overlap_exchange && G.nranks > 1 && G.p2p_on && grid2.y >= 3 &&
                      G.cfg.ew_boundary_type == POP_BNDY_CYCLIC;
   // Convergence checks.  One rank: the host reads rr right away.  P > 1 ranks: a check costs an all-gather
@@ -1209,7 +1220,7 @@ static int pcsi(double* X, const double* B) {
   // verdict: the pair is simply retired from the rotation until then (`held`: at most one at a time besides the one
   // whose verdict is being awaited), so three pairs suffice and nothing is copied.
   int cur = 0, nxt = 1, held = -1;
-  int m = 1, npass = 0;
+  int m = 1, npass = 0, npass2 = 0;
   while (m <= maxIt) {
     const bool check = (m % freq == 0) && (m >= start);
     const bool next_is_check = ((m + 1) % freq == 0) && (m + 1 >= start);
@@ -1239,6 +1250,7 @@ static int pcsi(double* X, const double* B) {
       Pcsi2Args a;
       a.v = view;
       a.deep = self_ghost ? 1 : 0; a.jw_max = jw_max;
+      a.early_const = (npass2++ > 0 && !G.no_pdl) ? 1 : 0;
       a.X = Xb[cur]; a.Q = Qb[cur]; a.B = B; a.Xn = Xb[nxt]; a.Qn = Qb[nxt];
       csomga = 1.0 / (csy - csomga / (4.0 * csalpha * csalpha));  // om_{m+1}
       a.om1 = csomga; a.c11 = csy * csomga - 1.0;

@@ -301,6 +301,7 @@ def test_pcsi_deep_strip_layout_is_bitwise_the_plain_solver(monkeypatch, ns, ny,
                    given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0)
     res = {}
     monkeypatch.setenv("POP_B200_DEEP_HALO", depth)
+    monkeypatch.setenv("POP_B200_DEEP_OVERLAP", "1" if depth == "22" else "0")   # the opt-in split of the pass after an exchange
     for tag, env in (("plain", "0"), ("deep", "1"), ("lagged", "0")):
         monkeypatch.setenv("POP_B200_DEEP_HALO_FORCE", env)
         # the multi-rank solver also reads the verdict of a convergence check one check period late (X_m of the check
