@@ -63,8 +63,8 @@ struct Ctx {
   std::vector<double> dzbc_strip;  // pop_set_bottom_cells: thickness of the bottom cell, physical strip
   int *d_iglob = nullptr, *d_jglob = nullptr;  // device copies
   cudaStream_t stream = nullptr;
-  // side stream: the velocity finish (impvmixu + barotropic-mean removal) of step n runs here, concurrently
-  // with the barotropic solve on `stream` (the solve only needs ZX,ZY of the column kernel)
+  // side stream: with finish_mode 1 (opt-in) the velocity finish (impvmixu + barotropic-mean removal) of step n runs
+  // here, concurrently with the barotropic solve on `stream` (the solve only needs ZX,ZY of the column kernel)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chk[2] = {nullptr, nullptr};  // lagged P-CSI convergence checks

@@ -10,8 +10,12 @@
 //                   carried quantities in registers.  The same kernel, restricted to one level and
 //                   one term, implements the slab entry points pop_advt / pop_hdifft / pop_vdifft.
 //   impvmixt_dev  : implicit vertical mixing of tracers (vertical_mix.F90:1164-1382) and its
-//                   corrector (:1460-1672): one column per thread, Thomas coefficients E(k) resident
-//                   in registers, the solution streamed in place through the output array.
+//                   corrector (:1460-1672): one column per thread, Thomas coefficients E(k) of the CTA's 128
+//                   columns in shared memory (km x 128 doubles), operands prefetched through a register ring,
+//                   the solution streamed in place through the output array; an opt-in variant stages the
+//                   operands with TMA (POP_B200_THOMAS_TMA=1).
+//   lw_lim tracers: their advective tendency is computed by pop_lwlim.cu into the output array, where the
+//                   column kernels pick it up.
 //
 // Data movement: per level a CTA stages the (32+4) x (8+4) halo tile of each tracer (and the
 // U*DYU, V*DXU flux operands) in shared memory; the k-invariant masks/coefficients (KMT, DTN..DTW,
