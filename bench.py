@@ -330,9 +330,22 @@ def run_pop(args):
 
     # ---- warm-up: forward-Euler first step, then leapfrog
     W, K = (max(args.warmup, 1) if args.no_e2e else max(args.warmup, 3)), args.steps
+    dbg = os.environ.get("POP_BENCH_DEBUG") == "1"   # decomposition-independence hunt: fingerprints after every warm-up step
+    if dbg:
+        cs0 = state_checksum(p)
+        if rank == 0:
+            print("DEBUG eigs", [x.hex() for x in p.solvers_get_eigs()], "initial", cs0, file=sys.stderr, flush=True)
     p.step(c.TS_EULER)
+    if dbg:
+        cs1 = state_checksum(p)
+        if rank == 0:
+            print("DEBUG after euler", cs1, p.solvers_get_diagnostics(), file=sys.stderr, flush=True)
     for _ in range(W - 1):
         p.step(c.TS_LEAPFROG)
+        if dbg:
+            cs1 = state_checksum(p)
+            if rank == 0:
+                print("DEBUG after leapfrog", cs1, p.solvers_get_diagnostics(), file=sys.stderr, flush=True)
     iters_warm = p.solvers_get_diagnostics()[0]
     # ---- timed region 1: state resident in HBM
     sampler = ClockSampler(local)
@@ -362,12 +375,19 @@ def run_pop(args):
             print(json.dumps({"profile_run": True, "ms_per_step": ms / K, "launches": launches, "solver_iterations": iters,
                               "phases_ms_per_step": {n: tm[n][0] / K for n in tm}}))
         return
+    checksum_resident = state_checksum(p)   # after the last step of the device-resident timed region (collective)
     # ---- timed region 2: end to end through pop_step_coupled with pinned host buffers
     strip = p.ny_local * nx
     h_in = torch.zeros((nt + 4) * strip, dtype=torch.float64).pin_memory()
     h_out = torch.zeros(5 * strip, dtype=torch.float64).pin_memory()
     hin = h_in.numpy()
-    hin[:] = 1.0e-6 * np.sin(np.arange(hin.size, dtype=np.float64))
+    # forcing from GLOBAL cell indices (field, global row, column), so that every decomposition applies the same forcing and
+    # the state checksum after the end-to-end steps is comparable across N as well
+    j0 = p.rows().start
+    for f in range(nt + 4):
+        gidx = float(f) * nx * ny + (np.arange(j0, j0 + p.ny_local, dtype=np.float64)[:, None] * nx
+                                     + np.arange(nx, dtype=np.float64)[None, :])
+        hin[f * strip:(f + 1) * strip] = (1.0e-6 * np.sin(gidx)).ravel()
     STF, SMF = hin[: nt * strip], hin[nt * strip:(nt + 2) * strip]
     QSW, FW = hin[(nt + 2) * strip:(nt + 3) * strip], hin[(nt + 3) * strip:]
     FW[:] *= 1.0e-3
@@ -463,7 +483,10 @@ def run_pop(args):
                 "ms_per_step": ms_e2e / K, "api": "pop_step_coupled (host forcing in, host surface state out)"},
         "gpu_launches": launches, "clocks": sampler.summary(),
     }
-    out["state_checksum"] = checksum
+    # decomposition-independent fingerprints (equal hex strings at N = 1, 2, 4, 8 mean equal bits): after the last step of the
+    # device-resident timed region, and after the end-to-end steps that follow it
+    out["state_checksum"] = checksum_resident
+    out["state_checksum_after_e2e"] = checksum
     if world == 1 and not args.no_cpu_baseline:
         base, check = cpu_baseline(args, steps=2, check=not args.no_check)
         out["cpu_baseline"] = base
