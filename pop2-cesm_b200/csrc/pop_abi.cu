@@ -566,9 +566,17 @@ extern "C" int pop_step(int ts_type) {
 // corrector has; only U1/V1 (final after the barotropic mean is added back, at the very end) are copied after the
 // step. Averaging and Robert-filtered steps rewrite the output level at the end, so everything leaves after the step.
 int coupled_wait_forcing() {
-  if (!G.cio.forcing_pending) return POP_SUCCESS;
-  POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_cp_in, 0));
-  G.cio.forcing_pending = false;
+  if (G.cio.forcing_pending) {
+    POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_cp_in, 0));
+    G.cio.forcing_pending = false;
+  }
+  if (G.cio.fw_halo_pending) {
+    // the coupler hands over physical cells; the reference fills the ghost cells of the fluxes before they are used
+    // (update_ghost_cells_coupler_fluxes, forcing_coupled.F90).  On this path only FW is read off its own cell: DH = ... -
+    // FW_OLD is averaged to U points (tgrid_to_ugrid) -- without this the answer depends on where the strips are cut.
+    G.cio.fw_halo_pending = false;
+    POP_TRY(halo_update(fld("FW"), 1, POP_LOC_CENTER, POP_KIND_SCALAR, 0.0));
+  }
   return POP_SUCCESS;
 }
 int coupled_after_barotropic() {
@@ -616,6 +624,7 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
     POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_in, G.stream_cp));
     G.cio.forcing_pending = true;
   }
+  G.cio.fw_halo_pending = (FW != nullptr);
   G.cio.out = sfc_out;
   G.cio.early = sfc_out && !G.no_overlap && (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER);
   G.cio.psurf_sent = G.cio.ts_sent = false;

@@ -89,6 +89,7 @@ struct Ctx {
   cudaEvent_t ev_cp_in = nullptr, ev_cp_a = nullptr, ev_cp_b = nullptr;
   struct {
     bool forcing_pending = false;  // SMF/SHF_QSW/FW still in flight on stream_cp
+    bool fw_halo_pending = false;  // FW arrived as a physical strip: its ghost cells are filled before the first reader
     double* out = nullptr;         // host buffer of the surface state, or null
     bool early = false;            // outputs may leave as soon as they are final (not on averaging / filtered steps)
     bool psurf_sent = false, ts_sent = false;

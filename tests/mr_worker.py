@@ -15,12 +15,24 @@ from parity import *  # noqa: F401,F403,E402
 FIELDS_CMP = ("TRACER", "UVEL", "VVEL", "RHO", "PSURF", "UBTROP", "VBTROP", "GRADPX", "GRADPY")
 
 
-def run(cs, cfg, comm_id, steps):
+def run(cs, cfg, comm_id, steps, coupled=False):
     p = load_pop(cs, cfg, comm_id)
     try:
         its = []
+        rng = np.random.default_rng(17)
         for ts in steps:
-            p.step(ts)
+            if coupled:
+                # the coupler's entry point: every rank hands over the physical cells of its strip of the same global forcing
+                r = p.rows()
+                ocean, oceanu = (cs.kmt > 0), (cs.kmu > 0)
+                f = [np.ascontiguousarray((1.0e-4 * rng.standard_normal((cs.nt, cs.ny, cs.nx)) * ocean)[:, r, :]),
+                     np.ascontiguousarray((0.5 * rng.standard_normal((2, cs.ny, cs.nx)) * oceanu)[:, r, :]),
+                     np.ascontiguousarray((1.0e-3 * rng.standard_normal((cs.ny, cs.nx)) * ocean)[r, :]),
+                     np.ascontiguousarray((1.0e-6 * rng.standard_normal((cs.ny, cs.nx)) * ocean)[r, :])]
+                out = np.zeros((5, r.stop - r.start, cs.nx))
+                p.step_coupled(ts, f[0], f[1], f[2], f[3], out)
+            else:
+                p.step(ts)
             its.append(p.solvers_get_diagnostics()[0])
         out = {n: p.gather(n, c.TIME_CUR) for n in FIELDS_CMP}
         return its, out, p.rows()
@@ -37,6 +49,9 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "pcsi"
     # (8 strips: 16 rows each, so that the deep-strip layout of the P-CSI passes -- 12 ghost rows -- is in play there too)
     kw = dict(nx=96, ny=64 if world < 8 else 128, km=6, seed=81)
+    coupled = (which == "coupled")   # pop_step_coupled with host forcing strips (FW needs its ghost cells across the strip cut)
+    if coupled:
+        which = "pcsi"
     if which in ("pcsi22", "pcsi_plain"):
         # the P-CSI passes run on deep strips by default (12 ghost rows); also 22 rows deep, and the plain layout
         os.environ.update({"POP_B200_DEEP_HALO": "22"} if which == "pcsi22" else {"POP_B200_NO_DEEP_HALO": "1"})
@@ -76,12 +91,12 @@ def main():
             its.append(o.solver_diag()[0])
         ref = (its, {n: oracle_global(o, n, c.TIME_CUR) for n in FIELDS_CMP}, None)
     elif rank == 0:
-        ref = run(cs, c.copy_config(cs.cfg, rank=0, nranks=1, device=0), None, steps)
+        ref = run(cs, c.copy_config(cs.cfg, rank=0, nranks=1, device=0), None, steps, coupled)
     dist.barrier()
     obj = [P.api.Pop.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
     its, out, rows = run(cs, c.copy_config(cs.cfg, rank=rank, nranks=world, device=int(os.environ["LOCAL_RANK"])),
-                         obj[0], steps)
+                         obj[0], steps, coupled)
     parts = [None] * world if rank == 0 else None
     dist.gather_object((its, out, (rows.start, rows.stop)), parts, dst=0)
     ok = True

@@ -16,7 +16,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("which", ["pcsi", "pcsi22", "pcsi_plain", "chrongear", "cyclic_pcg", "gm", "pbc", "lwlim", "evp"])
+@pytest.mark.parametrize("which", ["pcsi", "pcsi22", "pcsi_plain", "chrongear", "cyclic_pcg", "gm", "pbc", "lwlim", "coupled", "evp"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_strips_are_bitwise_the_single_strip_run(which, world):
     if _ngpu() < world:

@@ -238,6 +238,9 @@ def test_step_coupled_host_buffers_match_resident_step():
         for ts, f in zip(steps, forcing):
             for name in ("STF", "SMF", "SHF_QSW", "FW"):
                 p.scatter(name, 0, f[name])
+            # the coupled entry point fills the ghost cells of FW (the one flux read off its own cell: DH - FW is averaged
+            # to U points), as update_ghost_cells_coupler_fluxes does in the reference
+            p.halo_field("FW", 0, c.LOC_CENTER, c.KIND_SCALAR)
             p.step(ts)
             ref.append({n: pop_global(p, n, c.TIME_CUR) for n in ("TRACER", "PSURF", "UVEL", "VVEL")})
     finally:
