@@ -367,6 +367,7 @@ extern "C" int pop_init(const pop_config* cfg) {
   G.no_tma = getenv("POP_B200_NO_TMA") != nullptr && getenv("POP_B200_NO_TMA")[0] == '1';
   G.thomas_tma = getenv("POP_B200_THOMAS_TMA") != nullptr && getenv("POP_B200_THOMAS_TMA")[0] == '1';
   G.no_fast_tracer = getenv("POP_B200_NO_FAST_TRACER") != nullptr && getenv("POP_B200_NO_FAST_TRACER")[0] == '1';
+  G.no_pbc_fast = getenv("POP_B200_NO_PBC_FAST") != nullptr && getenv("POP_B200_NO_PBC_FAST")[0] == '1';
   G.no_pcsi_blocking = getenv("POP_B200_NO_PCSI_BLOCKING") != nullptr && getenv("POP_B200_NO_PCSI_BLOCKING")[0] == '1';
   G.timers.clear();
   G.grid_set = false;

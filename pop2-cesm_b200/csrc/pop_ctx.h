@@ -156,6 +156,7 @@ struct Ctx {
   int timer_suppress = 0;  // >0 inside the solver iterations (no per-iteration events)
   std::map<std::string, Timer> timers;
   int sm_count = 148;
+  bool no_pbc_fast = false;       // POP_B200_NO_PBC_FAST=1: partial bottom cells on the general tracer column kernel
   bool no_pcsi_blocking = false;  // POP_B200_NO_PCSI_BLOCKING=1: one P-CSI iteration per pass (debugging aid)
   bool no_fast_tracer = false;  // POP_B200_NO_FAST_TRACER=1: always the general tracer column kernel
   bool no_tma = false;  // POP_B200_NO_TMA=1: force the plain-load column kernels (debugging aid)

@@ -518,7 +518,7 @@ struct TracerFastArgs {
 #define TF_NS 3
 #define TF_STAGE (6 * POP_TN + NTC * POP_NTHREADS)  // tc[2], tm[2], u, v halo tiles + vdc[2] column tiles
 #define TF_FIXED 11                                  // ring-1 tiles: dtn dts dte dtw ahf dyu dxu ute vtn d2[2]
-template <bool DEL4>
+template <bool DEL4, bool PBC>
 __global__ void __launch_bounds__(POP_NTHREADS, 2)
 tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   POP_DYN_SMEM(smem_raw);
@@ -598,9 +598,41 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   const double tarea_r = active ? g.TAREA_R[q] : 0.0;
   // per-level intermediates of level kk from its stage: UTE, VTN (advection.F90:2031-2060) and, for
   // del4, D2 = AHF*L(TMIX) (hmix_del4.F90:1025-1046) on the ring-1 tile
+  // partial bottom cells: thickness of the U cell (gi,gj) at level kk (0 outside the block), and the mixing
+  // coefficients of a T cell scaled by the face thicknesses (hmix_del2.F90:1034-1062, hmix_del4.F90:964-988)
+  auto zu_at = [&](int kk, int gi, int gj) {
+    return (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb) ? g.DZU[(size_t)kk * n2 + (size_t)gj * nxb + gi] : 0.0;
+  };
+  auto pbc_scale = [&](int kk, int gi, int gj, double& dn, double& ds, double& de, double& dw) {
+    if (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
+      const double* dzt = g.DZT + (size_t)kk * n2 + (size_t)gj * nxb + gi;
+      const double z = dzt[0];
+      const RcpD rz = rcp_prepare(z);
+      dn = div_by(dn * fmin(z, dzt[nxb]), rz);
+      ds = div_by(ds * fmin(z, dzt[-nxb]), rz);
+      de = div_by(de * fmin(z, dzt[1]), rz);
+      dw = div_by(dw * fmin(z, dzt[-1]), rz);
+    } else {
+      dn = ds = de = dw = 0.0;
+    }
+  };
+  double p_dn = o_dtn, p_ds = o_dts, p_de = o_dte, p_dw = o_dtw;  // PBC: own-point coefficients of the level pre() saw last
   auto pre = [&](int kk, const double* st) {
     const double* su = st + 4 * POP_TN;
     const double* sv = st + 5 * POP_TN;
+    if (PBC) {  // advection.F90:2040-2066: (U*DYU)*DZU
+      s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] * zu_at(kk, i, j) + su[oT - POP_TW] * s_dyu[o1 - POP_T1W] * zu_at(kk, i, j - 1));
+      s_vtn[o1] = 0.5 * (sv[oT] * s_dxu[o1] * zu_at(kk, i, j) + sv[oT - 1] * s_dxu[o1 - 1] * zu_at(kk, i - 1, j));
+      if (tid < POP_BY) {
+        const int t1 = TIX1(-1, tid), tt = TIX(-1, tid), gi = i0 - 1, gj = j0 + tid;
+        s_ute[t1] = 0.5 * (su[tt] * s_dyu[t1] * zu_at(kk, gi, gj) + su[tt - POP_TW] * s_dyu[t1 - POP_T1W] * zu_at(kk, gi, gj - 1));
+      } else if (tid >= 32 && tid < 32 + POP_BX) {
+        const int t1 = TIX1(tid - 32, -1), tt = TIX(tid - 32, -1), gi = i0 + tid - 32, gj = j0 - 1;
+        s_vtn[t1] = 0.5 * (sv[tt] * s_dxu[t1] * zu_at(kk, gi, gj) + sv[tt - 1] * s_dxu[t1 - 1] * zu_at(kk, gi - 1, gj));
+      }
+      p_dn = o_dtn; p_ds = o_dts; p_de = o_dte; p_dw = o_dtw;
+      pbc_scale(kk, i, j, p_dn, p_ds, p_de, p_dw);
+    } else {
     // own point
     s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] + su[oT - POP_TW] * s_dyu[o1 - POP_T1W]);
     s_vtn[o1] = 0.5 * (sv[oT] * s_dxu[o1] + sv[oT - 1] * s_dxu[o1 - 1]);
@@ -612,10 +644,11 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
       const int t1 = TIX1(tid - 32, -1), tt = TIX(tid - 32, -1);
       s_vtn[t1] = 0.5 * (sv[tt] * s_dxu[t1] + sv[tt - 1] * s_dxu[t1 - 1]);
     }
+    }
     if (DEL4) {
       {  // own point: coefficients from registers
-        const double cn = (kk <= kmn) ? o_dtn : 0.0, cs = (kk <= kms) ? o_dts : 0.0;
-        const double ce = (kk <= kme) ? o_dte : 0.0, cw = (kk <= kmw) ? o_dtw : 0.0;
+        const double cn = (kk <= kmn) ? (PBC ? p_dn : o_dtn) : 0.0, cs = (kk <= kms) ? (PBC ? p_ds : o_dts) : 0.0;
+        const double ce = (kk <= kme) ? (PBC ? p_de : o_dte) : 0.0, cw = (kk <= kmw) ? (PBC ? p_dw : o_dtw) : 0.0;
         const double cc = -(cn + cs + ce + cw);
 #pragma unroll
         for (int m = 0; m < NTC; m++) {
@@ -631,10 +664,12 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         else { const int t = tid - 2 * POP_T1W; ii = (t < POP_BY) ? -1 : POP_BX; jj = t % POP_BY; }
         const int t1 = TIX1(ii, jj), tt = TIX(ii, jj);
         const int kc = s_kmt[tt];
-        const double cn = (kk <= s_kmt[tt + POP_TW] && kk <= kc) ? s_dtn[t1] : 0.0;
-        const double cs = (kk <= s_kmt[tt - POP_TW] && kk <= kc) ? s_dts[t1] : 0.0;
-        const double ce = (kk <= s_kmt[tt + 1] && kk <= kc) ? s_dte[t1] : 0.0;
-        const double cw = (kk <= s_kmt[tt - 1] && kk <= kc) ? s_dtw[t1] : 0.0;
+        double rn = s_dtn[t1], rs = s_dts[t1], re = s_dte[t1], rw = s_dtw[t1];
+        if (PBC) pbc_scale(kk, i0 + ii, j0 + jj, rn, rs, re, rw);
+        const double cn = (kk <= s_kmt[tt + POP_TW] && kk <= kc) ? rn : 0.0;
+        const double cs = (kk <= s_kmt[tt - POP_TW] && kk <= kc) ? rs : 0.0;
+        const double ce = (kk <= s_kmt[tt + 1] && kk <= kc) ? re : 0.0;
+        const double cw = (kk <= s_kmt[tt - 1] && kk <= kc) ? rw : 0.0;
         const double cc = -(cn + cs + ce + cw);
 #pragma unroll
         for (int m = 0; m < NTC; m++) {
@@ -674,11 +709,16 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
       double wtkb = 0.0;
       if (k < km) {
         const double FC = (vtn - vts + ute - utw) * tarea_r;
-        wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
+        if (PBC) wtkb = (k < kmt) ? wtk + FC : 0.0;  // advection.F90:2110-2111
+        else wtkb = (k < kmt) ? wtk + c_vc.dz[k] * FC : 0.0;
       }
-      const double cn = (k <= kmn) ? o_dtn : 0.0, cs = (k <= kms) ? o_dts : 0.0;
-      const double ce = (k <= kme) ? o_dte : 0.0, cw = (k <= kmw) ? o_dtw : 0.0;
+      const double cn = (k <= kmn) ? (PBC ? p_dn : o_dtn) : 0.0, cs = (k <= kms) ? (PBC ? p_ds : o_dts) : 0.0;
+      const double ce = (k <= kme) ? (PBC ? p_de : o_dte) : 0.0, cw = (k <= kmw) ? (PBC ? p_dw : o_dtw) : 0.0;
       const double cc = -(cn + cs + ce + cw);
+      const double dzt_c = PBC ? g.DZT[(size_t)k * n2 + q] : 0.0;
+      const RcpD rzt = PBC ? rcp_prepare(dzt_c) : RcpD{1.0, 1.0};
+      const double h_dzt = PBC ? div_by(0.5, rzt) : 0.0;
+      const double dzt_p = PBC ? g.DZT[(size_t)((k < km) ? k + 1 : km) * n2 + q] : 0.0;
 #pragma unroll
       for (int m = 0; m < NTC; m++) {
         const int n = a.n0 + m;
@@ -704,20 +744,31 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
           L = 0.5 *
               ((vtn - vts + ute - utw) * T + vtn * tc[POP_TW] - vts * tc[-POP_TW] + ute * tc[1] - utw * tc[-1]) *
               tarea_r;
+          if (PBC) L = div_by(L, rzt);  // advection.F90:2223-2238
           if (k == 1) {
             if (!a.varthick) L = L + c_vc.dzr[k] * wtk * T;
           } else {
-            L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
+            if (PBC) L = L + h_dzt * wtk * (tc_m[m] + T);  // :2278-2280
+            else L = L + c_vc.dz2r[k] * wtk * (tc_m[m] + T);
           }
-          if (k < km) L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+          if (k < km) {
+            if (PBC) L = L - h_dzt * wtkb * (T + Tp);
+            else L = L - c_vc.dz2r[k] * wtkb * (T + Tp);
+          }
         }
         tc_m[m] = T;
         // ---- vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
         const double vdc = st[6 * POP_TN + m * POP_NTHREADS + tid];
         const double told_p = (k < km) ? nst[(NTC + m) * POP_TN + oT] : told_c[m];
         if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
-        const double VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
-        const double vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        double VTFB, vd;
+        if (PBC) {  // vertical_mix.F90:790-803
+          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) / (0.5 * (dzt_c + dzt_p)) : 0.0;
+          vd = (k <= kmt) ? div_by(vtf[m] - VTFB, rzt) : 0.0;
+        } else {
+          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
+          vd = (k <= kmt) ? (vtf[m] - VTFB) * c_vc.dzr[k] : 0.0;
+        }
         vtf[m] = VTFB;
         told_c[m] = told_p;
         // ---- tracer_update: baroclinic.F90:1993-2300 (implicit vertical mixing)
@@ -745,7 +796,9 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
 }
 
 static int launch_tracer_fast(const TracerFastArgs& a, bool del4) {
-  void (*kfn)(const TracerFastArgs) = del4 ? tracer_fast_kernel<true> : tracer_fast_kernel<false>;
+  void (*kfn)(const TracerFastArgs);
+  if (a.g.DZT) kfn = del4 ? tracer_fast_kernel<true, true> : tracer_fast_kernel<false, true>;
+  else kfn = del4 ? tracer_fast_kernel<true, false> : tracer_fast_kernel<false, false>;
   const size_t smem = sizeof(double) * ((size_t)TF_NS * TF_STAGE + (size_t)TF_FIXED * POP_T1N) + sizeof(int) * POP_TN +
                       8 * TF_NS;
 #ifndef POP_EMUL
@@ -835,7 +888,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
     switch (mode) {
       case TR_FULL: {
         // fast path: a full pair of centred tracers, implicit vertical mixing, leapfrog-type levels
-        const bool fast_ok = !gm && !G.cfg.partial_bottom_cells && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
+        const bool fast_ok = !gm && !(G.cfg.partial_bottom_cells && G.no_pbc_fast) && !G.no_tma && !G.no_fast_tracer && a.nn == NTC && !upw && a.implicit_vmix &&
                              a.TMIX == a.TOLD && a.TMIX != a.TCUR && (G.nxb % 2) == 0 && G.km >= TF_NS;
         if (fast_ok) {
           TracerFastArgs f;

@@ -352,6 +352,26 @@ def test_staging_and_overlap_variants_are_bitwise_identical(monkeypatch, flags):
         assert np.array_equal(res[0][n], res[1][n]), n
 
 
+def test_partial_bottom_cell_fast_tracer_kernel_is_bitwise_the_general_kernel(monkeypatch):
+    """Partial bottom cells: the leapfrog-specialised tracer kernel (PBC template branch) against the general column
+    kernel (POP_B200_NO_PBC_FAST=1), tripole, variable del4, partial edge tiles."""
+    cs = make_case(104, 52, 6, seed=74, ns=c.BNDY_TRIPOLE, hmix_tracer_itype=c.HMIX_DEL4,
+                   hmix_momentum_itype=c.HMIX_DEL4, lvariable_hmixt=1, lvariable_hmixu=1, ah=-3.0e21, am=-27.0e21,
+                   given_vmix=True, solver_choice=c.SOLVER_PCSI, dtt=600.0, partial_bottom_cells=1)
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("POP_B200_NO_PBC_FAST", flag)
+        p = load_pop(cs)
+        try:
+            for ts in (c.TS_EULER, c.TS_LEAPFROG, c.TS_LEAPFROG):
+                p.step(ts)
+            res.append({n: pop_global(p, n, c.TIME_CUR) for n in PROG})
+        finally:
+            p.finalize()
+    for n in PROG:
+        assert np.array_equal(res[0][n], res[1][n]), n
+
+
 @pytest.mark.parametrize("kw", [
     dict(nx=45, ny=33, km=5, seed=73, convergence_criterion=1e-12),                      # odd nx: no TMA descriptors
     dict(nx=37, ny=29, km=3, seed=74, ns=c.BNDY_CYCLIC, hmix_tracer_itype=c.HMIX_DEL4, hmix_momentum_itype=c.HMIX_DEL4,
