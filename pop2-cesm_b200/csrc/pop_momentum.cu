@@ -25,6 +25,7 @@ struct MomentumArgs {
   int lvariable_hmixu, impcor, leapfrog, pavg;
   double am, c2dtu, beta, gamma, bottom_drag;
   PopTmap tm_uc, tm_vc, tm_um, tm_vm, tm_ro, tm_rc, tm_rn;  // TMA descriptors (FULL mode)
+  PopTmap tm_dz;                                             // DZU (partial bottom cells), levels 0..km+1
 };
 #define MO_NS 3  // TMA pipeline depth (levels in flight per CTA)
 
@@ -33,24 +34,24 @@ struct MomCoefTiles {  // ring-1 tiles; DMS = -DMN and DMW = -DME exactly (hmix_
 };
 // 5+5-point momentum stencil (hmix_del2.F90:892-921): s1 on A with the DU* set, s2 on B with DM*.
 // R1 = true: A and B are ring-1 tiles (TIX1); false: halo tiles of a pipeline stage (TIX).
-// dzu (partial bottom cells, hmix_del2.F90:852-863 / hmix_del4.F90:683-694): level k of DZU at the stencil centre
-// (array index gq, row pitch nxb), or null; inb: the centre and its four neighbours lie inside the padded block
+// dzu (partial bottom cells, hmix_del2.F90:852-863 / hmix_del4.F90:683-694): the staged halo tile (TIX) of level k of
+// DZU, or null; inb: the centre and its four neighbours lie inside the padded block
 template <bool R1>
 __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const double* A, const double* B,
-                                              int ii, int jj, bool plus, const double* dzu = nullptr, size_t gq = 0,
-                                              int nxb = 0, bool inb = false) {
+                                              int ii, int jj, bool plus, const double* dzu = nullptr, bool inb = false) {
   const int q = TIX1(ii, jj);
   const int o = R1 ? q : TIX(ii, jj);
   constexpr int W = R1 ? POP_T1W : POP_TW;
   double dn = c.dun[q], ds = c.dus[q], de = c.due[q], dw = c.duw[q];
   if (dzu) {
     if (inb) {
-      const double z = dzu[gq];
+      const double* zc = dzu + TIX(ii, jj);
+      const double z = zc[0];
       const RcpD rz = rcp_prepare(z);  // four IEEE quotients by the same thickness: one reciprocal refinement (div_by)
-      dn = div_by(dn * fmin(dzu[gq + nxb], z), rz);
-      ds = div_by(ds * fmin(dzu[gq - nxb], z), rz);
-      de = div_by(de * fmin(dzu[gq + 1], z), rz);
-      dw = div_by(dw * fmin(dzu[gq - 1], z), rz);
+      dn = div_by(dn * fmin(zc[POP_TW], z), rz);
+      ds = div_by(ds * fmin(zc[-POP_TW], z), rz);
+      de = div_by(de * fmin(zc[1], z), rz);
+      dw = div_by(dw * fmin(zc[-1], z), rz);
     } else {
       dn = ds = de = dw = 0.0;
     }
@@ -61,7 +62,8 @@ __device__ __forceinline__ double mom_stencil(const MomCoefTiles& c, const doubl
   return plus ? (s1 + s2) : (s1 - s2);
 }
 
-#define MOM_STAGE_TILES 7   // uc, vc, um, vm, rho old/cur/new (halo tiles, TMA boxes)
+#define MOM_STAGE_TILES 7   // uc, vc, um, vm, rho old/cur/new (halo tiles, TMA boxes); partial bottom cells: + DZU
+#define MO_NS_PBC 2         // pipeline depth with the eighth tile (two CTAs per SM must still fit)
 #define MOM_FIXED_TILES 13  // ring-1: cc, dun, dus, due, duw, dmc, dmn, dme, amf, ud, vd, d2u, d2v
 // Per level: every thread first finishes the "main" pass of level k (which reads the per-level
 // intermediates UD = U*DYU, VD = V*DXU and, for del4, D2U/D2V = AMF*L(U,V) of level k), then the CTA
@@ -71,10 +73,11 @@ template <int MODE, bool DEL4, bool TMA, bool PBC>
 __global__ void __launch_bounds__(POP_NTHREADS, 2)
 momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   POP_DYN_SMEM(smem_raw);
-  constexpr int NS = TMA ? MO_NS : 1;
+  constexpr int NS = TMA ? (PBC ? MO_NS_PBC : MO_NS) : 1;
+  constexpr int NTL = PBC ? MOM_STAGE_TILES + 1 : MOM_STAGE_TILES;  // tiles per stage
   double* sm = (double*)smem_raw;
-  double* s_stage = sm;  // [NS][MOM_STAGE_TILES][TN]
-  double* s_cc = s_stage + NS * MOM_STAGE_TILES * POP_TN;
+  double* s_stage = sm;  // [NS][NTL][TN]
+  double* s_cc = s_stage + NS * NTL * POP_TN;
   double* s_dun = s_cc + POP_T1N;
   double* s_dus = s_dun + POP_T1N;
   double* s_due = s_dus + POP_T1N;
@@ -107,12 +110,13 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   const bool same_mix = (a.UMIX == a.UCUR) && DO_ADV && (TMA || !DEL4);
 
   // ---- pipeline start (one thread): the first NS levels are in flight while the k-invariants load
-  const uint32_t stage_bytes = (uint32_t)((2 + (same_mix ? 0 : 2) + (a.pavg ? 3 : 1)) * POP_TILE_BYTES);
+  const uint32_t stage_bytes = (uint32_t)((2 + (same_mix ? 0 : 2) + (a.pavg ? 3 : 1) + (PBC ? 1 : 0)) * POP_TILE_BYTES);
   auto issue = [&](int kk) {
     const int sl = (kk - a.k0) % NS;
-    double* st = s_stage + (size_t)sl * MOM_STAGE_TILES * POP_TN;
+    double* st = s_stage + (size_t)sl * NTL * POP_TN;
     const int x = i0 - POP_H, y = j0 - POP_H, z = kk - 1;
     mbar_expect_tx(&s_bar[sl], stage_bytes);
+    if (PBC) tma_load_tile(st + 7 * POP_TN, &a.tm_dz, x, y, kk, &s_bar[sl]);  // DZU has levels 0..km+1
     tma_load_tile(st, &a.tm_uc, x, y, z, &s_bar[sl]);
     tma_load_tile(st + POP_TN, &a.tm_vc, x, y, z, &s_bar[sl]);
     if (!same_mix) {
@@ -208,7 +212,7 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
 
   // per-level intermediates on the ring-1 tile: flux operands (advection.F90:1307-1340) and the first
   // application of the del4 operator (hmix_del4.F90:730-790)
-  auto pre = [&](int kk, const double* uc, const double* vc, const double* um, const double* vm) {
+  auto pre = [&](int kk, const double* uc, const double* vc, const double* um, const double* vm, const double* dzu) {
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const int p = tid + s * POP_NTHREADS;
@@ -216,20 +220,18 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
         const int jj = p / POP_T1W - 1, ii = p % POP_T1W - 1;
         const int gi = i0 + ii, gj = j0 + jj;
         const bool inb = (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2);
-        const size_t gq = (size_t)gj * nxb + gi;
-        const double* dzu = PBC ? g.DZU + (size_t)kk * n2 : nullptr;
         if (DO_ADV) {
           s_ud[p] = uc[TIX(ii, jj)] * r_dyu[s];
           s_vd[p] = vc[TIX(ii, jj)] * r_dxu[s];
           if (PBC) {  // advection.F90:1245-1303: (U*DYU)*DZU
-            const double z = (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb) ? dzu[gq] : 0.0;
+            const double z = dzu[TIX(ii, jj)];  // zero outside the block, like the velocity tiles
             s_ud[p] = s_ud[p] * z;
             s_vd[p] = s_vd[p] * z;
           }
         }
         if (DO_HMIX && DEL4) {
-          double d2u = mom_stencil<false>(ct, um, vm, ii, jj, true, dzu, gq, nxb, inb);
-          double d2v = mom_stencil<false>(ct, vm, um, ii, jj, false, dzu, gq, nxb, inb);
+          double d2u = mom_stencil<false>(ct, um, vm, ii, jj, true, dzu, inb);
+          double d2v = mom_stencil<false>(ct, vm, um, ii, jj, false, dzu, inb);
           if (a.lvariable_hmixu) {
             if (kk <= s_kmu[p]) { d2u = s_amf[p] * d2u; d2v = s_amf[p] * d2v; }
             else { d2u = 0.0; d2v = 0.0; }
@@ -244,7 +246,7 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     mbar_wait(&s_bar[0], 0u);
     __syncthreads();  // coefficient tiles are staged
     pre(a.k0, s_stage, s_stage + POP_TN, same_mix ? s_stage : s_stage + 2 * POP_TN,
-        same_mix ? s_stage + POP_TN : s_stage + 3 * POP_TN);
+        same_mix ? s_stage + POP_TN : s_stage + 3 * POP_TN, PBC ? s_stage + 7 * POP_TN : nullptr);
     __syncthreads();
   }
   const bool uold_is_mix = (a.UOLD == a.UMIX) && !same_mix;
@@ -255,13 +257,14 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
   for (int k = a.k0; k <= a.k1; k++) {
     const size_t lev = (size_t)(k - 1) * n2;
     const int slot = (k - a.k0) % NS;
-    double* s_uc = s_stage + (size_t)slot * MOM_STAGE_TILES * POP_TN;
+    double* s_uc = s_stage + (size_t)slot * NTL * POP_TN;
     double* s_vc = s_uc + POP_TN;
     double* s_um = s_uc + 2 * POP_TN;
     double* s_vm = s_uc + 3 * POP_TN;
     double* s_ro = s_uc + 4 * POP_TN;
     double* s_rc = s_uc + 5 * POP_TN;
     double* s_rn = s_uc + 6 * POP_TN;
+    double* s_dz = PBC ? s_uc + 7 * POP_TN : nullptr;  // DZU of level k (halo tile)
     const double* um = same_mix ? s_uc : s_um;
     const double* vm = same_mix ? s_vc : s_vm;
     if (TMA) {
@@ -283,15 +286,16 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
           tile_load(s_rn, a.RHONEW + lev, i0, j0, nxb, nyb, 0, POP_BX, 0, POP_BY, tid);
         }
       }
+      if (PBC) tile_load(s_dz, g.DZU + (size_t)k * n2, i0, j0, nxb, nyb, -POP_H, POP_BX - 1 + POP_H, -POP_H, POP_BY - 1 + POP_H, tid);
       __syncthreads();
       if (DO_ADV || (DO_HMIX && DEL4)) {
-        pre(k, s_uc, s_vc, um, vm);
+        pre(k, s_uc, s_vc, um, vm, s_dz);
         __syncthreads();
       }
     }
     const bool have_next = TMA && (k < a.k1);
     const int nslot = (k + 1 - a.k0) % NS;
-    const double* n_uc = s_stage + (size_t)nslot * MOM_STAGE_TILES * POP_TN;
+    const double* n_uc = s_stage + (size_t)nslot * NTL * POP_TN;
     const double* n_vc = n_uc + POP_TN;
     const double* n_um = same_mix ? n_uc : n_uc + 2 * POP_TN;
     const double* n_vm = same_mix ? n_vc : n_uc + 3 * POP_TN;
@@ -299,8 +303,8 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     if (active) {
     double fx = 0.0, fy = 0.0;
     constexpr bool pbc = PBC;  // partial bottom cells: g.DZU is set
-    const double* dzu_k = pbc ? g.DZU + (size_t)k * n2 : nullptr;
-    const double dzu_c = pbc ? dzu_k[q] : 0.0;  // thickness of this U cell
+    const double* dzu_k = pbc ? s_dz : nullptr;
+    const double dzu_c = pbc ? s_dz[TIX(tx, ty)] : 0.0;  // thickness of this U cell
     const RcpD rzu = pbc ? rcp_prepare(dzu_c) : RcpD{1.0, 1.0};
     const double h_dzu = pbc ? div_by(0.5, rzu) : 0.0;  // 0.5 / DZU
     const double U = DO_ADV ? s_uc[TIX(tx, ty)] : 0.0, V = DO_ADV ? s_vc[TIX(tx, ty)] : 0.0;
@@ -392,11 +396,11 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
     double hdu = 0.0, hdv = 0.0;
     if (DO_HMIX) {
       if (DEL4) {
-        hdu = a.am * mom_stencil<true>(ct, s_d2u, s_d2v, tx, ty, true, dzu_k, q, nxb, true);
-        hdv = a.am * mom_stencil<true>(ct, s_d2v, s_d2u, tx, ty, false, dzu_k, q, nxb, true);
+        hdu = a.am * mom_stencil<true>(ct, s_d2u, s_d2v, tx, ty, true, dzu_k, true);
+        hdv = a.am * mom_stencil<true>(ct, s_d2v, s_d2u, tx, ty, false, dzu_k, true);
       } else {
-        hdu = a.am * mom_stencil<false>(ct, um, vm, tx, ty, true, dzu_k, q, nxb, true);
-        hdv = a.am * mom_stencil<false>(ct, vm, um, tx, ty, false, dzu_k, q, nxb, true);
+        hdu = a.am * mom_stencil<false>(ct, um, vm, tx, ty, true, dzu_k, true);
+        hdv = a.am * mom_stencil<false>(ct, vm, um, tx, ty, false, dzu_k, true);
       }
       if (k > kmu) { hdu = 0.0; hdv = 0.0; }
     }
@@ -487,7 +491,7 @@ momentum_column_kernel(const POP_GRID_CONSTANT MomentumArgs a) {
       __syncthreads();  // every thread is done with ring slot k and with the intermediates of level k
       if (tid == 0 && k + NS <= a.k1) issue(k + NS);
       if (have_next) {
-        pre(k + 1, n_uc, n_vc, n_um, n_vm);
+        pre(k + 1, n_uc, n_vc, n_um, n_vm, PBC ? n_uc + 7 * POP_TN : nullptr);
         __syncthreads();
       }
     }
@@ -517,8 +521,8 @@ static int launch_momentum(const MomentumArgs& a, bool del4, bool tma) {
     if (tma) kfn = del4 ? momentum_column_kernel<MODE, true, true, false> : momentum_column_kernel<MODE, false, true, false>;
     else kfn = del4 ? momentum_column_kernel<MODE, true, false, false> : momentum_column_kernel<MODE, false, false, false>;
   }
-  const int ns = tma ? MO_NS : 1;
-  const size_t smem = sizeof(double) * ((size_t)POP_TN * ns * MOM_STAGE_TILES + (size_t)POP_T1N * MOM_FIXED_TILES) +
+  const int ns = tma ? (pbc ? MO_NS_PBC : MO_NS) : 1;
+  const size_t smem = sizeof(double) * ((size_t)POP_TN * ns * (MOM_STAGE_TILES + (pbc ? 1 : 0)) + (size_t)POP_T1N * MOM_FIXED_TILES) +
                       sizeof(int) * POP_T1N + 8 * MO_NS;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -564,7 +568,8 @@ int momentum_column(int mode, int k, const MomentumIO& io) {
       const bool tma = !G.no_tma && make_tmap(&a.tm_uc, a.UCUR, G.km) && make_tmap(&a.tm_vc, a.VCUR, G.km) &&
                        make_tmap(&a.tm_um, a.UMIX, G.km) && make_tmap(&a.tm_vm, a.VMIX, G.km) &&
                        make_tmap(&a.tm_rc, a.RHOCUR, G.km) &&
-                       (!a.pavg || (make_tmap(&a.tm_ro, a.RHOOLD, G.km) && make_tmap(&a.tm_rn, a.RHONEW, G.km)));
+                       (!a.pavg || (make_tmap(&a.tm_ro, a.RHOOLD, G.km) && make_tmap(&a.tm_rn, a.RHONEW, G.km))) &&
+                       (!a.g.DZU || make_tmap(&a.tm_dz, a.g.DZU, G.km + 2));
       POP_TRY(launch_momentum<MO_FULL>(a, del4, tma));
       break;
     }
