@@ -680,14 +680,28 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
         nld--;
       }
     };
-    const double* DZUq = PBC ? g.DZU + q : nullptr;  // partial bottom cells: vertical_mix.F90:1777-1784
+    // partial bottom cells (vertical_mix.F90:1777-1784): zc = DZU(k), zn = DZU(k+1), zf = DZU(k+2) ride ahead in registers
+    const double* pz = PBC ? g.DZU + q + (size_t)5 * n2 : nullptr;
+    double zc = 0.0, zn = 0.0, zf = 0.0;
+    if (PBC) {
+      const double* z2 = g.DZU + q + (size_t)2 * n2;
+      zc = z2[0];
+      zn = (3 <= km + 1) ? z2[n2] : 0.0;
+      zf = (4 <= km + 1) ? z2[2 * n2] : 0.0;
+    }
     auto fwd_level = [&](int k, double vvc, double ru, double rw) {
       double hfac;
       C = A;
       if (PBC) {
-        const double zk = DZUq[(size_t)k * n2];
+        const double zk = zc;
         hfac = zk / c2dtu;
-        A = g.aidif * vvc / (0.5 * (zk + DZUq[(size_t)(k + 1) * n2]));
+        A = g.aidif * vvc / (0.5 * (zk + zn));
+        zc = zn; zn = zf;
+        if (k + 3 <= km + 1) {
+          zf = *pz;
+          if (MF_PD && k + 3 + MF_PD <= km + 1) prefetch_l2(pz + (ptrdiff_t)MF_PD * n2i);
+        }
+        pz += n2i;
       } else {
         hfac = c_vc.hfac_u[k];
         A = c_vc.afac_u[k] * vvc;

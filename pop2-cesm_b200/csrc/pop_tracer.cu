@@ -1026,14 +1026,29 @@ impvmixt_kernel(GridView g, double* __restrict__ TNEW, const double* __restrict_
         nld--;
       }
     };
-    const double* DZTq = PBC ? g.DZT + q : nullptr;  // partial bottom cells: vertical_mix.F90:1279-1286, :1577-1582
+    // partial bottom cells (vertical_mix.F90:1279-1286, :1577-1582): the thicknesses ride two levels ahead of the
+    // recurrence in registers (zc = DZT(k), zn = DZT(k+1), zf = DZT(k+2)) behind an L2 prefetch
+    const double* pz = PBC ? g.DZT + q + (size_t)5 * n2 : nullptr;  // next level to load (level 5)
+    double zc = 0.0, zn = 0.0, zf = 0.0;
+    if (PBC) {
+      const double* z2 = g.DZT + q + (size_t)2 * n2;
+      zc = z2[0];
+      zn = (3 <= km + 1) ? z2[n2] : 0.0;
+      zf = (4 <= km + 1) ? z2[2 * n2] : 0.0;
+    }
     auto fwd_level = [&](int k, double vdc, double rhs) {
       C = A;
       double hfac;
       if (PBC) {  // level 1 keeps the full-cell A and hfac (:1263-1269); DZT(k+1) is read at k = km too
-        const double zk = DZTq[(size_t)k * n2];
-        A = g.aidif * vdc / (0.5 * (zk + DZTq[(size_t)(k + 1) * n2]));
+        const double zk = zc;
+        A = g.aidif * vdc / (0.5 * (zk + zn));
         hfac = zk / c_vc.c2dtt[k];
+        zc = zn; zn = zf;
+        if (k + 3 <= km + 1) {
+          zf = *pz;
+          if (IV_PD && k + 3 + IV_PD <= km + 1) prefetch_l2(pz + (ptrdiff_t)IV_PD * n2i);
+        }
+        pz += n2i;
       } else {
         A = c_vc.afac_t[k] * vdc;
         hfac = c_vc.hfac_t[k];
