@@ -514,16 +514,21 @@ struct TracerFastArgs {
   int lvariable_hmixt, varthick, predictor;
   double ah;
   PopTmap tm_tcur, tm_tmix, tm_u, tm_v, tm_vdc;
+  PopTmap tm_dzt, tm_dzu;  // partial bottom cells: DZT, DZU (levels 0..km+1) as two more halo tiles of a stage
 };
 #define TF_NS 3
+#define TF_NS_PBC 2  // pipeline depth with the two extra tiles (two CTAs per SM must still fit)
 #define TF_STAGE (6 * POP_TN + NTC * POP_NTHREADS)  // tc[2], tm[2], u, v halo tiles + vdc[2] column tiles
 #define TF_FIXED 11                                  // ring-1 tiles: dtn dts dte dtw ahf dyu dxu ute vtn d2[2]
 template <bool DEL4, bool PBC>
 __global__ void __launch_bounds__(POP_NTHREADS, 2)
 tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   POP_DYN_SMEM(smem_raw);
-  double* s_stage = (double*)smem_raw;  // [TF_NS][TF_STAGE]
-  double* s_dtn = s_stage + TF_NS * TF_STAGE;
+  constexpr int NS = PBC ? TF_NS_PBC : TF_NS;
+  constexpr int NTL = PBC ? 8 : 6;                               // halo tiles per stage (PBC: + DZT, DZU)
+  constexpr int STAGE = NTL * POP_TN + NTC * POP_NTHREADS;      // + the vdc column tiles
+  double* s_stage = (double*)smem_raw;  // [NS][STAGE]
+  double* s_dtn = s_stage + NS * STAGE;
   double* s_dts = s_dtn + POP_T1N;
   double* s_dte = s_dts + POP_T1N;
   double* s_dtw = s_dte + POP_T1N;
@@ -545,27 +550,31 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   const int km = g.km, nxb = g.nxb, nyb = g.nyb;
 
   auto issue = [&](int kk) {
-    const int sl = (kk - 1) % TF_NS;
-    double* st = s_stage + (size_t)sl * TF_STAGE;
-    mbar_expect_tx(&s_bar[sl], (uint32_t)(6 * POP_TILE_BYTES + NTC * POP_NTHREADS * 8));
+    const int sl = (kk - 1) % NS;
+    double* st = s_stage + (size_t)sl * STAGE;
+    mbar_expect_tx(&s_bar[sl], (uint32_t)(NTL * POP_TILE_BYTES + NTC * POP_NTHREADS * 8));
+    if (PBC) {
+      tma_load_tile(st + 6 * POP_TN, &a.tm_dzt, i0 - POP_H, j0 - POP_H, kk, &s_bar[sl]);
+      tma_load_tile(st + 7 * POP_TN, &a.tm_dzu, i0 - POP_H, j0 - POP_H, kk, &s_bar[sl]);
+    }
 #pragma unroll
     for (int m = 0; m < NTC; m++) {
       const int z = (a.n0 + m) * km + (kk - 1);
       tma_load_tile(st + m * POP_TN, &a.tm_tcur, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
       tma_load_tile(st + (NTC + m) * POP_TN, &a.tm_tmix, i0 - POP_H, j0 - POP_H, z, &s_bar[sl]);
-      tma_load_tile(st + 6 * POP_TN + m * POP_NTHREADS, &a.tm_vdc, i0, j0, a.vdc_lev0[m] + kk * a.vdc_kstr,
+      tma_load_tile(st + NTL * POP_TN + m * POP_NTHREADS, &a.tm_vdc, i0, j0, a.vdc_lev0[m] + kk * a.vdc_kstr,
                     &s_bar[sl]);
     }
     tma_load_tile(st + 4 * POP_TN, &a.tm_u, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
     tma_load_tile(st + 5 * POP_TN, &a.tm_v, i0 - POP_H, j0 - POP_H, kk - 1, &s_bar[sl]);
   };
   if (tid == 0) {
-    for (int sl = 0; sl < TF_NS; sl++) mbar_init(&s_bar[sl], 1);
+    for (int sl = 0; sl < NS; sl++) mbar_init(&s_bar[sl], 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (tid == 0)
-    for (int kk = 1; kk <= km && kk <= TF_NS; kk++) issue(kk);
+    for (int kk = 1; kk <= km && kk <= NS; kk++) issue(kk);
 
   // ---- k-invariant staging (ring-1 coefficient tiles, KMT halo tile)
   tile_load_i(s_kmt, g.KMT, i0, j0, nxb, nyb, -2, POP_BX + 1, -2, POP_BY + 1, tid);
@@ -600,16 +609,16 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   // del4, D2 = AHF*L(TMIX) (hmix_del4.F90:1025-1046) on the ring-1 tile
   // partial bottom cells: thickness of the U cell (gi,gj) at level kk (0 outside the block), and the mixing
   // coefficients of a T cell scaled by the face thicknesses (hmix_del2.F90:1034-1062, hmix_del4.F90:964-988)
-  auto zu_at = [&](int kk, int gi, int gj) {
-    return (gi >= 0 && gi < nxb && gj >= 0 && gj < nyb) ? g.DZU[(size_t)kk * n2 + (size_t)gj * nxb + gi] : 0.0;
-  };
-  auto pbc_scale = [&](int kk, int gi, int gj, double& dn, double& ds, double& de, double& dw) {
+  // (st: the stage of that level; its DZT / DZU halo tiles are zero outside the block like every staged tile)
+  auto zu_at = [&](const double* st, int ii, int jj) { return st[7 * POP_TN + TIX(ii, jj)]; };
+  auto pbc_scale = [&](const double* st, int ii, int jj, double& dn, double& ds, double& de, double& dw) {
+    const int gi = i0 + ii, gj = j0 + jj;
     if (gi >= 1 && gi <= nxb - 2 && gj >= 1 && gj <= nyb - 2) {
-      const double* dzt = g.DZT + (size_t)kk * n2 + (size_t)gj * nxb + gi;
+      const double* dzt = st + 6 * POP_TN + TIX(ii, jj);
       const double z = dzt[0];
       const RcpD rz = rcp_prepare(z);
-      dn = div_by(dn * fmin(z, dzt[nxb]), rz);
-      ds = div_by(ds * fmin(z, dzt[-nxb]), rz);
+      dn = div_by(dn * fmin(z, dzt[POP_TW]), rz);
+      ds = div_by(ds * fmin(z, dzt[-POP_TW]), rz);
       de = div_by(de * fmin(z, dzt[1]), rz);
       dw = div_by(dw * fmin(z, dzt[-1]), rz);
     } else {
@@ -621,17 +630,17 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
     const double* su = st + 4 * POP_TN;
     const double* sv = st + 5 * POP_TN;
     if (PBC) {  // advection.F90:2040-2066: (U*DYU)*DZU
-      s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] * zu_at(kk, i, j) + su[oT - POP_TW] * s_dyu[o1 - POP_T1W] * zu_at(kk, i, j - 1));
-      s_vtn[o1] = 0.5 * (sv[oT] * s_dxu[o1] * zu_at(kk, i, j) + sv[oT - 1] * s_dxu[o1 - 1] * zu_at(kk, i - 1, j));
+      s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] * zu_at(st, tx, ty) + su[oT - POP_TW] * s_dyu[o1 - POP_T1W] * zu_at(st, tx, ty - 1));
+      s_vtn[o1] = 0.5 * (sv[oT] * s_dxu[o1] * zu_at(st, tx, ty) + sv[oT - 1] * s_dxu[o1 - 1] * zu_at(st, tx - 1, ty));
       if (tid < POP_BY) {
-        const int t1 = TIX1(-1, tid), tt = TIX(-1, tid), gi = i0 - 1, gj = j0 + tid;
-        s_ute[t1] = 0.5 * (su[tt] * s_dyu[t1] * zu_at(kk, gi, gj) + su[tt - POP_TW] * s_dyu[t1 - POP_T1W] * zu_at(kk, gi, gj - 1));
+        const int t1 = TIX1(-1, tid), tt = TIX(-1, tid);
+        s_ute[t1] = 0.5 * (su[tt] * s_dyu[t1] * zu_at(st, -1, tid) + su[tt - POP_TW] * s_dyu[t1 - POP_T1W] * zu_at(st, -1, tid - 1));
       } else if (tid >= 32 && tid < 32 + POP_BX) {
-        const int t1 = TIX1(tid - 32, -1), tt = TIX(tid - 32, -1), gi = i0 + tid - 32, gj = j0 - 1;
-        s_vtn[t1] = 0.5 * (sv[tt] * s_dxu[t1] * zu_at(kk, gi, gj) + sv[tt - 1] * s_dxu[t1 - 1] * zu_at(kk, gi - 1, gj));
+        const int t1 = TIX1(tid - 32, -1), tt = TIX(tid - 32, -1);
+        s_vtn[t1] = 0.5 * (sv[tt] * s_dxu[t1] * zu_at(st, tid - 32, -1) + sv[tt - 1] * s_dxu[t1 - 1] * zu_at(st, tid - 33, -1));
       }
       p_dn = o_dtn; p_ds = o_dts; p_de = o_dte; p_dw = o_dtw;
-      pbc_scale(kk, i, j, p_dn, p_ds, p_de, p_dw);
+      pbc_scale(st, tx, ty, p_dn, p_ds, p_de, p_dw);
     } else {
     // own point
     s_ute[o1] = 0.5 * (su[oT] * s_dyu[o1] + su[oT - POP_TW] * s_dyu[o1 - POP_T1W]);
@@ -665,7 +674,7 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         const int t1 = TIX1(ii, jj), tt = TIX(ii, jj);
         const int kc = s_kmt[tt];
         double rn = s_dtn[t1], rs = s_dts[t1], re = s_dte[t1], rw = s_dtw[t1];
-        if (PBC) pbc_scale(kk, i0 + ii, j0 + jj, rn, rs, re, rw);
+        if (PBC) pbc_scale(st, ii, jj, rn, rs, re, rw);
         const double cn = (kk <= s_kmt[tt + POP_TW] && kk <= kc) ? rn : 0.0;
         const double cs = (kk <= s_kmt[tt - POP_TW] && kk <= kc) ? rs : 0.0;
         const double ce = (kk <= s_kmt[tt + 1] && kk <= kc) ? re : 0.0;
@@ -698,12 +707,12 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
   __syncthreads();
 
   for (int k = 1; k <= km; k++) {
-    const int slot = (k - 1) % TF_NS;
-    const double* st = s_stage + (size_t)slot * TF_STAGE;
+    const int slot = (k - 1) % NS;
+    const double* st = s_stage + (size_t)slot * STAGE;
     const bool have_next = (k < km);
-    const int nslot = k % TF_NS;
-    const double* nst = s_stage + (size_t)nslot * TF_STAGE;
-    if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)((k / TF_NS) & 1));
+    const int nslot = k % NS;
+    const double* nst = s_stage + (size_t)nslot * STAGE;
+    if (have_next) mbar_wait(&s_bar[nslot], (uint32_t)((k / NS) & 1));
     if (active) {
       const double ute = s_ute[o1], utw = s_ute[o1 - 1], vtn = s_vtn[o1], vts = s_vtn[o1 - POP_T1W];
       double wtkb = 0.0;
@@ -715,10 +724,10 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
       const double cn = (k <= kmn) ? (PBC ? p_dn : o_dtn) : 0.0, cs = (k <= kms) ? (PBC ? p_ds : o_dts) : 0.0;
       const double ce = (k <= kme) ? (PBC ? p_de : o_dte) : 0.0, cw = (k <= kmw) ? (PBC ? p_dw : o_dtw) : 0.0;
       const double cc = -(cn + cs + ce + cw);
-      const double dzt_c = PBC ? g.DZT[(size_t)k * n2 + q] : 0.0;
+      const double dzt_c = PBC ? st[6 * POP_TN + oT] : 0.0;
       const RcpD rzt = PBC ? rcp_prepare(dzt_c) : RcpD{1.0, 1.0};
       const double h_dzt = PBC ? div_by(0.5, rzt) : 0.0;
-      const double dzt_p = PBC ? g.DZT[(size_t)((k < km) ? k + 1 : km) * n2 + q] : 0.0;
+      const double dzt_p = PBC ? ((k < km) ? nst[6 * POP_TN + oT] : dzt_c) : 0.0;  // DZT(min(k+1, km))
 #pragma unroll
       for (int m = 0; m < NTC; m++) {
         const int n = a.n0 + m;
@@ -758,7 +767,7 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         }
         tc_m[m] = T;
         // ---- vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
-        const double vdc = st[6 * POP_TN + m * POP_NTHREADS + tid];
+        const double vdc = st[NTL * POP_TN + m * POP_NTHREADS + tid];
         const double told_p = (k < km) ? nst[(NTC + m) * POP_TN + oT] : told_c[m];
         if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
         double VTFB, vd;
@@ -787,7 +796,7 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
       wtk = wtkb;
     }
     __syncthreads();  // every thread is done with ring slot k and with the intermediates of level k
-    if (tid == 0 && k + TF_NS <= km) issue(k + TF_NS);
+    if (tid == 0 && k + NS <= km) issue(k + NS);
     if (have_next) {
       pre(k + 1, nst);
       __syncthreads();
@@ -799,8 +808,10 @@ static int launch_tracer_fast(const TracerFastArgs& a, bool del4) {
   void (*kfn)(const TracerFastArgs);
   if (a.g.DZT) kfn = del4 ? tracer_fast_kernel<true, true> : tracer_fast_kernel<false, true>;
   else kfn = del4 ? tracer_fast_kernel<true, false> : tracer_fast_kernel<false, false>;
-  const size_t smem = sizeof(double) * ((size_t)TF_NS * TF_STAGE + (size_t)TF_FIXED * POP_T1N) + sizeof(int) * POP_TN +
-                      8 * TF_NS;
+  const bool pbc = (a.g.DZT != nullptr);
+  const size_t stage = (size_t)(pbc ? 8 : 6) * POP_TN + (size_t)NTC * POP_NTHREADS;
+  const size_t smem = sizeof(double) * ((size_t)(pbc ? TF_NS_PBC : TF_NS) * stage + (size_t)TF_FIXED * POP_T1N) +
+                      sizeof(int) * POP_TN + 8 * TF_NS;
 #ifndef POP_EMUL
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -905,7 +916,8 @@ int tracer_column(int mode, int k, const TracerIO& io) {
           }
           if (make_tmap(&f.tm_tcur, a.TCUR, G.km * G.nt) && make_tmap(&f.tm_tmix, a.TMIX, G.km * G.nt) &&
               make_tmap(&f.tm_u, a.UCUR, G.km) && make_tmap(&f.tm_v, a.VCUR, G.km) &&
-              make_tmap_box(&f.tm_vdc, a.g.VDC, G.vdc_nk * G.vdc_nd, POP_BX, POP_BY)) {
+              make_tmap_box(&f.tm_vdc, a.g.VDC, G.vdc_nk * G.vdc_nd, POP_BX, POP_BY) &&
+              (!a.g.DZT || (make_tmap(&f.tm_dzt, a.g.DZT, G.km + 2) && make_tmap(&f.tm_dzu, a.g.DZU, G.km + 2)))) {
             POP_TRY(launch_tracer_fast(f, del4));
             break;
           }
