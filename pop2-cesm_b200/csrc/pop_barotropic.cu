@@ -1217,9 +1217,9 @@ static int pcsi(double* X, const double* B) {
   }
 #endif
   // (X_m, Q_m) live in pair `cur`, a pass writes pair `nxt`.  With lagged checks X_m of a check must outlive its
-  // verdict: the pair is simply retired from the rotation until then (`held`: at most one at a time besides the one
-  // whose verdict is being awaited), so three pairs suffice and nothing is copied.
-  int cur = 0, nxt = 1, held = -1;
+  // verdict: the pair is simply retired from the rotation until then (pend.buf: one at a time, the next check frees it),
+  // so three pairs suffice and nothing is copied.
+  int cur = 0, nxt = 1;
   int m = 1, npass = 0, npass2 = 0;
   while (m <= maxIt) {
     const bool check = (m % freq == 0) && (m >= start);

@@ -771,8 +771,9 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         const double told_p = (k < km) ? nst[(NTC + m) * POP_TN + oT] : told_c[m];
         if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
         double VTFB, vd;
-        if (PBC) {  // vertical_mix.F90:790-803
-          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) / (0.5 * (dzt_c + dzt_p)) : 0.0;
+        if constexpr (PBC) {  // vertical_mix.F90:790-803
+          const double wz = 0.5 * (dzt_c + dzt_p);
+          VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) / wz : 0.0;
           vd = (k <= kmt) ? div_by(vtf[m] - VTFB, rzt) : 0.0;
         } else {
           VTFB = (kmt > k) ? vdc * (told_c[m] - told_p) * c_vc.dzwr[k] : 0.0;
