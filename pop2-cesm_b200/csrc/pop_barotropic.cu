@@ -691,20 +691,20 @@ pcsi_iter_kernel(const PcsiArgs a) {
     const double c = ldg(v.C + q);
     double ax = 0.0;
     if (i >= 1 && i <= nxb - 2 && j >= 1 && j <= v.nyb - 2) {
-      const double* X = a.X;
-      ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
-           ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
-           ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
-           ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
+      const double* X = a.X;  // written by the previous pass: L2 loads (ldcg), see pop_dev.cuh
+      ax = c * ldcg(X + q) + ldg(v.N + q) * ldcg(X + q + nxb) + ldg(v.N + q - nxb) * ldcg(X + q - nxb) +
+           ldg(v.E + q) * ldcg(X + q + 1) + ldg(v.E + q - 1) * ldcg(X + q - 1) +
+           ldg(v.NE + q) * ldcg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldcg(X + q - nxb + 1) +
+           ldg(v.NE + q - 1) * ldcg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldcg(X + q - nxb - 1);
     }
     const double r = ldg(a.B + q) - ax;
     if (SUM && !ghost_copy && bt_physical(v, i, j)) acc = dd_add_d(acc, (r * r) * ldg(v.mask + q));
     if (a.advance) {
       const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
       const double R = r * a0r;
-      const double qv = a.om * R + a.c1 * ldg(a.Q + q);
+      const double qv = a.om * R + a.c1 * ldcg(a.Q + q);
       a.Qn[qd] = qv;
-      a.Xn[qd] = ldg(a.X + q) + qv;
+      a.Xn[qd] = ldcg(a.X + q) + qv;
     }
     }
   }
@@ -858,15 +858,15 @@ pcsi_iter2_kernel(const POP_GRID_CONSTANT Pcsi2Args a) {
     mapped = (si != gi_ || sj != gj_);
     if (!mapped) return;
     const size_t q = (size_t)sj * nxb + si;
-    const double* X = a.X;
+    const double* X = a.X;  // written by the previous pass: L2 loads (ldcg), see pop_dev.cuh
     const double c = ldg(v.C + q);
-    const double ax = c * ldg(X + q) + ldg(v.N + q) * ldg(X + q + nxb) + ldg(v.N + q - nxb) * ldg(X + q - nxb) +
-                      ldg(v.E + q) * ldg(X + q + 1) + ldg(v.E + q - 1) * ldg(X + q - 1) +
-                      ldg(v.NE + q) * ldg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldg(X + q - nxb + 1) +
-                      ldg(v.NE + q - 1) * ldg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldg(X + q - nxb - 1);
+    const double ax = c * ldcg(X + q) + ldg(v.N + q) * ldcg(X + q + nxb) + ldg(v.N + q - nxb) * ldcg(X + q - nxb) +
+                      ldg(v.E + q) * ldcg(X + q + 1) + ldg(v.E + q - 1) * ldcg(X + q - 1) +
+                      ldg(v.NE + q) * ldcg(X + q + nxb + 1) + ldg(v.NE + q - nxb) * ldcg(X + q - nxb + 1) +
+                      ldg(v.NE + q - 1) * ldcg(X + q + nxb - 1) + ldg(v.NE + q - nxb - 1) * ldcg(X + q - nxb - 1);
     const double r = ldg(a.B + q) - ax;
     const double a0r = (c != 0.0) ? 1.0 / c : 0.0;
-    x1 = ldg(X + q) + (a.om1 * (r * a0r) + a.c11 * ldg(a.Q + q));
+    x1 = ldcg(X + q) + (a.om1 * (r * a0r) + a.c11 * ldcg(a.Q + q));
   };
   const bool edge_cta = (i0 + P2_TX + 1 >= nxb - POP_NGHOST) || (i0 - 1 < POP_NGHOST) || (j0 - 1 < POP_NGHOST) ||
                         (j0 + P2_TY >= nyb - POP_NGHOST) ||  // the tile + ring touches ghost cells of the block
