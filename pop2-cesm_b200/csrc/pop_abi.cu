@@ -627,11 +627,26 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
   G.cio.fw_halo_pending = (FW != nullptr);
   G.cio.out = sfc_out;
   G.cio.early = sfc_out && !G.no_overlap && (ts_type == POP_TS_LEAPFROG || ts_type == POP_TS_EULER);
-  G.cio.psurf_sent = G.cio.ts_sent = false;
+  G.cio.psurf_sent = G.cio.ts_sent = G.cio.uv_sent = false;
+  G.cio.uv_dev = nullptr;
+  if (G.cio.early && G.finish_mode == 0 && !(getenv("POP_B200_NO_DIRECT_SFC") && getenv("POP_B200_NO_DIRECT_SFC")[0] == '1')) {
+    // a pinned host buffer is device-accessible: the velocity-finish kernel can store U1/V1 into it directly
+    const size_t strip = (size_t)G.nxg * G.ny_local;
+#ifndef POP_EMUL
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, sfc_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      G.cio.uv_dev = (double*)at.devicePointer + 3 * strip;
+    else
+      cudaGetLastError();
+#else
+    G.cio.uv_dev = sfc_out + 3 * strip;
+#endif
+  }
   const int rc = step_dev(ts_type);
-  const bool psurf_sent = G.cio.psurf_sent, ts_sent = G.cio.ts_sent;
+  const bool psurf_sent = G.cio.psurf_sent, ts_sent = G.cio.ts_sent, uv_sent = G.cio.uv_sent;
   G.cio.out = nullptr;
   G.cio.early = false;
+  G.cio.uv_dev = nullptr;
   if (rc != POP_SUCCESS) {
     if (G.cio.forcing_pending) { cudaStreamSynchronize(G.stream_cp); G.cio.forcing_pending = false; }
     cudaStreamSynchronize(G.stream_cp);
@@ -650,10 +665,19 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
       POP_TRY(find_field("pop_step_coupled", "PSURF", POP_TIME_CUR, &f));
       POP_TRY(strip_copy(f, sfc_out + 2 * strip, false, 0, 1));
     }
-    POP_TRY(find_field("pop_step_coupled", "UVEL", POP_TIME_CUR, &f));
-    POP_TRY(strip_copy(f, sfc_out + 3 * strip, false, 0, 1));
-    POP_TRY(find_field("pop_step_coupled", "VVEL", POP_TIME_CUR, &f));
-    POP_TRY(strip_copy(f, sfc_out + 4 * strip, false, 0, 1));
+    if (!uv_sent) {
+      POP_TRY(find_field("pop_step_coupled", "UVEL", POP_TIME_CUR, &f));
+      POP_TRY(strip_copy(f, sfc_out + 3 * strip, false, 0, 1));
+      POP_TRY(find_field("pop_step_coupled", "VVEL", POP_TIME_CUR, &f));
+      POP_TRY(strip_copy(f, sfc_out + 4 * strip, false, 0, 1));
+    } else if (G.cfg.ns_boundary_type == POP_BNDY_TRIPOLE && G.rank == G.nranks - 1) {
+      // the kernel left out the tripole seam row (final only after the halo updates and its own barotropic add)
+      const size_t src = (size_t)(G.je - 1) * G.nxb + (G.ib - 1), dst = (size_t)(G.ny_local - 1) * G.nxg;
+      POP_CHECK_CUDA(cudaMemcpyAsync(sfc_out + 3 * strip + dst, fld_t("UVEL", G.curtime) + src, sizeof(double) * G.nxg,
+                                     cudaMemcpyDeviceToHost, G.stream));
+      POP_CHECK_CUDA(cudaMemcpyAsync(sfc_out + 4 * strip + dst, fld_t("VVEL", G.curtime) + src, sizeof(double) * G.nxg,
+                                     cudaMemcpyDeviceToHost, G.stream));
+    }
   }
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   POP_CHECK_CUDA(cudaStreamSynchronize(G.stream_cp));

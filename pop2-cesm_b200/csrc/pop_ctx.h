@@ -93,6 +93,10 @@ struct Ctx {
     double* out = nullptr;         // host buffer of the surface state, or null
     bool early = false;            // outputs may leave as soon as they are final (not on averaging / filtered steps)
     bool psurf_sent = false, ts_sent = false;
+    // U1/V1: when the host buffer is pinned (device-accessible) the velocity-finish kernel stores the surface level
+    // straight into it while it runs; uv_dev = device alias of out + 3*strip (V follows one strip later), or null
+    double* uv_dev = nullptr;
+    bool uv_sent = false;
   } cio;
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy

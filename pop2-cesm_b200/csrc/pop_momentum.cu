@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MINB)
 momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict__ VNEW,
                        const double* __restrict__ UOLD, const double* __restrict__ VOLD,
                        const double* __restrict__ UB, const double* __restrict__ VB, int bt_skip_row,
-                       int implicit_vmix, int finish, double c2dtu) {
+                       int implicit_vmix, int finish, double c2dtu, double* sfc_uv, int nxg) {
   POP_DYN_SMEM(smem_raw);
   double* sE = (double*)smem_raw + threadIdx.x;
   const int i = (g.ib - 1) + blockIdx.x * MF_THREADS + threadIdx.x;
@@ -877,6 +877,13 @@ momentum_finish_kernel(GridView g, double* __restrict__ UNEW, double* __restrict
       *tv = v;
       tu += n2i;
       tv += n2i;
+      if (k == 1 && sfc_uv != nullptr && j != bt_skip_row) {
+        // pop_step_coupled: the surface velocities go straight to the (pinned, device-mapped) host buffer of the coupler
+        // while the rest of the column is still being written; the tripole seam row is final only after the halo updates
+        const size_t sq = (size_t)(j - (g.jb - 1)) * nxg + (i - (g.ib - 1));
+        sfc_uv[sq] = u;
+        sfc_uv[(size_t)(g.je - g.jb + 1) * nxg + sq] = v;
+      }
     }
   }
 }
@@ -1124,8 +1131,11 @@ static int launch_finish(double* UNEW, double* VNEW, const double* UOLD, const d
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   POP_CHECK_CUDA(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #endif
+  // (only the call that also adds the barotropic velocities produces the final surface level)
+  double* sfc_uv = (UB != nullptr && finish) ? G.cio.uv_dev : nullptr;
   POP_LAUNCH(kfn, grid, block, smem, g, UNEW, VNEW, UOLD, VOLD, UB, VB, bt_skip_row, implicit_vmix,
-             finish, G.c2dtu);
+             finish, G.c2dtu, sfc_uv, G.nxg);
+  if (sfc_uv) G.cio.uv_sent = true;
   return pop_post_launch("momentum_finish");
 }
 
