@@ -607,17 +607,34 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
                                 const double* FW, double* sfc_out) {
   POP_TRY(check_ready("pop_step_coupled", nullptr, false));
   DevField* f;
-  if (STF) { POP_TRY(find_field("pop_step_coupled", "STF", 0, &f)); POP_TRY(strip_copy(f, (void*)STF, true, 0, G.nt)); }
-  // SHF_QSW is part of the coupler's forcing set but nothing on this path consumes it (penetrative short-wave
-  // absorption, add_sw_absorb, is outside SURVEY section 8): it is accepted and ignored -- not copied, not counted
-  (void)SHF_QSW;
-  const bool side = !G.no_overlap && (SMF || FW);
+  const bool side = !G.no_overlap && (SMF || FW || STF);
   cudaStream_t st_in = side ? G.stream_cp : G.stream;
   if (side) {
-    // the copy stream must not overwrite SMF / FW while kernels of a previous (unsynchronised) pop_step still read them
+    // the copy stream must not overwrite STF / SMF / FW while kernels of a previous (unsynchronised) pop_step still read them
     POP_CHECK_CUDA(cudaEventRecord(G.ev_cp_a, G.stream));
     POP_CHECK_CUDA(cudaStreamWaitEvent(G.stream_cp, G.ev_cp_a, 0));
   }
+  // STF is read by the first kernel of the step.  Pinned host buffer: that kernel reads it from the host directly (one value
+  // per column) and the copy into the device field joins the others on the copy stream; otherwise it is copied up front.
+  G.cio.stf_dev = nullptr;
+  if (STF && side && !(getenv("POP_B200_NO_DIRECT_SFC") && getenv("POP_B200_NO_DIRECT_SFC")[0] == '1')) {
+#ifndef POP_EMUL
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, STF) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      G.cio.stf_dev = (const double*)at.devicePointer;
+    else
+      cudaGetLastError();
+#else
+    G.cio.stf_dev = STF;
+#endif
+  }
+  if (STF) {
+    POP_TRY(find_field("pop_step_coupled", "STF", 0, &f));
+    POP_TRY(strip_copy(f, (void*)STF, true, 0, G.nt, G.cio.stf_dev ? st_in : G.stream));
+  }
+  // SHF_QSW is part of the coupler's forcing set but nothing on this path consumes it (penetrative short-wave
+  // absorption, add_sw_absorb, is outside SURVEY section 8): it is accepted and ignored -- not copied, not counted
+  (void)SHF_QSW;
   if (SMF) { POP_TRY(find_field("pop_step_coupled", "SMF", 0, &f)); POP_TRY(strip_copy(f, (void*)SMF, true, 0, 2, st_in)); }
   if (FW) { POP_TRY(find_field("pop_step_coupled", "FW", 0, &f)); POP_TRY(strip_copy(f, (void*)FW, true, 0, 1, st_in)); }
   if (side) {
@@ -647,6 +664,7 @@ extern "C" int pop_step_coupled(int ts_type, const double* STF, const double* SM
   G.cio.out = nullptr;
   G.cio.early = false;
   G.cio.uv_dev = nullptr;
+  G.cio.stf_dev = nullptr;
   if (rc != POP_SUCCESS) {
     if (G.cio.forcing_pending) { cudaStreamSynchronize(G.stream_cp); G.cio.forcing_pending = false; }
     cudaStreamSynchronize(G.stream_cp);

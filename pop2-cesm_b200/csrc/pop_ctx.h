@@ -97,6 +97,9 @@ struct Ctx {
     // straight into it while it runs; uv_dev = device alias of out + 3*strip (V follows one strip later), or null
     double* uv_dev = nullptr;
     bool uv_sent = false;
+    // STF: with a pinned host buffer the tracer kernel reads the surface flux of its columns straight from the host
+    // (once per column, at level 1) while the copy into the device field runs on the copy stream, off the critical path
+    const double* stf_dev = nullptr;
   } cio;
   std::map<std::string, DevField> fields;
   VertConst vc;  // host copy
@@ -317,6 +320,7 @@ int gm_tendency_dev(const double* TMIX);  // fills the field GM_HDT (nxb,nyb,km,
 enum { TR_FULL = 0, TR_ADVT = 1, TR_HDIFFT = 2, TR_VDIFFT = 3 };
 struct TracerIO {
   const double *TCUR, *TMIX, *TOLD, *UCUR, *VCUR, *STF, *TFW, *DH, *POLD, *PCUR;
+  bool stf_strip = false;  // STF is a (nt, ny_local, nx_global) strip of physical cells instead of a padded field
   double* TNEW;  // FULL: (nxb,nyb,km,nt); slab modes: OUT(nxb,nyb,nt)
   double* WTK;   // slab modes: carried vertical velocity (in/out); FULL: unused
 };

@@ -67,6 +67,7 @@ int baroclinic_driver_dev(bool defer_finish) {
     io.TCUR = fld_t("TRACER", c); io.TMIX = fld_t("TRACER", mx); io.TOLD = fld_t("TRACER", o);
     io.UCUR = fld_t("UVEL", c); io.VCUR = fld_t("VVEL", c);
     io.STF = fld("STF"); io.TFW = fld("TFW"); io.DH = fld("DH");
+    if (G.cio.stf_dev) { io.STF = G.cio.stf_dev; io.stf_strip = true; }  // pop_step_coupled, pinned host buffer
     io.POLD = fld_t("PSURF", o); io.PCUR = fld_t("PSURF", c);
     io.TNEW = fld_t("TRACER", n_);
     io.WTK = nullptr;

@@ -32,6 +32,10 @@ struct TracerArgs {
   double *VTF, *AUX;  // slab modes: carried fluxes (nxb,nyb,nt)
   const double* HDT;  // GM: precomputed horizontal-mixing tendency (nxb,nyb,km,nt), pop_gm.cu; else null
   int lwl;            // lw_lim: the advective tendency of such tracers is waiting in OUT (ocean cells), pop_lwlim.cu
+  // STF(i,j,n) = STF[n * stf_ns + (j - stf_j0) * stf_pitch + (i - stf_i0)]: the padded field (n2, nxb, 0, 0) or a strip of
+  // physical cells in pinned host memory (nx_global * ny_local, nx_global, ib-1, jb-1)
+  size_t stf_ns;
+  int stf_pitch, stf_i0, stf_j0;
   int k0, k1;    // level range (1-based, inclusive)
   int n0, nn;    // tracers n0 .. n0+nn-1 (0-based)
   int adv[NTC];  // advection scheme of each tracer of this pass
@@ -420,7 +424,7 @@ tracer_column_kernel(const POP_GRID_CONSTANT TracerArgs a) {
         if (k < a.k1) vdc_nx[m] = vdc_at(m, k + 1);
         const double told_p = (k < km) ? ((have_next && told_is_mix) ? n_tm[m * POP_TN + TIX(tx, ty)] : a.TOLD[lev + n2])
                                        : told_c[m];
-        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
+        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * a.stf_ns + (size_t)(j - a.stf_j0) * a.stf_pitch + (i - a.stf_i0)] : 0.0;
         double VTFB;
         if (pbc) {  // vertical_mix.F90:790-803
           const double dzt_p = g.DZT[(size_t)((k < km) ? k + 1 : km) * n2 + q];
@@ -510,6 +514,8 @@ struct TracerFastArgs {
   double* OUT;
   int n0;                      // first tracer (0-based) of the pair
   int lw[NTC];                 // tracer m is advected by lw_lim: its L(T) waits in OUT (ocean cells), pop_lwlim.cu
+  size_t stf_ns;               // STF addressing, as in TracerArgs
+  int stf_pitch, stf_i0, stf_j0;
   int vdc_lev0[NTC], vdc_kstr;  // VDC level of tracer m at level k: vdc_lev0[m] + k*vdc_kstr
   int lvariable_hmixt, varthick, predictor;
   double ah;
@@ -769,7 +775,7 @@ tracer_fast_kernel(const POP_GRID_CONSTANT TracerFastArgs a) {
         // ---- vertical diffusion (top/bottom fluxes): vertical_mix.F90:779-838
         const double vdc = st[NTL * POP_TN + m * POP_NTHREADS + tid];
         const double told_p = (k < km) ? nst[(NTC + m) * POP_TN + oT] : told_c[m];
-        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * n2 + q] : 0.0;
+        if (k == 1) vtf[m] = (kmt >= 1) ? a.STF[(size_t)n * a.stf_ns + (size_t)(j - a.stf_j0) * a.stf_pitch + (i - a.stf_i0)] : 0.0;
         double VTFB, vd;
         if constexpr (PBC) {  // vertical_mix.F90:790-803
           const double wz = 0.5 * (dzt_c + dzt_p);
@@ -855,6 +861,8 @@ int tracer_column(int mode, int k, const TracerIO& io) {
   a.g = grid_view();
   a.TCUR = io.TCUR; a.TMIX = io.TMIX; a.TOLD = io.TOLD; a.UCUR = io.UCUR; a.VCUR = io.VCUR;
   a.STF = io.STF; a.TFW = io.TFW; a.DH = io.DH; a.POLD = io.POLD; a.PCUR = io.PCUR;
+  if (io.stf_strip) { a.stf_ns = (size_t)G.nxg * G.ny_local; a.stf_pitch = G.nxg; a.stf_i0 = G.ib - 1; a.stf_j0 = G.jb - 1; }
+  else { a.stf_ns = G.n2; a.stf_pitch = G.nxb; a.stf_i0 = 0; a.stf_j0 = 0; }
   a.OUT = io.TNEW;
   a.WTK = io.WTK;
   a.VTF = fld("VTF");
@@ -905,6 +913,7 @@ int tracer_column(int mode, int k, const TracerIO& io) {
         if (fast_ok) {
           TracerFastArgs f;
           memset(&f, 0, sizeof(f));
+          f.stf_ns = a.stf_ns; f.stf_pitch = a.stf_pitch; f.stf_i0 = a.stf_i0; f.stf_j0 = a.stf_j0;
           f.g = a.g; f.STF = a.STF; f.TFW = a.TFW; f.DH = a.DH; f.POLD = a.POLD; f.PCUR = a.PCUR; f.OUT = a.OUT;
           for (int m = 0; m < NTC; m++) f.lw[m] = (a.adv[m] == POP_TADVECT_LW_LIM) ? 1 : 0;
           f.n0 = n0; f.lvariable_hmixt = a.lvariable_hmixt; f.varthick = a.varthick; f.predictor = a.predictor;
