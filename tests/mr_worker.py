@@ -29,12 +29,23 @@ def run(cs, cfg, comm_id, steps, coupled=False):
                      np.ascontiguousarray((0.5 * rng.standard_normal((2, cs.ny, cs.nx)) * oceanu)[:, r, :]),
                      np.ascontiguousarray((1.0e-3 * rng.standard_normal((cs.ny, cs.nx)) * ocean)[r, :]),
                      np.ascontiguousarray((1.0e-6 * rng.standard_normal((cs.ny, cs.nx)) * ocean)[r, :])]
-                out = np.zeros((5, r.stop - r.start, cs.nx))
-                p.step_coupled(ts, f[0], f[1], f[2], f[3], out)
+                # pinned buffers: STF is read and U1/V1 are stored by the kernels directly (the path bench.py times)
+                import torch
+                pin = [torch.from_numpy(x).pin_memory() for x in f]
+                out_t = torch.zeros((5, r.stop - r.start, cs.nx), dtype=torch.float64).pin_memory()
+                p.step_coupled(ts, pin[0].numpy(), pin[1].numpy(), pin[2].numpy(), pin[3].numpy(), out_t.numpy())
+                sfc = out_t.numpy().copy()
             else:
                 p.step(ts)
             its.append(p.solvers_get_diagnostics()[0])
         out = {n: p.gather(n, c.TIME_CUR) for n in FIELDS_CMP}
+        if coupled:
+            out["SFC_OUT"] = sfc   # what the coupler got back from the last step: SST, SSS, PSURF, U1, V1
+            km = cs.km
+            for idx, (name, lev) in enumerate((("TRACER", 0), ("TRACER", km), ("PSURF", 0), ("UVEL", 0), ("VVEL", 0))):
+                if not np.array_equal(sfc[idx], out[name][lev]):
+                    print("FAIL rank %d: surface output %d differs from the resident %s" % (cfg.rank, idx, name))
+                    out["SFC_OUT"] = sfc * np.nan
         return its, out, p.rows()
     finally:
         p.finalize()
@@ -106,7 +117,7 @@ def main():
             if itr != its1:
                 print("FAIL rank %d solver iterations %s vs single-strip %s" % (r, itr, its1))
                 ok = False
-        for n in FIELDS_CMP:
+        for n in FIELDS_CMP + (("SFC_OUT",) if coupled else ()):
             full = np.concatenate([p_[1][n] for p_ in parts], axis=1)
             if not np.array_equal(full, out1[n]):
                 d = np.max(np.abs(full - out1[n]))
