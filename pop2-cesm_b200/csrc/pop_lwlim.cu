@@ -19,8 +19,15 @@
 #include <cmath>
 #include "pop_dev.cuh"
 
+#ifndef LW_TX
 #define LW_TX 28
+#endif
+#ifndef LW_TY
 #define LW_TY 12
+#endif
+#ifndef LW_MINB
+#define LW_MINB 1   // resident CTAs per SM the register allocation aims for
+#endif
 #define LW_EX (LW_TX + 4)
 #define LW_EY (LW_TY + 4)
 #define LW_NT (LW_EX * LW_EY)
@@ -218,7 +225,7 @@ __device__ __forceinline__ double lw_psi(double dTR, double dTRu, double lw, dou
 }
 
 template <bool PBC>
-__global__ void __launch_bounds__(LW_NT) lw_lim_kernel(const LwArgs a) {
+__global__ void __launch_bounds__(LW_NT, LW_MINB) lw_lim_kernel(const LwArgs a) {
   __shared__ double s_ue[LW_NT], s_vn[LW_NT], s_lwx[LW_NT], s_lwy[LW_NT], s_ute[LW_NT], s_vtn[LW_NT];
   __shared__ double s_xs[LW_NTC][LW_NT], s_te[LW_NTC][LW_NT];
   double (*s_tn)[LW_NT] = s_te;  // the north-face values reuse the tile of the east-face values (a barrier apart)
